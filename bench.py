@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py — Wide&Deep CTR training throughput through libps_b200.so (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2]
+
+A "step" is one train.Trainer step (pullWeights → forward → loss → backward → KVStore.update →
+clear) of the WideDeepNN on one synthetic Criteo-libsvm-shaped batch.
+  value : samples/s with the batch ring already resident in HBM (device-timed, CUDA events on
+          the library's stream, max over ranks)
+  e2e   : samples/s through the host-facing C-ABI call (ps_model_submit / ps_model_collect, the
+          pipelined form of Trainer.train) with inputs in pinned HOST memory: every step copies
+          its E/X/W/Y host→device and reads its loss device→host inside the timed region
+  roofline : the dominant HBM-bound kernel's algorithmic bytes / its device time vs the measured
+          copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline : the CPU oracle (C++ restatement of the reference's standalone Java path; the JVM
+          cannot run in this image) timed on this box's host cores on a bounded sample
+--impl reference times that CPU restatement as the reference arm (rank 0 only).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from ps_b200.synth import CONFIGS, Synth  # noqa: E402
+
+METRIC = "Wide&Deep CTR training samples/sec"
+UNIT = "samples/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([t.strip() for t in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        reasons = []
+        for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if any(r[3 + i].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(self.rows)}
+
+
+def model_args(cfg, n_gpus):
+    return dict(kind=cfg["kind"], F=cfg["F"], D=cfg["D"], Xn=cfg["Xn"], fc=cfg["fc"])
+
+
+def oracle_model(cfg, seed):
+    import oracle_lib as ol
+    kind = {"widedeep": ol.KIND_WIDEDEEP, "dnn": ol.KIND_DNN, "fcnn": ol.KIND_FCNN}[cfg["kind"]]
+    return ol.OracleModel(kind, cfg["F"], cfg["D"], cfg["Xn"], cfg["fc"], seed, emb_opt=1 if cfg["emb_opt"] == "ftrl" else 0)
+
+
+def time_oracle(cfg, batches, budget_s, threads):
+    """Timed CPU restatement: returns (samples/s, steps run, gemm back-end)."""
+    import oracle_lib as ol
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    gemm = "openmp-loops"
+    ob = ol.openblas_path()
+    if ob and ol.lib().pso_set_gemm(2, ob.encode()) == 0:
+        gemm = "openblas-0.3.30 (numpy bundled)"
+        os.environ["OPENBLAS_NUM_THREADS"] = str(threads)
+    else:
+        ol.lib().pso_set_gemm(1, None)
+    o = oracle_model(cfg, 20261017)
+    b = batches[0]
+    o.train_step(b.get("E"), b["X"], b.get("W"), b["Y"])          # warm-up: creates keys
+    n, t0 = 0, time.perf_counter()
+    while True:
+        b = batches[(n + 1) % len(batches)]
+        o.train_step(b.get("E"), b["X"], b.get("W"), b["Y"])
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt >= budget_s or n >= 64:
+            break
+    ol.lib().pso_set_gemm(0, None)
+    return n * cfg["B"] / dt, n, gemm, dt
+
+
+def run_reference(args, cfg, rank):
+    if rank != 0:
+        return
+    syn = Synth(F=cfg["F"], Xn=cfg["Xn"], V=cfg["V"], dist=args.dist, seed=20261017 + 2)
+    batches = [syn.batch(cfg["B"]) for _ in range(4)]
+    threads = os.cpu_count() or 1
+    per_step_budget = 4.0
+    total = args.steps + args.warmup
+    sps, n, gemm, dt = time_oracle(cfg, batches, min(150.0, per_step_budget * total), threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * cfg["B"] / sps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": workload_name(args, cfg), "global_batch": cfg["B"]},
+        "cpu_baseline": {"value": sps, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{n} Trainer steps of batch {cfg['B']} in {dt:.1f}s; C++ restatement of the reference's standalone Java path "
+                                   f"(JVM/jblas unavailable in this image); sgemm={gemm}; everything but sgemm is single-threaded like thread=1"},
+        "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args, cfg):
+    return (f"{args.config}: {cfg['kind']} synthetic Criteo-libsvm, F={cfg['F']} Xn={cfg['Xn']} D={cfg['D']} vocab={cfg['V']} "
+            f"fc={cfg['fc']} batch={cfg['B']}/GPU emb_opt={cfg['emb_opt']} keys={args.dist}")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--config", default="cfg2")
+    ap.add_argument("--dist", default="zipf")
+    ap.add_argument("--precision", default=os.environ.get("PS_FC_PRECISION", "fp32"))
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--ring", type=int, default=16)
+    args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        import __graft_entry__ as g
+        if rank == 0:
+            g.build()
+            run_reference(args, cfg, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    if local_rank == 0:
+        g.build()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    from ps_b200 import binding as ps
+
+    torch.cuda.set_device(local_rank)
+    B, F, D, Xn = cfg["B"], cfg["F"], cfg["D"], cfg["Xn"]
+    ctx = ps.Context(local_rank, seed=20261017)
+    ctx.set_fc_precision(ps.PS_FC_TF32 if args.precision == "tf32" else ps.PS_FC_FP32)
+    cap = int(min(2 ** 31 - 1, max(1 << 16, 2 * cfg["V"]))) if cfg["V"] else 1024
+    upd = ps.UpdaterSpec.ftrl() if cfg["emb_opt"] == "ftrl" else None
+    model = ps.Model(ctx, cfg["kind"], F, D, Xn, cfg["fc"], emb_capacity=cap, emb_updater=upd, max_batch=B)
+
+    # every rank trains its own replica on its own shard of samples (weak scaling); the key-hash
+    # sharded table + NCCL exchange is the multi-GPU path of a later commit
+    syn = Synth(F=F, Xn=Xn, V=cfg["V"], dist=args.dist, seed=20261017 + 2 + 1000 * rank, n_classes=10 if cfg["kind"] == "fcnn" else 0)
+    ring = [syn.batch(B) for _ in range(args.ring)]
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=local_rank)
+
+    def to_dev(b):
+        d = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda(local_rank) for k, v in b.items()}
+        return d
+    dev_ring = [to_dev(b) for b in ring]
+    torch.cuda.synchronize()
+
+    def ptr(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else None
+
+    def dev_step(i):
+        d = dev_ring[i % len(dev_ring)]
+        model.train_step_dev(ptr(d.get("E")), ptr(d["X"]), ptr(d.get("W")), ptr(d["Y"]), B)
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") ----
+    for i in range(args.warmup):
+        dev_step(i)
+    loss = model.read_loss()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        dev_step(args.warmup + i)
+    e1.record(stream)
+    loss = model.read_loss()
+    barrier()
+    ms_dev = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - l0
+    if world > 1:
+        t = torch.tensor([ms_dev], device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev = float(t.item())
+
+    # ---- end-to-end through the host-facing call ("e2e") ----
+    pinned = []
+    for b in ring:
+        pb = {}
+        for k, v in b.items():
+            pa = ps.PinnedArray(v.shape, v.dtype)
+            pa.array[...] = v
+            pb[k] = pa
+        pinned.append(pb)
+
+    def hp(pb, k):
+        return pb[k].ptr if k in pb else None
+    h2d = sum(pa.nbytes for pa in pinned[0].values())
+
+    def host_loop(n, start):
+        for i in range(n):
+            pb = pinned[(start + i) % len(pinned)]
+            model.submit_ptrs(hp(pb, "E"), hp(pb, "X"), hp(pb, "W"), hp(pb, "Y"), B)
+            if i >= 1:
+                model.collect()
+        return model.collect()
+    host_loop(max(3, args.warmup), 0)
+    barrier()
+    t0 = time.perf_counter()
+    loss_e2e = host_loop(args.steps, args.warmup)
+    ctx.synchronize()
+    t1 = time.perf_counter()
+    ms_e2e = (t1 - t0) * 1e3
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    clocks = sampler.summary()
+
+    # ---- per-kernel device times and the roofline of the dominant HBM-bound kernel ----
+    model.profile(True)
+    acc = {}
+    reps = 20
+    for i in range(reps):
+        dev_step(i)
+        model.read_loss()
+        for k, v in model.phase_times().items():
+            acc.setdefault(k, []).append(v)
+    model.profile(False)
+    phase_us = {k: 1e3 * float(np.median(v)) for k, v in acc.items()}
+    L = B * F
+    uniq = float(np.mean([len(np.unique(b["E"] + (np.arange(F, dtype=np.int64) << 44)[None, :])) for b in ring])) if F else 0.0
+    alg = {                                                      # SURVEY.md §8(d) algorithmic bytes per launch
+        "emb_gather": L * (8 + 8 * D),
+        "emb_bwd_update": L * (8 + 4 * D) + uniq * 24 * D,
+    }
+    hbm_peak, peak_src = peaks()
+    kernels = {}
+    for k, bytes_ in alg.items():
+        us = phase_us.get(k, 0.0) + (phase_us.get("emb_probe", 0.0) if k == "emb_gather" else 0.0)
+        if us > 0:
+            kernels[k] = {"us": us, "alg_bytes": bytes_, "gbs": bytes_ / us / 1e3}
+    dom = max(kernels, key=lambda k: kernels[k]["us"]) if kernels else None
+    roofline = None
+    if dom:
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
+                    "frac": kernels[dom]["gbs"] / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "note": "emb_gather time includes the probe kernel that resolves the keys"}
+
+    if rank == 0:
+        cpu = None
+        if world == 1:
+            sps, n, gemm, dt = time_oracle(cfg, ring[:4], args.cpu_budget, 1)
+            cpu = {"value": sps, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"{n} Trainer steps of batch {B} in {dt:.1f}s, thread=1 (CTR.java:72); C++ restatement of the reference's standalone "
+                             f"Java path (no JVM in this image); sgemm={gemm} single-threaded"}
+        total = B * world * args.steps
+        line = {
+            "metric": METRIC, "value": total / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args, cfg), "global_batch": B * world,
+                       "parallelism": "replicas" if world > 1 else "single",
+                       "l2": "embedding table + optimiser state (%.0f MB) exceeds the 126 MB L2; a ring of %d distinct batches; no flush" % (
+                           cap * (16 + 12 * D) / 1e6, len(ring))},
+            "e2e": {"value": total / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
+                    "api": "ps_model_submit/ps_model_collect (2 steps in flight)"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels_us": phase_us, "hbm_kernels": kernels,
+            "cpu_baseline": cpu, "loss": loss, "loss_e2e": loss_e2e, "unique_keys_per_batch": uniq,
+        }
+        print(json.dumps(line), flush=True)
+    for pb in pinned:
+        for pa in pb.values():
+            pa.free()
+    model.close()
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,167 @@
+/*
+ * ps_b200.h — the C ABI of libps_b200.so: the drop-in boundary for the parameter-server
+ * training hot path of wudikua/ps.  The reference has no FFI layer; its
+ * boundary is a Java class surface.  Each entry point below names the Java method(s) it
+ * stands behind (paths relative to /root/reference/src/main/java/); INTEGRATION.md shows
+ * the JNI stubs a maintainer adds to call them from store.KVStore, layer.* and train.*.
+ *
+ * Conventions
+ *  - every function returns PS_OK (0) or a PS_ERR_* code; ps_last_error() gives the text.
+ *    (The reference swallows exceptions and returns null, KVStore.java:173-176,
+ *    PSClient.java:64-69, or System.exit(0)s, AdamUpdater.java:65-68; here misuse is an
+ *    error code and "key absent" is PS_NOT_FOUND, the 204 of net/PServer.java:84.)
+ *  - all pointers are HOST pointers owned by the caller unless the name ends in _dev;
+ *    device memory is owned by the library.  Matrices use the reference's layout: jblas
+ *    FloatMatrix, column-major rows x columns, i.e. a features x N activation is N
+ *    consecutive feature vectors.  "E" and "W" ids are int64 (the reference carries them in
+ *    a float matrix, exact below 2^24 only — SURVEY quirk 2; a float variant is provided).
+ *  - there is no CPU fallback: without a CUDA device every call fails with PS_ERR_CUDA.
+ */
+#ifndef PS_B200_H_
+#define PS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PS_OK 0
+#define PS_NOT_FOUND 204      /* net/PServer.java:28,84 — key absent */
+#define PS_ERR_ARG 400        /* bad argument / misuse (RuntimeException in the reference) */
+#define PS_ERR_CUDA 500       /* CUDA failure or no device (net/PServer.java:50-52 "500") */
+#define PS_ERR_CAPACITY 507   /* embedding table full */
+#define PS_ERR_STATE 409      /* call sequence violated (e.g. backward before forward) */
+
+/* FcLayer arithmetic: fp32 FFMA (exact-mode, parity to ~1e-6) or TF32 tcgen05 tensor cores */
+#define PS_FC_FP32 0
+#define PS_FC_TF32 1
+
+/* activations.* */
+#define PS_ACT_NONE 0
+#define PS_ACT_RELU 1      /* activations/Relu.java:7-19 */
+#define PS_ACT_SIGMOID 2   /* activations/Sigmoid.java:9-21 (clipped: 0.001 + 0.998*sigma) */
+#define PS_ACT_SOFTMAX 3   /* activations/Softmax.java:21-67 (inputs pre-scaled by 1/10000) */
+
+/* update.* */
+#define PS_UPD_ADAM 0      /* update/AdamUpdater.java:57-70  p = {alfa, beta1, beta2, epsilon} */
+#define PS_UPD_FTRL 1      /* update/FtrlUpdater.java:51-76  p = {alfa, beta, l1, l2}          */
+#define PS_UPD_SIMPLE 2    /* update/SimpleUpdater.java:20-22 p = {eta}                        */
+typedef struct ps_updater_spec {
+  int32_t kind;
+  float p[4];
+} ps_updater_spec;
+
+/* model.* */
+#define PS_MODEL_DNN 0        /* model/DNN.java:92-128 */
+#define PS_MODEL_WIDEDEEP 1   /* model/WideDeepNN.java:105-161 */
+#define PS_MODEL_FCNN 2       /* model/FullConnectedNN.java:86-110 */
+
+typedef struct ps_ctx ps_ctx;       /* the process-wide store.KVStore + device (KVStore.java:36,70) */
+typedef struct ps_emb ps_emb;       /* layer.EmbeddingLayer with its F EmbeddingFields */
+typedef struct ps_model ps_model;   /* a model.* network driven by train.Trainer, thread = 1 */
+
+const char* ps_last_error(void);
+int ps_abi_version(void);
+
+/* ---- context ------------------------------------------------------------------- */
+/* KVStore.ins() (KVStore.java:70) + Context.init() (context/Context.java:60-88).
+ * `seed` keys the deterministic replacement of the unseeded MatrixUtil.rand (ps_spec.h). */
+int ps_ctx_create(int device, uint64_t seed, ps_ctx** out);
+int ps_ctx_destroy(ps_ctx* ctx);
+int ps_ctx_set_fc_precision(ps_ctx* ctx, int mode);   /* PS_FC_FP32 | PS_FC_TF32 */
+int ps_ctx_synchronize(ps_ctx* ctx);
+int ps_ctx_launch_count(ps_ctx* ctx, int64_t* out);   /* kernels this library launched so far */
+int ps_ctx_device_info(ps_ctx* ctx, char* name, int cap, int* sms, int* cc_major, int* cc_minor);
+int ps_ctx_stream(ps_ctx* ctx, void** stream);        /* the cudaStream_t every step is ordered on (for event timing) */
+
+/* page-locked host memory for batch buffers (what a JNI caller wraps in a direct ByteBuffer):
+ * submit()/train_step() copy asynchronously only from such memory.                          */
+int ps_host_alloc(size_t bytes, void** out);
+int ps_host_free(void* p);
+
+/* ---- update.* -------------------------------------------------------------------
+ * AdamUpdater(String) / FtrlUpdater(String) (AdamUpdater.java:50-55, FtrlUpdater.java:44-49):
+ * parses "adam@alfa:0.005@beta1:0.9@beta2:0.999@epsilon:1.0E-8@" or the Ftrl spelling
+ * "adam@alfa:..@beta:..@l1:..@l2:..@" (FtrlUpdater.getName says "adam@", sic, :78-80).   */
+int ps_updater_parse(const char* name, ps_updater_spec* out);
+/* getName() (AdamUpdater.java:72-74, FtrlUpdater.java:78-80) with Java float spelling    */
+int ps_updater_name(const ps_updater_spec* spec, char* buf, int cap);
+/* Updater.update(key, w, dw) (update/Updater.java:8) on caller-held state, n elements,
+ * executed by the same device code the fused kernels use (test hook).                     */
+int ps_updater_apply(ps_ctx* ctx, const ps_updater_spec* spec, float* w, float* s1, float* s2, const float* g, int n);
+
+/* ---- layer.EmbeddingLayer / layer.EmbeddingField ---------------------------------
+ * EmbeddingLayer(name, F, F*D).build(F, D) (EmbeddingLayer.java:21,50-57).  Rows live in a
+ * GPU-resident open-addressing table of `capacity` slots keyed (field, id) — the reference's
+ * "emF<field>.<id>" strings (EmbeddingField.java:70) — created on first touch with the
+ * Xavier bound of EmbeddingField.java:40 (KVStore.java:136-159,168-190).                  */
+int ps_emb_create(ps_ctx* ctx, int F, int D, int64_t capacity, const ps_updater_spec* upd, ps_emb** out);
+int ps_emb_destroy(ps_emb* emb);
+/* EmbeddingLayer.forward() (EmbeddingLayer.java:25-48) → EmbeddingField.forward ×F
+ * (EmbeddingField.java:66-78): E is F x N (ids), out is (F*D) x N, ReLU applied.          */
+int ps_emb_forward(ps_emb* emb, const int64_t* E, int N, float* out);
+int ps_emb_forward_f32ids(ps_emb* emb, const float* E, int N, float* out);   /* the FloatMatrix "E" as the reference carries it */
+/* EmbeddingLayer.backward() called `calls` times (the reference makes 2 per step:
+ * ConcatLayer.java:44 and DNN.java:66-68) on delta (ld x N, rows >= F*D ignored), then
+ * KVStore.update(updaters) + KVStore.clear() (Trainer.java:93,95) for the touched rows:
+ * scatter-add, occurrence normalisation and the Adam/Ftrl step run in ONE kernel.        */
+int ps_emb_backward_update(ps_emb* emb, const float* delta, int ld, int N, int calls);
+/* KVStore.get(String) / PSClient.getList (KVStore.java:129-134, PSClient.java:72-97):
+ * host snapshot of rows (and optimiser state when s1/s2 non-null); found[i] = 0 if absent. */
+int ps_emb_get_rows(ps_emb* emb, const int32_t* fields, const int64_t* ids, int n, float* w, float* s1, float* s2, int32_t* found);
+/* KVStore.put / PSClient.updateList (KVStore.java:161-166, PSClient.java:128-151):
+ * replace != 0 overwrites, replace == 0 is insert-if-absent and returns the winner in w.   */
+int ps_emb_put_rows(ps_emb* emb, const int32_t* fields, const int64_t* ids, int n, float* w, int replace);
+int ps_emb_size(ps_emb* emb, int64_t* rows);
+
+/* ---- model.* driven by train.Trainer (thread = 1) --------------------------------
+ * DNN.buildModel / WideDeepNN.buildModel / FullConnectedNN.buildModel with the reference's
+ * default updaters (DNN.java:95, WideDeepNN.java:109-113).  emb_updater may be NULL (the
+ * "default" Adam) or e.g. Ftrl to express updaters.put("emF", ftrl) (KVStore.java:244-248). */
+int ps_model_create(ps_ctx* ctx, int kind, int F, int D, int Xn, const int32_t* fc_dims, int n_fc,
+                    int64_t emb_capacity, const ps_updater_spec* emb_updater, int max_batch, ps_model** out);
+int ps_model_destroy(ps_model* m);
+/* TrainerThread.call (TrainerThread.java:29-39: pullWeights + Model.train) followed by
+ * Trainer.train's KVStore.update(updaters) + clear() (Trainer.java:93,95).  Inputs as
+ * CTR.parseFeature builds them (CTR.java:47-68): E, W are F x N, X is Xn x N, Y is 1 x N.
+ * Returns the loss Model.train returns (Model.java:11).                                    */
+int ps_model_train_step(ps_model* m, const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, float* loss);
+/* the same step split in two so the host copy of batch i+1 overlaps the kernels of batch i
+ * (what the reference's DataSet reader thread does for parsing, data/DataSet.java:77-100):
+ * submit() enqueues H2D + the whole step, collect() waits for the oldest and returns its loss.
+ * At most 2 steps may be in flight; host buffers must stay valid until the matching collect. */
+int ps_model_submit(ps_model* m, const int64_t* E, const float* X, const int64_t* W, const float* Y, int N);
+int ps_model_collect(ps_model* m, float* loss);
+/* the step on inputs ALREADY resident in device memory (bench `value` leg); loss stays on the
+ * device until ps_model_read_loss.                                                         */
+int ps_model_train_step_dev(ps_model* m, const int64_t* E_dev, const float* X_dev, const int64_t* W_dev, const float* Y_dev, int N);
+int ps_model_read_loss(ps_model* m, float* loss);
+/* PredictThread.call + Trainer.predict (train/PredictThread.java, Trainer.java:44-68)      */
+int ps_model_predict(ps_model* m, const int64_t* E, const float* X, const int64_t* W, int N, float* out);
+/* KVStore.get(String) on any key the reference would hold: "fc0.weights" (out x in, column
+ * major), "fc0.bias", "wide.bias", "emF3.15757.0", "wide.weights.77.0".  *n = element count. */
+int ps_model_get(ps_model* m, const char* key, float* out, int cap, int* n);
+int ps_model_put(ps_model* m, const char* key, const float* in, int n);      /* KVStore.put */
+/* updater state of a key: which = 0 Adam M / Ftrl Z, 1 Adam V / Ftrl N                       */
+int ps_model_get_state(ps_model* m, const char* key, int which, float* out, int cap, int* n);
+/* Layer.getA() / getDelta() after the last step (layer/Layer.java:16-45): what = 0 A, 1 delta;
+ * layers: "embedding", "concat", "fc<i>", "wide", "addWideDeep"                               */
+int ps_model_tap(ps_model* m, const char* layer, int what, float* out, int cap, int* n);
+int ps_model_num_keys(ps_model* m, int64_t* out);            /* KVStore.store.size() */
+int ps_model_skipped_backward(ps_model* m, int* out);        /* DNN.java:58-63 early exit taken */
+/* step-level timing of the last ps_model_train_step_dev: device milliseconds per phase
+ * (CUDA events on the library's stream); names returned as a ';'-separated list.             */
+int ps_model_profile(ps_model* m, int enable);
+int ps_model_phase_times(ps_model* m, float* ms, int cap, int* n, char* names, int names_cap);
+
+/* ---- test hooks -------------------------------------------------------------------- */
+/* C (M x N, row-major, ldc) = A (M x K, row-major, lda) * B^T (B is N x K, row-major, ldb),
+ * through the FcLayer GEMM of the given precision mode.                                      */
+int ps_test_gemm_nt(ps_ctx* ctx, int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PS_B200_H_ */

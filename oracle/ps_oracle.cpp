@@ -325,7 +325,8 @@ static MP ce_backward(const FM& p, const FM& l) {                               
 }
 static float sml_forward(const FM& p, const FM& l) {                                       /* SoftmaxLoss.java:9-17 */
   float sum = 0;
-  for (int i = 0; i < p.cols; ++i) { const int hot = (int)l.at(0, i); sum += (float)(-std::log((double)p.at(hot, i))); }
+  /* `sum += -FastMath.log(p)` is a float/double compound assignment: the add happens in double, then narrows */
+  for (int i = 0; i < p.cols; ++i) { const int hot = (int)l.at(0, i); sum = (float)((double)sum + (-std::log((double)p.at(hot, i)))); }
   return sum / p.cols;
 }
 static MP sml_backward(const FM& p, const FM& l) {                                         /* :20-28 */

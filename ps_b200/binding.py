@@ -1,0 +1,339 @@
+"""ctypes binding of libps_b200.so (include/ps_b200.h) — what the JNI shim of
+integration/java does from Java, done from Python for the tests and the bench.
+
+There is NO fallback: if the shared library is missing or no CUDA device is present every
+entry point raises.  Nothing here touches oracle/.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(ROOT, "ps_b200", "lib", "libps_b200.so")
+
+PS_OK, PS_NOT_FOUND = 0, 204
+PS_FC_FP32, PS_FC_TF32 = 0, 1
+PS_UPD_ADAM, PS_UPD_FTRL, PS_UPD_SIMPLE = 0, 1, 2
+PS_MODEL_DNN, PS_MODEL_WIDEDEEP, PS_MODEL_FCNN = 0, 1, 2
+KINDS = {"dnn": PS_MODEL_DNN, "widedeep": PS_MODEL_WIDEDEEP, "fcnn": PS_MODEL_FCNN}
+
+
+class UpdaterSpec(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("p", C.c_float * 4)]
+
+    @staticmethod
+    def adam(alfa=0.005, beta1=0.9, beta2=0.999, epsilon=1e-8):
+        s = UpdaterSpec()
+        s.kind = PS_UPD_ADAM
+        s.p[:] = [alfa, beta1, beta2, epsilon]
+        return s
+
+    @staticmethod
+    def ftrl(alfa=0.005, beta=1.0, l1=0.001, l2=0.001):
+        s = UpdaterSpec()
+        s.kind = PS_UPD_FTRL
+        s.p[:] = [alfa, beta, l1, l2]
+        return s
+
+    @staticmethod
+    def simple(eta):
+        s = UpdaterSpec()
+        s.kind = PS_UPD_SIMPLE
+        s.p[:] = [eta, 0, 0, 0]
+        return s
+
+
+# every symbol include/ps_b200.h declares: name -> (restype, argtypes)
+_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_pp = C.POINTER(C.c_void_p)
+SYMBOLS = {
+    "ps_last_error": (C.c_char_p, []),
+    "ps_abi_version": (_i, []),
+    "ps_ctx_create": (_i, [_i, C.c_uint64, _pp]),
+    "ps_ctx_destroy": (_i, [_vp]),
+    "ps_ctx_set_fc_precision": (_i, [_vp, _i]),
+    "ps_ctx_synchronize": (_i, [_vp]),
+    "ps_ctx_launch_count": (_i, [_vp, C.POINTER(_i64)]),
+    "ps_ctx_device_info": (_i, [_vp, C.c_char_p, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "ps_ctx_stream": (_i, [_vp, _pp]),
+    "ps_host_alloc": (_i, [C.c_size_t, _pp]),
+    "ps_host_free": (_i, [_vp]),
+    "ps_updater_parse": (_i, [C.c_char_p, C.POINTER(UpdaterSpec)]),
+    "ps_updater_name": (_i, [C.POINTER(UpdaterSpec), C.c_char_p, _i]),
+    "ps_updater_apply": (_i, [_vp, C.POINTER(UpdaterSpec), _vp, _vp, _vp, _vp, _i]),
+    "ps_emb_create": (_i, [_vp, _i, _i, _i64, C.POINTER(UpdaterSpec), _pp]),
+    "ps_emb_destroy": (_i, [_vp]),
+    "ps_emb_forward": (_i, [_vp, _vp, _i, _vp]),
+    "ps_emb_forward_f32ids": (_i, [_vp, _vp, _i, _vp]),
+    "ps_emb_backward_update": (_i, [_vp, _vp, _i, _i, _i]),
+    "ps_emb_get_rows": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "ps_emb_put_rows": (_i, [_vp, _vp, _vp, _i, _vp, _i]),
+    "ps_emb_size": (_i, [_vp, C.POINTER(_i64)]),
+    "ps_model_create": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i64, C.POINTER(UpdaterSpec), _i, _pp]),
+    "ps_model_destroy": (_i, [_vp]),
+    "ps_model_train_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i, C.POINTER(_f)]),
+    "ps_model_submit": (_i, [_vp, _vp, _vp, _vp, _vp, _i]),
+    "ps_model_collect": (_i, [_vp, C.POINTER(_f)]),
+    "ps_model_train_step_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _i]),
+    "ps_model_read_loss": (_i, [_vp, C.POINTER(_f)]),
+    "ps_model_predict": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
+    "ps_model_get": (_i, [_vp, C.c_char_p, _vp, _i, C.POINTER(_i)]),
+    "ps_model_put": (_i, [_vp, C.c_char_p, _vp, _i]),
+    "ps_model_get_state": (_i, [_vp, C.c_char_p, _i, _vp, _i, C.POINTER(_i)]),
+    "ps_model_tap": (_i, [_vp, C.c_char_p, _i, _vp, _i, C.POINTER(_i)]),
+    "ps_model_num_keys": (_i, [_vp, C.POINTER(_i64)]),
+    "ps_model_skipped_backward": (_i, [_vp, C.POINTER(_i)]),
+    "ps_model_profile": (_i, [_vp, _i]),
+    "ps_model_phase_times": (_i, [_vp, _vp, _i, C.POINTER(_i), C.c_char_p, _i]),
+    "ps_test_gemm_nt": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i]),
+}
+
+_lib = None
+
+
+class PsError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libps_b200 error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    """Loads libps_b200.so; raises if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != PS_OK:
+        raise PsError(rc, lib().ps_last_error().decode())
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a, dt):
+    return None if a is None else np.ascontiguousarray(a, dt)
+
+
+class PinnedArray:
+    """numpy view over page-locked memory from ps_host_alloc."""
+
+    def __init__(self, shape, dtype):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = C.c_void_p()
+        check(lib().ps_host_alloc(self.nbytes, C.byref(self.ptr)))
+        buf = (C.c_byte * self.nbytes).from_address(self.ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().ps_host_free(self.ptr)
+            self.ptr = None
+
+
+class Context:
+    """store.KVStore.ins() + the device it lives on."""
+
+    def __init__(self, device=0, seed=0):
+        self.h = C.c_void_p()
+        check(lib().ps_ctx_create(device, seed, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().ps_ctx_destroy(self.h)
+            self.h = None
+
+    def set_fc_precision(self, mode):
+        check(lib().ps_ctx_set_fc_precision(self.h, mode))
+
+    def synchronize(self):
+        check(lib().ps_ctx_synchronize(self.h))
+
+    def launch_count(self):
+        v = C.c_int64()
+        check(lib().ps_ctx_launch_count(self.h, C.byref(v)))
+        return v.value
+
+    def stream(self):
+        s = C.c_void_p()
+        check(lib().ps_ctx_stream(self.h, C.byref(s)))
+        return s.value
+
+    def device_info(self):
+        name = C.create_string_buffer(128)
+        sms, ma, mi = C.c_int(), C.c_int(), C.c_int()
+        check(lib().ps_ctx_device_info(self.h, name, 128, C.byref(sms), C.byref(ma), C.byref(mi)))
+        return dict(name=name.value.decode(), sms=sms.value, cc=(ma.value, mi.value))
+
+    def updater_apply(self, spec, w, s1, s2, g):
+        check(lib().ps_updater_apply(self.h, C.byref(spec), _p(w), _p(s1), _p(s2), _p(g), w.size))
+
+    def gemm_nt(self, mode, A, B):
+        A, B = _c(A, np.float32), _c(B, np.float32)
+        M, K = A.shape
+        N = B.shape[0]
+        Cm = np.zeros((M, N), np.float32)
+        check(lib().ps_test_gemm_nt(self.h, mode, M, N, K, _p(A), K, _p(B), K, _p(Cm), N))
+        return Cm
+
+
+def updater_parse(name):
+    s = UpdaterSpec()
+    check(lib().ps_updater_parse(name.encode(), C.byref(s)))
+    return s
+
+
+def updater_name(spec):
+    buf = C.create_string_buffer(256)
+    check(lib().ps_updater_name(C.byref(spec), buf, 256))
+    return buf.value.decode()
+
+
+class EmbeddingLayer:
+    """layer.EmbeddingLayer (+ its EmbeddingFields) over the GPU-resident table."""
+
+    def __init__(self, ctx, F, D, capacity, updater=None):
+        self.ctx, self.F, self.D = ctx, F, D
+        self.h = C.c_void_p()
+        check(lib().ps_emb_create(ctx.h, F, D, capacity, C.byref(updater) if updater is not None else None, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().ps_emb_destroy(self.h)
+            self.h = None
+
+    def forward(self, E):
+        if E.dtype == np.float32:
+            E = _c(E, np.float32)
+            fn = lib().ps_emb_forward_f32ids
+        else:
+            E = _c(E, np.int64)
+            fn = lib().ps_emb_forward
+        N = E.shape[0]
+        out = np.empty((N, self.F * self.D), np.float32)
+        check(fn(self.h, _p(E), N, _p(out)))
+        return out
+
+    def backward_update(self, delta, calls=2):
+        delta = _c(delta, np.float32)
+        N, ld = delta.shape
+        check(lib().ps_emb_backward_update(self.h, _p(delta), ld, N, calls))
+
+    def get_rows(self, fields, ids, state=False):
+        fields, ids = _c(fields, np.int32), _c(ids, np.int64)
+        n = ids.size
+        w = np.zeros((n, self.D), np.float32)
+        s1 = np.zeros((n, self.D), np.float32) if state else None
+        s2 = np.zeros((n, self.D), np.float32) if state else None
+        found = np.zeros(n, np.int32)
+        check(lib().ps_emb_get_rows(self.h, _p(fields), _p(ids), n, _p(w), _p(s1), _p(s2), _p(found)))
+        return (w, s1, s2, found) if state else (w, found)
+
+    def put_rows(self, fields, ids, w, replace=True):
+        fields, ids, w = _c(fields, np.int32), _c(ids, np.int64), np.array(w, np.float32, order="C")
+        check(lib().ps_emb_put_rows(self.h, _p(fields), _p(ids), ids.size, _p(w), 1 if replace else 0))
+        return w
+
+    def size(self):
+        v = C.c_int64()
+        check(lib().ps_emb_size(self.h, C.byref(v)))
+        return v.value
+
+
+class Model:
+    """model.DNN / WideDeepNN / FullConnectedNN stepped like train.Trainer with thread = 1."""
+
+    def __init__(self, ctx, kind, F, D, Xn, fc, emb_capacity=1 << 20, emb_updater=None, max_batch=4096):
+        self.ctx, self.kind, self.F, self.D, self.Xn, self.fc = ctx, kind, F, D, Xn, list(fc)
+        self.h = C.c_void_p()
+        fca = np.asarray(fc, np.int32)
+        check(lib().ps_model_create(ctx.h, KINDS[kind] if isinstance(kind, str) else kind, F, D, Xn, _p(fca), len(fc), emb_capacity,
+                                    C.byref(emb_updater) if emb_updater is not None else None, max_batch, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().ps_model_destroy(self.h)
+            self.h = None
+
+    def train_step(self, E, X, W, Y):
+        E, W, X, Y = _c(E, np.int64), _c(W, np.int64), _c(X, np.float32), _c(Y, np.float32)
+        loss = C.c_float()
+        check(lib().ps_model_train_step(self.h, _p(E), _p(X), _p(W), _p(Y), Y.shape[0], C.byref(loss)))
+        return loss.value
+
+    def submit_ptrs(self, E, X, W, Y, N):
+        check(lib().ps_model_submit(self.h, E, X, W, Y, N))
+
+    def collect(self):
+        loss = C.c_float()
+        check(lib().ps_model_collect(self.h, C.byref(loss)))
+        return loss.value
+
+    def train_step_dev(self, E, X, W, Y, N):
+        check(lib().ps_model_train_step_dev(self.h, E, X, W, Y, N))
+
+    def read_loss(self):
+        loss = C.c_float()
+        check(lib().ps_model_read_loss(self.h, C.byref(loss)))
+        return loss.value
+
+    def predict(self, E, X, W, N, out_rows=1):
+        E, W, X = _c(E, np.int64), _c(W, np.int64), _c(X, np.float32)
+        out = np.zeros(N * out_rows, np.float32)
+        check(lib().ps_model_predict(self.h, _p(E), _p(X), _p(W), N, _p(out)))
+        return out
+
+    def _fetch(self, fn, key, *extra):
+        n = C.c_int()
+        rc = fn(self.h, key.encode(), *extra, None, 0, C.byref(n))
+        if rc == PS_NOT_FOUND:
+            return None
+        check(rc)
+        out = np.zeros(n.value, np.float32)
+        check(fn(self.h, key.encode(), *extra, _p(out), n.value, C.byref(n)))
+        return out
+
+    def get(self, key):
+        return self._fetch(lib().ps_model_get, key)
+
+    def get_state(self, key, which):
+        return self._fetch(lib().ps_model_get_state, key, which)
+
+    def tap(self, layer, what=0):
+        return self._fetch(lib().ps_model_tap, layer, what)
+
+    def put(self, key, v):
+        v = _c(v, np.float32)
+        check(lib().ps_model_put(self.h, key.encode(), _p(v), v.size))
+
+    def num_keys(self):
+        v = C.c_int64()
+        check(lib().ps_model_num_keys(self.h, C.byref(v)))
+        return v.value
+
+    def skipped_backward(self):
+        v = C.c_int()
+        check(lib().ps_model_skipped_backward(self.h, C.byref(v)))
+        return bool(v.value)
+
+    def profile(self, enable=True):
+        check(lib().ps_model_profile(self.h, 1 if enable else 0))
+
+    def phase_times(self):
+        n = C.c_int()
+        ms = np.zeros(64, np.float32)
+        names = C.create_string_buffer(1024)
+        check(lib().ps_model_phase_times(self.h, _p(ms), 64, C.byref(n), names, 1024))
+        nm = names.value.decode().split(";") if names.value else []
+        return dict(zip(nm, ms[: n.value].tolist()))

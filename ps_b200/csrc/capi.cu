@@ -1,0 +1,445 @@
+/*
+ * capi.cu — the extern "C" surface declared in include/ps_b200.h.  Every entry point catches
+ * psb::Error, stores the message for ps_last_error() and returns the code; nothing here computes
+ * on the CPU — if no CUDA device is present ps_ctx_create fails with PS_ERR_CUDA.
+ */
+#include <cmath>
+#include <cstdlib>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "model.cuh"
+
+namespace psb {
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& s) { g_last_error = s; }
+}  // namespace psb
+
+using namespace psb;
+
+struct ps_ctx { Ctx c; };
+struct ps_model { Model m; };
+struct ps_emb {
+  Ctx* ctx = nullptr;
+  EmbTable t;
+  int Ncap = 0, lastN = 0;
+  int64_t* dE = nullptr; float* dEf = nullptr; float* dOut = nullptr; float* dDelta = nullptr; size_t delta_cap = 0;
+};
+
+#define PS_TRY try {
+#define PS_CATCH                                                                  \
+  }                                                                               \
+  catch (const psb::Error& e) { set_last_error(e.what()); return e.code; }        \
+  catch (const std::exception& e) { set_last_error(e.what()); return PS_ERR_ARG; } \
+  return PS_OK;
+
+extern "C" {
+
+const char* ps_last_error(void) { return g_last_error.c_str(); }
+int ps_abi_version(void) { return 1; }
+
+int ps_ctx_create(int device, uint64_t seed, ps_ctx** out) {
+  PS_TRY
+  PS_REQUIRE(out != nullptr, PS_ERR_ARG, "ps_ctx_create: out is null");
+  int n = 0;
+  PS_CUDA(cudaGetDeviceCount(&n));
+  PS_REQUIRE(n > 0 && device >= 0 && device < n, PS_ERR_CUDA, "ps_ctx_create: no such CUDA device (there is no CPU fallback)");
+  PS_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  PS_CUDA(cudaGetDeviceProperties(&prop, device));
+  PS_REQUIRE(prop.major >= 10, PS_ERR_CUDA, "ps_ctx_create: libps_b200 is built for sm_100a (Blackwell) only");
+  ps_ctx* c = new ps_ctx();
+  c->c.device = device; c->c.seed = seed; c->c.num_sms = prop.multiProcessorCount;
+  PS_CUDA(cudaStreamCreateWithFlags(&c->c.stream, cudaStreamNonBlocking));
+  PS_CUDA(cudaStreamCreateWithFlags(&c->c.copy_stream, cudaStreamNonBlocking));
+  *out = c;
+  PS_CATCH
+}
+int ps_ctx_destroy(ps_ctx* ctx) {
+  PS_TRY
+  if (ctx) {
+    cudaStreamSynchronize(ctx->c.stream);
+    cudaStreamDestroy(ctx->c.stream); cudaStreamDestroy(ctx->c.copy_stream);
+    delete ctx;
+  }
+  PS_CATCH
+}
+int ps_ctx_set_fc_precision(ps_ctx* ctx, int mode) {
+  PS_TRY
+  PS_REQUIRE(ctx && (mode == PS_FC_FP32 || mode == PS_FC_TF32), PS_ERR_ARG, "ps_ctx_set_fc_precision: bad mode");
+  ctx->c.fc_precision = mode;
+  PS_CATCH
+}
+int ps_ctx_synchronize(ps_ctx* ctx) {
+  PS_TRY
+  PS_REQUIRE(ctx, PS_ERR_ARG, "null ctx");
+  PS_CUDA(cudaStreamSynchronize(ctx->c.copy_stream));
+  PS_CUDA(cudaStreamSynchronize(ctx->c.stream));
+  PS_CATCH
+}
+int ps_ctx_launch_count(ps_ctx* ctx, int64_t* out) {
+  PS_TRY
+  PS_REQUIRE(ctx && out, PS_ERR_ARG, "null argument");
+  *out = ctx->c.launches;
+  PS_CATCH
+}
+int ps_ctx_device_info(ps_ctx* ctx, char* name, int cap, int* sms, int* cc_major, int* cc_minor) {
+  PS_TRY
+  PS_REQUIRE(ctx, PS_ERR_ARG, "null ctx");
+  cudaDeviceProp prop;
+  PS_CUDA(cudaGetDeviceProperties(&prop, ctx->c.device));
+  if (name && cap > 0) { std::strncpy(name, prop.name, cap - 1); name[cap - 1] = 0; }
+  if (sms) *sms = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  PS_CATCH
+}
+int ps_ctx_stream(ps_ctx* ctx, void** stream) {   /* for callers that time with events on the library's stream */
+  PS_TRY
+  PS_REQUIRE(ctx && stream, PS_ERR_ARG, "null argument");
+  *stream = (void*)ctx->c.stream;
+  PS_CATCH
+}
+
+int ps_host_alloc(size_t bytes, void** out) {
+  PS_TRY
+  PS_REQUIRE(out, PS_ERR_ARG, "null out");
+  PS_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  PS_CATCH
+}
+int ps_host_free(void* p) {
+  PS_TRY
+  if (p) PS_CUDA(cudaFreeHost(p));
+  PS_CATCH
+}
+
+/* ---- update.* ---- */
+static bool between(const std::string& s, const std::string& open, float* v) {   /* StringUtils.substringBetween(str, open, "@") */
+  const size_t a = s.find(open);
+  if (a == std::string::npos) return false;
+  const size_t b = s.find('@', a + open.size());
+  if (b == std::string::npos) return false;
+  const std::string t = s.substr(a + open.size(), b - a - open.size());
+  char* end = nullptr;
+  *v = std::strtof(t.c_str(), &end);
+  return end != t.c_str();
+}
+
+int ps_updater_parse(const char* name, ps_updater_spec* out) {
+  PS_TRY
+  PS_REQUIRE(name && out, PS_ERR_ARG, "null argument");
+  const std::string s(name);
+  ps_updater_spec r{};
+  if (s.find("l1:") != std::string::npos) {       /* FtrlUpdater(String), FtrlUpdater.java:44-49 */
+    r.kind = PS_UPD_FTRL;
+    PS_REQUIRE(between(s, "alfa:", &r.p[0]) && between(s, "beta:", &r.p[1]) && between(s, "l1:", &r.p[2]) && between(s, "l2:", &r.p[3]),
+               PS_ERR_ARG, "ps_updater_parse: malformed ftrl name");
+  } else if (s.find("beta1:") != std::string::npos) {   /* AdamUpdater(String), AdamUpdater.java:50-55 */
+    r.kind = PS_UPD_ADAM;
+    PS_REQUIRE(between(s, "alfa:", &r.p[0]) && between(s, "beta1:", &r.p[1]) && between(s, "beta2:", &r.p[2]) && between(s, "epsilon:", &r.p[3]),
+               PS_ERR_ARG, "ps_updater_parse: malformed adam name");
+  } else if (s.find("eta:") != std::string::npos) {
+    r.kind = PS_UPD_SIMPLE;
+    PS_REQUIRE(between(s, "eta:", &r.p[0]), PS_ERR_ARG, "ps_updater_parse: malformed simple name");
+  } else {
+    PS_REQUIRE(false, PS_ERR_ARG, "ps_updater_parse: unknown updater name");
+  }
+  *out = r;
+  PS_CATCH
+}
+
+/* Float.toString: shortest decimal that round-trips; plain notation in [1e-3, 1e7), else d.dddE<n> */
+static std::string java_float(float v) {
+  if (v == 0.0f) return std::signbit(v) ? "-0.0" : "0.0";
+  char buf[64];
+  int prec = 1;
+  for (; prec <= 9; ++prec) { snprintf(buf, sizeof buf, "%.*e", prec - 1, (double)v); if (std::strtof(buf, nullptr) == v) break; }
+  std::string m(buf);
+  const size_t epos = m.find('e');
+  std::string digits = m.substr(0, epos);
+  const int ex = std::atoi(m.c_str() + epos + 1);
+  const bool neg = digits[0] == '-';
+  if (neg) digits = digits.substr(1);
+  std::string d;
+  for (char ch : digits) if (ch != '.') d.push_back(ch);
+  std::string r;
+  const float a = std::fabs(v);
+  if (a >= 1e-3f && a < 1e7f) {
+    if (ex >= 0) {
+      std::string ip = d.substr(0, std::min<size_t>(d.size(), (size_t)ex + 1));
+      while ((int)ip.size() < ex + 1) ip.push_back('0');
+      std::string fp = (int)d.size() > ex + 1 ? d.substr(ex + 1) : "0";
+      r = ip + "." + fp;
+    } else {
+      r = "0." + std::string((size_t)(-ex - 1), '0') + d;
+    }
+  } else {
+    r = d.substr(0, 1) + "." + (d.size() > 1 ? d.substr(1) : "0") + "E" + std::to_string(ex);
+  }
+  return neg ? "-" + r : r;
+}
+
+int ps_updater_name(const ps_updater_spec* spec, char* buf, int cap) {
+  PS_TRY
+  PS_REQUIRE(spec && buf && cap > 0, PS_ERR_ARG, "null argument");
+  std::string s;
+  const float* p = spec->p;
+  if (spec->kind == PS_UPD_ADAM) s = "adam@alfa:" + java_float(p[0]) + "@beta1:" + java_float(p[1]) + "@beta2:" + java_float(p[2]) + "@epsilon:" + java_float(p[3]) + "@";
+  else if (spec->kind == PS_UPD_FTRL) s = "adam@alfa:" + java_float(p[0]) + "@beta:" + java_float(p[1]) + "@l1:" + java_float(p[2]) + "@l2:" + java_float(p[3]) + "@";
+  else s = "simple@eta:" + java_float(p[0]) + "@";
+  PS_REQUIRE((int)s.size() + 1 <= cap, PS_ERR_ARG, "ps_updater_name: buffer too small");
+  std::memcpy(buf, s.c_str(), s.size() + 1);
+  PS_CATCH
+}
+
+int ps_updater_apply(ps_ctx* ctx, const ps_updater_spec* spec, float* w, float* s1, float* s2, const float* g, int n) {
+  PS_TRY
+  PS_REQUIRE(ctx && spec && w && s1 && s2 && g && n > 0, PS_ERR_ARG, "null argument");
+  cudaStream_t st = ctx->c.stream;
+  float* d = dmalloc<float>((size_t)4 * n);
+  PS_CUDA(cudaMemcpyAsync(d, w, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+  PS_CUDA(cudaMemcpyAsync(d + n, s1, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+  PS_CUDA(cudaMemcpyAsync(d + 2 * n, s2, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+  PS_CUDA(cudaMemcpyAsync(d + 3 * n, g, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+  updater_apply(&ctx->c, make_updater_dev(*spec), d, d + n, d + 2 * n, d + 3 * n, n);
+  PS_CUDA(cudaMemcpyAsync(w, d, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+  PS_CUDA(cudaMemcpyAsync(s1, d + n, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+  PS_CUDA(cudaMemcpyAsync(s2, d + 2 * n, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+  PS_CUDA(cudaStreamSynchronize(st));
+  dfree(d);
+  PS_CATCH
+}
+
+/* ---- layer.EmbeddingLayer ---- */
+int ps_emb_create(ps_ctx* ctx, int F, int D, int64_t capacity, const ps_updater_spec* upd, ps_emb** out) {
+  PS_TRY
+  PS_REQUIRE(ctx && out, PS_ERR_ARG, "null argument");
+  ps_updater_spec u;
+  if (upd) u = *upd;
+  else { u.kind = PS_UPD_ADAM; u.p[0] = (float)0.005; u.p[1] = (float)0.9; u.p[2] = (float)0.999; u.p[3] = (float)std::pow(10.0, -8); }
+  ps_emb* e = new ps_emb();
+  e->ctx = &ctx->c;
+  e->t.create(&ctx->c, F, D, capacity, u, 1);
+  PS_CUDA(cudaStreamSynchronize(ctx->c.stream));
+  *out = e;
+  PS_CATCH
+}
+int ps_emb_destroy(ps_emb* e) {
+  PS_TRY
+  if (e) {
+    cudaStreamSynchronize(e->ctx->stream);
+    e->t.destroy(); dfree(e->dE); dfree(e->dEf); dfree(e->dOut); dfree(e->dDelta);
+    delete e;
+  }
+  PS_CATCH
+}
+static void emb_reserve(ps_emb* e, int N) {
+  if (N <= e->Ncap) return;
+  PS_CUDA(cudaStreamSynchronize(e->ctx->stream));
+  dfree(e->dE); dfree(e->dEf); dfree(e->dOut);
+  e->Ncap = N;
+  const size_t L = (size_t)N * e->t.F;
+  e->dE = dmalloc<int64_t>(L); e->dEf = dmalloc<float>(L);
+  e->dOut = dmalloc<float>(L * e->t.D);
+  e->t.reserve((int64_t)L);
+}
+static int emb_forward_impl(ps_emb* e, const int64_t* E, const float* Ef, int N, float* out) {
+  PS_TRY
+  PS_REQUIRE(e && (E || Ef) && out && N > 0, PS_ERR_ARG, "null argument");
+  emb_reserve(e, N);
+  cudaStream_t st = e->ctx->stream;
+  const size_t L = (size_t)N * e->t.F;
+  if (E) PS_CUDA(cudaMemcpyAsync(e->dE, E, sizeof(int64_t) * L, cudaMemcpyHostToDevice, st));
+  else PS_CUDA(cudaMemcpyAsync(e->dEf, Ef, sizeof(float) * L, cudaMemcpyHostToDevice, st));
+  if (e->lastN) e->t.clear_batch();            /* a forward that was never followed by backward: drop its counts */
+  e->t.probe(E ? e->dE : nullptr, E ? nullptr : e->dEf, N);
+  e->t.gather(e->dOut, e->t.F * e->t.D, N);
+  PS_CUDA(cudaMemcpyAsync(out, e->dOut, sizeof(float) * L * e->t.D, cudaMemcpyDeviceToHost, st));
+  e->lastN = N;
+  e->t.check_errors();
+  PS_CATCH
+}
+int ps_emb_forward(ps_emb* e, const int64_t* E, int N, float* out) { return emb_forward_impl(e, E, nullptr, N, out); }
+int ps_emb_forward_f32ids(ps_emb* e, const float* E, int N, float* out) { return emb_forward_impl(e, nullptr, E, N, out); }
+
+int ps_emb_backward_update(ps_emb* e, const float* delta, int ld, int N, int calls) {
+  PS_TRY
+  PS_REQUIRE(e && delta && N > 0, PS_ERR_ARG, "null argument");
+  PS_REQUIRE(N == e->lastN, PS_ERR_STATE, "ps_emb_backward_update: no matching forward");
+  PS_REQUIRE(ld >= e->t.F * e->t.D, PS_ERR_ARG, "ps_emb_backward_update: delta has fewer rows than F*D");
+  cudaStream_t st = e->ctx->stream;
+  const size_t need = (size_t)N * ld;
+  if (need > e->delta_cap) { PS_CUDA(cudaStreamSynchronize(st)); dfree(e->dDelta); e->dDelta = dmalloc<float>(need); e->delta_cap = need; }
+  PS_CUDA(cudaMemcpyAsync(e->dDelta, delta, sizeof(float) * need, cudaMemcpyHostToDevice, st));
+  e->t.scatter_update(e->dDelta, ld, e->dOut, e->t.F * e->t.D, N, calls, nullptr);
+  e->lastN = 0;
+  PS_CUDA(cudaStreamSynchronize(st));
+  PS_CATCH
+}
+int ps_emb_get_rows(ps_emb* e, const int32_t* fields, const int64_t* ids, int n, float* w, float* s1, float* s2, int32_t* found) {
+  PS_TRY
+  PS_REQUIRE(e && fields && ids && w && found && n >= 0, PS_ERR_ARG, "null argument");
+  e->t.get_rows(fields, ids, n, w, s1, s2, found);
+  PS_CATCH
+}
+int ps_emb_put_rows(ps_emb* e, const int32_t* fields, const int64_t* ids, int n, float* w, int replace) {
+  PS_TRY
+  PS_REQUIRE(e && fields && ids && w && n >= 0, PS_ERR_ARG, "null argument");
+  e->t.put_rows(fields, ids, n, w, replace);
+  PS_CATCH
+}
+int ps_emb_size(ps_emb* e, int64_t* rows) {
+  PS_TRY
+  PS_REQUIRE(e && rows, PS_ERR_ARG, "null argument");
+  *rows = e->t.size();
+  PS_CATCH
+}
+
+/* ---- model.* ---- */
+int ps_model_create(ps_ctx* ctx, int kind, int F, int D, int Xn, const int32_t* fc_dims, int n_fc, int64_t emb_capacity,
+                    const ps_updater_spec* emb_updater, int max_batch, ps_model** out) {
+  PS_TRY
+  PS_REQUIRE(ctx && fc_dims && out, PS_ERR_ARG, "null argument");
+  ps_model* m = new ps_model();
+  try { m->m.create(&ctx->c, kind, F, D, Xn, fc_dims, n_fc, emb_capacity, emb_updater, max_batch); }
+  catch (...) { delete m; throw; }
+  *out = m;
+  PS_CATCH
+}
+int ps_model_destroy(ps_model* m) {
+  PS_TRY
+  if (m) { m->m.destroy(); delete m; }
+  PS_CATCH
+}
+int ps_model_submit(ps_model* m, const int64_t* E, const float* X, const int64_t* W, const float* Y, int N) {
+  PS_TRY
+  PS_REQUIRE(m, PS_ERR_ARG, "null model");
+  HostBatch b; b.E = E; b.X = X; b.W = W; b.Y = Y; b.N = N;
+  m->m.submit(b);
+  PS_CATCH
+}
+int ps_model_collect(ps_model* m, float* loss) {
+  PS_TRY
+  PS_REQUIRE(m && loss, PS_ERR_ARG, "null argument");
+  *loss = m->m.collect();
+  PS_CATCH
+}
+int ps_model_train_step(ps_model* m, const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, float* loss) {
+  PS_TRY
+  PS_REQUIRE(m && loss, PS_ERR_ARG, "null argument");
+  HostBatch b; b.E = E; b.X = X; b.W = W; b.Y = Y; b.N = N;
+  m->m.submit(b);
+  *loss = m->m.collect();
+  PS_CATCH
+}
+int ps_model_train_step_dev(ps_model* m, const int64_t* E_dev, const float* X_dev, const int64_t* W_dev, const float* Y_dev, int N) {
+  PS_TRY
+  PS_REQUIRE(m, PS_ERR_ARG, "null model");
+  PS_REQUIRE(m->m.in_flight == 0, PS_ERR_STATE, "host steps in flight; collect first");
+  m->m.step_device(E_dev, X_dev, W_dev, Y_dev, N, true);
+  m->m.last_N = N; m->m.last_train = true;
+  PS_CATCH
+}
+int ps_model_read_loss(ps_model* m, float* loss) {
+  PS_TRY
+  PS_REQUIRE(m && loss, PS_ERR_ARG, "null argument");
+  *loss = m->m.read_loss();
+  PS_CATCH
+}
+int ps_model_predict(ps_model* m, const int64_t* E, const float* X, const int64_t* W, int N, float* out) {
+  PS_TRY
+  PS_REQUIRE(m && X && out, PS_ERR_ARG, "null argument");
+  HostBatch b; b.E = E; b.X = X; b.W = W; b.Y = nullptr; b.N = N;
+  m->m.predict(b, out);
+  PS_CATCH
+}
+static int copy_out(const std::vector<float>& v, float* out, int cap, int* n) {
+  if (n) *n = (int)v.size();
+  if (out && cap >= (int)v.size()) std::memcpy(out, v.data(), sizeof(float) * v.size());
+  return PS_OK;
+}
+int ps_model_get(ps_model* m, const char* key, float* out, int cap, int* n) {
+  PS_TRY
+  PS_REQUIRE(m && key, PS_ERR_ARG, "null argument");
+  std::vector<float> v;
+  const int rc = m->m.get(key, v);
+  if (rc != PS_OK) { set_last_error(std::string("key absent: ") + key); return rc; }
+  copy_out(v, out, cap, n);
+  PS_CATCH
+}
+int ps_model_put(ps_model* m, const char* key, const float* in, int n) {
+  PS_TRY
+  PS_REQUIRE(m && key && in, PS_ERR_ARG, "null argument");
+  m->m.put(key, in, n);
+  PS_CATCH
+}
+int ps_model_get_state(ps_model* m, const char* key, int which, float* out, int cap, int* n) {
+  PS_TRY
+  PS_REQUIRE(m && key, PS_ERR_ARG, "null argument");
+  std::vector<float> v;
+  const int rc = m->m.get_state(key, which, v);
+  if (rc != PS_OK) { set_last_error(std::string("key absent: ") + key); return rc; }
+  copy_out(v, out, cap, n);
+  PS_CATCH
+}
+int ps_model_tap(ps_model* m, const char* layer, int what, float* out, int cap, int* n) {
+  PS_TRY
+  PS_REQUIRE(m && layer, PS_ERR_ARG, "null argument");
+  std::vector<float> v;
+  const int rc = m->m.tap(layer, what, v);
+  if (rc != PS_OK) { set_last_error(std::string("no such tap: ") + layer); return rc; }
+  copy_out(v, out, cap, n);
+  PS_CATCH
+}
+int ps_model_num_keys(ps_model* m, int64_t* out) {
+  PS_TRY
+  PS_REQUIRE(m && out, PS_ERR_ARG, "null argument");
+  *out = m->m.num_keys();
+  PS_CATCH
+}
+int ps_model_skipped_backward(ps_model* m, int* out) {
+  PS_TRY
+  PS_REQUIRE(m && out, PS_ERR_ARG, "null argument");
+  *out = m->m.last_status.skip;
+  PS_CATCH
+}
+int ps_model_profile(ps_model* m, int enable) {
+  PS_TRY
+  PS_REQUIRE(m, PS_ERR_ARG, "null model");
+  m->m.profile = enable != 0;
+  PS_CATCH
+}
+int ps_model_phase_times(ps_model* m, float* ms, int cap, int* n, char* names, int names_cap) {
+  PS_TRY
+  PS_REQUIRE(m && n, PS_ERR_ARG, "null argument");
+  const auto& v = m->m.phase_ms;
+  *n = (int)v.size();
+  if (ms && cap >= (int)v.size()) std::memcpy(ms, v.data(), sizeof(float) * v.size());
+  if (names && names_cap > 0) {
+    std::string s;
+    for (size_t i = 0; i < m->m.phase_names.size() && i < v.size(); ++i) { if (i) s += ";"; s += m->m.phase_names[i]; }
+    std::strncpy(names, s.c_str(), names_cap - 1); names[names_cap - 1] = 0;
+  }
+  PS_CATCH
+}
+
+/* ---- test hook ---- */
+int ps_test_gemm_nt(ps_ctx* ctx, int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc) {
+  PS_TRY
+  PS_REQUIRE(ctx && A && B && C && M > 0 && N > 0 && K > 0, PS_ERR_ARG, "bad argument");
+  cudaStream_t st = ctx->c.stream;
+  float* dA = dmalloc<float>((size_t)M * lda); float* dB = dmalloc<float>((size_t)N * ldb); float* dC = dmalloc_zero<float>((size_t)M * ldc, st);
+  float* dbias = dmalloc_zero<float>(N, st);
+  PS_CUDA(cudaMemcpyAsync(dA, A, sizeof(float) * M * lda, cudaMemcpyHostToDevice, st));
+  PS_CUDA(cudaMemcpyAsync(dB, B, sizeof(float) * N * ldb, cudaMemcpyHostToDevice, st));
+  FcFwdArgs a{};
+  a.B = M; a.in = K; a.out = N; a.A = dA; a.lda = lda; a.W = dB; a.ldw = ldb; a.bias = dbias; a.act = PS_ACT_NONE; a.Z = dC; a.ldz = ldc;
+  if (mode == PS_FC_FP32) fc_forward_fp32(&ctx->c, a); else fc_forward_tf32(&ctx->c, a);
+  PS_CUDA(cudaMemcpyAsync(C, dC, sizeof(float) * M * ldc, cudaMemcpyDeviceToHost, st));
+  PS_CUDA(cudaStreamSynchronize(st));
+  dfree(dA); dfree(dB); dfree(dC); dfree(dbias);
+  PS_CATCH
+}
+
+}  // extern "C"

@@ -1,0 +1,97 @@
+/*
+ * common.cuh — error handling, the device context and small device helpers shared by
+ * every translation unit of libps_b200.so (sm_100a only; there is no CPU fallback:
+ * every entry point fails with PS_ERR_CUDA when no B200 is present).
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/ps_b200.h"
+#include "../../include/ps_spec.h"
+
+namespace psb {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+void set_last_error(const std::string& s);
+
+#define PS_CUDA(expr)                                                                        \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess) {                                                                \
+      char b__[512];                                                                         \
+      snprintf(b__, sizeof b__, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      throw psb::Error(PS_ERR_CUDA, b__);                                                    \
+    }                                                                                        \
+  } while (0)
+
+#define PS_REQUIRE(cond, code, msg)                                                          \
+  do {                                                                                       \
+    if (!(cond)) {                                                                           \
+      char b__[512];                                                                         \
+      snprintf(b__, sizeof b__, "%s (%s:%d)", msg, __FILE__, __LINE__);                      \
+      throw psb::Error(code, b__);                                                           \
+    }                                                                                        \
+  } while (0)
+
+#define PS_LAUNCH_CHECK() PS_CUDA(cudaGetLastError())
+
+/* One per process and device (the reference's KVStore is a process-wide singleton,
+ * store/KVStore.java:36,70; here the context owns what that singleton owned).       */
+struct Ctx {
+  int device = 0;
+  int num_sms = 148;
+  uint64_t seed = 0;
+  cudaStream_t stream = nullptr;   /* compute stream: every kernel of a step is ordered on it */
+  cudaStream_t copy_stream = nullptr; /* H2D staging for the pipelined trainer */
+  int fc_precision = PS_FC_FP32;
+  long launches = 0;               /* kernels launched by this library (bench gpu_launches) */
+};
+
+template <class T>
+T* dmalloc(size_t n) {
+  T* p = nullptr;
+  if (n == 0) n = 1;
+  PS_CUDA(cudaMalloc(&p, n * sizeof(T)));
+  return p;
+}
+template <class T>
+T* dmalloc_zero(size_t n, cudaStream_t s) {
+  T* p = dmalloc<T>(n);
+  PS_CUDA(cudaMemsetAsync(p, 0, (n ? n : 1) * sizeof(T), s));
+  return p;
+}
+inline void dfree(void* p) { if (p) cudaFree(p); }
+
+static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+/* ---- device helpers ----------------------------------------------------------- */
+#if defined(__CUDACC__)
+__device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st_f4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+/* streaming (read-once / write-once) 128-bit accesses that do not allocate in L1 */
+__device__ __forceinline__ float4 ld_f4_stream(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_f4_stream(float* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+/* 128-bit vector reduction into global memory (sm_90+): one L2 atomic transaction per 16 B */
+__device__ __forceinline__ void red_add_f4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+#endif
+
+}  // namespace psb

@@ -1,0 +1,241 @@
+/*
+ * dense.cu — dense parameter kernels and the network tail (sm_100a).
+ *
+ * Reference restated (/root/reference/src/main/java/):
+ *   dense_update      store/KVStore.java:240-268 (g = sum / cnt) + update/*.java, for FcLayer keys
+ *   tail_binary       layer/AddLayer.java:33-61, activations/Sigmoid.java:9-21,
+ *                     loss/CrossEntropy.java:10-28, model/DNN.java:47-63
+ *   tail_softmax      activations/Softmax.java:21-67, loss/SoftmaxLoss.java:9-28
+ */
+#include "dense.cuh"
+#include "gemm.cuh"
+
+namespace psb {
+
+/* ------------------------------------------------------------------ init */
+/* MatrixUtil.rand(out, in, max) (util/MatrixUtil.java:62-74) with the counter-based draw of
+ * ps_spec.h; element j of the reference's column-major out x in matrix is j = o + out*i.     */
+__global__ void dense_init_kernel(float* __restrict__ W, int out, int in, int ldw, float* __restrict__ Wt, int ldwt, uint64_t seed, uint64_t key, float maxv) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)out * in) return;
+  const int o = (int)(idx / in), i = (int)(idx - (long)o * in);
+  const float v = ps_init_value(seed, key, (uint32_t)(o + out * i), maxv);
+  W[(size_t)o * ldw + i] = v;
+  if (Wt) Wt[(size_t)i * ldwt + o] = v;
+}
+void dense_init(Ctx* ctx, float* W, int out, int in, int ldw, float* Wt, int ldwt, uint64_t key, float maxv) {
+  dense_init_kernel<<<ceil_div((long)out * in, 256), 256, 0, ctx->stream>>>(W, out, in, ldw, Wt, ldwt, ctx->seed, key, maxv);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+}
+
+__global__ void fill_column_kernel(float* buf, int ld, int col, int rows, float value) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < rows) buf[(size_t)r * ld + col] = value;
+}
+void fill_column(Ctx* ctx, float* buf, int ld, int col, int rows, float value) {
+  fill_column_kernel<<<ceil_div(rows, 256), 256, 0, ctx->stream>>>(buf, ld, col, rows, value);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+}
+
+__global__ void transpose_copy_kernel(const float* __restrict__ in, int ldi, float* __restrict__ out, int ldo, int rows, int cols) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)rows * cols) return;
+  const int r = (int)(idx / cols), c = (int)(idx - (long)r * cols);
+  out[(size_t)c * ldo + r] = in[(size_t)r * ldi + c];
+}
+void transpose_copy(Ctx* ctx, const float* in, int ldi, float* out, int ldo, int rows, int cols) {
+  transpose_copy_kernel<<<ceil_div((long)rows * cols, 256), 256, 0, ctx->stream>>>(in, ldi, out, ldo, rows, cols);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+}
+
+/* ------------------------------------------------------------------ fused dense update */
+/* One work item per (o, c), c in [0, in]: c < in is weight (o, c), c == in is bias o.  The
+ * gradient is the sum of the wgrad partial slabs divided by N: FcLayer.java:103 rowMeans and
+ * :105 divi(N); KVStore.update's own division is by sumCnt = 1 (thread = 1).  Ftrl's early
+ * return looks at element 0 of the key's gradient (FtrlUpdater.java:52).                     */
+__global__ void __launch_bounds__(256) dense_update_kernel(const __grid_constant__ DenseUpdateArgs a, const StepStatus* __restrict__ st) {
+  if (st->skip) return;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.total) return;
+  int li = 0;
+  while (li + 1 < a.n_layers && idx >= a.l[li + 1].first) ++li;
+  const DenseLayerDesc& L = a.l[li];
+  const long r = idx - L.first;
+  const int cols = L.in + 1;
+  const int o = (int)(r / cols), c = (int)(r - (long)o * cols);
+  const float Nf = (float)a.N;
+  float g = 0.0f;
+  for (int z = 0; z < L.nsplit; ++z) g = __fadd_rn(g, L.G[(size_t)z * L.slab + (size_t)o * L.ldg + c]);
+  g = __fdiv_rn(g, Nf);
+  const bool is_bias = c == L.in;
+  const UpdaterDev& u = is_bias ? L.updB : L.updW;
+  if (u.kind == PS_UPD_FTRL) {
+    float g0 = 0.0f;
+    const size_t o0 = is_bias ? (size_t)L.in : 0;
+    for (int z = 0; z < L.nsplit; ++z) g0 = __fadd_rn(g0, L.G[(size_t)z * L.slab + o0]);
+    if (__fdiv_rn(g0, Nf) == 0.0f) return;
+  }
+  if (is_bias) {
+    float w = L.bias[o], m1 = L.sb1[o], m2 = L.sb2[o];
+    apply_elem(u, w, m1, m2, g);
+    L.bias[o] = w; L.sb1[o] = m1; L.sb2[o] = m2;
+  } else {
+    const size_t off = (size_t)o * L.ldw + c;
+    float w = L.W[off], m1 = L.sW1[off], m2 = L.sW2[off];
+    apply_elem(u, w, m1, m2, g);
+    L.W[off] = w; L.sW1[off] = m1; L.sW2[off] = m2;
+    if (L.Wt) L.Wt[(size_t)c * L.ldwt + o] = w;
+  }
+}
+void dense_update(Ctx* ctx, const DenseUpdateArgs& a, const StepStatus* st) {
+  if (a.total <= 0) return;
+  dense_update_kernel<<<ceil_div(a.total, 256), 256, 0, ctx->stream>>>(a, st);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+}
+
+__global__ void wide_bias_update_kernel(float* bias, float* s1, float* s2, UpdaterDev upd, const StepStatus* st) {
+  if (st->skip) return;
+  const float g = st->gbar;
+  if (upd.kind == PS_UPD_FTRL && g == 0.0f) return;
+  float w = bias[0], a = s1[0], b = s2[0];
+  apply_elem(upd, w, a, b, g);
+  bias[0] = w; s1[0] = a; s2[0] = b;
+}
+void wide_bias_update(Ctx* ctx, float* bias, float* s1, float* s2, const UpdaterDev& upd, const StepStatus* st) {
+  wide_bias_update_kernel<<<1, 1, 0, ctx->stream>>>(bias, s1, s2, upd, st);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+}
+
+__global__ void updater_apply_kernel(UpdaterDev u, float* w, float* s1, float* s2, const float* g, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (u.kind == PS_UPD_FTRL && g[0] == 0.0f) return;
+  float wv = w[i], a = s1[i], b = s2[i];
+  apply_elem(u, wv, a, b, g[i]);
+  w[i] = wv; s1[i] = a; s2[i] = b;
+}
+void updater_apply(Ctx* ctx, const UpdaterDev& u, float* w, float* s1, float* s2, const float* g, int n) {
+  updater_apply_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(u, w, s1, s2, g, n);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+}
+
+/* ------------------------------------------------------------------ tails */
+constexpr int kTailThreads = 1024;
+
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  const int t = threadIdx.x;
+  sh[t] = v;
+  __syncthreads();
+  for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+    if (t < s) sh[t] = __fadd_rn(sh[t], sh[t + s]);
+    __syncthreads();
+  }
+  const float r = sh[0];
+  __syncthreads();
+  return r;
+}
+
+/* One block: the batch is at most a few 10^4 scalars.  Per-sample arithmetic follows the Java
+ * expressions operation by operation (double exp/log, float elsewhere); the two batch sums
+ * (loss, rowMeans of delta) are tree reductions, so they agree with the reference's running
+ * float sums to ~1e-7 relative, not bit for bit.                                              */
+__global__ void __launch_bounds__(kTailThreads) tail_binary_kernel(int N, const float* __restrict__ zdeep, int ldz, const float* __restrict__ zwide,
+                                                                   const float* __restrict__ Y, float* __restrict__ p_out, int ldp,
+                                                                   float* __restrict__ d_out, int ldd, int train, StepStatus* __restrict__ st) {
+  __shared__ float sh[kTailThreads];
+  float loss_part = 0.0f, d_part = 0.0f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float z = zdeep[(size_t)n * ldz];
+    if (zwide) z = __fadd_rn(z, zwide[n]);                                   /* AddLayer.java:36 */
+    const float p = sigmoid_clipped(z);                                      /* Sigmoid.java:11 */
+    p_out[(size_t)n * ldp] = p;
+    if (train) {
+      const float l = Y[n];
+      const float omp = __fsub_rn(1.0f, p);
+      loss_part = __fadd_rn(loss_part, (float)((double)(-l) * log((double)p) - ((double)__fsub_rn(1.0f, l) * log((double)omp))));   /* CrossEntropy.java:15 */
+      float d = __fdiv_rn(__fsub_rn(p, l), __fmul_rn(p, omp));                /* CrossEntropy.java:25 */
+      d = __fmul_rn(d, __fmul_rn(p, omp));                                   /* Sigmoid.java:18 */
+      d_out[(size_t)n * ldd] = d;
+      d_part = __fadd_rn(d_part, d);
+    }
+  }
+  if (!train) return;
+  const float loss = __fdiv_rn(block_sum(loss_part, sh), (float)N);
+  const float gbar = __fdiv_rn(block_sum(d_part, sh), (float)N);
+  if (threadIdx.x == 0) {
+    st->loss = loss;
+    st->gbar = gbar;
+    st->skip = (loss <= 0.01f || isnan(loss)) ? 1 : 0;                       /* DNN.java:58, CrossEntropy.slim */
+  }
+}
+void tail_binary(Ctx* ctx, int N, const float* zdeep, int ldz, const float* zwide, const float* Y, float* p_out, int ldp, float* d_out, int ldd,
+                 int train, StepStatus* st) {
+  tail_binary_kernel<<<1, kTailThreads, 0, ctx->stream>>>(N, zdeep, ldz, zwide, Y, p_out, ldp, d_out, ldd, train, st);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+}
+
+__global__ void __launch_bounds__(kTailThreads) tail_softmax_kernel(int N, int C, float* __restrict__ Z, int ldz, const float* __restrict__ Y,
+                                                                    float* __restrict__ d_out, int ldd, int train, StepStatus* __restrict__ st) {
+  __shared__ float sh[kTailThreads];
+  float loss_part = 0.0f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float* z = Z + (size_t)n * ldz;
+    float mx = -INFINITY;
+    for (int i = 0; i < C; ++i) { const float x = __fdiv_rn(z[i], 10000.0f); z[i] = x; mx = fmaxf(mx, x); }      /* Softmax.java:22-24 */
+    float s = 0.0f;
+    for (int i = 0; i < C; ++i) { const float e = (float)exp((double)__fsub_rn(z[i], mx)); z[i] = e; s = __fadd_rn(s, e); }   /* :26-33 */
+    for (int i = 0; i < C; ++i) {
+      float v = __fdiv_rn(z[i], s);
+      if (v == 0.0f) v = 0.001f; else if (v == 1.0f) v = 0.999f;             /* :36-40 */
+      z[i] = v;
+    }
+    if (train) {
+      const int hot = (int)Y[n];                                             /* SoftmaxLoss.java:12 */
+      const float ph = z[hot];
+      loss_part = __fadd_rn(loss_part, (float)(-log((double)ph)));
+      const float dy = __fdiv_rn(-1.0f, ph);                                 /* SoftmaxLoss.java:26 */
+      float* d = d_out + (size_t)n * ldd;
+      for (int k = 0; k < C; ++k) {                                          /* Softmax.java:51-63, one-hot dy */
+        const float yk = z[k];
+        const float t = (k == hot) ? __fmul_rn(yk, __fsub_rn(1.0f, yk)) : __fmul_rn(-ph, yk);
+        d[k] = __fmul_rn(t, dy);
+      }
+    }
+  }
+  if (!train) return;
+  const float loss = __fdiv_rn(block_sum(loss_part, sh), (float)N);
+  if (threadIdx.x == 0) {
+    st->loss = loss;
+    st->gbar = 0.0f;
+    st->skip = (loss <= 0.01f || isnan(loss)) ? 1 : 0;                       /* FullConnectedNN.java: same early exit */
+  }
+}
+void tail_softmax(Ctx* ctx, int N, int C, float* Z, int ldz, const float* Y, float* d_out, int ldd, int train, StepStatus* st) {
+  tail_softmax_kernel<<<1, kTailThreads, 0, ctx->stream>>>(N, C, Z, ldz, Y, d_out, ldd, train, st);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+}
+
+__global__ void publish_status_kernel(StepStatus* st, const uint32_t* emb_counters, const uint32_t* wide_counters, uint32_t seq, StepStatus* host) {
+  StepStatus s = *st;
+  s.emb_err = emb_counters ? emb_counters[1] : 0u;
+  s.n_unique = emb_counters ? emb_counters[0] : 0u;
+  s.wide_err = wide_counters ? wide_counters[0] : 0u;
+  s.seq = seq;
+  *host = s;
+  __threadfence_system();
+}
+void publish_status(Ctx* ctx, StepStatus* st, const uint32_t* emb_counters, const uint32_t* wide_counters, uint32_t seq, StepStatus* host_mapped) {
+  publish_status_kernel<<<1, 1, 0, ctx->stream>>>(st, emb_counters, wide_counters, seq, host_mapped);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+}
+
+}  // namespace psb

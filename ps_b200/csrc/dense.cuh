@@ -1,0 +1,61 @@
+/*
+ * dense.cuh — dense-parameter side of store.KVStore (FcLayer weights / biases, wide.bias):
+ * initialisation, the fused gradient-mean + updater step, and the network tail
+ * (AddLayer + Sigmoid/Softmax + loss + loss gradient + last activation derivative).
+ */
+#pragma once
+#include "common.cuh"
+#include "updaters.cuh"
+
+namespace psb {
+
+/* device-resident step status; published to mapped host memory by the last kernel of a step */
+struct StepStatus {
+  float loss;       /* Model.train return value (model/DNN.java:47) */
+  int skip;         /* 1 when loss <= CrossEntropy.slim or NaN: backward + update skipped (DNN.java:58-63) */
+  float gbar;       /* rowMeans of the top delta: LRLayer's gradient (layer/LRLayer.java:110) */
+  uint32_t emb_err; /* embedding table full */
+  uint32_t wide_err;
+  uint32_t n_unique;/* unique embedding keys of the batch */
+  uint32_t seq;     /* step sequence number */
+  uint32_t pad;
+};
+
+/* one FcLayer's parameters as the fused update kernel sees them */
+struct DenseLayerDesc {
+  float *W, *Wt, *bias;           /* W [out][ldw]; Wt [in][ldwt] transposed copy or null; bias [out] */
+  float *sW1, *sW2, *sb1, *sb2;   /* updater state of "fc<i>.weights" / "fc<i>.bias" */
+  const float* G;                 /* [nsplit][out][ldg]; column `in` is the bias-gradient sum */
+  size_t slab;
+  int nsplit, out, in, ldw, ldwt, ldg;
+  UpdaterDev updW, updB;
+  long first;                     /* index of this layer's first work item */
+};
+constexpr int kMaxDenseLayers = 16;
+struct DenseUpdateArgs {
+  DenseLayerDesc l[kMaxDenseLayers];
+  int n_layers;
+  long total;
+  int N;                          /* batch size: gradients are batch means (FcLayer.java:103,105) */
+};
+
+void dense_init(Ctx* ctx, float* W, int out, int in, int ldw, float* Wt, int ldwt, uint64_t key, float maxv);
+void fill_column(Ctx* ctx, float* buf, int ld, int col, int rows, float value);
+void dense_update(Ctx* ctx, const DenseUpdateArgs& a, const StepStatus* st);
+
+/* binary tail: z = deep (+ wide); p = clipped sigmoid; CrossEntropy forward/backward; sigmoid
+ * derivative.  Writes p to p_out (stride ldp), the post-derivative delta to d_out (stride ldd). */
+void tail_binary(Ctx* ctx, int N, const float* zdeep, int ldz, const float* zwide, const float* Y, float* p_out, int ldp,
+                 float* d_out, int ldd, int train, StepStatus* st);
+/* multi-class tail (FullConnectedNN): Softmax(10000) in place on Z, SoftmaxLoss, Softmax.backward */
+void tail_softmax(Ctx* ctx, int N, int C, float* Z, int ldz, const float* Y, float* d_out, int ldd, int train, StepStatus* st);
+/* wide.bias step with the same gbar the wide weights receive (LRLayer.java:112-113) */
+void wide_bias_update(Ctx* ctx, float* bias, float* s1, float* s2, const UpdaterDev& upd, const StepStatus* st);
+/* copies the status (plus table error flags) to mapped host memory */
+void publish_status(Ctx* ctx, StepStatus* st, const uint32_t* emb_counters, const uint32_t* wide_counters, uint32_t seq, StepStatus* host_mapped);
+/* Updater.update on caller-provided device arrays (test hook for ps_updater_apply) */
+void updater_apply(Ctx* ctx, const UpdaterDev& u, float* w, float* s1, float* s2, const float* g, int n);
+/* out[c*ldo + r] = in[r*ldi + c]  (layout conversion at the get/put boundary) */
+void transpose_copy(Ctx* ctx, const float* in, int ldi, float* out, int ldo, int rows, int cols);
+
+}  // namespace psb

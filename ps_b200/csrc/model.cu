@@ -1,0 +1,476 @@
+/*
+ * model.cu — model.DNN / model.WideDeepNN / model.FullConnectedNN wired to the GPU store and
+ * stepped the way train.Trainer steps them with thread = 1 (TrainerThread.java:29-39,
+ * Trainer.java:70-101): pullWeights → forward loop → loss → reverse loop → KVStore.update →
+ * KVStore.clear, as ONE ordered sequence of kernels on one stream.
+ *
+ * Layer order of the reference and where it went:
+ *   EmbeddingLayer.forward + ConcatLayer.forward   → EmbTable::probe + gather straight into the
+ *        concat buffer act[0] = [emb | X | 1]       (EmbeddingLayer.java:25-48, ConcatLayer.java:30-37)
+ *   FcLayer.forward ×L                             → fc_forward_*        (FcLayer.java:74-91)
+ *   LRLayer.forward                                → WideTable::forward  (LRLayer.java:62-98)
+ *   AddLayer + Sigmoid + CrossEntropy fwd/bwd      → tail_binary         (AddLayer.java:33-61, CrossEntropy.java:10-28)
+ *   FcLayer.backward ×L                            → fc_wgrad_* + fc_dgrad_* (FcLayer.java:93-110)
+ *   EmbeddingLayer.backward ×2 + KVStore.update    → EmbTable::scatter_update
+ *   LRLayer.backward + KVStore.update              → WideTable::update_all + wide_bias_update
+ *   KVStore.update for fc keys                     → dense_update
+ */
+#include "model.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstddef>
+#include <cstdlib>
+
+namespace psb {
+
+static float xavier(int in, int out) { /* FcLayer.java:39,46 / EmbeddingField.java:40 */
+  return (float)(4 * (std::sqrt(6.0) / std::sqrt((double)(in + out))));
+}
+
+void FcLayer::create(Ctx* ctx, const std::string& nm, int in_, int out_, int act_, const ps_updater_spec& u, int nsplit_) {
+  name = nm; in = in_; out = out_; act = act_; nsplit = nsplit_;
+  ldw = round_up(in + 1, 8); ldwt = round_up(out, 8);
+  updW = u; updB = u;
+  cudaStream_t s = ctx->stream;
+  W = dmalloc_zero<float>((size_t)out * ldw, s);
+  Wt = dmalloc_zero<float>((size_t)in * ldwt, s);
+  bias = dmalloc_zero<float>(out, s);
+  sW1 = dmalloc_zero<float>((size_t)out * ldw, s); sW2 = dmalloc_zero<float>((size_t)out * ldw, s);
+  sb1 = dmalloc_zero<float>(out, s); sb2 = dmalloc_zero<float>(out, s);
+  G = dmalloc_zero<float>((size_t)nsplit * out * ldw, s);
+  /* FcLayer.pullWeights (FcLayer.java:112-115): KVStore.get(name + ".weights", initW) creates on first use */
+  dense_init(ctx, W, out, in, ldw, Wt, ldwt, ps_name_key((name + ".weights").c_str()), xavier(in, out));
+  dense_init(ctx, bias, out, 1, 1, nullptr, 0, ps_name_key((name + ".bias").c_str()), xavier(in, 1));
+}
+void FcLayer::destroy() {
+  dfree(W); dfree(Wt); dfree(bias); dfree(sW1); dfree(sW2); dfree(sb1); dfree(sb2); dfree(G);
+  W = Wt = bias = sW1 = sW2 = sb1 = sb2 = G = nullptr;
+}
+
+static ps_updater_spec mk_spec(int kind, float a, float b, float c, float d) {
+  ps_updater_spec s; s.kind = kind; s.p[0] = a; s.p[1] = b; s.p[2] = c; s.p[3] = d; return s;
+}
+
+void Model::create(Ctx* c, int kind_, int F_, int D_, int Xn_, const int32_t* fc_dims, int n_fc, int64_t emb_capacity,
+                   const ps_updater_spec* emb_updater, int max_batch) {
+  PS_REQUIRE(kind_ >= PS_MODEL_DNN && kind_ <= PS_MODEL_FCNN, PS_ERR_ARG, "model: unknown kind");
+  PS_REQUIRE(n_fc >= 1 && n_fc <= kMaxDenseLayers && max_batch > 0 && Xn_ > 0, PS_ERR_ARG, "model: bad dims");
+  ctx = c; kind = kind_; Xn = Xn_; Bmax = max_batch; L = n_fc;
+  has_emb = kind != PS_MODEL_FCNN; has_wide = kind == PS_MODEL_WIDEDEEP;
+  F = has_emb ? F_ : 0; D = has_emb ? D_ : 0;
+  if (has_emb) PS_REQUIRE(F > 0 && D > 0, PS_ERR_ARG, "model: need F > 0 and D > 0");
+  if (kind != PS_MODEL_FCNN) PS_REQUIRE(fc_dims[n_fc - 1] == 1, PS_ERR_ARG, "model: DNN/WideDeepNN end in a 1-unit layer");
+  upd_default = mk_spec(PS_UPD_ADAM, (float)0.005, (float)0.9, (float)0.999, (float)std::pow(10.0, -8));   /* DNN.java:95 */
+  upd_wide = mk_spec(PS_UPD_FTRL, 0.005f, 1.0f, 0.001f, 0.001f);                                           /* WideDeepNN.java:109 */
+  cudaStream_t s = ctx->stream;
+
+  width.assign(L + 1, 0); ld.assign(L + 1, 0);
+  width[0] = has_emb ? F * D + Xn : Xn;
+  for (int l = 0; l < L; ++l) width[l + 1] = fc_dims[l];
+  act.assign(L + 1, nullptr); delta.assign(L + 1, nullptr);
+  for (int l = 0; l <= L; ++l) {
+    ld[l] = round_up(width[l] + 1, 8);
+    act[l] = dmalloc_zero<float>((size_t)Bmax * ld[l], s);
+    delta[l] = dmalloc_zero<float>((size_t)Bmax * ld[l], s);
+    if (l < L) fill_column(ctx, act[l], ld[l], width[l], Bmax, 1.0f);   /* the constant-1 column that yields db in wgrad */
+  }
+  fcs.resize(L);
+  for (int l = 0; l < L; ++l)   /* FcLayer.build (FcLayer.java:53-70): ReLU inside, the top activation belongs to the tail */
+    fcs[l].create(ctx, "fc" + std::to_string(l), width[l], width[l + 1], l + 1 == L ? PS_ACT_NONE : PS_ACT_RELU, upd_default, 8);
+
+  if (has_emb) emb.create(ctx, F, D, emb_capacity, emb_updater ? *emb_updater : upd_default, (int64_t)Bmax * F);
+  if (has_wide) {
+    wide.create(ctx, 1 << 18, upd_wide);                   /* CTR.wideSize = 100000 hashed ids (CTR.java:36) */
+    wide_bias = dmalloc_zero<float>(4, s);                 /* LRLayer ctor: zeros(1) (LRLayer.java:45-52) */
+    wide_z = dmalloc_zero<float>(Bmax, s);
+    P = dmalloc_zero<float>(Bmax, s);
+  }
+  st_dev = dmalloc_zero<StepStatus>(1, s);
+  for (auto& S : stage) {
+    if (has_emb) S.E = dmalloc<int64_t>((size_t)Bmax * F);
+    if (has_wide) S.W = dmalloc<int64_t>((size_t)Bmax * F);
+    S.X = dmalloc<float>((size_t)Bmax * Xn);
+    S.Y = dmalloc<float>(Bmax);
+    PS_CUDA(cudaHostAlloc(&S.st_host, sizeof(StepStatus), cudaHostAllocMapped));
+    std::memset(S.st_host, 0, sizeof(StepStatus));
+    PS_CUDA(cudaEventCreateWithFlags(&S.h2d_done, cudaEventDisableTiming));
+    PS_CUDA(cudaEventCreateWithFlags(&S.step_done, cudaEventDisableTiming));
+  }
+  PS_CUDA(cudaStreamSynchronize(s));
+}
+
+void Model::destroy() {
+  if (!ctx) return;
+  cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->copy_stream);
+  for (auto& f : fcs) f.destroy();
+  for (auto p : act) dfree(p);
+  for (auto p : delta) dfree(p);
+  if (has_emb) emb.destroy();
+  if (has_wide) { wide.destroy(); dfree(wide_bias); dfree(wide_z); dfree(P); }
+  dfree(st_dev);
+  for (auto& S : stage) {
+    dfree(S.E); dfree(S.W); dfree(S.X); dfree(S.Y);
+    if (S.st_host) cudaFreeHost(S.st_host);
+    if (S.h2d_done) cudaEventDestroy(S.h2d_done);
+    if (S.step_done) cudaEventDestroy(S.step_done);
+  }
+  for (auto e : ev) cudaEventDestroy(e);
+  ctx = nullptr;
+}
+
+void Model::mark(const char* phase) {
+  if (!profile) return;
+  cudaEvent_t e;
+  PS_CUDA(cudaEventCreate(&e));
+  PS_CUDA(cudaEventRecord(e, ctx->stream));
+  ev.push_back(e);
+  phase_names.push_back(phase);
+}
+void Model::finish_profile() {
+  if (!profile || ev.empty()) return;
+  PS_CUDA(cudaStreamSynchronize(ctx->stream));
+  phase_ms.clear();
+  std::vector<std::string> names;
+  for (size_t i = 1; i < ev.size(); ++i) {
+    float ms = 0.f;
+    PS_CUDA(cudaEventElapsedTime(&ms, ev[i - 1], ev[i]));
+    phase_ms.push_back(ms);
+    names.push_back(phase_names[i]);
+  }
+  for (auto e : ev) cudaEventDestroy(e);
+  ev.clear();
+  phase_names = names;
+}
+
+static const int* skip_ptr(const StepStatus* st) {
+  return reinterpret_cast<const int*>(reinterpret_cast<const char*>(st) + offsetof(StepStatus, skip));
+}
+static const float* gbar_ptr(const StepStatus* st) {
+  return reinterpret_cast<const float*>(reinterpret_cast<const char*>(st) + offsetof(StepStatus, gbar));
+}
+
+void Model::step_device(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, bool train) {
+  PS_REQUIRE(N > 0 && N <= Bmax, PS_ERR_ARG, "model: batch size must be in [1, max_batch]");
+  cudaStream_t s = ctx->stream;
+  const bool fp32 = ctx->fc_precision == PS_FC_FP32;
+  if (profile) { for (auto e : ev) cudaEventDestroy(e); ev.clear(); phase_names.clear(); }
+  mark("begin");
+  /* ---- forward (DNN.java:44-46) ---- */
+  if (has_emb) {
+    emb.probe(E, nullptr, N);
+    mark("emb_probe");
+    emb.gather(act[0], ld[0], N);
+    mark("emb_gather");
+    PS_CUDA(cudaMemcpy2DAsync(act[0] + F * D, sizeof(float) * ld[0], X, sizeof(float) * Xn, sizeof(float) * Xn, N, cudaMemcpyDeviceToDevice, s));
+  } else {
+    PS_CUDA(cudaMemcpy2DAsync(act[0], sizeof(float) * ld[0], X, sizeof(float) * Xn, sizeof(float) * Xn, N, cudaMemcpyDeviceToDevice, s));
+  }
+  mark("x_concat");
+  if (has_wide) { wide.forward(W, N, F, wide_bias, wide_z); mark("wide_fwd"); }
+  for (int l = 0; l < L; ++l) {
+    FcFwdArgs a{};
+    a.B = N; a.in = fcs[l].in; a.out = fcs[l].out;
+    a.A = act[l]; a.lda = ld[l]; a.W = fcs[l].W; a.ldw = fcs[l].ldw; a.bias = fcs[l].bias; a.act = fcs[l].act;
+    a.Z = act[l + 1]; a.ldz = ld[l + 1];
+    if (fp32) fc_forward_fp32(ctx, a); else fc_forward_tf32(ctx, a);
+  }
+  mark("fc_fwd");
+  if (kind == PS_MODEL_FCNN)
+    tail_softmax(ctx, N, width[L], act[L], ld[L], Y, delta[L], ld[L], train ? 1 : 0, st_dev);
+  else
+    tail_binary(ctx, N, act[L], ld[L], has_wide ? wide_z : nullptr, Y, has_wide ? P : act[L], has_wide ? 1 : ld[L], delta[L], ld[L],
+                train ? 1 : 0, st_dev);
+  mark("tail");
+  if (!train) {
+    if (has_emb) emb.clear_batch();
+    return;
+  }
+  /* ---- backward (DNN.java:64-68) ---- */
+  for (int l = L - 1; l >= 0; --l) {
+    FcWgradArgs g{};
+    g.B = N; g.in = fcs[l].in; g.out = fcs[l].out;
+    g.dl = delta[l + 1]; g.ldd = ld[l + 1]; g.A = act[l]; g.lda = ld[l];
+    g.G = fcs[l].G; g.ldg = fcs[l].ldw; g.slab = (size_t)fcs[l].out * fcs[l].ldw; g.nsplit = fcs[l].nsplit;
+    if (fp32) fc_wgrad_fp32(ctx, g); else fc_wgrad_tf32(ctx, g);
+    FcDgradArgs d{};
+    d.B = N; d.in = fcs[l].in; d.out = fcs[l].out;
+    d.dl = delta[l + 1]; d.ldd = ld[l + 1]; d.W = fcs[l].W; d.ldw = fcs[l].ldw; d.Wt = fcs[l].Wt; d.ldwt = fcs[l].ldwt;
+    d.act_below = l > 0 ? fcs[l - 1].act : PS_ACT_NONE; d.Y = act[l]; d.ldy = ld[l];
+    d.n_cols = fcs[l].in; d.dX = delta[l]; d.ldx = ld[l];
+    if (fp32) fc_dgrad_fp32(ctx, d); else fc_dgrad_tf32(ctx, d);
+  }
+  mark("fc_bwd");
+  /* ---- KVStore.update + clear (Trainer.java:93,95) ---- */
+  if (has_emb) { emb.scatter_update(delta[0], ld[0], act[0], ld[0], N, 2, skip_ptr(st_dev)); mark("emb_bwd_update"); }
+  if (has_wide) {
+    wide.update_all(gbar_ptr(st_dev), skip_ptr(st_dev));
+    wide_bias_update(ctx, wide_bias, wide_bias + 1, wide_bias + 2, make_updater_dev(upd_wide), st_dev);
+    mark("wide_update");
+  }
+  DenseUpdateArgs u{};
+  u.n_layers = L; u.N = N;
+  long first = 0;
+  for (int l = 0; l < L; ++l) {
+    DenseLayerDesc& q = u.l[l];
+    const FcLayer& f = fcs[l];
+    q.W = f.W; q.Wt = f.Wt; q.bias = f.bias; q.sW1 = f.sW1; q.sW2 = f.sW2; q.sb1 = f.sb1; q.sb2 = f.sb2;
+    q.G = f.G; q.slab = (size_t)f.out * f.ldw; q.nsplit = f.nsplit; q.out = f.out; q.in = f.in; q.ldw = f.ldw; q.ldwt = f.ldwt; q.ldg = f.ldw;
+    q.updW = make_updater_dev(f.updW); q.updB = make_updater_dev(f.updB);
+    q.first = first; first += (long)f.out * (f.in + 1);
+  }
+  u.total = first;
+  dense_update(ctx, u, st_dev);
+  mark("dense_update");
+}
+
+void Model::submit(const HostBatch& b) {
+  PS_REQUIRE(in_flight < 2, PS_ERR_STATE, "model: two steps already in flight; collect first");
+  PS_REQUIRE(b.N > 0 && b.N <= Bmax, PS_ERR_ARG, "model: batch size must be in [1, max_batch]");
+  PS_REQUIRE(b.X && b.Y && (!has_emb || b.E) && (!has_wide || b.W), PS_ERR_ARG, "model: missing input matrix");
+  Stage& S = stage[next_stage];
+  cudaStream_t cs = ctx->copy_stream;
+  const size_t N = (size_t)b.N;
+  if (has_emb) PS_CUDA(cudaMemcpyAsync(S.E, b.E, sizeof(int64_t) * N * F, cudaMemcpyHostToDevice, cs));
+  if (has_wide) PS_CUDA(cudaMemcpyAsync(S.W, b.W, sizeof(int64_t) * N * F, cudaMemcpyHostToDevice, cs));
+  PS_CUDA(cudaMemcpyAsync(S.X, b.X, sizeof(float) * N * Xn, cudaMemcpyHostToDevice, cs));
+  PS_CUDA(cudaMemcpyAsync(S.Y, b.Y, sizeof(float) * N, cudaMemcpyHostToDevice, cs));
+  PS_CUDA(cudaEventRecord(S.h2d_done, cs));
+  PS_CUDA(cudaStreamWaitEvent(ctx->stream, S.h2d_done, 0));
+  S.N = b.N;
+  step_device(S.E, S.X, S.W, S.Y, b.N, true);
+  publish_status(ctx, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, ++seq, S.st_host);
+  PS_CUDA(cudaEventRecord(S.step_done, ctx->stream));
+  S.busy = true;
+  next_stage ^= 1; in_flight++;
+  last_N = b.N; last_train = true;
+}
+
+float Model::collect() {
+  PS_REQUIRE(in_flight > 0, PS_ERR_STATE, "model: nothing in flight");
+  Stage& S = stage[oldest_stage];
+  PS_CUDA(cudaEventSynchronize(S.step_done));
+  last_status = *S.st_host;
+  S.busy = false;
+  oldest_stage ^= 1; in_flight--;
+  if (profile && in_flight == 0) finish_profile();
+  PS_REQUIRE(last_status.emb_err == 0, PS_ERR_CAPACITY, "embedding table is full: raise emb_capacity");
+  PS_REQUIRE(last_status.wide_err == 0, PS_ERR_CAPACITY, "wide table is full");
+  return last_status.loss;
+}
+
+float Model::read_loss() {
+  PS_REQUIRE(in_flight == 0, PS_ERR_STATE, "model: host steps in flight");
+  publish_status(ctx, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, ++seq, stage[0].st_host);
+  PS_CUDA(cudaStreamSynchronize(ctx->stream));
+  last_status = *stage[0].st_host;
+  if (profile) finish_profile();
+  PS_REQUIRE(last_status.emb_err == 0, PS_ERR_CAPACITY, "embedding table is full: raise emb_capacity");
+  PS_REQUIRE(last_status.wide_err == 0, PS_ERR_CAPACITY, "wide table is full");
+  return last_status.loss;
+}
+
+void Model::predict(const HostBatch& b, float* out) {
+  PS_REQUIRE(in_flight == 0, PS_ERR_STATE, "model: steps in flight; collect first");
+  PS_REQUIRE(b.N > 0 && b.N <= Bmax, PS_ERR_ARG, "model: batch size must be in [1, max_batch]");
+  Stage& S = stage[0];
+  cudaStream_t s = ctx->stream;
+  const size_t N = (size_t)b.N;
+  if (has_emb) PS_CUDA(cudaMemcpyAsync(S.E, b.E, sizeof(int64_t) * N * F, cudaMemcpyHostToDevice, s));
+  if (has_wide) PS_CUDA(cudaMemcpyAsync(S.W, b.W, sizeof(int64_t) * N * F, cudaMemcpyHostToDevice, s));
+  PS_CUDA(cudaMemcpyAsync(S.X, b.X, sizeof(float) * N * Xn, cudaMemcpyHostToDevice, s));
+  step_device(S.E, S.X, S.W, nullptr, b.N, false);
+  if (kind == PS_MODEL_FCNN)
+    PS_CUDA(cudaMemcpy2DAsync(out, sizeof(float) * width[L], act[L], sizeof(float) * ld[L], sizeof(float) * width[L], N, cudaMemcpyDeviceToHost, s));
+  else if (has_wide)
+    PS_CUDA(cudaMemcpyAsync(out, P, sizeof(float) * N, cudaMemcpyDeviceToHost, s));
+  else
+    PS_CUDA(cudaMemcpy2DAsync(out, sizeof(float), act[L], sizeof(float) * ld[L], sizeof(float), N, cudaMemcpyDeviceToHost, s));
+  PS_CUDA(cudaStreamSynchronize(s));
+  last_N = b.N; last_train = false;
+  if (has_emb) emb.check_errors();
+  if (has_wide) wide.check_errors();
+}
+
+/* ------------------------------------------------------------------ KVStore.get / put by reference key */
+/* Java's Float.toString / Double.toString spellings of an integer id ("15757.0", "1.6777216E7"):
+ * strtod accepts both (EmbeddingField.java:70-71,88-89; LRLayer.java:78).                      */
+int parse_key(const std::string& key, int* field, int64_t* id) {
+  if (key.compare(0, 3, "emF") == 0) {
+    char* end = nullptr;
+    const long f = std::strtol(key.c_str() + 3, &end, 10);
+    if (end && *end == '.' && end != key.c_str() + 3) {
+      char* end2 = nullptr;
+      const double v = std::strtod(end + 1, &end2);
+      if (end2 && *end2 == '\0' && end2 != end + 1) { *field = (int)f; *id = (int64_t)v; return 0; }
+    }
+  }
+  static const std::string wp = "wide.weights.";
+  if (key.compare(0, wp.size(), wp) == 0) {
+    char* end2 = nullptr;
+    const double v = std::strtod(key.c_str() + wp.size(), &end2);
+    if (end2 && *end2 == '\0' && end2 != key.c_str() + wp.size()) { *field = 0; *id = (int64_t)v; return 1; }
+  }
+  return 2;
+}
+
+static bool fc_key(const std::vector<FcLayer>& fcs, const std::string& key, int* l, bool* is_bias) {
+  for (size_t i = 0; i < fcs.size(); ++i) {
+    if (key == fcs[i].name + ".weights") { *l = (int)i; *is_bias = false; return true; }
+    if (key == fcs[i].name + ".bias") { *l = (int)i; *is_bias = true; return true; }
+  }
+  return false;
+}
+
+static void fetch_fc(Ctx* ctx, const FcLayer& f, bool is_bias, const float* Wsrc, const float* bsrc, std::vector<float>& out) {
+  if (is_bias) {
+    out.resize(f.out);
+    PS_CUDA(cudaMemcpyAsync(out.data(), bsrc, sizeof(float) * f.out, cudaMemcpyDeviceToHost, ctx->stream));
+    PS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return;
+  }
+  std::vector<float> tmp((size_t)f.out * f.ldw);
+  PS_CUDA(cudaMemcpyAsync(tmp.data(), Wsrc, sizeof(float) * tmp.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  PS_CUDA(cudaStreamSynchronize(ctx->stream));
+  out.resize((size_t)f.out * f.in);   /* jblas out x in, column-major: index(o, i) = o + out*i */
+  for (int i = 0; i < f.in; ++i)
+    for (int o = 0; o < f.out; ++o) out[(size_t)o + (size_t)f.out * i] = tmp[(size_t)o * f.ldw + i];
+}
+
+int Model::get(const std::string& key, std::vector<float>& out) {
+  int field = 0; int64_t id = 0; int l = 0; bool is_bias = false;
+  const int k = parse_key(key, &field, &id);
+  if (k == 0) {
+    if (!has_emb || field < 0 || field >= F) return PS_NOT_FOUND;
+    out.resize(D);
+    int32_t f32 = field, found = 0;
+    emb.get_rows(&f32, &id, 1, out.data(), nullptr, nullptr, &found);
+    return found ? PS_OK : PS_NOT_FOUND;
+  }
+  if (k == 1) {
+    if (!has_wide) return PS_NOT_FOUND;
+    out.resize(1);
+    return wide.get(id, out.data(), nullptr, nullptr) ? PS_OK : PS_NOT_FOUND;
+  }
+  if (fc_key(fcs, key, &l, &is_bias)) { fetch_fc(ctx, fcs[l], is_bias, fcs[l].W, fcs[l].bias, out); return PS_OK; }
+  if (has_wide && key == "wide.bias") {
+    out.resize(1);
+    PS_CUDA(cudaMemcpyAsync(out.data(), wide_bias, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    PS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PS_OK;
+  }
+  return PS_NOT_FOUND;
+}
+
+int Model::get_state(const std::string& key, int which, std::vector<float>& out) {
+  int field = 0; int64_t id = 0; int l = 0; bool is_bias = false;
+  const int k = parse_key(key, &field, &id);
+  if (k == 0) {
+    if (!has_emb || field < 0 || field >= F) return PS_NOT_FOUND;
+    std::vector<float> w(D), a(D), b(D);
+    int32_t f32 = field, found = 0;
+    emb.get_rows(&f32, &id, 1, w.data(), a.data(), b.data(), &found);
+    if (!found) return PS_NOT_FOUND;
+    out = which ? b : a;
+    return PS_OK;
+  }
+  if (k == 1) {
+    if (!has_wide) return PS_NOT_FOUND;
+    float w, a, b;
+    if (!wide.get(id, &w, &a, &b)) return PS_NOT_FOUND;
+    out.assign(1, which ? b : a);
+    return PS_OK;
+  }
+  if (fc_key(fcs, key, &l, &is_bias)) {
+    fetch_fc(ctx, fcs[l], is_bias, which ? fcs[l].sW2 : fcs[l].sW1, which ? fcs[l].sb2 : fcs[l].sb1, out);
+    return PS_OK;
+  }
+  if (has_wide && key == "wide.bias") {
+    out.resize(1);
+    PS_CUDA(cudaMemcpyAsync(out.data(), wide_bias + 1 + (which ? 1 : 0), sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    PS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PS_OK;
+  }
+  return PS_NOT_FOUND;
+}
+
+void Model::put(const std::string& key, const float* in, int n) {
+  int field = 0; int64_t id = 0; int l = 0; bool is_bias = false;
+  const int k = parse_key(key, &field, &id);
+  if (k == 0) {
+    PS_REQUIRE(has_emb && field >= 0 && field < F && n == D, PS_ERR_ARG, "put: bad embedding key or length");
+    std::vector<float> tmp(in, in + n);
+    int32_t f32 = field;
+    emb.put_rows(&f32, &id, 1, tmp.data(), 1);
+    return;
+  }
+  if (k == 1) {
+    PS_REQUIRE(has_wide && n == 1, PS_ERR_ARG, "put: bad wide key or length");
+    wide.put(id, in[0]);
+    PS_CUDA(cudaStreamSynchronize(ctx->stream));
+    wide.check_errors();
+    return;
+  }
+  if (fc_key(fcs, key, &l, &is_bias)) {
+    FcLayer& f = fcs[l];
+    if (is_bias) {
+      PS_REQUIRE(n == f.out, PS_ERR_ARG, "put: bias length mismatch");
+      PS_CUDA(cudaMemcpyAsync(f.bias, in, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
+      PS_CUDA(cudaStreamSynchronize(ctx->stream));
+      return;
+    }
+    PS_REQUIRE(n == f.out * f.in, PS_ERR_ARG, "put: weight length mismatch");
+    std::vector<float> tmp((size_t)f.out * f.ldw, 0.f), tmpt((size_t)f.in * f.ldwt, 0.f);
+    for (int i = 0; i < f.in; ++i)
+      for (int o = 0; o < f.out; ++o) {
+        const float v = in[(size_t)o + (size_t)f.out * i];
+        tmp[(size_t)o * f.ldw + i] = v; tmpt[(size_t)i * f.ldwt + o] = v;
+      }
+    PS_CUDA(cudaMemcpyAsync(f.W, tmp.data(), sizeof(float) * tmp.size(), cudaMemcpyHostToDevice, ctx->stream));
+    PS_CUDA(cudaMemcpyAsync(f.Wt, tmpt.data(), sizeof(float) * tmpt.size(), cudaMemcpyHostToDevice, ctx->stream));
+    PS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return;
+  }
+  if (has_wide && key == "wide.bias") {
+    PS_REQUIRE(n == 1, PS_ERR_ARG, "put: wide.bias is 1x1");
+    PS_CUDA(cudaMemcpyAsync(wide_bias, in, sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    PS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return;
+  }
+  PS_REQUIRE(false, PS_ERR_ARG, "put: unknown key");
+}
+
+static void fetch_cols(Ctx* ctx, const float* src, int ldsrc, int cols, int N, std::vector<float>& out) {
+  out.resize((size_t)N * cols);
+  PS_CUDA(cudaMemcpy2DAsync(out.data(), sizeof(float) * cols, src, sizeof(float) * ldsrc, sizeof(float) * cols, N, cudaMemcpyDeviceToHost, ctx->stream));
+  PS_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+/* Layer.getA() / getDelta() of the last step.  delta semantics follow the reference's in-place
+ * updates: fc<l>.delta = W_l^T d_l, later multiplied in place by the activation derivative of
+ * fc<l-1> (FcLayer.java:100-102 acting on next.delta).                                         */
+int Model::tap(const std::string& layer, int what, std::vector<float>& out) {
+  const int N = last_N;
+  if (N <= 0) return PS_NOT_FOUND;
+  if (what == 1 && !last_train) return PS_NOT_FOUND;
+  if (has_emb && layer == "embedding") { fetch_cols(ctx, what ? delta[0] : act[0], ld[0], what ? width[0] : F * D, N, out); return PS_OK; }
+  if (has_emb && layer == "concat") { fetch_cols(ctx, what ? delta[0] : act[0], ld[0], width[0], N, out); return PS_OK; }
+  for (int l = 0; l < L; ++l)
+    if (layer == fcs[l].name) {
+      if (what == 0) fetch_cols(ctx, act[l + 1], ld[l + 1], width[l + 1], N, out);
+      else fetch_cols(ctx, delta[l], ld[l], width[l], N, out);
+      return PS_OK;
+    }
+  if (has_wide && layer == "wide" && what == 0) { fetch_cols(ctx, wide_z, 1, 1, N, out); return PS_OK; }
+  if (has_wide && layer == "addWideDeep") { fetch_cols(ctx, what ? delta[L] : P, what ? ld[L] : 1, 1, N, out); return PS_OK; }
+  return PS_NOT_FOUND;
+}
+
+int64_t Model::num_keys() {
+  int64_t n = 2 * (int64_t)L;
+  if (has_emb) n += emb.size();
+  if (has_wide) n += wide.size() + 1;
+  return n;
+}
+
+}  // namespace psb

@@ -1,0 +1,90 @@
+/*
+ * model.cuh — host-side mirror of the reference's class surface for the hot path, in C++
+ * because the reference is compiled (Java) code and no JDK exists in this image
+ * (SURVEY.md §8b).  Names follow the reference: layer.FcLayer, layer.EmbeddingLayer,
+ * layer.LRLayer, layer.AddLayer, model.DNN / WideDeepNN / FullConnectedNN, train.Trainer.
+ * Every object keeps its parameters in the GPU-resident store (store.KVStore's role); the
+ * Java classes of integration/java/ forward to these through the C ABI.
+ */
+#pragma once
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "dense.cuh"
+#include "gemm.cuh"
+#include "table.cuh"
+
+namespace psb {
+
+/* layer/FcLayer.java — weights "fc<i>.weights" (out x in), bias "fc<i>.bias" */
+struct FcLayer {
+  std::string name;
+  int in = 0, out = 0, act = PS_ACT_NONE;
+  int ldw = 0, ldwt = 0;
+  float *W = nullptr, *Wt = nullptr, *bias = nullptr;
+  float *sW1 = nullptr, *sW2 = nullptr, *sb1 = nullptr, *sb2 = nullptr;
+  float* G = nullptr;            /* wgrad partial slabs [nsplit][out][ldw] */
+  int nsplit = 1;
+  ps_updater_spec updW, updB;
+  void create(Ctx* ctx, const std::string& nm, int in_, int out_, int act_, const ps_updater_spec& u, int nsplit_);
+  void destroy();
+};
+
+struct HostBatch {               /* host pointers of one submitted step (CTR.parseFeature's map, CTR.java:47-68) */
+  const int64_t* E = nullptr; const float* X = nullptr; const int64_t* W = nullptr; const float* Y = nullptr; int N = 0;
+};
+
+struct Model {
+  Ctx* ctx = nullptr;
+  int kind = 0, F = 0, D = 0, Xn = 0, Bmax = 0, L = 0;
+  bool has_emb = false, has_wide = false;
+  EmbTable emb;                  /* layer.EmbeddingLayer "embedding" (EmbeddingLayer.java) */
+  WideTable wide;                /* layer.LRLayer "wide" weights (LRLayer.java) */
+  float* wide_bias = nullptr;    /* {w, s1, s2} of "wide.bias" */
+  ps_updater_spec upd_default, upd_wide;
+  std::vector<FcLayer> fcs;
+  std::vector<float*> act;       /* act[0] = concat output, act[l+1] = fc<l>.A ; [Bmax][ld[l]] */
+  std::vector<float*> delta;     /* delta[l] = fc<l>.delta (input side, shape of act[l]); delta[L] = top delta */
+  std::vector<int> width, ld;
+  float *wide_z = nullptr, *P = nullptr;
+  StepStatus* st_dev = nullptr;
+  /* two staging sets so the H2D of step i+1 overlaps the kernels of step i */
+  struct Stage {
+    int64_t *E = nullptr, *W = nullptr; float *X = nullptr, *Y = nullptr;
+    StepStatus* st_host = nullptr;       /* mapped pinned */
+    cudaEvent_t h2d_done = nullptr, step_done = nullptr;
+    int N = 0; bool busy = false;
+  } stage[2];
+  int next_stage = 0, oldest_stage = 0, in_flight = 0;
+  uint32_t seq = 0;
+  int last_N = 0; bool last_train = false;
+  StepStatus last_status{};
+  /* per-phase device timing */
+  bool profile = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<std::string> phase_names;
+  std::vector<float> phase_ms;
+
+  void create(Ctx* c, int kind_, int F_, int D_, int Xn_, const int32_t* fc_dims, int n_fc, int64_t emb_capacity,
+              const ps_updater_spec* emb_updater, int max_batch);
+  void destroy();
+  /* the whole step on device-resident inputs, enqueued on ctx->stream; status lands in st_dev */
+  void step_device(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, bool train);
+  void submit(const HostBatch& b);
+  float collect();
+  float read_loss();
+  void predict(const HostBatch& b, float* out);
+  int get(const std::string& key, std::vector<float>& out);
+  void put(const std::string& key, const float* in, int n);
+  int get_state(const std::string& key, int which, std::vector<float>& out);
+  int tap(const std::string& layer, int what, std::vector<float>& out);
+  int64_t num_keys();
+  void mark(const char* phase);
+  void finish_profile();
+};
+
+/* "emF3.15757.0" → (kind 0, field 3, id 15757); "wide.weights.77.0" → (kind 1, 0, 77); else kind 2 (dense name) */
+int parse_key(const std::string& key, int* field, int64_t* id);
+
+}  // namespace psb

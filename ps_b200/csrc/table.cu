@@ -1,0 +1,540 @@
+/*
+ * table.cu — kernels of the GPU-resident embedding / wide tables (sm_100a).
+ *
+ * Path restated (reference, /root/reference/src/main/java/):
+ *   probe   = EmbeddingField.checkExists + KVStore.get(key, init)   layer/EmbeddingField.java:49-54, store/KVStore.java:136-159,168-190
+ *   gather  = EmbeddingField.forward + EmbeddingLayer.forward       layer/EmbeddingField.java:66-78, layer/EmbeddingLayer.java:25-48
+ *   scatter = EmbeddingField.backward (x2) + KVStore.sum + KVStore.update + Updater.update
+ *                                                                   layer/EmbeddingField.java:86-104, store/KVStore.java:192-200,240-268
+ *   wide    = LRLayer.forward / backward                            layer/LRLayer.java:62-120
+ *
+ * All of it is HBM/L2-bound integer and copy work: no tensor cores, 128-bit accesses,
+ * one thread group (Dp/4 lanes) per looked-up row.
+ */
+#include <vector>
+
+#include "table.cuh"
+
+namespace psb {
+
+static constexpr int kProbeLimit = 1 << 16;
+
+/* ------------------------------------------------------------------ find / find-or-insert */
+__device__ __forceinline__ int emb_find(const EmbSlot* slots, uint32_t C, unsigned long long key) {
+  uint32_t slot = ps_bucket_of(key, C);
+  const int limit = C < (uint32_t)kProbeLimit ? (int)C : kProbeLimit;
+  for (int p = 0; p < limit; ++p) {
+    const unsigned long long k = *reinterpret_cast<const volatile unsigned long long*>(&slots[slot].key);
+    if (k == key) return (int)slot;
+    if (k == PS_KEY_EMPTY) return -1;
+    slot = slot + 1 == C ? 0 : slot + 1;
+  }
+  return -1;
+}
+
+/* returns the slot, or -1 when the table is full; *inserted tells the caller to initialise the row */
+__device__ __forceinline__ int emb_find_or_insert(EmbSlot* slots, uint32_t C, unsigned long long key, bool* inserted) {
+  uint32_t slot = ps_bucket_of(key, C);
+  const int limit = C < (uint32_t)kProbeLimit ? (int)C : kProbeLimit;
+  *inserted = false;
+  for (int p = 0; p < limit; ++p) {
+    const unsigned long long k = *reinterpret_cast<const volatile unsigned long long*>(&slots[slot].key);
+    if (k == key) return (int)slot;
+    if (k == PS_KEY_EMPTY) {
+      const unsigned long long old = atomicCAS(&slots[slot].key, (unsigned long long)PS_KEY_EMPTY, key);
+      if (old == PS_KEY_EMPTY) { *inserted = true; return (int)slot; }
+      if (old == key) return (int)slot;
+    }
+    slot = slot + 1 == C ? 0 : slot + 1;
+  }
+  return -1;
+}
+
+/* One thread per lookup l = n*F + j.  Row creation follows KVStore.create (KVStore.java:168-190):
+ * the creating thread draws the row from the deterministic initialiser of ps_spec.h; optimiser
+ * state stays at the zero the arena was allocated with (AdamUpdater.initMandV, :76-84).        */
+template <class IdT>
+__global__ void __launch_bounds__(256) emb_probe_kernel(EmbSlot* __restrict__ slots, uint32_t C, float* __restrict__ w, int Dp, int D,
+                                                        const IdT* __restrict__ ids, int L, int F, uint64_t seed, float maxv,
+                                                        int32_t* __restrict__ lk_slot, uint32_t* __restrict__ uniq_slot,
+                                                        uint32_t* __restrict__ counters) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= L) return;
+  const int field = l % F;
+  const unsigned long long key = ps_pack_key((uint32_t)field, (uint64_t)(int64_t)ids[l]);
+  bool inserted;
+  const int slot = emb_find_or_insert(slots, C, key, &inserted);
+  lk_slot[l] = slot;
+  if (slot < 0) { counters[1] = 1u; return; }
+  if (inserted) {
+    float* row = w + (size_t)slot * Dp;
+    for (int d = 0; d < D; ++d) row[d] = ps_init_value(seed, key, (uint32_t)d, maxv);
+    atomicAdd(reinterpret_cast<unsigned long long*>(counters + 2), 1ull);
+  }
+  const uint32_t old = atomicAdd(&slots[slot].cnt, 1u);
+  if (old == 0u) {                      /* first occurrence in this batch: number the unique key */
+    const uint32_t u = atomicAdd(&counters[0], 1u);
+    slots[slot].uidx = u;
+    uniq_slot[u] = (uint32_t)slot;
+  }
+}
+
+/* TPL lanes per lookup, each moving one 16 B chunk of the row: consecutive lanes write
+ * consecutive addresses of the (F*D) x N output (fields of one sample are adjacent), so the
+ * stores of a warp coalesce into full 128 B lines; ReLU (EmbeddingField.java:75) is fused.     */
+template <int TPL, bool ALIGNED>
+__global__ void __launch_bounds__(256) emb_gather_kernel(const float* __restrict__ w, int Dp, int D, const int32_t* __restrict__ lk_slot,
+                                                         int L, int F, float* __restrict__ out, int ldo) {
+  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int l = (int)(g / TPL), part = (int)(g % TPL);
+  if (l >= L || part * 4 >= D) return;
+  const int slot = lk_slot[l];
+  if (slot < 0) return;
+  const int n = l / F, j = l - n * F;
+  float4 v = __ldg(reinterpret_cast<const float4*>(w + (size_t)slot * Dp + part * 4));
+  v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+  float* o = out + (size_t)n * ldo + j * D + part * 4;
+  if (ALIGNED) {
+    st_f4(o, v);
+  } else {
+    const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (part * 4 + i < D) o[i] = e[i];
+  }
+}
+
+__device__ __forceinline__ float4 shfl_f4(float4 v, int src) {
+  float4 r;
+  r.x = __shfl_sync(0xffffffffu, v.x, src); r.y = __shfl_sync(0xffffffffu, v.y, src);
+  r.z = __shfl_sync(0xffffffffu, v.z, src); r.w = __shfl_sync(0xffffffffu, v.w, src);
+  return r;
+}
+
+/* Effective gradient the reference ends up applying for a key with n occurrences and S = sum of
+ * its per-occurrence gradients.  calls == 2 (what DNN/WideDeepNN do): pass 1
+ * stores S/n by reference in KVStore.sum, pass 2 adds the n gradients again, divides by 2n, the
+ * aliased sum doubles it and KVStore.update halves it: ((S/n) + S) / (2n).  calls == 1: S/n.  */
+__device__ __forceinline__ float emb_geff(float S, uint32_t n, int calls) {
+  const float q = __fdiv_rn(S, (float)n);
+  if (calls == 1) return q;
+  return __fdiv_rn(__fadd_rn(q, S), (float)(2u * n));
+}
+
+/* Fused sparse backward: one launch does
+ *   (1) g_k = delta[:,k] * (A[:,k] > 0)                          EmbeddingField.java:91-93
+ *   (2) warp-aggregated scatter-add of g_k into the batch-unique accumulator (lanes of a warp work
+ *       on the SAME field for consecutive samples, so hot keys collapse before the L2 reduction)
+ *   (3) the group that delivers a key's last occurrence (ticket == cnt) reads S back from L2,
+ *       forms g_eff, runs the Adam / Ftrl / SGD step on w, s1, s2 in place, and resets the
+ *       per-batch state (acc, ticket, cnt) — KVStore.sum + update + clear in one pass.          */
+template <int TPL, bool ALIGNED>
+__global__ void __launch_bounds__(256) emb_scatter_update_kernel(EmbSlot* __restrict__ slots, float* __restrict__ w, float* __restrict__ s1,
+                                                                 float* __restrict__ s2, int Dp, int D, const int32_t* __restrict__ lk_slot,
+                                                                 int N, int F, const float* __restrict__ delta, int ldd,
+                                                                 const float* __restrict__ act, int lda, float* __restrict__ acc,
+                                                                 uint32_t* __restrict__ arrived, UpdaterDev upd, int calls,
+                                                                 const int* __restrict__ skip_flag) {
+  const bool skip = skip_flag != nullptr && *skip_flag != 0;
+  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long L = (long)N * F;
+  const long lk = g / TPL;
+  const int part = (int)(g % TPL);
+  const int lane = threadIdx.x & 31;
+  const int my_group = lane / TPL;
+  bool valid = lk < L;
+  int slot = -1, n = 0, j = 0;
+  if (valid) {
+    j = (int)(lk / N); n = (int)(lk - (long)j * N);
+    slot = lk_slot[(long)n * F + j];
+    valid = slot >= 0;
+  }
+  uint32_t cnt = 0, uidx = 0;
+  if (valid) {
+    const uint4 m = *reinterpret_cast<const uint4*>(&slots[slot]);
+    cnt = m.z; uidx = m.w;
+  }
+  if (skip) {                                   /* DNN.java:58-63 early exit: nothing was pushed, just forget the batch */
+    if (valid && part == 0) slots[slot].cnt = 0u;
+    return;
+  }
+  const bool lane_on = valid && part * 4 < D;
+  float4 gk = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (lane_on) {
+    const size_t od = (size_t)n * ldd + j * D + part * 4, oa = (size_t)n * lda + j * D + part * 4;
+    float dv[4] = {0.f, 0.f, 0.f, 0.f}, av[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ALIGNED) {
+      const float4 d4 = ld_f4(delta + od), a4 = ld_f4(act + oa);
+      dv[0] = d4.x; dv[1] = d4.y; dv[2] = d4.z; dv[3] = d4.w;
+      av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) if (part * 4 + i < D) { dv[i] = delta[od + i]; av[i] = act[oa + i]; }
+    }
+    /* Relu.backward: dy *= (y > 0 ? 1 : 0)  (activations/Relu.java:14-19) */
+    gk.x = __fmul_rn(dv[0], av[0] > 0.f ? 1.f : 0.f); gk.y = __fmul_rn(dv[1], av[1] > 0.f ? 1.f : 0.f);
+    gk.z = __fmul_rn(dv[2], av[2] > 0.f ? 1.f : 0.f); gk.w = __fmul_rn(dv[3], av[3] > 0.f ? 1.f : 0.f);
+  }
+  /* ---- warp aggregation of duplicate keys ---- */
+  const unsigned peers = __match_any_sync(0xffffffffu, valid ? slot : (-1 - lane));
+  const int ngroups = __popc(peers) / TPL;      /* groups of this warp holding the same key (>= 1 when valid) */
+  const bool leader = (( __ffs(peers) - 1) / TPL) == my_group;
+  if (__any_sync(0xffffffffu, valid && ngroups > 1)) {
+    float4 sum = gk;
+#pragma unroll
+    for (int og = 0; og < 32 / TPL; ++og) {
+      const int src = og * TPL + part;
+      const float4 o = shfl_f4(gk, src);
+      if (og != my_group && ((peers >> src) & 1u)) { sum.x += o.x; sum.y += o.y; sum.z += o.z; sum.w += o.w; }
+    }
+    gk = sum;
+  }
+  if (lane_on && leader) red_add_f4(acc + (size_t)uidx * Dp + part * 4, gk);
+  __threadfence();
+  __syncwarp();
+  uint32_t ticket = 0;
+  if (valid && leader && part == 0) ticket = atomicAdd(&arrived[uidx], (uint32_t)ngroups);
+  ticket = __shfl_sync(0xffffffffu, ticket, my_group * TPL);
+  const bool last = valid && leader && (ticket + (uint32_t)ngroups == cnt);
+  if (!last) return;
+  __threadfence();
+  bool do_upd = true;
+  if (upd.kind == PS_UPD_FTRL) {                /* FtrlUpdater.java:52: `if (dw.get(0) == 0) return w` */
+    const float S0 = __ldcg(acc + (size_t)uidx * Dp);
+    do_upd = emb_geff(S0, cnt, calls) != 0.0f;
+  }
+  if (lane_on) {
+    float* ap = acc + (size_t)uidx * Dp + part * 4;
+    const float4 S = __ldcg(reinterpret_cast<const float4*>(ap));
+    if (do_upd) {
+      const size_t o = (size_t)slot * Dp + part * 4;
+      float4 wv = ld_f4(w + o), m1 = make_float4(0.f, 0.f, 0.f, 0.f), m2 = m1;
+      if (upd.kind != PS_UPD_SIMPLE) { m1 = ld_f4(s1 + o); m2 = ld_f4(s2 + o); }
+      apply_elem(upd, wv.x, m1.x, m2.x, emb_geff(S.x, cnt, calls));
+      apply_elem(upd, wv.y, m1.y, m2.y, emb_geff(S.y, cnt, calls));
+      apply_elem(upd, wv.z, m1.z, m2.z, emb_geff(S.z, cnt, calls));
+      apply_elem(upd, wv.w, m1.w, m2.w, emb_geff(S.w, cnt, calls));
+      st_f4(w + o, wv);
+      if (upd.kind != PS_UPD_SIMPLE) { st_f4(s1 + o, m1); st_f4(s2 + o, m2); }
+    }
+    st_f4(ap, make_float4(0.f, 0.f, 0.f, 0.f));
+  }
+  if (part == 0) { arrived[uidx] = 0u; slots[slot].cnt = 0u; }
+}
+
+__global__ void emb_clear_batch_kernel(EmbSlot* __restrict__ slots, const uint32_t* __restrict__ uniq_slot, const uint32_t* __restrict__ counters) {
+  const uint32_t nu = counters[0];
+  for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < nu; u += gridDim.x * blockDim.x) slots[uniq_slot[u]].cnt = 0u;
+}
+
+/* host-driven row access: thread per key */
+__global__ void emb_get_rows_kernel(const EmbSlot* __restrict__ slots, uint32_t C, const float* __restrict__ w, const float* __restrict__ s1,
+                                    const float* __restrict__ s2, int Dp, int D, const int32_t* __restrict__ fields,
+                                    const int64_t* __restrict__ ids, int n, float* __restrict__ wo, float* __restrict__ s1o,
+                                    float* __restrict__ s2o, int32_t* __restrict__ found) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int slot = emb_find(slots, C, ps_pack_key((uint32_t)fields[i], (uint64_t)ids[i]));
+  found[i] = slot >= 0;
+  for (int d = 0; d < D; ++d) {
+    const size_t o = (size_t)(slot < 0 ? 0 : slot) * Dp + d;
+    wo[(size_t)i * D + d] = slot < 0 ? 0.f : w[o];
+    if (s1o) s1o[(size_t)i * D + d] = slot < 0 ? 0.f : s1[o];
+    if (s2o) s2o[(size_t)i * D + d] = slot < 0 ? 0.f : s2[o];
+  }
+}
+
+/* KVStore.put (replace) / PServer.upsertList with replace=false (net/PServer.java:144-162):
+ * insert-if-absent; the caller's buffer receives the winning row.                              */
+__global__ void emb_put_rows_kernel(EmbSlot* __restrict__ slots, uint32_t C, float* __restrict__ w, int Dp, int D,
+                                    const int32_t* __restrict__ fields, const int64_t* __restrict__ ids, int n, float* __restrict__ wio,
+                                    int replace, uint32_t* __restrict__ counters) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool inserted;
+  const int slot = emb_find_or_insert(slots, C, ps_pack_key((uint32_t)fields[i], (uint64_t)ids[i]), &inserted);
+  if (slot < 0) { counters[1] = 1u; return; }
+  if (inserted) atomicAdd(reinterpret_cast<unsigned long long*>(counters + 2), 1ull);
+  float* row = w + (size_t)slot * Dp;
+  if (inserted || replace) { for (int d = 0; d < D; ++d) row[d] = wio[(size_t)i * D + d]; }
+  else { for (int d = 0; d < D; ++d) wio[(size_t)i * D + d] = row[d]; }
+}
+
+/* ------------------------------------------------------------------ EmbTable host side */
+static int pow2_ge(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+void EmbTable::create(Ctx* c, int F_, int D_, int64_t capacity, const ps_updater_spec& u, int64_t max_lookups) {
+  PS_REQUIRE(F_ > 0 && D_ > 0 && D_ <= 128, PS_ERR_ARG, "embedding: need F > 0 and 0 < D <= 128");
+  PS_REQUIRE(capacity > 0 && capacity < (1ll << 31), PS_ERR_ARG, "embedding: capacity must be in (0, 2^31)");
+  ctx = c; F = F_; D = D_; Dp = round_up(D_, 4); tpl = pow2_ge(Dp / 4); C = capacity;
+  maxv = (float)(4 * (std::sqrt(6.0) / std::sqrt((double)(1 + D_))));   /* EmbeddingField.java:40 with in=1,out=D (EmbeddingLayer.java:52) */
+  upd = make_updater_dev(u);
+  slots = dmalloc_zero<EmbSlot>((size_t)C, ctx->stream);
+  w = dmalloc_zero<float>((size_t)C * Dp, ctx->stream);
+  s1 = dmalloc_zero<float>((size_t)C * Dp, ctx->stream);
+  s2 = dmalloc_zero<float>((size_t)C * Dp, ctx->stream);
+  counters = dmalloc_zero<uint32_t>(4, ctx->stream);
+  reserve(max_lookups > 0 ? max_lookups : 1);
+}
+
+void EmbTable::reserve(int64_t L) {
+  if (L <= Lcap) return;
+  PS_CUDA(cudaStreamSynchronize(ctx->stream));
+  dfree(lk_slot); dfree(uniq_slot); dfree(acc); dfree(arrived);
+  Lcap = L;
+  lk_slot = dmalloc<int32_t>((size_t)L);
+  uniq_slot = dmalloc<uint32_t>((size_t)L);
+  acc = dmalloc_zero<float>((size_t)L * Dp, ctx->stream);
+  arrived = dmalloc_zero<uint32_t>((size_t)L, ctx->stream);
+}
+
+void EmbTable::destroy() {
+  dfree(slots); dfree(w); dfree(s1); dfree(s2); dfree(counters);
+  dfree(lk_slot); dfree(uniq_slot); dfree(acc); dfree(arrived);
+  slots = nullptr; w = s1 = s2 = nullptr;
+}
+
+void EmbTable::probe(const int64_t* ids_i64, const float* ids_f32, int N) {
+  const int64_t L = (int64_t)N * F;
+  PS_REQUIRE(L <= Lcap, PS_ERR_ARG, "embedding: batch larger than the reserved workspace");
+  last_L = L;
+  PS_CUDA(cudaMemsetAsync(counters, 0, sizeof(uint32_t), ctx->stream));
+  const int grid = ceil_div(L, 256);
+  if (ids_i64)
+    emb_probe_kernel<int64_t><<<grid, 256, 0, ctx->stream>>>(slots, (uint32_t)C, w, Dp, D, ids_i64, (int)L, F, ctx->seed, maxv, lk_slot, uniq_slot, counters);
+  else
+    emb_probe_kernel<float><<<grid, 256, 0, ctx->stream>>>(slots, (uint32_t)C, w, Dp, D, ids_f32, (int)L, F, ctx->seed, maxv, lk_slot, uniq_slot, counters);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+}
+
+template <int TPL>
+static void launch_gather(EmbTable& t, float* out, int ldo, int N) {
+  const long L = (long)N * t.F;
+  const bool aligned = (t.D % 4 == 0) && (ldo % 4 == 0) && ((uintptr_t)out % 16 == 0);
+  const int grid = ceil_div(L * TPL, 256);
+  if (aligned) emb_gather_kernel<TPL, true><<<grid, 256, 0, t.ctx->stream>>>(t.w, t.Dp, t.D, t.lk_slot, (int)L, t.F, out, ldo);
+  else emb_gather_kernel<TPL, false><<<grid, 256, 0, t.ctx->stream>>>(t.w, t.Dp, t.D, t.lk_slot, (int)L, t.F, out, ldo);
+}
+
+void EmbTable::gather(float* out, int ldo, int N) {
+  PS_REQUIRE((int64_t)N * F == last_L, PS_ERR_STATE, "embedding: gather without a matching probe");
+  switch (tpl) {
+    case 1: launch_gather<1>(*this, out, ldo, N); break;
+    case 2: launch_gather<2>(*this, out, ldo, N); break;
+    case 4: launch_gather<4>(*this, out, ldo, N); break;
+    case 8: launch_gather<8>(*this, out, ldo, N); break;
+    case 16: launch_gather<16>(*this, out, ldo, N); break;
+    default: launch_gather<32>(*this, out, ldo, N); break;
+  }
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+}
+
+template <int TPL>
+static void launch_scatter(EmbTable& t, const float* delta, int ldd, const float* act, int lda, int N, int calls, const int* skip) {
+  const long L = (long)N * t.F;
+  const bool aligned = (t.D % 4 == 0) && (ldd % 4 == 0) && (lda % 4 == 0) && ((uintptr_t)delta % 16 == 0) && ((uintptr_t)act % 16 == 0);
+  const int grid = ceil_div(L * TPL, 256);
+  if (aligned)
+    emb_scatter_update_kernel<TPL, true><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.w, t.s1, t.s2, t.Dp, t.D, t.lk_slot, N, t.F, delta, ldd, act, lda, t.acc, t.arrived, t.upd, calls, skip);
+  else
+    emb_scatter_update_kernel<TPL, false><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.w, t.s1, t.s2, t.Dp, t.D, t.lk_slot, N, t.F, delta, ldd, act, lda, t.acc, t.arrived, t.upd, calls, skip);
+}
+
+void EmbTable::scatter_update(const float* delta, int ldd, const float* act, int lda, int N, int calls, const int* skip_flag) {
+  PS_REQUIRE((int64_t)N * F == last_L, PS_ERR_STATE, "embedding: backward without a matching forward");
+  PS_REQUIRE(calls == 1 || calls == 2, PS_ERR_ARG, "embedding: backward calls must be 1 or 2");
+  switch (tpl) {
+    case 1: launch_scatter<1>(*this, delta, ldd, act, lda, N, calls, skip_flag); break;
+    case 2: launch_scatter<2>(*this, delta, ldd, act, lda, N, calls, skip_flag); break;
+    case 4: launch_scatter<4>(*this, delta, ldd, act, lda, N, calls, skip_flag); break;
+    case 8: launch_scatter<8>(*this, delta, ldd, act, lda, N, calls, skip_flag); break;
+    case 16: launch_scatter<16>(*this, delta, ldd, act, lda, N, calls, skip_flag); break;
+    default: launch_scatter<32>(*this, delta, ldd, act, lda, N, calls, skip_flag); break;
+  }
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+  last_L = 0;
+}
+
+void EmbTable::clear_batch() {
+  emb_clear_batch_kernel<<<ctx->num_sms, 256, 0, ctx->stream>>>(slots, uniq_slot, counters);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+  last_L = 0;
+}
+
+void EmbTable::check_errors() {
+  uint32_t h[4];
+  PS_CUDA(cudaMemcpyAsync(h, counters, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+  PS_CUDA(cudaStreamSynchronize(ctx->stream));
+  PS_REQUIRE(h[1] == 0, PS_ERR_CAPACITY, "embedding table is full: raise capacity");
+}
+
+int64_t EmbTable::size() {
+  uint32_t h[4];
+  PS_CUDA(cudaMemcpyAsync(h, counters, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+  PS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return (int64_t)(((uint64_t)h[3] << 32) | h[2]);
+}
+
+void EmbTable::get_rows(const int32_t* fields, const int64_t* ids, int n, float* w_out, float* s1_out, float* s2_out, int32_t* found) {
+  if (n <= 0) return;
+  cudaStream_t st = ctx->stream;
+  int32_t* d_f = dmalloc<int32_t>(n); int64_t* d_i = dmalloc<int64_t>(n); int32_t* d_found = dmalloc<int32_t>(n);
+  float* d_w = dmalloc<float>((size_t)n * D);
+  float* d_s1 = s1_out ? dmalloc<float>((size_t)n * D) : nullptr;
+  float* d_s2 = s2_out ? dmalloc<float>((size_t)n * D) : nullptr;
+  PS_CUDA(cudaMemcpyAsync(d_f, fields, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+  PS_CUDA(cudaMemcpyAsync(d_i, ids, sizeof(int64_t) * n, cudaMemcpyHostToDevice, st));
+  emb_get_rows_kernel<<<ceil_div(n, 128), 128, 0, st>>>(slots, (uint32_t)C, w, s1, s2, Dp, D, d_f, d_i, n, d_w, d_s1, d_s2, d_found);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+  PS_CUDA(cudaMemcpyAsync(w_out, d_w, sizeof(float) * n * D, cudaMemcpyDeviceToHost, st));
+  if (s1_out) PS_CUDA(cudaMemcpyAsync(s1_out, d_s1, sizeof(float) * n * D, cudaMemcpyDeviceToHost, st));
+  if (s2_out) PS_CUDA(cudaMemcpyAsync(s2_out, d_s2, sizeof(float) * n * D, cudaMemcpyDeviceToHost, st));
+  PS_CUDA(cudaMemcpyAsync(found, d_found, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+  PS_CUDA(cudaStreamSynchronize(st));
+  dfree(d_f); dfree(d_i); dfree(d_found); dfree(d_w); dfree(d_s1); dfree(d_s2);
+}
+
+void EmbTable::put_rows(const int32_t* fields, const int64_t* ids, int n, float* w_io, int replace) {
+  if (n <= 0) return;
+  cudaStream_t st = ctx->stream;
+  int32_t* d_f = dmalloc<int32_t>(n); int64_t* d_i = dmalloc<int64_t>(n);
+  float* d_w = dmalloc<float>((size_t)n * D);
+  PS_CUDA(cudaMemcpyAsync(d_f, fields, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+  PS_CUDA(cudaMemcpyAsync(d_i, ids, sizeof(int64_t) * n, cudaMemcpyHostToDevice, st));
+  PS_CUDA(cudaMemcpyAsync(d_w, w_io, sizeof(float) * n * D, cudaMemcpyHostToDevice, st));
+  emb_put_rows_kernel<<<ceil_div(n, 128), 128, 0, st>>>(slots, (uint32_t)C, w, Dp, D, d_f, d_i, n, d_w, replace, counters);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+  PS_CUDA(cudaMemcpyAsync(w_io, d_w, sizeof(float) * n * D, cudaMemcpyDeviceToHost, st));
+  PS_CUDA(cudaStreamSynchronize(st));
+  dfree(d_f); dfree(d_i); dfree(d_w);
+  check_errors();
+}
+
+/* ------------------------------------------------------------------ WideTable */
+__device__ __forceinline__ int wide_find_or_insert(WideSlot* slots, uint32_t C, unsigned long long key, bool insert, bool* inserted) {
+  uint32_t slot = ps_bucket_of(key, C);
+  const int limit = C < (uint32_t)kProbeLimit ? (int)C : kProbeLimit;
+  *inserted = false;
+  for (int p = 0; p < limit; ++p) {
+    const unsigned long long k = *reinterpret_cast<const volatile unsigned long long*>(&slots[slot].key);
+    if (k == key) return (int)slot;
+    if (k == PS_KEY_EMPTY) {
+      if (!insert) return -1;
+      const unsigned long long old = atomicCAS(&slots[slot].key, (unsigned long long)PS_KEY_EMPTY, key);
+      if (old == PS_KEY_EMPTY) { *inserted = true; return (int)slot; }
+      if (old == key) return (int)slot;
+    }
+    slot = slot + 1 == C ? 0 : slot + 1;
+  }
+  return -1;
+}
+
+/* One warp per sample: lane j resolves "wide.weights.<W[j,n]>" (created as zeros(1) on first
+ * touch, LRLayer.java:40-44,78), lane 0 then adds the F weights in j order exactly like the
+ * reference's `sumW += wi.get(0)` loop (:76-81) and adds the bias (:84).                      */
+__global__ void __launch_bounds__(256) wide_forward_kernel(WideSlot* __restrict__ slots, uint32_t C, const int64_t* __restrict__ ids, int N, int F,
+                                                           const float* __restrict__ bias, float* __restrict__ z, uint32_t* __restrict__ counters) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  float sum = 0.0f;
+  for (int j0 = 0; j0 < F; j0 += 32) {
+    const int j = j0 + lane;
+    float v = 0.0f;
+    if (j < F) {
+      bool inserted;
+      const int slot = wide_find_or_insert(slots, C, ps_pack_key(0u, (uint64_t)ids[(size_t)warp * F + j]), true, &inserted);
+      if (slot < 0) counters[0] = 1u;
+      else {
+        if (inserted) atomicAdd(reinterpret_cast<unsigned long long*>(counters + 2), 1ull);
+        v = *reinterpret_cast<const volatile float*>(&slots[slot].w);
+      }
+    }
+    const int cnt = min(32, F - j0);
+    for (int k = 0; k < cnt; ++k) sum = __fadd_rn(sum, __shfl_sync(0xffffffffu, v, k));
+  }
+  if (lane == 0) z[warp] = __fadd_rn(sum, bias[0]);
+}
+
+__global__ void __launch_bounds__(256) wide_update_all_kernel(WideSlot* __restrict__ slots, uint32_t C, UpdaterDev upd, const float* __restrict__ gbar,
+                                                              const int* __restrict__ skip_flag) {
+  if (skip_flag != nullptr && *skip_flag != 0) return;
+  const float g = *gbar;
+  if (upd.kind == PS_UPD_FTRL && g == 0.0f) return;   /* FtrlUpdater.java:52 */
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < C; s += gridDim.x * blockDim.x) {
+    WideSlot r = slots[s];
+    if (r.key == PS_KEY_EMPTY) continue;
+    apply_elem(upd, r.w, r.s1, r.s2, g);
+    slots[s].w = r.w; slots[s].s1 = r.s1; slots[s].s2 = r.s2;
+  }
+}
+
+__global__ void wide_get_kernel(WideSlot* slots, uint32_t C, int64_t id, float* out) {
+  bool ins;
+  const int slot = wide_find_or_insert(slots, C, ps_pack_key(0u, (uint64_t)id), false, &ins);
+  out[0] = slot >= 0 ? 1.f : 0.f;
+  if (slot >= 0) { out[1] = slots[slot].w; out[2] = slots[slot].s1; out[3] = slots[slot].s2; }
+}
+__global__ void wide_put_kernel(WideSlot* slots, uint32_t C, int64_t id, float wv, uint32_t* counters) {
+  bool ins;
+  const int slot = wide_find_or_insert(slots, C, ps_pack_key(0u, (uint64_t)id), true, &ins);
+  if (slot < 0) { counters[0] = 1u; return; }
+  if (ins) atomicAdd(reinterpret_cast<unsigned long long*>(counters + 2), 1ull);
+  slots[slot].w = wv;
+}
+
+void WideTable::create(Ctx* c, int64_t capacity, const ps_updater_spec& u) {
+  PS_REQUIRE(capacity > 0 && capacity < (1ll << 31), PS_ERR_ARG, "wide: capacity must be in (0, 2^31)");
+  ctx = c; C = capacity; upd = make_updater_dev(u);
+  slots = dmalloc_zero<WideSlot>((size_t)C, ctx->stream);
+  counters = dmalloc_zero<uint32_t>(4, ctx->stream);
+}
+void WideTable::destroy() { dfree(slots); dfree(counters); slots = nullptr; counters = nullptr; }
+
+void WideTable::forward(const int64_t* ids, int N, int F, const float* bias, float* z) {
+  wide_forward_kernel<<<ceil_div((long)N * 32, 256), 256, 0, ctx->stream>>>(slots, (uint32_t)C, ids, N, F, bias, z, counters);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+}
+void WideTable::update_all(const float* gbar, const int* skip_flag) {
+  const int grid = std::min<long>(ceil_div(C, 256), (long)ctx->num_sms * 8);
+  wide_update_all_kernel<<<grid, 256, 0, ctx->stream>>>(slots, (uint32_t)C, upd, gbar, skip_flag);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+}
+int64_t WideTable::size() {
+  uint32_t h[4];
+  PS_CUDA(cudaMemcpyAsync(h, counters, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+  PS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return (int64_t)(((uint64_t)h[3] << 32) | h[2]);
+}
+void WideTable::check_errors() {
+  uint32_t h[4];
+  PS_CUDA(cudaMemcpyAsync(h, counters, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+  PS_CUDA(cudaStreamSynchronize(ctx->stream));
+  PS_REQUIRE(h[0] == 0, PS_ERR_CAPACITY, "wide table is full: raise capacity");
+}
+int WideTable::get(int64_t id, float* wv, float* s1v, float* s2v) {
+  float* d = dmalloc_zero<float>(4, ctx->stream);
+  wide_get_kernel<<<1, 1, 0, ctx->stream>>>(slots, (uint32_t)C, id, d);
+  ctx->launches++;
+  float h[4];
+  PS_CUDA(cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+  PS_CUDA(cudaStreamSynchronize(ctx->stream));
+  dfree(d);
+  if (h[0] == 0.f) return 0;
+  if (wv) *wv = h[1]; if (s1v) *s1v = h[2]; if (s2v) *s2v = h[3];
+  return 1;
+}
+void WideTable::put(int64_t id, float wv) {
+  wide_put_kernel<<<1, 1, 0, ctx->stream>>>(slots, (uint32_t)C, id, wv, counters);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+}
+
+}  // namespace psb

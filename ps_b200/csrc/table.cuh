@@ -1,0 +1,95 @@
+/*
+ * table.cuh — the GPU-resident parameter tables behind store.KVStore for sparse keys.
+ *
+ * EmbTable: one open-addressing hash table for all F embedding fields of a layer
+ * (keys "emF<j>.<id>" of layer/EmbeddingField.java:70, packed by ps_pack_key).  HBM layout:
+ *
+ *   slots[C]   16 B records {key u64, cnt u32, uidx u32}: two per 32 B sector, so the probe
+ *              that finds the key also brings the per-batch occurrence count and the
+ *              per-batch unique index into L2 at no extra DRAM cost
+ *   w[C][Dp], s1[C][Dp], s2[C][Dp]   row = slot index; SoA across {weight, Adam M | Ftrl Z,
+ *              Adam V | Ftrl N} so the forward gather touches only w.  Dp = D rounded to 4
+ *              floats: every row is 16 B aligned for 128-bit loads
+ *   per-batch workspace (L = N*F lookups): lk_slot[L]; uniq_slot[U]; acc[U][Dp] gradient
+ *              accumulators and arrived[U] tickets, indexed by the batch-unique index — a few
+ *              MB that stay L2-resident, so the scatter-add never round-trips HBM
+ *
+ * WideTable: layer/LRLayer.java's 1x1 weights "wide.weights.<id>": 32 B records
+ * {key, w, s1, s2} — one sector holds everything a probe, the forward sum and the update need.
+ */
+#pragma once
+#include "common.cuh"
+#include "updaters.cuh"
+
+namespace psb {
+
+struct __align__(16) EmbSlot {
+  unsigned long long key;
+  uint32_t cnt;    /* occurrences of this key in the current batch (EmbeddingField.java:96 wgN) */
+  uint32_t uidx;   /* index of this key among the batch's unique keys */
+};
+
+struct __align__(32) WideSlot {
+  unsigned long long key;
+  float w, s1, s2;
+  uint32_t pad0;
+  unsigned long long pad1;
+};
+
+struct EmbTable {
+  Ctx* ctx = nullptr;
+  int F = 0, D = 0, Dp = 0, tpl = 1;   /* tpl: lanes cooperating on one lookup (power of two >= Dp/4) */
+  int64_t C = 0;
+  float maxv = 0.f;                    /* Xavier bound of EmbeddingField.java:40 */
+  UpdaterDev upd;
+  EmbSlot* slots = nullptr;
+  float *w = nullptr, *s1 = nullptr, *s2 = nullptr;
+  /* per-batch workspace */
+  int64_t Lcap = 0;
+  int32_t* lk_slot = nullptr;
+  uint32_t* uniq_slot = nullptr;
+  float* acc = nullptr;
+  uint32_t* arrived = nullptr;
+  uint32_t* counters = nullptr;        /* [0] nuniq of the batch, [1] error flag, [2..3] u64 row count */
+  int64_t last_L = 0;
+
+  void create(Ctx* c, int F_, int D_, int64_t capacity, const ps_updater_spec& u, int64_t max_lookups);
+  void destroy();
+  void reserve(int64_t L);
+  /* find-or-insert every (field, id) of the batch, count occurrences, number the unique keys.
+   * ids: device pointer, [N][F]; exactly one of ids_i64 / ids_f32 non-null.                  */
+  void probe(const int64_t* ids_i64, const float* ids_f32, int N);
+  /* out[n*ldo + j*D + d] = relu(w[slot(n,j)][d])   (EmbeddingField.java:73-76)               */
+  void gather(float* out, int ldo, int N);
+  /* fused scatter-add + occurrence normalisation + updater step (see table.cu)               */
+  void scatter_update(const float* delta, int ldd, const float* act, int lda, int N, int calls, const int* skip_flag);
+  /* forget the batch without updating (predict path / early exit): cnt = 0 for touched slots */
+  void clear_batch();
+  void check_errors();                 /* syncs; throws PS_ERR_CAPACITY if an insert found the table full */
+  int64_t size();
+  /* host-driven row access (KVStore.get / put, PSClient.getList / updateList) */
+  void get_rows(const int32_t* fields, const int64_t* ids, int n, float* w_out, float* s1_out, float* s2_out, int32_t* found);
+  void put_rows(const int32_t* fields, const int64_t* ids, int n, float* w_io, int replace);
+};
+
+struct WideTable {
+  Ctx* ctx = nullptr;
+  int64_t C = 0;
+  WideSlot* slots = nullptr;
+  uint32_t* counters = nullptr;        /* [0] error flag, [2..3] u64 key count */
+  UpdaterDev upd;
+
+  void create(Ctx* c, int64_t capacity, const ps_updater_spec& u);
+  void destroy();
+  /* z[n] = bias + sum_j w[W[n][j]]  in j order (LRLayer.java:70-84); inserts unseen keys with w = 0 */
+  void forward(const int64_t* ids, int N, int F, const float* bias, float* z);
+  /* LRLayer.backward pushes the SAME batch-mean delta to every key ever seen (LRLayer.java:110-117,
+   * SURVEY quirk 7): sweep all occupied slots and apply the updater with g = *gbar.             */
+  void update_all(const float* gbar, const int* skip_flag);
+  int64_t size();
+  int get(int64_t id, float* w, float* s1, float* s2);   /* 0 = absent */
+  void put(int64_t id, float w);
+  void check_errors();
+};
+
+}  // namespace psb

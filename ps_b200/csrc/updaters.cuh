@@ -1,0 +1,68 @@
+/*
+ * updaters.cuh — per-element device forms of update.AdamUpdater / FtrlUpdater / SimpleUpdater.
+ * The operation ORDER and rounding of the reference are kept (every step is a single
+ * correctly-rounded fp32 operation: __f*_rn intrinsics are never contracted into FMAs), so
+ * given the same gradient bits the new weight and state bits equal the Java/jblas ones.
+ */
+#pragma once
+#include "common.cuh"
+
+namespace psb {
+
+struct UpdaterDev {
+  int kind;
+  float a, b, c, d;      /* adam: alfa, beta1, beta2, epsilon | ftrl: alfa, beta, l1, l2 | simple: eta */
+  float omb1, omb2;      /* adam: (1 - beta1), (1 - beta2) evaluated in float like the Java code */
+};
+
+inline UpdaterDev make_updater_dev(const ps_updater_spec& s) {
+  UpdaterDev u;
+  u.kind = s.kind; u.a = s.p[0]; u.b = s.p[1]; u.c = s.p[2]; u.d = s.p[3];
+  u.omb1 = 1.0f - u.b; u.omb2 = 1.0f - u.c;
+  return u;
+}
+
+#if defined(__CUDACC__)
+/* update/AdamUpdater.java:61-69.  m,v are the M/V maps' entries (zero until first touch). */
+__device__ __forceinline__ void adam_elem(const UpdaterDev& u, float& w, float& m, float& v, float g) {
+  const float m_new = __fadd_rn(__fmul_rn(g, u.omb1), __fmul_rn(m, u.b));                 /* :61 */
+  const float v_new = __fadd_rn(__fmul_rn(__fmul_rn(g, g), u.omb2), __fmul_rn(v, u.c));   /* :62 */
+  const float Mm = __fdiv_rn(m_new, u.omb1);                                               /* :63 */
+  const float Vv = __fdiv_rn(v_new, u.omb2);                                               /* :64 */
+  const float den = __fadd_rn(__fsqrt_rn(Vv), u.d);
+  const float stp = __fmul_rn(__fdiv_rn(Mm, den), -u.a);                                   /* :69 */
+  w = __fadd_rn(w, stp);
+  m = m_new; v = v_new;
+}
+
+/* update/FtrlUpdater.java:64-74 (the early return of :52 is decided by the caller on g[0]). */
+__device__ __forceinline__ void ftrl_elem(const UpdaterDev& u, float& w, float& z, float& n, float g) {
+  float wn;
+  if (fabsf(z) <= u.c) {
+    wn = 0.0f;
+  } else {
+    const float sign = z >= 0.0f ? 1.0f : -1.0f;
+    const float num = -__fsub_rn(z, __fmul_rn(sign, u.c));
+    const float den = __fdiv_rn(__fadd_rn(u.d, __fadd_rn(u.b, __fsqrt_rn(n))), u.a);
+    wn = __fdiv_rn(num, den);
+  }
+  const float g2 = __fmul_rn(g, g);
+  const float s = __fsub_rn(__fsqrt_rn(__fadd_rn(n, g2)), __fsqrt_rn(__fdiv_rn(n, u.a)));   /* :72, sic */
+  z = __fadd_rn(z, __fsub_rn(g, __fmul_rn(s, wn)));                                         /* :73 */
+  n = __fadd_rn(n, g2);                                                                     /* :74 */
+  w = wn;
+}
+
+/* update/SimpleUpdater.java:20-22 */
+__device__ __forceinline__ void simple_elem(const UpdaterDev& u, float& w, float g) {
+  w = __fadd_rn(w, __fmul_rn(g, -u.a));
+}
+
+__device__ __forceinline__ void apply_elem(const UpdaterDev& u, float& w, float& s1, float& s2, float g) {
+  if (u.kind == PS_UPD_ADAM) adam_elem(u, w, s1, s2, g);
+  else if (u.kind == PS_UPD_FTRL) ftrl_elem(u, w, s1, s2, g);
+  else simple_elem(u, w, g);
+}
+#endif
+
+}  // namespace psb
