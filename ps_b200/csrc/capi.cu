@@ -337,7 +337,7 @@ int ps_model_train_step_dev(ps_model* m, const int64_t* E_dev, const float* X_de
   PS_TRY
   PS_REQUIRE(m, PS_ERR_ARG, "null model");
   PS_REQUIRE(m->m.in_flight == 0, PS_ERR_STATE, "host steps in flight; collect first");
-  m->m.step_device(E_dev, X_dev, W_dev, Y_dev, N, true);
+  m->m.run_step(E_dev, X_dev, W_dev, Y_dev, N, true, nullptr);
   m->m.last_N = N; m->m.last_train = true;
   PS_CATCH
 }

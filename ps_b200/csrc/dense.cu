@@ -10,6 +10,8 @@
 #include "dense.cuh"
 #include "gemm.cuh"
 
+#include <algorithm>
+
 namespace psb {
 
 /* ------------------------------------------------------------------ init */
@@ -56,7 +58,19 @@ void transpose_copy(Ctx* ctx, const float* in, int ldi, float* out, int ldo, int
  * gradient is the sum of the wgrad partial slabs divided by N: FcLayer.java:103 rowMeans and
  * :105 divi(N); KVStore.update's own division is by sumCnt = 1 (thread = 1).  Ftrl's early
  * return looks at element 0 of the key's gradient (FtrlUpdater.java:52).                     */
-__global__ void __launch_bounds__(256) dense_update_kernel(const __grid_constant__ DenseUpdateArgs a, const StepStatus* __restrict__ st) {
+__device__ __forceinline__ void publish(const StepStatus* st, const uint32_t* emb_counters, const uint32_t* wide_counters, StepStatus* host) {
+  StepStatus s = *st;
+  s.emb_err = emb_counters ? emb_counters[1] : 0u;
+  s.n_unique = emb_counters ? emb_counters[0] : 0u;
+  s.wide_err = wide_counters ? wide_counters[0] : 0u;
+  *host = s;
+  __threadfence_system();
+}
+
+__global__ void __launch_bounds__(256) dense_update_kernel(const __grid_constant__ DenseUpdateArgs a, const StepStatus* __restrict__ st,
+                                                           const uint32_t* __restrict__ emb_counters, const uint32_t* __restrict__ wide_counters,
+                                                           StepStatus* __restrict__ host) {
+  if (host != nullptr && blockIdx.x == 0 && threadIdx.x == 0) publish(st, emb_counters, wide_counters, host);   /* status is final before the updates */
   if (st->skip) return;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.total) return;
@@ -90,23 +104,9 @@ __global__ void __launch_bounds__(256) dense_update_kernel(const __grid_constant
     if (L.Wt) L.Wt[(size_t)c * L.ldwt + o] = w;
   }
 }
-void dense_update(Ctx* ctx, const DenseUpdateArgs& a, const StepStatus* st) {
-  if (a.total <= 0) return;
-  dense_update_kernel<<<ceil_div(a.total, 256), 256, 0, ctx->stream>>>(a, st);
-  PS_LAUNCH_CHECK();
-  ctx->launches++;
-}
-
-__global__ void wide_bias_update_kernel(float* bias, float* s1, float* s2, UpdaterDev upd, const StepStatus* st) {
-  if (st->skip) return;
-  const float g = st->gbar;
-  if (upd.kind == PS_UPD_FTRL && g == 0.0f) return;
-  float w = bias[0], a = s1[0], b = s2[0];
-  apply_elem(upd, w, a, b, g);
-  bias[0] = w; s1[0] = a; s2[0] = b;
-}
-void wide_bias_update(Ctx* ctx, float* bias, float* s1, float* s2, const UpdaterDev& upd, const StepStatus* st) {
-  wide_bias_update_kernel<<<1, 1, 0, ctx->stream>>>(bias, s1, s2, upd, st);
+void dense_update(Ctx* ctx, const DenseUpdateArgs& a, const StepStatus* st, const uint32_t* emb_counters, const uint32_t* wide_counters,
+                  StepStatus* host_mapped) {
+  dense_update_kernel<<<ceil_div(a.total, 256), 256, 0, ctx->stream>>>(a, st, emb_counters, wide_counters, host_mapped);
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }
@@ -126,7 +126,8 @@ void updater_apply(Ctx* ctx, const UpdaterDev& u, float* w, float* s1, float* s2
 }
 
 /* ------------------------------------------------------------------ tails */
-constexpr int kTailThreads = 1024;
+constexpr int kTailThreads = 256;
+constexpr int kTailMaxBlocks = 64;
 
 __device__ __forceinline__ float block_sum(float v, float* sh) {
   const int t = threadIdx.x;
@@ -141,16 +142,43 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
   return r;
 }
 
-/* One block: the batch is at most a few 10^4 scalars.  Per-sample arithmetic follows the Java
- * expressions operation by operation (double exp/log, float elsewhere); the two batch sums
- * (loss, rowMeans of delta) are tree reductions, so they agree with the reference's running
- * float sums to ~1e-7 relative, not bit for bit.                                              */
+/* Each block reduces its samples, the block that takes the last ticket adds the per-block
+ * partials in block order (a fixed tree: same bits every run) and writes the step status.
+ * ws: [0, 2*kTailMaxBlocks) partial sums, then one u32 ticket that the finisher resets.       */
+__device__ __forceinline__ void tail_finish(float loss_part, float d_part, int N, float* ws, StepStatus* st, float* sh) {
+  const float bl = block_sum(loss_part, sh), bd = block_sum(d_part, sh);
+  __shared__ bool is_last;
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(ws + 2 * kTailMaxBlocks);
+  if (threadIdx.x == 0) {
+    ws[2 * blockIdx.x] = bl; ws[2 * blockIdx.x + 1] = bd;
+    __threadfence();
+    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  float l = 0.0f, d = 0.0f;
+  if (threadIdx.x < gridDim.x) { l = __ldcg(ws + 2 * threadIdx.x); d = __ldcg(ws + 2 * threadIdx.x + 1); }
+  l = block_sum(l, sh); d = block_sum(d, sh);
+  if (threadIdx.x == 0) {
+    const float loss = __fdiv_rn(l, (float)N);
+    st->loss = loss;
+    st->gbar = __fdiv_rn(d, (float)N);
+    st->skip = (loss <= 0.01f || isnan(loss)) ? 1 : 0;                       /* DNN.java:58, CrossEntropy.slim */
+    st->seq += 1u;
+    *ticket = 0u;
+  }
+}
+
+/* Per-sample arithmetic follows the Java expressions operation by operation (double exp/log,
+ * float elsewhere); the two batch sums (loss, rowMeans of delta) are tree reductions, so they
+ * agree with the reference's running float sums to ~1e-7 relative, not bit for bit.           */
 __global__ void __launch_bounds__(kTailThreads) tail_binary_kernel(int N, const float* __restrict__ zdeep, int ldz, const float* __restrict__ zwide,
                                                                    const float* __restrict__ Y, float* __restrict__ p_out, int ldp,
-                                                                   float* __restrict__ d_out, int ldd, int train, StepStatus* __restrict__ st) {
+                                                                   float* __restrict__ d_out, int ldd, float* __restrict__ dt_out, int train,
+                                                                   StepStatus* __restrict__ st, float* __restrict__ ws) {
   __shared__ float sh[kTailThreads];
   float loss_part = 0.0f, d_part = 0.0f;
-  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
     float z = zdeep[(size_t)n * ldz];
     if (zwide) z = __fadd_rn(z, zwide[n]);                                   /* AddLayer.java:36 */
     const float p = sigmoid_clipped(z);                                      /* Sigmoid.java:11 */
@@ -162,30 +190,27 @@ __global__ void __launch_bounds__(kTailThreads) tail_binary_kernel(int N, const 
       float d = __fdiv_rn(__fsub_rn(p, l), __fmul_rn(p, omp));                /* CrossEntropy.java:25 */
       d = __fmul_rn(d, __fmul_rn(p, omp));                                   /* Sigmoid.java:18 */
       d_out[(size_t)n * ldd] = d;
+      if (dt_out) dt_out[n] = d;
       d_part = __fadd_rn(d_part, d);
     }
   }
   if (!train) return;
-  const float loss = __fdiv_rn(block_sum(loss_part, sh), (float)N);
-  const float gbar = __fdiv_rn(block_sum(d_part, sh), (float)N);
-  if (threadIdx.x == 0) {
-    st->loss = loss;
-    st->gbar = gbar;
-    st->skip = (loss <= 0.01f || isnan(loss)) ? 1 : 0;                       /* DNN.java:58, CrossEntropy.slim */
-  }
+  tail_finish(loss_part, d_part, N, ws, st, sh);
 }
+static int tail_blocks(int N) { return std::max(1, std::min(kTailMaxBlocks, ceil_div(N, kTailThreads))); }
 void tail_binary(Ctx* ctx, int N, const float* zdeep, int ldz, const float* zwide, const float* Y, float* p_out, int ldp, float* d_out, int ldd,
-                 int train, StepStatus* st) {
-  tail_binary_kernel<<<1, kTailThreads, 0, ctx->stream>>>(N, zdeep, ldz, zwide, Y, p_out, ldp, d_out, ldd, train, st);
+                 float* dt_out, int train, StepStatus* st, float* ws) {
+  tail_binary_kernel<<<tail_blocks(N), kTailThreads, 0, ctx->stream>>>(N, zdeep, ldz, zwide, Y, p_out, ldp, d_out, ldd, dt_out, train, st, ws);
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }
 
 __global__ void __launch_bounds__(kTailThreads) tail_softmax_kernel(int N, int C, float* __restrict__ Z, int ldz, const float* __restrict__ Y,
-                                                                    float* __restrict__ d_out, int ldd, int train, StepStatus* __restrict__ st) {
+                                                                    float* __restrict__ d_out, int ldd, float* __restrict__ dt_out, int ldt, int train,
+                                                                    StepStatus* __restrict__ st, float* __restrict__ ws) {
   __shared__ float sh[kTailThreads];
   float loss_part = 0.0f;
-  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
     float* z = Z + (size_t)n * ldz;
     float mx = -INFINITY;
     for (int i = 0; i < C; ++i) { const float x = __fdiv_rn(z[i], 10000.0f); z[i] = x; mx = fmaxf(mx, x); }      /* Softmax.java:22-24 */
@@ -206,34 +231,25 @@ __global__ void __launch_bounds__(kTailThreads) tail_softmax_kernel(int N, int C
         const float yk = z[k];
         const float t = (k == hot) ? __fmul_rn(yk, __fsub_rn(1.0f, yk)) : __fmul_rn(-ph, yk);
         d[k] = __fmul_rn(t, dy);
+        if (dt_out) dt_out[(size_t)k * ldt + n] = d[k];
       }
     }
   }
   if (!train) return;
-  const float loss = __fdiv_rn(block_sum(loss_part, sh), (float)N);
-  if (threadIdx.x == 0) {
-    st->loss = loss;
-    st->gbar = 0.0f;
-    st->skip = (loss <= 0.01f || isnan(loss)) ? 1 : 0;                       /* FullConnectedNN.java: same early exit */
-  }
+  tail_finish(loss_part, 0.0f, N, ws, st, sh);
 }
-void tail_softmax(Ctx* ctx, int N, int C, float* Z, int ldz, const float* Y, float* d_out, int ldd, int train, StepStatus* st) {
-  tail_softmax_kernel<<<1, kTailThreads, 0, ctx->stream>>>(N, C, Z, ldz, Y, d_out, ldd, train, st);
+void tail_softmax(Ctx* ctx, int N, int C, float* Z, int ldz, const float* Y, float* d_out, int ldd, float* dt_out, int ldt, int train,
+                  StepStatus* st, float* ws) {
+  tail_softmax_kernel<<<tail_blocks(N), kTailThreads, 0, ctx->stream>>>(N, C, Z, ldz, Y, d_out, ldd, dt_out, ldt, train, st, ws);
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }
 
-__global__ void publish_status_kernel(StepStatus* st, const uint32_t* emb_counters, const uint32_t* wide_counters, uint32_t seq, StepStatus* host) {
-  StepStatus s = *st;
-  s.emb_err = emb_counters ? emb_counters[1] : 0u;
-  s.n_unique = emb_counters ? emb_counters[0] : 0u;
-  s.wide_err = wide_counters ? wide_counters[0] : 0u;
-  s.seq = seq;
-  *host = s;
-  __threadfence_system();
+__global__ void publish_status_kernel(StepStatus* st, const uint32_t* emb_counters, const uint32_t* wide_counters, StepStatus* host) {
+  publish(st, emb_counters, wide_counters, host);
 }
-void publish_status(Ctx* ctx, StepStatus* st, const uint32_t* emb_counters, const uint32_t* wide_counters, uint32_t seq, StepStatus* host_mapped) {
-  publish_status_kernel<<<1, 1, 0, ctx->stream>>>(st, emb_counters, wide_counters, seq, host_mapped);
+void publish_status(Ctx* ctx, StepStatus* st, const uint32_t* emb_counters, const uint32_t* wide_counters, StepStatus* host_mapped) {
+  publish_status_kernel<<<1, 1, 0, ctx->stream>>>(st, emb_counters, wide_counters, host_mapped);
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }

@@ -41,18 +41,20 @@ struct DenseUpdateArgs {
 
 void dense_init(Ctx* ctx, float* W, int out, int in, int ldw, float* Wt, int ldwt, uint64_t key, float maxv);
 void fill_column(Ctx* ctx, float* buf, int ld, int col, int rows, float value);
-void dense_update(Ctx* ctx, const DenseUpdateArgs& a, const StepStatus* st);
+/* also publishes the step status to mapped host memory when host_mapped is non-null */
+void dense_update(Ctx* ctx, const DenseUpdateArgs& a, const StepStatus* st, const uint32_t* emb_counters, const uint32_t* wide_counters,
+                  StepStatus* host_mapped);
+constexpr int kTailWorkspaceFloats = 2 * 64 + 4;
 
 /* binary tail: z = deep (+ wide); p = clipped sigmoid; CrossEntropy forward/backward; sigmoid
  * derivative.  Writes p to p_out (stride ldp), the post-derivative delta to d_out (stride ldd). */
 void tail_binary(Ctx* ctx, int N, const float* zdeep, int ldz, const float* zwide, const float* Y, float* p_out, int ldp,
-                 float* d_out, int ldd, int train, StepStatus* st);
+                 float* d_out, int ldd, float* dt_out, int train, StepStatus* st, float* ws);
 /* multi-class tail (FullConnectedNN): Softmax(10000) in place on Z, SoftmaxLoss, Softmax.backward */
-void tail_softmax(Ctx* ctx, int N, int C, float* Z, int ldz, const float* Y, float* d_out, int ldd, int train, StepStatus* st);
-/* wide.bias step with the same gbar the wide weights receive (LRLayer.java:112-113) */
-void wide_bias_update(Ctx* ctx, float* bias, float* s1, float* s2, const UpdaterDev& upd, const StepStatus* st);
+void tail_softmax(Ctx* ctx, int N, int C, float* Z, int ldz, const float* Y, float* d_out, int ldd, float* dt_out, int ldt, int train,
+                  StepStatus* st, float* ws);
 /* copies the status (plus table error flags) to mapped host memory */
-void publish_status(Ctx* ctx, StepStatus* st, const uint32_t* emb_counters, const uint32_t* wide_counters, uint32_t seq, StepStatus* host_mapped);
+void publish_status(Ctx* ctx, StepStatus* st, const uint32_t* emb_counters, const uint32_t* wide_counters, StepStatus* host_mapped);
 /* Updater.update on caller-provided device arrays (test hook for ps_updater_apply) */
 void updater_apply(Ctx* ctx, const UpdaterDev& u, float* w, float* s1, float* s2, const float* g, int n);
 /* out[c*ldo + r] = in[r*ldi + c]  (layout conversion at the get/put boundary) */

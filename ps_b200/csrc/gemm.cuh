@@ -26,6 +26,7 @@ struct FcFwdArgs {
   const float* bias;              /* [out] */
   int act;                        /* PS_ACT_NONE | RELU | SIGMOID (softmax is applied by the tail kernel) */
   float* Z; int ldz;              /* [B][ldz] */
+  float* Zt; int ldzt;            /* optional transposed copy [out][ldzt] (operand of the TF32 wgrad) */
 };
 
 struct FcDgradArgs {
@@ -37,12 +38,14 @@ struct FcDgradArgs {
   const float* Y; int ldy;        /* [B][ldy] */
   int n_cols;                     /* how many of the `in` columns are needed (F*D for the first layer) */
   float* dX; int ldx;             /* [B][ldx] */
+  float* dXt; int ldxt;           /* optional transposed copy [in][ldxt] */
 };
 
 struct FcWgradArgs {
   int B, in, out;
   const float* dl; int ldd;       /* [B][ldd] */
   const float* A; int lda;        /* [B][lda], column `in` == 1 */
+  const float* dlT; const float* AT; int ldt;   /* transposed copies [out][ldt], [in+1][ldt] (row `in` == 1): TF32 path */
   float* G; int ldg;              /* [nsplit][out][ldg] partial sums over batch chunks */
   size_t slab;                    /* elements between consecutive partial slabs */
   int nsplit;
@@ -55,6 +58,7 @@ void fc_wgrad_fp32(Ctx* ctx, const FcWgradArgs& a);
 void fc_forward_tf32(Ctx* ctx, const FcFwdArgs& a);
 void fc_dgrad_tf32(Ctx* ctx, const FcDgradArgs& a);
 void fc_wgrad_tf32(Ctx* ctx, const FcWgradArgs& a);
+void fc_tf32_init();   /* one-time kernel attributes (must not happen inside a stream capture) */
 
 #if defined(__CUDACC__)
 /* activations/Sigmoid.java:9-14: (float)(0.001f + (.999f-0.001f) / (1f + Math.exp(-x))) */

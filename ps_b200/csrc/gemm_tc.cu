@@ -1,7 +1,333 @@
-/* placeholder until the tcgen05 kernels land (next commit) */
+/*
+ * gemm_tc.cu — TF32 tensor-core form of the FcLayer contractions on sm_100a (PS_FC_TF32):
+ * tcgen05.mma (kind::tf32, fp32 accumulate in TMEM) fed by TMA (cp.async.bulk.tensor, 128 B
+ * swizzle) through a 4-stage mbarrier pipeline; 128 threads per CTA:
+ *     warp 0 / one lane  : TMA producer
+ *     warp 1 / one lane  : MMA issuer (tcgen05.mma + tcgen05.commit)
+ *     warps 0-3          : epilogue (tcgen05.ld 32x32b → registers → bias / activation /
+ *                          activation derivative → global), each warp its own 32 TMEM lanes
+ * One output tile (128 x BLOCK_N) per CTA, optional split over K (wgrad: K = batch).
+ *
+ * All three contractions are expressed as C[M][N] = sum_k A[m][k] * B[n][k] with BOTH operands
+ * K-major (K contiguous), the one operand layout whose 128B-swizzle UMMA descriptor is the
+ * plain canonical form; the transposed operand copies this needs (activations^T, delta^T, W^T)
+ * are written by the producing epilogues, where the TMEM register layout (one row per lane)
+ * makes the transposed store the naturally coalesced one.
+ *
+ *   forward  Z  [B][out]   : A = act [B][in],        B = W  [out][in]
+ *   dgrad    dX [B][in]    : A = delta [B][out],     B = Wt [in][out]
+ *   wgrad    G  [out][in+1]: A = delta^T [out][B],   B = [act | 1]^T [in+1][B]   (split over B)
+ *
+ * Tensor maps carry the LOGICAL extents, so every ragged edge (K not a multiple of 32, N not a
+ * multiple of BLOCK_N, batch tail) is zero-filled by TMA; stores are clipped.
+ */
+#include <cuda.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #include "gemm.cuh"
+
 namespace psb {
-void fc_forward_tf32(Ctx*, const FcFwdArgs&) { throw Error(PS_ERR_ARG, "PS_FC_TF32 not built"); }
-void fc_dgrad_tf32(Ctx*, const FcDgradArgs&) { throw Error(PS_ERR_ARG, "PS_FC_TF32 not built"); }
-void fc_wgrad_tf32(Ctx*, const FcWgradArgs&) { throw Error(PS_ERR_ARG, "PS_FC_TF32 not built"); }
+
+namespace {
+
+constexpr int BM = 128, BK = 32, STAGES = 4, UMMA_K = 8;
+enum { EPI_FWD = 0, EPI_DGRAD = 1, EPI_WGRAD = 2 };
+
+struct TcParams {
+  int M, N, K;
+  int kb_per_split;            /* k-blocks (of 32) handled by one blockIdx.z */
+  float* C; long ldc; size_t slab;
+  float* Ct; long ldct;        /* transposed copy Ct[n][m] or null */
+  const float* bias; int act;  /* EPI_FWD */
+  const float* Y; long ldy;    /* EPI_DGRAD */
+  int epi;
+};
+
+/* ---- PTX wrappers ------------------------------------------------------------------ */
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+/* shared-memory matrix descriptor, K-major, 128 B swizzle: rows are 128 B apart, 8-row groups
+ * 1024 B apart (SBO); LBO is unused for swizzled K-major; bit 46 = descriptor version 1 (sm_100);
+ * bits 61-63 = 2 (SWIZZLE_128B).                                                             */
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+/* instruction descriptor (kind::tf32): D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2),
+ * both K-major (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28                 */
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+template <int BLOCK_N>
+struct SmemLayout {
+  static constexpr uint32_t A_BYTES = BM * BK * 4;
+  static constexpr uint32_t B_BYTES = BLOCK_N * BK * 4;
+  static constexpr uint32_t BAR_OFF = STAGES * (A_BYTES + B_BYTES);
+  static constexpr uint32_t TOTAL = BAR_OFF + 128 + 1024;   /* + barriers/tmem slot + manual 1024 B alignment slack */
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(128) gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                        const TcParams p) {
+  using SL = SmemLayout<BLOCK_N>;
+  constexpr int TMEM_COLS = BLOCK_N <= 32 ? 32 : (BLOCK_N <= 64 ? 64 : (BLOCK_N <= 128 ? 128 : 256));
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sA = base, sB = base + STAGES * SL::A_BYTES, bars = base + SL::BAR_OFF;
+  /* bars: full[STAGES] | empty[STAGES] | tmem_full | tmem slot */
+  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull = bars + 16 * STAGES, tslot = bars + 16 * STAGES + 8;
+  volatile uint32_t* tslot_gen = reinterpret_cast<volatile uint32_t*>(gen_base + SL::BAR_OFF + 16 * STAGES + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BLOCK_N;
+  const int nkb_total = (p.K + BK - 1) / BK;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int num_kb = max(0, min(nkb_total, kb_begin + p.kb_per_split) - kb_begin);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "r"((uint32_t)TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot_gen;
+
+  if (warp == 0 && lane == 0) {
+    /* ===== TMA producer ===== */
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % STAGES;
+      mbar_wait(empty0 + 8 * s, ((kb / STAGES) & 1) ^ 1);
+      mbar_expect_tx(full0 + 8 * s, SL::A_BYTES + SL::B_BYTES);
+      const int k = (kb_begin + kb) * BK;
+      tma_load_2d(sA + s * SL::A_BYTES, &tmA, full0 + 8 * s, k, m0);
+      tma_load_2d(sB + s * SL::B_BYTES, &tmB, full0 + 8 * s, k, n0);
+    }
+  } else if (warp == 1 && lane == 0) {
+    /* ===== MMA issuer ===== */
+    constexpr uint32_t idesc = make_idesc_tf32(BM, BLOCK_N);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % STAGES;
+      mbar_wait(full0 + 8 * s, (kb / STAGES) & 1);
+      tc_fence_after();
+      const uint64_t ad = make_kmajor_sw128_desc(sA + s * SL::A_BYTES);
+      const uint64_t bd = make_kmajor_sw128_desc(sB + s * SL::B_BYTES);
+#pragma unroll
+      for (int k = 0; k < BK / UMMA_K; ++k)   /* advance 32 B inside the 128 B swizzle atom: +2 in the 16 B-unit address field */
+        tc_mma_tf32(tmem, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+      tc_commit(empty0 + 8 * s);               /* frees the stage once these MMAs have read it */
+    }
+    if (num_kb > 0) tc_commit(tfull);          /* accumulator complete */
+  }
+  __syncwarp();
+
+  /* ===== epilogue: warp w owns TMEM lanes [32w, 32w+32) = output rows m0 + 32w + lane ===== */
+  if (num_kb > 0) {
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+  }
+  const int m = m0 + warp * 32 + lane;
+  float* Cz = p.C + (size_t)blockIdx.z * p.slab;
+  const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0);
+#pragma unroll 1
+  for (int c = 0; c < BLOCK_N; c += 16) {
+    float v[16];
+    if (num_kb > 0) tc_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
+    else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    }
+    const int nb = n0 + c;
+    if (nb >= p.N) continue;                   /* warp-uniform */
+    if (p.epi == EPI_FWD) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) if (nb + i < p.N) v[i] = act_forward(p.act, __fadd_rn(v[i], __ldg(p.bias + nb + i)));
+    } else if (p.epi == EPI_DGRAD && p.act != PS_ACT_NONE) {
+      if (m < p.M) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) if (nb + i < p.N) v[i] = act_backward(p.act, v[i], p.Y[(long)m * p.ldy + nb + i]);
+      }
+    }
+    if (m < p.M) {
+      float* row = Cz + (long)m * p.ldc + nb;
+      if (vec_ok && nb + 15 < p.N) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) st_f4(row + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) if (nb + i < p.N) row[i] = v[i];
+      }
+      if (p.Ct) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) if (nb + i < p.N) p.Ct[(long)(nb + i) * p.ldct + m] = v[i];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+/* ---- host: tensor maps ---------------------------------------------------------------- */
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  PS_REQUIRE(fn != nullptr, PS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  return fn;
+}
+
+/* a K-major fp32 operand [rows][k_extent], leading dimension ld floats; box = 32 floats x box_rows */
+const CUtensorMap& tensor_map(const float* ptr, int rows, int k_extent, long ld, int box_rows) {
+  using Key = std::tuple<const float*, int, int, long, int>;
+  static std::map<Key, CUtensorMap> cache;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  const Key key(ptr, rows, k_extent, ld, box_rows);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  PS_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ld % 4 == 0, PS_ERR_ARG, "tf32 gemm: operand must be 16 B aligned with ld % 4 == 0");
+  CUtensorMap m;
+  const cuuint64_t dims[2] = {(cuuint64_t)k_extent, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PS_REQUIRE(r == CUDA_SUCCESS, PS_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  if (cache.size() > 4096) cache.clear();
+  return cache.emplace(key, m).first->second;
+}
+
+template <int BLOCK_N>
+void launch_tc(Ctx* ctx, const float* A, long lda, const float* B, long ldb, TcParams& p, int nsplit) {
+  using SL = SmemLayout<BLOCK_N>;
+  const CUtensorMap ta = tensor_map(A, p.M, p.K, lda, BM);
+  const CUtensorMap tb = tensor_map(B, p.N, p.K, ldb, BLOCK_N);
+  const int nkb = (p.K + BK - 1) / BK;
+  p.kb_per_split = (nkb + nsplit - 1) / nsplit;
+  dim3 grid(ceil_div(p.N, BLOCK_N), ceil_div(p.M, BM), nsplit);
+  gemm_tf32_kernel<BLOCK_N><<<grid, 128, SL::TOTAL, ctx->stream>>>(ta, tb, p);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+}
+
+void dispatch_tc(Ctx* ctx, const float* A, long lda, const float* B, long ldb, TcParams& p, int nsplit) {
+  if (p.N <= 16) launch_tc<16>(ctx, A, lda, B, ldb, p, nsplit);
+  else if (p.N <= 32) launch_tc<32>(ctx, A, lda, B, ldb, p, nsplit);
+  else launch_tc<64>(ctx, A, lda, B, ldb, p, nsplit);
+}
+
+template <int BLOCK_N>
+void set_attr() {
+  PS_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<BLOCK_N>::TOTAL));
+}
+
+}  // namespace
+
+void fc_tf32_init() {
+  static bool done = false;
+  if (done) return;
+  set_attr<16>(); set_attr<32>(); set_attr<64>();
+  encode_fn();
+  done = true;
+}
+
+void fc_forward_tf32(Ctx* ctx, const FcFwdArgs& a) {
+  TcParams p{};
+  p.M = a.B; p.N = a.out; p.K = a.in;
+  p.C = a.Z; p.ldc = a.ldz; p.slab = 0; p.Ct = a.Zt; p.ldct = a.ldzt;
+  p.bias = a.bias; p.act = a.act; p.epi = EPI_FWD;
+  dispatch_tc(ctx, a.A, a.lda, a.W, a.ldw, p, 1);
+}
+
+void fc_dgrad_tf32(Ctx* ctx, const FcDgradArgs& a) {
+  PS_REQUIRE(a.Wt != nullptr, PS_ERR_ARG, "tf32 dgrad needs the transposed weight copy");
+  TcParams p{};
+  p.M = a.B; p.N = a.n_cols; p.K = a.out;
+  p.C = a.dX; p.ldc = a.ldx; p.slab = 0; p.Ct = a.dXt; p.ldct = a.ldxt;
+  p.act = a.act_below; p.Y = a.Y; p.ldy = a.ldy; p.epi = EPI_DGRAD;
+  dispatch_tc(ctx, a.dl, a.ldd, a.Wt, a.ldwt, p, 1);
+}
+
+void fc_wgrad_tf32(Ctx* ctx, const FcWgradArgs& a) {
+  PS_REQUIRE(a.dlT != nullptr && a.AT != nullptr, PS_ERR_ARG, "tf32 wgrad needs the transposed delta / activation copies");
+  TcParams p{};
+  p.M = a.out; p.N = a.in + 1; p.K = a.B;
+  p.C = a.G; p.ldc = a.ldg; p.slab = a.slab; p.Ct = nullptr; p.epi = EPI_WGRAD;
+  dispatch_tc(ctx, a.dlT, a.ldt, a.AT, a.ldt, p, a.nsplit);
+}
+
+}  // namespace psb

@@ -68,12 +68,18 @@ void Model::create(Ctx* c, int kind_, int F_, int D_, int Xn_, const int32_t* fc
   width.assign(L + 1, 0); ld.assign(L + 1, 0);
   width[0] = has_emb ? F * D + Xn : Xn;
   for (int l = 0; l < L; ++l) width[l + 1] = fc_dims[l];
-  act.assign(L + 1, nullptr); delta.assign(L + 1, nullptr);
+  act.assign(L + 1, nullptr); delta.assign(L + 1, nullptr); act_t.assign(L + 1, nullptr); delta_t.assign(L + 1, nullptr);
+  ldt = round_up(Bmax, 4);
   for (int l = 0; l <= L; ++l) {
     ld[l] = round_up(width[l] + 1, 8);
     act[l] = dmalloc_zero<float>((size_t)Bmax * ld[l], s);
     delta[l] = dmalloc_zero<float>((size_t)Bmax * ld[l], s);
-    if (l < L) fill_column(ctx, act[l], ld[l], width[l], Bmax, 1.0f);   /* the constant-1 column that yields db in wgrad */
+    act_t[l] = dmalloc_zero<float>((size_t)(width[l] + 1) * ldt, s);
+    delta_t[l] = dmalloc_zero<float>((size_t)width[l] * ldt, s);
+    if (l < L) {                     /* the constant-1 column (row of the transposed copy) that yields db in wgrad */
+      fill_column(ctx, act[l], ld[l], width[l], Bmax, 1.0f);
+      fill_column(ctx, act_t[l] + (size_t)width[l] * ldt, 1, 0, ldt, 1.0f);
+    }
   }
   fcs.resize(L);
   for (int l = 0; l < L; ++l)   /* FcLayer.build (FcLayer.java:53-70): ReLU inside, the top activation belongs to the tail */
@@ -87,6 +93,8 @@ void Model::create(Ctx* c, int kind_, int F_, int D_, int Xn_, const int32_t* fc
     P = dmalloc_zero<float>(Bmax, s);
   }
   st_dev = dmalloc_zero<StepStatus>(1, s);
+  tail_ws = dmalloc_zero<float>(kTailWorkspaceFloats, s);
+  fc_tf32_init();
   for (auto& S : stage) {
     if (has_emb) S.E = dmalloc<int64_t>((size_t)Bmax * F);
     if (has_wide) S.W = dmalloc<int64_t>((size_t)Bmax * F);
@@ -106,9 +114,13 @@ void Model::destroy() {
   for (auto& f : fcs) f.destroy();
   for (auto p : act) dfree(p);
   for (auto p : delta) dfree(p);
+  for (auto p : act_t) dfree(p);
+  for (auto p : delta_t) dfree(p);
   if (has_emb) emb.destroy();
   if (has_wide) { wide.destroy(); dfree(wide_bias); dfree(wide_z); dfree(P); }
-  dfree(st_dev);
+  dfree(st_dev); dfree(tail_ws);
+  for (auto& g : graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+  graphs.clear();
   for (auto& S : stage) {
     dfree(S.E); dfree(S.W); dfree(S.X); dfree(S.Y);
     if (S.st_host) cudaFreeHost(S.st_host);
@@ -150,7 +162,35 @@ static const float* gbar_ptr(const StepStatus* st) {
   return reinterpret_cast<const float*>(reinterpret_cast<const char*>(st) + offsetof(StepStatus, gbar));
 }
 
-void Model::step_device(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, bool train) {
+void Model::run_step(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, bool train, StepStatus* publish_to) {
+  PS_REQUIRE(N > 0 && N <= Bmax, PS_ERR_ARG, "model: batch size must be in [1, max_batch]");
+  if (profile || !use_graph) { step_device(E, X, W, Y, N, train, publish_to); return; }
+  const auto key = std::make_tuple((const void*)E, (const void*)X, (const void*)W, (const void*)Y, N, train ? 1 : 0, (const void*)publish_to,
+                                   ctx->fc_precision);
+  auto it = graphs.find(key);
+  if (it == graphs.end()) {
+    if (graphs.size() >= 256) {
+      for (auto& g : graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+      graphs.clear();
+    }
+    const long l0 = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    PS_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    try { step_device(E, X, W, Y, N, train, publish_to); }
+    catch (...) { cudaStreamEndCapture(ctx->stream, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+    PS_CUDA(cudaStreamEndCapture(ctx->stream, &graph));
+    GraphEntry ge;
+    ge.kernels = ctx->launches - l0;
+    ctx->launches = l0;
+    PS_CUDA(cudaGraphInstantiate(&ge.exec, graph, 0));
+    PS_CUDA(cudaGraphDestroy(graph));
+    it = graphs.emplace(key, ge).first;
+  }
+  PS_CUDA(cudaGraphLaunch(it->second.exec, ctx->stream));
+  ctx->launches += it->second.kernels;
+}
+
+void Model::step_device(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, bool train, StepStatus* publish_to) {
   PS_REQUIRE(N > 0 && N <= Bmax, PS_ERR_ARG, "model: batch size must be in [1, max_batch]");
   cudaStream_t s = ctx->stream;
   const bool fp32 = ctx->fc_precision == PS_FC_FP32;
@@ -166,6 +206,7 @@ void Model::step_device(const int64_t* E, const float* X, const int64_t* W, cons
   } else {
     PS_CUDA(cudaMemcpy2DAsync(act[0], sizeof(float) * ld[0], X, sizeof(float) * Xn, sizeof(float) * Xn, N, cudaMemcpyDeviceToDevice, s));
   }
+  if (!fp32) { transpose_copy(ctx, act[0], ld[0], act_t[0], ldt, N, width[0]); }
   mark("x_concat");
   if (has_wide) { wide.forward(W, N, F, wide_bias, wide_z); mark("wide_fwd"); }
   for (int l = 0; l < L; ++l) {
@@ -173,17 +214,19 @@ void Model::step_device(const int64_t* E, const float* X, const int64_t* W, cons
     a.B = N; a.in = fcs[l].in; a.out = fcs[l].out;
     a.A = act[l]; a.lda = ld[l]; a.W = fcs[l].W; a.ldw = fcs[l].ldw; a.bias = fcs[l].bias; a.act = fcs[l].act;
     a.Z = act[l + 1]; a.ldz = ld[l + 1];
+    a.Zt = (!fp32 && l + 1 < L) ? act_t[l + 1] : nullptr; a.ldzt = ldt;
     if (fp32) fc_forward_fp32(ctx, a); else fc_forward_tf32(ctx, a);
   }
   mark("fc_fwd");
   if (kind == PS_MODEL_FCNN)
-    tail_softmax(ctx, N, width[L], act[L], ld[L], Y, delta[L], ld[L], train ? 1 : 0, st_dev);
+    tail_softmax(ctx, N, width[L], act[L], ld[L], Y, delta[L], ld[L], fp32 ? nullptr : delta_t[L], ldt, train ? 1 : 0, st_dev, tail_ws);
   else
     tail_binary(ctx, N, act[L], ld[L], has_wide ? wide_z : nullptr, Y, has_wide ? P : act[L], has_wide ? 1 : ld[L], delta[L], ld[L],
-                train ? 1 : 0, st_dev);
+                fp32 ? nullptr : delta_t[L], train ? 1 : 0, st_dev, tail_ws);
   mark("tail");
   if (!train) {
     if (has_emb) emb.clear_batch();
+    if (publish_to) publish_status(ctx, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, publish_to);
     return;
   }
   /* ---- backward (DNN.java:64-68) ---- */
@@ -191,6 +234,7 @@ void Model::step_device(const int64_t* E, const float* X, const int64_t* W, cons
     FcWgradArgs g{};
     g.B = N; g.in = fcs[l].in; g.out = fcs[l].out;
     g.dl = delta[l + 1]; g.ldd = ld[l + 1]; g.A = act[l]; g.lda = ld[l];
+    g.dlT = delta_t[l + 1]; g.AT = act_t[l]; g.ldt = ldt;
     g.G = fcs[l].G; g.ldg = fcs[l].ldw; g.slab = (size_t)fcs[l].out * fcs[l].ldw; g.nsplit = fcs[l].nsplit;
     if (fp32) fc_wgrad_fp32(ctx, g); else fc_wgrad_tf32(ctx, g);
     FcDgradArgs d{};
@@ -198,14 +242,14 @@ void Model::step_device(const int64_t* E, const float* X, const int64_t* W, cons
     d.dl = delta[l + 1]; d.ldd = ld[l + 1]; d.W = fcs[l].W; d.ldw = fcs[l].ldw; d.Wt = fcs[l].Wt; d.ldwt = fcs[l].ldwt;
     d.act_below = l > 0 ? fcs[l - 1].act : PS_ACT_NONE; d.Y = act[l]; d.ldy = ld[l];
     d.n_cols = fcs[l].in; d.dX = delta[l]; d.ldx = ld[l];
+    d.dXt = (!fp32 && l > 0) ? delta_t[l] : nullptr; d.ldxt = ldt;
     if (fp32) fc_dgrad_fp32(ctx, d); else fc_dgrad_tf32(ctx, d);
   }
   mark("fc_bwd");
   /* ---- KVStore.update + clear (Trainer.java:93,95) ---- */
   if (has_emb) { emb.scatter_update(delta[0], ld[0], act[0], ld[0], N, 2, skip_ptr(st_dev)); mark("emb_bwd_update"); }
   if (has_wide) {
-    wide.update_all(gbar_ptr(st_dev), skip_ptr(st_dev));
-    wide_bias_update(ctx, wide_bias, wide_bias + 1, wide_bias + 2, make_updater_dev(upd_wide), st_dev);
+    wide.update_all(gbar_ptr(st_dev), skip_ptr(st_dev), wide_bias, &upd_wide);
     mark("wide_update");
   }
   DenseUpdateArgs u{};
@@ -220,7 +264,7 @@ void Model::step_device(const int64_t* E, const float* X, const int64_t* W, cons
     q.first = first; first += (long)f.out * (f.in + 1);
   }
   u.total = first;
-  dense_update(ctx, u, st_dev);
+  dense_update(ctx, u, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, publish_to);
   mark("dense_update");
 }
 
@@ -238,8 +282,7 @@ void Model::submit(const HostBatch& b) {
   PS_CUDA(cudaEventRecord(S.h2d_done, cs));
   PS_CUDA(cudaStreamWaitEvent(ctx->stream, S.h2d_done, 0));
   S.N = b.N;
-  step_device(S.E, S.X, S.W, S.Y, b.N, true);
-  publish_status(ctx, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, ++seq, S.st_host);
+  run_step(S.E, S.X, S.W, S.Y, b.N, true, S.st_host);
   PS_CUDA(cudaEventRecord(S.step_done, ctx->stream));
   S.busy = true;
   next_stage ^= 1; in_flight++;
@@ -261,7 +304,7 @@ float Model::collect() {
 
 float Model::read_loss() {
   PS_REQUIRE(in_flight == 0, PS_ERR_STATE, "model: host steps in flight");
-  publish_status(ctx, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, ++seq, stage[0].st_host);
+  publish_status(ctx, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, stage[0].st_host);
   PS_CUDA(cudaStreamSynchronize(ctx->stream));
   last_status = *stage[0].st_host;
   if (profile) finish_profile();
@@ -279,7 +322,7 @@ void Model::predict(const HostBatch& b, float* out) {
   if (has_emb) PS_CUDA(cudaMemcpyAsync(S.E, b.E, sizeof(int64_t) * N * F, cudaMemcpyHostToDevice, s));
   if (has_wide) PS_CUDA(cudaMemcpyAsync(S.W, b.W, sizeof(int64_t) * N * F, cudaMemcpyHostToDevice, s));
   PS_CUDA(cudaMemcpyAsync(S.X, b.X, sizeof(float) * N * Xn, cudaMemcpyHostToDevice, s));
-  step_device(S.E, S.X, S.W, nullptr, b.N, false);
+  step_device(S.E, S.X, S.W, nullptr, b.N, false, nullptr);
   if (kind == PS_MODEL_FCNN)
     PS_CUDA(cudaMemcpy2DAsync(out, sizeof(float) * width[L], act[L], sizeof(float) * ld[L], sizeof(float) * width[L], N, cudaMemcpyDeviceToHost, s));
   else if (has_wide)

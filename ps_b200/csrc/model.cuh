@@ -7,7 +7,9 @@
  * Java classes of integration/java/ forward to these through the C ABI.
  */
 #pragma once
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "common.cuh"
@@ -46,9 +48,16 @@ struct Model {
   std::vector<FcLayer> fcs;
   std::vector<float*> act;       /* act[0] = concat output, act[l+1] = fc<l>.A ; [Bmax][ld[l]] */
   std::vector<float*> delta;     /* delta[l] = fc<l>.delta (input side, shape of act[l]); delta[L] = top delta */
+  std::vector<float*> act_t;     /* act_t[l] = [act[l] | 1]^T, [width[l]+1][ldt]: K-major operand of the TF32 wgrad */
+  std::vector<float*> delta_t;   /* delta_t[l] = delta[l]^T, [width[l]][ldt] */
+  int ldt = 0;
   std::vector<int> width, ld;
-  float *wide_z = nullptr, *P = nullptr;
+  float *wide_z = nullptr, *P = nullptr, *tail_ws = nullptr;
   StepStatus* st_dev = nullptr;
+  /* one CUDA graph per (input buffers, batch size, mode): a step is ~25 small launches, replayed as one */
+  bool use_graph = true;
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; long kernels = 0; };
+  std::map<std::tuple<const void*, const void*, const void*, const void*, int, int, const void*, int>, GraphEntry> graphs;
   /* two staging sets so the H2D of step i+1 overlaps the kernels of step i */
   struct Stage {
     int64_t *E = nullptr, *W = nullptr; float *X = nullptr, *Y = nullptr;
@@ -70,7 +79,9 @@ struct Model {
               const ps_updater_spec* emb_updater, int max_batch);
   void destroy();
   /* the whole step on device-resident inputs, enqueued on ctx->stream; status lands in st_dev */
-  void step_device(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, bool train);
+  void step_device(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, bool train, StepStatus* publish_to);
+  /* the same through the graph cache (falls back to direct launches while profiling) */
+  void run_step(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, bool train, StepStatus* publish_to);
   void submit(const HostBatch& b);
   float collect();
   float read_loss();

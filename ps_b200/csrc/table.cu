@@ -189,14 +189,18 @@ __global__ void __launch_bounds__(256) emb_scatter_update_kernel(EmbSlot* __rest
     gk = sum;
   }
   if (lane_on && leader) red_add_f4(acc + (size_t)uidx * Dp + part * 4, gk);
-  __threadfence();
+  /* release: every lane's reduction happens-before lane 0's fence (warp barrier), which
+   * happens-before the ticket increments issued after the second barrier — one MEMBAR per warp
+   * instead of one per thread.  The reader side needs no fence: its loads are control-dependent
+   * on the ticket value and go straight to L2 (ld.cg), where the reductions were performed.   */
+  __syncwarp();
+  if (lane == 0) __threadfence();
   __syncwarp();
   uint32_t ticket = 0;
   if (valid && leader && part == 0) ticket = atomicAdd(&arrived[uidx], (uint32_t)ngroups);
   ticket = __shfl_sync(0xffffffffu, ticket, my_group * TPL);
   const bool last = valid && leader && (ticket + (uint32_t)ngroups == cnt);
   if (!last) return;
-  __threadfence();
   bool do_upd = true;
   if (upd.kind == PS_UPD_FTRL) {                /* FtrlUpdater.java:52: `if (dw.get(0) == 0) return w` */
     const float S0 = __ldcg(acc + (size_t)uidx * Dp);
@@ -462,9 +466,14 @@ __global__ void __launch_bounds__(256) wide_forward_kernel(WideSlot* __restrict_
 }
 
 __global__ void __launch_bounds__(256) wide_update_all_kernel(WideSlot* __restrict__ slots, uint32_t C, UpdaterDev upd, const float* __restrict__ gbar,
-                                                              const int* __restrict__ skip_flag) {
+                                                              const int* __restrict__ skip_flag, float* __restrict__ bias, UpdaterDev bias_upd) {
   if (skip_flag != nullptr && *skip_flag != 0) return;
   const float g = *gbar;
+  if (bias != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && !(bias_upd.kind == PS_UPD_FTRL && g == 0.0f)) {
+    float w = bias[0], a = bias[1], b = bias[2];       /* "wide.bias" gets the same gbar (LRLayer.java:112-113) */
+    apply_elem(bias_upd, w, a, b, g);
+    bias[0] = w; bias[1] = a; bias[2] = b;
+  }
   if (upd.kind == PS_UPD_FTRL && g == 0.0f) return;   /* FtrlUpdater.java:52 */
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < C; s += gridDim.x * blockDim.x) {
     WideSlot r = slots[s];
@@ -501,9 +510,9 @@ void WideTable::forward(const int64_t* ids, int N, int F, const float* bias, flo
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }
-void WideTable::update_all(const float* gbar, const int* skip_flag) {
+void WideTable::update_all(const float* gbar, const int* skip_flag, float* bias, const ps_updater_spec* bias_upd) {
   const int grid = std::min<long>(ceil_div(C, 256), (long)ctx->num_sms * 8);
-  wide_update_all_kernel<<<grid, 256, 0, ctx->stream>>>(slots, (uint32_t)C, upd, gbar, skip_flag);
+  wide_update_all_kernel<<<grid, 256, 0, ctx->stream>>>(slots, (uint32_t)C, upd, gbar, skip_flag, bias, bias_upd ? make_updater_dev(*bias_upd) : upd);
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }

@@ -85,7 +85,7 @@ struct WideTable {
   void forward(const int64_t* ids, int N, int F, const float* bias, float* z);
   /* LRLayer.backward pushes the SAME batch-mean delta to every key ever seen (LRLayer.java:110-117,
    * SURVEY quirk 7): sweep all occupied slots and apply the updater with g = *gbar.             */
-  void update_all(const float* gbar, const int* skip_flag);
+  void update_all(const float* gbar, const int* skip_flag, float* bias /* {w,s1,s2} or null */, const ps_updater_spec* bias_upd);
   int64_t size();
   int get(int64_t id, float* w, float* s1, float* s2);   /* 0 = absent */
   void put(int64_t id, float w);

@@ -324,3 +324,68 @@ def test_pipelined_submit_equals_sync(ps, ctx):
         m.close()
         c2.close()
     assert np.allclose(losses[0], losses[1], rtol=1e-5, atol=1e-7)
+
+
+# --------------------------------------------------------------------------- TF32 tcgen05 path
+@pytest.mark.parametrize("M,N,K", [(128, 64, 32), (256, 256, 413), (4096, 256, 256), (100, 1, 256), (37, 10, 50), (300, 150, 784), (1, 8, 7)])
+def test_tf32_gemm_matches_fp64(ps, ctx, M, N, K):
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    B = rng.standard_normal((N, K)).astype(np.float32)
+    Kp = (K + 3) // 4 * 4                                   # TMA needs 16 B-aligned rows
+    Ap, Bp = np.zeros((M, Kp), np.float32), np.zeros((N, Kp), np.float32)
+    Ap[:, :K], Bp[:, :K] = A, B
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    c32 = ctx.gemm_nt(ps.PS_FC_FP32, Ap, Bp)
+    assert rel_err(c32, ref) <= 1e-5
+    ctf = ctx.gemm_nt(ps.PS_FC_TF32, Ap, Bp)
+    # TF32 keeps 10 mantissa bits of each operand (truncated): |err| <~ 2 * 2^-10 * sum|a||b|
+    bound = 2.5e-3 * (np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64).T)
+    assert np.all(np.abs(ctf - ref) <= bound + 1e-6), float(np.abs(ctf - ref).max())
+    # and exact when the operands are representable in TF32
+    At = (Ap.view(np.uint32) & 0xFFFFE000).view(np.float32)
+    Bt = (Bp.view(np.uint32) & 0xFFFFE000).view(np.float32)
+    ref_t = At.astype(np.float64) @ Bt.astype(np.float64).T
+    assert rel_err(ctx.gemm_nt(ps.PS_FC_TF32, At, Bt), ref_t) <= 1e-5   # fp32 accumulation over K
+
+
+@pytest.mark.parametrize("kind,F,D,Xn,fc,N,V", [
+    ("widedeep", 23, 16, 45, [256, 256, 256, 1], 1024, 50000),     # BASELINE config 2 network
+    ("dnn", 23, 10, 45, [150, 10, 1], 250, 3000),
+    ("widedeep", 5, 8, 3, [16, 1], 37, 60),
+])
+def test_model_steps_match_oracle_tf32(ps, ctx, kind, F, D, Xn, fc, N, V):
+    ctx.set_fc_precision(ps.PS_FC_TF32)
+    m = ps.Model(ctx, kind, F, D, Xn, fc, emb_capacity=1 << 17, max_batch=N)
+    o = ol.OracleModel(ol.KIND_WIDEDEEP if kind == "widedeep" else ol.KIND_DNN, F, D, Xn, fc, SEED)
+    syn = Synth(F=F, Xn=Xn, V=V, seed=11)
+    for it in range(3):
+        b = syn.batch(N)
+        lg = m.train_step(b["E"], b["X"], b["W"], b["Y"])
+        lo = o.train_step(b["E"], b["X"], b["W"], b["Y"])
+        assert abs(lg - lo) <= 2e-2 * max(1.0, abs(lo)), (it, lg, lo)
+        if it == 0:   # same parameters on both sides: activations and deltas agree to TF32 accuracy
+            for l in range(len(fc)):
+                assert rel_err(m.tap(f"fc{l}", 0), o.tap(f"fc{l}", 0)) <= 5e-3, f"fc{l}.A"
+                assert rel_err(m.tap(f"fc{l}", 1), o.tap(f"fc{l}", 1)) <= 1e-2, f"fc{l}.delta"
+    # Adam's first steps move every weight by ~alfa regardless of |g|, so sign flips of tiny
+    # gradients are visible: compare the bulk, not the worst element
+    for l in range(len(fc)):
+        wg, wo = m.get(f"fc{l}.weights"), o.get(f"fc{l}.weights")
+        assert np.mean(np.abs(wg - wo)) <= 2e-3 * np.mean(np.abs(wo)) + 1e-4, f"fc{l}.weights"
+    m.close()
+
+
+def test_fcnn_tf32(ps, ctx):
+    ctx.set_fc_precision(ps.PS_FC_TF32)
+    Xn, fc, N = 784, [150, 50, 10], 1024               # BASELINE config 5
+    m = ps.Model(ctx, "fcnn", 0, 0, Xn, fc, max_batch=N)
+    o = ol.OracleModel(ol.KIND_FCNN, 0, 0, Xn, fc, SEED)
+    b = Synth(F=0, Xn=Xn, V=0, seed=17, n_classes=10).batch(N)
+    lg = m.train_step(None, b["X"], None, b["Y"])
+    lo = o.train_step(None, b["X"], None, b["Y"])
+    assert abs(lg - lo) <= 1e-3 * max(1.0, abs(lo))
+    for l in range(3):
+        assert rel_err(m.tap(f"fc{l}", 0), o.tap(f"fc{l}", 0)) <= 5e-3
+        assert rel_err(m.tap(f"fc{l}", 1), o.tap(f"fc{l}", 1)) <= 1e-2
+    m.close()
