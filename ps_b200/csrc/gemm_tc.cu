@@ -306,6 +306,7 @@ void fc_tf32_init() {
 }
 
 void fc_forward_tf32(Ctx* ctx, const FcFwdArgs& a) {
+  fc_tf32_init();
   TcParams p{};
   p.M = a.B; p.N = a.out; p.K = a.in;
   p.C = a.Z; p.ldc = a.ldz; p.slab = 0; p.Ct = a.Zt; p.ldct = a.ldzt;
