@@ -418,7 +418,7 @@ int ps_model_phase_times(ps_model* m, float* ms, int cap, int* n, char* names, i
   if (ms && cap >= (int)v.size()) std::memcpy(ms, v.data(), sizeof(float) * v.size());
   if (names && names_cap > 0) {
     std::string s;
-    for (size_t i = 0; i < m->m.phase_names.size() && i < v.size(); ++i) { if (i) s += ";"; s += m->m.phase_names[i]; }
+    for (size_t i = 1; i < m->m.phase_names.size() && i - 1 < v.size(); ++i) { if (i > 1) s += ";"; s += m->m.phase_names[i]; }
     std::strncpy(names, s.c_str(), names_cap - 1); names[names_cap - 1] = 0;
   }
   PS_CATCH

@@ -94,6 +94,8 @@ void Model::create(Ctx* c, int kind_, int F_, int D_, int Xn_, const int32_t* fc
   }
   st_dev = dmalloc_zero<StepStatus>(1, s);
   tail_ws = dmalloc_zero<float>(kTailWorkspaceFloats, s);
+  ev_pool.resize(48);
+  for (auto& e : ev_pool) PS_CUDA(cudaEventCreate(&e));
   fc_tf32_init();
   for (auto& S : stage) {
     if (has_emb) S.E = dmalloc<int64_t>((size_t)Bmax * F);
@@ -127,32 +129,26 @@ void Model::destroy() {
     if (S.h2d_done) cudaEventDestroy(S.h2d_done);
     if (S.step_done) cudaEventDestroy(S.step_done);
   }
-  for (auto e : ev) cudaEventDestroy(e);
+  for (auto e : ev_pool) cudaEventDestroy(e);
+  ev_pool.clear();
   ctx = nullptr;
 }
 
 void Model::mark(const char* phase) {
-  if (!profile) return;
-  cudaEvent_t e;
-  PS_CUDA(cudaEventCreate(&e));
-  PS_CUDA(cudaEventRecord(e, ctx->stream));
-  ev.push_back(e);
-  phase_names.push_back(phase);
+  if (!profile || ev_n >= (int)ev_pool.size()) return;
+  PS_CUDA(cudaEventRecordWithFlags(ev_pool[ev_n], ctx->stream, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
+  ev_n++;
+  ev_names.push_back(phase);
 }
 void Model::finish_profile() {
-  if (!profile || ev.empty()) return;
+  if (!profile || phase_names.size() < 2) return;
   PS_CUDA(cudaStreamSynchronize(ctx->stream));
   phase_ms.clear();
-  std::vector<std::string> names;
-  for (size_t i = 1; i < ev.size(); ++i) {
+  for (size_t i = 1; i < phase_names.size(); ++i) {
     float ms = 0.f;
-    PS_CUDA(cudaEventElapsedTime(&ms, ev[i - 1], ev[i]));
+    PS_CUDA(cudaEventElapsedTime(&ms, ev_pool[i - 1], ev_pool[i]));
     phase_ms.push_back(ms);
-    names.push_back(phase_names[i]);
   }
-  for (auto e : ev) cudaEventDestroy(e);
-  ev.clear();
-  phase_names = names;
 }
 
 static const int* skip_ptr(const StepStatus* st) {
@@ -164,9 +160,14 @@ static const float* gbar_ptr(const StepStatus* st) {
 
 void Model::run_step(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, bool train, StepStatus* publish_to) {
   PS_REQUIRE(N > 0 && N <= Bmax, PS_ERR_ARG, "model: batch size must be in [1, max_batch]");
-  if (profile || !use_graph) { step_device(E, X, W, Y, N, train, publish_to); return; }
-  const auto key = std::make_tuple((const void*)E, (const void*)X, (const void*)W, (const void*)Y, N, train ? 1 : 0, (const void*)publish_to,
-                                   ctx->fc_precision);
+  if (!use_graph) {
+    ev_n = 0; ev_names.clear();
+    step_device(E, X, W, Y, N, train, publish_to);
+    phase_names = ev_names;
+    return;
+  }
+  const auto key = std::make_tuple((const void*)E, (const void*)X, (const void*)W, (const void*)Y, N, (train ? 1 : 0) | (profile ? 2 : 0),
+                                   (const void*)publish_to, ctx->fc_precision);
   auto it = graphs.find(key);
   if (it == graphs.end()) {
     if (graphs.size() >= 256) {
@@ -176,10 +177,13 @@ void Model::run_step(const int64_t* E, const float* X, const int64_t* W, const f
     const long l0 = ctx->launches;
     cudaGraph_t graph = nullptr;
     PS_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    capturing = true; ev_n = 0; ev_names.clear();
     try { step_device(E, X, W, Y, N, train, publish_to); }
-    catch (...) { cudaStreamEndCapture(ctx->stream, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+    catch (...) { capturing = false; cudaStreamEndCapture(ctx->stream, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+    capturing = false;
     PS_CUDA(cudaStreamEndCapture(ctx->stream, &graph));
     GraphEntry ge;
+    ge.names = ev_names;
     ge.kernels = ctx->launches - l0;
     ctx->launches = l0;
     PS_CUDA(cudaGraphInstantiate(&ge.exec, graph, 0));
@@ -188,13 +192,13 @@ void Model::run_step(const int64_t* E, const float* X, const int64_t* W, const f
   }
   PS_CUDA(cudaGraphLaunch(it->second.exec, ctx->stream));
   ctx->launches += it->second.kernels;
+  phase_names = it->second.names;
 }
 
 void Model::step_device(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, bool train, StepStatus* publish_to) {
   PS_REQUIRE(N > 0 && N <= Bmax, PS_ERR_ARG, "model: batch size must be in [1, max_batch]");
   cudaStream_t s = ctx->stream;
   const bool fp32 = ctx->fc_precision == PS_FC_FP32;
-  if (profile) { for (auto e : ev) cudaEventDestroy(e); ev.clear(); phase_names.clear(); }
   mark("begin");
   /* ---- forward (DNN.java:44-46) ---- */
   if (has_emb) {
@@ -216,8 +220,8 @@ void Model::step_device(const int64_t* E, const float* X, const int64_t* W, cons
     a.Z = act[l + 1]; a.ldz = ld[l + 1];
     a.Zt = (!fp32 && l + 1 < L) ? act_t[l + 1] : nullptr; a.ldzt = ldt;
     if (fp32) fc_forward_fp32(ctx, a); else fc_forward_tf32(ctx, a);
+    mark(("fc_fwd" + std::to_string(l)).c_str());
   }
-  mark("fc_fwd");
   if (kind == PS_MODEL_FCNN)
     tail_softmax(ctx, N, width[L], act[L], ld[L], Y, delta[L], ld[L], fp32 ? nullptr : delta_t[L], ldt, train ? 1 : 0, st_dev, tail_ws);
   else
@@ -237,6 +241,7 @@ void Model::step_device(const int64_t* E, const float* X, const int64_t* W, cons
     g.dlT = delta_t[l + 1]; g.AT = act_t[l]; g.ldt = ldt;
     g.G = fcs[l].G; g.ldg = fcs[l].ldw; g.slab = (size_t)fcs[l].out * fcs[l].ldw; g.nsplit = fcs[l].nsplit;
     if (fp32) fc_wgrad_fp32(ctx, g); else fc_wgrad_tf32(ctx, g);
+    mark(("fc_wgrad" + std::to_string(l)).c_str());
     FcDgradArgs d{};
     d.B = N; d.in = fcs[l].in; d.out = fcs[l].out;
     d.dl = delta[l + 1]; d.ldd = ld[l + 1]; d.W = fcs[l].W; d.ldw = fcs[l].ldw; d.Wt = fcs[l].Wt; d.ldwt = fcs[l].ldwt;
@@ -244,8 +249,8 @@ void Model::step_device(const int64_t* E, const float* X, const int64_t* W, cons
     d.n_cols = fcs[l].in; d.dX = delta[l]; d.ldx = ld[l];
     d.dXt = (!fp32 && l > 0) ? delta_t[l] : nullptr; d.ldxt = ldt;
     if (fp32) fc_dgrad_fp32(ctx, d); else fc_dgrad_tf32(ctx, d);
+    mark(("fc_dgrad" + std::to_string(l)).c_str());
   }
-  mark("fc_bwd");
   /* ---- KVStore.update + clear (Trainer.java:93,95) ---- */
   if (has_emb) { emb.scatter_update(delta[0], ld[0], act[0], ld[0], N, 2, skip_ptr(st_dev)); mark("emb_bwd_update"); }
   if (has_wide) {

@@ -56,7 +56,7 @@ struct Model {
   StepStatus* st_dev = nullptr;
   /* one CUDA graph per (input buffers, batch size, mode): a step is ~25 small launches, replayed as one */
   bool use_graph = true;
-  struct GraphEntry { cudaGraphExec_t exec = nullptr; long kernels = 0; };
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; long kernels = 0; std::vector<std::string> names; };
   std::map<std::tuple<const void*, const void*, const void*, const void*, int, int, const void*, int>, GraphEntry> graphs;
   /* two staging sets so the H2D of step i+1 overlaps the kernels of step i */
   struct Stage {
@@ -70,9 +70,12 @@ struct Model {
   int last_N = 0; bool last_train = false;
   StepStatus last_status{};
   /* per-phase device timing */
-  bool profile = false;
-  std::vector<cudaEvent_t> ev;
-  std::vector<std::string> phase_names;
+  /* per-phase device timing: event-record nodes INSIDE the step's CUDA graph (cudaEventRecordExternal),
+   * so the times are those of the graph-replayed kernels, not of host launch cadence */
+  bool profile = false, capturing = false;
+  std::vector<cudaEvent_t> ev_pool;
+  int ev_n = 0;
+  std::vector<std::string> ev_names, phase_names;
   std::vector<float> phase_ms;
 
   void create(Ctx* c, int kind_, int F_, int D_, int Xn_, const int32_t* fc_dims, int n_fc, int64_t emb_capacity,

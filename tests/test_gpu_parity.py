@@ -349,6 +349,11 @@ def test_tf32_gemm_matches_fp64(ps, ctx, M, N, K):
     assert rel_err(ctx.gemm_nt(ps.PS_FC_TF32, At, Bt), ref_t) <= 1e-5   # fp32 accumulation over K
 
 
+def fro_err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(1e-30, np.linalg.norm(b)))
+
+
 @pytest.mark.parametrize("kind,F,D,Xn,fc,N,V", [
     ("widedeep", 23, 16, 45, [256, 256, 256, 1], 1024, 50000),     # BASELINE config 2 network
     ("dnn", 23, 10, 45, [150, 10, 1], 250, 3000),
@@ -361,13 +366,30 @@ def test_model_steps_match_oracle_tf32(ps, ctx, kind, F, D, Xn, fc, N, V):
     syn = Synth(F=F, Xn=Xn, V=V, seed=11)
     for it in range(3):
         b = syn.batch(N)
+        W_before = [m.get(f"fc{l}.weights") for l in range(len(fc))] if it == 0 else None
         lg = m.train_step(b["E"], b["X"], b["W"], b["Y"])
         lo = o.train_step(b["E"], b["X"], b["W"], b["Y"])
         assert abs(lg - lo) <= 2e-2 * max(1.0, abs(lo)), (it, lg, lo)
-        if it == 0:   # same parameters on both sides: activations and deltas agree to TF32 accuracy
+        if it == 0:
+            # same parameters on both sides: activations agree to TF32 accuracy element-wise; deltas are
+            # compared in Frobenius norm (a ReLU whose pre-activation is ~0 may flip and move one element)
             for l in range(len(fc)):
                 assert rel_err(m.tap(f"fc{l}", 0), o.tap(f"fc{l}", 0)) <= 5e-3, f"fc{l}.A"
-                assert rel_err(m.tap(f"fc{l}", 1), o.tap(f"fc{l}", 1)) <= 1e-2, f"fc{l}.delta"
+                assert fro_err(m.tap(f"fc{l}", 1), o.tap(f"fc{l}", 1)) <= 2e-2, f"fc{l}.delta"
+            # and each dgrad GEMM against fp64 on ITS OWN inputs, to the TF32 truncation bound
+            for l in range(len(fc)):
+                d_in = (m.tap(f"fc{l + 1}", 1) if l + 1 < len(fc) else m.tap("addWideDeep", 1) if kind == "widedeep" else None)
+                if d_in is None:
+                    continue
+                out, inn = fc[l], W_before[l].size // fc[l]
+                Wm = W_before[l].reshape(inn, out).T.astype(np.float64)          # out x in (column-major on the wire)
+                d_in = d_in.reshape(N, out).astype(np.float64)
+                exp = d_in @ Wm
+                if l > 0:
+                    exp = exp * (m.tap(f"fc{l - 1}", 0).reshape(N, inn) > 0)
+                got = m.tap(f"fc{l}", 1).reshape(N, inn)
+                bound = 2.5e-3 * (np.abs(d_in) @ np.abs(Wm)) + 1e-9
+                assert np.all(np.abs(got - exp) <= bound), (l, float(np.abs(got - exp).max()))
     # Adam's first steps move every weight by ~alfa regardless of |g|, so sign flips of tiny
     # gradients are visible: compare the bulk, not the worst element
     for l in range(len(fc)):
@@ -387,5 +409,5 @@ def test_fcnn_tf32(ps, ctx):
     assert abs(lg - lo) <= 1e-3 * max(1.0, abs(lo))
     for l in range(3):
         assert rel_err(m.tap(f"fc{l}", 0), o.tap(f"fc{l}", 0)) <= 5e-3
-        assert rel_err(m.tap(f"fc{l}", 1), o.tap(f"fc{l}", 1)) <= 1e-2
+        assert fro_err(m.tap(f"fc{l}", 1), o.tap(f"fc{l}", 1)) <= 2e-2
     m.close()
