@@ -36,6 +36,7 @@ struct FcDgradArgs {
   const float* Wt; int ldwt;      /* [in][ldwt] transposed copy (TF32 path; may be null for fp32) */
   int act_below;                  /* activation of the layer below, whose output is Y */
   const float* Y; int ldy;        /* [B][ldy] */
+  const float* Yt; int ldyt;      /* transposed copy [in][ldyt] (TF32 path: coalesced read in the epilogue) */
   int n_cols;                     /* how many of the `in` columns are needed (F*D for the first layer) */
   float* dX; int ldx;             /* [B][ldx] */
   float* dXt; int ldxt;           /* optional transposed copy [in][ldxt] */

@@ -42,8 +42,7 @@ struct TcParams {
   float* C; long ldc; size_t slab;
   float* Ct; long ldct;        /* transposed copy Ct[n][m] or null */
   const float* bias; int act;  /* EPI_FWD */
-  const float* Y; long ldy;    /* EPI_DGRAD */
-  int epi;
+  const float* Yt; long ldyt;  /* EPI_DGRAD: activation of the layer below, TRANSPOSED [n][m] */
 };
 
 /* ---- PTX wrappers ------------------------------------------------------------------ */
@@ -81,16 +80,12 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
+__device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, uint32_t* r) {   /* caller waits with tcgen05.wait::ld */
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
         "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 /* shared-memory matrix descriptor, K-major, 128 B swizzle: rows are 128 B apart, 8-row groups
@@ -119,7 +114,7 @@ struct SmemLayout {
   static constexpr uint32_t TOTAL = BAR_OFF + 128 + 1024;   /* + barriers/tmem slot + manual 1024 B alignment slack */
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(128) gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                         const TcParams p) {
   using SL = SmemLayout<BLOCK_N>;
@@ -182,34 +177,59 @@ __global__ void __launch_bounds__(128) gemm_tf32_kernel(const __grid_constant__ 
   }
   __syncwarp();
 
-  /* ===== epilogue: warp w owns TMEM lanes [32w, 32w+32) = output rows m0 + 32w + lane ===== */
+  /* ===== epilogue: warp w owns TMEM lanes [32w, 32w+32) = output rows m0 + 32w + lane =====
+   * All TMEM loads of the tile are issued first; the epilogue operands (bias: warp-uniform; the
+   * activation of the layer below for its derivative: read from the TRANSPOSED copy, so the 32
+   * lanes = 32 consecutive rows read one 128 B line per column) are fetched while they fly.   */
+  constexpr int NCH = BLOCK_N / 16;
+  const int m = m0 + warp * 32 + lane;
+  const bool row_ok = m < p.M;
+  float* Cz = p.C + (size_t)blockIdx.z * p.slab;
+  const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0);
+  uint32_t r[NCH][16];
   if (num_kb > 0) {
     mbar_wait(tfull, 0);
     tc_fence_after();
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) tc_ld16_issue(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ch * 16), r[ch]);
+  } else {
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) r[ch][i] = 0u;
   }
-  const int m = m0 + warp * 32 + lane;
-  float* Cz = p.C + (size_t)blockIdx.z * p.slab;
-  const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0);
-#pragma unroll 1
-  for (int c = 0; c < BLOCK_N; c += 16) {
-    float v[16];
-    if (num_kb > 0) tc_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
-    else {
+  float e[NCH][16];
+  if (EPI == EPI_FWD) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { const int n = n0 + ch * 16 + i; e[ch][i] = n < p.N ? __ldg(p.bias + n) : 0.f; }
+  } else if (EPI == EPI_DGRAD) {
+    if (p.act != PS_ACT_NONE) {
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { const int n = n0 + ch * 16 + i; e[ch][i] = (row_ok && n < p.N) ? __ldg(p.Yt + (long)n * p.ldyt + m) : 0.f; }
     }
-    const int nb = n0 + c;
+  }
+  if (num_kb > 0) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int nb = n0 + ch * 16;
     if (nb >= p.N) continue;                   /* warp-uniform */
-    if (p.epi == EPI_FWD) {
+    float v[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) if (nb + i < p.N) v[i] = act_forward(p.act, __fadd_rn(v[i], __ldg(p.bias + nb + i)));
-    } else if (p.epi == EPI_DGRAD && p.act != PS_ACT_NONE) {
-      if (m < p.M) {
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[ch][i]);
+    if (EPI == EPI_FWD) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) if (nb + i < p.N) v[i] = act_backward(p.act, v[i], p.Y[(long)m * p.ldy + nb + i]);
+      for (int i = 0; i < 16; ++i) v[i] = act_forward(p.act, __fadd_rn(v[i], e[ch][i]));
+    } else if (EPI == EPI_DGRAD) {
+      if (p.act != PS_ACT_NONE) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = act_backward(p.act, v[i], e[ch][i]);
       }
     }
-    if (m < p.M) {
+    if (row_ok) {
       float* row = Cz + (long)m * p.ldc + nb;
       if (vec_ok && nb + 15 < p.N) {
 #pragma unroll
@@ -218,7 +238,7 @@ __global__ void __launch_bounds__(128) gemm_tf32_kernel(const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 16; ++i) if (nb + i < p.N) row[i] = v[i];
       }
-      if (p.Ct) {
+      if (EPI != EPI_WGRAD && p.Ct) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) if (nb + i < p.N) p.Ct[(long)(nb + i) * p.ldct + m] = v[i];
       }
@@ -271,7 +291,7 @@ const CUtensorMap& tensor_map(const float* ptr, int rows, int k_extent, long ld,
   return cache.emplace(key, m).first->second;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int EPI>
 void launch_tc(Ctx* ctx, const float* A, long lda, const float* B, long ldb, TcParams& p, int nsplit) {
   using SL = SmemLayout<BLOCK_N>;
   const CUtensorMap ta = tensor_map(A, p.M, p.K, lda, BM);
@@ -279,20 +299,23 @@ void launch_tc(Ctx* ctx, const float* A, long lda, const float* B, long ldb, TcP
   const int nkb = (p.K + BK - 1) / BK;
   p.kb_per_split = (nkb + nsplit - 1) / nsplit;
   dim3 grid(ceil_div(p.N, BLOCK_N), ceil_div(p.M, BM), nsplit);
-  gemm_tf32_kernel<BLOCK_N><<<grid, 128, SL::TOTAL, ctx->stream>>>(ta, tb, p);
+  gemm_tf32_kernel<BLOCK_N, EPI><<<grid, 128, SL::TOTAL, ctx->stream>>>(ta, tb, p);
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }
 
+template <int EPI>
 void dispatch_tc(Ctx* ctx, const float* A, long lda, const float* B, long ldb, TcParams& p, int nsplit) {
-  if (p.N <= 16) launch_tc<16>(ctx, A, lda, B, ldb, p, nsplit);
-  else if (p.N <= 32) launch_tc<32>(ctx, A, lda, B, ldb, p, nsplit);
-  else launch_tc<64>(ctx, A, lda, B, ldb, p, nsplit);
+  if (p.N <= 16) launch_tc<16, EPI>(ctx, A, lda, B, ldb, p, nsplit);
+  else if (p.N <= 32) launch_tc<32, EPI>(ctx, A, lda, B, ldb, p, nsplit);
+  else launch_tc<64, EPI>(ctx, A, lda, B, ldb, p, nsplit);
 }
 
 template <int BLOCK_N>
 void set_attr() {
-  PS_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<BLOCK_N>::TOTAL));
+  PS_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, EPI_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<BLOCK_N>::TOTAL));
+  PS_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, EPI_DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<BLOCK_N>::TOTAL));
+  PS_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, EPI_WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<BLOCK_N>::TOTAL));
 }
 
 }  // namespace
@@ -310,8 +333,8 @@ void fc_forward_tf32(Ctx* ctx, const FcFwdArgs& a) {
   TcParams p{};
   p.M = a.B; p.N = a.out; p.K = a.in;
   p.C = a.Z; p.ldc = a.ldz; p.slab = 0; p.Ct = a.Zt; p.ldct = a.ldzt;
-  p.bias = a.bias; p.act = a.act; p.epi = EPI_FWD;
-  dispatch_tc(ctx, a.A, a.lda, a.W, a.ldw, p, 1);
+  p.bias = a.bias; p.act = a.act;
+  dispatch_tc<EPI_FWD>(ctx, a.A, a.lda, a.W, a.ldw, p, 1);
 }
 
 void fc_dgrad_tf32(Ctx* ctx, const FcDgradArgs& a) {
@@ -319,16 +342,17 @@ void fc_dgrad_tf32(Ctx* ctx, const FcDgradArgs& a) {
   TcParams p{};
   p.M = a.B; p.N = a.n_cols; p.K = a.out;
   p.C = a.dX; p.ldc = a.ldx; p.slab = 0; p.Ct = a.dXt; p.ldct = a.ldxt;
-  p.act = a.act_below; p.Y = a.Y; p.ldy = a.ldy; p.epi = EPI_DGRAD;
-  dispatch_tc(ctx, a.dl, a.ldd, a.Wt, a.ldwt, p, 1);
+  p.act = a.act_below; p.Yt = a.Yt; p.ldyt = a.ldyt;
+  PS_REQUIRE(p.act == PS_ACT_NONE || p.Yt != nullptr, PS_ERR_ARG, "tf32 dgrad needs the transposed activation of the layer below");
+  dispatch_tc<EPI_DGRAD>(ctx, a.dl, a.ldd, a.Wt, a.ldwt, p, 1);
 }
 
 void fc_wgrad_tf32(Ctx* ctx, const FcWgradArgs& a) {
   PS_REQUIRE(a.dlT != nullptr && a.AT != nullptr, PS_ERR_ARG, "tf32 wgrad needs the transposed delta / activation copies");
   TcParams p{};
   p.M = a.out; p.N = a.in + 1; p.K = a.B;
-  p.C = a.G; p.ldc = a.ldg; p.slab = a.slab; p.Ct = nullptr; p.epi = EPI_WGRAD;
-  dispatch_tc(ctx, a.dlT, a.ldt, a.AT, a.ldt, p, a.nsplit);
+  p.C = a.G; p.ldc = a.ldg; p.slab = a.slab; p.Ct = nullptr;
+  dispatch_tc<EPI_WGRAD>(ctx, a.dlT, a.ldt, a.AT, a.ldt, p, a.nsplit);
 }
 
 }  // namespace psb

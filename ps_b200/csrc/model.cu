@@ -245,7 +245,7 @@ void Model::step_device(const int64_t* E, const float* X, const int64_t* W, cons
     FcDgradArgs d{};
     d.B = N; d.in = fcs[l].in; d.out = fcs[l].out;
     d.dl = delta[l + 1]; d.ldd = ld[l + 1]; d.W = fcs[l].W; d.ldw = fcs[l].ldw; d.Wt = fcs[l].Wt; d.ldwt = fcs[l].ldwt;
-    d.act_below = l > 0 ? fcs[l - 1].act : PS_ACT_NONE; d.Y = act[l]; d.ldy = ld[l];
+    d.act_below = l > 0 ? fcs[l - 1].act : PS_ACT_NONE; d.Y = act[l]; d.ldy = ld[l]; d.Yt = act_t[l]; d.ldyt = ldt;
     d.n_cols = fcs[l].in; d.dX = delta[l]; d.ldx = ld[l];
     d.dXt = (!fp32 && l > 0) ? delta_t[l] : nullptr; d.ldxt = ldt;
     if (fp32) fc_dgrad_fp32(ctx, d); else fc_dgrad_tf32(ctx, d);

@@ -115,6 +115,7 @@ __device__ __forceinline__ float4 shfl_f4(float4 v, int src) {
  * stores S/n by reference in KVStore.sum, pass 2 adds the n gradients again, divides by 2n, the
  * aliased sum doubles it and KVStore.update halves it: ((S/n) + S) / (2n).  calls == 1: S/n.  */
 __device__ __forceinline__ float emb_geff(float S, uint32_t n, int calls) {
+  if (S == 0.0f) return S;
   const float q = __fdiv_rn(S, (float)n);
   if (calls == 1) return q;
   return __fdiv_rn(__fadd_rn(q, S), (float)(2u * n));

@@ -23,14 +23,21 @@ inline UpdaterDev make_updater_dev(const ps_updater_spec& s) {
 }
 
 #if defined(__CUDACC__)
+/* IEEE division / square root with the trivial cases peeled off: a zero numerator (a ReLU-masked
+ * gradient element, an untouched moment) otherwise sends __fdiv_rn down its slow path, which
+ * dominated the instruction count of the update kernels.  b is positive wherever these are used,
+ * so 0 / b == 0 with the sign of the numerator, exactly what IEEE division returns.          */
+__device__ __forceinline__ float pdiv(float a, float b) { return a == 0.0f ? a : __fdiv_rn(a, b); }
+__device__ __forceinline__ float psqrt(float a) { return a == 0.0f ? a : __fsqrt_rn(a); }
+
 /* update/AdamUpdater.java:61-69.  m,v are the M/V maps' entries (zero until first touch). */
 __device__ __forceinline__ void adam_elem(const UpdaterDev& u, float& w, float& m, float& v, float g) {
   const float m_new = __fadd_rn(__fmul_rn(g, u.omb1), __fmul_rn(m, u.b));                 /* :61 */
   const float v_new = __fadd_rn(__fmul_rn(__fmul_rn(g, g), u.omb2), __fmul_rn(v, u.c));   /* :62 */
-  const float Mm = __fdiv_rn(m_new, u.omb1);                                               /* :63 */
-  const float Vv = __fdiv_rn(v_new, u.omb2);                                               /* :64 */
-  const float den = __fadd_rn(__fsqrt_rn(Vv), u.d);
-  const float stp = __fmul_rn(__fdiv_rn(Mm, den), -u.a);                                   /* :69 */
+  const float Mm = pdiv(m_new, u.omb1);                                                    /* :63 */
+  const float Vv = pdiv(v_new, u.omb2);                                                    /* :64 */
+  const float den = __fadd_rn(psqrt(Vv), u.d);
+  const float stp = __fmul_rn(pdiv(Mm, den), -u.a);                                        /* :69 */
   w = __fadd_rn(w, stp);
   m = m_new; v = v_new;
 }
@@ -43,11 +50,11 @@ __device__ __forceinline__ void ftrl_elem(const UpdaterDev& u, float& w, float& 
   } else {
     const float sign = z >= 0.0f ? 1.0f : -1.0f;
     const float num = -__fsub_rn(z, __fmul_rn(sign, u.c));
-    const float den = __fdiv_rn(__fadd_rn(u.d, __fadd_rn(u.b, __fsqrt_rn(n))), u.a);
+    const float den = __fdiv_rn(__fadd_rn(u.d, __fadd_rn(u.b, psqrt(n))), u.a);
     wn = __fdiv_rn(num, den);
   }
   const float g2 = __fmul_rn(g, g);
-  const float s = __fsub_rn(__fsqrt_rn(__fadd_rn(n, g2)), __fsqrt_rn(__fdiv_rn(n, u.a)));   /* :72, sic */
+  const float s = __fsub_rn(psqrt(__fadd_rn(n, g2)), psqrt(pdiv(n, u.a)));                  /* :72, sic */
   z = __fadd_rn(z, __fsub_rn(g, __fmul_rn(s, wn)));                                         /* :73 */
   n = __fadd_rn(n, g2);                                                                     /* :74 */
   w = wn;
