@@ -96,6 +96,8 @@ void Model::create(Ctx* c, int kind_, int F_, int D_, int Xn_, const int32_t* fc
   tail_ws = dmalloc_zero<float>(kTailWorkspaceFloats, s);
   ev_pool.resize(48);
   for (auto& e : ev_pool) PS_CUDA(cudaEventCreate(&e));
+  for (auto& a : aux) PS_CUDA(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+  for (auto& e : sync_ev) PS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   fc_tf32_init();
   for (auto& S : stage) {
     if (has_emb) S.E = dmalloc<int64_t>((size_t)Bmax * F);
@@ -131,6 +133,8 @@ void Model::destroy() {
   }
   for (auto e : ev_pool) cudaEventDestroy(e);
   ev_pool.clear();
+  for (auto& a : aux) if (a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); a = nullptr; }
+  for (auto& e : sync_ev) if (e) { cudaEventDestroy(e); e = nullptr; }
   ctx = nullptr;
 }
 
@@ -195,12 +199,29 @@ void Model::run_step(const int64_t* E, const float* X, const int64_t* W, const f
   phase_names = it->second.names;
 }
 
+namespace {
+struct StreamScope {   /* every launch helper reads ctx->stream: run a few of them on a side stream */
+  Ctx* c; cudaStream_t saved;
+  StreamScope(Ctx* ctx, cudaStream_t s) : c(ctx), saved(ctx->stream) { c->stream = s; }
+  ~StreamScope() { c->stream = saved; }
+};
+}  // namespace
+
+/* `to` waits for everything enqueued on `from` so far */
+void Model::fork(cudaStream_t from, cudaStream_t to) {
+  cudaEvent_t e = sync_ev[sync_n++ % 24];
+  PS_CUDA(cudaEventRecord(e, from));
+  PS_CUDA(cudaStreamWaitEvent(to, e, 0));
+}
+
 void Model::step_device(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, bool train, StepStatus* publish_to) {
   PS_REQUIRE(N > 0 && N <= Bmax, PS_ERR_ARG, "model: batch size must be in [1, max_batch]");
-  cudaStream_t s = ctx->stream;
+  cudaStream_t s = ctx->stream, s1 = aux[0], s2 = aux[1];
   const bool fp32 = ctx->fc_precision == PS_FC_FP32;
   mark("begin");
   /* ---- forward (DNN.java:44-46) ---- */
+  fork(s, s1);
+  if (has_wide) { StreamScope sc(ctx, s1); wide.forward(W, N, F, wide_bias, wide_z); }   /* LRLayer.forward beside the deep branch */
   if (has_emb) {
     emb.probe(E, nullptr, N);
     mark("emb_probe");
@@ -210,9 +231,9 @@ void Model::step_device(const int64_t* E, const float* X, const int64_t* W, cons
   } else {
     PS_CUDA(cudaMemcpy2DAsync(act[0], sizeof(float) * ld[0], X, sizeof(float) * Xn, sizeof(float) * Xn, N, cudaMemcpyDeviceToDevice, s));
   }
-  if (!fp32) { transpose_copy(ctx, act[0], ld[0], act_t[0], ldt, N, width[0]); }
   mark("x_concat");
-  if (has_wide) { wide.forward(W, N, F, wide_bias, wide_z); mark("wide_fwd"); }
+  fork(s, s2);
+  if (!fp32 && train) { StreamScope sc(ctx, s2); transpose_copy(ctx, act[0], ld[0], act_t[0], ldt, N, width[0]); }   /* only wgrad0 needs it */
   for (int l = 0; l < L; ++l) {
     FcFwdArgs a{};
     a.B = N; a.in = fcs[l].in; a.out = fcs[l].out;
@@ -222,6 +243,7 @@ void Model::step_device(const int64_t* E, const float* X, const int64_t* W, cons
     if (fp32) fc_forward_fp32(ctx, a); else fc_forward_tf32(ctx, a);
     mark(("fc_fwd" + std::to_string(l)).c_str());
   }
+  fork(s1, s);                                   /* wide_z */
   if (kind == PS_MODEL_FCNN)
     tail_softmax(ctx, N, width[L], act[L], ld[L], Y, delta[L], ld[L], fp32 ? nullptr : delta_t[L], ldt, train ? 1 : 0, st_dev, tail_ws);
   else
@@ -231,17 +253,24 @@ void Model::step_device(const int64_t* E, const float* X, const int64_t* W, cons
   if (!train) {
     if (has_emb) emb.clear_batch();
     if (publish_to) publish_status(ctx, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, publish_to);
+    fork(s2, s);
     return;
   }
-  /* ---- backward (DNN.java:64-68) ---- */
+  /* ---- backward (DNN.java:64-68): the dgrad chain is the critical path; each wgrad runs beside it ---- */
+  fork(s, s2);
+  if (has_wide) { StreamScope sc(ctx, s2); wide.update_all(gbar_ptr(st_dev), skip_ptr(st_dev), wide_bias, &upd_wide); }
   for (int l = L - 1; l >= 0; --l) {
-    FcWgradArgs g{};
-    g.B = N; g.in = fcs[l].in; g.out = fcs[l].out;
-    g.dl = delta[l + 1]; g.ldd = ld[l + 1]; g.A = act[l]; g.lda = ld[l];
-    g.dlT = delta_t[l + 1]; g.AT = act_t[l]; g.ldt = ldt;
-    g.G = fcs[l].G; g.ldg = fcs[l].ldw; g.slab = (size_t)fcs[l].out * fcs[l].ldw; g.nsplit = fcs[l].nsplit;
-    if (fp32) fc_wgrad_fp32(ctx, g); else fc_wgrad_tf32(ctx, g);
-    mark(("fc_wgrad" + std::to_string(l)).c_str());
+    fork(s, s1);                                 /* delta[l+1] (tail or dgrad(l+1)) is ready */
+    if (l == 0) fork(s2, s1);                    /* act_t[0] */
+    {
+      StreamScope sc(ctx, s1);
+      FcWgradArgs g{};
+      g.B = N; g.in = fcs[l].in; g.out = fcs[l].out;
+      g.dl = delta[l + 1]; g.ldd = ld[l + 1]; g.A = act[l]; g.lda = ld[l];
+      g.dlT = delta_t[l + 1]; g.AT = act_t[l]; g.ldt = ldt;
+      g.G = fcs[l].G; g.ldg = fcs[l].ldw; g.slab = (size_t)fcs[l].out * fcs[l].ldw; g.nsplit = fcs[l].nsplit;
+      if (fp32) fc_wgrad_fp32(ctx, g); else fc_wgrad_tf32(ctx, g);
+    }
     FcDgradArgs d{};
     d.B = N; d.in = fcs[l].in; d.out = fcs[l].out;
     d.dl = delta[l + 1]; d.ldd = ld[l + 1]; d.W = fcs[l].W; d.ldw = fcs[l].ldw; d.Wt = fcs[l].Wt; d.ldwt = fcs[l].ldwt;
@@ -252,25 +281,27 @@ void Model::step_device(const int64_t* E, const float* X, const int64_t* W, cons
     mark(("fc_dgrad" + std::to_string(l)).c_str());
   }
   /* ---- KVStore.update + clear (Trainer.java:93,95) ---- */
+  fork(s, s1);                                   /* every dgrad has read W / Wt: the dense update may overwrite them */
+  {
+    StreamScope sc(ctx, s1);
+    DenseUpdateArgs u{};
+    u.n_layers = L; u.N = N;
+    long first = 0;
+    for (int l = 0; l < L; ++l) {
+      DenseLayerDesc& q = u.l[l];
+      const FcLayer& f = fcs[l];
+      q.W = f.W; q.Wt = f.Wt; q.bias = f.bias; q.sW1 = f.sW1; q.sW2 = f.sW2; q.sb1 = f.sb1; q.sb2 = f.sb2;
+      q.G = f.G; q.slab = (size_t)f.out * f.ldw; q.nsplit = f.nsplit; q.out = f.out; q.in = f.in; q.ldw = f.ldw; q.ldwt = f.ldwt; q.ldg = f.ldw;
+      q.updW = make_updater_dev(f.updW); q.updB = make_updater_dev(f.updB);
+      q.first = first; first += (long)f.out * (f.in + 1);
+    }
+    u.total = first;
+    dense_update(ctx, u, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, publish_to);
+  }
   if (has_emb) { emb.scatter_update(delta[0], ld[0], act[0], ld[0], N, 2, skip_ptr(st_dev)); mark("emb_bwd_update"); }
-  if (has_wide) {
-    wide.update_all(gbar_ptr(st_dev), skip_ptr(st_dev), wide_bias, &upd_wide);
-    mark("wide_update");
-  }
-  DenseUpdateArgs u{};
-  u.n_layers = L; u.N = N;
-  long first = 0;
-  for (int l = 0; l < L; ++l) {
-    DenseLayerDesc& q = u.l[l];
-    const FcLayer& f = fcs[l];
-    q.W = f.W; q.Wt = f.Wt; q.bias = f.bias; q.sW1 = f.sW1; q.sW2 = f.sW2; q.sb1 = f.sb1; q.sb2 = f.sb2;
-    q.G = f.G; q.slab = (size_t)f.out * f.ldw; q.nsplit = f.nsplit; q.out = f.out; q.in = f.in; q.ldw = f.ldw; q.ldwt = f.ldwt; q.ldg = f.ldw;
-    q.updW = make_updater_dev(f.updW); q.updB = make_updater_dev(f.updB);
-    q.first = first; first += (long)f.out * (f.in + 1);
-  }
-  u.total = first;
-  dense_update(ctx, u, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, publish_to);
-  mark("dense_update");
+  fork(s1, s);
+  fork(s2, s);
+  mark("end");
 }
 
 void Model::submit(const HostBatch& b) {

@@ -54,6 +54,13 @@ struct Model {
   std::vector<int> width, ld;
   float *wide_z = nullptr, *P = nullptr, *tail_ws = nullptr;
   StepStatus* st_dev = nullptr;
+  /* side streams: independent kernels of a step (wide branch, weight gradients, dense update) run
+   * beside the critical chain probe → gather → fc forward → tail → dgrad chain → scatter/update;
+   * inside a capture they become parallel branches of the step graph */
+  cudaStream_t aux[2] = {nullptr, nullptr};
+  cudaEvent_t sync_ev[24] = {};
+  int sync_n = 0;
+  void fork(cudaStream_t from, cudaStream_t to);
   /* one CUDA graph per (input buffers, batch size, mode): a step is ~25 small launches, replayed as one */
   bool use_graph = true;
   struct GraphEntry { cudaGraphExec_t exec = nullptr; long kernels = 0; std::vector<std::string> names; };
