@@ -156,6 +156,39 @@ int ps_model_skipped_backward(ps_model* m, int* out);        /* DNN.java:58-63 e
 int ps_model_profile(ps_model* m, int enable);
 int ps_model_phase_times(ps_model* m, float* ms, int cap, int* n, char* names, int names_cap);
 
+/* ---- key-hash sharded table across the GPUs of one box (net/PSRouterClient.java:60-151) ----------
+ * One process per GPU.  PSRouterClient buckets keys by router.shard(key), sends one batched
+ * getList / updateList per shard and merges (PSRouterClient.java:60-85, 93-122); here the buckets
+ * travel in ONE all-to-all over NVLink per direction, issued by the host between these calls
+ * (ps_b200/sharded.py with torch.distributed; INTEGRATION.md shows the sequence).  All pointers
+ * in this group are DEVICE pointers; calls are asynchronous on the context's stream.
+ *   requester: ps_shard_route_dev → [all-to-all keys] → owner: ps_model_shard_lookup_dev →
+ *   [all-to-all rows] → requester: ps_model_shard_unpack_dev, ps_model_shard_dense_step_dev,
+ *   ps_model_shard_pack_grads_dev → [all-reduce grad buffer] [all-to-all row gradients] →
+ *   ps_model_shard_finish_dev, owner: ps_model_shard_apply_dev.
+ * Semantics: the R ranks together perform ONE Trainer step on the concatenated batch
+ * (thread = 1): an N-GPU step equals the 1-GPU step on the same global batch.   */
+/* owner(key) = ps_owner_of(pack(field, id), R) (include/ps_spec.h): a net/Router.java:5.  counts_dev[R]
+ * and cursor_dev[R] are int32 scratch (zeroed by the call); send_keys_dev[N*F] is grouped by owner,
+ * send_pos_dev[N*F] maps each lookup to its place in that order.                                      */
+int ps_shard_route_dev(ps_ctx* ctx, const int64_t* E_dev, int N, int F, int R, uint64_t* send_keys_dev, int32_t* send_pos_dev,
+                       int32_t* counts_dev, int32_t* cursor_dev);
+/* PServer.getList (net/PServer.java:102-117) for the keys this rank owns: rows_out_dev[n][Dp], ReLU applied */
+int ps_model_shard_lookup_dev(ps_model* m, const uint64_t* keys_dev, int n, float* rows_out_dev);
+int ps_model_shard_row_stride(ps_model* m, int* Dp);       /* floats per exchanged row (D rounded up to 4) */
+int ps_model_shard_unpack_dev(ps_model* m, const float* rows_dev, const int32_t* send_pos_dev, int N);
+/* concat + wide + FcLayer forward/backward on this rank's N samples; W_all_dev holds the wide ids of
+ * EVERY rank (the replicated wide table must learn them all, LRLayer.java:79)                          */
+int ps_model_shard_dense_step_dev(ps_model* m, const float* X_dev, const int64_t* W_local_dev, const int64_t* W_all_dev, int n_all,
+                                  const float* Y_dev, int N);
+/* the flat fp32 buffer [dense gradient sums | loss | gbar] to all-reduce (SUM) across ranks           */
+int ps_model_shard_grad_buffer(ps_model* m, float** buf_dev, int64_t* count);
+int ps_model_shard_pack_grads_dev(ps_model* m, const int32_t* send_pos_dev, int N, float* grads_send_dev);
+/* KVStore.update for dense keys and the wide branch with the GLOBAL batch mean (Trainer.java:93)      */
+int ps_model_shard_finish_dev(ps_model* m, int N_global, int R);
+/* PServer.push + psUpdate (net/PServer.java:164-214) for the rows this rank owns: fused scatter + update */
+int ps_model_shard_apply_dev(ps_model* m, const float* grads_recv_dev, int n);
+
 /* ---- test hooks -------------------------------------------------------------------- */
 /* C (M x N, row-major, ldc) = A (M x K, row-major, lda) * B^T (B is N x K, row-major, ldb),
  * through the FcLayer GEMM of the given precision mode.                                      */

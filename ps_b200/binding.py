@@ -86,6 +86,15 @@ SYMBOLS = {
     "ps_model_skipped_backward": (_i, [_vp, C.POINTER(_i)]),
     "ps_model_profile": (_i, [_vp, _i]),
     "ps_model_phase_times": (_i, [_vp, _vp, _i, C.POINTER(_i), C.c_char_p, _i]),
+    "ps_shard_route_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "ps_model_shard_lookup_dev": (_i, [_vp, _vp, _i, _vp]),
+    "ps_model_shard_row_stride": (_i, [_vp, C.POINTER(_i)]),
+    "ps_model_shard_unpack_dev": (_i, [_vp, _vp, _vp, _i]),
+    "ps_model_shard_dense_step_dev": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i]),
+    "ps_model_shard_grad_buffer": (_i, [_vp, _pp, C.POINTER(_i64)]),
+    "ps_model_shard_pack_grads_dev": (_i, [_vp, _vp, _i, _vp]),
+    "ps_model_shard_finish_dev": (_i, [_vp, _i, _i]),
+    "ps_model_shard_apply_dev": (_i, [_vp, _vp, _i]),
     "ps_test_gemm_nt": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i]),
 }
 

@@ -424,6 +424,73 @@ int ps_model_phase_times(ps_model* m, float* ms, int cap, int* n, char* names, i
   PS_CATCH
 }
 
+/* ---- sharded table ---- */
+int ps_shard_route_dev(ps_ctx* ctx, const int64_t* E_dev, int N, int F, int R, uint64_t* send_keys_dev, int32_t* send_pos_dev,
+                       int32_t* counts_dev, int32_t* cursor_dev) {
+  PS_TRY
+  PS_REQUIRE(ctx && E_dev && send_keys_dev && send_pos_dev && counts_dev && cursor_dev && N > 0 && F > 0 && R > 0, PS_ERR_ARG, "bad argument");
+  PS_CUDA(cudaMemsetAsync(counts_dev, 0, sizeof(int32_t) * R, ctx->c.stream));
+  PS_CUDA(cudaMemsetAsync(cursor_dev, 0, sizeof(int32_t) * R, ctx->c.stream));
+  shard_count(&ctx->c, E_dev, N, F, R, counts_dev);
+  shard_place(&ctx->c, E_dev, N, F, R, counts_dev, cursor_dev, send_keys_dev, send_pos_dev);
+  PS_CATCH
+}
+int ps_model_shard_lookup_dev(ps_model* m, const uint64_t* keys_dev, int n, float* rows_out_dev) {
+  PS_TRY
+  PS_REQUIRE(m && n >= 0, PS_ERR_ARG, "bad argument");
+  m->m.shard_emb_lookup(keys_dev, n, rows_out_dev);
+  PS_CATCH
+}
+int ps_model_shard_row_stride(ps_model* m, int* Dp) {
+  PS_TRY
+  PS_REQUIRE(m && Dp && m->m.has_emb, PS_ERR_ARG, "bad argument");
+  *Dp = m->m.emb.Dp;
+  PS_CATCH
+}
+int ps_model_shard_unpack_dev(ps_model* m, const float* rows_dev, const int32_t* send_pos_dev, int N) {
+  PS_TRY
+  PS_REQUIRE(m && rows_dev && send_pos_dev, PS_ERR_ARG, "bad argument");
+  m->m.shard_unpack_rows(rows_dev, send_pos_dev, N);
+  PS_CATCH
+}
+int ps_model_shard_dense_step_dev(ps_model* m, const float* X_dev, const int64_t* W_local_dev, const int64_t* W_all_dev, int n_all,
+                                  const float* Y_dev, int N) {
+  PS_TRY
+  PS_REQUIRE(m && X_dev && Y_dev, PS_ERR_ARG, "bad argument");
+  m->m.shard_dense_step(X_dev, W_local_dev, W_all_dev, n_all, Y_dev, N);
+  PS_CATCH
+}
+int ps_model_shard_grad_buffer(ps_model* m, float** buf_dev, int64_t* count) {
+  PS_TRY
+  PS_REQUIRE(m && buf_dev && count, PS_ERR_ARG, "bad argument");
+  if (!m->m.gsum) {
+    const DenseUpdateArgs u = m->m.dense_args(1);
+    m->m.gsum_len = u.total + 2;
+    m->m.gsum = dmalloc_zero<float>((size_t)m->m.gsum_len, m->m.ctx->stream);
+    PS_CUDA(cudaStreamSynchronize(m->m.ctx->stream));
+  }
+  *buf_dev = m->m.gsum; *count = m->m.gsum_len;
+  PS_CATCH
+}
+int ps_model_shard_pack_grads_dev(ps_model* m, const int32_t* send_pos_dev, int N, float* grads_send_dev) {
+  PS_TRY
+  PS_REQUIRE(m && send_pos_dev && grads_send_dev, PS_ERR_ARG, "bad argument");
+  m->m.shard_pack(send_pos_dev, N, grads_send_dev);
+  PS_CATCH
+}
+int ps_model_shard_finish_dev(ps_model* m, int N_global, int R) {
+  PS_TRY
+  PS_REQUIRE(m && N_global > 0 && R > 0, PS_ERR_ARG, "bad argument");
+  m->m.shard_finish(N_global, R);
+  PS_CATCH
+}
+int ps_model_shard_apply_dev(ps_model* m, const float* grads_recv_dev, int n) {
+  PS_TRY
+  PS_REQUIRE(m && n >= 0, PS_ERR_ARG, "bad argument");
+  m->m.shard_emb_apply(grads_recv_dev, n);
+  PS_CATCH
+}
+
 /* ---- test hook ---- */
 int ps_test_gemm_nt(ps_ctx* ctx, int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc) {
   PS_TRY

@@ -123,6 +123,39 @@ void dense_update(Ctx* ctx, const DenseUpdateArgs& a, const StepStatus* st, cons
   ctx->launches++;
 }
 
+__global__ void __launch_bounds__(256) dense_reduce_kernel(const __grid_constant__ DenseUpdateArgs a, const StepStatus* __restrict__ st,
+                                                           float* __restrict__ gsum) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx == 0) { gsum[a.total] = st->loss; gsum[a.total + 1] = st->gbar; }
+  if (idx >= a.total) return;
+  int li = 0;
+  while (li + 1 < a.n_layers && idx >= a.l[li + 1].first) ++li;
+  const DenseLayerDesc& L = a.l[li];
+  const long r = idx - L.first;
+  const int cols = L.in + 1;
+  const int o = (int)(r / cols), c = (int)(r - (long)o * cols);
+  float g = 0.0f;
+  for (int z = 0; z < L.nsplit; ++z) g = __fadd_rn(g, L.G[(size_t)z * L.slab + (size_t)o * L.ldg + c]);
+  gsum[idx] = g;
+}
+void dense_reduce(Ctx* ctx, const DenseUpdateArgs& a, const StepStatus* st, float* gsum) {
+  dense_reduce_kernel<<<ceil_div(a.total + 1, 256), 256, 0, ctx->stream>>>(a, st, gsum);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+}
+
+__global__ void shard_finish_scalars_kernel(StepStatus* st, const float* tail, int R) {
+  const float loss = __fdiv_rn(tail[0], (float)R);
+  st->loss = loss;
+  st->gbar = __fdiv_rn(tail[1], (float)R);
+  st->skip = (loss <= 0.01f || isnan(loss)) ? 1 : 0;
+}
+void shard_finish_scalars(Ctx* ctx, StepStatus* st, const float* gsum_tail, int R) {
+  shard_finish_scalars_kernel<<<1, 1, 0, ctx->stream>>>(st, gsum_tail, R);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+}
+
 __global__ void updater_apply_kernel(UpdaterDev u, float* w, float* s1, float* s2, const float* g, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;

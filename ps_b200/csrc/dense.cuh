@@ -55,6 +55,12 @@ void tail_softmax(Ctx* ctx, int N, int C, float* Z, int ldz, const float* Y, flo
                   StepStatus* st, float* ws);
 /* copies the status (plus table error flags) to mapped host memory */
 void publish_status(Ctx* ctx, StepStatus* st, const uint32_t* emb_counters, const uint32_t* wide_counters, StepStatus* host_mapped);
+/* sharded (multi-GPU) step: gsum[compact (o, c) index] = sum of the wgrad slabs, then [loss, gbar] at
+ * gsum[total], gsum[total+1] — ONE flat buffer the host all-reduces across ranks               */
+void dense_reduce(Ctx* ctx, const DenseUpdateArgs& a, const StepStatus* st, float* gsum);
+/* after the all-reduce (sum over R ranks of per-rank means): global loss / gbar / early-exit flag */
+void shard_finish_scalars(Ctx* ctx, StepStatus* st, const float* gsum_tail, int R);
+
 /* Updater.update on caller-provided device arrays (test hook for ps_updater_apply) */
 void updater_apply(Ctx* ctx, const UpdaterDev& u, float* w, float* s1, float* s2, const float* g, int n);
 /* out[c*ldo + r] = in[r*ldi + c]  (layout conversion at the get/put boundary) */

@@ -122,7 +122,7 @@ void Model::destroy() {
   for (auto p : delta_t) dfree(p);
   if (has_emb) emb.destroy();
   if (has_wide) { wide.destroy(); dfree(wide_bias); dfree(wide_z); dfree(P); }
-  dfree(st_dev); dfree(tail_ws);
+  dfree(st_dev); dfree(tail_ws); dfree(gsum);
   for (auto& g : graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
   graphs.clear();
   for (auto& S : stage) {
@@ -302,6 +302,103 @@ void Model::step_device(const int64_t* E, const float* X, const int64_t* W, cons
   fork(s1, s);
   fork(s2, s);
   mark("end");
+}
+
+/* ------------------------------------------------------------------ sharded step pieces */
+DenseUpdateArgs Model::dense_args(int N) {
+  DenseUpdateArgs u{};
+  u.n_layers = L; u.N = N;
+  long first = 0;
+  for (int l = 0; l < L; ++l) {
+    DenseLayerDesc& q = u.l[l];
+    const FcLayer& f = fcs[l];
+    q.W = f.W; q.Wt = f.Wt; q.bias = f.bias; q.sW1 = f.sW1; q.sW2 = f.sW2; q.sb1 = f.sb1; q.sb2 = f.sb2;
+    q.G = f.G; q.slab = (size_t)f.out * f.ldw; q.nsplit = f.nsplit; q.out = f.out; q.in = f.in; q.ldw = f.ldw; q.ldwt = f.ldwt; q.ldg = f.ldw;
+    q.updW = make_updater_dev(f.updW); q.updB = make_updater_dev(f.updB);
+    q.first = first; first += (long)f.out * (f.in + 1);
+  }
+  u.total = first;
+  return u;
+}
+
+void Model::shard_emb_lookup(const uint64_t* keys, int n, float* rows_out) {
+  PS_REQUIRE(has_emb, PS_ERR_STATE, "model has no embedding layer");
+  emb.probe_packed(keys, n);
+  if (n > 0) emb.gather(rows_out, emb.Dp, n, 1);
+}
+
+void Model::shard_unpack_rows(const float* rows, const int32_t* send_pos, int N) {
+  PS_REQUIRE(has_emb && N > 0 && N <= Bmax, PS_ERR_ARG, "shard_unpack_rows: bad batch");
+  shard_unpack(ctx, rows, send_pos, N, F, D, emb.Dp, act[0], ld[0]);
+}
+
+/* everything between the two exchanges: concat, wide branch, FcLayer forward, tail, FcLayer backward,
+ * then the per-rank gradient sums and scalars go into ONE flat buffer for the all-reduce.      */
+void Model::shard_dense_step(const float* X, const int64_t* W_local, const int64_t* W_all, int n_all, const float* Y, int N) {
+  PS_REQUIRE(N > 0 && N <= Bmax, PS_ERR_ARG, "model: batch size must be in [1, max_batch]");
+  cudaStream_t s = ctx->stream;
+  const bool fp32 = ctx->fc_precision == PS_FC_FP32;
+  if (has_emb) PS_CUDA(cudaMemcpy2DAsync(act[0] + F * D, sizeof(float) * ld[0], X, sizeof(float) * Xn, sizeof(float) * Xn, N, cudaMemcpyDeviceToDevice, s));
+  else PS_CUDA(cudaMemcpy2DAsync(act[0], sizeof(float) * ld[0], X, sizeof(float) * Xn, sizeof(float) * Xn, N, cudaMemcpyDeviceToDevice, s));
+  if (!fp32) transpose_copy(ctx, act[0], ld[0], act_t[0], ldt, N, width[0]);
+  if (has_wide) {
+    wide.insert(W_all, n_all);                     /* the union of every replica's keys */
+    wide.forward(W_local, N, F, wide_bias, wide_z);
+  }
+  for (int l = 0; l < L; ++l) {
+    FcFwdArgs a{};
+    a.B = N; a.in = fcs[l].in; a.out = fcs[l].out;
+    a.A = act[l]; a.lda = ld[l]; a.W = fcs[l].W; a.ldw = fcs[l].ldw; a.bias = fcs[l].bias; a.act = fcs[l].act;
+    a.Z = act[l + 1]; a.ldz = ld[l + 1];
+    a.Zt = (!fp32 && l + 1 < L) ? act_t[l + 1] : nullptr; a.ldzt = ldt;
+    if (fp32) fc_forward_fp32(ctx, a); else fc_forward_tf32(ctx, a);
+  }
+  if (kind == PS_MODEL_FCNN)
+    tail_softmax(ctx, N, width[L], act[L], ld[L], Y, delta[L], ld[L], fp32 ? nullptr : delta_t[L], ldt, 1, st_dev, tail_ws);
+  else
+    tail_binary(ctx, N, act[L], ld[L], has_wide ? wide_z : nullptr, Y, has_wide ? P : act[L], has_wide ? 1 : ld[L], delta[L], ld[L],
+                fp32 ? nullptr : delta_t[L], 1, st_dev, tail_ws);
+  for (int l = L - 1; l >= 0; --l) {
+    FcWgradArgs g{};
+    g.B = N; g.in = fcs[l].in; g.out = fcs[l].out;
+    g.dl = delta[l + 1]; g.ldd = ld[l + 1]; g.A = act[l]; g.lda = ld[l];
+    g.dlT = delta_t[l + 1]; g.AT = act_t[l]; g.ldt = ldt;
+    g.G = fcs[l].G; g.ldg = fcs[l].ldw; g.slab = (size_t)fcs[l].out * fcs[l].ldw; g.nsplit = fcs[l].nsplit;
+    if (fp32) fc_wgrad_fp32(ctx, g); else fc_wgrad_tf32(ctx, g);
+    FcDgradArgs d{};
+    d.B = N; d.in = fcs[l].in; d.out = fcs[l].out;
+    d.dl = delta[l + 1]; d.ldd = ld[l + 1]; d.W = fcs[l].W; d.ldw = fcs[l].ldw; d.Wt = fcs[l].Wt; d.ldwt = fcs[l].ldwt;
+    d.act_below = l > 0 ? fcs[l - 1].act : PS_ACT_NONE; d.Y = act[l]; d.ldy = ld[l]; d.Yt = act_t[l]; d.ldyt = ldt;
+    d.n_cols = fcs[l].in; d.dX = delta[l]; d.ldx = ld[l];
+    d.dXt = (!fp32 && l > 0) ? delta_t[l] : nullptr; d.ldxt = ldt;
+    if (fp32) fc_dgrad_fp32(ctx, d); else fc_dgrad_tf32(ctx, d);
+  }
+  const DenseUpdateArgs u = dense_args(N);
+  if (!gsum) { gsum_len = u.total + 2; gsum = dmalloc_zero<float>((size_t)gsum_len, s); }
+  dense_reduce(ctx, u, st_dev, gsum);
+  last_N = N; last_train = true;
+}
+
+void Model::shard_pack(const int32_t* send_pos, int N, float* grads_send) {
+  PS_REQUIRE(has_emb, PS_ERR_STATE, "model has no embedding layer");
+  shard_pack_grads(ctx, delta[0], ld[0], act[0], ld[0], send_pos, N, F, D, emb.Dp, grads_send);
+}
+
+/* gsum now holds the SUM over R ranks of per-rank batch sums / means: every replica applies the
+ * same global-batch update — N-GPU result == 1-GPU result on the concatenated batch */
+void Model::shard_finish(int N_global, int R) {
+  PS_REQUIRE(gsum != nullptr, PS_ERR_STATE, "shard_finish before shard_dense_step");
+  DenseUpdateArgs u = dense_args(N_global);
+  shard_finish_scalars(ctx, st_dev, gsum + u.total, R);
+  if (has_wide) wide.update_all(gbar_ptr(st_dev), skip_ptr(st_dev), wide_bias, &upd_wide);
+  for (int l = 0; l < L; ++l) { u.l[l].G = gsum + u.l[l].first; u.l[l].slab = 0; u.l[l].nsplit = 1; u.l[l].ldg = fcs[l].in + 1; }
+  dense_update(ctx, u, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, nullptr);
+}
+
+void Model::shard_emb_apply(const float* grads_recv, int n) {
+  PS_REQUIRE(has_emb, PS_ERR_STATE, "model has no embedding layer");
+  if (n > 0) emb.scatter_update(grads_recv, emb.Dp, nullptr, emb.Dp, n, 2, skip_ptr(st_dev), 1);
+  else emb.last_L = 0;
 }
 
 void Model::submit(const HostBatch& b) {

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "dense.cuh"
 #include "gemm.cuh"
+#include "shard.cuh"
 #include "table.cuh"
 
 namespace psb {
@@ -92,6 +93,15 @@ struct Model {
   void step_device(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, bool train, StepStatus* publish_to);
   /* the same through the graph cache (falls back to direct launches while profiling) */
   void run_step(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, bool train, StepStatus* publish_to);
+  /* ---- key-hash sharded (multi-GPU) step, split at the exchanges ---- */
+  float* gsum = nullptr; long gsum_len = 0;          /* flat [dense gradient sums | loss | gbar]: the all-reduce buffer */
+  DenseUpdateArgs dense_args(int N);
+  void shard_emb_lookup(const uint64_t* keys, int n, float* rows_out);                    /* owner: find-or-insert + gather */
+  void shard_unpack_rows(const float* rows, const int32_t* send_pos, int N);              /* requester: rows → act[0] */
+  void shard_dense_step(const float* X, const int64_t* W_local, const int64_t* W_all, int n_all, const float* Y, int N);
+  void shard_pack(const int32_t* send_pos, int N, float* grads_send);
+  void shard_finish(int N_global, int R);                                                 /* after the all-reduce of gsum */
+  void shard_emb_apply(const float* grads_recv, int n);                                   /* owner: scatter + update */
   void submit(const HostBatch& b);
   float collect();
   float read_loss();

@@ -53,6 +53,7 @@ __device__ __forceinline__ int emb_find_or_insert(EmbSlot* slots, uint32_t C, un
 /* One thread per lookup l = n*F + j.  Row creation follows KVStore.create (KVStore.java:168-190):
  * the creating thread draws the row from the deterministic initialiser of ps_spec.h; optimiser
  * state stays at the zero the arena was allocated with (AdamUpdater.initMandV, :76-84).        */
+/* F == 0: `ids` already holds packed keys (the owner side of the sharded exchange) */
 template <class IdT>
 __global__ void __launch_bounds__(256) emb_probe_kernel(EmbSlot* __restrict__ slots, uint32_t C, float* __restrict__ w, int Dp, int D,
                                                         const IdT* __restrict__ ids, int L, int F, uint64_t seed, float maxv,
@@ -60,8 +61,7 @@ __global__ void __launch_bounds__(256) emb_probe_kernel(EmbSlot* __restrict__ sl
                                                         uint32_t* __restrict__ counters) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= L) return;
-  const int field = l % F;
-  const unsigned long long key = ps_pack_key((uint32_t)field, (uint64_t)(int64_t)ids[l]);
+  const unsigned long long key = F > 0 ? ps_pack_key((uint32_t)(l % F), (uint64_t)(int64_t)ids[l]) : (unsigned long long)ids[l];
   bool inserted;
   const int slot = emb_find_or_insert(slots, C, key, &inserted);
   lk_slot[l] = slot;
@@ -164,12 +164,13 @@ __global__ void __launch_bounds__(256) emb_scatter_update_kernel(EmbSlot* __rest
     const size_t od = (size_t)n * ldd + j * D + part * 4, oa = (size_t)n * lda + j * D + part * 4;
     float dv[4] = {0.f, 0.f, 0.f, 0.f}, av[4] = {0.f, 0.f, 0.f, 0.f};
     if (ALIGNED) {
-      const float4 d4 = ld_f4(delta + od), a4 = ld_f4(act + oa);
+      const float4 d4 = ld_f4(delta + od);
+      const float4 a4 = act ? ld_f4(act + oa) : make_float4(1.f, 1.f, 1.f, 1.f);   /* act == null: the mask was applied by the sender */
       dv[0] = d4.x; dv[1] = d4.y; dv[2] = d4.z; dv[3] = d4.w;
       av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
     } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) if (part * 4 + i < D) { dv[i] = delta[od + i]; av[i] = act[oa + i]; }
+      for (int i = 0; i < 4; ++i) if (part * 4 + i < D) { dv[i] = delta[od + i]; av[i] = act ? act[oa + i] : 1.f; }
     }
     /* Relu.backward: dy *= (y > 0 ? 1 : 0)  (activations/Relu.java:14-19) */
     gk.x = __fmul_rn(dv[0], av[0] > 0.f ? 1.f : 0.f); gk.y = __fmul_rn(dv[1], av[1] > 0.f ? 1.f : 0.f);
@@ -312,50 +313,63 @@ void EmbTable::probe(const int64_t* ids_i64, const float* ids_f32, int N) {
   ctx->launches++;
 }
 
-template <int TPL>
-static void launch_gather(EmbTable& t, float* out, int ldo, int N) {
-  const long L = (long)N * t.F;
-  const bool aligned = (t.D % 4 == 0) && (ldo % 4 == 0) && ((uintptr_t)out % 16 == 0);
-  const int grid = ceil_div(L * TPL, 256);
-  if (aligned) emb_gather_kernel<TPL, true><<<grid, 256, 0, t.ctx->stream>>>(t.w, t.Dp, t.D, t.lk_slot, (int)L, t.F, out, ldo);
-  else emb_gather_kernel<TPL, false><<<grid, 256, 0, t.ctx->stream>>>(t.w, t.Dp, t.D, t.lk_slot, (int)L, t.F, out, ldo);
+void EmbTable::probe_packed(const uint64_t* keys, int n) {
+  reserve(n);
+  last_L = n;
+  PS_CUDA(cudaMemsetAsync(counters, 0, sizeof(uint32_t), ctx->stream));
+  if (n <= 0) return;
+  emb_probe_kernel<unsigned long long><<<ceil_div(n, 256), 256, 0, ctx->stream>>>(slots, (uint32_t)C, w, Dp, D, reinterpret_cast<const unsigned long long*>(keys), n, 0,
+                                                                                  ctx->seed, maxv, lk_slot, uniq_slot, counters);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
 }
 
-void EmbTable::gather(float* out, int ldo, int N) {
-  PS_REQUIRE((int64_t)N * F == last_L, PS_ERR_STATE, "embedding: gather without a matching probe");
+template <int TPL>
+static void launch_gather(EmbTable& t, float* out, int ldo, int N, int F) {
+  const long L = (long)N * F;
+  const bool aligned = (t.D % 4 == 0) && (ldo % 4 == 0) && ((uintptr_t)out % 16 == 0);
+  const int grid = ceil_div(L * TPL, 256);
+  if (aligned) emb_gather_kernel<TPL, true><<<grid, 256, 0, t.ctx->stream>>>(t.w, t.Dp, t.D, t.lk_slot, (int)L, F, out, ldo);
+  else emb_gather_kernel<TPL, false><<<grid, 256, 0, t.ctx->stream>>>(t.w, t.Dp, t.D, t.lk_slot, (int)L, F, out, ldo);
+}
+
+void EmbTable::gather(float* out, int ldo, int N, int F_eff) {
+  const int Fe = F_eff > 0 ? F_eff : F;
+  PS_REQUIRE((int64_t)N * Fe == last_L, PS_ERR_STATE, "embedding: gather without a matching probe");
   switch (tpl) {
-    case 1: launch_gather<1>(*this, out, ldo, N); break;
-    case 2: launch_gather<2>(*this, out, ldo, N); break;
-    case 4: launch_gather<4>(*this, out, ldo, N); break;
-    case 8: launch_gather<8>(*this, out, ldo, N); break;
-    case 16: launch_gather<16>(*this, out, ldo, N); break;
-    default: launch_gather<32>(*this, out, ldo, N); break;
+    case 1: launch_gather<1>(*this, out, ldo, N, Fe); break;
+    case 2: launch_gather<2>(*this, out, ldo, N, Fe); break;
+    case 4: launch_gather<4>(*this, out, ldo, N, Fe); break;
+    case 8: launch_gather<8>(*this, out, ldo, N, Fe); break;
+    case 16: launch_gather<16>(*this, out, ldo, N, Fe); break;
+    default: launch_gather<32>(*this, out, ldo, N, Fe); break;
   }
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }
 
 template <int TPL>
-static void launch_scatter(EmbTable& t, const float* delta, int ldd, const float* act, int lda, int N, int calls, const int* skip) {
-  const long L = (long)N * t.F;
+static void launch_scatter(EmbTable& t, const float* delta, int ldd, const float* act, int lda, int N, int F, int calls, const int* skip) {
+  const long L = (long)N * F;
   const bool aligned = (t.D % 4 == 0) && (ldd % 4 == 0) && (lda % 4 == 0) && ((uintptr_t)delta % 16 == 0) && ((uintptr_t)act % 16 == 0);
   const int grid = ceil_div(L * TPL, 256);
   if (aligned)
-    emb_scatter_update_kernel<TPL, true><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.w, t.s1, t.s2, t.Dp, t.D, t.lk_slot, N, t.F, delta, ldd, act, lda, t.acc, t.arrived, t.upd, calls, skip);
+    emb_scatter_update_kernel<TPL, true><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.w, t.s1, t.s2, t.Dp, t.D, t.lk_slot, N, F, delta, ldd, act, lda, t.acc, t.arrived, t.upd, calls, skip);
   else
-    emb_scatter_update_kernel<TPL, false><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.w, t.s1, t.s2, t.Dp, t.D, t.lk_slot, N, t.F, delta, ldd, act, lda, t.acc, t.arrived, t.upd, calls, skip);
+    emb_scatter_update_kernel<TPL, false><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.w, t.s1, t.s2, t.Dp, t.D, t.lk_slot, N, F, delta, ldd, act, lda, t.acc, t.arrived, t.upd, calls, skip);
 }
 
-void EmbTable::scatter_update(const float* delta, int ldd, const float* act, int lda, int N, int calls, const int* skip_flag) {
-  PS_REQUIRE((int64_t)N * F == last_L, PS_ERR_STATE, "embedding: backward without a matching forward");
+void EmbTable::scatter_update(const float* delta, int ldd, const float* act, int lda, int N, int calls, const int* skip_flag, int F_eff) {
+  const int Fe = F_eff > 0 ? F_eff : F;
+  PS_REQUIRE((int64_t)N * Fe == last_L, PS_ERR_STATE, "embedding: backward without a matching forward");
   PS_REQUIRE(calls == 1 || calls == 2, PS_ERR_ARG, "embedding: backward calls must be 1 or 2");
   switch (tpl) {
-    case 1: launch_scatter<1>(*this, delta, ldd, act, lda, N, calls, skip_flag); break;
-    case 2: launch_scatter<2>(*this, delta, ldd, act, lda, N, calls, skip_flag); break;
-    case 4: launch_scatter<4>(*this, delta, ldd, act, lda, N, calls, skip_flag); break;
-    case 8: launch_scatter<8>(*this, delta, ldd, act, lda, N, calls, skip_flag); break;
-    case 16: launch_scatter<16>(*this, delta, ldd, act, lda, N, calls, skip_flag); break;
-    default: launch_scatter<32>(*this, delta, ldd, act, lda, N, calls, skip_flag); break;
+    case 1: launch_scatter<1>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag); break;
+    case 2: launch_scatter<2>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag); break;
+    case 4: launch_scatter<4>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag); break;
+    case 8: launch_scatter<8>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag); break;
+    case 16: launch_scatter<16>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag); break;
+    default: launch_scatter<32>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag); break;
   }
   PS_LAUNCH_CHECK();
   ctx->launches++;
@@ -484,6 +498,17 @@ __global__ void __launch_bounds__(256) wide_update_all_kernel(WideSlot* __restri
   }
 }
 
+/* replicas of the wide table must know every key any rank has seen (LRLayer.weights never shrinks) */
+__global__ void __launch_bounds__(256) wide_insert_kernel(WideSlot* __restrict__ slots, uint32_t C, const int64_t* __restrict__ ids, int n,
+                                                          uint32_t* __restrict__ counters) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool inserted;
+  const int slot = wide_find_or_insert(slots, C, ps_pack_key(0u, (uint64_t)ids[i]), true, &inserted);
+  if (slot < 0) counters[0] = 1u;
+  else if (inserted) atomicAdd(reinterpret_cast<unsigned long long*>(counters + 2), 1ull);
+}
+
 __global__ void wide_get_kernel(WideSlot* slots, uint32_t C, int64_t id, float* out) {
   bool ins;
   const int slot = wide_find_or_insert(slots, C, ps_pack_key(0u, (uint64_t)id), false, &ins);
@@ -508,6 +533,12 @@ void WideTable::destroy() { dfree(slots); dfree(counters); slots = nullptr; coun
 
 void WideTable::forward(const int64_t* ids, int N, int F, const float* bias, float* z) {
   wide_forward_kernel<<<ceil_div((long)N * 32, 256), 256, 0, ctx->stream>>>(slots, (uint32_t)C, ids, N, F, bias, z, counters);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+}
+void WideTable::insert(const int64_t* ids, int n) {
+  if (n <= 0) return;
+  wide_insert_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(slots, (uint32_t)C, ids, n, counters);
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }

@@ -1,0 +1,109 @@
+"""GPU test of the key-hash sharded step (ps_b200/sharded.py + the ps_*_shard_* C ABI, NCCL):
+R ranks, each with a slice of the global batch, must reproduce the CPU oracle's single Trainer
+step (thread = 1) on the CONCATENATED batch — loss, dense weights, and the embedding rows held by
+whichever rank owns them.  R = 1 exercises every shard kernel on one GPU; R = 2 needs two."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+pytestmark = pytest.mark.gpu
+SEED = 20261017
+CFG = dict(kind="widedeep", F=23, D=16, Xn=45, fc=[64, 32, 1], N=192, V=4000, steps=3)
+
+
+def batches(R, cfg):
+    from ps_b200.synth import Synth
+    syn = Synth(F=cfg["F"], Xn=cfg["Xn"], V=cfg["V"], seed=31)
+    return [syn.batch(R * cfg["N"]) for _ in range(cfg["steps"])]
+
+
+def worker(rank, R, port, out, cfg, emb_opt):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=R, device_id=torch.device("cuda", rank))
+    from ps_b200 import binding as ps
+    from ps_b200.sharded import GpuOps, ShardedTrainer
+    ctx = ps.Context(rank, seed=SEED)
+    upd = ps.UpdaterSpec.ftrl() if emb_opt == "ftrl" else None
+    m = ps.Model(ctx, cfg["kind"], cfg["F"], cfg["D"], cfg["Xn"], cfg["fc"], emb_capacity=1 << 16, emb_updater=upd, max_batch=cfg["N"])
+    tr = ShardedTrainer(GpuOps(ps, ctx, m, rank), rank, R)
+    N = cfg["N"]
+    losses, keys = [], set()
+    for b in batches(R, cfg):
+        sl = slice(rank * N, (rank + 1) * N)
+        dev = {k: torch.from_numpy(np.ascontiguousarray(v[sl])).cuda(rank) for k, v in b.items()}
+        losses.append(tr.step(dev["E"], dev["X"], dev["W"] if cfg["kind"] == "widedeep" else None, dev["Y"]))
+        for n in range(0, R * N, 7):
+            for j in range(cfg["F"]):
+                keys.add((j, int(b["E"][n, j])))
+    import oracle_lib as ol
+    rows = {}
+    for (j, v) in sorted(keys):
+        k = ol.key_string(0, j, v)
+        w = m.get(k)
+        if w is not None:
+            rows[k] = (w, m.get_state(k, 0), m.get_state(k, 1))
+    dense = {f"fc{l}.{p}": m.get(f"fc{l}.{p}") for l in range(len(cfg["fc"])) for p in ("weights", "bias")}
+    wide = {}
+    if cfg["kind"] == "widedeep":
+        dense["wide.bias"] = m.get("wide.bias")
+        for n in range(0, R * N, 11):
+            k = ol.key_string(1, 0, int(b["W"][n, 3]))
+            wide[k] = m.get(k)
+    torch.save(dict(losses=losses, rows=rows, dense=dense, wide=wide, nkeys=m.num_keys()), os.path.join(out, f"r{rank}.pt"))
+    dist.barrier()
+    m.close()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("R,emb_opt", [(1, "adam"), (2, "adam"), (2, "ftrl")])
+def test_sharded_step_matches_oracle_global_batch(tmp_path, R, emb_opt):
+    if torch.cuda.device_count() < R:
+        pytest.skip(f"needs {R} GPUs")
+    import __graft_entry__ as g
+    g.build()
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    cfg = CFG
+    mp.spawn(worker, args=(R, port, str(tmp_path), cfg, emb_opt), nprocs=R, join=True)
+    res = [torch.load(os.path.join(tmp_path, f"r{r}.pt"), weights_only=False) for r in range(R)]
+    import oracle_lib as ol
+    o = ol.OracleModel(ol.KIND_WIDEDEEP, cfg["F"], cfg["D"], cfg["Xn"], cfg["fc"], SEED, emb_opt=1 if emb_opt == "ftrl" else 0)
+    lo = [o.train_step(b["E"], b["X"], b["W"], b["Y"]) for b in batches(R, cfg)]
+    for r in range(R):
+        assert np.allclose(res[r]["losses"], lo, rtol=5e-5, atol=1e-6), (r, res[r]["losses"], lo)
+        for k, v in res[r]["dense"].items():                     # every replica holds the same dense parameters
+            ov = o.get(k)
+            assert np.abs(v - ov).max() <= 1e-4 * max(1e-3, np.abs(ov).max()), (r, k)
+        for k, v in res[r]["wide"].items():
+            assert np.allclose(v, o.get(k), rtol=1e-3, atol=1e-6), (r, k)
+    merged = {}
+    for r in range(R):
+        for k, t in res[r]["rows"].items():
+            assert k not in merged, f"{k} lives on two shards"
+            merged[k] = t
+    assert len(merged) > 100
+    for k, (w, s1, s2) in merged.items():
+        assert np.allclose(w, o.get(k), rtol=5e-4, atol=2e-6), k
+        so = o.get_state(k, 0)
+        if so is not None:
+            assert np.allclose(s1, so, rtol=5e-4, atol=2e-6), k
+    # union of the shards = the oracle's key set
+    n_dense = 2 * len(cfg["fc"]) + 1
+    emb_wide_total = sum(res[r]["nkeys"] - n_dense for r in range(R))
+    n_wide = res[0]["nkeys"] - n_dense - len([1 for _ in ()])  # replicated wide table is counted on every rank
+    assert emb_wide_total >= o.num_keys() - n_dense
