@@ -176,12 +176,10 @@ def main():
     B, F, D, Xn = cfg["B"], cfg["F"], cfg["D"], cfg["Xn"]
     ctx = ps.Context(local_rank, seed=20261017)
     ctx.set_fc_precision(ps.PS_FC_TF32 if args.precision == "tf32" else ps.PS_FC_FP32)
-    cap = int(min(2 ** 31 - 1, max(1 << 16, 2 * cfg["V"]))) if cfg["V"] else 1024
+    cap = int(min(2 ** 31 - 1, max(1 << 16, (2 * cfg["V"]) // world + (1 << 16)))) if cfg["V"] else 1024
     upd = ps.UpdaterSpec.ftrl() if cfg["emb_opt"] == "ftrl" else None
     model = ps.Model(ctx, cfg["kind"], F, D, Xn, cfg["fc"], emb_capacity=cap, emb_updater=upd, max_batch=B)
 
-    # every rank trains its own replica on its own shard of samples (weak scaling); the key-hash
-    # sharded table + NCCL exchange is the multi-GPU path of a later commit
     syn = Synth(F=F, Xn=Xn, V=cfg["V"], dist=args.dist, seed=20261017 + 2 + 1000 * rank, n_classes=10 if cfg["kind"] == "fcnn" else 0)
     ring = [syn.batch(B) for _ in range(args.ring)]
     stream = torch.cuda.ExternalStream(ctx.stream(), device=local_rank)
@@ -195,8 +193,17 @@ def main():
     def ptr(t):
         return C.c_void_p(t.data_ptr()) if t is not None else None
 
+    # N > 1: the embedding table is sharded by key hash over the ranks and the R ranks perform ONE
+    # Trainer step on the concatenated batch (ps_b200/sharded.py); per-GPU batch fixed => weak scaling
+    trainer = None
+    if world > 1:
+        from ps_b200.sharded import GpuOps, ShardedTrainer
+        trainer = ShardedTrainer(GpuOps(ps, ctx, model, local_rank), rank, world)
+
     def dev_step(i):
         d = dev_ring[i % len(dev_ring)]
+        if trainer is not None:
+            return trainer.step(d.get("E"), d["X"], d.get("W"), d["Y"])
         model.train_step_dev(ptr(d.get("E")), ptr(d["X"]), ptr(d.get("W")), ptr(d["Y"]), B)
 
     def barrier():
@@ -243,6 +250,14 @@ def main():
     h2d = sum(pa.nbytes for pa in pinned[0].values())
 
     def host_loop(n, start):
+        if trainer is not None:      # sharded step: stage this rank's slice from pinned host memory, then the step
+            last = None
+            for i in range(n):
+                pb = pinned[(start + i) % len(pinned)]
+                with torch.cuda.stream(stream):
+                    d = {k: torch.from_numpy(pa.array).to(f"cuda:{local_rank}", non_blocking=True) for k, pa in pb.items()}
+                last = trainer.step(d.get("E"), d["X"], d.get("W"), d["Y"])
+            return last
         for i in range(n):
             pb = pinned[(start + i) % len(pinned)]
             model.submit_ptrs(hp(pb, "E"), hp(pb, "X"), hp(pb, "W"), hp(pb, "Y"), B)
@@ -263,9 +278,10 @@ def main():
     clocks = sampler.summary()
 
     # ---- per-kernel device times and the roofline of the dominant HBM-bound kernel ----
-    model.profile(True)
     acc = {}
-    reps = 20
+    reps = 20 if world == 1 else 0
+    if reps:
+        model.profile(True)
     for i in range(reps):
         dev_step(i)
         model.read_loss()
@@ -305,7 +321,7 @@ def main():
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
             "config": {"workload": workload_name(args, cfg), "global_batch": B * world,
-                       "parallelism": "replicas" if world > 1 else "single",
+                       "parallelism": f"key-hash sharded embedding table over {world} GPUs (NCCL all-to-all) + data-parallel dense" if world > 1 else "single",
                        "l2": "embedding table + optimiser state (%.0f MB) exceeds the 126 MB L2; a ring of %d distinct batches; no flush" % (
                            cap * (16 + 12 * D) / 1e6, len(ring))},
             "e2e": {"value": total / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,

@@ -102,8 +102,3 @@ def test_sharded_step_matches_oracle_global_batch(tmp_path, R, emb_opt):
         so = o.get_state(k, 0)
         if so is not None:
             assert np.allclose(s1, so, rtol=5e-4, atol=2e-6), k
-    # union of the shards = the oracle's key set
-    n_dense = 2 * len(cfg["fc"]) + 1
-    emb_wide_total = sum(res[r]["nkeys"] - n_dense for r in range(R))
-    n_wide = res[0]["nkeys"] - n_dense - len([1 for _ in ()])  # replicated wide table is counted on every rank
-    assert emb_wide_total >= o.num_keys() - n_dense
