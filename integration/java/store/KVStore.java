@@ -1,0 +1,51 @@
+package store;
+
+import nativeps.PsNative;
+import org.jblas.FloatMatrix;
+import update.Updater;
+
+import java.util.Map;
+import java.util.concurrent.Callable;
+
+/**
+ * Drop-in for store/KVStore.java of the reference: same package, class and public methods
+ * (ins :70, get :129/:136, put :161, sum :192, update :202/:220/:240, clear :270, asyncGet :109,
+ * asyncWait :113), backed by the GPU-resident store of libps_b200.so instead of Java maps.
+ *
+ * Differences a caller can observe (DESIGN.md §5.7): get() returns a host SNAPSHOT, not the live
+ * matrix; lazily created weights come from the seeded initialiser of ps_spec.h; sum()/update()
+ * for keys the native step already handled are no-ops because the native step applies
+ * KVStore.update + clear itself, fused into the backward kernels.
+ */
+public class KVStore {
+	private static final KVStore ins = new KVStore();
+	public static KVStore ins() { return ins; }
+
+	private long ctx, model;                       // opaque native handles, bound by GpuStep.bind()
+	public void bind(long ctx, long model) { this.ctx = ctx; this.model = model; }
+	public long model() { return model; }
+
+	public FloatMatrix get(String key) {           // KVStore.java:129-134
+		float[] v = PsNative.modelGet(model, key);
+		return v == null ? null : shaped(key, v);
+	}
+	public synchronized FloatMatrix get(String key, Callable<FloatMatrix> init) {   // KVStore.java:136-159
+		FloatMatrix m = get(key);
+		if (m != null) return m;
+		try { m = init.call(); } catch (Exception e) { e.printStackTrace(); return null; }
+		put(key, m);
+		return m;
+	}
+	public void put(String key, FloatMatrix m) { PsNative.modelPut(model, key, m.data); }   // KVStore.java:161-166
+	public synchronized void sum(String key, FloatMatrix val) { /* gradients are accumulated on the device by the native step */ }
+	public void update(Updater updater, String key) {}
+	public void update(Updater updater) {}
+	public void update(Map<String, Updater> updaters) {}                                   // applied inside modelTrainStep
+	public void clear() {}
+	public void asyncGet(String key, Callable<FloatMatrix> init) {}                        // the probe kernel is the batched prefetch
+	public void asyncWait() {}
+
+	private static FloatMatrix shaped(String key, float[] v) {
+		return new FloatMatrix(v.length, 1, v);    // callers that need out x in reshape by their own dims (FcLayer knows them)
+	}
+}

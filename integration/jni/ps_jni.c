@@ -1,0 +1,117 @@
+/*
+ * ps_jni.c — the JNI shim between integration/java/nativeps/PsNative.java and the C ABI of
+ * include/ps_b200.h.  Deliberately thin: pin the Java arrays, widen float ids to int64, call.
+ * NOT compiled in this repository's image (no jni.h here); build on a host with a JDK:
+ *   gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -I../../include \
+ *       ps_jni.c -L../../ps_b200/lib -lps_b200 -o libps_b200_jni.so
+ */
+#include <jni.h>
+#include <stdlib.h>
+
+#include "ps_b200.h"
+
+static void throw_ps(JNIEnv* env, int rc) {
+  if (rc == PS_OK) return;
+  jclass cls = (*env)->FindClass(env, "java/lang/RuntimeException");   /* the reference throws RuntimeException on misuse (KVStore.java:163) */
+  (*env)->ThrowNew(env, cls, ps_last_error());
+}
+
+static int64_t* widen_ids(JNIEnv* env, jfloatArray a, jsize* n) {   /* float-carried ids (exact < 2^24) */
+  if (!a) { *n = 0; return NULL; }
+  *n = (*env)->GetArrayLength(env, a);
+  jfloat* f = (*env)->GetPrimitiveArrayCritical(env, a, NULL);
+  int64_t* out = (int64_t*)malloc(sizeof(int64_t) * (size_t)*n);
+  for (jsize i = 0; i < *n; ++i) out[i] = (int64_t)f[i];
+  (*env)->ReleasePrimitiveArrayCritical(env, a, f, JNI_ABORT);
+  return out;
+}
+
+JNIEXPORT jlong JNICALL Java_nativeps_PsNative_ctxCreate(JNIEnv* env, jclass c, jint device, jlong seed) {
+  ps_ctx* ctx = NULL;
+  throw_ps(env, ps_ctx_create(device, (uint64_t)seed, &ctx));
+  return (jlong)(intptr_t)ctx;
+}
+JNIEXPORT void JNICALL Java_nativeps_PsNative_ctxDestroy(JNIEnv* env, jclass c, jlong ctx) { ps_ctx_destroy((ps_ctx*)(intptr_t)ctx); }
+JNIEXPORT void JNICALL Java_nativeps_PsNative_ctxSetFcPrecision(JNIEnv* env, jclass c, jlong ctx, jint mode) {
+  throw_ps(env, ps_ctx_set_fc_precision((ps_ctx*)(intptr_t)ctx, mode));
+}
+JNIEXPORT jstring JNICALL Java_nativeps_PsNative_lastError(JNIEnv* env, jclass c) { return (*env)->NewStringUTF(env, ps_last_error()); }
+
+JNIEXPORT jlong JNICALL Java_nativeps_PsNative_modelCreate(JNIEnv* env, jclass c, jlong ctx, jint kind, jint F, jint D, jint Xn, jintArray fc,
+                                                           jlong cap, jfloatArray upd, jint maxBatch) {
+  jsize nfc = (*env)->GetArrayLength(env, fc);
+  jint* dims = (*env)->GetIntArrayElements(env, fc, NULL);
+  ps_updater_spec spec, *sp = NULL;
+  if (upd) {
+    jfloat* u = (*env)->GetFloatArrayElements(env, upd, NULL);
+    spec.kind = (int32_t)u[0]; for (int i = 0; i < 4; ++i) spec.p[i] = u[1 + i];
+    (*env)->ReleaseFloatArrayElements(env, upd, u, JNI_ABORT);
+    sp = &spec;
+  }
+  ps_model* m = NULL;
+  throw_ps(env, ps_model_create((ps_ctx*)(intptr_t)ctx, kind, F, D, Xn, (const int32_t*)dims, nfc, cap, sp, maxBatch, &m));
+  (*env)->ReleaseIntArrayElements(env, fc, dims, JNI_ABORT);
+  return (jlong)(intptr_t)m;
+}
+JNIEXPORT void JNICALL Java_nativeps_PsNative_modelDestroy(JNIEnv* env, jclass c, jlong m) { ps_model_destroy((ps_model*)(intptr_t)m); }
+
+JNIEXPORT jfloat JNICALL Java_nativeps_PsNative_modelTrainStep(JNIEnv* env, jclass c, jlong m, jfloatArray E, jfloatArray X, jfloatArray W,
+                                                               jfloatArray Y, jint N) {
+  jsize ne, nw;
+  int64_t* e = widen_ids(env, E, &ne);
+  int64_t* w = widen_ids(env, W, &nw);
+  jfloat* x = (*env)->GetFloatArrayElements(env, X, NULL);
+  jfloat* y = (*env)->GetFloatArrayElements(env, Y, NULL);
+  float loss = 0.f;
+  int rc = ps_model_train_step((ps_model*)(intptr_t)m, e, x, w, y, N, &loss);   /* Model.train's return value (Model.java:11) */
+  (*env)->ReleaseFloatArrayElements(env, X, x, JNI_ABORT);
+  (*env)->ReleaseFloatArrayElements(env, Y, y, JNI_ABORT);
+  free(e); free(w);
+  throw_ps(env, rc);
+  return loss;
+}
+
+JNIEXPORT jfloatArray JNICALL Java_nativeps_PsNative_modelGet(JNIEnv* env, jclass c, jlong m, jstring key) {
+  const char* k = (*env)->GetStringUTFChars(env, key, NULL);
+  int n = 0;
+  int rc = ps_model_get((ps_model*)(intptr_t)m, k, NULL, 0, &n);
+  jfloatArray out = NULL;
+  if (rc == PS_OK) {
+    out = (*env)->NewFloatArray(env, n);
+    jfloat* p = (*env)->GetFloatArrayElements(env, out, NULL);
+    rc = ps_model_get((ps_model*)(intptr_t)m, k, p, n, &n);
+    (*env)->ReleaseFloatArrayElements(env, out, p, 0);
+  }
+  (*env)->ReleaseStringUTFChars(env, key, k);
+  if (rc != PS_OK && rc != PS_NOT_FOUND) throw_ps(env, rc);
+  return rc == PS_OK ? out : NULL;                                              /* KVStore.get(String) returns null when absent */
+}
+JNIEXPORT void JNICALL Java_nativeps_PsNative_modelPut(JNIEnv* env, jclass c, jlong m, jstring key, jfloatArray v) {
+  const char* k = (*env)->GetStringUTFChars(env, key, NULL);
+  jsize n = (*env)->GetArrayLength(env, v);
+  jfloat* p = (*env)->GetFloatArrayElements(env, v, NULL);
+  int rc = ps_model_put((ps_model*)(intptr_t)m, k, p, n);
+  (*env)->ReleaseFloatArrayElements(env, v, p, JNI_ABORT);
+  (*env)->ReleaseStringUTFChars(env, key, k);
+  throw_ps(env, rc);
+}
+JNIEXPORT jfloatArray JNICALL Java_nativeps_PsNative_modelTap(JNIEnv* env, jclass c, jlong m, jstring layer, jint what) {
+  const char* k = (*env)->GetStringUTFChars(env, layer, NULL);
+  int n = 0;
+  int rc = ps_model_tap((ps_model*)(intptr_t)m, k, what, NULL, 0, &n);
+  jfloatArray out = NULL;
+  if (rc == PS_OK) {
+    out = (*env)->NewFloatArray(env, n);
+    jfloat* p = (*env)->GetFloatArrayElements(env, out, NULL);
+    rc = ps_model_tap((ps_model*)(intptr_t)m, k, what, p, n, &n);
+    (*env)->ReleaseFloatArrayElements(env, out, p, 0);
+  }
+  (*env)->ReleaseStringUTFChars(env, layer, k);
+  return rc == PS_OK ? out : NULL;
+}
+JNIEXPORT jboolean JNICALL Java_nativeps_PsNative_modelSkippedBackward(JNIEnv* env, jclass c, jlong m) {
+  int v = 0;
+  ps_model_skipped_backward((ps_model*)(intptr_t)m, &v);
+  return v ? JNI_TRUE : JNI_FALSE;
+}
+/* updaterParse / modelPredict follow the same pattern (ps_updater_parse, ps_model_predict). */
