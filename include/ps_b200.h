@@ -34,9 +34,10 @@ extern "C" {
 #define PS_ERR_CAPACITY 507   /* embedding table full */
 #define PS_ERR_STATE 409      /* call sequence violated (e.g. backward before forward) */
 
-/* FcLayer arithmetic: fp32 FFMA (exact-mode, parity to ~1e-6) or TF32 tcgen05 tensor cores */
+/* FcLayer arithmetic: fp32 FFMA (exact mode), TF32 tcgen05 tensor cores, or 3xTF32 tcgen05 (fp32-grade) */
 #define PS_FC_FP32 0
 #define PS_FC_TF32 1
+#define PS_FC_TF32X3 2     /* tcgen05 with error-compensated operand split (3 MMAs per product): fp32-grade results */
 
 /* activations.* */
 #define PS_ACT_NONE 0
@@ -70,7 +71,7 @@ int ps_abi_version(void);
  * `seed` keys the deterministic replacement of the unseeded MatrixUtil.rand (ps_spec.h). */
 int ps_ctx_create(int device, uint64_t seed, ps_ctx** out);
 int ps_ctx_destroy(ps_ctx* ctx);
-int ps_ctx_set_fc_precision(ps_ctx* ctx, int mode);   /* PS_FC_FP32 | PS_FC_TF32 */
+int ps_ctx_set_fc_precision(ps_ctx* ctx, int mode);   /* PS_FC_FP32 | PS_FC_TF32 | PS_FC_TF32X3 */
 int ps_ctx_synchronize(ps_ctx* ctx);
 int ps_ctx_launch_count(ps_ctx* ctx, int64_t* out);   /* kernels this library launched so far */
 int ps_ctx_device_info(ps_ctx* ctx, char* name, int cap, int* sms, int* cc_major, int* cc_minor);

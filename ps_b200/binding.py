@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(ROOT, "ps_b200", "lib", "libps_b200.so")
 
 PS_OK, PS_NOT_FOUND = 0, 204
-PS_FC_FP32, PS_FC_TF32 = 0, 1
+PS_FC_FP32, PS_FC_TF32, PS_FC_TF32X3 = 0, 1, 2
 PS_UPD_ADAM, PS_UPD_FTRL, PS_UPD_SIMPLE = 0, 1, 2
 PS_MODEL_DNN, PS_MODEL_WIDEDEEP, PS_MODEL_FCNN = 0, 1, 2
 KINDS = {"dnn": PS_MODEL_DNN, "widedeep": PS_MODEL_WIDEDEEP, "fcnn": PS_MODEL_FCNN}

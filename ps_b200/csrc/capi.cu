@@ -67,7 +67,7 @@ int ps_ctx_destroy(ps_ctx* ctx) {
 }
 int ps_ctx_set_fc_precision(ps_ctx* ctx, int mode) {
   PS_TRY
-  PS_REQUIRE(ctx && (mode == PS_FC_FP32 || mode == PS_FC_TF32), PS_ERR_ARG, "ps_ctx_set_fc_precision: bad mode");
+  PS_REQUIRE(ctx && (mode == PS_FC_FP32 || mode == PS_FC_TF32 || mode == PS_FC_TF32X3), PS_ERR_ARG, "ps_ctx_set_fc_precision: bad mode");
   ctx->c.fc_precision = mode;
   PS_CATCH
 }
@@ -502,7 +502,10 @@ int ps_test_gemm_nt(ps_ctx* ctx, int mode, int M, int N, int K, const float* A, 
   PS_CUDA(cudaMemcpyAsync(dB, B, sizeof(float) * N * ldb, cudaMemcpyHostToDevice, st));
   FcFwdArgs a{};
   a.B = M; a.in = K; a.out = N; a.A = dA; a.lda = lda; a.W = dB; a.ldw = ldb; a.bias = dbias; a.act = PS_ACT_NONE; a.Z = dC; a.ldz = ldc;
-  if (mode == PS_FC_FP32) fc_forward_fp32(&ctx->c, a); else fc_forward_tf32(&ctx->c, a);
+  const int saved = ctx->c.fc_precision;
+  ctx->c.fc_precision = mode;
+  try { if (mode == PS_FC_FP32) fc_forward_fp32(&ctx->c, a); else fc_forward_tf32(&ctx->c, a); } catch (...) { ctx->c.fc_precision = saved; throw; }
+  ctx->c.fc_precision = saved;
   PS_CUDA(cudaMemcpyAsync(C, dC, sizeof(float) * M * ldc, cudaMemcpyDeviceToHost, st));
   PS_CUDA(cudaStreamSynchronize(st));
   dfree(dA); dfree(dB); dfree(dC); dfree(dbias);

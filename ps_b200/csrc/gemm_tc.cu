@@ -106,26 +106,30 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-template <int BLOCK_N>
+/* SPLIT (3xTF32): every stage also holds the residual tiles A_lo = A - tf32(A), B_lo = B - tf32(B) */
+template <int BLOCK_N, bool SPLIT>
 struct SmemLayout {
   static constexpr uint32_t A_BYTES = BM * BK * 4;
   static constexpr uint32_t B_BYTES = BLOCK_N * BK * 4;
-  static constexpr uint32_t BAR_OFF = STAGES * (A_BYTES + B_BYTES);
-  static constexpr uint32_t TOTAL = BAR_OFF + 128 + 1024;   /* + barriers/tmem slot + manual 1024 B alignment slack */
+  static constexpr uint32_t STAGE_BYTES = (SPLIT ? 2u : 1u) * (A_BYTES + B_BYTES);
+  static constexpr uint32_t BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr uint32_t TOTAL = BAR_OFF + 256 + 1024;   /* + barriers/tmem slot + manual 1024 B alignment slack */
 };
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, bool SPLIT>
 __global__ void __launch_bounds__(128) gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                         const TcParams p) {
-  using SL = SmemLayout<BLOCK_N>;
+  using SL = SmemLayout<BLOCK_N, SPLIT>;
   constexpr int TMEM_COLS = BLOCK_N <= 32 ? 32 : (BLOCK_N <= 64 ? 64 : (BLOCK_N <= 128 ? 128 : 256));
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t sA = base, sB = base + STAGES * SL::A_BYTES, bars = base + SL::BAR_OFF;
-  /* bars: full[STAGES] | empty[STAGES] | tmem_full | tmem slot */
-  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull = bars + 16 * STAGES, tslot = bars + 16 * STAGES + 8;
-  volatile uint32_t* tslot_gen = reinterpret_cast<volatile uint32_t*>(gen_base + SL::BAR_OFF + 16 * STAGES + 8);
+  /* stage s: [A | B | A_lo | B_lo] (the residual tiles only with SPLIT); all tile bases stay 1024 B aligned */
+  const uint32_t stage0 = base, bars = base + SL::BAR_OFF;
+  constexpr uint32_t OFF_B = SL::A_BYTES, OFF_ALO = SL::A_BYTES + SL::B_BYTES, OFF_BLO = 2 * SL::A_BYTES + SL::B_BYTES;
+  /* bars: full[STAGES] | empty[STAGES] | split[STAGES] | tmem_full | tmem slot */
+  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, split0 = bars + 16 * STAGES, tfull = bars + 24 * STAGES, tslot = bars + 24 * STAGES + 8;
+  volatile uint32_t* tslot_gen = reinterpret_cast<volatile uint32_t*>(gen_base + SL::BAR_OFF + 24 * STAGES + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BLOCK_N;
@@ -134,7 +138,7 @@ __global__ void __launch_bounds__(128) gemm_tf32_kernel(const __grid_constant__ 
   const int num_kb = max(0, min(nkb_total, kb_begin + p.kb_per_split) - kb_begin);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); mbar_init(split0 + 8 * s, 64); }
     mbar_init(tfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -156,24 +160,62 @@ __global__ void __launch_bounds__(128) gemm_tf32_kernel(const __grid_constant__ 
       mbar_wait(empty0 + 8 * s, ((kb / STAGES) & 1) ^ 1);
       mbar_expect_tx(full0 + 8 * s, SL::A_BYTES + SL::B_BYTES);
       const int k = (kb_begin + kb) * BK;
-      tma_load_2d(sA + s * SL::A_BYTES, &tmA, full0 + 8 * s, k, m0);
-      tma_load_2d(sB + s * SL::B_BYTES, &tmB, full0 + 8 * s, k, n0);
+      tma_load_2d(stage0 + s * SL::STAGE_BYTES, &tmA, full0 + 8 * s, k, m0);
+      tma_load_2d(stage0 + s * SL::STAGE_BYTES + OFF_B, &tmB, full0 + 8 * s, k, n0);
     }
   } else if (warp == 1 && lane == 0) {
     /* ===== MMA issuer ===== */
     constexpr uint32_t idesc = make_idesc_tf32(BM, BLOCK_N);
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % STAGES;
-      mbar_wait(full0 + 8 * s, (kb / STAGES) & 1);
+      mbar_wait((SPLIT ? split0 : full0) + 8 * s, (kb / STAGES) & 1);
       tc_fence_after();
-      const uint64_t ad = make_kmajor_sw128_desc(sA + s * SL::A_BYTES);
-      const uint64_t bd = make_kmajor_sw128_desc(sB + s * SL::B_BYTES);
+      const uint32_t st = stage0 + s * SL::STAGE_BYTES;
+      const uint64_t ad = make_kmajor_sw128_desc(st);
+      const uint64_t bd = make_kmajor_sw128_desc(st + OFF_B);
+      if (SPLIT) {
+        /* 3xTF32: the tensor core truncates each operand to its top 19 bits, so the raw tile IS the
+         * high part; a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi (small terms first), fp32 accumulate */
+        const uint64_t al = make_kmajor_sw128_desc(st + OFF_ALO);
+        const uint64_t bl = make_kmajor_sw128_desc(st + OFF_BLO);
 #pragma unroll
-      for (int k = 0; k < BK / UMMA_K; ++k)   /* advance 32 B inside the 128 B swizzle atom: +2 in the 16 B-unit address field */
-        tc_mma_tf32(tmem, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          tc_mma_tf32(tmem, al + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          tc_mma_tf32(tmem, ad + 2 * k, bl + 2 * k, idesc, 1u);
+          tc_mma_tf32(tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k)   /* advance 32 B inside the 128 B swizzle atom: +2 in the 16 B-unit address field */
+          tc_mma_tf32(tmem, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+      }
       tc_commit(empty0 + 8 * s);               /* frees the stage once these MMAs have read it */
     }
     if (num_kb > 0) tc_commit(tfull);          /* accumulator complete */
+  } else if (SPLIT && warp >= 2) {
+    /* ===== residual producers (64 threads): lo = x - tf32(x), element-wise, so the swizzled tile
+     * layout carries over byte for byte; generic-proxy stores are fenced for the async proxy ===== */
+    const int t = threadIdx.x - 64;
+    constexpr int CHUNKS = (int)((SL::A_BYTES + SL::B_BYTES) / 16);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % STAGES;
+      mbar_wait(full0 + 8 * s, (kb / STAGES) & 1);
+      uint8_t* src = gen_base + s * SL::STAGE_BYTES;
+      uint8_t* dst = src + OFF_ALO;
+#pragma unroll 4
+      for (int c = t; c < CHUNKS; c += 64) {
+        const float4 x = *reinterpret_cast<const float4*>(src + 16 * c);
+        float4 hi, lo;
+        hi.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); lo.x = x.x - hi.x;
+        hi.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); lo.y = x.y - hi.y;
+        hi.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); lo.z = x.z - hi.z;
+        hi.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); lo.w = x.w - hi.w;
+        *reinterpret_cast<float4*>(src + 16 * c) = hi;     /* explicit high part: exact in TF32 whatever the core's rounding */
+        *reinterpret_cast<float4*>(dst + 16 * c) = lo;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(split0 + 8 * s) : "memory");
+    }
   }
   __syncwarp();
 
@@ -291,31 +333,38 @@ const CUtensorMap& tensor_map(const float* ptr, int rows, int k_extent, long ld,
   return cache.emplace(key, m).first->second;
 }
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, bool SPLIT>
 void launch_tc(Ctx* ctx, const float* A, long lda, const float* B, long ldb, TcParams& p, int nsplit) {
-  using SL = SmemLayout<BLOCK_N>;
+  using SL = SmemLayout<BLOCK_N, SPLIT>;
   const CUtensorMap ta = tensor_map(A, p.M, p.K, lda, BM);
   const CUtensorMap tb = tensor_map(B, p.N, p.K, ldb, BLOCK_N);
   const int nkb = (p.K + BK - 1) / BK;
   p.kb_per_split = (nkb + nsplit - 1) / nsplit;
   dim3 grid(ceil_div(p.N, BLOCK_N), ceil_div(p.M, BM), nsplit);
-  gemm_tf32_kernel<BLOCK_N, EPI><<<grid, 128, SL::TOTAL, ctx->stream>>>(ta, tb, p);
+  gemm_tf32_kernel<BLOCK_N, EPI, SPLIT><<<grid, 128, SL::TOTAL, ctx->stream>>>(ta, tb, p);
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }
 
 template <int EPI>
 void dispatch_tc(Ctx* ctx, const float* A, long lda, const float* B, long ldb, TcParams& p, int nsplit) {
-  if (p.N <= 16) launch_tc<16, EPI>(ctx, A, lda, B, ldb, p, nsplit);
-  else if (p.N <= 32) launch_tc<32, EPI>(ctx, A, lda, B, ldb, p, nsplit);
-  else launch_tc<64, EPI>(ctx, A, lda, B, ldb, p, nsplit);
+  if (ctx->fc_precision == PS_FC_TF32X3) {
+    if (p.N <= 16) launch_tc<16, EPI, true>(ctx, A, lda, B, ldb, p, nsplit);
+    else if (p.N <= 32) launch_tc<32, EPI, true>(ctx, A, lda, B, ldb, p, nsplit);
+    else launch_tc<64, EPI, true>(ctx, A, lda, B, ldb, p, nsplit);
+  } else {
+    if (p.N <= 16) launch_tc<16, EPI, false>(ctx, A, lda, B, ldb, p, nsplit);
+    else if (p.N <= 32) launch_tc<32, EPI, false>(ctx, A, lda, B, ldb, p, nsplit);
+    else launch_tc<64, EPI, false>(ctx, A, lda, B, ldb, p, nsplit);
+  }
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool SPLIT>
 void set_attr() {
-  PS_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, EPI_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<BLOCK_N>::TOTAL));
-  PS_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, EPI_DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<BLOCK_N>::TOTAL));
-  PS_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, EPI_WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<BLOCK_N>::TOTAL));
+  const int bytes = (int)SmemLayout<BLOCK_N, SPLIT>::TOTAL;
+  PS_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, EPI_FWD, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  PS_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, EPI_DGRAD, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  PS_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, EPI_WGRAD, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
 }
 
 }  // namespace
@@ -323,7 +372,8 @@ void set_attr() {
 void fc_tf32_init() {
   static bool done = false;
   if (done) return;
-  set_attr<16>(); set_attr<32>(); set_attr<64>();
+  set_attr<16, false>(); set_attr<32, false>(); set_attr<64, false>();
+  set_attr<16, true>(); set_attr<32, true>(); set_attr<64, true>();
   encode_fn();
   done = true;
 }
