@@ -175,7 +175,7 @@ def main():
     torch.cuda.set_device(local_rank)
     B, F, D, Xn = cfg["B"], cfg["F"], cfg["D"], cfg["Xn"]
     ctx = ps.Context(local_rank, seed=20261017)
-    ctx.set_fc_precision(ps.PS_FC_TF32 if args.precision == "tf32" else ps.PS_FC_FP32)
+    ctx.set_fc_precision({"fp32": ps.PS_FC_FP32, "tf32": ps.PS_FC_TF32, "tf32x3": ps.PS_FC_TF32X3}[args.precision])
     cap = int(min(2 ** 31 - 1, max(1 << 16, (2 * cfg["V"]) // world + (1 << 16)))) if cfg["V"] else 1024
     upd = ps.UpdaterSpec.ftrl() if cfg["emb_opt"] == "ftrl" else None
     model = ps.Model(ctx, cfg["kind"], F, D, Xn, cfg["fc"], emb_capacity=cap, emb_updater=upd, max_batch=B)
@@ -291,22 +291,21 @@ def main():
     phase_us = {k: 1e3 * float(np.median(v)) for k, v in acc.items()}
     L = B * F
     uniq = float(np.mean([len(np.unique(b["E"] + (np.arange(F, dtype=np.int64) << 44)[None, :])) for b in ring])) if F else 0.0
-    alg = {                                                      # SURVEY.md §8(d) algorithmic bytes per launch
-        "emb_gather": L * (8 + 8 * D),
-        "emb_bwd_update": L * (8 + 4 * D) + uniq * 24 * D,
-    }
     hbm_peak, peak_src = peaks()
-    kernels = {}
-    for k, bytes_ in alg.items():
-        us = phase_us.get(k, 0.0) + (phase_us.get("emb_probe", 0.0) if k == "emb_gather" else 0.0)
-        if us > 0:
-            kernels[k] = {"us": us, "alg_bytes": bytes_, "gbs": bytes_ / us / 1e3}
-    dom = max(kernels, key=lambda k: kernels[k]["us"]) if kernels else None
-    roofline = None
-    if dom:
+    kernels, roofline = {}, None
+    if F and world == 1:
+        # each embedding kernel replayed 64x inside a CUDA graph over the batch ring, CUDA events on the library's stream
+        kt = model.kernel_times([d["E"].data_ptr() for d in dev_ring], B, reps=64)
+        alg = {"emb_gather": L * (8 + 8 * D), "emb_scatter_update": L * (8 + 4 * D) + uniq * 24 * D}
+        for k, bytes_ in alg.items():
+            us = kt[k] + (kt["emb_probe"] if k == "emb_gather" else 0.0)     # the gather's key resolution is the probe kernel
+            kernels[k] = {"us": us, "alg_bytes": bytes_, "gbs": bytes_ / max(us, 1e-3) / 1e3}
+        kernels["emb_probe"] = {"us": kt["emb_probe"]}
+        dom = max(alg, key=lambda k: kernels[k]["us"])
         roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
                     "frac": kernels[dom]["gbs"] / hbm_peak, "traffic": None, "peak_source": peak_src,
-                    "note": "emb_gather time includes the probe kernel that resolves the keys"}
+                    "how": "algorithmic bytes (SURVEY 8d) / mean device time of the kernel replayed 64x in a CUDA graph over the batch ring "
+                           "(CUDA events on the library's stream); emb_gather includes its probe kernel"}
 
     if rank == 0:
         cpu = None

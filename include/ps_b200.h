@@ -157,6 +157,12 @@ int ps_model_skipped_backward(ps_model* m, int* out);        /* DNN.java:58-63 e
 int ps_model_profile(ps_model* m, int enable);
 int ps_model_phase_times(ps_model* m, float* ms, int cap, int* n, char* names, int names_cap);
 
+/* measurement hook: average device microseconds of the embedding kernels of this model, each
+ * replayed `reps` times inside a CUDA graph over a ring of device-resident E batches and timed with
+ * CUDA events on the library's stream: us[4] = {probe, gather, scatter_update, clear_batch}.  The
+ * scatter_update repetitions apply real (meaningless) updates: call it after the timed training. */
+int ps_model_kernel_times(ps_model* m, const int64_t* const* E_dev_ring, int n_ring, int N, int reps, float* us);
+
 /* ---- key-hash sharded table across the GPUs of one box (net/PSRouterClient.java:60-151) ----------
  * One process per GPU.  PSRouterClient buckets keys by router.shard(key), sends one batched
  * getList / updateList per shard and merges (PSRouterClient.java:60-85, 93-122); here the buckets

@@ -86,6 +86,7 @@ SYMBOLS = {
     "ps_model_skipped_backward": (_i, [_vp, C.POINTER(_i)]),
     "ps_model_profile": (_i, [_vp, _i]),
     "ps_model_phase_times": (_i, [_vp, _vp, _i, C.POINTER(_i), C.c_char_p, _i]),
+    "ps_model_kernel_times": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "ps_shard_route_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "ps_model_shard_lookup_dev": (_i, [_vp, _vp, _i, _vp]),
     "ps_model_shard_row_stride": (_i, [_vp, C.POINTER(_i)]),
@@ -335,6 +336,13 @@ class Model:
         v = C.c_int()
         check(lib().ps_model_skipped_backward(self.h, C.byref(v)))
         return bool(v.value)
+
+    def kernel_times(self, E_ptrs, N, reps=64):
+        """device us of {probe, gather, scatter_update, clear_batch}; E_ptrs: device addresses of [N][F] int64 id batches"""
+        arr = (C.c_void_p * len(E_ptrs))(*E_ptrs)
+        us = np.zeros(4, np.float32)
+        check(lib().ps_model_kernel_times(self.h, arr, len(E_ptrs), N, reps, _p(us)))
+        return dict(zip(["emb_probe", "emb_gather", "emb_scatter_update", "emb_clear"], us.tolist()))
 
     def profile(self, enable=True):
         check(lib().ps_model_profile(self.h, 1 if enable else 0))

@@ -424,6 +424,13 @@ int ps_model_phase_times(ps_model* m, float* ms, int cap, int* n, char* names, i
   PS_CATCH
 }
 
+int ps_model_kernel_times(ps_model* m, const int64_t* const* E_dev_ring, int n_ring, int N, int reps, float* us) {
+  PS_TRY
+  PS_REQUIRE(m && E_dev_ring && us, PS_ERR_ARG, "null argument");
+  m->m.kernel_times(E_dev_ring, n_ring, N, reps, us);
+  PS_CATCH
+}
+
 /* ---- sharded table ---- */
 int ps_shard_route_dev(ps_ctx* ctx, const int64_t* E_dev, int N, int F, int R, uint64_t* send_keys_dev, int32_t* send_pos_dev,
                        int32_t* counts_dev, int32_t* cursor_dev) {

@@ -401,6 +401,50 @@ void Model::shard_emb_apply(const float* grads_recv, int n) {
   else emb.last_L = 0;
 }
 
+void Model::kernel_times(const int64_t* const* E_ring, int n_ring, int N, int reps, float* out) {
+  PS_REQUIRE(has_emb && n_ring > 0 && reps > 0 && N > 0 && N <= Bmax, PS_ERR_ARG, "kernel_times: bad argument");
+  PS_REQUIRE(in_flight == 0, PS_ERR_STATE, "kernel_times: steps in flight");
+  cudaStream_t s = ctx->stream;
+  cudaEvent_t e0, e1;
+  PS_CUDA(cudaEventCreate(&e0)); PS_CUDA(cudaEventCreate(&e1));
+  float total[4] = {0, 0, 0, 0};
+  for (int variant = 0; variant < 4; ++variant) {
+    /* 0: probe+clear   1: probe+gather+clear   2: probe+gather+scatter_update   3: probe+clear+clear */
+    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+    const long l0 = ctx->launches;
+    PS_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    try {
+      for (int r = 0; r < reps; ++r) {
+        emb.probe(E_ring[r % n_ring], nullptr, N);
+        if (variant == 1 || variant == 2) emb.gather(act[0], ld[0], N);
+        if (variant == 2) emb.scatter_update(delta[0], ld[0], act[0], ld[0], N, 2, nullptr);
+        else emb.clear_batch();
+        if (variant == 3) emb.clear_batch();
+      }
+    } catch (...) { cudaStreamEndCapture(s, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+    PS_CUDA(cudaStreamEndCapture(s, &graph));
+    const long per_graph = ctx->launches - l0;
+    PS_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+    PS_CUDA(cudaGraphLaunch(exec, s));                       /* warm-up */
+    PS_CUDA(cudaEventRecord(e0, s));
+    PS_CUDA(cudaGraphLaunch(exec, s));
+    PS_CUDA(cudaEventRecord(e1, s));
+    PS_CUDA(cudaStreamSynchronize(s));
+    ctx->launches += per_graph;
+    float ms = 0.f;
+    PS_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    total[variant] = 1e3f * ms / (float)reps;
+    cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  const float clear = total[3] - total[0];
+  out[0] = total[0] - clear;                 /* probe (includes the 4-byte counter memset node) */
+  out[1] = total[1] - total[0];              /* gather */
+  out[2] = total[2] - total[1] + clear;      /* scatter_update */
+  out[3] = clear;
+  emb.check_errors();
+}
+
 void Model::submit(const HostBatch& b) {
   PS_REQUIRE(in_flight < 2, PS_ERR_STATE, "model: two steps already in flight; collect first");
   PS_REQUIRE(b.N > 0 && b.N <= Bmax, PS_ERR_ARG, "model: batch size must be in [1, max_batch]");

@@ -102,6 +102,9 @@ struct Model {
   void shard_pack(const int32_t* send_pos, int N, float* grads_send);
   void shard_finish(int N_global, int R);                                                 /* after the all-reduce of gsum */
   void shard_emb_apply(const float* grads_recv, int n);                                   /* owner: scatter + update */
+  /* average device time (us) of the embedding kernels over `reps` graph-replayed repetitions on a ring
+   * of device batches: out = {probe, gather, scatter_update, clear_batch} (differences of four loops) */
+  void kernel_times(const int64_t* const* E_ring, int n_ring, int N, int reps, float* out);
   void submit(const HostBatch& b);
   float collect();
   float read_loss();
