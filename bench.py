@@ -301,6 +301,13 @@ def main():
             us = kt[k] + (kt["emb_probe"] if k == "emb_gather" else 0.0)     # the gather's key resolution is the probe kernel
             kernels[k] = {"us": us, "alg_bytes": bytes_, "gbs": bytes_ / max(us, 1e-3) / 1e3}
         kernels["emb_probe"] = {"us": kt["emb_probe"]}
+        gt = model.gemm_times(B, reps=64)
+        flops = {}
+        dims = [F * D + Xn] + list(cfg["fc"])
+        for l in range(len(cfg["fc"])):
+            for n in ("forward", "dgrad", "wgrad"):
+                us = gt[f"fc{l}.{n}"]
+                kernels[f"fc{l}.{n}"] = {"us": us, "tflops": 2.0 * B * dims[l] * dims[l + 1] / max(us, 1e-3) / 1e6}
         dom = max(alg, key=lambda k: kernels[k]["us"])
         roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
                     "frac": kernels[dom]["gbs"] / hbm_peak, "traffic": None, "peak_source": peak_src,
@@ -318,7 +325,7 @@ def main():
         line = {
             "metric": METRIC, "value": total / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
+            "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "f32 via 3xTF32 tcgen05"}[args.precision], "data": "synthetic",
             "config": {"workload": workload_name(args, cfg), "global_batch": B * world,
                        "parallelism": f"key-hash sharded embedding table over {world} GPUs (NCCL all-to-all) + data-parallel dense" if world > 1 else "single",
                        "l2": "embedding table + optimiser state (%.0f MB) exceeds the 126 MB L2; a ring of %d distinct batches; no flush" % (

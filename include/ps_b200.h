@@ -162,6 +162,8 @@ int ps_model_phase_times(ps_model* m, float* ms, int cap, int* n, char* names, i
  * CUDA events on the library's stream: us[4] = {probe, gather, scatter_update, clear_batch}.  The
  * scatter_update repetitions apply real (meaningless) updates: call it after the timed training. */
 int ps_model_kernel_times(ps_model* m, const int64_t* const* E_dev_ring, int n_ring, int N, int reps, float* us);
+/* the same for the FcLayer GEMMs (idempotent on the buffers of the last step): us[3*l + {0,1,2}] = {forward, dgrad, wgrad} of fc<l> */
+int ps_model_gemm_times(ps_model* m, int N, int reps, float* us, int cap);
 
 /* ---- key-hash sharded table across the GPUs of one box (net/PSRouterClient.java:60-151) ----------
  * One process per GPU.  PSRouterClient buckets keys by router.shard(key), sends one batched

@@ -87,6 +87,7 @@ SYMBOLS = {
     "ps_model_profile": (_i, [_vp, _i]),
     "ps_model_phase_times": (_i, [_vp, _vp, _i, C.POINTER(_i), C.c_char_p, _i]),
     "ps_model_kernel_times": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "ps_model_gemm_times": (_i, [_vp, _i, _i, _vp, _i]),
     "ps_shard_route_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "ps_model_shard_lookup_dev": (_i, [_vp, _vp, _i, _vp]),
     "ps_model_shard_row_stride": (_i, [_vp, C.POINTER(_i)]),
@@ -343,6 +344,11 @@ class Model:
         us = np.zeros(4, np.float32)
         check(lib().ps_model_kernel_times(self.h, arr, len(E_ptrs), N, reps, _p(us)))
         return dict(zip(["emb_probe", "emb_gather", "emb_scatter_update", "emb_clear"], us.tolist()))
+
+    def gemm_times(self, N, reps=64):
+        us = np.zeros(3 * len(self.fc), np.float32)
+        check(lib().ps_model_gemm_times(self.h, N, reps, _p(us), us.size))
+        return {f"fc{l}.{n}": float(us[3 * l + i]) for l in range(len(self.fc)) for i, n in enumerate(("forward", "dgrad", "wgrad"))}
 
     def profile(self, enable=True):
         check(lib().ps_model_profile(self.h, 1 if enable else 0))

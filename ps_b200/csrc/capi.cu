@@ -431,6 +431,13 @@ int ps_model_kernel_times(ps_model* m, const int64_t* const* E_dev_ring, int n_r
   PS_CATCH
 }
 
+int ps_model_gemm_times(ps_model* m, int N, int reps, float* us, int cap) {
+  PS_TRY
+  PS_REQUIRE(m && us && cap >= 3 * m->m.L, PS_ERR_ARG, "bad argument");
+  m->m.gemm_times(N, reps, us);
+  PS_CATCH
+}
+
 /* ---- sharded table ---- */
 int ps_shard_route_dev(ps_ctx* ctx, const int64_t* E_dev, int N, int F, int R, uint64_t* send_keys_dev, int32_t* send_pos_dev,
                        int32_t* counts_dev, int32_t* cursor_dev) {

@@ -445,6 +445,62 @@ void Model::kernel_times(const int64_t* const* E_ring, int n_ring, int N, int re
   emb.check_errors();
 }
 
+void Model::gemm_times(int N, int reps, float* out) {
+  PS_REQUIRE(reps > 0 && N > 0 && N <= Bmax, PS_ERR_ARG, "gemm_times: bad argument");
+  PS_REQUIRE(in_flight == 0, PS_ERR_STATE, "gemm_times: steps in flight");
+  cudaStream_t s = ctx->stream;
+  const bool fp32 = ctx->fc_precision == PS_FC_FP32;
+  cudaEvent_t e0, e1;
+  PS_CUDA(cudaEventCreate(&e0)); PS_CUDA(cudaEventCreate(&e1));
+  for (int l = 0; l < L; ++l)
+    for (int which = 0; which < 3; ++which) {
+      cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+      const long l0 = ctx->launches;
+      PS_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      try {
+        for (int r = 0; r < reps; ++r) {
+          if (which == 0) {
+            FcFwdArgs a{};
+            a.B = N; a.in = fcs[l].in; a.out = fcs[l].out;
+            a.A = act[l]; a.lda = ld[l]; a.W = fcs[l].W; a.ldw = fcs[l].ldw; a.bias = fcs[l].bias; a.act = fcs[l].act;
+            a.Z = act[l + 1]; a.ldz = ld[l + 1];
+            a.Zt = (!fp32 && l + 1 < L) ? act_t[l + 1] : nullptr; a.ldzt = ldt;
+            if (fp32) fc_forward_fp32(ctx, a); else fc_forward_tf32(ctx, a);
+          } else if (which == 1) {
+            FcDgradArgs d{};
+            d.B = N; d.in = fcs[l].in; d.out = fcs[l].out;
+            d.dl = delta[l + 1]; d.ldd = ld[l + 1]; d.W = fcs[l].W; d.ldw = fcs[l].ldw; d.Wt = fcs[l].Wt; d.ldwt = fcs[l].ldwt;
+            d.act_below = l > 0 ? fcs[l - 1].act : PS_ACT_NONE; d.Y = act[l]; d.ldy = ld[l]; d.Yt = act_t[l]; d.ldyt = ldt;
+            d.n_cols = fcs[l].in; d.dX = delta[l]; d.ldx = ld[l];
+            d.dXt = (!fp32 && l > 0) ? delta_t[l] : nullptr; d.ldxt = ldt;
+            if (fp32) fc_dgrad_fp32(ctx, d); else fc_dgrad_tf32(ctx, d);
+          } else {
+            FcWgradArgs g{};
+            g.B = N; g.in = fcs[l].in; g.out = fcs[l].out;
+            g.dl = delta[l + 1]; g.ldd = ld[l + 1]; g.A = act[l]; g.lda = ld[l];
+            g.dlT = delta_t[l + 1]; g.AT = act_t[l]; g.ldt = ldt;
+            g.G = fcs[l].G; g.ldg = fcs[l].ldw; g.slab = (size_t)fcs[l].out * fcs[l].ldw; g.nsplit = fcs[l].nsplit;
+            if (fp32) fc_wgrad_fp32(ctx, g); else fc_wgrad_tf32(ctx, g);
+          }
+        }
+      } catch (...) { cudaStreamEndCapture(s, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+      PS_CUDA(cudaStreamEndCapture(s, &graph));
+      const long per_graph = ctx->launches - l0;
+      PS_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+      PS_CUDA(cudaGraphLaunch(exec, s));
+      PS_CUDA(cudaEventRecord(e0, s));
+      PS_CUDA(cudaGraphLaunch(exec, s));
+      PS_CUDA(cudaEventRecord(e1, s));
+      PS_CUDA(cudaStreamSynchronize(s));
+      ctx->launches += per_graph;
+      float ms = 0.f;
+      PS_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      out[3 * l + which] = 1e3f * ms / (float)reps;
+      cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+    }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+}
+
 void Model::submit(const HostBatch& b) {
   PS_REQUIRE(in_flight < 2, PS_ERR_STATE, "model: two steps already in flight; collect first");
   PS_REQUIRE(b.N > 0 && b.N <= Bmax, PS_ERR_ARG, "model: batch size must be in [1, max_batch]");

@@ -105,6 +105,8 @@ struct Model {
   /* average device time (us) of the embedding kernels over `reps` graph-replayed repetitions on a ring
    * of device batches: out = {probe, gather, scatter_update, clear_batch} (differences of four loops) */
   void kernel_times(const int64_t* const* E_ring, int n_ring, int N, int reps, float* out);
+  /* the same for the FcLayer GEMMs on the buffers of the last step: out[3*l + {0,1,2}] = {forward, dgrad, wgrad} of layer l */
+  void gemm_times(int N, int reps, float* out);
   void submit(const HostBatch& b);
   float collect();
   float read_loss();

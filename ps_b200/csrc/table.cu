@@ -60,20 +60,33 @@ __global__ void __launch_bounds__(256) emb_probe_kernel(EmbSlot* __restrict__ sl
                                                         int32_t* __restrict__ lk_slot, uint32_t* __restrict__ uniq_slot,
                                                         uint32_t* __restrict__ counters) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= L) return;
-  const unsigned long long key = F > 0 ? ps_pack_key((uint32_t)(l % F), (uint64_t)(int64_t)ids[l]) : (unsigned long long)ids[l];
-  bool inserted;
-  const int slot = emb_find_or_insert(slots, C, key, &inserted);
-  lk_slot[l] = slot;
-  if (slot < 0) { counters[1] = 1u; return; }
-  if (inserted) {
-    float* row = w + (size_t)slot * Dp;
-    for (int d = 0; d < D; ++d) row[d] = ps_init_value(seed, key, (uint32_t)d, maxv);
-    atomicAdd(reinterpret_cast<unsigned long long*>(counters + 2), 1ull);
+  const int lane = threadIdx.x & 31;
+  int slot = -1;
+  bool first = false;
+  if (l < L) {
+    const unsigned long long key = F > 0 ? ps_pack_key((uint32_t)(l % F), (uint64_t)(int64_t)ids[l]) : (unsigned long long)ids[l];
+    bool inserted;
+    slot = emb_find_or_insert(slots, C, key, &inserted);
+    lk_slot[l] = slot;
+    if (slot < 0) counters[1] = 1u;
+    else {
+      if (inserted) {
+        float* row = w + (size_t)slot * Dp;
+        for (int d = 0; d < D; ++d) row[d] = ps_init_value(seed, key, (uint32_t)d, maxv);
+        atomicAdd(reinterpret_cast<unsigned long long*>(counters + 2), 1ull);
+      }
+      first = atomicAdd(&slots[slot].cnt, 1u) == 0u;   /* first occurrence in this batch: number the unique key */
+    }
   }
-  const uint32_t old = atomicAdd(&slots[slot].cnt, 1u);
-  if (old == 0u) {                      /* first occurrence in this batch: number the unique key */
-    const uint32_t u = atomicAdd(&counters[0], 1u);
+  /* one atomic per warp on the batch-wide unique counter instead of one per unique key */
+  const unsigned firsts = __ballot_sync(0xffffffffu, first);
+  if (firsts == 0u) return;
+  const int leader = __ffs(firsts) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(&counters[0], (uint32_t)__popc(firsts));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (first) {
+    const uint32_t u = base + (uint32_t)__popc(firsts & ((1u << lane) - 1u));
     slots[slot].uidx = u;
     uniq_slot[u] = (uint32_t)slot;
   }
