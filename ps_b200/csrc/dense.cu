@@ -70,16 +70,18 @@ void transpose_copy(Ctx* ctx, const float* in, int ldi, float* out, int ldo, int
  * gradient is the sum of the wgrad partial slabs divided by N: FcLayer.java:103 rowMeans and
  * :105 divi(N); KVStore.update's own division is by sumCnt = 1 (thread = 1).  Ftrl's early
  * return looks at element 0 of the key's gradient (FtrlUpdater.java:52).                     */
-__device__ __forceinline__ void publish(const StepStatus* st, const uint32_t* emb_counters, const uint32_t* wide_counters, StepStatus* host) {
+__device__ __forceinline__ void publish(StepStatus* st, const uint32_t* emb_counters, const uint32_t* wide_counters, StepStatus* host) {
   StepStatus s = *st;
   s.emb_err = emb_counters ? emb_counters[1] : 0u;
-  s.n_unique = emb_counters ? emb_counters[0] : 0u;
+  const uint32_t cur = emb_counters ? emb_counters[0] : 0u;     /* monotonic: this step's unique keys = the increment */
+  s.n_unique = cur - st->pad;
   s.wide_err = wide_counters ? wide_counters[0] : 0u;
+  st->pad = cur;
   *host = s;
   __threadfence_system();
 }
 
-__global__ void __launch_bounds__(256) dense_update_kernel(const __grid_constant__ DenseUpdateArgs a, const StepStatus* __restrict__ st,
+__global__ void __launch_bounds__(256) dense_update_kernel(const __grid_constant__ DenseUpdateArgs a, StepStatus* __restrict__ st,
                                                            const uint32_t* __restrict__ emb_counters, const uint32_t* __restrict__ wide_counters,
                                                            StepStatus* __restrict__ host) {
   if (host != nullptr && blockIdx.x == 0 && threadIdx.x == 0) publish(st, emb_counters, wide_counters, host);   /* status is final before the updates */
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(256) dense_update_kernel(const __grid_constant
     if (L.Wt) L.Wt[(size_t)c * L.ldwt + o] = w;
   }
 }
-void dense_update(Ctx* ctx, const DenseUpdateArgs& a, const StepStatus* st, const uint32_t* emb_counters, const uint32_t* wide_counters,
+void dense_update(Ctx* ctx, const DenseUpdateArgs& a, StepStatus* st, const uint32_t* emb_counters, const uint32_t* wide_counters,
                   StepStatus* host_mapped) {
   dense_update_kernel<<<ceil_div(a.total, 256), 256, 0, ctx->stream>>>(a, st, emb_counters, wide_counters, host_mapped);
   PS_LAUNCH_CHECK();
@@ -286,6 +288,115 @@ __global__ void __launch_bounds__(kTailThreads) tail_softmax_kernel(int N, int C
 void tail_softmax(Ctx* ctx, int N, int C, float* Z, int ldz, const float* Y, float* d_out, int ldd, float* dt_out, int ldt, int train,
                   StepStatus* st, float* ws) {
   tail_softmax_kernel<<<tail_blocks(N), kTailThreads, 0, ctx->stream>>>(N, C, Z, ldz, Y, d_out, ldd, dt_out, ldt, train, st, ws);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+}
+
+/* ------------------------------------------------------------------ the 1-unit top FcLayer on CUDA cores
+ * With out = 1 (FcLayer.build's last layer in DNN / WideDeepNN, FcLayer.java:53-70) the three
+ * contractions are a GEMV, a rank-1 outer product and a weighted column sum: memory-trivial, no
+ * tensor-core shape.  Fusing the forward GEMV with the tail takes two launches off the critical path. */
+__global__ void __launch_bounds__(kTailThreads) fc1_forward_tail_kernel(int N, int in, const float* __restrict__ A, int lda, const float* __restrict__ w,
+                                                                        const float* __restrict__ bias, const float* __restrict__ zwide,
+                                                                        const float* __restrict__ Y, float* __restrict__ z_out, int ldz,
+                                                                        float* __restrict__ p_out, int ldp, float* __restrict__ d_out, int ldd,
+                                                                        float* __restrict__ dt_out, int train, StepStatus* __restrict__ st,
+                                                                        float* __restrict__ ws) {
+  __shared__ float sh[kTailThreads];
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const bool vec = (in % 4 == 0) && (lda % 4 == 0);
+  float loss_part = 0.0f, d_part = 0.0f;
+  for (int n = warp; n < N; n += nwarps) {
+    const float* a = A + (size_t)n * lda;
+    float acc = 0.0f;
+    if (vec) {
+      for (int c = lane * 4; c < in; c += 128) {
+        const float4 x = ld_f4(a + c), y = __ldg(reinterpret_cast<const float4*>(w + c));
+        acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+      }
+    } else {
+      for (int c = lane; c < in; c += 32) acc = fmaf(a[c], __ldg(w + c), acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      float z = __fadd_rn(acc, bias[0]);                                       /* FcLayer.java:76-77 */
+      z_out[(size_t)n * ldz] = z;
+      if (zwide) z = __fadd_rn(z, zwide[n]);                                   /* AddLayer.java:36 */
+      const float p = sigmoid_clipped(z);                                      /* Sigmoid.java:11 */
+      p_out[(size_t)n * ldp] = p;
+      if (train) {
+        const float l = Y[n];
+        const float omp = __fsub_rn(1.0f, p);
+        loss_part = __fadd_rn(loss_part, (float)((double)(-l) * log((double)p) - ((double)__fsub_rn(1.0f, l) * log((double)omp))));
+        float d = __fdiv_rn(__fsub_rn(p, l), __fmul_rn(p, omp));                /* CrossEntropy.java:25 */
+        d = __fmul_rn(d, __fmul_rn(p, omp));                                   /* Sigmoid.java:18 */
+        d_out[(size_t)n * ldd] = d;
+        if (dt_out) dt_out[n] = d;
+        d_part = __fadd_rn(d_part, d);
+      }
+    }
+  }
+  if (!train) return;
+  tail_finish(loss_part, d_part, N, ws, st, sh);
+}
+void fc1_forward_tail(Ctx* ctx, int N, int in, const float* A, int lda, const float* w, const float* bias, const float* zwide, const float* Y,
+                      float* z_out, int ldz, float* p_out, int ldp, float* d_out, int ldd, float* dt_out, int train, StepStatus* st, float* ws) {
+  const int blocks = std::max(1, std::min(kTailMaxBlocks, ceil_div((long)N * 32, kTailThreads)));
+  fc1_forward_tail_kernel<<<blocks, kTailThreads, 0, ctx->stream>>>(N, in, A, lda, w, bias, zwide, Y, z_out, ldz, p_out, ldp, d_out, ldd, dt_out, train, st, ws);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+}
+
+/* pass 0: row-major dX; pass 1 (dXt != null): the transposed copy, reading the transposed activation */
+__global__ void __launch_bounds__(256) fc1_dgrad_kernel(int N, int in, const float* __restrict__ d, int ldd, const float* __restrict__ w, int act_below,
+                                                        const float* __restrict__ Y, int ldy, float* __restrict__ dX, int ldx,
+                                                        const float* __restrict__ Yt, int ldyt, float* __restrict__ dXt, int ldxt) {
+  const long total = (long)N * in;
+  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < total) {
+    const int n = (int)(g / in), i = (int)(g - (long)n * in);
+    const float v = __fmul_rn(w[i], d[(size_t)n * ldd]);
+    dX[(size_t)n * ldx + i] = act_backward(act_below, v, act_below != PS_ACT_NONE ? Y[(size_t)n * ldy + i] : 1.f);
+  } else if (dXt != nullptr && g < 2 * total) {
+    const long h = g - total;
+    const int i = (int)(h / N), n = (int)(h - (long)i * N);
+    const float v = __fmul_rn(w[i], d[(size_t)n * ldd]);
+    dXt[(size_t)i * ldxt + n] = act_backward(act_below, v, act_below != PS_ACT_NONE ? Yt[(size_t)i * ldyt + n] : 1.f);
+  }
+}
+void fc1_dgrad(Ctx* ctx, int N, int in, const float* d, int ldd, const float* w, int act_below, const float* Y, int ldy, float* dX, int ldx,
+               const float* Yt, int ldyt, float* dXt, int ldxt) {
+  const long total = (long)N * in * (dXt ? 2 : 1);
+  fc1_dgrad_kernel<<<ceil_div(total, 256), 256, 0, ctx->stream>>>(N, in, d, ldd, w, act_below, Y, ldy, dX, ldx, Yt, ldyt, dXt, ldxt);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+}
+
+/* G[z][c] = sum over the z-th batch chunk of d[b] * [A | 1][b][c]; 32 columns x 8 row lanes per block */
+__global__ void __launch_bounds__(256) fc1_wgrad_kernel(int N, int cols, const float* __restrict__ d, int ldd, const float* __restrict__ A, int lda,
+                                                        float* __restrict__ G, size_t slab, int chunk) {
+  __shared__ float sh[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  const int b0 = blockIdx.y * chunk, b1 = min(N, b0 + chunk);
+  float acc = 0.0f;
+  if (c < cols)
+    for (int b = b0 + ry; b < b1; b += 8) acc = fmaf(d[(size_t)b * ldd], A[(size_t)b * lda + c], acc);
+  sh[ry][cx] = acc;
+  __syncthreads();
+  if (ry == 0 && c < cols) {
+    float s = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s += sh[r][cx];
+    G[(size_t)blockIdx.y * slab + c] = s;
+  }
+}
+void fc1_wgrad(Ctx* ctx, int N, int in, const float* d, int ldd, const float* A, int lda, float* G, size_t slab, int nsplit) {
+  const int chunk = ceil_div(N, nsplit);
+  dim3 grid(ceil_div(in + 1, 32), nsplit);
+  fc1_wgrad_kernel<<<grid, 256, 0, ctx->stream>>>(N, in + 1, d, ldd, A, lda, G, slab, chunk);
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }

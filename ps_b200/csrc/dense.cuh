@@ -18,7 +18,7 @@ struct StepStatus {
   uint32_t wide_err;
   uint32_t n_unique;/* unique embedding keys of the batch */
   uint32_t seq;     /* step sequence number */
-  uint32_t pad;
+  uint32_t pad;     /* device-side: unique-key counter value at the previous publish */
 };
 
 /* one FcLayer's parameters as the fused update kernel sees them */
@@ -42,7 +42,7 @@ struct DenseUpdateArgs {
 void dense_init(Ctx* ctx, float* W, int out, int in, int ldw, float* Wt, int ldwt, uint64_t key, float maxv);
 void fill_column(Ctx* ctx, float* buf, int ld, int col, int rows, float value);
 /* also publishes the step status to mapped host memory when host_mapped is non-null */
-void dense_update(Ctx* ctx, const DenseUpdateArgs& a, const StepStatus* st, const uint32_t* emb_counters, const uint32_t* wide_counters,
+void dense_update(Ctx* ctx, const DenseUpdateArgs& a, StepStatus* st, const uint32_t* emb_counters, const uint32_t* wide_counters,
                   StepStatus* host_mapped);
 constexpr int kTailWorkspaceFloats = 2 * 64 + 4;
 
@@ -53,6 +53,13 @@ void tail_binary(Ctx* ctx, int N, const float* zdeep, int ldz, const float* zwid
 /* multi-class tail (FullConnectedNN): Softmax(10000) in place on Z, SoftmaxLoss, Softmax.backward */
 void tail_softmax(Ctx* ctx, int N, int C, float* Z, int ldz, const float* Y, float* d_out, int ldd, float* dt_out, int ldt, int train,
                   StepStatus* st, float* ws);
+/* the 1-unit top FcLayer on CUDA cores (see dense.cu): forward GEMV fused with the binary tail, dgrad, wgrad */
+void fc1_forward_tail(Ctx* ctx, int N, int in, const float* A, int lda, const float* w, const float* bias, const float* zwide, const float* Y,
+                      float* z_out, int ldz, float* p_out, int ldp, float* d_out, int ldd, float* dt_out, int train, StepStatus* st, float* ws);
+void fc1_dgrad(Ctx* ctx, int N, int in, const float* d, int ldd, const float* w, int act_below, const float* Y, int ldy, float* dX, int ldx,
+               const float* Yt, int ldyt, float* dXt, int ldxt);
+void fc1_wgrad(Ctx* ctx, int N, int in, const float* d, int ldd, const float* A, int lda, float* G, size_t slab, int nsplit);
+
 /* copies the status (plus table error flags) to mapped host memory */
 void publish_status(Ctx* ctx, StepStatus* st, const uint32_t* emb_counters, const uint32_t* wide_counters, StepStatus* host_mapped);
 /* sharded (multi-GPU) step: gsum[compact (o, c) index] = sum of the wgrad slabs, then [loss, gbar] at

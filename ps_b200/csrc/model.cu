@@ -199,6 +199,64 @@ void Model::run_step(const int64_t* E, const float* X, const int64_t* W, const f
   phase_names = it->second.names;
 }
 
+/* ------------------------------------------------------------------ per-layer pieces */
+void Model::fwd_layer(int l, int N) {                /* FcLayer.forward (FcLayer.java:74-91) */
+  if (l == L - 1 && top_is_unit()) return;           /* the 1-unit top layer is fused into the tail */
+  const bool fp32 = ctx->fc_precision == PS_FC_FP32;
+  FcFwdArgs a{};
+  a.B = N; a.in = fcs[l].in; a.out = fcs[l].out;
+  a.A = act[l]; a.lda = ld[l]; a.W = fcs[l].W; a.ldw = fcs[l].ldw; a.bias = fcs[l].bias; a.act = fcs[l].act;
+  a.Z = act[l + 1]; a.ldz = ld[l + 1];
+  a.Zt = (!fp32 && l + 1 < L) ? act_t[l + 1] : nullptr; a.ldzt = ldt;
+  if (fp32) fc_forward_fp32(ctx, a); else fc_forward_tf32(ctx, a);
+}
+
+void Model::run_tail(const float* Y, int N, bool train) {
+  const bool fp32 = ctx->fc_precision == PS_FC_FP32;
+  if (kind == PS_MODEL_FCNN) {
+    tail_softmax(ctx, N, width[L], act[L], ld[L], Y, delta[L], ld[L], fp32 ? nullptr : delta_t[L], ldt, train ? 1 : 0, st_dev, tail_ws);
+  } else if (top_is_unit()) {
+    const FcLayer& f = fcs[L - 1];
+    fc1_forward_tail(ctx, N, f.in, act[L - 1], ld[L - 1], f.W, f.bias, has_wide ? wide_z : nullptr, Y, act[L], ld[L], has_wide ? P : act[L],
+                     has_wide ? 1 : ld[L], delta[L], ld[L], fp32 ? nullptr : delta_t[L], train ? 1 : 0, st_dev, tail_ws);
+  } else {
+    tail_binary(ctx, N, act[L], ld[L], has_wide ? wide_z : nullptr, Y, has_wide ? P : act[L], has_wide ? 1 : ld[L], delta[L], ld[L],
+                fp32 ? nullptr : delta_t[L], train ? 1 : 0, st_dev, tail_ws);
+  }
+}
+
+void Model::wgrad_layer(int l, int N) {              /* FcLayer.backward: db, dW (FcLayer.java:103-106) */
+  const bool fp32 = ctx->fc_precision == PS_FC_FP32;
+  const FcLayer& f = fcs[l];
+  if (l == L - 1 && top_is_unit()) {
+    fc1_wgrad(ctx, N, f.in, delta[L], ld[L], act[l], ld[l], f.G, (size_t)f.out * f.ldw, f.nsplit);
+    return;
+  }
+  FcWgradArgs g{};
+  g.B = N; g.in = f.in; g.out = f.out;
+  g.dl = delta[l + 1]; g.ldd = ld[l + 1]; g.A = act[l]; g.lda = ld[l];
+  g.dlT = delta_t[l + 1]; g.AT = act_t[l]; g.ldt = ldt;
+  g.G = f.G; g.ldg = f.ldw; g.slab = (size_t)f.out * f.ldw; g.nsplit = f.nsplit;
+  if (fp32) fc_wgrad_fp32(ctx, g); else fc_wgrad_tf32(ctx, g);
+}
+
+void Model::dgrad_layer(int l, int N) {              /* FcLayer.backward: delta = W^T delta (FcLayer.java:108) + the derivative below */
+  const bool fp32 = ctx->fc_precision == PS_FC_FP32;
+  const FcLayer& f = fcs[l];
+  const int act_below = l > 0 ? fcs[l - 1].act : PS_ACT_NONE;
+  if (l == L - 1 && top_is_unit()) {
+    fc1_dgrad(ctx, N, f.in, delta[L], ld[L], f.W, act_below, act[l], ld[l], delta[l], ld[l], act_t[l], ldt, (!fp32 && l > 0) ? delta_t[l] : nullptr, ldt);
+    return;
+  }
+  FcDgradArgs d{};
+  d.B = N; d.in = f.in; d.out = f.out;
+  d.dl = delta[l + 1]; d.ldd = ld[l + 1]; d.W = f.W; d.ldw = f.ldw; d.Wt = f.Wt; d.ldwt = f.ldwt;
+  d.act_below = act_below; d.Y = act[l]; d.ldy = ld[l]; d.Yt = act_t[l]; d.ldyt = ldt;
+  d.n_cols = f.in; d.dX = delta[l]; d.ldx = ld[l];
+  d.dXt = (!fp32 && l > 0) ? delta_t[l] : nullptr; d.ldxt = ldt;
+  if (fp32) fc_dgrad_fp32(ctx, d); else fc_dgrad_tf32(ctx, d);
+}
+
 namespace {
 struct StreamScope {   /* every launch helper reads ctx->stream: run a few of them on a side stream */
   Ctx* c; cudaStream_t saved;
@@ -225,30 +283,19 @@ void Model::step_device(const int64_t* E, const float* X, const int64_t* W, cons
   if (has_emb) {
     emb.probe(E, nullptr, N);
     mark("emb_probe");
-    emb.gather(act[0], ld[0], N);
+    emb.gather(act[0], ld[0], N, 0, X, Xn, F * D);      /* EmbeddingLayer.forward + ConcatLayer.forward */
     mark("emb_gather");
-    PS_CUDA(cudaMemcpy2DAsync(act[0] + F * D, sizeof(float) * ld[0], X, sizeof(float) * Xn, sizeof(float) * Xn, N, cudaMemcpyDeviceToDevice, s));
   } else {
     PS_CUDA(cudaMemcpy2DAsync(act[0], sizeof(float) * ld[0], X, sizeof(float) * Xn, sizeof(float) * Xn, N, cudaMemcpyDeviceToDevice, s));
   }
-  mark("x_concat");
   fork(s, s2);
   if (!fp32 && train) { StreamScope sc(ctx, s2); transpose_copy(ctx, act[0], ld[0], act_t[0], ldt, N, width[0]); }   /* only wgrad0 needs it */
   for (int l = 0; l < L; ++l) {
-    FcFwdArgs a{};
-    a.B = N; a.in = fcs[l].in; a.out = fcs[l].out;
-    a.A = act[l]; a.lda = ld[l]; a.W = fcs[l].W; a.ldw = fcs[l].ldw; a.bias = fcs[l].bias; a.act = fcs[l].act;
-    a.Z = act[l + 1]; a.ldz = ld[l + 1];
-    a.Zt = (!fp32 && l + 1 < L) ? act_t[l + 1] : nullptr; a.ldzt = ldt;
-    if (fp32) fc_forward_fp32(ctx, a); else fc_forward_tf32(ctx, a);
+    fwd_layer(l, N);
     mark(("fc_fwd" + std::to_string(l)).c_str());
   }
   fork(s1, s);                                   /* wide_z */
-  if (kind == PS_MODEL_FCNN)
-    tail_softmax(ctx, N, width[L], act[L], ld[L], Y, delta[L], ld[L], fp32 ? nullptr : delta_t[L], ldt, train ? 1 : 0, st_dev, tail_ws);
-  else
-    tail_binary(ctx, N, act[L], ld[L], has_wide ? wide_z : nullptr, Y, has_wide ? P : act[L], has_wide ? 1 : ld[L], delta[L], ld[L],
-                fp32 ? nullptr : delta_t[L], train ? 1 : 0, st_dev, tail_ws);
+  run_tail(Y, N, train);
   mark("tail");
   if (!train) {
     if (has_emb) emb.clear_batch();
@@ -262,40 +309,15 @@ void Model::step_device(const int64_t* E, const float* X, const int64_t* W, cons
   for (int l = L - 1; l >= 0; --l) {
     fork(s, s1);                                 /* delta[l+1] (tail or dgrad(l+1)) is ready */
     if (l == 0) fork(s2, s1);                    /* act_t[0] */
-    {
-      StreamScope sc(ctx, s1);
-      FcWgradArgs g{};
-      g.B = N; g.in = fcs[l].in; g.out = fcs[l].out;
-      g.dl = delta[l + 1]; g.ldd = ld[l + 1]; g.A = act[l]; g.lda = ld[l];
-      g.dlT = delta_t[l + 1]; g.AT = act_t[l]; g.ldt = ldt;
-      g.G = fcs[l].G; g.ldg = fcs[l].ldw; g.slab = (size_t)fcs[l].out * fcs[l].ldw; g.nsplit = fcs[l].nsplit;
-      if (fp32) fc_wgrad_fp32(ctx, g); else fc_wgrad_tf32(ctx, g);
-    }
-    FcDgradArgs d{};
-    d.B = N; d.in = fcs[l].in; d.out = fcs[l].out;
-    d.dl = delta[l + 1]; d.ldd = ld[l + 1]; d.W = fcs[l].W; d.ldw = fcs[l].ldw; d.Wt = fcs[l].Wt; d.ldwt = fcs[l].ldwt;
-    d.act_below = l > 0 ? fcs[l - 1].act : PS_ACT_NONE; d.Y = act[l]; d.ldy = ld[l]; d.Yt = act_t[l]; d.ldyt = ldt;
-    d.n_cols = fcs[l].in; d.dX = delta[l]; d.ldx = ld[l];
-    d.dXt = (!fp32 && l > 0) ? delta_t[l] : nullptr; d.ldxt = ldt;
-    if (fp32) fc_dgrad_fp32(ctx, d); else fc_dgrad_tf32(ctx, d);
+    { StreamScope sc(ctx, s1); wgrad_layer(l, N); }
+    dgrad_layer(l, N);
     mark(("fc_dgrad" + std::to_string(l)).c_str());
   }
   /* ---- KVStore.update + clear (Trainer.java:93,95) ---- */
   fork(s, s1);                                   /* every dgrad has read W / Wt: the dense update may overwrite them */
   {
     StreamScope sc(ctx, s1);
-    DenseUpdateArgs u{};
-    u.n_layers = L; u.N = N;
-    long first = 0;
-    for (int l = 0; l < L; ++l) {
-      DenseLayerDesc& q = u.l[l];
-      const FcLayer& f = fcs[l];
-      q.W = f.W; q.Wt = f.Wt; q.bias = f.bias; q.sW1 = f.sW1; q.sW2 = f.sW2; q.sb1 = f.sb1; q.sb2 = f.sb2;
-      q.G = f.G; q.slab = (size_t)f.out * f.ldw; q.nsplit = f.nsplit; q.out = f.out; q.in = f.in; q.ldw = f.ldw; q.ldwt = f.ldwt; q.ldg = f.ldw;
-      q.updW = make_updater_dev(f.updW); q.updB = make_updater_dev(f.updB);
-      q.first = first; first += (long)f.out * (f.in + 1);
-    }
-    u.total = first;
+    const DenseUpdateArgs u = dense_args(N);
     dense_update(ctx, u, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, publish_to);
   }
   if (has_emb) { emb.scatter_update(delta[0], ld[0], act[0], ld[0], N, 2, skip_ptr(st_dev)); mark("emb_bwd_update"); }
@@ -345,34 +367,9 @@ void Model::shard_dense_step(const float* X, const int64_t* W_local, const int64
     wide.insert(W_all, n_all);                     /* the union of every replica's keys */
     wide.forward(W_local, N, F, wide_bias, wide_z);
   }
-  for (int l = 0; l < L; ++l) {
-    FcFwdArgs a{};
-    a.B = N; a.in = fcs[l].in; a.out = fcs[l].out;
-    a.A = act[l]; a.lda = ld[l]; a.W = fcs[l].W; a.ldw = fcs[l].ldw; a.bias = fcs[l].bias; a.act = fcs[l].act;
-    a.Z = act[l + 1]; a.ldz = ld[l + 1];
-    a.Zt = (!fp32 && l + 1 < L) ? act_t[l + 1] : nullptr; a.ldzt = ldt;
-    if (fp32) fc_forward_fp32(ctx, a); else fc_forward_tf32(ctx, a);
-  }
-  if (kind == PS_MODEL_FCNN)
-    tail_softmax(ctx, N, width[L], act[L], ld[L], Y, delta[L], ld[L], fp32 ? nullptr : delta_t[L], ldt, 1, st_dev, tail_ws);
-  else
-    tail_binary(ctx, N, act[L], ld[L], has_wide ? wide_z : nullptr, Y, has_wide ? P : act[L], has_wide ? 1 : ld[L], delta[L], ld[L],
-                fp32 ? nullptr : delta_t[L], 1, st_dev, tail_ws);
-  for (int l = L - 1; l >= 0; --l) {
-    FcWgradArgs g{};
-    g.B = N; g.in = fcs[l].in; g.out = fcs[l].out;
-    g.dl = delta[l + 1]; g.ldd = ld[l + 1]; g.A = act[l]; g.lda = ld[l];
-    g.dlT = delta_t[l + 1]; g.AT = act_t[l]; g.ldt = ldt;
-    g.G = fcs[l].G; g.ldg = fcs[l].ldw; g.slab = (size_t)fcs[l].out * fcs[l].ldw; g.nsplit = fcs[l].nsplit;
-    if (fp32) fc_wgrad_fp32(ctx, g); else fc_wgrad_tf32(ctx, g);
-    FcDgradArgs d{};
-    d.B = N; d.in = fcs[l].in; d.out = fcs[l].out;
-    d.dl = delta[l + 1]; d.ldd = ld[l + 1]; d.W = fcs[l].W; d.ldw = fcs[l].ldw; d.Wt = fcs[l].Wt; d.ldwt = fcs[l].ldwt;
-    d.act_below = l > 0 ? fcs[l - 1].act : PS_ACT_NONE; d.Y = act[l]; d.ldy = ld[l]; d.Yt = act_t[l]; d.ldyt = ldt;
-    d.n_cols = fcs[l].in; d.dX = delta[l]; d.ldx = ld[l];
-    d.dXt = (!fp32 && l > 0) ? delta_t[l] : nullptr; d.ldxt = ldt;
-    if (fp32) fc_dgrad_fp32(ctx, d); else fc_dgrad_tf32(ctx, d);
-  }
+  for (int l = 0; l < L; ++l) fwd_layer(l, N);
+  run_tail(Y, N, true);
+  for (int l = L - 1; l >= 0; --l) { wgrad_layer(l, N); dgrad_layer(l, N); }
   const DenseUpdateArgs u = dense_args(N);
   if (!gsum) { gsum_len = u.total + 2; gsum = dmalloc_zero<float>((size_t)gsum_len, s); }
   dense_reduce(ctx, u, st_dev, gsum);
@@ -449,7 +446,6 @@ void Model::gemm_times(int N, int reps, float* out) {
   PS_REQUIRE(reps > 0 && N > 0 && N <= Bmax, PS_ERR_ARG, "gemm_times: bad argument");
   PS_REQUIRE(in_flight == 0, PS_ERR_STATE, "gemm_times: steps in flight");
   cudaStream_t s = ctx->stream;
-  const bool fp32 = ctx->fc_precision == PS_FC_FP32;
   cudaEvent_t e0, e1;
   PS_CUDA(cudaEventCreate(&e0)); PS_CUDA(cudaEventCreate(&e1));
   for (int l = 0; l < L; ++l)
@@ -459,29 +455,9 @@ void Model::gemm_times(int N, int reps, float* out) {
       PS_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
       try {
         for (int r = 0; r < reps; ++r) {
-          if (which == 0) {
-            FcFwdArgs a{};
-            a.B = N; a.in = fcs[l].in; a.out = fcs[l].out;
-            a.A = act[l]; a.lda = ld[l]; a.W = fcs[l].W; a.ldw = fcs[l].ldw; a.bias = fcs[l].bias; a.act = fcs[l].act;
-            a.Z = act[l + 1]; a.ldz = ld[l + 1];
-            a.Zt = (!fp32 && l + 1 < L) ? act_t[l + 1] : nullptr; a.ldzt = ldt;
-            if (fp32) fc_forward_fp32(ctx, a); else fc_forward_tf32(ctx, a);
-          } else if (which == 1) {
-            FcDgradArgs d{};
-            d.B = N; d.in = fcs[l].in; d.out = fcs[l].out;
-            d.dl = delta[l + 1]; d.ldd = ld[l + 1]; d.W = fcs[l].W; d.ldw = fcs[l].ldw; d.Wt = fcs[l].Wt; d.ldwt = fcs[l].ldwt;
-            d.act_below = l > 0 ? fcs[l - 1].act : PS_ACT_NONE; d.Y = act[l]; d.ldy = ld[l]; d.Yt = act_t[l]; d.ldyt = ldt;
-            d.n_cols = fcs[l].in; d.dX = delta[l]; d.ldx = ld[l];
-            d.dXt = (!fp32 && l > 0) ? delta_t[l] : nullptr; d.ldxt = ldt;
-            if (fp32) fc_dgrad_fp32(ctx, d); else fc_dgrad_tf32(ctx, d);
-          } else {
-            FcWgradArgs g{};
-            g.B = N; g.in = fcs[l].in; g.out = fcs[l].out;
-            g.dl = delta[l + 1]; g.ldd = ld[l + 1]; g.A = act[l]; g.lda = ld[l];
-            g.dlT = delta_t[l + 1]; g.AT = act_t[l]; g.ldt = ldt;
-            g.G = fcs[l].G; g.ldg = fcs[l].ldw; g.slab = (size_t)fcs[l].out * fcs[l].ldw; g.nsplit = fcs[l].nsplit;
-            if (fp32) fc_wgrad_fp32(ctx, g); else fc_wgrad_tf32(ctx, g);
-          }
+          if (which == 0) { if (l == L - 1 && top_is_unit()) run_tail(stage[0].Y, N, true); else fwd_layer(l, N); }
+          else if (which == 1) dgrad_layer(l, N);
+          else wgrad_layer(l, N);
         }
       } catch (...) { cudaStreamEndCapture(s, &graph); if (graph) cudaGraphDestroy(graph); throw; }
       PS_CUDA(cudaStreamEndCapture(s, &graph));

@@ -90,6 +90,12 @@ struct Model {
               const ps_updater_spec* emb_updater, int max_batch);
   void destroy();
   /* the whole step on device-resident inputs, enqueued on ctx->stream; status lands in st_dev */
+  /* per-layer pieces shared by the single-GPU step, the sharded step and the timing hooks */
+  bool top_is_unit() const { return kind != PS_MODEL_FCNN && fcs[L - 1].out == 1; }   /* the fused GEMV + tail path applies */
+  void fwd_layer(int l, int N);
+  void run_tail(const float* Y, int N, bool train);
+  void wgrad_layer(int l, int N);
+  void dgrad_layer(int l, int N);
   void step_device(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, bool train, StepStatus* publish_to);
   /* the same through the graph cache (falls back to direct launches while profiling) */
   void run_step(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, bool train, StepStatus* publish_to);

@@ -11,6 +11,8 @@
  * All of it is HBM/L2-bound integer and copy work: no tensor cores, 128-bit accesses,
  * one thread group (Dp/4 lanes) per looked-up row.
  */
+#include <algorithm>
+#include <cmath>
 #include <vector>
 
 #include "table.cuh"
@@ -57,7 +59,7 @@ __device__ __forceinline__ int emb_find_or_insert(EmbSlot* slots, uint32_t C, un
 template <class IdT>
 __global__ void __launch_bounds__(256) emb_probe_kernel(EmbSlot* __restrict__ slots, uint32_t C, float* __restrict__ w, int Dp, int D,
                                                         const IdT* __restrict__ ids, int L, int F, uint64_t seed, float maxv,
-                                                        int32_t* __restrict__ lk_slot, uint32_t* __restrict__ uniq_slot,
+                                                        int32_t* __restrict__ lk_slot, uint32_t umask,
                                                         uint32_t* __restrict__ counters) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -78,7 +80,9 @@ __global__ void __launch_bounds__(256) emb_probe_kernel(EmbSlot* __restrict__ sl
       first = atomicAdd(&slots[slot].cnt, 1u) == 0u;   /* first occurrence in this batch: number the unique key */
     }
   }
-  /* one atomic per warp on the batch-wide unique counter instead of one per unique key */
+  /* one atomic per warp on the unique-key counter instead of one per unique key.  The counter is
+   * MONOTONIC across batches (no per-step reset node): accumulator rows are a ring indexed by
+   * counter & umask, and every entry is zeroed again by the group that consumed it.             */
   const unsigned firsts = __ballot_sync(0xffffffffu, first);
   if (firsts == 0u) return;
   const int leader = __ffs(firsts) - 1;
@@ -86,9 +90,7 @@ __global__ void __launch_bounds__(256) emb_probe_kernel(EmbSlot* __restrict__ sl
   if (lane == leader) base = atomicAdd(&counters[0], (uint32_t)__popc(firsts));
   base = __shfl_sync(0xffffffffu, base, leader);
   if (first) {
-    const uint32_t u = base + (uint32_t)__popc(firsts & ((1u << lane) - 1u));
-    slots[slot].uidx = u;
-    uniq_slot[u] = (uint32_t)slot;
+    slots[slot].uidx = (base + (uint32_t)__popc(firsts & ((1u << lane) - 1u))) & umask;
   }
 }
 
@@ -97,10 +99,16 @@ __global__ void __launch_bounds__(256) emb_probe_kernel(EmbSlot* __restrict__ sl
  * stores of a warp coalesce into full 128 B lines; ReLU (EmbeddingField.java:75) is fused.     */
 template <int TPL, bool ALIGNED>
 __global__ void __launch_bounds__(256) emb_gather_kernel(const float* __restrict__ w, int Dp, int D, const int32_t* __restrict__ lk_slot,
-                                                         int L, int F, float* __restrict__ out, int ldo) {
+                                                         int L, int F, float* __restrict__ out, int ldo, const float* __restrict__ X, int Xn,
+                                                         int xoff, int N) {
   const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long)L * TPL) {                    /* ConcatLayer.forward (ConcatLayer.java:30-37): numeric features next to the embeddings */
+    const long i = g - (long)L * TPL;
+    if (X != nullptr && i < (long)N * Xn) { const int n = (int)(i / Xn), x = (int)(i - (long)n * Xn); out[(size_t)n * ldo + xoff + x] = X[i]; }
+    return;
+  }
   const int l = (int)(g / TPL), part = (int)(g % TPL);
-  if (l >= L || part * 4 >= D) return;
+  if (part * 4 >= D) return;
   const int slot = lk_slot[l];
   if (slot < 0) return;
   const int n = l / F, j = l - n * F;
@@ -240,9 +248,11 @@ __global__ void __launch_bounds__(256) emb_scatter_update_kernel(EmbSlot* __rest
   if (part == 0) { arrived[uidx] = 0u; slots[slot].cnt = 0u; }
 }
 
-__global__ void emb_clear_batch_kernel(EmbSlot* __restrict__ slots, const uint32_t* __restrict__ uniq_slot, const uint32_t* __restrict__ counters) {
-  const uint32_t nu = counters[0];
-  for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < nu; u += gridDim.x * blockDim.x) slots[uniq_slot[u]].cnt = 0u;
+__global__ void emb_clear_batch_kernel(EmbSlot* __restrict__ slots, const int32_t* __restrict__ lk_slot, int L) {
+  for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < L; l += gridDim.x * blockDim.x) {
+    const int slot = lk_slot[l];
+    if (slot >= 0) slots[slot].cnt = 0u;       /* duplicates store the same zero */
+  }
 }
 
 /* host-driven row access: thread per key */
@@ -298,17 +308,18 @@ void EmbTable::create(Ctx* c, int F_, int D_, int64_t capacity, const ps_updater
 void EmbTable::reserve(int64_t L) {
   if (L <= Lcap) return;
   PS_CUDA(cudaStreamSynchronize(ctx->stream));
-  dfree(lk_slot); dfree(uniq_slot); dfree(acc); dfree(arrived);
+  dfree(lk_slot); dfree(acc); dfree(arrived);
   Lcap = L;
+  ucap = 1024;
+  while ((int64_t)ucap < L) ucap <<= 1;        /* ring of accumulator rows: a power of two >= the most unique keys one batch can have */
   lk_slot = dmalloc<int32_t>((size_t)L);
-  uniq_slot = dmalloc<uint32_t>((size_t)L);
-  acc = dmalloc_zero<float>((size_t)L * Dp, ctx->stream);
-  arrived = dmalloc_zero<uint32_t>((size_t)L, ctx->stream);
+  acc = dmalloc_zero<float>((size_t)ucap * Dp, ctx->stream);
+  arrived = dmalloc_zero<uint32_t>((size_t)ucap, ctx->stream);
 }
 
 void EmbTable::destroy() {
   dfree(slots); dfree(w); dfree(s1); dfree(s2); dfree(counters);
-  dfree(lk_slot); dfree(uniq_slot); dfree(acc); dfree(arrived);
+  dfree(lk_slot); dfree(acc); dfree(arrived);
   slots = nullptr; w = s1 = s2 = nullptr;
 }
 
@@ -316,12 +327,11 @@ void EmbTable::probe(const int64_t* ids_i64, const float* ids_f32, int N) {
   const int64_t L = (int64_t)N * F;
   PS_REQUIRE(L <= Lcap, PS_ERR_ARG, "embedding: batch larger than the reserved workspace");
   last_L = L;
-  PS_CUDA(cudaMemsetAsync(counters, 0, sizeof(uint32_t), ctx->stream));
   const int grid = ceil_div(L, 256);
   if (ids_i64)
-    emb_probe_kernel<int64_t><<<grid, 256, 0, ctx->stream>>>(slots, (uint32_t)C, w, Dp, D, ids_i64, (int)L, F, ctx->seed, maxv, lk_slot, uniq_slot, counters);
+    emb_probe_kernel<int64_t><<<grid, 256, 0, ctx->stream>>>(slots, (uint32_t)C, w, Dp, D, ids_i64, (int)L, F, ctx->seed, maxv, lk_slot, ucap - 1, counters);
   else
-    emb_probe_kernel<float><<<grid, 256, 0, ctx->stream>>>(slots, (uint32_t)C, w, Dp, D, ids_f32, (int)L, F, ctx->seed, maxv, lk_slot, uniq_slot, counters);
+    emb_probe_kernel<float><<<grid, 256, 0, ctx->stream>>>(slots, (uint32_t)C, w, Dp, D, ids_f32, (int)L, F, ctx->seed, maxv, lk_slot, ucap - 1, counters);
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }
@@ -329,33 +339,32 @@ void EmbTable::probe(const int64_t* ids_i64, const float* ids_f32, int N) {
 void EmbTable::probe_packed(const uint64_t* keys, int n) {
   reserve(n);
   last_L = n;
-  PS_CUDA(cudaMemsetAsync(counters, 0, sizeof(uint32_t), ctx->stream));
   if (n <= 0) return;
   emb_probe_kernel<unsigned long long><<<ceil_div(n, 256), 256, 0, ctx->stream>>>(slots, (uint32_t)C, w, Dp, D, reinterpret_cast<const unsigned long long*>(keys), n, 0,
-                                                                                  ctx->seed, maxv, lk_slot, uniq_slot, counters);
+                                                                                  ctx->seed, maxv, lk_slot, ucap - 1, counters);
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }
 
 template <int TPL>
-static void launch_gather(EmbTable& t, float* out, int ldo, int N, int F) {
+static void launch_gather(EmbTable& t, float* out, int ldo, int N, int F, const float* X, int Xn, int xoff) {
   const long L = (long)N * F;
   const bool aligned = (t.D % 4 == 0) && (ldo % 4 == 0) && ((uintptr_t)out % 16 == 0);
-  const int grid = ceil_div(L * TPL, 256);
-  if (aligned) emb_gather_kernel<TPL, true><<<grid, 256, 0, t.ctx->stream>>>(t.w, t.Dp, t.D, t.lk_slot, (int)L, F, out, ldo);
-  else emb_gather_kernel<TPL, false><<<grid, 256, 0, t.ctx->stream>>>(t.w, t.Dp, t.D, t.lk_slot, (int)L, F, out, ldo);
+  const int grid = ceil_div(L * TPL + (X ? (long)N * Xn : 0), 256);
+  if (aligned) emb_gather_kernel<TPL, true><<<grid, 256, 0, t.ctx->stream>>>(t.w, t.Dp, t.D, t.lk_slot, (int)L, F, out, ldo, X, Xn, xoff, N);
+  else emb_gather_kernel<TPL, false><<<grid, 256, 0, t.ctx->stream>>>(t.w, t.Dp, t.D, t.lk_slot, (int)L, F, out, ldo, X, Xn, xoff, N);
 }
 
-void EmbTable::gather(float* out, int ldo, int N, int F_eff) {
+void EmbTable::gather(float* out, int ldo, int N, int F_eff, const float* X, int Xn, int xoff) {
   const int Fe = F_eff > 0 ? F_eff : F;
   PS_REQUIRE((int64_t)N * Fe == last_L, PS_ERR_STATE, "embedding: gather without a matching probe");
   switch (tpl) {
-    case 1: launch_gather<1>(*this, out, ldo, N, Fe); break;
-    case 2: launch_gather<2>(*this, out, ldo, N, Fe); break;
-    case 4: launch_gather<4>(*this, out, ldo, N, Fe); break;
-    case 8: launch_gather<8>(*this, out, ldo, N, Fe); break;
-    case 16: launch_gather<16>(*this, out, ldo, N, Fe); break;
-    default: launch_gather<32>(*this, out, ldo, N, Fe); break;
+    case 1: launch_gather<1>(*this, out, ldo, N, Fe, X, Xn, xoff); break;
+    case 2: launch_gather<2>(*this, out, ldo, N, Fe, X, Xn, xoff); break;
+    case 4: launch_gather<4>(*this, out, ldo, N, Fe, X, Xn, xoff); break;
+    case 8: launch_gather<8>(*this, out, ldo, N, Fe, X, Xn, xoff); break;
+    case 16: launch_gather<16>(*this, out, ldo, N, Fe, X, Xn, xoff); break;
+    default: launch_gather<32>(*this, out, ldo, N, Fe, X, Xn, xoff); break;
   }
   PS_LAUNCH_CHECK();
   ctx->launches++;
@@ -390,7 +399,8 @@ void EmbTable::scatter_update(const float* delta, int ldd, const float* act, int
 }
 
 void EmbTable::clear_batch() {
-  emb_clear_batch_kernel<<<ctx->num_sms, 256, 0, ctx->stream>>>(slots, uniq_slot, counters);
+  if (last_L <= 0) return;
+  emb_clear_batch_kernel<<<std::min<long>(ceil_div(last_L, 256), (long)ctx->num_sms * 4), 256, 0, ctx->stream>>>(slots, lk_slot, (int)last_L);
   PS_LAUNCH_CHECK();
   ctx->launches++;
   last_L = 0;

@@ -10,9 +10,10 @@
  *   w[C][Dp], s1[C][Dp], s2[C][Dp]   row = slot index; SoA across {weight, Adam M | Ftrl Z,
  *              Adam V | Ftrl N} so the forward gather touches only w.  Dp = D rounded to 4
  *              floats: every row is 16 B aligned for 128-bit loads
- *   per-batch workspace (L = N*F lookups): lk_slot[L]; uniq_slot[U]; acc[U][Dp] gradient
- *              accumulators and arrived[U] tickets, indexed by the batch-unique index — a few
- *              MB that stay L2-resident, so the scatter-add never round-trips HBM
+ *   per-batch workspace (L = N*F lookups): lk_slot[L]; a ring of acc[ucap][Dp] gradient
+ *              accumulators and arrived[ucap] tickets indexed by a monotonic unique-key counter
+ *              (no per-step reset) — a few MB that stay L2-resident, so the scatter-add never
+ *              round-trips HBM
  *
  * WideTable: layer/LRLayer.java's 1x1 weights "wide.weights.<id>": 32 B records
  * {key, w, s1, s2} — one sector holds everything a probe, the forward sum and the update need.
@@ -47,10 +48,10 @@ struct EmbTable {
   /* per-batch workspace */
   int64_t Lcap = 0;
   int32_t* lk_slot = nullptr;
-  uint32_t* uniq_slot = nullptr;
+  uint32_t ucap = 0;                   /* accumulator ring size (power of two) */
   float* acc = nullptr;
   uint32_t* arrived = nullptr;
-  uint32_t* counters = nullptr;        /* [0] nuniq of the batch, [1] error flag, [2..3] u64 row count */
+  uint32_t* counters = nullptr;        /* [0] monotonic unique-key counter, [1] error flag, [2..3] u64 row count */
   int64_t last_L = 0;
 
   void create(Ctx* c, int F_, int D_, int64_t capacity, const ps_updater_spec& u, int64_t max_lookups);
@@ -62,7 +63,8 @@ struct EmbTable {
   /* out[n*ldo + j*D + d] = relu(w[slot(n,j)][d])   (EmbeddingField.java:73-76)               */
   /* the same on already-packed keys (owner side of the key-hash sharded exchange): n lookups, one "field" */
   void probe_packed(const uint64_t* keys, int n);
-  void gather(float* out, int ldo, int N, int F_eff = 0);
+  /* X != null: also copies the numeric features X[N][Xn] to columns [xoff, xoff+Xn) (ConcatLayer) */
+  void gather(float* out, int ldo, int N, int F_eff = 0, const float* X = nullptr, int Xn = 0, int xoff = 0);
   /* fused scatter-add + occurrence normalisation + updater step (see table.cu)               */
   void scatter_update(const float* delta, int ldd, const float* act /* null: mask already applied */, int lda, int N, int calls,
                       const int* skip_flag, int F_eff = 0);
