@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("PS_FC_PRECISION", "fp32"))
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--ring", type=int, default=16)
+    ap.add_argument("--slack", type=float, default=2.0)
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     rank = int(os.environ.get("RANK", "0"))
@@ -197,8 +198,9 @@ def main():
     # Trainer step on the concatenated batch (ps_b200/sharded.py); per-GPU batch fixed => weak scaling
     trainer = None
     if world > 1:
-        from ps_b200.sharded import GpuOps, ShardedTrainer
-        trainer = ShardedTrainer(GpuOps(ps, ctx, model, local_rank), rank, world)
+        from ps_b200.sharded import GpuOps, GraphedShardedTrainer
+        # the whole sharded step (local kernels + NCCL collectives, fixed-capacity buckets) is one CUDA graph per rank
+        trainer = GraphedShardedTrainer(GpuOps(ps, ctx, model, local_rank), rank, world, B, F, cfg["kind"] == "widedeep", slack=args.slack)
 
     def dev_step(i):
         d = dev_ring[i % len(dev_ring)]
@@ -256,7 +258,8 @@ def main():
                 pb = pinned[(start + i) % len(pinned)]
                 with torch.cuda.stream(stream):
                     d = {k: torch.from_numpy(pa.array).to(f"cuda:{local_rank}", non_blocking=True) for k, pa in pb.items()}
-                last = trainer.step(d.get("E"), d["X"], d.get("W"), d["Y"])
+                trainer.step(d.get("E"), d["X"], d.get("W"), d["Y"])
+                last = model.read_loss()                       # the step's result is read back every step
             return last
         for i in range(n):
             pb = pinned[(start + i) % len(pinned)]
@@ -276,6 +279,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t.item())
     clocks = sampler.summary()
+    if trainer is not None:
+        trainer.check()
 
     # ---- per-kernel device times and the roofline of the dominant HBM-bound kernel ----
     acc = {}

@@ -182,6 +182,11 @@ int ps_model_gemm_times(ps_model* m, int N, int reps, float* us, int cap);
  * send_pos_dev[N*F] maps each lookup to its place in that order.                                      */
 int ps_shard_route_dev(ps_ctx* ctx, const int64_t* E_dev, int N, int F, int R, uint64_t* send_keys_dev, int32_t* send_pos_dev,
                        int32_t* counts_dev, int32_t* cursor_dev);
+/* the same with a FIXED bucket capacity per owner (send_keys_dev[R*cap], unused entries = 0 = EMPTY, which
+ * the owner skips): no count has to reach the host, so route → all-to-all → lookup → … → apply can be
+ * captured in ONE CUDA graph per rank.  *overflow_dev is set to 1 if a bucket did not fit.              */
+int ps_shard_route_padded_dev(ps_ctx* ctx, const int64_t* E_dev, int N, int F, int R, int cap, uint64_t* send_keys_dev, int32_t* send_pos_dev,
+                              int32_t* cursor_dev, int32_t* overflow_dev);
 /* PServer.getList (net/PServer.java:102-117) for the keys this rank owns: rows_out_dev[n][Dp], ReLU applied */
 int ps_model_shard_lookup_dev(ps_model* m, const uint64_t* keys_dev, int n, float* rows_out_dev);
 int ps_model_shard_row_stride(ps_model* m, int* Dp);       /* floats per exchanged row (D rounded up to 4) */

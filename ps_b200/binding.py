@@ -89,6 +89,7 @@ SYMBOLS = {
     "ps_model_kernel_times": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "ps_model_gemm_times": (_i, [_vp, _i, _i, _vp, _i]),
     "ps_shard_route_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "ps_shard_route_padded_dev": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "ps_model_shard_lookup_dev": (_i, [_vp, _vp, _i, _vp]),
     "ps_model_shard_row_stride": (_i, [_vp, C.POINTER(_i)]),
     "ps_model_shard_unpack_dev": (_i, [_vp, _vp, _vp, _i]),

@@ -449,6 +449,13 @@ int ps_shard_route_dev(ps_ctx* ctx, const int64_t* E_dev, int N, int F, int R, u
   shard_place(&ctx->c, E_dev, N, F, R, counts_dev, cursor_dev, send_keys_dev, send_pos_dev);
   PS_CATCH
 }
+int ps_shard_route_padded_dev(ps_ctx* ctx, const int64_t* E_dev, int N, int F, int R, int cap, uint64_t* send_keys_dev, int32_t* send_pos_dev,
+                              int32_t* cursor_dev, int32_t* overflow_dev) {
+  PS_TRY
+  PS_REQUIRE(ctx && E_dev && send_keys_dev && send_pos_dev && cursor_dev && overflow_dev && N > 0 && F > 0 && R > 0 && cap > 0, PS_ERR_ARG, "bad argument");
+  shard_place_padded(&ctx->c, E_dev, N, F, R, cap, cursor_dev, send_keys_dev, send_pos_dev, overflow_dev);
+  PS_CATCH
+}
 int ps_model_shard_lookup_dev(ps_model* m, const uint64_t* keys_dev, int n, float* rows_out_dev) {
   PS_TRY
   PS_REQUIRE(m && n >= 0, PS_ERR_ARG, "bad argument");

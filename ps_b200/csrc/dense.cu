@@ -307,21 +307,28 @@ __global__ void __launch_bounds__(kTailThreads) fc1_forward_tail_kernel(int N, i
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   const bool vec = (in % 4 == 0) && (lda % 4 == 0);
   float loss_part = 0.0f, d_part = 0.0f;
-  for (int n = warp; n < N; n += nwarps) {
-    const float* a = A + (size_t)n * lda;
-    float acc = 0.0f;
-    if (vec) {
-      for (int c = lane * 4; c < in; c += 128) {
-        const float4 x = ld_f4(a + c), y = __ldg(reinterpret_cast<const float4*>(w + c));
-        acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+  /* a warp owns 32 consecutive samples: 32 cooperative dot products (lane j keeps the j-th), then the
+   * double-precision sigmoid / log work runs on all 32 lanes at once */
+  for (int nb = warp * 32; nb < N; nb += nwarps * 32) {
+    float zmine = 0.0f;
+    for (int j = 0; j < 32 && nb + j < N; ++j) {
+      const float* a = A + (size_t)(nb + j) * lda;
+      float acc = 0.0f;
+      if (vec) {
+        for (int c = lane * 4; c < in; c += 128) {
+          const float4 x = ld_f4(a + c), y = __ldg(reinterpret_cast<const float4*>(w + c));
+          acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+        }
+      } else {
+        for (int c = lane; c < in; c += 32) acc = fmaf(a[c], __ldg(w + c), acc);
       }
-    } else {
-      for (int c = lane; c < in; c += 32) acc = fmaf(a[c], __ldg(w + c), acc);
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
-      float z = __fadd_rn(acc, bias[0]);                                       /* FcLayer.java:76-77 */
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == j) zmine = acc;
+    }
+    const int n = nb + lane;
+    if (n < N) {
+      float z = __fadd_rn(zmine, bias[0]);                                     /* FcLayer.java:76-77 */
       z_out[(size_t)n * ldz] = z;
       if (zwide) z = __fadd_rn(z, zwide[n]);                                   /* AddLayer.java:36 */
       const float p = sigmoid_clipped(z);                                      /* Sigmoid.java:11 */
@@ -343,33 +350,72 @@ __global__ void __launch_bounds__(kTailThreads) fc1_forward_tail_kernel(int N, i
 }
 void fc1_forward_tail(Ctx* ctx, int N, int in, const float* A, int lda, const float* w, const float* bias, const float* zwide, const float* Y,
                       float* z_out, int ldz, float* p_out, int ldp, float* d_out, int ldd, float* dt_out, int train, StepStatus* st, float* ws) {
-  const int blocks = std::max(1, std::min(kTailMaxBlocks, ceil_div((long)N * 32, kTailThreads)));
+  const int blocks = std::max(1, std::min(kTailMaxBlocks, ceil_div(ceil_div(N, 32) * 32L, kTailThreads)));
   fc1_forward_tail_kernel<<<blocks, kTailThreads, 0, ctx->stream>>>(N, in, A, lda, w, bias, zwide, Y, z_out, ldz, p_out, ldp, d_out, ldd, dt_out, train, st, ws);
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }
 
-/* pass 0: row-major dX; pass 1 (dXt != null): the transposed copy, reading the transposed activation */
-__global__ void __launch_bounds__(256) fc1_dgrad_kernel(int N, int in, const float* __restrict__ d, int ldd, const float* __restrict__ w, int act_below,
-                                                        const float* __restrict__ Y, int ldy, float* __restrict__ dX, int ldx,
-                                                        const float* __restrict__ Yt, int ldyt, float* __restrict__ dXt, int ldxt) {
-  const long total = (long)N * in;
+/* dX[b][i] = d[b] * w[i] times the activation derivative below; 4 elements per thread.  Work items
+ * [0, N*in/4): row-major output; [N*in/4, ...): the transposed copy (TF32 path), read from the
+ * transposed activation so both halves are fully coalesced.                                       */
+template <bool VEC>
+__global__ void __launch_bounds__(256) fc1_dgrad_kernel(int N, int in, const float* __restrict__ d, int ldd, const float* __restrict__ dT,
+                                                        const float* __restrict__ w, int act_below, const float* __restrict__ Y, int ldy,
+                                                        float* __restrict__ dX, int ldx, const float* __restrict__ Yt, int ldyt,
+                                                        float* __restrict__ dXt, int ldxt) {
   const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g < total) {
-    const int n = (int)(g / in), i = (int)(g - (long)n * in);
-    const float v = __fmul_rn(w[i], d[(size_t)n * ldd]);
-    dX[(size_t)n * ldx + i] = act_backward(act_below, v, act_below != PS_ACT_NONE ? Y[(size_t)n * ldy + i] : 1.f);
-  } else if (dXt != nullptr && g < 2 * total) {
-    const long h = g - total;
-    const int i = (int)(h / N), n = (int)(h - (long)i * N);
-    const float v = __fmul_rn(w[i], d[(size_t)n * ldd]);
-    dXt[(size_t)i * ldxt + n] = act_backward(act_below, v, act_below != PS_ACT_NONE ? Yt[(size_t)i * ldyt + n] : 1.f);
+  if (VEC) {
+    const int in4 = in >> 2, n4 = (N + 3) >> 2;
+    const long rowwork = (long)N * in4;
+    if (g < rowwork) {
+      const int n = (int)(g / in4), i = (int)(g - (long)n * in4) << 2;
+      const float dv = d[(size_t)n * ldd];
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + i));
+      float4 y = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (act_below != PS_ACT_NONE) y = ld_f4(Y + (size_t)n * ldy + i);
+      float4 v;
+      v.x = act_backward(act_below, __fmul_rn(wv.x, dv), y.x); v.y = act_backward(act_below, __fmul_rn(wv.y, dv), y.y);
+      v.z = act_backward(act_below, __fmul_rn(wv.z, dv), y.z); v.w = act_backward(act_below, __fmul_rn(wv.w, dv), y.w);
+      st_f4(dX + (size_t)n * ldx + i, v);
+    } else if (dXt != nullptr && g < rowwork + (long)in * n4) {
+      const long h = g - rowwork;
+      const int i = (int)(h / n4), n = (int)(h - (long)i * n4) << 2;
+      const float wi = __ldg(w + i);
+      float dv[4], yv[4] = {1.f, 1.f, 1.f, 1.f};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dv[k] = n + k < N ? (dT ? dT[n + k] : d[(size_t)(n + k) * ldd]) : 0.f;
+      if (act_below != PS_ACT_NONE) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (n + k < N) yv[k] = Yt[(size_t)i * ldyt + n + k];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (n + k < N) dXt[(size_t)i * ldxt + n + k] = act_backward(act_below, __fmul_rn(wi, dv[k]), yv[k]);
+    }
+  } else {
+    const long total = (long)N * in;
+    if (g < total) {
+      const int n = (int)(g / in), i = (int)(g - (long)n * in);
+      const float v = __fmul_rn(w[i], d[(size_t)n * ldd]);
+      dX[(size_t)n * ldx + i] = act_backward(act_below, v, act_below != PS_ACT_NONE ? Y[(size_t)n * ldy + i] : 1.f);
+    } else if (dXt != nullptr && g < 2 * total) {
+      const long h = g - total;
+      const int i = (int)(h / N), n = (int)(h - (long)i * N);
+      const float v = __fmul_rn(w[i], d[(size_t)n * ldd]);
+      dXt[(size_t)i * ldxt + n] = act_backward(act_below, v, act_below != PS_ACT_NONE ? Yt[(size_t)i * ldyt + n] : 1.f);
+    }
   }
 }
-void fc1_dgrad(Ctx* ctx, int N, int in, const float* d, int ldd, const float* w, int act_below, const float* Y, int ldy, float* dX, int ldx,
-               const float* Yt, int ldyt, float* dXt, int ldxt) {
-  const long total = (long)N * in * (dXt ? 2 : 1);
-  fc1_dgrad_kernel<<<ceil_div(total, 256), 256, 0, ctx->stream>>>(N, in, d, ldd, w, act_below, Y, ldy, dX, ldx, Yt, ldyt, dXt, ldxt);
+void fc1_dgrad(Ctx* ctx, int N, int in, const float* d, int ldd, const float* dT, const float* w, int act_below, const float* Y, int ldy, float* dX,
+               int ldx, const float* Yt, int ldyt, float* dXt, int ldxt) {
+  const bool vec = (in % 4 == 0) && (ldy % 4 == 0) && (ldx % 4 == 0);
+  if (vec) {
+    const long total = (long)N * (in / 4) + (dXt ? (long)in * ((N + 3) / 4) : 0);
+    fc1_dgrad_kernel<true><<<ceil_div(total, 256), 256, 0, ctx->stream>>>(N, in, d, ldd, dT, w, act_below, Y, ldy, dX, ldx, Yt, ldyt, dXt, ldxt);
+  } else {
+    const long total = (long)N * in * (dXt ? 2 : 1);
+    fc1_dgrad_kernel<false><<<ceil_div(total, 256), 256, 0, ctx->stream>>>(N, in, d, ldd, dT, w, act_below, Y, ldy, dX, ldx, Yt, ldyt, dXt, ldxt);
+  }
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }

@@ -56,7 +56,7 @@ void tail_softmax(Ctx* ctx, int N, int C, float* Z, int ldz, const float* Y, flo
 /* the 1-unit top FcLayer on CUDA cores (see dense.cu): forward GEMV fused with the binary tail, dgrad, wgrad */
 void fc1_forward_tail(Ctx* ctx, int N, int in, const float* A, int lda, const float* w, const float* bias, const float* zwide, const float* Y,
                       float* z_out, int ldz, float* p_out, int ldp, float* d_out, int ldd, float* dt_out, int train, StepStatus* st, float* ws);
-void fc1_dgrad(Ctx* ctx, int N, int in, const float* d, int ldd, const float* w, int act_below, const float* Y, int ldy, float* dX, int ldx,
+void fc1_dgrad(Ctx* ctx, int N, int in, const float* d, int ldd, const float* dT /* contiguous copy of d or null */, const float* w, int act_below, const float* Y, int ldy, float* dX, int ldx,
                const float* Yt, int ldyt, float* dXt, int ldxt);
 void fc1_wgrad(Ctx* ctx, int N, int in, const float* d, int ldd, const float* A, int lda, float* G, size_t slab, int nsplit);
 

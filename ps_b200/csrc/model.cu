@@ -245,7 +245,7 @@ void Model::dgrad_layer(int l, int N) {              /* FcLayer.backward: delta 
   const FcLayer& f = fcs[l];
   const int act_below = l > 0 ? fcs[l - 1].act : PS_ACT_NONE;
   if (l == L - 1 && top_is_unit()) {
-    fc1_dgrad(ctx, N, f.in, delta[L], ld[L], f.W, act_below, act[l], ld[l], delta[l], ld[l], act_t[l], ldt, (!fp32 && l > 0) ? delta_t[l] : nullptr, ldt);
+    fc1_dgrad(ctx, N, f.in, delta[L], ld[L], fp32 ? nullptr : delta_t[L], f.W, act_below, act[l], ld[l], delta[l], ld[l], act_t[l], ldt, (!fp32 && l > 0) ? delta_t[l] : nullptr, ldt);
     return;
   }
   FcDgradArgs d{};

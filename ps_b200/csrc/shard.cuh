@@ -15,6 +15,10 @@ void shard_count(Ctx* ctx, const int64_t* E, int N, int F, int R, int32_t* count
 /* send_keys: packed keys grouped by owner (group r starts at sum(counts[:r])); send_pos[l] = index of
  * lookup l in that buffer; cursor: R zeroed ints of scratch                                           */
 void shard_place(Ctx* ctx, const int64_t* E, int N, int F, int R, const int32_t* counts, int32_t* cursor, uint64_t* send_keys, int32_t* send_pos);
+/* fixed-capacity routing (graph-capturable: no count reaches the host): bucket r = send_keys[r*cap, (r+1)*cap),
+ * unused entries EMPTY; send_pos[l] = r*cap + position or -1 on overflow (then *overflow = 1)      */
+void shard_place_padded(Ctx* ctx, const int64_t* E, int N, int F, int R, int cap, int32_t* cursor, uint64_t* send_keys, int32_t* send_pos,
+                        int32_t* overflow);
 /* out[n*ldo + j*D + d] = rows[send_pos[n*F+j]*Dp + d]  (rows come back already ReLU'd by their owner) */
 void shard_unpack(Ctx* ctx, const float* rows, const int32_t* send_pos, int N, int F, int D, int Dp, float* out, int ldo);
 /* grads[send_pos[l]*Dp + d] = delta[n*ldd + j*D + d] * (act[n*lda + j*D + d] > 0)   (EmbeddingField.java:91-93) */

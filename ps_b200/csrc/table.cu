@@ -61,25 +61,31 @@ __global__ void __launch_bounds__(256) emb_probe_kernel(EmbSlot* __restrict__ sl
                                                         const IdT* __restrict__ ids, int L, int F, uint64_t seed, float maxv,
                                                         int32_t* __restrict__ lk_slot, uint32_t umask,
                                                         uint32_t* __restrict__ counters) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  /* field-major work order (t = j*N + n): the 32 lanes of a warp probe the SAME field for consecutive
+   * samples, so a hot key (a low-cardinality field) is counted with one L2 atomic per warp, not 32 */
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   int slot = -1;
   bool first = false;
-  if (l < L) {
+  if (t < L) {
+    int l = t;
+    if (F > 0) { const int N = L / F; const int j = t / N; l = (t - j * N) * F + j; }
     const unsigned long long key = F > 0 ? ps_pack_key((uint32_t)(l % F), (uint64_t)(int64_t)ids[l]) : (unsigned long long)ids[l];
-    bool inserted;
-    slot = emb_find_or_insert(slots, C, key, &inserted);
-    lk_slot[l] = slot;
-    if (slot < 0) counters[1] = 1u;
-    else {
-      if (inserted) {
+    if (key != PS_KEY_EMPTY) {                 /* EMPTY marks padding in the fixed-capacity sharded exchange */
+      bool inserted;
+      slot = emb_find_or_insert(slots, C, key, &inserted);
+      if (slot < 0) counters[1] = 1u;
+      else if (inserted) {
         float* row = w + (size_t)slot * Dp;
         for (int d = 0; d < D; ++d) row[d] = ps_init_value(seed, key, (uint32_t)d, maxv);
         atomicAdd(reinterpret_cast<unsigned long long*>(counters + 2), 1ull);
       }
-      first = atomicAdd(&slots[slot].cnt, 1u) == 0u;   /* first occurrence in this batch: number the unique key */
     }
+    lk_slot[l] = slot;
   }
+  /* warp-aggregated occurrence count: lanes holding the same slot add once */
+  const unsigned peers = __match_any_sync(0xffffffffu, slot >= 0 ? slot : (-1 - lane));
+  if (slot >= 0 && (__ffs(peers) - 1) == lane) first = atomicAdd(&slots[slot].cnt, (uint32_t)__popc(peers)) == 0u;
   /* one atomic per warp on the unique-key counter instead of one per unique key.  The counter is
    * MONOTONIC across batches (no per-step reset node): accumulator rows are a ring indexed by
    * counter & umask, and every entry is zeroed again by the group that consumed it.             */

@@ -71,6 +71,71 @@ class ShardedTrainer:
         return ops.loss()
 
 
+class GraphedShardedTrainer:
+    """The sharded step with FIXED per-owner bucket capacity, captured once into a CUDA graph per rank
+    (local kernels + the NCCL collectives) and replayed: no host synchronisation inside a step, one graph
+    launch per step.  Buckets are padded with the EMPTY key, which owners skip.  If a bucket ever
+    overflows (`overflow` flag, checked by check()), use ShardedTrainer (exact sizes) for that workload
+    or raise `slack`."""
+
+    def __init__(self, ops, rank, world, N, F, has_wide, group=None, slack=2.0):
+        self.ops, self.rank, self.world, self.group, self.N, self.F, self.has_wide = ops, rank, world, group, N, F, has_wide
+        L = N * F
+        self.cap = int(-(-int(L / world * slack + 64) // 32) * 32) if world > 1 else L
+        self.graph, self.static = None, None
+
+    def _body(self, E, X, W, Y):
+        ops, R, N, cap = self.ops, self.world, self.N, self.cap
+        send_keys, send_pos = ops.route_padded(E, R, cap)
+        recv_keys = ops.empty(R * cap, torch.int64)
+        dist.all_to_all_single(recv_keys, send_keys, group=self.group)
+        rows_out = ops.lookup(recv_keys)
+        rows_back = ops.empty((R * cap, rows_out.shape[1]), torch.float32)
+        dist.all_to_all_single(rows_back, rows_out, group=self.group)
+        ops.unpack(rows_back, send_pos, N)
+        W_all = None
+        if W is not None and self.has_wide:
+            W_all = ops.empty((R * N,) + tuple(W.shape[1:]), torch.int64)
+            dist.all_gather_into_tensor(W_all, W, group=self.group)
+        ops.dense_step(X, W, W_all, Y, N)
+        dist.all_reduce(ops.grad_buffer(), group=self.group)
+        grads_send = ops.pack_grads_padded(send_pos, N, R * cap)
+        grads_recv = ops.empty((R * cap, grads_send.shape[1]), torch.float32)
+        dist.all_to_all_single(grads_recv, grads_send, group=self.group)
+        ops.finish(N * R, R)
+        ops.apply(grads_recv)
+
+    def step(self, E, X, W, Y, warmup_eager=2):
+        """Enqueues one step (asynchronous).  The first calls run eagerly (allocations, NCCL warm-up), then
+        the step is captured; afterwards each call copies the inputs into the graph's static buffers and
+        replays.  Returns nothing: read the loss with ops.loss() when needed."""
+        ops = self.ops
+        with ops.scope():
+            if self.static is None:
+                self.static = {"E": E.clone(), "X": X.clone(), "W": None if W is None else W.clone(), "Y": Y.clone()}
+                self.calls = 0
+            st = self.static
+            st["E"].copy_(E); st["X"].copy_(X); st["Y"].copy_(Y)
+            if W is not None:
+                st["W"].copy_(W)
+            if self.graph is None and self.calls < warmup_eager:
+                self._body(st["E"], st["X"], st["W"], st["Y"])
+                self.calls += 1
+                return
+            if self.graph is None:
+                ops.synchronize()
+                dist.barrier(group=self.group)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=ops.stream, capture_error_mode="thread_local"):
+                    self._body(st["E"], st["X"], st["W"], st["Y"])
+                self.graph = g
+            self.graph.replay()
+
+    def check(self):
+        if self.ops.overflowed():
+            raise RuntimeError("sharded exchange bucket overflow: raise slack or use ShardedTrainer")
+
+
 class _DevArray:
     def __init__(self, ptr, n, typestr="<f4"):
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
@@ -112,6 +177,27 @@ class GpuOps:
         self.ps.check(self.lib.ps_shard_route_dev(self.ctx.h, self._ptr(E), N, F, R, self._ptr(send_keys), self._ptr(send_pos),
                                                   self._ptr(counts), self._ptr(cursor)))
         return send_keys, send_pos, counts
+
+    def route_padded(self, E, R, cap):
+        N, F = E.shape
+        send_keys, send_pos = self.empty(R * cap, torch.int64), self.empty(N * F, torch.int32)
+        if not hasattr(self, "_cursor"):
+            self._cursor, self._overflow = self.empty(64, torch.int32), torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.ps.check(self.lib.ps_shard_route_padded_dev(self.ctx.h, self._ptr(E), N, F, R, cap, self._ptr(send_keys), self._ptr(send_pos),
+                                                         self._ptr(self._cursor), self._ptr(self._overflow)))
+        return send_keys, send_pos
+
+    def overflowed(self):
+        return hasattr(self, "_overflow") and bool(self._overflow.item())
+
+    def synchronize(self):
+        self.ctx.synchronize()
+        torch.cuda.synchronize(self.device)
+
+    def pack_grads_padded(self, send_pos, N, rows):
+        g = self.empty((rows, self.Dp), torch.float32)
+        self.ps.check(self.lib.ps_model_shard_pack_grads_dev(self.model.h, self._ptr(send_pos), N, self._ptr(g)))
+        return g
 
     def lookup(self, keys):
         n = keys.numel()

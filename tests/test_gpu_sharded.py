@@ -18,7 +18,7 @@ sys.path.insert(0, HERE)
 
 pytestmark = pytest.mark.gpu
 SEED = 20261017
-CFG = dict(kind="widedeep", F=23, D=16, Xn=45, fc=[64, 32, 1], N=192, V=4000, steps=3)
+CFG = dict(kind="widedeep", F=23, D=16, Xn=45, fc=[64, 32, 1], N=192, V=4000, steps=4)
 
 
 def batches(R, cfg):
@@ -27,23 +27,27 @@ def batches(R, cfg):
     return [syn.batch(R * cfg["N"]) for _ in range(cfg["steps"])]
 
 
-def worker(rank, R, port, out, cfg, emb_opt):
+def worker(rank, R, port, out, cfg, emb_opt, graphed):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=R, device_id=torch.device("cuda", rank))
     from ps_b200 import binding as ps
-    from ps_b200.sharded import GpuOps, ShardedTrainer
+    from ps_b200.sharded import GpuOps, GraphedShardedTrainer, ShardedTrainer
     ctx = ps.Context(rank, seed=SEED)
     upd = ps.UpdaterSpec.ftrl() if emb_opt == "ftrl" else None
     m = ps.Model(ctx, cfg["kind"], cfg["F"], cfg["D"], cfg["Xn"], cfg["fc"], emb_capacity=1 << 16, emb_updater=upd, max_batch=cfg["N"])
-    tr = ShardedTrainer(GpuOps(ps, ctx, m, rank), rank, R)
+    ops = GpuOps(ps, ctx, m, rank)
     N = cfg["N"]
+    tr = GraphedShardedTrainer(ops, rank, R, N, cfg["F"], cfg["kind"] == "widedeep", slack=3.0) if graphed else ShardedTrainer(ops, rank, R)
     losses, keys = [], set()
     for b in batches(R, cfg):
         sl = slice(rank * N, (rank + 1) * N)
         dev = {k: torch.from_numpy(np.ascontiguousarray(v[sl])).cuda(rank) for k, v in b.items()}
-        losses.append(tr.step(dev["E"], dev["X"], dev["W"] if cfg["kind"] == "widedeep" else None, dev["Y"]))
+        r = tr.step(dev["E"], dev["X"], dev["W"] if cfg["kind"] == "widedeep" else None, dev["Y"])
+        losses.append(ops.loss() if graphed else r)
+        if graphed:
+            tr.check()
         for n in range(0, R * N, 7):
             for j in range(cfg["F"]):
                 keys.add((j, int(b["E"][n, j])))
@@ -68,8 +72,8 @@ def worker(rank, R, port, out, cfg, emb_opt):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("R,emb_opt", [(1, "adam"), (2, "adam"), (2, "ftrl")])
-def test_sharded_step_matches_oracle_global_batch(tmp_path, R, emb_opt):
+@pytest.mark.parametrize("R,emb_opt,graphed", [(1, "adam", False), (1, "adam", True), (2, "adam", False), (2, "ftrl", False), (2, "adam", True)])
+def test_sharded_step_matches_oracle_global_batch(tmp_path, R, emb_opt, graphed):
     if torch.cuda.device_count() < R:
         pytest.skip(f"needs {R} GPUs")
     import __graft_entry__ as g
@@ -79,7 +83,7 @@ def test_sharded_step_matches_oracle_global_batch(tmp_path, R, emb_opt):
     port = s.getsockname()[1]
     s.close()
     cfg = CFG
-    mp.spawn(worker, args=(R, port, str(tmp_path), cfg, emb_opt), nprocs=R, join=True)
+    mp.spawn(worker, args=(R, port, str(tmp_path), cfg, emb_opt, graphed), nprocs=R, join=True)
     res = [torch.load(os.path.join(tmp_path, f"r{r}.pt"), weights_only=False) for r in range(R)]
     import oracle_lib as ol
     o = ol.OracleModel(ol.KIND_WIDEDEEP, cfg["F"], cfg["D"], cfg["Xn"], cfg["fc"], SEED, emb_opt=1 if emb_opt == "ftrl" else 0)
