@@ -341,14 +341,18 @@ def main():
             "cpu_baseline": cpu, "loss": loss, "loss_e2e": loss_e2e, "unique_keys_per_batch": uniq,
         }
         print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    if world > 1:
+        # captured NCCL graphs + communicator teardown order is fragile: everything is measured and printed, leave hard
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        dist.barrier()
+        os._exit(0)
     for pb in pinned:
         for pa in pb.values():
             pa.free()
     model.close()
     ctx.close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

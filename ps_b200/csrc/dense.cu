@@ -174,7 +174,7 @@ void updater_apply(Ctx* ctx, const UpdaterDev& u, float* w, float* s1, float* s2
 
 /* ------------------------------------------------------------------ tails */
 constexpr int kTailThreads = 256;
-constexpr int kTailMaxBlocks = 64;
+constexpr int kTailMaxBlocks = 1024;
 
 __device__ __forceinline__ float block_sum(float v, float* sh) {
   const int t = threadIdx.x;
@@ -204,7 +204,7 @@ __device__ __forceinline__ void tail_finish(float loss_part, float d_part, int N
   __syncthreads();
   if (!is_last) return;
   float l = 0.0f, d = 0.0f;
-  if (threadIdx.x < gridDim.x) { l = __ldcg(ws + 2 * threadIdx.x); d = __ldcg(ws + 2 * threadIdx.x + 1); }
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) { l = __fadd_rn(l, __ldcg(ws + 2 * b)); d = __fadd_rn(d, __ldcg(ws + 2 * b + 1)); }
   l = block_sum(l, sh); d = block_sum(d, sh);
   if (threadIdx.x == 0) {
     const float loss = __fdiv_rn(l, (float)N);
@@ -307,28 +307,23 @@ __global__ void __launch_bounds__(kTailThreads) fc1_forward_tail_kernel(int N, i
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   const bool vec = (in % 4 == 0) && (lda % 4 == 0);
   float loss_part = 0.0f, d_part = 0.0f;
-  /* a warp owns 32 consecutive samples: 32 cooperative dot products (lane j keeps the j-th), then the
-   * double-precision sigmoid / log work runs on all 32 lanes at once */
-  for (int nb = warp * 32; nb < N; nb += nwarps * 32) {
-    float zmine = 0.0f;
-    for (int j = 0; j < 32 && nb + j < N; ++j) {
-      const float* a = A + (size_t)(nb + j) * lda;
-      float acc = 0.0f;
-      if (vec) {
-        for (int c = lane * 4; c < in; c += 128) {
-          const float4 x = ld_f4(a + c), y = __ldg(reinterpret_cast<const float4*>(w + c));
-          acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
-        }
-      } else {
-        for (int c = lane; c < in; c += 32) acc = fmaf(a[c], __ldg(w + c), acc);
+  /* one warp per sample: a cooperative 128-bit dot product (one L2 round trip), then lane 0 runs the
+   * scalar tail; 8 samples per block keep thousands of warps in flight instead of a serial chain */
+  for (int n = warp; n < N; n += nwarps) {
+    const float* a = A + (size_t)n * lda;
+    float acc = 0.0f;
+    if (vec) {
+      for (int c = lane * 4; c < in; c += 128) {
+        const float4 x = ld_f4(a + c), y = __ldg(reinterpret_cast<const float4*>(w + c));
+        acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == j) zmine = acc;
+    } else {
+      for (int c = lane; c < in; c += 32) acc = fmaf(a[c], __ldg(w + c), acc);
     }
-    const int n = nb + lane;
-    if (n < N) {
-      float z = __fadd_rn(zmine, bias[0]);                                     /* FcLayer.java:76-77 */
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      float z = __fadd_rn(acc, bias[0]);                                       /* FcLayer.java:76-77 */
       z_out[(size_t)n * ldz] = z;
       if (zwide) z = __fadd_rn(z, zwide[n]);                                   /* AddLayer.java:36 */
       const float p = sigmoid_clipped(z);                                      /* Sigmoid.java:11 */
@@ -350,7 +345,7 @@ __global__ void __launch_bounds__(kTailThreads) fc1_forward_tail_kernel(int N, i
 }
 void fc1_forward_tail(Ctx* ctx, int N, int in, const float* A, int lda, const float* w, const float* bias, const float* zwide, const float* Y,
                       float* z_out, int ldz, float* p_out, int ldp, float* d_out, int ldd, float* dt_out, int train, StepStatus* st, float* ws) {
-  const int blocks = std::max(1, std::min(kTailMaxBlocks, ceil_div(ceil_div(N, 32) * 32L, kTailThreads)));
+  const int blocks = std::max(1, std::min(kTailMaxBlocks, ceil_div((long)N * 32, kTailThreads)));
   fc1_forward_tail_kernel<<<blocks, kTailThreads, 0, ctx->stream>>>(N, in, A, lda, w, bias, zwide, Y, z_out, ldz, p_out, ldp, d_out, ldd, dt_out, train, st, ws);
   PS_LAUNCH_CHECK();
   ctx->launches++;

@@ -44,7 +44,7 @@ void fill_column(Ctx* ctx, float* buf, int ld, int col, int rows, float value);
 /* also publishes the step status to mapped host memory when host_mapped is non-null */
 void dense_update(Ctx* ctx, const DenseUpdateArgs& a, StepStatus* st, const uint32_t* emb_counters, const uint32_t* wide_counters,
                   StepStatus* host_mapped);
-constexpr int kTailWorkspaceFloats = 2 * 64 + 4;
+constexpr int kTailWorkspaceFloats = 2 * 1024 + 4;
 
 /* binary tail: z = deep (+ wide); p = clipped sigmoid; CrossEntropy forward/backward; sigmoid
  * derivative.  Writes p to p_out (stride ldp), the post-derivative delta to d_out (stride ldd). */

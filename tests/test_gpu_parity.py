@@ -198,7 +198,7 @@ def _compare_models(m, o, F, fc, tol, keys_sample, kind, err=None):
             for which in (0, 1):
                 so = o.get_state(nm, which)
                 if so is not None:
-                    assert err(m.get_state(nm, which), so) <= 10 * tol, (nm, which)
+                    assert err(m.get_state(nm, which), so) <= (10 * tol if err is rel_err else 50 * tol), (nm, which)
     bad = 0
     for key in keys_sample:
         wo = o.get(key)
