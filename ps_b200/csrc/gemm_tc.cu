@@ -33,7 +33,9 @@ namespace psb {
 
 namespace {
 
-constexpr int BM = 128, BK = 32, STAGES = 4, UMMA_K = 8;
+constexpr int BM = 128, BK = 32, UMMA_K = 8;
+/* pipeline depth: 8 stages cover a whole K = 256 operand in ONE L2 round trip; the 3xTF32 stages are twice as large */
+template <bool SPLIT> struct Depth { static constexpr int STAGES = SPLIT ? 4 : 8; };
 enum { EPI_FWD = 0, EPI_DGRAD = 1, EPI_WGRAD = 2 };
 
 struct TcParams {
@@ -111,6 +113,7 @@ template <int BLOCK_N, bool SPLIT>
 struct SmemLayout {
   static constexpr uint32_t A_BYTES = BM * BK * 4;
   static constexpr uint32_t B_BYTES = BLOCK_N * BK * 4;
+  static constexpr int STAGES = Depth<SPLIT>::STAGES;
   static constexpr uint32_t STAGE_BYTES = (SPLIT ? 2u : 1u) * (A_BYTES + B_BYTES);
   static constexpr uint32_t BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr uint32_t TOTAL = BAR_OFF + 256 + 1024;   /* + barriers/tmem slot + manual 1024 B alignment slack */
@@ -120,6 +123,7 @@ template <int BLOCK_N, int EPI, bool SPLIT>
 __global__ void __launch_bounds__(128) gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                         const TcParams p) {
   using SL = SmemLayout<BLOCK_N, SPLIT>;
+  constexpr int STAGES = SL::STAGES;
   constexpr int TMEM_COLS = BLOCK_N <= 32 ? 32 : (BLOCK_N <= 64 ? 64 : (BLOCK_N <= 128 ? 128 : 256));
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;

@@ -86,17 +86,27 @@ __global__ void __launch_bounds__(256) emb_probe_kernel(EmbSlot* __restrict__ sl
   /* warp-aggregated occurrence count: lanes holding the same slot add once */
   const unsigned peers = __match_any_sync(0xffffffffu, slot >= 0 ? slot : (-1 - lane));
   if (slot >= 0 && (__ffs(peers) - 1) == lane) first = atomicAdd(&slots[slot].cnt, (uint32_t)__popc(peers)) == 0u;
-  /* one atomic per warp on the unique-key counter instead of one per unique key.  The counter is
-   * MONOTONIC across batches (no per-step reset node): accumulator rows are a ring indexed by
-   * counter & umask, and every entry is zeroed again by the group that consumed it.             */
+  /* ONE atomic per block on the unique-key counter (a single address: per-warp atomics with return
+   * serialise in one L2 slice).  The counter is MONOTONIC across batches (no per-step reset node):
+   * accumulator rows are a ring indexed by counter & umask, and every entry is zeroed again by the
+   * group that consumed it.                                                                       */
+  __shared__ uint32_t warp_firsts[8];
+  __shared__ uint32_t block_base;
   const unsigned firsts = __ballot_sync(0xffffffffu, first);
-  if (firsts == 0u) return;
-  const int leader = __ffs(firsts) - 1;
-  uint32_t base = 0;
-  if (lane == leader) base = atomicAdd(&counters[0], (uint32_t)__popc(firsts));
-  base = __shfl_sync(0xffffffffu, base, leader);
+  const int wid = threadIdx.x >> 5;
+  if (lane == 0) warp_firsts[wid] = (uint32_t)__popc(firsts);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t total = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) total += warp_firsts[i];
+    block_base = total ? atomicAdd(&counters[0], total) : 0u;
+  }
+  __syncthreads();
   if (first) {
-    slots[slot].uidx = (base + (uint32_t)__popc(firsts & ((1u << lane) - 1u))) & umask;
+    uint32_t before = 0;
+    for (int i = 0; i < wid; ++i) before += warp_firsts[i];
+    slots[slot].uidx = (block_base + before + (uint32_t)__popc(firsts & ((1u << lane) - 1u))) & umask;
   }
 }
 

@@ -263,7 +263,10 @@ def test_model_steps_match_oracle_fp32(ps, ctx, kind, F, D, Xn, fc, N, V, mode):
     b = syn.batch(N)
     pg = m.predict(b["E"], b["X"], b["W"], N)
     po = o.predict(b["E"], b["X"], b["W"], N)
-    assert np.allclose(pg, po, rtol=1e-4, atol=1e-6)
+    if mode == "fp32":
+        assert np.allclose(pg, po, rtol=1e-4, atol=1e-6)
+    else:
+        assert fro_err(pg, po) <= 50 * tol
     m.close()
 
 
