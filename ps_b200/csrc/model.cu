@@ -272,10 +272,37 @@ void Model::fork(cudaStream_t from, cudaStream_t to) {
   PS_CUDA(cudaStreamWaitEvent(to, e, 0));
 }
 
+void Model::forward_backward(const int64_t* W, const int64_t* W_all, int n_all, const float* Y, int N, bool train, bool wide_update_now) {
+  cudaStream_t s = ctx->stream, s1 = aux[0], s2 = aux[1];
+  const bool fp32 = ctx->fc_precision == PS_FC_FP32;
+  fork(s, s2);
+  if (!fp32 && train) { StreamScope sc(ctx, s2); transpose_copy(ctx, act[0], ld[0], act_t[0], ldt, N, width[0]); }   /* only wgrad0 needs it */
+  for (int l = 0; l < L; ++l) {
+    fwd_layer(l, N);
+    mark(("fc_fwd" + std::to_string(l)).c_str());
+  }
+  fork(s1, s);                                   /* wide_z (the caller started the wide branch on side stream 1) */
+  run_tail(Y, N, train);
+  mark("tail");
+  if (!train) return;
+  /* ---- backward (DNN.java:64-68): the dgrad chain is the critical path; each wgrad runs beside it ---- */
+  if (has_wide && wide_update_now) {
+    fork(s, s2);
+    StreamScope sc(ctx, s2);
+    wide.update_all(gbar_ptr(st_dev), skip_ptr(st_dev), wide_bias, &upd_wide);
+  }
+  for (int l = L - 1; l >= 0; --l) {
+    fork(s, s1);                                 /* delta[l+1] (tail or dgrad(l+1)) is ready */
+    if (l == 0) fork(s2, s1);                    /* act_t[0] */
+    { StreamScope sc(ctx, s1); wgrad_layer(l, N); }
+    dgrad_layer(l, N);
+    mark(("fc_dgrad" + std::to_string(l)).c_str());
+  }
+}
+
 void Model::step_device(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, bool train, StepStatus* publish_to) {
   PS_REQUIRE(N > 0 && N <= Bmax, PS_ERR_ARG, "model: batch size must be in [1, max_batch]");
   cudaStream_t s = ctx->stream, s1 = aux[0], s2 = aux[1];
-  const bool fp32 = ctx->fc_precision == PS_FC_FP32;
   mark("begin");
   /* ---- forward (DNN.java:44-46) ---- */
   fork(s, s1);
@@ -288,30 +315,12 @@ void Model::step_device(const int64_t* E, const float* X, const int64_t* W, cons
   } else {
     PS_CUDA(cudaMemcpy2DAsync(act[0], sizeof(float) * ld[0], X, sizeof(float) * Xn, sizeof(float) * Xn, N, cudaMemcpyDeviceToDevice, s));
   }
-  fork(s, s2);
-  if (!fp32 && train) { StreamScope sc(ctx, s2); transpose_copy(ctx, act[0], ld[0], act_t[0], ldt, N, width[0]); }   /* only wgrad0 needs it */
-  for (int l = 0; l < L; ++l) {
-    fwd_layer(l, N);
-    mark(("fc_fwd" + std::to_string(l)).c_str());
-  }
-  fork(s1, s);                                   /* wide_z */
-  run_tail(Y, N, train);
-  mark("tail");
+  forward_backward(W, nullptr, 0, Y, N, train, true);
   if (!train) {
     if (has_emb) emb.clear_batch();
     if (publish_to) publish_status(ctx, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, publish_to);
     fork(s2, s);
     return;
-  }
-  /* ---- backward (DNN.java:64-68): the dgrad chain is the critical path; each wgrad runs beside it ---- */
-  fork(s, s2);
-  if (has_wide) { StreamScope sc(ctx, s2); wide.update_all(gbar_ptr(st_dev), skip_ptr(st_dev), wide_bias, &upd_wide); }
-  for (int l = L - 1; l >= 0; --l) {
-    fork(s, s1);                                 /* delta[l+1] (tail or dgrad(l+1)) is ready */
-    if (l == 0) fork(s2, s1);                    /* act_t[0] */
-    { StreamScope sc(ctx, s1); wgrad_layer(l, N); }
-    dgrad_layer(l, N);
-    mark(("fc_dgrad" + std::to_string(l)).c_str());
   }
   /* ---- KVStore.update + clear (Trainer.java:93,95) ---- */
   fork(s, s1);                                   /* every dgrad has read W / Wt: the dense update may overwrite them */
@@ -358,18 +367,18 @@ void Model::shard_unpack_rows(const float* rows, const int32_t* send_pos, int N)
  * then the per-rank gradient sums and scalars go into ONE flat buffer for the all-reduce.      */
 void Model::shard_dense_step(const float* X, const int64_t* W_local, const int64_t* W_all, int n_all, const float* Y, int N) {
   PS_REQUIRE(N > 0 && N <= Bmax, PS_ERR_ARG, "model: batch size must be in [1, max_batch]");
-  cudaStream_t s = ctx->stream;
-  const bool fp32 = ctx->fc_precision == PS_FC_FP32;
-  if (has_emb) PS_CUDA(cudaMemcpy2DAsync(act[0] + F * D, sizeof(float) * ld[0], X, sizeof(float) * Xn, sizeof(float) * Xn, N, cudaMemcpyDeviceToDevice, s));
-  else PS_CUDA(cudaMemcpy2DAsync(act[0], sizeof(float) * ld[0], X, sizeof(float) * Xn, sizeof(float) * Xn, N, cudaMemcpyDeviceToDevice, s));
-  if (!fp32) transpose_copy(ctx, act[0], ld[0], act_t[0], ldt, N, width[0]);
+  cudaStream_t s = ctx->stream, s1 = aux[0], s2 = aux[1];
+  fork(s, s1);
   if (has_wide) {
+    StreamScope sc(ctx, s1);
     wide.insert(W_all, n_all);                     /* the union of every replica's keys */
     wide.forward(W_local, N, F, wide_bias, wide_z);
   }
-  for (int l = 0; l < L; ++l) fwd_layer(l, N);
-  run_tail(Y, N, true);
-  for (int l = L - 1; l >= 0; --l) { wgrad_layer(l, N); dgrad_layer(l, N); }
+  if (has_emb) PS_CUDA(cudaMemcpy2DAsync(act[0] + F * D, sizeof(float) * ld[0], X, sizeof(float) * Xn, sizeof(float) * Xn, N, cudaMemcpyDeviceToDevice, s));
+  else PS_CUDA(cudaMemcpy2DAsync(act[0], sizeof(float) * ld[0], X, sizeof(float) * Xn, sizeof(float) * Xn, N, cudaMemcpyDeviceToDevice, s));
+  forward_backward(W_local, W_all, n_all, Y, N, true, false);
+  fork(s1, s);                                     /* all wgrads */
+  fork(s2, s);
   const DenseUpdateArgs u = dense_args(N);
   if (!gsum) { gsum_len = u.total + 2; gsum = dmalloc_zero<float>((size_t)gsum_len, s); }
   dense_reduce(ctx, u, st_dev, gsum);

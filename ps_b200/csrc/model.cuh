@@ -96,6 +96,10 @@ struct Model {
   void run_tail(const float* Y, int N, bool train);
   void wgrad_layer(int l, int N);
   void dgrad_layer(int l, int N);
+  /* everything between "act[0] is filled" and "delta[0] is ready": wide branch (side stream 1), FcLayer
+   * forward, tail, dgrad chain on the main stream with each wgrad beside it on side stream 1.  On return
+   * the main stream holds delta[0]; side stream 1 holds the wgrads; side stream 2 the transposes / wide update. */
+  void forward_backward(const int64_t* W, const int64_t* W_all, int n_all, const float* Y, int N, bool train, bool wide_update_now);
   void step_device(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, bool train, StepStatus* publish_to);
   /* the same through the graph cache (falls back to direct launches while profiling) */
   void run_step(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, bool train, StepStatus* publish_to);
