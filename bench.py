@@ -146,7 +146,9 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--config", default="cfg2")
     ap.add_argument("--dist", default="zipf")
-    ap.add_argument("--precision", default=os.environ.get("PS_FC_PRECISION", "fp32"))
+    # FcLayer arithmetic: tf32x3 = tcgen05 tensor cores with error-compensated operand split (fp32-grade results, the
+    # default: the reference computes in fp32); tf32 = plain TF32 tensor cores; fp32 = FFMA exact mode
+    ap.add_argument("--precision", default=os.environ.get("PS_FC_PRECISION", "tf32x3"))
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--ring", type=int, default=16)
     ap.add_argument("--slack", type=float, default=2.0)
@@ -232,6 +234,8 @@ def main():
     barrier()
     ms_dev = e0.elapsed_time(e1)
     launches = ctx.launch_count() - l0
+    if trainer is not None:
+        launches = args.steps * getattr(trainer, "launches_per_step", 0)   # graph replays: counted at the eager warm-up step
     if world > 1:
         t = torch.tensor([ms_dev], device=f"cuda:{local_rank}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -120,7 +120,7 @@ struct SmemLayout {
 };
 
 template <int BLOCK_N, int EPI, bool SPLIT>
-__global__ void __launch_bounds__(128) gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+__global__ void __launch_bounds__(SPLIT ? 256 : 128) gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                         const TcParams p) {
   using SL = SmemLayout<BLOCK_N, SPLIT>;
   constexpr int STAGES = SL::STAGES;
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(128) gemm_tf32_kernel(const __grid_constant__ 
   const int num_kb = max(0, min(nkb_total, kb_begin + p.kb_per_split) - kb_begin);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); mbar_init(split0 + 8 * s, 64); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); mbar_init(split0 + 8 * s, 192); }
     mbar_init(tfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -197,9 +197,9 @@ __global__ void __launch_bounds__(128) gemm_tf32_kernel(const __grid_constant__ 
     }
     if (num_kb > 0) tc_commit(tfull);          /* accumulator complete */
   } else if (SPLIT && warp >= 2) {
-    /* ===== residual producers (64 threads): lo = x - tf32(x), element-wise, so the swizzled tile
+    /* ===== residual producers (warps 2-7, 192 threads): lo = x - tf32(x), element-wise, so the swizzled tile
      * layout carries over byte for byte; generic-proxy stores are fenced for the async proxy ===== */
-    const int t = threadIdx.x - 64;
+    const int t = threadIdx.x - 64;                 /* 0..191 */
     constexpr int CHUNKS = (int)((SL::A_BYTES + SL::B_BYTES) / 16);
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % STAGES;
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(128) gemm_tf32_kernel(const __grid_constant__ 
       uint8_t* src = gen_base + s * SL::STAGE_BYTES;
       uint8_t* dst = src + OFF_ALO;
 #pragma unroll 4
-      for (int c = t; c < CHUNKS; c += 64) {
+      for (int c = t; c < CHUNKS; c += 192) {
         const float4 x = *reinterpret_cast<const float4*>(src + 16 * c);
         float4 hi, lo;
         hi.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); lo.x = x.x - hi.x;
@@ -227,6 +227,7 @@ __global__ void __launch_bounds__(128) gemm_tf32_kernel(const __grid_constant__ 
    * All TMEM loads of the tile are issued first; the epilogue operands (bias: warp-uniform; the
    * activation of the layer below for its derivative: read from the TRANSPOSED copy, so the 32
    * lanes = 32 consecutive rows read one 128 B line per column) are fetched while they fly.   */
+  if (warp < 4) {   /* the four TMEM lane quadrants; with SPLIT warps 4-7 only produced residual tiles */
   constexpr int NCH = BLOCK_N / 16;
   const int m = m0 + warp * 32 + lane;
   const bool row_ok = m < p.M;
@@ -290,6 +291,7 @@ __global__ void __launch_bounds__(128) gemm_tf32_kernel(const __grid_constant__ 
       }
     }
   }
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -345,7 +347,7 @@ void launch_tc(Ctx* ctx, const float* A, long lda, const float* B, long ldb, TcP
   const int nkb = (p.K + BK - 1) / BK;
   p.kb_per_split = (nkb + nsplit - 1) / nsplit;
   dim3 grid(ceil_div(p.N, BLOCK_N), ceil_div(p.M, BM), nsplit);
-  gemm_tf32_kernel<BLOCK_N, EPI, SPLIT><<<grid, 128, SL::TOTAL, ctx->stream>>>(ta, tb, p);
+  gemm_tf32_kernel<BLOCK_N, EPI, SPLIT><<<grid, SPLIT ? 256 : 128, SL::TOTAL, ctx->stream>>>(ta, tb, p);
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }

@@ -119,7 +119,9 @@ class GraphedShardedTrainer:
             if W is not None:
                 st["W"].copy_(W)
             if self.graph is None and self.calls < warmup_eager:
+                l0 = ops.ctx.launch_count()
                 self._body(st["E"], st["X"], st["W"], st["Y"])
+                self.launches_per_step = ops.ctx.launch_count() - l0      # this library's kernels per step (NCCL's not counted)
                 self.calls += 1
                 return
             if self.graph is None:
