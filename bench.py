@@ -318,8 +318,13 @@ def main():
                 us = gt[f"fc{l}.{n}"]
                 kernels[f"fc{l}.{n}"] = {"us": us, "tflops": 2.0 * B * dims[l] * dims[l + 1] / max(us, 1e-3) / 1e6}
         dom = max(alg, key=lambda k: kernels[k]["us"])
+        traffic = None                      # dram__bytes_read+write per launch from the committed ncu --set full capture
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tp) and args.config == "cfg2":
+            tk = json.load(open(tp))["kernels"].get({"emb_gather": "emb_gather_kernel", "emb_scatter_update": "emb_scatter_update_kernel"}[dom])
+            traffic = tk["dram_bytes_per_launch"] if tk else None
         roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": kernels[dom]["gbs"] / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "frac": kernels[dom]["gbs"] / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                     "how": "algorithmic bytes (SURVEY 8d) / mean device time of the kernel replayed 64x in a CUDA graph over the batch ring "
                            "(CUDA events on the library's stream); emb_gather includes its probe kernel"}
 
