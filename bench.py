@@ -152,6 +152,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--ring", type=int, default=16)
     ap.add_argument("--slack", type=float, default=2.0)
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     rank = int(os.environ.get("RANK", "0"))
@@ -200,9 +201,13 @@ def main():
     # Trainer step on the concatenated batch (ps_b200/sharded.py); per-GPU batch fixed => weak scaling
     trainer = None
     if world > 1:
-        from ps_b200.sharded import GpuOps, GraphedShardedTrainer
-        # the whole sharded step (local kernels + NCCL collectives, fixed-capacity buckets) is one CUDA graph per rank
-        trainer = GraphedShardedTrainer(GpuOps(ps, ctx, model, local_rank), rank, world, B, F, cfg["kind"] == "widedeep", slack=args.slack)
+        from ps_b200.sharded import GpuOps, GraphedShardedTrainer, P2PShardedTrainer
+        if args.exchange == "p2p":
+            # every exchange is a store into the consumer's HBM over NVLink by the kernel that produced the data
+            trainer = P2PShardedTrainer(ps, ctx, model, rank, world, B, F, slack=args.slack, device=local_rank)
+        else:
+            # the whole sharded step (local kernels + NCCL collectives, fixed-capacity buckets) is one CUDA graph per rank
+            trainer = GraphedShardedTrainer(GpuOps(ps, ctx, model, local_rank), rank, world, B, F, cfg["kind"] == "widedeep", slack=args.slack)
 
     def dev_step(i):
         d = dev_ring[i % len(dev_ring)]
@@ -235,7 +240,8 @@ def main():
     ms_dev = e0.elapsed_time(e1)
     launches = ctx.launch_count() - l0
     if trainer is not None:
-        launches = args.steps * getattr(trainer, "launches_per_step", 0)   # graph replays: counted at the eager warm-up step
+        if hasattr(trainer, "launches_per_step"):
+            launches = args.steps * trainer.launches_per_step               # torch graph replays: counted at the eager warm-up step
     if world > 1:
         t = torch.tensor([ms_dev], device=f"cuda:{local_rank}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -341,7 +347,9 @@ def main():
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "f32 via 3xTF32 tcgen05"}[args.precision], "data": "synthetic",
             "config": {"workload": workload_name(args, cfg), "global_batch": B * world,
-                       "parallelism": f"key-hash sharded embedding table over {world} GPUs (NCCL all-to-all) + data-parallel dense" if world > 1 else "single",
+                       "parallelism": (f"key-hash sharded embedding table over {world} GPUs, exchange={args.exchange} "
+                                       f"({'NVLink peer-memory stores, no collective calls' if args.exchange == 'p2p' else 'NCCL all-to-all'}) "
+                                       "+ data-parallel dense") if world > 1 else "single",
                        "l2": "embedding table + optimiser state (%.0f MB) exceeds the 126 MB L2; a ring of %d distinct batches; no flush" % (
                            cap * (16 + 12 * D) / 1e6, len(ring))},
             "e2e": {"value": total / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,

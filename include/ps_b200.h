@@ -203,6 +203,20 @@ int ps_model_shard_finish_dev(ps_model* m, int N_global, int R);
 /* PServer.push + psUpdate (net/PServer.java:164-214) for the rows this rank owns: fused scatter + update */
 int ps_model_shard_apply_dev(ps_model* m, const float* grads_recv_dev, int n);
 
+/* ---- the same sharded step over NVLink PEER MEMORY (no collective library on the data path) --------
+ * Every rank maps every peer's mailbox slab (CUDA IPC); the kernel that produces a bucket (routed keys,
+ * gathered rows, row gradients, dense gradient sums, wide ids) stores it straight into the consumer's HBM
+ * through NVSwitch and publishes a flag; consumers run a one-warp wait kernel.  A whole step is ONE CUDA
+ * graph per rank: ps_model_p2p_step_dev enqueues it (asynchronous), ps_model_read_loss reads the result.
+ *   ps_model_p2p_init    → allocates the slab, returns its 64-byte cudaIpcMemHandle_t
+ *   [host: all-gather the R handles, e.g. torch.distributed.all_gather]
+ *   ps_model_p2p_connect → opens the peers' slabs (rank order); all ranks must then barrier once
+ * cap = capacity of one per-owner bucket (>= the most lookups one rank sends to one owner in a step). */
+int ps_model_p2p_init(ps_model* m, int R, int rank, int cap, void* ipc_handle_out64);
+int ps_model_p2p_connect(ps_model* m, const void* all_handles /* R x 64 bytes */);
+int ps_model_p2p_step_dev(ps_model* m, const int64_t* E_dev, const float* X_dev, const int64_t* W_dev, const float* Y_dev, int N);
+int ps_model_p2p_overflowed(ps_model* m, int* out);   /* a bucket exceeded cap at some step: results invalid, raise cap */
+
 /* ---- test hooks -------------------------------------------------------------------- */
 /* C (M x N, row-major, ldc) = A (M x K, row-major, lda) * B^T (B is N x K, row-major, ldb),
  * through the FcLayer GEMM of the given precision mode.                                      */

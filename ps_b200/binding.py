@@ -98,6 +98,10 @@ SYMBOLS = {
     "ps_model_shard_pack_grads_dev": (_i, [_vp, _vp, _i, _vp]),
     "ps_model_shard_finish_dev": (_i, [_vp, _i, _i]),
     "ps_model_shard_apply_dev": (_i, [_vp, _vp, _i]),
+    "ps_model_p2p_init": (_i, [_vp, _i, _i, _i, _vp]),
+    "ps_model_p2p_connect": (_i, [_vp, _vp]),
+    "ps_model_p2p_step_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _i]),
+    "ps_model_p2p_overflowed": (_i, [_vp, C.POINTER(_i)]),
     "ps_test_gemm_nt": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i]),
 }
 

@@ -512,6 +512,32 @@ int ps_model_shard_apply_dev(ps_model* m, const float* grads_recv_dev, int n) {
   PS_CATCH
 }
 
+int ps_model_p2p_init(ps_model* m, int R, int rank, int cap, void* ipc_handle_out64) {
+  PS_TRY
+  PS_REQUIRE(m && ipc_handle_out64, PS_ERR_ARG, "null argument");
+  m->m.p2p_init(R, rank, cap, ipc_handle_out64);
+  PS_CATCH
+}
+int ps_model_p2p_connect(ps_model* m, const void* all_handles) {
+  PS_TRY
+  PS_REQUIRE(m && all_handles, PS_ERR_ARG, "null argument");
+  m->m.p2p_connect(all_handles);
+  PS_CATCH
+}
+int ps_model_p2p_step_dev(ps_model* m, const int64_t* E_dev, const float* X_dev, const int64_t* W_dev, const float* Y_dev, int N) {
+  PS_TRY
+  PS_REQUIRE(m && X_dev && Y_dev, PS_ERR_ARG, "null argument");
+  PS_REQUIRE(m->m.in_flight == 0, PS_ERR_STATE, "host steps in flight; collect first");
+  m->m.run_step(E_dev, X_dev, W_dev, Y_dev, N, true, nullptr, 1);
+  PS_CATCH
+}
+int ps_model_p2p_overflowed(ps_model* m, int* out) {
+  PS_TRY
+  PS_REQUIRE(m && out, PS_ERR_ARG, "null argument");
+  *out = m->m.p2p.slab ? (m->m.p2p.overflowed() ? 1 : 0) : 0;
+  PS_CATCH
+}
+
 /* ---- test hook ---- */
 int ps_test_gemm_nt(ps_ctx* ctx, int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc) {
   PS_TRY

@@ -122,7 +122,8 @@ void Model::destroy() {
   for (auto p : delta_t) dfree(p);
   if (has_emb) emb.destroy();
   if (has_wide) { wide.destroy(); dfree(wide_bias); dfree(wide_z); dfree(P); }
-  dfree(st_dev); dfree(tail_ws); dfree(gsum);
+  dfree(st_dev); dfree(tail_ws); dfree(gsum); dfree(send_pos);
+  if (p2p.slab) p2p.destroy();
   for (auto& g : graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
   graphs.clear();
   for (auto& S : stage) {
@@ -162,15 +163,15 @@ static const float* gbar_ptr(const StepStatus* st) {
   return reinterpret_cast<const float*>(reinterpret_cast<const char*>(st) + offsetof(StepStatus, gbar));
 }
 
-void Model::run_step(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, bool train, StepStatus* publish_to) {
+void Model::run_step(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, bool train, StepStatus* publish_to, int mode) {
   PS_REQUIRE(N > 0 && N <= Bmax, PS_ERR_ARG, "model: batch size must be in [1, max_batch]");
   if (!use_graph) {
     ev_n = 0; ev_names.clear();
-    step_device(E, X, W, Y, N, train, publish_to);
+    if (mode == 1) p2p_step(E, X, W, Y, N); else step_device(E, X, W, Y, N, train, publish_to);
     phase_names = ev_names;
     return;
   }
-  const auto key = std::make_tuple((const void*)E, (const void*)X, (const void*)W, (const void*)Y, N, (train ? 1 : 0) | (profile ? 2 : 0),
+  const auto key = std::make_tuple((const void*)E, (const void*)X, (const void*)W, (const void*)Y, N, (train ? 1 : 0) | (profile ? 2 : 0) | (mode << 2),
                                    (const void*)publish_to, ctx->fc_precision);
   auto it = graphs.find(key);
   if (it == graphs.end()) {
@@ -182,7 +183,7 @@ void Model::run_step(const int64_t* E, const float* X, const int64_t* W, const f
     cudaGraph_t graph = nullptr;
     PS_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
     capturing = true; ev_n = 0; ev_names.clear();
-    try { step_device(E, X, W, Y, N, train, publish_to); }
+    try { if (mode == 1) p2p_step(E, X, W, Y, N); else step_device(E, X, W, Y, N, train, publish_to); }
     catch (...) { capturing = false; cudaStreamEndCapture(ctx->stream, &graph); if (graph) cudaGraphDestroy(graph); throw; }
     capturing = false;
     PS_CUDA(cudaStreamEndCapture(ctx->stream, &graph));
@@ -405,6 +406,67 @@ void Model::shard_emb_apply(const float* grads_recv, int n) {
   PS_REQUIRE(has_emb, PS_ERR_STATE, "model has no embedding layer");
   if (n > 0) emb.scatter_update(grads_recv, emb.Dp, nullptr, emb.Dp, n, 2, skip_ptr(st_dev), 1);
   else emb.last_L = 0;
+}
+
+/* ------------------------------------------------------------------ sharded step over peer memory */
+void Model::p2p_init(int R, int rank, int cap, void* handle_out64) {
+  PS_REQUIRE(!p2p.slab, PS_ERR_STATE, "p2p already initialised");
+  const DenseUpdateArgs u = dense_args(1);
+  const long glen = (u.total + 2 + 3) / 4 * 4;
+  if (!gsum) { gsum_len = glen; gsum = dmalloc_zero<float>((size_t)gsum_len, ctx->stream); }
+  PS_REQUIRE(gsum_len >= glen, PS_ERR_STATE, "gradient buffer was created before p2p_init with a smaller size");
+  p2p.create(ctx, R, rank, has_emb ? cap : 1, has_emb ? emb.Dp : 4, std::max(2, Bmax * std::max(F, 1)), (int)glen);
+  if (has_emb) { send_pos = dmalloc<int32_t>((size_t)Bmax * F); emb.reserve((int64_t)R * cap); }
+  p2p.get_handle(handle_out64);
+}
+
+void Model::p2p_connect(const void* all_handles) { p2p.connect(all_handles); }
+
+/* one Trainer step of the R-rank group on the concatenated batch, this rank's share: every exchange is a
+ * store into the consumer's mailbox by the kernel that produced the data (see p2p.cuh)              */
+void Model::p2p_step(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N) {
+  PS_REQUIRE(p2p.connected, PS_ERR_STATE, "p2p_step before p2p_connect");
+  PS_REQUIRE(N > 0 && N <= Bmax, PS_ERR_ARG, "model: batch size must be in [1, max_batch]");
+  cudaStream_t s = ctx->stream, s1 = aux[0], s2 = aux[1];
+  const int R = p2p.R, cap = p2p.cap;
+  p2p.begin();
+  if (has_emb) p2p.route_send(E, N, F, send_pos);                               /* PSRouterClient.getList: keys out */
+  if (has_wide) {
+    PS_REQUIRE(((size_t)N * F * 8) % 16 == 0, PS_ERR_ARG, "p2p: N*F must be even");
+    p2p.bcast(W, (size_t)N * F * 8, CH_WIDE);
+  }
+  fork(s, s1);
+  if (has_wide) {
+    StreamScope sc(ctx, s1);
+    p2p.wait(CH_WIDE);
+    wide.insert(nullptr, R * N * F, p2p.state());                               /* the union of every replica's keys */
+    wide.forward(W, N, F, wide_bias, wide_z);
+  }
+  if (has_emb) {
+    p2p.wait(CH_KEYS);
+    emb.probe_packed(nullptr, R * cap, p2p.state());                            /* PServer.getList on the owner */
+    p2p.gather_send(emb.w, D, emb.lk_slot);                                     /* rows back, stored by the gather itself */
+    p2p.wait(CH_ROWS);
+    p2p.unpack(send_pos, N, F, D, act[0], ld[0]);
+    PS_CUDA(cudaMemcpy2DAsync(act[0] + F * D, sizeof(float) * ld[0], X, sizeof(float) * Xn, sizeof(float) * Xn, N, cudaMemcpyDeviceToDevice, s));
+  } else {
+    PS_CUDA(cudaMemcpy2DAsync(act[0], sizeof(float) * ld[0], X, sizeof(float) * Xn, sizeof(float) * Xn, N, cudaMemcpyDeviceToDevice, s));
+  }
+  forward_backward(W, nullptr, 0, Y, N, true, false);
+  fork(s1, s);
+  fork(s2, s);
+  const DenseUpdateArgs u = dense_args(N);
+  dense_reduce(ctx, u, st_dev, gsum);                                           /* local dense gradient sums + loss + gbar */
+  p2p.bcast(gsum, (size_t)p2p.glen * 4, CH_GSUM);                               /* PServer sync mode: everybody's push */
+  if (has_emb) p2p.pack_send(delta[0], ld[0], act[0], ld[0], send_pos, N, F, D); /* client.push of the row gradients */
+  p2p.wait(CH_GSUM);
+  p2p.reduce_gsum(gsum);
+  shard_finish(N * R, R);                                                       /* psUpdate for dense + wide keys */
+  if (has_emb) {
+    p2p.wait(CH_GRADS);
+    emb.scatter_update(nullptr, emb.Dp, nullptr, emb.Dp, R * cap, 2, skip_ptr(st_dev), 1, p2p.state());
+  }
+  last_N = N; last_train = true;
 }
 
 void Model::kernel_times(const int64_t* const* E_ring, int n_ring, int N, int reps, float* out) {

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "dense.cuh"
 #include "gemm.cuh"
+#include "p2p.cuh"
 #include "shard.cuh"
 #include "table.cuh"
 
@@ -102,7 +103,7 @@ struct Model {
   void forward_backward(const int64_t* W, const int64_t* W_all, int n_all, const float* Y, int N, bool train, bool wide_update_now);
   void step_device(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, bool train, StepStatus* publish_to);
   /* the same through the graph cache (falls back to direct launches while profiling) */
-  void run_step(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, bool train, StepStatus* publish_to);
+  void run_step(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, bool train, StepStatus* publish_to, int mode = 0);
   /* ---- key-hash sharded (multi-GPU) step, split at the exchanges ---- */
   float* gsum = nullptr; long gsum_len = 0;          /* flat [dense gradient sums | loss | gbar]: the all-reduce buffer */
   DenseUpdateArgs dense_args(int N);
@@ -117,6 +118,12 @@ struct Model {
   void kernel_times(const int64_t* const* E_ring, int n_ring, int N, int reps, float* out);
   /* the same for the FcLayer GEMMs on the buffers of the last step: out[3*l + {0,1,2}] = {forward, dgrad, wgrad} of layer l */
   void gemm_times(int N, int reps, float* out);
+  /* ---- the same sharded step over NVLink peer memory (p2p.cuh): no collective calls, one CUDA graph per rank ---- */
+  P2P p2p;
+  int32_t* send_pos = nullptr;
+  void p2p_init(int R, int rank, int cap, void* handle_out64);
+  void p2p_connect(const void* all_handles);
+  void p2p_step(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N);
   void submit(const HostBatch& b);
   float collect();
   float read_loss();

@@ -1,0 +1,77 @@
+/*
+ * p2p.cuh — the sharded exchange over NVLink peer memory.
+ *
+ * net/PSRouterClient.java:60-151 fans a batch of keys out to the PS shards over gRPC and merges
+ * the answers; on one B200 box every GPU maps every peer's mailbox slab (CUDA IPC) and the
+ * kernels that PRODUCE a bucket store it straight into the consumer's HBM through NVSwitch:
+ * the pack step and the transfer are one kernel, there is no collective call and no host
+ * involvement — a whole sharded step is one CUDA graph per rank.
+ *
+ * Mailbox slab of a rank (double-buffered by step parity p = seq & 1):
+ *   keys_in [p][R][cap]      u64   packed keys sent by rank r                (getList request)
+ *   rows_in [p][R][cap][Dp]  f32   rows returned by owner r                  (getList response)
+ *   grads_in[p][R][cap][Dp]  f32   row gradients pushed by rank r            (push)
+ *   wide_in [p][R][NF]       i64   wide ids of rank r                        (replicated wide table)
+ *   gsum_in [p][R][glen]     f32   dense gradient sums + loss + gbar of r    (PServer sync-mode sum)
+ *   counts  [p][R]           i32   number of valid keys from rank r
+ *   flags   [p][CH][R]       u32   step sequence number, written last with release.sys
+ * A producer kernel stores its payload into the consumer's slab, fences (system scope), and its
+ * last block publishes the flag; the consumer's stream runs a one-warp wait kernel (acquire.sys
+ * spin) before the kernels that read the mailbox.  Every send precedes the matching wait in every
+ * rank's program order, so there is no circular wait; ranks can drift by at most one step, which
+ * the parity double-buffering covers.
+ */
+#pragma once
+#include "common.cuh"
+
+namespace psb {
+
+constexpr int kP2PMaxRanks = 8;
+enum { CH_KEYS = 0, CH_ROWS = 1, CH_GRADS = 2, CH_WIDE = 3, CH_GSUM = 4, CH_COUNT = 5 };
+
+struct P2PState {                      /* lives in device memory; kernels read it, p2p_begin advances seq */
+  int R, me, cap, Dp, NF, glen;
+  unsigned char* peer[kP2PMaxRanks];   /* base of every rank's slab as mapped into THIS process */
+  size_t off_keys, off_rows, off_grads, off_wide, off_gsum, off_counts, off_flags, parity_stride;
+  uint32_t seq;
+  int32_t cursor[kP2PMaxRanks];
+  uint32_t done[CH_COUNT];
+  int32_t overflow;
+};
+
+struct P2P {
+  Ctx* ctx = nullptr;
+  int R = 0, me = 0, cap = 0, Dp = 0, NF = 0, glen = 0;
+  size_t slab_bytes = 0;
+  unsigned char* slab = nullptr;       /* this rank's mailbox */
+  void* peer_mapped[kP2PMaxRanks] = {};
+  P2PState host{};
+  P2PState* dev = nullptr;
+  bool connected = false;
+
+  void create(Ctx* c, int R_, int me_, int cap_, int Dp_, int NF_, int glen_);
+  void get_handle(void* out64);                                  /* cudaIpcMemHandle_t of the slab */
+  void connect(const void* all_handles /* R x 64 bytes, rank order */);
+  void destroy();
+
+  /* --- kernels (asynchronous on ctx->stream) --- */
+  void begin();                                                                     /* seq += 1, cursors = 0 */
+  void route_send(const int64_t* E, int N, int F, int32_t* send_pos);               /* keys → owners' keys_in */
+  void bcast(const void* src, size_t bytes, int channel);                           /* wide ids / gsum → every peer */
+  void wait(int channel);
+  void gather_send(const float* w, int D, const int32_t* lk_slot);                  /* rows → requesters' rows_in */
+  void unpack(const int32_t* send_pos, int N, int F, int D, float* out, int ldo);   /* rows_in → concat buffer */
+  void reduce_gsum(float* gsum);                                                    /* sum over ranks, fixed order */
+  void pack_send(const float* delta, int ldd, const float* act, int lda, const int32_t* send_pos, int N, int F, int D);
+  /* device addresses inside the LOCAL slab for the current parity are resolved in-kernel from seq */
+  const P2PState* state() const { return dev; }
+  bool overflowed();
+};
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ unsigned char* p2p_region(const P2PState* st, int rank, size_t off) {
+  return st->peer[rank] + (size_t)(st->seq & 1u) * st->parity_stride + off;
+}
+#endif
+
+}  // namespace psb

@@ -15,6 +15,7 @@
 #include <cmath>
 #include <vector>
 
+#include "p2p.cuh"
 #include "table.cuh"
 
 namespace psb {
@@ -60,7 +61,7 @@ template <class IdT>
 __global__ void __launch_bounds__(256) emb_probe_kernel(EmbSlot* __restrict__ slots, uint32_t C, float* __restrict__ w, int Dp, int D,
                                                         const IdT* __restrict__ ids, int L, int F, uint64_t seed, float maxv,
                                                         int32_t* __restrict__ lk_slot, uint32_t umask,
-                                                        uint32_t* __restrict__ counters) {
+                                                        uint32_t* __restrict__ counters, const P2PState* __restrict__ p2p) {
   /* field-major work order (t = j*N + n): the 32 lanes of a warp probe the SAME field for consecutive
    * samples, so a hot key (a low-cardinality field) is counted with one L2 atomic per warp, not 32 */
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -69,8 +70,17 @@ __global__ void __launch_bounds__(256) emb_probe_kernel(EmbSlot* __restrict__ sl
   bool first = false;
   if (t < L) {
     int l = t;
-    if (F > 0) { const int N = L / F; const int j = t / N; l = (t - j * N) * F + j; }
-    const unsigned long long key = F > 0 ? ps_pack_key((uint32_t)(l % F), (uint64_t)(int64_t)ids[l]) : (unsigned long long)ids[l];
+    unsigned long long key = PS_KEY_EMPTY;
+    if (p2p != nullptr) {                      /* owner side of the peer-memory exchange: this step's keys_in mailbox */
+      const int src = t / p2p->cap, idx = t - src * p2p->cap;
+      if (idx < reinterpret_cast<const int32_t*>(p2p_region(p2p, p2p->me, p2p->off_counts))[src])
+        key = reinterpret_cast<const unsigned long long*>(p2p_region(p2p, p2p->me, p2p->off_keys))[t];
+    } else if (F > 0) {
+      const int N = L / F; const int j = t / N; l = (t - j * N) * F + j;
+      key = ps_pack_key((uint32_t)(l % F), (uint64_t)(int64_t)ids[l]);
+    } else {
+      key = (unsigned long long)ids[l];
+    }
     if (key != PS_KEY_EMPTY) {                 /* EMPTY marks padding in the fixed-capacity sharded exchange */
       bool inserted;
       slot = emb_find_or_insert(slots, C, key, &inserted);
@@ -171,7 +181,8 @@ __global__ void __launch_bounds__(256) emb_scatter_update_kernel(EmbSlot* __rest
                                                                  int N, int F, const float* __restrict__ delta, int ldd,
                                                                  const float* __restrict__ act, int lda, float* __restrict__ acc,
                                                                  uint32_t* __restrict__ arrived, UpdaterDev upd, int calls,
-                                                                 const int* __restrict__ skip_flag) {
+                                                                 const int* __restrict__ skip_flag, const P2PState* __restrict__ p2p) {
+  if (p2p != nullptr) delta = reinterpret_cast<const float*>(p2p_region(p2p, p2p->me, p2p->off_grads));   /* this step's grads_in mailbox */
   const bool skip = skip_flag != nullptr && *skip_flag != 0;
   const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long L = (long)N * F;
@@ -345,19 +356,19 @@ void EmbTable::probe(const int64_t* ids_i64, const float* ids_f32, int N) {
   last_L = L;
   const int grid = ceil_div(L, 256);
   if (ids_i64)
-    emb_probe_kernel<int64_t><<<grid, 256, 0, ctx->stream>>>(slots, (uint32_t)C, w, Dp, D, ids_i64, (int)L, F, ctx->seed, maxv, lk_slot, ucap - 1, counters);
+    emb_probe_kernel<int64_t><<<grid, 256, 0, ctx->stream>>>(slots, (uint32_t)C, w, Dp, D, ids_i64, (int)L, F, ctx->seed, maxv, lk_slot, ucap - 1, counters, nullptr);
   else
-    emb_probe_kernel<float><<<grid, 256, 0, ctx->stream>>>(slots, (uint32_t)C, w, Dp, D, ids_f32, (int)L, F, ctx->seed, maxv, lk_slot, ucap - 1, counters);
+    emb_probe_kernel<float><<<grid, 256, 0, ctx->stream>>>(slots, (uint32_t)C, w, Dp, D, ids_f32, (int)L, F, ctx->seed, maxv, lk_slot, ucap - 1, counters, nullptr);
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }
 
-void EmbTable::probe_packed(const uint64_t* keys, int n) {
+void EmbTable::probe_packed(const uint64_t* keys, int n, const P2PState* p2p) {
   reserve(n);
   last_L = n;
   if (n <= 0) return;
   emb_probe_kernel<unsigned long long><<<ceil_div(n, 256), 256, 0, ctx->stream>>>(slots, (uint32_t)C, w, Dp, D, reinterpret_cast<const unsigned long long*>(keys), n, 0,
-                                                                                  ctx->seed, maxv, lk_slot, ucap - 1, counters);
+                                                                                  ctx->seed, maxv, lk_slot, ucap - 1, counters, p2p);
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }
@@ -387,27 +398,29 @@ void EmbTable::gather(float* out, int ldo, int N, int F_eff, const float* X, int
 }
 
 template <int TPL>
-static void launch_scatter(EmbTable& t, const float* delta, int ldd, const float* act, int lda, int N, int F, int calls, const int* skip) {
+static void launch_scatter(EmbTable& t, const float* delta, int ldd, const float* act, int lda, int N, int F, int calls, const int* skip,
+                           const P2PState* p2p) {
   const long L = (long)N * F;
   const bool aligned = (t.D % 4 == 0) && (ldd % 4 == 0) && (lda % 4 == 0) && ((uintptr_t)delta % 16 == 0) && ((uintptr_t)act % 16 == 0);
   const int grid = ceil_div(L * TPL, 256);
   if (aligned)
-    emb_scatter_update_kernel<TPL, true><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.w, t.s1, t.s2, t.Dp, t.D, t.lk_slot, N, F, delta, ldd, act, lda, t.acc, t.arrived, t.upd, calls, skip);
+    emb_scatter_update_kernel<TPL, true><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.w, t.s1, t.s2, t.Dp, t.D, t.lk_slot, N, F, delta, ldd, act, lda, t.acc, t.arrived, t.upd, calls, skip, p2p);
   else
-    emb_scatter_update_kernel<TPL, false><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.w, t.s1, t.s2, t.Dp, t.D, t.lk_slot, N, F, delta, ldd, act, lda, t.acc, t.arrived, t.upd, calls, skip);
+    emb_scatter_update_kernel<TPL, false><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.w, t.s1, t.s2, t.Dp, t.D, t.lk_slot, N, F, delta, ldd, act, lda, t.acc, t.arrived, t.upd, calls, skip, p2p);
 }
 
-void EmbTable::scatter_update(const float* delta, int ldd, const float* act, int lda, int N, int calls, const int* skip_flag, int F_eff) {
+void EmbTable::scatter_update(const float* delta, int ldd, const float* act, int lda, int N, int calls, const int* skip_flag, int F_eff,
+                              const P2PState* p2p) {
   const int Fe = F_eff > 0 ? F_eff : F;
   PS_REQUIRE((int64_t)N * Fe == last_L, PS_ERR_STATE, "embedding: backward without a matching forward");
   PS_REQUIRE(calls == 1 || calls == 2, PS_ERR_ARG, "embedding: backward calls must be 1 or 2");
   switch (tpl) {
-    case 1: launch_scatter<1>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag); break;
-    case 2: launch_scatter<2>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag); break;
-    case 4: launch_scatter<4>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag); break;
-    case 8: launch_scatter<8>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag); break;
-    case 16: launch_scatter<16>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag); break;
-    default: launch_scatter<32>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag); break;
+    case 1: launch_scatter<1>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
+    case 2: launch_scatter<2>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
+    case 4: launch_scatter<4>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
+    case 8: launch_scatter<8>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
+    case 16: launch_scatter<16>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
+    default: launch_scatter<32>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
   }
   PS_LAUNCH_CHECK();
   ctx->launches++;
@@ -539,9 +552,10 @@ __global__ void __launch_bounds__(256) wide_update_all_kernel(WideSlot* __restri
 
 /* replicas of the wide table must know every key any rank has seen (LRLayer.weights never shrinks) */
 __global__ void __launch_bounds__(256) wide_insert_kernel(WideSlot* __restrict__ slots, uint32_t C, const int64_t* __restrict__ ids, int n,
-                                                          uint32_t* __restrict__ counters) {
+                                                          uint32_t* __restrict__ counters, const P2PState* __restrict__ p2p) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (p2p != nullptr) ids = reinterpret_cast<const int64_t*>(p2p_region(p2p, p2p->me, p2p->off_wide));   /* this step's wide_in mailbox */
   bool inserted;
   const int slot = wide_find_or_insert(slots, C, ps_pack_key(0u, (uint64_t)ids[i]), true, &inserted);
   if (slot < 0) counters[0] = 1u;
@@ -575,9 +589,9 @@ void WideTable::forward(const int64_t* ids, int N, int F, const float* bias, flo
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }
-void WideTable::insert(const int64_t* ids, int n) {
+void WideTable::insert(const int64_t* ids, int n, const P2PState* p2p) {
   if (n <= 0) return;
-  wide_insert_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(slots, (uint32_t)C, ids, n, counters);
+  wide_insert_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(slots, (uint32_t)C, ids, n, counters, p2p);
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }

@@ -22,6 +22,8 @@
 #include "common.cuh"
 #include "updaters.cuh"
 
+namespace psb { struct P2PState; }
+
 namespace psb {
 
 struct __align__(16) EmbSlot {
@@ -62,12 +64,12 @@ struct EmbTable {
   void probe(const int64_t* ids_i64, const float* ids_f32, int N);
   /* out[n*ldo + j*D + d] = relu(w[slot(n,j)][d])   (EmbeddingField.java:73-76)               */
   /* the same on already-packed keys (owner side of the key-hash sharded exchange): n lookups, one "field" */
-  void probe_packed(const uint64_t* keys, int n);
+  void probe_packed(const uint64_t* keys, int n, const P2PState* p2p = nullptr);   /* p2p: keys come from this step's mailbox */
   /* X != null: also copies the numeric features X[N][Xn] to columns [xoff, xoff+Xn) (ConcatLayer) */
   void gather(float* out, int ldo, int N, int F_eff = 0, const float* X = nullptr, int Xn = 0, int xoff = 0);
   /* fused scatter-add + occurrence normalisation + updater step (see table.cu)               */
   void scatter_update(const float* delta, int ldd, const float* act /* null: mask already applied */, int lda, int N, int calls,
-                      const int* skip_flag, int F_eff = 0);
+                      const int* skip_flag, int F_eff = 0, const P2PState* p2p = nullptr /* delta = this step's grads_in mailbox */);
   /* forget the batch without updating (predict path / early exit): cnt = 0 for touched slots */
   void clear_batch();
   void check_errors();                 /* syncs; throws PS_ERR_CAPACITY if an insert found the table full */
@@ -88,7 +90,7 @@ struct WideTable {
   void destroy();
   /* z[n] = bias + sum_j w[W[n][j]]  in j order (LRLayer.java:70-84); inserts unseen keys with w = 0 */
   void forward(const int64_t* ids, int N, int F, const float* bias, float* z);
-  void insert(const int64_t* ids, int n);   /* create keys other replicas saw (multi-GPU) */
+  void insert(const int64_t* ids, int n, const P2PState* p2p = nullptr);   /* create keys other replicas saw (multi-GPU) */
   /* LRLayer.backward pushes the SAME batch-mean delta to every key ever seen (LRLayer.java:110-117,
    * SURVEY quirk 7): sweep all occupied slots and apply the updater with g = *gbar.             */
   void update_all(const float* gbar, const int* skip_flag, float* bias /* {w,s1,s2} or null */, const ps_updater_spec* bias_upd);

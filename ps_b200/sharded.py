@@ -138,6 +138,41 @@ class GraphedShardedTrainer:
             raise RuntimeError("sharded exchange bucket overflow: raise slack or use ShardedTrainer")
 
 
+class P2PShardedTrainer:
+    """The sharded step over NVLink peer memory (ps_b200/csrc/p2p.cu): torch.distributed is used ONCE, to
+    exchange the CUDA-IPC handles of the mailbox slabs; afterwards a step is a single C call that
+    replays one CUDA graph per rank — no collective library, no host synchronisation on the data path."""
+
+    def __init__(self, ps, ctx, model, rank, world, N, F, group=None, slack=2.0, device=None):
+        self.ps, self.ctx, self.model, self.rank, self.world, self.group = ps, ctx, model, rank, world, group
+        self.lib = ps.lib()
+        L = N * max(F, 1)
+        self.cap = int(-(-int(L / world * slack + 64) // 32) * 32) if world > 1 else L
+        dev = torch.device("cuda", rank if device is None else device)
+        handle = (C.c_ubyte * 64)()
+        ps.check(self.lib.ps_model_p2p_init(model.h, world, rank, self.cap, handle))
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+        allh = torch.empty(64 * world, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        buf = (C.c_ubyte * (64 * world))(*allh.cpu().tolist())
+        ps.check(self.lib.ps_model_p2p_connect(model.h, buf))
+        dist.barrier(group=group)                 # every slab is mapped everywhere before the first store
+
+    def step(self, E, X, W, Y):
+        """Enqueues one step (asynchronous) on this rank's slice of the global batch (device tensors)."""
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        self.ps.check(self.lib.ps_model_p2p_step_dev(self.model.h, p(E), p(X), p(W), p(Y), int(Y.shape[0])))
+
+    def loss(self):
+        return self.model.read_loss()
+
+    def check(self):
+        v = C.c_int()
+        self.ps.check(self.lib.ps_model_p2p_overflowed(self.model.h, C.byref(v)))
+        if v.value:
+            raise RuntimeError("p2p exchange bucket overflow: raise slack")
+
+
 class _DevArray:
     def __init__(self, ptr, n, typestr="<f4"):
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}

@@ -33,19 +33,23 @@ def worker(rank, R, port, out, cfg, emb_opt, graphed):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=R, device_id=torch.device("cuda", rank))
     from ps_b200 import binding as ps
-    from ps_b200.sharded import GpuOps, GraphedShardedTrainer, ShardedTrainer
+    from ps_b200.sharded import GpuOps, GraphedShardedTrainer, P2PShardedTrainer, ShardedTrainer
     ctx = ps.Context(rank, seed=SEED)
     upd = ps.UpdaterSpec.ftrl() if emb_opt == "ftrl" else None
     m = ps.Model(ctx, cfg["kind"], cfg["F"], cfg["D"], cfg["Xn"], cfg["fc"], emb_capacity=1 << 16, emb_updater=upd, max_batch=cfg["N"])
-    ops = GpuOps(ps, ctx, m, rank)
     N = cfg["N"]
-    tr = GraphedShardedTrainer(ops, rank, R, N, cfg["F"], cfg["kind"] == "widedeep", slack=3.0) if graphed else ShardedTrainer(ops, rank, R)
+    if graphed == "p2p":
+        ops = None
+        tr = P2PShardedTrainer(ps, ctx, m, rank, R, N, cfg["F"], slack=3.0)
+    else:
+        ops = GpuOps(ps, ctx, m, rank)
+        tr = GraphedShardedTrainer(ops, rank, R, N, cfg["F"], cfg["kind"] == "widedeep", slack=3.0) if graphed else ShardedTrainer(ops, rank, R)
     losses, keys = [], set()
     for b in batches(R, cfg):
         sl = slice(rank * N, (rank + 1) * N)
         dev = {k: torch.from_numpy(np.ascontiguousarray(v[sl])).cuda(rank) for k, v in b.items()}
         r = tr.step(dev["E"], dev["X"], dev["W"] if cfg["kind"] == "widedeep" else None, dev["Y"])
-        losses.append(ops.loss() if graphed else r)
+        losses.append(tr.loss() if graphed == "p2p" else ops.loss() if graphed else r)
         if graphed:
             tr.check()
         for n in range(0, R * N, 7):
@@ -72,7 +76,8 @@ def worker(rank, R, port, out, cfg, emb_opt, graphed):
     os._exit(0)        # captured NCCL graphs + communicator teardown order is fragile; results are on disk
 
 
-@pytest.mark.parametrize("R,emb_opt,graphed", [(1, "adam", False), (1, "adam", True), (2, "adam", False), (2, "ftrl", False), (2, "adam", True)])
+@pytest.mark.parametrize("R,emb_opt,graphed", [(1, "adam", False), (1, "adam", True), (1, "adam", "p2p"), (2, "adam", False), (2, "ftrl", False),
+                                                 (2, "adam", True), (2, "adam", "p2p"), (2, "ftrl", "p2p")])
 def test_sharded_step_matches_oracle_global_batch(tmp_path, R, emb_opt, graphed):
     if torch.cuda.device_count() < R:
         pytest.skip(f"needs {R} GPUs")
