@@ -23,15 +23,14 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
  * been fenced at system scope, so whatever the last block publishes next is ordered after all of them */
 __device__ __forceinline__ bool block_is_last(uint32_t* done) {
   __shared__ bool last;
-  __threadfence_system();
-  __syncthreads();
+  __syncthreads();                   /* every store of this block happens-before thread 0's fence ... */
   if (threadIdx.x == 0) {
+    __threadfence_system();          /* ... which (cumulativity) orders them before the counter update: ONE system fence per block */
     const uint32_t old = atomicAdd(done, 1u);
     last = old == gridDim.x - 1;
-    if (last) *done = 0u;
+    if (last) { *done = 0u; __threadfence_system(); }
   }
   __syncthreads();
-  if (last) __threadfence_system();
   return last;
 }
 
@@ -52,13 +51,21 @@ __global__ void p2p_begin_kernel(P2PState* st) {
 /* PSRouterClient.getList, request side (PSRouterClient.java:60-68): bucket by owner and store each key
  * directly into the owner's keys_in[me][pos]; the last block publishes the per-owner counts and flags. */
 __global__ void __launch_bounds__(256) p2p_route_send_kernel(P2PState* st, const int64_t* __restrict__ E, int L, int F, int32_t* __restrict__ send_pos) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  /* field-major work order (t = j*N + n): consecutive bucket positions then hold the same field for consecutive
+   * samples, so the OWNER's probe and scatter kernels can collapse a hot key warp-wide (one atomic per 32) */
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const int R = st->R, cap = st->cap, me = st->me;
-  const bool valid = l < L;
+  const bool valid = t < L;
+  int l = 0;
   unsigned long long key = 0;
   int owner = -1 - lane;
-  if (valid) { key = ps_pack_key((uint32_t)(l % F), (uint64_t)E[l]); owner = (int)ps_owner_of(key, (uint32_t)R); }
+  if (valid) {
+    const int N = L / F, j = t / N;
+    l = (t - j * N) * F + j;
+    key = ps_pack_key((uint32_t)j, (uint64_t)E[l]);
+    owner = (int)ps_owner_of(key, (uint32_t)R);
+  }
   const unsigned peers = __match_any_sync(0xffffffffu, owner);
   const int leader = __ffs(peers) - 1;
   int base = 0;
@@ -128,17 +135,29 @@ __global__ void __launch_bounds__(256) p2p_gather_send_kernel(P2PState* st, cons
   if (block_is_last(&st->done[CH_ROWS])) publish(st, CH_ROWS);
 }
 
+template <bool VEC>
 __global__ void __launch_bounds__(256) p2p_unpack_kernel(const P2PState* st, const int32_t* __restrict__ send_pos, int L, int F, int D,
                                                          float* __restrict__ out, int ldo) {
   const int Dp = st->Dp;
   const float* rows = reinterpret_cast<const float*>(p2p_region(st, st->me, st->off_rows));
   const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long l = g / Dp;
-  const int d = (int)(g - l * Dp);
-  if (l >= L || d >= D) return;
-  const int n = (int)(l / F), j = (int)(l - (long)n * F);
-  const int pos = send_pos[l];
-  out[(size_t)n * ldo + j * D + d] = pos >= 0 ? rows[(size_t)pos * Dp + d] : 0.f;
+  if (VEC) {                                   /* Dp/4 lanes per lookup, 128-bit moves */
+    const int tpl = Dp >> 2;
+    const long l = g / tpl;
+    const int part = (int)(g - l * tpl);
+    if (l >= L) return;
+    const int n = (int)(l / F), j = (int)(l - (long)n * F);
+    const int pos = send_pos[l];
+    const float4 v = pos >= 0 ? ld_f4(rows + (size_t)pos * Dp + part * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    st_f4(out + (size_t)n * ldo + j * D + part * 4, v);
+  } else {
+    const long l = g / Dp;
+    const int d = (int)(g - l * Dp);
+    if (l >= L || d >= D) return;
+    const int n = (int)(l / F), j = (int)(l - (long)n * F);
+    const int pos = send_pos[l];
+    out[(size_t)n * ldo + j * D + d] = pos >= 0 ? rows[(size_t)pos * Dp + d] : 0.f;
+  }
 }
 
 /* PServer sync mode sums the pushes of all workers (PServer.java:164-195): every rank adds the R
@@ -155,10 +174,30 @@ __global__ void __launch_bounds__(256) p2p_reduce_kernel(const P2PState* st, flo
 
 /* KVStore.update → client.push per key (KVStore.java:257-260): per-lookup row gradient (ReLU mask of
  * EmbeddingField.java:91-93 applied here) stored into the owner's grads_in[me][pos]                 */
+template <bool VEC>
 __global__ void __launch_bounds__(256) p2p_pack_send_kernel(P2PState* st, const float* __restrict__ delta, int ldd, const float* __restrict__ act, int lda,
                                                             const int32_t* __restrict__ send_pos, int L, int F, int D) {
   const int Dp = st->Dp, cap = st->cap, me = st->me;
   const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (VEC) {
+    const int tpl = Dp >> 2;
+    const long l = g / tpl;
+    const int part = (int)(g - l * tpl);
+    if (l < L) {
+      const int pos = send_pos[l];
+      if (pos >= 0) {
+        const int n = (int)(l / F), j = (int)(l - (long)n * F);
+        const float4 dv = ld_f4(delta + (size_t)n * ldd + j * D + part * 4), av = ld_f4(act + (size_t)n * lda + j * D + part * 4);
+        float4 v;
+        v.x = __fmul_rn(dv.x, av.x > 0.f ? 1.f : 0.f); v.y = __fmul_rn(dv.y, av.y > 0.f ? 1.f : 0.f);
+        v.z = __fmul_rn(dv.z, av.z > 0.f ? 1.f : 0.f); v.w = __fmul_rn(dv.w, av.w > 0.f ? 1.f : 0.f);
+        const int owner = pos / cap, idx = pos - owner * cap;
+        st_f4(reinterpret_cast<float*>(p2p_region(st, owner, st->off_grads)) + ((size_t)me * cap + idx) * Dp + part * 4, v);
+      }
+    }
+    if (block_is_last(&st->done[CH_GRADS])) publish(st, CH_GRADS);
+    return;
+  }
   const long l = g / Dp;
   const int d = (int)(g - l * Dp);
   if (l < L) {
@@ -255,8 +294,9 @@ void P2P::gather_send(const float* w, int D, const int32_t* lk_slot) {
 }
 
 void P2P::unpack(const int32_t* send_pos, int N, int F, int D, float* out, int ldo) {
-  const long total = (long)N * F * Dp;
-  p2p_unpack_kernel<<<ceil_div(total, 256), 256, 0, ctx->stream>>>(dev, send_pos, N * F, F, D, out, ldo);
+  const bool vec = D % 4 == 0 && ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  if (vec) p2p_unpack_kernel<true><<<ceil_div((long)N * F * (Dp / 4), 256), 256, 0, ctx->stream>>>(dev, send_pos, N * F, F, D, out, ldo);
+  else p2p_unpack_kernel<false><<<ceil_div((long)N * F * Dp, 256), 256, 0, ctx->stream>>>(dev, send_pos, N * F, F, D, out, ldo);
   P2P_LAUNCHED();
 }
 
@@ -266,8 +306,9 @@ void P2P::reduce_gsum(float* gsum) {
 }
 
 void P2P::pack_send(const float* delta, int ldd, const float* act, int lda, const int32_t* send_pos, int N, int F, int D) {
-  const long total = (long)N * F * Dp;
-  p2p_pack_send_kernel<<<ceil_div(total, 256), 256, 0, ctx->stream>>>(dev, delta, ldd, act, lda, send_pos, N * F, F, D);
+  const bool vec = D % 4 == 0 && ldd % 4 == 0 && lda % 4 == 0 && (reinterpret_cast<uintptr_t>(delta) & 15) == 0 && (reinterpret_cast<uintptr_t>(act) & 15) == 0;
+  if (vec) p2p_pack_send_kernel<true><<<ceil_div((long)N * F * (Dp / 4), 256), 256, 0, ctx->stream>>>(dev, delta, ldd, act, lda, send_pos, N * F, F, D);
+  else p2p_pack_send_kernel<false><<<ceil_div((long)N * F * Dp, 256), 256, 0, ctx->stream>>>(dev, delta, ldd, act, lda, send_pos, N * F, F, D);
   P2P_LAUNCHED();
 }
 
