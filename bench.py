@@ -153,6 +153,7 @@ def main():
     ap.add_argument("--ring", type=int, default=16)
     ap.add_argument("--slack", type=float, default=2.0)
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
+    ap.add_argument("--force-sharded", action="store_true", help="use the sharded step even with one rank (profiling)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     rank = int(os.environ.get("RANK", "0"))
@@ -171,8 +172,13 @@ def main():
     import __graft_entry__ as g
     if local_rank == 0:
         g.build()
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if world > 1 or args.force_sharded:
+        if world == 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29533")
+            dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist.barrier()
     from ps_b200 import binding as ps
 
@@ -200,7 +206,7 @@ def main():
     # N > 1: the embedding table is sharded by key hash over the ranks and the R ranks perform ONE
     # Trainer step on the concatenated batch (ps_b200/sharded.py); per-GPU batch fixed => weak scaling
     trainer = None
-    if world > 1:
+    if world > 1 or args.force_sharded:
         from ps_b200.sharded import GpuOps, GraphedShardedTrainer, P2PShardedTrainer
         if args.exchange == "p2p":
             # every exchange is a store into the consumer's HBM over NVLink by the kernel that produced the data
@@ -294,7 +300,7 @@ def main():
 
     # ---- per-kernel device times and the roofline of the dominant HBM-bound kernel ----
     acc = {}
-    reps = 20 if world == 1 else 0
+    reps = 20 if (world == 1 and trainer is None) else 0
     if reps:
         model.profile(True)
     for i in range(reps):
@@ -308,7 +314,7 @@ def main():
     uniq = float(np.mean([len(np.unique(b["E"] + (np.arange(F, dtype=np.int64) << 44)[None, :])) for b in ring])) if F else 0.0
     hbm_peak, peak_src = peaks()
     kernels, roofline = {}, None
-    if F and world == 1:
+    if F and world == 1 and trainer is None:
         # each embedding kernel replayed 64x inside a CUDA graph over the batch ring, CUDA events on the library's stream
         kt = model.kernel_times([d["E"].data_ptr() for d in dev_ring], B, reps=64)
         alg = {"emb_gather": L * (8 + 8 * D), "emb_scatter_update": L * (8 + 4 * D) + uniq * 24 * D}
@@ -359,7 +365,7 @@ def main():
         }
         print(json.dumps(line), flush=True)
     sys.stdout.flush()
-    if world > 1:
+    if world > 1 or trainer is not None:
         # captured NCCL graphs + communicator teardown order is fragile: everything is measured and printed, leave hard
         ctx.synchronize()
         torch.cuda.synchronize()

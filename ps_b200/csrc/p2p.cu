@@ -19,28 +19,19 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   return v;
 }
 
-/* true (in every thread) for the block that finishes last; by then every block's remote stores have
- * been fenced at system scope, so whatever the last block publishes next is ordered after all of them */
-__device__ __forceinline__ bool block_is_last(uint32_t* done) {
-  __shared__ bool last;
-  __syncthreads();                   /* every store of this block happens-before thread 0's fence ... */
-  if (threadIdx.x == 0) {
-    __threadfence_system();          /* ... which (cumulativity) orders them before the counter update: ONE system fence per block */
-    const uint32_t old = atomicAdd(done, 1u);
-    last = old == gridDim.x - 1;
-    if (last) { *done = 0u; __threadfence_system(); }
-  }
-  __syncthreads();
-  return last;
-}
-
-/* called by the last block: thread r tells rank r that this rank's payload of `channel` is complete */
-__device__ __forceinline__ void publish(const P2PState* st, int channel) {
+/* Runs as its own one-warp kernel right after a producer kernel: the kernel boundary has completed every
+ * store of the producer (including those that crossed NVLink), so ONE system-scope fence and one release
+ * store per peer publish the payload — no per-block fences inside the bandwidth-bound producers.       */
+__global__ void p2p_publish_kernel(P2PState* st, int channel) {
   const int r = threadIdx.x;
-  if (r < st->R) {
-    uint32_t* f = reinterpret_cast<uint32_t*>(p2p_region(st, r, st->off_flags)) + channel * kP2PMaxRanks + st->me;
-    st_release_sys(f, st->seq);
+  if (r >= st->R) return;
+  if (channel == CH_KEYS) {
+    const int c = min(*reinterpret_cast<volatile int32_t*>(&st->cursor[r]), st->cap);
+    reinterpret_cast<volatile int32_t*>(p2p_region(st, r, st->off_counts))[st->me] = c;
   }
+  __threadfence_system();
+  uint32_t* f = reinterpret_cast<uint32_t*>(p2p_region(st, r, st->off_flags)) + channel * kP2PMaxRanks + st->me;
+  st_release_sys(f, st->seq);
 }
 
 __global__ void p2p_begin_kernel(P2PState* st) {
@@ -81,15 +72,6 @@ __global__ void __launch_bounds__(256) p2p_route_send_kernel(P2PState* st, const
       st->overflow = 1;
     }
   }
-  if (block_is_last(&st->done[CH_KEYS])) {
-    const int r = threadIdx.x;
-    if (r < R) {
-      const int c = min(*reinterpret_cast<volatile int32_t*>(&st->cursor[r]), cap);
-      reinterpret_cast<volatile int32_t*>(p2p_region(st, r, st->off_counts))[me] = c;
-    }
-    __threadfence_system();
-    publish(st, CH_KEYS);
-  }
 }
 
 /* all-gather by stores: this rank's `bytes` go to slot `me` of the channel's region on every rank */
@@ -101,7 +83,6 @@ __global__ void __launch_bounds__(256) p2p_bcast_kernel(P2PState* st, const uint
     const size_t c = i - (size_t)r * n16;
     reinterpret_cast<uint4*>(p2p_region(st, r, off))[(size_t)me * n16 + c] = src[c];
   }
-  if (block_is_last(&st->done[channel])) publish(st, channel);
 }
 
 __global__ void p2p_wait_kernel(const P2PState* st, int channel) {
@@ -132,7 +113,6 @@ __global__ void __launch_bounds__(256) p2p_gather_send_kernel(P2PState* st, cons
       st_f4(dst, v);
     }
   }
-  if (block_is_last(&st->done[CH_ROWS])) publish(st, CH_ROWS);
 }
 
 template <bool VEC>
@@ -195,7 +175,6 @@ __global__ void __launch_bounds__(256) p2p_pack_send_kernel(P2PState* st, const 
         st_f4(reinterpret_cast<float*>(p2p_region(st, owner, st->off_grads)) + ((size_t)me * cap + idx) * Dp + part * 4, v);
       }
     }
-    if (block_is_last(&st->done[CH_GRADS])) publish(st, CH_GRADS);
     return;
   }
   const long l = g / Dp;
@@ -210,7 +189,6 @@ __global__ void __launch_bounds__(256) p2p_pack_send_kernel(P2PState* st, const 
       reinterpret_cast<float*>(p2p_region(st, owner, st->off_grads))[((size_t)me * cap + idx) * Dp + d] = v;
     }
   }
-  if (block_is_last(&st->done[CH_GRADS])) publish(st, CH_GRADS);
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -268,12 +246,15 @@ void P2P::destroy() {
 
 #define P2P_LAUNCHED() do { PS_LAUNCH_CHECK(); ctx->launches++; } while (0)
 
+void P2P::publish(int channel) { p2p_publish_kernel<<<1, 32, 0, ctx->stream>>>(dev, channel); P2P_LAUNCHED(); }
+
 void P2P::begin() { p2p_begin_kernel<<<1, 32, 0, ctx->stream>>>(dev); P2P_LAUNCHED(); }
 
 void P2P::route_send(const int64_t* E, int N, int F, int32_t* send_pos) {
   const int L = N * F;
   p2p_route_send_kernel<<<ceil_div(L, 256), 256, 0, ctx->stream>>>(dev, E, L, F, send_pos);
   P2P_LAUNCHED();
+  publish(CH_KEYS);
 }
 
 void P2P::bcast(const void* src, size_t bytes, int channel) {
@@ -283,6 +264,7 @@ void P2P::bcast(const void* src, size_t bytes, int channel) {
   const int grid = (int)std::min<size_t>((n16 * R + 255) / 256, (size_t)ctx->num_sms * 4);
   p2p_bcast_kernel<<<std::max(grid, 1), 256, 0, ctx->stream>>>(dev, static_cast<const uint4*>(src), n16, channel == CH_WIDE ? host.off_wide : host.off_gsum, channel);
   P2P_LAUNCHED();
+  publish(channel);
 }
 
 void P2P::wait(int channel) { p2p_wait_kernel<<<1, 32, 0, ctx->stream>>>(dev, channel); P2P_LAUNCHED(); }
@@ -291,6 +273,7 @@ void P2P::gather_send(const float* w, int D, const int32_t* lk_slot) {
   const long total = (long)R * cap * (Dp / 4);
   p2p_gather_send_kernel<<<ceil_div(total, 256), 256, 0, ctx->stream>>>(dev, w, D, lk_slot);
   P2P_LAUNCHED();
+  publish(CH_ROWS);
 }
 
 void P2P::unpack(const int32_t* send_pos, int N, int F, int D, float* out, int ldo) {
@@ -310,6 +293,7 @@ void P2P::pack_send(const float* delta, int ldd, const float* act, int lda, cons
   if (vec) p2p_pack_send_kernel<true><<<ceil_div((long)N * F * (Dp / 4), 256), 256, 0, ctx->stream>>>(dev, delta, ldd, act, lda, send_pos, N * F, F, D);
   else p2p_pack_send_kernel<false><<<ceil_div((long)N * F * Dp, 256), 256, 0, ctx->stream>>>(dev, delta, ldd, act, lda, send_pos, N * F, F, D);
   P2P_LAUNCHED();
+  publish(CH_GRADS);
 }
 
 bool P2P::overflowed() {

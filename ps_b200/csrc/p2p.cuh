@@ -15,9 +15,9 @@
  *   gsum_in [p][R][glen]     f32   dense gradient sums + loss + gbar of r    (PServer sync-mode sum)
  *   counts  [p][R]           i32   number of valid keys from rank r
  *   flags   [p][CH][R]       u32   step sequence number, written last with release.sys
- * A producer kernel stores its payload into the consumer's slab, fences (system scope), and its
- * last block publishes the flag; the consumer's stream runs a one-warp wait kernel (acquire.sys
- * spin) before the kernels that read the mailbox.  Every send precedes the matching wait in every
+ * A producer kernel stores its payload into the consumer's slab; a one-warp publish kernel right after
+ * it (kernel boundary = all stores complete) fences at system scope and release-stores the flag; the
+ * consumer's stream runs a one-warp wait kernel (acquire.sys spin) before the kernels that read the mailbox.  Every send precedes the matching wait in every
  * rank's program order, so there is no circular wait; ranks can drift by at most one step, which
  * the parity double-buffering covers.
  */
@@ -58,6 +58,7 @@ struct P2P {
   void begin();                                                                     /* seq += 1, cursors = 0 */
   void route_send(const int64_t* E, int N, int F, int32_t* send_pos);               /* keys → owners' keys_in */
   void bcast(const void* src, size_t bytes, int channel);                           /* wide ids / gsum → every peer */
+  void publish(int channel);                                                        /* flag every peer (after a producer kernel) */
   void wait(int channel);
   void gather_send(const float* w, int D, const int32_t* lk_slot);                  /* rows → requesters' rows_in */
   void unpack(const int32_t* send_pos, int N, int F, int D, float* out, int ldo);   /* rows_in → concat buffer */
