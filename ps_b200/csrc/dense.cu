@@ -9,6 +9,7 @@
  */
 #include "dense.cuh"
 #include "gemm.cuh"
+#include "p2p.cuh"
 
 #include <algorithm>
 
@@ -83,7 +84,7 @@ __device__ __forceinline__ void publish(StepStatus* st, const uint32_t* emb_coun
 
 __global__ void __launch_bounds__(256) dense_update_kernel(const __grid_constant__ DenseUpdateArgs a, StepStatus* __restrict__ st,
                                                            const uint32_t* __restrict__ emb_counters, const uint32_t* __restrict__ wide_counters,
-                                                           StepStatus* __restrict__ host) {
+                                                           StepStatus* __restrict__ host, const P2PState* __restrict__ p2p) {
   if (host != nullptr && blockIdx.x == 0 && threadIdx.x == 0) publish(st, emb_counters, wide_counters, host);   /* status is final before the updates */
   if (st->skip) return;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -95,15 +96,24 @@ __global__ void __launch_bounds__(256) dense_update_kernel(const __grid_constant
   const int cols = L.in + 1;
   const int o = (int)(r / cols), c = (int)(r - (long)o * cols);
   const float Nf = (float)a.N;
+  /* single GPU: the wgrad partial slabs; sharded over peer memory: the R ranks' flat gradient buffers in this
+   * step's gsum_in mailbox, added in rank order (every replica computes the same bits)                        */
+  const float* G = L.G;
+  size_t slab = L.slab;
+  int nsplit = L.nsplit, ldg = L.ldg;
+  if (p2p != nullptr) {
+    G = reinterpret_cast<const float*>(p2p_region(p2p, p2p->me, p2p->off_gsum)) + L.first;
+    slab = (size_t)p2p->glen; nsplit = p2p->R; ldg = cols;
+  }
   float g = 0.0f;
-  for (int z = 0; z < L.nsplit; ++z) g = __fadd_rn(g, L.G[(size_t)z * L.slab + (size_t)o * L.ldg + c]);
+  for (int z = 0; z < nsplit; ++z) g = __fadd_rn(g, G[(size_t)z * slab + (size_t)o * ldg + c]);
   g = __fdiv_rn(g, Nf);
   const bool is_bias = c == L.in;
   const UpdaterDev& u = is_bias ? L.updB : L.updW;
   if (u.kind == PS_UPD_FTRL) {
     float g0 = 0.0f;
     const size_t o0 = is_bias ? (size_t)L.in : 0;
-    for (int z = 0; z < L.nsplit; ++z) g0 = __fadd_rn(g0, L.G[(size_t)z * L.slab + o0]);
+    for (int z = 0; z < nsplit; ++z) g0 = __fadd_rn(g0, G[(size_t)z * slab + o0]);
     if (__fdiv_rn(g0, Nf) == 0.0f) return;
   }
   if (is_bias) {
@@ -119,8 +129,8 @@ __global__ void __launch_bounds__(256) dense_update_kernel(const __grid_constant
   }
 }
 void dense_update(Ctx* ctx, const DenseUpdateArgs& a, StepStatus* st, const uint32_t* emb_counters, const uint32_t* wide_counters,
-                  StepStatus* host_mapped) {
-  dense_update_kernel<<<ceil_div(a.total, 256), 256, 0, ctx->stream>>>(a, st, emb_counters, wide_counters, host_mapped);
+                  StepStatus* host_mapped, const P2PState* p2p) {
+  dense_update_kernel<<<ceil_div(a.total, 256), 256, 0, ctx->stream>>>(a, st, emb_counters, wide_counters, host_mapped, p2p);
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }
@@ -142,6 +152,50 @@ __global__ void __launch_bounds__(256) dense_reduce_kernel(const __grid_constant
 }
 void dense_reduce(Ctx* ctx, const DenseUpdateArgs& a, const StepStatus* st, float* gsum) {
   dense_reduce_kernel<<<ceil_div(a.total + 1, 256), 256, 0, ctx->stream>>>(a, st, gsum);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+}
+
+/* dense_reduce + all-gather by stores: every rank's slot `me` of gsum_in receives this rank's sums */
+__global__ void __launch_bounds__(256) dense_reduce_send_kernel(const __grid_constant__ DenseUpdateArgs a, const StepStatus* __restrict__ st,
+                                                                const P2PState* __restrict__ p2p) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int R = p2p->R, me = p2p->me, glen = p2p->glen;
+  if (idx == 0) {
+    for (int r = 0; r < R; ++r) {
+      float* dst = reinterpret_cast<float*>(p2p_region(p2p, r, p2p->off_gsum)) + (size_t)me * glen;
+      dst[a.total] = st->loss; dst[a.total + 1] = st->gbar;
+    }
+  }
+  if (idx >= a.total) return;
+  int li = 0;
+  while (li + 1 < a.n_layers && idx >= a.l[li + 1].first) ++li;
+  const DenseLayerDesc& L = a.l[li];
+  const long r0 = idx - L.first;
+  const int cols = L.in + 1;
+  const int o = (int)(r0 / cols), c = (int)(r0 - (long)o * cols);
+  float g = 0.0f;
+  for (int z = 0; z < L.nsplit; ++z) g = __fadd_rn(g, L.G[(size_t)z * L.slab + (size_t)o * L.ldg + c]);
+  for (int r = 0; r < R; ++r) reinterpret_cast<float*>(p2p_region(p2p, r, p2p->off_gsum))[(size_t)me * glen + idx] = g;
+}
+void dense_reduce_send(Ctx* ctx, const DenseUpdateArgs& a, const StepStatus* st, const P2PState* p2p) {
+  dense_reduce_send_kernel<<<ceil_div(a.total + 1, 256), 256, 0, ctx->stream>>>(a, st, p2p);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+}
+
+/* global loss / gbar / early-exit flag from the R ranks' [loss, gbar] in the gsum_in mailbox (rank order) */
+__global__ void shard_finish_scalars_p2p_kernel(StepStatus* st, const P2PState* p2p, long total) {
+  const float* in = reinterpret_cast<const float*>(p2p_region(p2p, p2p->me, p2p->off_gsum));
+  float l = 0.f, g = 0.f;
+  for (int r = 0; r < p2p->R; ++r) { l = __fadd_rn(l, in[(size_t)r * p2p->glen + total]); g = __fadd_rn(g, in[(size_t)r * p2p->glen + total + 1]); }
+  const float loss = __fdiv_rn(l, (float)p2p->R);
+  st->loss = loss;
+  st->gbar = __fdiv_rn(g, (float)p2p->R);
+  st->skip = (loss <= 0.01f || isnan(loss)) ? 1 : 0;
+}
+void shard_finish_scalars_p2p(Ctx* ctx, StepStatus* st, const P2PState* p2p, long total) {
+  shard_finish_scalars_p2p_kernel<<<1, 1, 0, ctx->stream>>>(st, p2p, total);
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }

@@ -9,6 +9,8 @@
 
 namespace psb {
 
+struct P2PState;
+
 /* device-resident step status; published to mapped host memory by the last kernel of a step */
 struct StepStatus {
   float loss;       /* Model.train return value (model/DNN.java:47) */
@@ -43,7 +45,10 @@ void dense_init(Ctx* ctx, float* W, int out, int in, int ldw, float* Wt, int ldw
 void fill_column(Ctx* ctx, float* buf, int ld, int col, int rows, float value);
 /* also publishes the step status to mapped host memory when host_mapped is non-null */
 void dense_update(Ctx* ctx, const DenseUpdateArgs& a, StepStatus* st, const uint32_t* emb_counters, const uint32_t* wide_counters,
-                  StepStatus* host_mapped);
+                  StepStatus* host_mapped, const P2PState* p2p = nullptr /* gradients come from this step's gsum_in mailbox */);
+/* peer-memory forms of dense_reduce / shard_finish_scalars (p2p.cuh): sums stored straight into every rank's mailbox */
+void dense_reduce_send(Ctx* ctx, const DenseUpdateArgs& a, const StepStatus* st, const P2PState* p2p);
+void shard_finish_scalars_p2p(Ctx* ctx, StepStatus* st, const P2PState* p2p, long total);
 constexpr int kTailWorkspaceFloats = 2 * 1024 + 4;
 
 /* binary tail: z = deep (+ wide); p = clipped sigmoid; CrossEntropy forward/backward; sigmoid

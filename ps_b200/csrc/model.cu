@@ -430,42 +430,50 @@ void Model::p2p_step(const int64_t* E, const float* X, const int64_t* W, const f
   cudaStream_t s = ctx->stream, s1 = aux[0], s2 = aux[1];
   const int R = p2p.R, cap = p2p.cap;
   p2p.begin();
-  if (has_emb) p2p.route_send(E, N, F, send_pos);                               /* PSRouterClient.getList: keys out */
-  if (has_wide) {
-    PS_REQUIRE(((size_t)N * F * 8) % 16 == 0, PS_ERR_ARG, "p2p: N*F must be even");
-    p2p.bcast(W, (size_t)N * F * 8, CH_WIDE);
-  }
   fork(s, s1);
-  if (has_wide) {
+  if (has_wide) {                                                               /* wide branch beside the embedding exchange */
+    PS_REQUIRE(((size_t)N * F * 8) % 16 == 0, PS_ERR_ARG, "p2p: N*F must be even");
     StreamScope sc(ctx, s1);
-    p2p.wait(CH_WIDE);
+    p2p.bcast(W, (size_t)N * F * 8, CH_WIDE);
+    p2p.publish_wait(CH_WIDE);
     wide.insert(nullptr, R * N * F, p2p.state());                               /* the union of every replica's keys */
     wide.forward(W, N, F, wide_bias, wide_z);
   }
   if (has_emb) {
-    p2p.wait(CH_KEYS);
+    p2p.route_send(E, N, F, send_pos);                                          /* PSRouterClient.getList: keys out */
+    p2p.publish_wait(CH_KEYS);
     emb.probe_packed(nullptr, R * cap, p2p.state());                            /* PServer.getList on the owner */
     p2p.gather_send(emb.w, D, emb.lk_slot);                                     /* rows back, stored by the gather itself */
-    p2p.wait(CH_ROWS);
-    p2p.unpack(send_pos, N, F, D, act[0], ld[0]);
-    PS_CUDA(cudaMemcpy2DAsync(act[0] + F * D, sizeof(float) * ld[0], X, sizeof(float) * Xn, sizeof(float) * Xn, N, cudaMemcpyDeviceToDevice, s));
+    p2p.publish_wait(CH_ROWS);
+    p2p.unpack(send_pos, N, F, D, act[0], ld[0], X, Xn, F * D);                 /* + ConcatLayer */
   } else {
     PS_CUDA(cudaMemcpy2DAsync(act[0], sizeof(float) * ld[0], X, sizeof(float) * Xn, sizeof(float) * Xn, N, cudaMemcpyDeviceToDevice, s));
   }
-  forward_backward(W, nullptr, 0, Y, N, true, false);
-  fork(s1, s);
-  fork(s2, s);
-  const DenseUpdateArgs u = dense_args(N);
-  dense_reduce(ctx, u, st_dev, gsum);                                           /* local dense gradient sums + loss + gbar */
-  p2p.bcast(gsum, (size_t)p2p.glen * 4, CH_GSUM);                               /* PServer sync mode: everybody's push */
-  if (has_emb) p2p.pack_send(delta[0], ld[0], act[0], ld[0], send_pos, N, F, D); /* client.push of the row gradients */
-  p2p.wait(CH_GSUM);
-  p2p.reduce_gsum(gsum);
-  shard_finish(N * R, R);                                                       /* psUpdate for dense + wide keys */
-  if (has_emb) {
-    p2p.wait(CH_GRADS);
-    emb.scatter_update(nullptr, emb.Dp, nullptr, emb.Dp, R * cap, 2, skip_ptr(st_dev), 1, p2p.state());
+  forward_backward(W, nullptr, 0, Y, N, true, false);                           /* main: delta[0]; side 1: the wgrads */
+  /* side stream 1: PServer sync mode — every rank's dense gradient sums + [loss, gbar] into every mailbox, then the
+   * global scalars, the wide update and the dense update, all beside the row-gradient push on the main stream      */
+  fork(s2, s1);
+  {
+    StreamScope sc(ctx, s1);
+    const DenseUpdateArgs u = dense_args(N * R);
+    dense_reduce_send(ctx, u, st_dev, p2p.state());
+    p2p.publish_wait(CH_GSUM);
+    shard_finish_scalars_p2p(ctx, st_dev, p2p.state(), u.total);
   }
+  if (has_emb) {
+    p2p.pack_send(delta[0], ld[0], act[0], ld[0], send_pos, N, F, D);           /* client.push of the row gradients */
+    p2p.publish_wait(CH_GRADS);
+  }
+  fork(s1, s);                                                                  /* the global skip flag */
+  fork(s, s2);
+  {
+    StreamScope sc(ctx, s2);                                                    /* psUpdate for dense + wide keys beside the embedding update */
+    const DenseUpdateArgs u = dense_args(N * R);
+    if (has_wide) wide.update_all(gbar_ptr(st_dev), skip_ptr(st_dev), wide_bias, &upd_wide);
+    dense_update(ctx, u, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, nullptr, p2p.state());
+  }
+  if (has_emb) emb.scatter_update(nullptr, emb.Dp, nullptr, emb.Dp, R * cap, 2, skip_ptr(st_dev), 1, p2p.state());
+  fork(s2, s);
   last_N = N; last_train = true;
 }
 

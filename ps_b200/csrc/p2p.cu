@@ -85,6 +85,23 @@ __global__ void __launch_bounds__(256) p2p_bcast_kernel(P2PState* st, const uint
   }
 }
 
+/* publish this rank's payload of `channel` and wait for everybody else's, in one launch */
+__global__ void p2p_publish_wait_kernel(P2PState* st, int channel) {
+  const int r = threadIdx.x;
+  if (r < st->R) {
+    if (channel == CH_KEYS) {
+      const int c = min(*reinterpret_cast<volatile int32_t*>(&st->cursor[r]), st->cap);
+      reinterpret_cast<volatile int32_t*>(p2p_region(st, r, st->off_counts))[st->me] = c;
+    }
+    __threadfence_system();
+    const uint32_t seq = st->seq;
+    st_release_sys(reinterpret_cast<uint32_t*>(p2p_region(st, r, st->off_flags)) + channel * kP2PMaxRanks + st->me, seq);
+    const uint32_t* f = reinterpret_cast<const uint32_t*>(p2p_region(st, st->me, st->off_flags)) + channel * kP2PMaxRanks + r;
+    while ((int32_t)(ld_acquire_sys(f) - seq) < 0) __nanosleep(32);
+  }
+  __threadfence_system();
+}
+
 __global__ void p2p_wait_kernel(const P2PState* st, int channel) {
   const int r = threadIdx.x;
   if (r < st->R) {
@@ -117,10 +134,16 @@ __global__ void __launch_bounds__(256) p2p_gather_send_kernel(P2PState* st, cons
 
 template <bool VEC>
 __global__ void __launch_bounds__(256) p2p_unpack_kernel(const P2PState* st, const int32_t* __restrict__ send_pos, int L, int F, int D,
-                                                         float* __restrict__ out, int ldo) {
+                                                         float* __restrict__ out, int ldo, const float* __restrict__ X, int Xn, int xoff, int N) {
   const int Dp = st->Dp;
   const float* rows = reinterpret_cast<const float*>(p2p_region(st, st->me, st->off_rows));
-  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long emb_work = VEC ? (long)L * (Dp >> 2) : (long)L * Dp;
+  if (g >= emb_work) {                         /* ConcatLayer: the numeric features next to the embeddings */
+    g -= emb_work;
+    if (X != nullptr && g < (long)N * Xn) { const int n = (int)(g / Xn), x = (int)(g - (long)n * Xn); out[(size_t)n * ldo + xoff + x] = X[g]; }
+    return;
+  }
   if (VEC) {                                   /* Dp/4 lanes per lookup, 128-bit moves */
     const int tpl = Dp >> 2;
     const long l = g / tpl;
@@ -254,7 +277,6 @@ void P2P::route_send(const int64_t* E, int N, int F, int32_t* send_pos) {
   const int L = N * F;
   p2p_route_send_kernel<<<ceil_div(L, 256), 256, 0, ctx->stream>>>(dev, E, L, F, send_pos);
   P2P_LAUNCHED();
-  publish(CH_KEYS);
 }
 
 void P2P::bcast(const void* src, size_t bytes, int channel) {
@@ -264,22 +286,22 @@ void P2P::bcast(const void* src, size_t bytes, int channel) {
   const int grid = (int)std::min<size_t>((n16 * R + 255) / 256, (size_t)ctx->num_sms * 4);
   p2p_bcast_kernel<<<std::max(grid, 1), 256, 0, ctx->stream>>>(dev, static_cast<const uint4*>(src), n16, channel == CH_WIDE ? host.off_wide : host.off_gsum, channel);
   P2P_LAUNCHED();
-  publish(channel);
 }
 
+void P2P::publish_wait(int channel) { p2p_publish_wait_kernel<<<1, 32, 0, ctx->stream>>>(dev, channel); P2P_LAUNCHED(); }
 void P2P::wait(int channel) { p2p_wait_kernel<<<1, 32, 0, ctx->stream>>>(dev, channel); P2P_LAUNCHED(); }
 
 void P2P::gather_send(const float* w, int D, const int32_t* lk_slot) {
   const long total = (long)R * cap * (Dp / 4);
   p2p_gather_send_kernel<<<ceil_div(total, 256), 256, 0, ctx->stream>>>(dev, w, D, lk_slot);
   P2P_LAUNCHED();
-  publish(CH_ROWS);
 }
 
-void P2P::unpack(const int32_t* send_pos, int N, int F, int D, float* out, int ldo) {
+void P2P::unpack(const int32_t* send_pos, int N, int F, int D, float* out, int ldo, const float* X, int Xn, int xoff) {
   const bool vec = D % 4 == 0 && ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-  if (vec) p2p_unpack_kernel<true><<<ceil_div((long)N * F * (Dp / 4), 256), 256, 0, ctx->stream>>>(dev, send_pos, N * F, F, D, out, ldo);
-  else p2p_unpack_kernel<false><<<ceil_div((long)N * F * Dp, 256), 256, 0, ctx->stream>>>(dev, send_pos, N * F, F, D, out, ldo);
+  const long xw = X ? (long)N * Xn : 0;
+  if (vec) p2p_unpack_kernel<true><<<ceil_div((long)N * F * (Dp / 4) + xw, 256), 256, 0, ctx->stream>>>(dev, send_pos, N * F, F, D, out, ldo, X, Xn, xoff, N);
+  else p2p_unpack_kernel<false><<<ceil_div((long)N * F * Dp + xw, 256), 256, 0, ctx->stream>>>(dev, send_pos, N * F, F, D, out, ldo, X, Xn, xoff, N);
   P2P_LAUNCHED();
 }
 
@@ -293,7 +315,6 @@ void P2P::pack_send(const float* delta, int ldd, const float* act, int lda, cons
   if (vec) p2p_pack_send_kernel<true><<<ceil_div((long)N * F * (Dp / 4), 256), 256, 0, ctx->stream>>>(dev, delta, ldd, act, lda, send_pos, N * F, F, D);
   else p2p_pack_send_kernel<false><<<ceil_div((long)N * F * Dp, 256), 256, 0, ctx->stream>>>(dev, delta, ldd, act, lda, send_pos, N * F, F, D);
   P2P_LAUNCHED();
-  publish(CH_GRADS);
 }
 
 bool P2P::overflowed() {

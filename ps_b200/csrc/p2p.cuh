@@ -59,9 +59,10 @@ struct P2P {
   void route_send(const int64_t* E, int N, int F, int32_t* send_pos);               /* keys → owners' keys_in */
   void bcast(const void* src, size_t bytes, int channel);                           /* wide ids / gsum → every peer */
   void publish(int channel);                                                        /* flag every peer (after a producer kernel) */
+  void publish_wait(int channel);                                                   /* publish + wait for all peers, one launch */
   void wait(int channel);
   void gather_send(const float* w, int D, const int32_t* lk_slot);                  /* rows → requesters' rows_in */
-  void unpack(const int32_t* send_pos, int N, int F, int D, float* out, int ldo);   /* rows_in → concat buffer */
+  void unpack(const int32_t* send_pos, int N, int F, int D, float* out, int ldo, const float* X, int Xn, int xoff);   /* rows_in (+ X) → concat buffer */
   void reduce_gsum(float* gsum);                                                    /* sum over ranks, fixed order */
   void pack_send(const float* delta, int ldd, const float* act, int lda, const int32_t* send_pos, int N, int F, int D);
   /* device addresses inside the LOCAL slab for the current parity are resolved in-kernel from seq */
