@@ -57,13 +57,20 @@ __global__ void __launch_bounds__(256) p2p_route_send_kernel(P2PState* st, const
     key = ps_pack_key((uint32_t)j, (uint64_t)E[l]);
     owner = (int)ps_owner_of(key, (uint32_t)R);
   }
+  /* bucket positions: warp-aggregated counts into shared memory, then ONE global atomic per (block, owner) */
+  __shared__ int s_cnt[kP2PMaxRanks], s_base[kP2PMaxRanks];
+  if (threadIdx.x < kP2PMaxRanks) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
   const unsigned peers = __match_any_sync(0xffffffffu, owner);
   const int leader = __ffs(peers) - 1;
-  int base = 0;
-  if (valid && lane == leader) base = atomicAdd(&st->cursor[owner], __popc(peers));
-  base = __shfl_sync(0xffffffffu, base, leader);
+  int rank_in_block = 0;
+  if (valid && lane == leader) rank_in_block = atomicAdd(&s_cnt[owner], __popc(peers));
+  rank_in_block = __shfl_sync(0xffffffffu, rank_in_block, leader) + __popc(peers & ((1u << lane) - 1u));
+  __syncthreads();
+  if (threadIdx.x < R) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&st->cursor[threadIdx.x], s_cnt[threadIdx.x]) : 0;
+  __syncthreads();
   if (valid) {
-    const int pos = base + __popc(peers & ((1u << lane) - 1u));
+    const int pos = s_base[owner] + rank_in_block;
     if (pos < cap) {
       reinterpret_cast<unsigned long long*>(p2p_region(st, owner, st->off_keys))[(size_t)me * cap + pos] = key;
       send_pos[l] = owner * cap + pos;
