@@ -415,8 +415,8 @@ void Model::p2p_init(int R, int rank, int cap, void* handle_out64) {
   const long glen = (u.total + 2 + 3) / 4 * 4;
   if (!gsum) { gsum_len = glen; gsum = dmalloc_zero<float>((size_t)gsum_len, ctx->stream); }
   PS_REQUIRE(gsum_len >= glen, PS_ERR_STATE, "gradient buffer was created before p2p_init with a smaller size");
-  p2p.create(ctx, R, rank, has_emb ? cap : 1, has_emb ? emb.Dp : 4, std::max(2, Bmax * std::max(F, 1)), (int)glen);
-  if (has_emb) { send_pos = dmalloc<int32_t>((size_t)Bmax * F); emb.reserve((int64_t)R * cap); }
+  p2p.create(ctx, R, rank, has_emb ? cap : 1, has_emb ? emb.Dp : 4, std::max(2, Bmax * std::max(F, 1)), (int)glen, (int64_t)Bmax * std::max(F, 1));
+  if (has_emb) emb.reserve((int64_t)R * cap);
   p2p.get_handle(handle_out64);
 }
 
@@ -440,12 +440,13 @@ void Model::p2p_step(const int64_t* E, const float* X, const int64_t* W, const f
     wide.forward(W, N, F, wide_bias, wide_z);
   }
   if (has_emb) {
-    p2p.route_send(E, N, F, send_pos);                                          /* PSRouterClient.getList: keys out */
+    p2p.dedup_route(E, N, F);                                                   /* PSRouterClient.getList: each key of the batch once */
+    p2p.send_keys();
     p2p.publish_wait(CH_KEYS);
     emb.probe_packed(nullptr, R * cap, p2p.state());                            /* PServer.getList on the owner */
     p2p.gather_send(emb.w, D, emb.lk_slot);                                     /* rows back, stored by the gather itself */
     p2p.publish_wait(CH_ROWS);
-    p2p.unpack(send_pos, N, F, D, act[0], ld[0], X, Xn, F * D);                 /* + ConcatLayer */
+    p2p.unpack(N, F, D, act[0], ld[0], X, Xn, F * D);                           /* + ConcatLayer */
   } else {
     PS_CUDA(cudaMemcpy2DAsync(act[0], sizeof(float) * ld[0], X, sizeof(float) * Xn, sizeof(float) * Xn, N, cudaMemcpyDeviceToDevice, s));
   }
@@ -461,7 +462,8 @@ void Model::p2p_step(const int64_t* E, const float* X, const int64_t* W, const f
     shard_finish_scalars_p2p(ctx, st_dev, p2p.state(), u.total);
   }
   if (has_emb) {
-    p2p.pack_send(delta[0], ld[0], act[0], ld[0], send_pos, N, F, D);           /* client.push of the row gradients */
+    p2p.grad_reduce(delta[0], ld[0], act[0], ld[0], N, F, D);                   /* client.push: one gradient sum per unique key */
+    p2p.grad_send();
     p2p.publish_wait(CH_GRADS);
   }
   fork(s1, s);                                                                  /* the global skip flag */

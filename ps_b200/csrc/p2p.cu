@@ -39,46 +39,58 @@ __global__ void p2p_begin_kernel(P2PState* st) {
   if (threadIdx.x < kP2PMaxRanks) st->cursor[threadIdx.x] = 0;
 }
 
-/* PSRouterClient.getList, request side (PSRouterClient.java:60-68): bucket by owner and store each key
- * directly into the owner's keys_in[me][pos]; the last block publishes the per-owner counts and flags. */
-__global__ void __launch_bounds__(256) p2p_route_send_kernel(P2PState* st, const int64_t* __restrict__ E, int L, int F, int32_t* __restrict__ send_pos) {
-  /* field-major work order (t = j*N + n): consecutive bucket positions then hold the same field for consecutive
-   * samples, so the OWNER's probe and scatter kernels can collapse a hot key warp-wide (one atomic per 32) */
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+/* PSRouterClient.getList, request side (PSRouterClient.java:60-68): the router sends each key of the batch ONCE to
+ * its shard.  Phase 1: every lookup finds-or-inserts its key in the per-batch table, counts itself, and the first
+ * occurrence reserves a position in the owner's bucket (one global atomic per (block, owner)).              */
+__global__ void __launch_bounds__(256) p2p_dedup_kernel(P2PState* st, BatchSlot* __restrict__ bt, uint32_t BT, const int64_t* __restrict__ E, int L, int F,
+                                                        int32_t* __restrict__ lk_b) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;      /* field-major: a warp works on one field, consecutive samples */
   const int lane = threadIdx.x & 31;
-  const int R = st->R, cap = st->cap, me = st->me;
-  const bool valid = t < L;
-  int l = 0;
-  unsigned long long key = 0;
-  int owner = -1 - lane;
-  if (valid) {
+  const int R = st->R, cap = st->cap;
+  int b = -1, owner = 0;
+  if (t < L) {
     const int N = L / F, j = t / N;
-    l = (t - j * N) * F + j;
-    key = ps_pack_key((uint32_t)j, (uint64_t)E[l]);
+    const int l = (t - j * N) * F + j;
+    const unsigned long long key = ps_pack_key((uint32_t)j, (uint64_t)E[l]);
     owner = (int)ps_owner_of(key, (uint32_t)R);
+    uint32_t s = (uint32_t)(ps_mix64(key) >> 20) & (BT - 1u);
+    for (uint32_t p = 0; p < BT; ++p) {
+      const unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(&bt[s].key);
+      if (k == key) { b = (int)s; break; }
+      if (k == PS_KEY_EMPTY) {
+        const unsigned long long old = atomicCAS(&bt[s].key, (unsigned long long)PS_KEY_EMPTY, key);
+        if (old == PS_KEY_EMPTY || old == key) { b = (int)s; break; }
+      }
+      s = (s + 1u) & (BT - 1u);
+    }
+    lk_b[l] = b;
   }
-  /* bucket positions: warp-aggregated counts into shared memory, then ONE global atomic per (block, owner) */
+  const unsigned peers = __match_any_sync(0xffffffffu, b >= 0 ? b : (-1 - lane));
+  bool first = false;
+  if (b >= 0 && (__ffs(peers) - 1) == lane) first = atomicAdd(&bt[b].cnt, (uint32_t)__popc(peers)) == 0u;
   __shared__ int s_cnt[kP2PMaxRanks], s_base[kP2PMaxRanks];
   if (threadIdx.x < kP2PMaxRanks) s_cnt[threadIdx.x] = 0;
   __syncthreads();
-  const unsigned peers = __match_any_sync(0xffffffffu, owner);
-  const int leader = __ffs(peers) - 1;
   int rank_in_block = 0;
-  if (valid && lane == leader) rank_in_block = atomicAdd(&s_cnt[owner], __popc(peers));
-  rank_in_block = __shfl_sync(0xffffffffu, rank_in_block, leader) + __popc(peers & ((1u << lane) - 1u));
+  if (first) rank_in_block = atomicAdd(&s_cnt[owner], 1);
   __syncthreads();
   if (threadIdx.x < R) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&st->cursor[threadIdx.x], s_cnt[threadIdx.x]) : 0;
   __syncthreads();
-  if (valid) {
+  if (first) {
     const int pos = s_base[owner] + rank_in_block;
-    if (pos < cap) {
-      reinterpret_cast<unsigned long long*>(p2p_region(st, owner, st->off_keys))[(size_t)me * cap + pos] = key;
-      send_pos[l] = owner * cap + pos;
-    } else {
-      send_pos[l] = -1;
-      st->overflow = 1;
-    }
+    if (pos < cap) bt[b].upos = owner * cap + pos;
+    else { bt[b].upos = -1; st->overflow = 1; }
   }
+}
+
+/* Phase 2: {key, occurrences} of every unique key goes straight into its owner's keys_in[me][pos] */
+__global__ void __launch_bounds__(256) p2p_send_keys_kernel(P2PState* st, const BatchSlot* __restrict__ bt, uint32_t BT) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= BT) return;
+  const BatchSlot e = bt[s];
+  if (e.key == PS_KEY_EMPTY || e.upos < 0) return;
+  const int owner = e.upos / st->cap, pos = e.upos - owner * st->cap;
+  reinterpret_cast<ulonglong2*>(p2p_region(st, owner, st->off_keys))[(size_t)st->me * st->cap + pos] = make_ulonglong2(e.key, (unsigned long long)e.cnt);
 }
 
 /* all-gather by stores: this rank's `bytes` go to slot `me` of the channel's region on every rank */
@@ -140,7 +152,7 @@ __global__ void __launch_bounds__(256) p2p_gather_send_kernel(P2PState* st, cons
 }
 
 template <bool VEC>
-__global__ void __launch_bounds__(256) p2p_unpack_kernel(const P2PState* st, const int32_t* __restrict__ send_pos, int L, int F, int D,
+__global__ void __launch_bounds__(256) p2p_unpack_kernel(const P2PState* st, const BatchSlot* __restrict__ bt, const int32_t* __restrict__ lk_b, int L, int F, int D,
                                                          float* __restrict__ out, int ldo, const float* __restrict__ X, int Xn, int xoff, int N) {
   const int Dp = st->Dp;
   const float* rows = reinterpret_cast<const float*>(p2p_region(st, st->me, st->off_rows));
@@ -157,7 +169,8 @@ __global__ void __launch_bounds__(256) p2p_unpack_kernel(const P2PState* st, con
     const int part = (int)(g - l * tpl);
     if (l >= L) return;
     const int n = (int)(l / F), j = (int)(l - (long)n * F);
-    const int pos = send_pos[l];
+    const int b = lk_b[l];
+    const int pos = b >= 0 ? bt[b].upos : -1;
     const float4 v = pos >= 0 ? ld_f4(rows + (size_t)pos * Dp + part * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     st_f4(out + (size_t)n * ldo + j * D + part * 4, v);
   } else {
@@ -165,7 +178,8 @@ __global__ void __launch_bounds__(256) p2p_unpack_kernel(const P2PState* st, con
     const int d = (int)(g - l * Dp);
     if (l >= L || d >= D) return;
     const int n = (int)(l / F), j = (int)(l - (long)n * F);
-    const int pos = send_pos[l];
+    const int b = lk_b[l];
+    const int pos = b >= 0 ? bt[b].upos : -1;
     out[(size_t)n * ldo + j * D + d] = pos >= 0 ? rows[(size_t)pos * Dp + d] : 0.f;
   }
 }
@@ -182,56 +196,79 @@ __global__ void __launch_bounds__(256) p2p_reduce_kernel(const P2PState* st, flo
   gsum[i] = s;
 }
 
-/* KVStore.update → client.push per key (KVStore.java:257-260): per-lookup row gradient (ReLU mask of
- * EmbeddingField.java:91-93 applied here) stored into the owner's grads_in[me][pos]                 */
-template <bool VEC>
-__global__ void __launch_bounds__(256) p2p_pack_send_kernel(P2PState* st, const float* __restrict__ delta, int ldd, const float* __restrict__ act, int lda,
-                                                            const int32_t* __restrict__ send_pos, int L, int F, int D) {
-  const int Dp = st->Dp, cap = st->cap, me = st->me;
+/* KVStore.update → client.push per key (KVStore.java:257-260).  Phase 1: per-lookup row gradient (ReLU mask of
+ * EmbeddingField.java:91-93) summed per unique key into the local accumulator gacc[upos]; lanes of a warp work on the
+ * same field for consecutive samples, so duplicates collapse by shuffle before one 128-bit reduction.            */
+template <int TPL>
+__global__ void __launch_bounds__(256) p2p_grad_reduce_kernel(const P2PState* st, const BatchSlot* __restrict__ bt, const int32_t* __restrict__ lk_b,
+                                                              const float* __restrict__ delta, int ldd, const float* __restrict__ act, int lda,
+                                                              int N, int F, int D, float* __restrict__ gacc) {
+  const int Dp = st->Dp;
   const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (VEC) {
-    const int tpl = Dp >> 2;
-    const long l = g / tpl;
-    const int part = (int)(g - l * tpl);
-    if (l < L) {
-      const int pos = send_pos[l];
-      if (pos >= 0) {
-        const int n = (int)(l / F), j = (int)(l - (long)n * F);
-        const float4 dv = ld_f4(delta + (size_t)n * ldd + j * D + part * 4), av = ld_f4(act + (size_t)n * lda + j * D + part * 4);
-        float4 v;
-        v.x = __fmul_rn(dv.x, av.x > 0.f ? 1.f : 0.f); v.y = __fmul_rn(dv.y, av.y > 0.f ? 1.f : 0.f);
-        v.z = __fmul_rn(dv.z, av.z > 0.f ? 1.f : 0.f); v.w = __fmul_rn(dv.w, av.w > 0.f ? 1.f : 0.f);
-        const int owner = pos / cap, idx = pos - owner * cap;
-        st_f4(reinterpret_cast<float*>(p2p_region(st, owner, st->off_grads)) + ((size_t)me * cap + idx) * Dp + part * 4, v);
-      }
-    }
-    return;
+  const long L = (long)N * F;
+  const long lk = g / TPL;
+  const int part = (int)(g % TPL);
+  const int lane = threadIdx.x & 31, my_group = lane / TPL;
+  int upos = -1, n = 0, j = 0;
+  if (lk < L) {
+    j = (int)(lk / N); n = (int)(lk - (long)j * N);
+    const int b = lk_b[(long)n * F + j];
+    if (b >= 0) upos = bt[b].upos;
   }
-  const long l = g / Dp;
-  const int d = (int)(g - l * Dp);
-  if (l < L) {
-    const int pos = send_pos[l];
-    if (pos >= 0) {
-      const int n = (int)(l / F), j = (int)(l - (long)n * F);
-      float v = 0.f;
-      if (d < D) v = __fmul_rn(delta[(size_t)n * ldd + j * D + d], act[(size_t)n * lda + j * D + d] > 0.f ? 1.f : 0.f);
-      const int owner = pos / cap, idx = pos - owner * cap;
-      reinterpret_cast<float*>(p2p_region(st, owner, st->off_grads))[((size_t)me * cap + idx) * Dp + d] = v;
-    }
+  const bool valid = upos >= 0;
+  const bool lane_on = valid && part * 4 < D;
+  float4 gk = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (lane_on) {
+    const size_t od = (size_t)n * ldd + j * D + part * 4, oa = (size_t)n * lda + j * D + part * 4;
+    float dv[4] = {0.f, 0.f, 0.f, 0.f}, av[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (part * 4 + i < D) { dv[i] = delta[od + i]; av[i] = act[oa + i]; }
+    gk.x = __fmul_rn(dv[0], av[0] > 0.f ? 1.f : 0.f); gk.y = __fmul_rn(dv[1], av[1] > 0.f ? 1.f : 0.f);
+    gk.z = __fmul_rn(dv[2], av[2] > 0.f ? 1.f : 0.f); gk.w = __fmul_rn(dv[3], av[3] > 0.f ? 1.f : 0.f);
   }
+  const unsigned peers = __match_any_sync(0xffffffffu, valid ? upos : (-1 - lane));
+  const bool leader = ((__ffs(peers) - 1) / TPL) == my_group;
+  if (__any_sync(0xffffffffu, valid && __popc(peers) > TPL)) {
+    float4 sum = gk;
+#pragma unroll
+    for (int og = 0; og < 32 / TPL; ++og) {
+      const int src = og * TPL + part;
+      float4 o;
+      o.x = __shfl_sync(0xffffffffu, gk.x, src); o.y = __shfl_sync(0xffffffffu, gk.y, src);
+      o.z = __shfl_sync(0xffffffffu, gk.z, src); o.w = __shfl_sync(0xffffffffu, gk.w, src);
+      if (og != my_group && ((peers >> src) & 1u)) { sum.x += o.x; sum.y += o.y; sum.z += o.z; sum.w += o.w; }
+    }
+    gk = sum;
+  }
+  if (lane_on && leader) red_add_f4(gacc + (size_t)upos * Dp + part * 4, gk);
+}
+
+/* Phase 2: one gradient sum per unique key → its owner's grads_in[me][pos]; the local accumulator is zeroed for the next step */
+__global__ void __launch_bounds__(256) p2p_grad_send_kernel(P2PState* st, float* __restrict__ gacc) {
+  const int cap = st->cap, Dp = st->Dp, me = st->me, tpl = Dp >> 2;
+  const long total = (long)st->R * cap * tpl;
+  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  const int q = (int)(g / tpl), part = (int)(g - (long)q * tpl);
+  const int owner = q / cap, pos = q - owner * cap;
+  if (pos >= min(*reinterpret_cast<volatile int32_t*>(&st->cursor[owner]), cap)) return;
+  float* a = gacc + (size_t)q * Dp + part * 4;
+  const float4 v = __ldcg(reinterpret_cast<const float4*>(a));
+  st_f4(reinterpret_cast<float*>(p2p_region(st, owner, st->off_grads)) + ((size_t)me * cap + pos) * Dp + part * 4, v);
+  st_f4(a, make_float4(0.f, 0.f, 0.f, 0.f));
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
-void P2P::create(Ctx* c, int R_, int me_, int cap_, int Dp_, int NF_, int glen_) {
+void P2P::create(Ctx* c, int R_, int me_, int cap_, int Dp_, int NF_, int glen_, int64_t max_lookups) {
   PS_REQUIRE(R_ >= 1 && R_ <= kP2PMaxRanks && me_ >= 0 && me_ < R_ && cap_ > 0, PS_ERR_ARG, "p2p: bad rank layout");
   ctx = c; R = R_; me = me_; cap = cap_; Dp = Dp_; NF = NF_; glen = (glen_ + 3) / 4 * 4;
   size_t off = 0;
   host = P2PState{};
   host.R = R; host.me = me; host.cap = cap; host.Dp = Dp; host.NF = NF; host.glen = glen;
-  host.off_keys = off; off = align_up(off + (size_t)R * cap * 8, 256);
+  host.off_keys = off; off = align_up(off + (size_t)R * cap * 16, 256);
   host.off_rows = off; off = align_up(off + (size_t)R * cap * Dp * 4, 256);
   host.off_grads = off; off = align_up(off + (size_t)R * cap * Dp * 4, 256);
   host.off_wide = off; off = align_up(off + (size_t)R * NF * 8, 256);
@@ -243,6 +280,12 @@ void P2P::create(Ctx* c, int R_, int me_, int cap_, int Dp_, int NF_, int glen_)
   PS_CUDA(cudaMalloc(&slab, slab_bytes));
   PS_CUDA(cudaMemsetAsync(slab, 0, slab_bytes, ctx->stream));
   dev = dmalloc_zero<P2PState>(1, ctx->stream);
+  Lmax = max_lookups;
+  BT = 1024;
+  while ((int64_t)BT < 2 * Lmax) BT <<= 1;
+  bt = dmalloc_zero<BatchSlot>(BT, ctx->stream);
+  lk_b = dmalloc<int32_t>((size_t)std::max<int64_t>(Lmax, 1));
+  gacc = dmalloc_zero<float>((size_t)R * cap * Dp, ctx->stream);
   PS_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
@@ -270,8 +313,8 @@ void P2P::connect(const void* all_handles) {
 
 void P2P::destroy() {
   for (int r = 0; r < R; ++r) if (peer_mapped[r]) { cudaIpcCloseMemHandle(peer_mapped[r]); peer_mapped[r] = nullptr; }
-  dfree(slab); dfree(dev);
-  slab = nullptr; dev = nullptr; connected = false;
+  dfree(slab); dfree(dev); dfree(bt); dfree(lk_b); dfree(gacc);
+  slab = nullptr; dev = nullptr; bt = nullptr; lk_b = nullptr; gacc = nullptr; connected = false;
 }
 
 #define P2P_LAUNCHED() do { PS_LAUNCH_CHECK(); ctx->launches++; } while (0)
@@ -280,9 +323,16 @@ void P2P::publish(int channel) { p2p_publish_kernel<<<1, 32, 0, ctx->stream>>>(d
 
 void P2P::begin() { p2p_begin_kernel<<<1, 32, 0, ctx->stream>>>(dev); P2P_LAUNCHED(); }
 
-void P2P::route_send(const int64_t* E, int N, int F, int32_t* send_pos) {
+void P2P::dedup_route(const int64_t* E, int N, int F) {
   const int L = N * F;
-  p2p_route_send_kernel<<<ceil_div(L, 256), 256, 0, ctx->stream>>>(dev, E, L, F, send_pos);
+  PS_REQUIRE(L <= Lmax, PS_ERR_ARG, "p2p: batch larger than the de-duplication table");
+  PS_CUDA(cudaMemsetAsync(bt, 0, sizeof(BatchSlot) * BT, ctx->stream));
+  p2p_dedup_kernel<<<ceil_div(L, 256), 256, 0, ctx->stream>>>(dev, bt, BT, E, L, F, lk_b);
+  P2P_LAUNCHED();
+}
+
+void P2P::send_keys() {
+  p2p_send_keys_kernel<<<ceil_div(BT, 256), 256, 0, ctx->stream>>>(dev, bt, BT);
   P2P_LAUNCHED();
 }
 
@@ -304,11 +354,11 @@ void P2P::gather_send(const float* w, int D, const int32_t* lk_slot) {
   P2P_LAUNCHED();
 }
 
-void P2P::unpack(const int32_t* send_pos, int N, int F, int D, float* out, int ldo, const float* X, int Xn, int xoff) {
+void P2P::unpack(int N, int F, int D, float* out, int ldo, const float* X, int Xn, int xoff) {
   const bool vec = D % 4 == 0 && ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   const long xw = X ? (long)N * Xn : 0;
-  if (vec) p2p_unpack_kernel<true><<<ceil_div((long)N * F * (Dp / 4) + xw, 256), 256, 0, ctx->stream>>>(dev, send_pos, N * F, F, D, out, ldo, X, Xn, xoff, N);
-  else p2p_unpack_kernel<false><<<ceil_div((long)N * F * Dp + xw, 256), 256, 0, ctx->stream>>>(dev, send_pos, N * F, F, D, out, ldo, X, Xn, xoff, N);
+  if (vec) p2p_unpack_kernel<true><<<ceil_div((long)N * F * (Dp / 4) + xw, 256), 256, 0, ctx->stream>>>(dev, bt, lk_b, N * F, F, D, out, ldo, X, Xn, xoff, N);
+  else p2p_unpack_kernel<false><<<ceil_div((long)N * F * Dp + xw, 256), 256, 0, ctx->stream>>>(dev, bt, lk_b, N * F, F, D, out, ldo, X, Xn, xoff, N);
   P2P_LAUNCHED();
 }
 
@@ -317,10 +367,20 @@ void P2P::reduce_gsum(float* gsum) {
   P2P_LAUNCHED();
 }
 
-void P2P::pack_send(const float* delta, int ldd, const float* act, int lda, const int32_t* send_pos, int N, int F, int D) {
-  const bool vec = D % 4 == 0 && ldd % 4 == 0 && lda % 4 == 0 && (reinterpret_cast<uintptr_t>(delta) & 15) == 0 && (reinterpret_cast<uintptr_t>(act) & 15) == 0;
-  if (vec) p2p_pack_send_kernel<true><<<ceil_div((long)N * F * (Dp / 4), 256), 256, 0, ctx->stream>>>(dev, delta, ldd, act, lda, send_pos, N * F, F, D);
-  else p2p_pack_send_kernel<false><<<ceil_div((long)N * F * Dp, 256), 256, 0, ctx->stream>>>(dev, delta, ldd, act, lda, send_pos, N * F, F, D);
+void P2P::grad_reduce(const float* delta, int ldd, const float* act, int lda, int N, int F, int D) {
+  int tpl = 1;
+  while (tpl < Dp / 4) tpl <<= 1;
+  const long total = (long)N * F * tpl;
+  const int grid = ceil_div(total, 256);
+#define PS_GR(T) p2p_grad_reduce_kernel<T><<<grid, 256, 0, ctx->stream>>>(dev, bt, lk_b, delta, ldd, act, lda, N, F, D, gacc)
+  switch (tpl) { case 1: PS_GR(1); break; case 2: PS_GR(2); break; case 4: PS_GR(4); break; case 8: PS_GR(8); break; case 16: PS_GR(16); break; default: PS_GR(32); break; }
+#undef PS_GR
+  P2P_LAUNCHED();
+}
+
+void P2P::grad_send() {
+  const long total = (long)R * cap * (Dp / 4);
+  p2p_grad_send_kernel<<<ceil_div(total, 256), 256, 0, ctx->stream>>>(dev, gacc);
   P2P_LAUNCHED();
 }
 

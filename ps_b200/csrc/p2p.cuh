@@ -8,9 +8,9 @@
  * involvement — a whole sharded step is one CUDA graph per rank.
  *
  * Mailbox slab of a rank (double-buffered by step parity p = seq & 1):
- *   keys_in [p][R][cap]      u64   packed keys sent by rank r                (getList request)
+ *   keys_in [p][R][cap]      2xu64 {packed key, occurrences at the sender}: rank r's DE-DUPLICATED keys (getList request)
  *   rows_in [p][R][cap][Dp]  f32   rows returned by owner r                  (getList response)
- *   grads_in[p][R][cap][Dp]  f32   row gradients pushed by rank r            (push)
+ *   grads_in[p][R][cap][Dp]  f32   per-key gradient SUMS pushed by rank r    (push)
  *   wide_in [p][R][NF]       i64   wide ids of rank r                        (replicated wide table)
  *   gsum_in [p][R][glen]     f32   dense gradient sums + loss + gbar of r    (PServer sync-mode sum)
  *   counts  [p][R]           i32   number of valid keys from rank r
@@ -39,6 +39,12 @@ struct P2PState {                      /* lives in device memory; kernels read i
   int32_t overflow;
 };
 
+struct __align__(16) BatchSlot {       /* the sender's per-batch de-duplication table: key → bucket position, occurrences */
+  unsigned long long key;
+  uint32_t cnt;
+  int32_t upos;                       /* owner * cap + position in the owner's bucket, -1 on overflow */
+};
+
 struct P2P {
   Ctx* ctx = nullptr;
   int R = 0, me = 0, cap = 0, Dp = 0, NF = 0, glen = 0;
@@ -49,22 +55,28 @@ struct P2P {
   P2PState* dev = nullptr;
   bool connected = false;
 
-  void create(Ctx* c, int R_, int me_, int cap_, int Dp_, int NF_, int glen_);
+  void create(Ctx* c, int R_, int me_, int cap_, int Dp_, int NF_, int glen_, int64_t max_lookups);
   void get_handle(void* out64);                                  /* cudaIpcMemHandle_t of the slab */
   void connect(const void* all_handles /* R x 64 bytes, rank order */);
   void destroy();
 
   /* --- kernels (asynchronous on ctx->stream) --- */
   void begin();                                                                     /* seq += 1, cursors = 0 */
-  void route_send(const int64_t* E, int N, int F, int32_t* send_pos);               /* keys → owners' keys_in */
+  /* sender-side de-duplication (what PSRouterClient's key→shard map does): unique keys get a bucket position,
+   * every lookup remembers its batch slot; then {key, occurrences} of each unique key goes to its owner    */
+  BatchSlot* bt = nullptr; uint32_t BT = 0; int32_t* lk_b = nullptr; float* gacc = nullptr; int64_t Lmax = 0;
+  void dedup_route(const int64_t* E, int N, int F);
+  void send_keys();
   void bcast(const void* src, size_t bytes, int channel);                           /* wide ids / gsum → every peer */
   void publish(int channel);                                                        /* flag every peer (after a producer kernel) */
   void publish_wait(int channel);                                                   /* publish + wait for all peers, one launch */
   void wait(int channel);
   void gather_send(const float* w, int D, const int32_t* lk_slot);                  /* rows → requesters' rows_in */
-  void unpack(const int32_t* send_pos, int N, int F, int D, float* out, int ldo, const float* X, int Xn, int xoff);   /* rows_in (+ X) → concat buffer */
+  void unpack(int N, int F, int D, float* out, int ldo, const float* X, int Xn, int xoff);   /* rows_in (+ X) → concat buffer */
   void reduce_gsum(float* gsum);                                                    /* sum over ranks, fixed order */
-  void pack_send(const float* delta, int ldd, const float* act, int lda, const int32_t* send_pos, int N, int F, int D);
+  /* per-lookup row gradients (ReLU mask applied) summed per unique key locally, then one sum per key to its owner */
+  void grad_reduce(const float* delta, int ldd, const float* act, int lda, int N, int F, int D);
+  void grad_send();
   /* device addresses inside the LOCAL slab for the current parity are resolved in-kernel from seq */
   const P2PState* state() const { return dev; }
   bool overflowed();

@@ -68,13 +68,18 @@ __global__ void __launch_bounds__(256) emb_probe_kernel(EmbSlot* __restrict__ sl
   const int lane = threadIdx.x & 31;
   int slot = -1;
   bool first = false;
+  uint32_t add = 1u;
   if (t < L) {
     int l = t;
     unsigned long long key = PS_KEY_EMPTY;
     if (p2p != nullptr) {                      /* owner side of the peer-memory exchange: this step's keys_in mailbox */
       const int src = t / p2p->cap, idx = t - src * p2p->cap;
-      if (idx < reinterpret_cast<const int32_t*>(p2p_region(p2p, p2p->me, p2p->off_counts))[src])
-        key = reinterpret_cast<const unsigned long long*>(p2p_region(p2p, p2p->me, p2p->off_keys))[t];
+      if (idx < reinterpret_cast<const int32_t*>(p2p_region(p2p, p2p->me, p2p->off_counts))[src]) {
+        /* entries are {key, occurrences at the sender}: senders de-duplicate their batch (PSRouterClient sends a key once) */
+        const ulonglong2 e = reinterpret_cast<const ulonglong2*>(p2p_region(p2p, p2p->me, p2p->off_keys))[t];
+        key = e.x;
+        add = (uint32_t)e.y + (1u << 24);       /* low 24 bits: occurrences; high 8 bits: entries (= arrivals the update waits for) */
+      }
     } else if (F > 0) {
       const int N = L / F; const int j = t / N; l = (t - j * N) * F + j;
       key = ps_pack_key((uint32_t)(l % F), (uint64_t)(int64_t)ids[l]);
@@ -95,7 +100,8 @@ __global__ void __launch_bounds__(256) emb_probe_kernel(EmbSlot* __restrict__ sl
   }
   /* warp-aggregated occurrence count: lanes holding the same slot add once */
   const unsigned peers = __match_any_sync(0xffffffffu, slot >= 0 ? slot : (-1 - lane));
-  if (slot >= 0 && (__ffs(peers) - 1) == lane) first = atomicAdd(&slots[slot].cnt, (uint32_t)__popc(peers)) == 0u;
+  const uint32_t total_add = __reduce_add_sync(peers, add);
+  if (slot >= 0 && (__ffs(peers) - 1) == lane) first = atomicAdd(&slots[slot].cnt, total_add) == 0u;
   /* ONE atomic per block on the unique-key counter (a single address: per-warp atomics with return
    * serialise in one L2 slice).  The counter is MONOTONIC across batches (no per-step reset node):
    * accumulator rows are a ring indexed by counter & umask, and every entry is zeroed again by the
@@ -202,6 +208,10 @@ __global__ void __launch_bounds__(256) emb_scatter_update_kernel(EmbSlot* __rest
     const uint4 m = *reinterpret_cast<const uint4*>(&slots[slot]);
     cnt = m.z; uidx = m.w;
   }
+  /* single GPU: every occurrence arrives here, so arrivals == occurrences; peer-memory exchange: senders pre-reduce,
+   * cnt packs {entries << 24 | occurrences}                                                                        */
+  const uint32_t n_arrivals = p2p != nullptr ? (cnt >> 24) : cnt;
+  const uint32_t n_occ = p2p != nullptr ? (cnt & 0xFFFFFFu) : cnt;
   if (skip) {                                   /* DNN.java:58-63 early exit: nothing was pushed, just forget the batch */
     if (valid && part == 0) slots[slot].cnt = 0u;
     return;
@@ -249,12 +259,12 @@ __global__ void __launch_bounds__(256) emb_scatter_update_kernel(EmbSlot* __rest
   uint32_t ticket = 0;
   if (valid && leader && part == 0) ticket = atomicAdd(&arrived[uidx], (uint32_t)ngroups);
   ticket = __shfl_sync(0xffffffffu, ticket, my_group * TPL);
-  const bool last = valid && leader && (ticket + (uint32_t)ngroups == cnt);
+  const bool last = valid && leader && (ticket + (uint32_t)ngroups == n_arrivals);
   if (!last) return;
   bool do_upd = true;
   if (upd.kind == PS_UPD_FTRL) {                /* FtrlUpdater.java:52: `if (dw.get(0) == 0) return w` */
     const float S0 = __ldcg(acc + (size_t)uidx * Dp);
-    do_upd = emb_geff(S0, cnt, calls) != 0.0f;
+    do_upd = emb_geff(S0, n_occ, calls) != 0.0f;
   }
   if (lane_on) {
     float* ap = acc + (size_t)uidx * Dp + part * 4;
@@ -263,10 +273,10 @@ __global__ void __launch_bounds__(256) emb_scatter_update_kernel(EmbSlot* __rest
       const size_t o = (size_t)slot * Dp + part * 4;
       float4 wv = ld_f4(w + o), m1 = make_float4(0.f, 0.f, 0.f, 0.f), m2 = m1;
       if (upd.kind != PS_UPD_SIMPLE) { m1 = ld_f4(s1 + o); m2 = ld_f4(s2 + o); }
-      apply_elem(upd, wv.x, m1.x, m2.x, emb_geff(S.x, cnt, calls));
-      apply_elem(upd, wv.y, m1.y, m2.y, emb_geff(S.y, cnt, calls));
-      apply_elem(upd, wv.z, m1.z, m2.z, emb_geff(S.z, cnt, calls));
-      apply_elem(upd, wv.w, m1.w, m2.w, emb_geff(S.w, cnt, calls));
+      apply_elem(upd, wv.x, m1.x, m2.x, emb_geff(S.x, n_occ, calls));
+      apply_elem(upd, wv.y, m1.y, m2.y, emb_geff(S.y, n_occ, calls));
+      apply_elem(upd, wv.z, m1.z, m2.z, emb_geff(S.z, n_occ, calls));
+      apply_elem(upd, wv.w, m1.w, m2.w, emb_geff(S.w, n_occ, calls));
       st_f4(w + o, wv);
       if (upd.kind != PS_UPD_SIMPLE) { st_f4(s1 + o, m1); st_f4(s2 + o, m2); }
     }
