@@ -47,12 +47,19 @@ __global__ void __launch_bounds__(256) p2p_dedup_kernel(P2PState* st, BatchSlot*
   const int t = blockIdx.x * blockDim.x + threadIdx.x;      /* field-major: a warp works on one field, consecutive samples */
   const int lane = threadIdx.x & 31;
   const int R = st->R, cap = st->cap;
-  int b = -1, owner = 0;
+  int b = -1, owner = 0, l = -1;
+  unsigned long long key = PS_KEY_EMPTY;
   if (t < L) {
     const int N = L / F, j = t / N;
-    const int l = (t - j * N) * F + j;
-    const unsigned long long key = ps_pack_key((uint32_t)j, (uint64_t)E[l]);
+    l = (t - j * N) * F + j;
+    key = ps_pack_key((uint32_t)j, (uint64_t)E[l]);
     owner = (int)ps_owner_of(key, (uint32_t)R);
+  }
+  /* duplicates inside the warp (a hot key fills whole warps) are resolved by ONE lane: one probe, one count update */
+  const unsigned peers = __match_any_sync(0xffffffffu, key != PS_KEY_EMPTY ? key : (unsigned long long)lane);
+  const int leader = __ffs(peers) - 1;
+  bool first = false;
+  if (key != PS_KEY_EMPTY && lane == leader) {
     uint32_t s = (uint32_t)(ps_mix64(key) >> 20) & (BT - 1u);
     for (uint32_t p = 0; p < BT; ++p) {
       const unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(&bt[s].key);
@@ -63,11 +70,10 @@ __global__ void __launch_bounds__(256) p2p_dedup_kernel(P2PState* st, BatchSlot*
       }
       s = (s + 1u) & (BT - 1u);
     }
-    lk_b[l] = b;
+    if (b >= 0) first = atomicAdd(&bt[b].cnt, (uint32_t)__popc(peers)) == 0u;
   }
-  const unsigned peers = __match_any_sync(0xffffffffu, b >= 0 ? b : (-1 - lane));
-  bool first = false;
-  if (b >= 0 && (__ffs(peers) - 1) == lane) first = atomicAdd(&bt[b].cnt, (uint32_t)__popc(peers)) == 0u;
+  b = __shfl_sync(0xffffffffu, b, leader);
+  if (l >= 0) lk_b[l] = b;
   __shared__ int s_cnt[kP2PMaxRanks], s_base[kP2PMaxRanks];
   if (threadIdx.x < kP2PMaxRanks) s_cnt[threadIdx.x] = 0;
   __syncthreads();
