@@ -133,6 +133,36 @@ def run_reference(args, cfg, rank):
     print(json.dumps(line), flush=True)
 
 
+def large_batch_roofline(ps, ctx, dev, hbm_peak, name, seed):
+    """The embedding kernels at a batch large enough to be bandwidth- rather than launch-latency-bound (cfg4 shapes:
+    B=16384, D=64, 10 M keys): same kernels, same measurement (replayed in a CUDA graph, CUDA events on the library's stream)."""
+    import torch
+    cfg = dict(CONFIGS[name])
+    B, F, D, Xn, V = cfg["B"], cfg["F"], cfg["D"], cfg["Xn"], cfg["V"]
+    model = ps.Model(ctx, cfg["kind"], F, D, Xn, cfg["fc"], emb_capacity=2 * V + (1 << 16), max_batch=B)
+    syn = Synth(F=F, Xn=Xn, V=V, dist="zipf", seed=seed)
+    ring = [syn.batch(B) for _ in range(8)]
+    dev_ring = [{k: torch.from_numpy(np.ascontiguousarray(v)).cuda(dev) for k, v in b.items()} for b in ring]
+    torch.cuda.synchronize()
+
+    def p(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else None
+    for _ in range(2):                       # create the ring's keys, reach the steady state of the table
+        for d in dev_ring:
+            model.train_step_dev(p(d.get("E")), p(d["X"]), p(d.get("W")), p(d["Y"]), B)
+    model.read_loss()
+    kt = model.kernel_times([d["E"].data_ptr() for d in dev_ring], B, reps=32)
+    L = B * F
+    uniq = float(np.mean([len(np.unique(b["E"])) for b in ring]))
+    out = {"workload": f"{name} shapes: B={B} F={F} D={D} vocab={V} zipf, {uniq:.0f} unique keys/batch", "peak": hbm_peak, "unit": "GB/s"}
+    for k, bytes_ in {"emb_gather": L * (8 + 8 * D), "emb_scatter_update": L * (8 + 4 * D) + uniq * 24 * D}.items():
+        us = kt[k] + (kt["emb_probe"] if k == "emb_gather" else 0.0)
+        out[k] = {"us": us, "alg_bytes": bytes_, "gbs": bytes_ / max(us, 1e-3) / 1e3, "frac": bytes_ / max(us, 1e-3) / 1e3 / hbm_peak}
+    out["emb_probe_us"] = kt["emb_probe"]
+    model.close()
+    return out
+
+
 def workload_name(args, cfg):
     return (f"{args.config}: {cfg['kind']} synthetic Criteo-libsvm, F={cfg['F']} Xn={cfg['Xn']} D={cfg['D']} vocab={cfg['V']} "
             f"fc={cfg['fc']} batch={cfg['B']}/GPU emb_opt={cfg['emb_opt']} keys={args.dist}")
@@ -154,6 +184,7 @@ def main():
     ap.add_argument("--slack", type=float, default=2.0)
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
     ap.add_argument("--force-sharded", action="store_true", help="use the sharded step even with one rank (profiling)")
+    ap.add_argument("--large", default="cfg4", help="shapes for the large-batch embedding roofline ('' = skip)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     rank = int(os.environ.get("RANK", "0"))
@@ -340,6 +371,10 @@ def main():
                     "how": "algorithmic bytes (SURVEY 8d) / mean device time of the kernel replayed 64x in a CUDA graph over the batch ring "
                            "(CUDA events on the library's stream); emb_gather includes its probe kernel"}
 
+    large = None
+    if roofline is not None and args.large:
+        large = large_batch_roofline(ps, ctx, local_rank, hbm_peak, args.large, 20261017 + 4)
+
     if rank == 0:
         cpu = None
         if world == 1:
@@ -360,7 +395,7 @@ def main():
                            cap * (16 + 12 * D) / 1e6, len(ring))},
             "e2e": {"value": total / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
                     "api": "ps_model_submit/ps_model_collect (2 steps in flight)"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels_us": phase_us, "hbm_kernels": kernels,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_large_batch": large, "kernels_us": phase_us, "hbm_kernels": kernels,
             "cpu_baseline": cpu, "loss": loss, "loss_e2e": loss_e2e, "unique_keys_per_batch": uniq,
         }
         print(json.dumps(line), flush=True)

@@ -51,7 +51,14 @@ int ps_ctx_create(int device, uint64_t seed, ps_ctx** out) {
   PS_REQUIRE(prop.major >= 10, PS_ERR_CUDA, "ps_ctx_create: libps_b200 is built for sm_100a (Blackwell) only");
   ps_ctx* c = new ps_ctx();
   c->c.device = device; c->c.seed = seed; c->c.num_sms = prop.multiProcessorCount;
-  PS_CUDA(cudaStreamCreateWithFlags(&c->c.stream, cudaStreamNonBlocking));
+  /* the step's critical chain (forward, dgrad, embedding update) runs on the HIGHEST priority: its CTAs are dispatched
+   * before those of the side branches (weight gradients, dense update) whenever both are pending (PS_STREAM_PRIO=0: off) */
+  int prio_lo = 0, prio_hi = 0;
+  PS_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  const char* pe = std::getenv("PS_STREAM_PRIO");
+  c->c.prio_main = (pe && pe[0] == '0') ? 0 : prio_hi;
+  c->c.prio_side = (pe && pe[0] == '0') ? 0 : prio_lo;
+  PS_CUDA(cudaStreamCreateWithPriority(&c->c.stream, cudaStreamNonBlocking, c->c.prio_main));
   PS_CUDA(cudaStreamCreateWithFlags(&c->c.copy_stream, cudaStreamNonBlocking));
   *out = c;
   PS_CATCH

@@ -54,6 +54,7 @@ struct Ctx {
   cudaStream_t stream = nullptr;   /* compute stream: every kernel of a step is ordered on it */
   cudaStream_t copy_stream = nullptr; /* H2D staging for the pipelined trainer */
   int fc_precision = PS_FC_FP32;
+  int prio_main = 0, prio_side = 0; /* stream priorities of the critical chain / the side branches */
   long launches = 0;               /* kernels launched by this library (bench gpu_launches) */
 };
 

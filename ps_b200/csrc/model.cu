@@ -96,7 +96,7 @@ void Model::create(Ctx* c, int kind_, int F_, int D_, int Xn_, const int32_t* fc
   tail_ws = dmalloc_zero<float>(kTailWorkspaceFloats, s);
   ev_pool.resize(48);
   for (auto& e : ev_pool) PS_CUDA(cudaEventCreate(&e));
-  for (auto& a : aux) PS_CUDA(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+  for (auto& a : aux) PS_CUDA(cudaStreamCreateWithPriority(&a, cudaStreamNonBlocking, ctx->prio_side));
   for (auto& e : sync_ev) PS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   fc_tf32_init();
   for (auto& S : stage) {
@@ -295,8 +295,8 @@ void Model::forward_backward(const int64_t* W, const int64_t* W_all, int n_all, 
   for (int l = L - 1; l >= 0; --l) {
     fork(s, s1);                                 /* delta[l+1] (tail or dgrad(l+1)) is ready */
     if (l == 0) fork(s2, s1);                    /* act_t[0] */
+    dgrad_layer(l, N);                           /* captured first: the critical chain's node precedes its sibling */
     { StreamScope sc(ctx, s1); wgrad_layer(l, N); }
-    dgrad_layer(l, N);
     mark(("fc_dgrad" + std::to_string(l)).c_str());
   }
 }

@@ -60,7 +60,7 @@ __device__ __forceinline__ int emb_find_or_insert(EmbSlot* slots, uint32_t C, un
 template <class IdT>
 __global__ void __launch_bounds__(256) emb_probe_kernel(EmbSlot* __restrict__ slots, uint32_t C, float* __restrict__ w, int Dp, int D,
                                                         const IdT* __restrict__ ids, int L, int F, uint64_t seed, float maxv,
-                                                        int32_t* __restrict__ lk_slot, uint32_t umask,
+                                                        int32_t* __restrict__ lk_slot,
                                                         uint32_t* __restrict__ counters, const P2PState* __restrict__ p2p) {
   /* field-major work order (t = j*N + n): the 32 lanes of a warp probe the SAME field for consecutive
    * samples, so a hot key (a low-cardinality field) is counted with one L2 atomic per warp, not 32 */
@@ -102,27 +102,19 @@ __global__ void __launch_bounds__(256) emb_probe_kernel(EmbSlot* __restrict__ sl
   const unsigned peers = __match_any_sync(0xffffffffu, slot >= 0 ? slot : (-1 - lane));
   const uint32_t total_add = __reduce_add_sync(peers, add);
   if (slot >= 0 && (__ffs(peers) - 1) == lane) first = atomicAdd(&slots[slot].cnt, total_add) == 0u;
-  /* ONE atomic per block on the unique-key counter (a single address: per-warp atomics with return
-   * serialise in one L2 slice).  The counter is MONOTONIC across batches (no per-step reset node):
-   * accumulator rows are a ring indexed by counter & umask, and every entry is zeroed again by the
-   * group that consumed it.                                                                       */
+  /* the key's accumulator row for this batch is the one indexed by the work index of its FIRST lookup: no
+   * numbering pass, nothing to reset (the row is zeroed again by the lookup that consumes it)            */
+  if (first) slots[slot].uidx = (uint32_t)t;
+  /* statistics only (StepStatus.n_unique): one fire-and-forget reduction per block on a monotonic counter */
   __shared__ uint32_t warp_firsts[8];
-  __shared__ uint32_t block_base;
   const unsigned firsts = __ballot_sync(0xffffffffu, first);
-  const int wid = threadIdx.x >> 5;
-  if (lane == 0) warp_firsts[wid] = (uint32_t)__popc(firsts);
+  if (lane == 0) warp_firsts[threadIdx.x >> 5] = (uint32_t)__popc(firsts);
   __syncthreads();
   if (threadIdx.x == 0) {
     uint32_t total = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) total += warp_firsts[i];
-    block_base = total ? atomicAdd(&counters[0], total) : 0u;
-  }
-  __syncthreads();
-  if (first) {
-    uint32_t before = 0;
-    for (int i = 0; i < wid; ++i) before += warp_firsts[i];
-    slots[slot].uidx = (block_base + before + (uint32_t)__popc(firsts & ((1u << lane) - 1u))) & umask;
+    if (total) atomicAdd(&counters[0], total);
   }
 }
 
@@ -174,115 +166,186 @@ __device__ __forceinline__ float emb_geff(float S, uint32_t n, int calls) {
   return __fdiv_rn(__fadd_rn(q, S), (float)(2u * n));
 }
 
-/* Fused sparse backward: one launch does
- *   (1) g_k = delta[:,k] * (A[:,k] > 0)                          EmbeddingField.java:91-93
- *   (2) warp-aggregated scatter-add of g_k into the batch-unique accumulator (lanes of a warp work
- *       on the SAME field for consecutive samples, so hot keys collapse before the L2 reduction)
- *   (3) the group that delivers a key's last occurrence (ticket == cnt) reads S back from L2,
- *       forms g_eff, runs the Adam / Ftrl / SGD step on w, s1, s2 in place, and resets the
- *       per-batch state (acc, ticket, cnt) — KVStore.sum + update + clear in one pass.          */
-template <int TPL, bool ALIGNED>
-__global__ void __launch_bounds__(256) emb_scatter_update_kernel(EmbSlot* __restrict__ slots, float* __restrict__ w, float* __restrict__ s1,
-                                                                 float* __restrict__ s2, int Dp, int D, const int32_t* __restrict__ lk_slot,
-                                                                 int N, int F, const float* __restrict__ delta, int ldd,
-                                                                 const float* __restrict__ act, int lda, float* __restrict__ acc,
-                                                                 uint32_t* __restrict__ arrived, UpdaterDev upd, int calls,
-                                                                 const int* __restrict__ skip_flag, const P2PState* __restrict__ p2p) {
+/* Grid-wide barrier for a kernel whose WHOLE grid is resident (launch_scatter sizes the grid with the occupancy
+ * API): bar[0] counts arrivals, bar[1] is the generation the waiters watch.  Everything a block did before the
+ * barrier (its L2 reductions included) is visible to every block after it.  A bounded spin turns a scheduling
+ * accident into an error flag instead of a hung GPU.                                                          */
+__device__ __forceinline__ void grid_barrier(uint32_t* bar, uint32_t nblocks, uint32_t* err) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t gen, cur;
+    asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");
+    __threadfence();
+    if (atomicAdd(bar, 1u) == nblocks - 1u) {
+      bar[0] = 0u;
+      __threadfence();
+      asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(bar + 1), "r"(gen + 1u) : "memory");
+    } else {
+      unsigned long long t0 = 0, t1;
+      uint32_t spins = 0;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      do {
+        asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(cur) : "l"(bar + 1) : "memory");
+        if (cur == gen && (++spins & 1023u) == 0u) {
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+          if (t1 - t0 > 2000000000ull) { *err = 2u; break; }
+        }
+      } while (cur == gen);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+/* Fused sparse backward, ONE launch, two phases separated by a grid barrier:
+ *   phase 1  g_k = delta[:,k] * (A[:,k] > 0)  (EmbeddingField.java:91-93); lanes of a warp work on the SAME field
+ *            for consecutive samples, so duplicates of a hot key are first summed inside the warp (a reduce-by-key
+ *            tree over the lanes __match_any_sync groups) and the warp issues ONE red.global.add.v4.f32 per key and
+ *            16 B chunk into the key's accumulator row (L2-resident, indexed by the work index of the key's first
+ *            lookup, which emb_probe left in the slot record)
+ *   phase 2  the lookup that owns the accumulator row reads S back from L2, forms g_eff, runs the Adam / Ftrl /
+ *            SGD step on w, s1, s2 in place and resets the per-batch state (acc, cnt) — KVStore.sum + update +
+ *            clear (KVStore.java:192-200,240-277).
+ * TPL lanes cooperate on one lookup, each owning CPL 16 B chunks of the row.                                   */
+template <int TPL, int CPL, bool ALIGNED>
+__global__ void __launch_bounds__(256, CPL == 2 ? 5 : 6)
+emb_scatter_update_kernel(EmbSlot* __restrict__ slots, float* __restrict__ w, float* __restrict__ s1, float* __restrict__ s2, int Dp, int D,
+                          const int32_t* __restrict__ lk_slot, int N, int F, const float* __restrict__ delta, int ldd,
+                          const float* __restrict__ act, int lda, float* __restrict__ acc, uint32_t* __restrict__ bar,
+                          uint32_t* __restrict__ counters, UpdaterDev upd, int calls, const int* __restrict__ skip_flag,
+                          const P2PState* __restrict__ p2p) {
+  constexpr int GPW = 32 / TPL;                  /* lookups (lane groups) per warp */
   if (p2p != nullptr) delta = reinterpret_cast<const float*>(p2p_region(p2p, p2p->me, p2p->off_grads));   /* this step's grads_in mailbox */
   const bool skip = skip_flag != nullptr && *skip_flag != 0;
-  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long L = (long)N * F;
-  const long lk = g / TPL;
-  const int part = (int)(g % TPL);
   const int lane = threadIdx.x & 31;
-  const int my_group = lane / TPL;
-  bool valid = lk < L;
-  int slot = -1, n = 0, j = 0;
-  if (valid) {
-    j = (int)(lk / N); n = (int)(lk - (long)j * N);
-    slot = lk_slot[(long)n * F + j];
-    valid = slot >= 0;
-  }
-  uint32_t cnt = 0, uidx = 0;
-  if (valid) {
-    const uint4 m = *reinterpret_cast<const uint4*>(&slots[slot]);
-    cnt = m.z; uidx = m.w;
-  }
-  /* single GPU: every occurrence arrives here, so arrivals == occurrences; peer-memory exchange: senders pre-reduce,
-   * cnt packs {entries << 24 | occurrences}                                                                        */
-  const uint32_t n_arrivals = p2p != nullptr ? (cnt >> 24) : cnt;
-  const uint32_t n_occ = p2p != nullptr ? (cnt & 0xFFFFFFu) : cnt;
-  if (skip) {                                   /* DNN.java:58-63 early exit: nothing was pushed, just forget the batch */
-    if (valid && part == 0) slots[slot].cnt = 0u;
+  const int part = lane % TPL, my_group = lane / TPL;
+  const int c0 = part * CPL * 4;                 /* first float of this lane's chunks */
+  const long stride = (long)gridDim.x * (256 / TPL);
+  const long warp_first = ((long)blockIdx.x * 256 + (threadIdx.x & ~31)) / TPL;
+  if (skip) {                                    /* DNN.java:58-63 early exit: nothing was pushed, just forget the batch */
+    for (long wb = warp_first; wb < L; wb += stride) {
+      const long lk = wb + my_group;
+      if (lk < L && part == 0) {
+        const int j = (int)(lk / N), n = (int)(lk - (long)j * N);
+        const int slot = lk_slot[(long)n * F + j];
+        if (slot >= 0) slots[slot].cnt = 0u;
+      }
+    }
     return;
   }
-  const bool lane_on = valid && part * 4 < D;
-  float4 gk = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (lane_on) {
-    const size_t od = (size_t)n * ldd + j * D + part * 4, oa = (size_t)n * lda + j * D + part * 4;
-    float dv[4] = {0.f, 0.f, 0.f, 0.f}, av[4] = {0.f, 0.f, 0.f, 0.f};
-    if (ALIGNED) {
-      const float4 d4 = ld_f4(delta + od);
-      const float4 a4 = act ? ld_f4(act + oa) : make_float4(1.f, 1.f, 1.f, 1.f);   /* act == null: the mask was applied by the sender */
-      dv[0] = d4.x; dv[1] = d4.y; dv[2] = d4.z; dv[3] = d4.w;
-      av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
-    } else {
+  /* lanes holding the same `part` of their lookups: bits at multiples of TPL, shifted by part */
+  unsigned part_lanes = 0u;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) if (part * 4 + i < D) { dv[i] = delta[od + i]; av[i] = act ? act[oa + i] : 1.f; }
-    }
-    /* Relu.backward: dy *= (y > 0 ? 1 : 0)  (activations/Relu.java:14-19) */
-    gk.x = __fmul_rn(dv[0], av[0] > 0.f ? 1.f : 0.f); gk.y = __fmul_rn(dv[1], av[1] > 0.f ? 1.f : 0.f);
-    gk.z = __fmul_rn(dv[2], av[2] > 0.f ? 1.f : 0.f); gk.w = __fmul_rn(dv[3], av[3] > 0.f ? 1.f : 0.f);
-  }
-  /* ---- warp aggregation of duplicate keys ---- */
-  const unsigned peers = __match_any_sync(0xffffffffu, valid ? slot : (-1 - lane));
-  const int ngroups = __popc(peers) / TPL;      /* groups of this warp holding the same key (>= 1 when valid) */
-  const bool leader = (( __ffs(peers) - 1) / TPL) == my_group;
-  if (__any_sync(0xffffffffu, valid && ngroups > 1)) {
-    float4 sum = gk;
+  for (int g = 0; g < GPW; ++g) part_lanes |= 1u << (g * TPL);
+  part_lanes <<= part;
+
+  int slot_r = -1; uint32_t cnt_r = 0u, uidx_r = 0u;     /* the first iteration's lookup stays in registers across the barrier */
+  /* ---------------- phase 1: masked gradients → warp reduce-by-key → L2 reductions ---------------- */
+  for (long wb = warp_first; wb < L; wb += stride) {
+    const long lk = wb + my_group;
+    bool valid = lk < L;
+    int slot = -1, n = 0, j = 0;
+    if (valid) { j = (int)(lk / N); n = (int)(lk - (long)j * N); }
+    float4 gk[CPL];
 #pragma unroll
-    for (int og = 0; og < 32 / TPL; ++og) {
-      const int src = og * TPL + part;
-      const float4 o = shfl_f4(gk, src);
-      if (og != my_group && ((peers >> src) & 1u)) { sum.x += o.x; sum.y += o.y; sum.z += o.z; sum.w += o.w; }
+    for (int c = 0; c < CPL; ++c) gk[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+      /* the gradient / activation loads do not depend on the slot: issue them first */
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        const int cc = c0 + 4 * c;
+        if (cc < D) {
+          const size_t od = (size_t)n * ldd + j * D + cc, oa = (size_t)n * lda + j * D + cc;
+          float dv[4] = {0.f, 0.f, 0.f, 0.f}, av[4] = {0.f, 0.f, 0.f, 0.f};
+          if (ALIGNED) {
+            const float4 d4 = ld_f4(delta + od);
+            const float4 a4 = act ? ld_f4(act + oa) : make_float4(1.f, 1.f, 1.f, 1.f);   /* act == null: the mask was applied by the sender */
+            dv[0] = d4.x; dv[1] = d4.y; dv[2] = d4.z; dv[3] = d4.w;
+            av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if (cc + i < D) { dv[i] = delta[od + i]; av[i] = act ? act[oa + i] : 1.f; }
+          }
+          /* Relu.backward: dy *= (y > 0 ? 1 : 0)  (activations/Relu.java:14-19) */
+          gk[c].x = __fmul_rn(dv[0], av[0] > 0.f ? 1.f : 0.f); gk[c].y = __fmul_rn(dv[1], av[1] > 0.f ? 1.f : 0.f);
+          gk[c].z = __fmul_rn(dv[2], av[2] > 0.f ? 1.f : 0.f); gk[c].w = __fmul_rn(dv[3], av[3] > 0.f ? 1.f : 0.f);
+        }
+      }
+      slot = lk_slot[(long)n * F + j];
+      valid = slot >= 0;
     }
-    gk = sum;
-  }
-  if (lane_on && leader) red_add_f4(acc + (size_t)uidx * Dp + part * 4, gk);
-  /* release: every lane's reduction happens-before lane 0's fence (warp barrier), which
-   * happens-before the ticket increments issued after the second barrier — one MEMBAR per warp
-   * instead of one per thread.  The reader side needs no fence: its loads are control-dependent
-   * on the ticket value and go straight to L2 (ld.cg), where the reductions were performed.   */
-  __syncwarp();
-  if (lane == 0) __threadfence();
-  __syncwarp();
-  uint32_t ticket = 0;
-  if (valid && leader && part == 0) ticket = atomicAdd(&arrived[uidx], (uint32_t)ngroups);
-  ticket = __shfl_sync(0xffffffffu, ticket, my_group * TPL);
-  const bool last = valid && leader && (ticket + (uint32_t)ngroups == n_arrivals);
-  if (!last) return;
-  bool do_upd = true;
-  if (upd.kind == PS_UPD_FTRL) {                /* FtrlUpdater.java:52: `if (dw.get(0) == 0) return w` */
-    const float S0 = __ldcg(acc + (size_t)uidx * Dp);
-    do_upd = emb_geff(S0, n_occ, calls) != 0.0f;
-  }
-  if (lane_on) {
-    float* ap = acc + (size_t)uidx * Dp + part * 4;
-    const float4 S = __ldcg(reinterpret_cast<const float4*>(ap));
-    if (do_upd) {
-      const size_t o = (size_t)slot * Dp + part * 4;
-      float4 wv = ld_f4(w + o), m1 = make_float4(0.f, 0.f, 0.f, 0.f), m2 = m1;
-      if (upd.kind != PS_UPD_SIMPLE) { m1 = ld_f4(s1 + o); m2 = ld_f4(s2 + o); }
-      apply_elem(upd, wv.x, m1.x, m2.x, emb_geff(S.x, n_occ, calls));
-      apply_elem(upd, wv.y, m1.y, m2.y, emb_geff(S.y, n_occ, calls));
-      apply_elem(upd, wv.z, m1.z, m2.z, emb_geff(S.z, n_occ, calls));
-      apply_elem(upd, wv.w, m1.w, m2.w, emb_geff(S.w, n_occ, calls));
-      st_f4(w + o, wv);
-      if (upd.kind != PS_UPD_SIMPLE) { st_f4(s1 + o, m1); st_f4(s2 + o, m2); }
+    uint32_t cnt = 0u, uidx = 0u;
+    if (valid) {
+      const uint4 m = *reinterpret_cast<const uint4*>(&slots[slot]);
+      cnt = m.z; uidx = m.w;
     }
-    st_f4(ap, make_float4(0.f, 0.f, 0.f, 0.f));
+    if (wb == warp_first) { slot_r = slot; cnt_r = cnt; uidx_r = uidx; }
+    /* ---- reduce-by-key inside the warp: rank r of a key's lanes adds rank r+s, s = 1, 2, 4, ... ---- */
+    const unsigned pmask = __match_any_sync(0xffffffffu, valid ? slot : (-1 - lane)) & part_lanes;
+    const int npeer = __popc(pmask);
+    const int rank = __popc(pmask & ((1u << lane) - 1u));
+    const int maxn = __reduce_max_sync(0xffffffffu, npeer);
+    for (int s = 1; s < maxn; s <<= 1) {
+      const bool has = rank + s < npeer;
+      const int partner = has ? (int)__fns(pmask, (unsigned)lane, s + 1) : lane;
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        const float4 o = shfl_f4(gk[c], partner);
+        if (has) { gk[c].x += o.x; gk[c].y += o.y; gk[c].z += o.z; gk[c].w += o.w; }
+      }
+    }
+    if (valid && rank == 0) {
+#pragma unroll
+      for (int c = 0; c < CPL; ++c)
+        if (c0 + 4 * c < D) red_add_f4(acc + (size_t)uidx * Dp + c0 + 4 * c, gk[c]);
+    }
   }
-  if (part == 0) { arrived[uidx] = 0u; slots[slot].cnt = 0u; }
+  grid_barrier(bar, gridDim.x, counters + 1);
+  /* ---------------- phase 2: the key's first lookup applies the update ---------------- */
+  for (long wb = warp_first; wb < L; wb += stride) {
+    const long lk = wb + my_group;
+    int slot = -1; uint32_t cnt = 0u, uidx = 0u;
+    if (wb == warp_first) { slot = slot_r; cnt = cnt_r; uidx = uidx_r; }
+    else if (lk < L) {
+      const int j = (int)(lk / N), n = (int)(lk - (long)j * N);
+      slot = lk_slot[(long)n * F + j];
+      if (slot >= 0) { const uint4 m = *reinterpret_cast<const uint4*>(&slots[slot]); cnt = m.z; uidx = m.w; }
+    }
+    const bool owner = slot >= 0 && lk < L && uidx == (uint32_t)lk;
+    /* peer-memory exchange: senders pre-reduce, cnt packs {entries << 24 | occurrences} */
+    const uint32_t n_occ = p2p != nullptr ? (cnt & 0xFFFFFFu) : cnt;
+    float4 S[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const int cc = c0 + 4 * c;
+      S[c] = (owner && cc < D) ? __ldcg(reinterpret_cast<const float4*>(acc + (size_t)uidx * Dp + cc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    bool do_upd = true;
+    if (upd.kind == PS_UPD_FTRL) {                /* FtrlUpdater.java:52: `if (dw.get(0) == 0) return w` */
+      const float S0 = __shfl_sync(0xffffffffu, S[0].x, my_group * TPL);
+      do_upd = emb_geff(S0, n_occ, calls) != 0.0f;
+    }
+    if (!owner) continue;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const int cc = c0 + 4 * c;
+      if (cc >= D) continue;
+      if (do_upd) {
+        const size_t o = (size_t)slot * Dp + cc;
+        float4 wv = ld_f4(w + o), m1 = make_float4(0.f, 0.f, 0.f, 0.f), m2 = m1;
+        if (upd.kind != PS_UPD_SIMPLE) { m1 = ld_f4(s1 + o); m2 = ld_f4(s2 + o); }
+        apply_elem(upd, wv.x, m1.x, m2.x, emb_geff(S[c].x, n_occ, calls));
+        apply_elem(upd, wv.y, m1.y, m2.y, emb_geff(S[c].y, n_occ, calls));
+        apply_elem(upd, wv.z, m1.z, m2.z, emb_geff(S[c].z, n_occ, calls));
+        apply_elem(upd, wv.w, m1.w, m2.w, emb_geff(S[c].w, n_occ, calls));
+        st_f4(w + o, wv);
+        if (upd.kind != PS_UPD_SIMPLE) { st_f4(s1 + o, m1); st_f4(s2 + o, m2); }
+      }
+      st_f4(acc + (size_t)uidx * Dp + cc, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+    if (part == 0) slots[slot].cnt = 0u;
+  }
 }
 
 __global__ void emb_clear_batch_kernel(EmbSlot* __restrict__ slots, const int32_t* __restrict__ lk_slot, int L) {
@@ -339,24 +402,22 @@ void EmbTable::create(Ctx* c, int F_, int D_, int64_t capacity, const ps_updater
   s1 = dmalloc_zero<float>((size_t)C * Dp, ctx->stream);
   s2 = dmalloc_zero<float>((size_t)C * Dp, ctx->stream);
   counters = dmalloc_zero<uint32_t>(4, ctx->stream);
+  bar = dmalloc_zero<uint32_t>(4, ctx->stream);
   reserve(max_lookups > 0 ? max_lookups : 1);
 }
 
 void EmbTable::reserve(int64_t L) {
   if (L <= Lcap) return;
   PS_CUDA(cudaStreamSynchronize(ctx->stream));
-  dfree(lk_slot); dfree(acc); dfree(arrived);
+  dfree(lk_slot); dfree(acc);
   Lcap = L;
-  ucap = 1024;
-  while ((int64_t)ucap < L) ucap <<= 1;        /* ring of accumulator rows: a power of two >= the most unique keys one batch can have */
   lk_slot = dmalloc<int32_t>((size_t)L);
-  acc = dmalloc_zero<float>((size_t)ucap * Dp, ctx->stream);
-  arrived = dmalloc_zero<uint32_t>((size_t)ucap, ctx->stream);
+  acc = dmalloc_zero<float>((size_t)L * Dp, ctx->stream);   /* one accumulator row per lookup index; a batch uses those of its keys' first lookups */
 }
 
 void EmbTable::destroy() {
   dfree(slots); dfree(w); dfree(s1); dfree(s2); dfree(counters);
-  dfree(lk_slot); dfree(acc); dfree(arrived);
+  dfree(lk_slot); dfree(acc); dfree(bar);
   slots = nullptr; w = s1 = s2 = nullptr;
 }
 
@@ -366,9 +427,9 @@ void EmbTable::probe(const int64_t* ids_i64, const float* ids_f32, int N) {
   last_L = L;
   const int grid = ceil_div(L, 256);
   if (ids_i64)
-    emb_probe_kernel<int64_t><<<grid, 256, 0, ctx->stream>>>(slots, (uint32_t)C, w, Dp, D, ids_i64, (int)L, F, ctx->seed, maxv, lk_slot, ucap - 1, counters, nullptr);
+    emb_probe_kernel<int64_t><<<grid, 256, 0, ctx->stream>>>(slots, (uint32_t)C, w, Dp, D, ids_i64, (int)L, F, ctx->seed, maxv, lk_slot, counters, nullptr);
   else
-    emb_probe_kernel<float><<<grid, 256, 0, ctx->stream>>>(slots, (uint32_t)C, w, Dp, D, ids_f32, (int)L, F, ctx->seed, maxv, lk_slot, ucap - 1, counters, nullptr);
+    emb_probe_kernel<float><<<grid, 256, 0, ctx->stream>>>(slots, (uint32_t)C, w, Dp, D, ids_f32, (int)L, F, ctx->seed, maxv, lk_slot, counters, nullptr);
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }
@@ -378,7 +439,7 @@ void EmbTable::probe_packed(const uint64_t* keys, int n, const P2PState* p2p) {
   last_L = n;
   if (n <= 0) return;
   emb_probe_kernel<unsigned long long><<<ceil_div(n, 256), 256, 0, ctx->stream>>>(slots, (uint32_t)C, w, Dp, D, reinterpret_cast<const unsigned long long*>(keys), n, 0,
-                                                                                  ctx->seed, maxv, lk_slot, ucap - 1, counters, p2p);
+                                                                                  ctx->seed, maxv, lk_slot, counters, p2p);
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }
@@ -407,16 +468,32 @@ void EmbTable::gather(float* out, int ldo, int N, int F_eff, const float* X, int
   ctx->launches++;
 }
 
-template <int TPL>
+/* the scatter kernel synchronises its whole grid once: the grid never exceeds what is resident at one time */
+template <int TPL, int CPL, bool ALIGNED>
+static int scatter_max_blocks(int num_sms) {
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    PS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, emb_scatter_update_kernel<TPL, CPL, ALIGNED>, 256, 0));
+    PS_REQUIRE(per_sm > 0, PS_ERR_CUDA, "embedding: scatter kernel does not fit an SM");
+  }
+  return per_sm * num_sms;
+}
+
+template <int TPL, int CPL>
 static void launch_scatter(EmbTable& t, const float* delta, int ldd, const float* act, int lda, int N, int F, int calls, const int* skip,
                            const P2PState* p2p) {
   const long L = (long)N * F;
   const bool aligned = (t.D % 4 == 0) && (ldd % 4 == 0) && (lda % 4 == 0) && ((uintptr_t)delta % 16 == 0) && ((uintptr_t)act % 16 == 0);
-  const int grid = ceil_div(L * TPL, 256);
-  if (aligned)
-    emb_scatter_update_kernel<TPL, true><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.w, t.s1, t.s2, t.Dp, t.D, t.lk_slot, N, F, delta, ldd, act, lda, t.acc, t.arrived, t.upd, calls, skip, p2p);
-  else
-    emb_scatter_update_kernel<TPL, false><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.w, t.s1, t.s2, t.Dp, t.D, t.lk_slot, N, F, delta, ldd, act, lda, t.acc, t.arrived, t.upd, calls, skip, p2p);
+  const long want = ceil_div(L * TPL, 256);
+  if (aligned) {
+    const int grid = (int)std::min<long>(want, scatter_max_blocks<TPL, CPL, true>(t.ctx->num_sms));
+    emb_scatter_update_kernel<TPL, CPL, true><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.w, t.s1, t.s2, t.Dp, t.D, t.lk_slot, N, F, delta, ldd, act, lda, t.acc,
+                                                                               t.bar, t.counters, t.upd, calls, skip, p2p);
+  } else {
+    const int grid = (int)std::min<long>(want, scatter_max_blocks<TPL, CPL, false>(t.ctx->num_sms));
+    emb_scatter_update_kernel<TPL, CPL, false><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.w, t.s1, t.s2, t.Dp, t.D, t.lk_slot, N, F, delta, ldd, act, lda, t.acc,
+                                                                                t.bar, t.counters, t.upd, calls, skip, p2p);
+  }
 }
 
 void EmbTable::scatter_update(const float* delta, int ldd, const float* act, int lda, int N, int calls, const int* skip_flag, int F_eff,
@@ -424,13 +501,23 @@ void EmbTable::scatter_update(const float* delta, int ldd, const float* act, int
   const int Fe = F_eff > 0 ? F_eff : F;
   PS_REQUIRE((int64_t)N * Fe == last_L, PS_ERR_STATE, "embedding: backward without a matching forward");
   PS_REQUIRE(calls == 1 || calls == 2, PS_ERR_ARG, "embedding: backward calls must be 1 or 2");
-  switch (tpl) {
-    case 1: launch_scatter<1>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
-    case 2: launch_scatter<2>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
-    case 4: launch_scatter<4>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
-    case 8: launch_scatter<8>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
-    case 16: launch_scatter<16>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
-    default: launch_scatter<32>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
+  if (Dp % 8 == 0) {                            /* two 16 B chunks per lane: half the threads, the whole grid resident at cfg2 */
+    switch (pow2_ge(Dp / 8)) {
+      case 1: launch_scatter<1, 2>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
+      case 2: launch_scatter<2, 2>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
+      case 4: launch_scatter<4, 2>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
+      case 8: launch_scatter<8, 2>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
+      default: launch_scatter<16, 2>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
+    }
+  } else {
+    switch (tpl) {
+      case 1: launch_scatter<1, 1>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
+      case 2: launch_scatter<2, 1>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
+      case 4: launch_scatter<4, 1>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
+      case 8: launch_scatter<8, 1>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
+      case 16: launch_scatter<16, 1>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
+      default: launch_scatter<32, 1>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
+    }
   }
   PS_LAUNCH_CHECK();
   ctx->launches++;
@@ -449,6 +536,7 @@ void EmbTable::check_errors() {
   uint32_t h[4];
   PS_CUDA(cudaMemcpyAsync(h, counters, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
   PS_CUDA(cudaStreamSynchronize(ctx->stream));
+  PS_REQUIRE(h[1] != 2, PS_ERR_CUDA, "embedding: grid barrier of the scatter kernel timed out");
   PS_REQUIRE(h[1] == 0, PS_ERR_CAPACITY, "embedding table is full: raise capacity");
 }
 

@@ -10,10 +10,10 @@
  *   w[C][Dp], s1[C][Dp], s2[C][Dp]   row = slot index; SoA across {weight, Adam M | Ftrl Z,
  *              Adam V | Ftrl N} so the forward gather touches only w.  Dp = D rounded to 4
  *              floats: every row is 16 B aligned for 128-bit loads
- *   per-batch workspace (L = N*F lookups): lk_slot[L]; a ring of acc[ucap][Dp] gradient
- *              accumulators and arrived[ucap] tickets indexed by a monotonic unique-key counter
- *              (no per-step reset) — a few MB that stay L2-resident, so the scatter-add never
- *              round-trips HBM
+ *   per-batch workspace (L = N*F lookups): lk_slot[L]; acc[L][Dp] gradient accumulators — a
+ *              key uses the row of its FIRST lookup in the batch (emb_probe leaves that index in
+ *              the slot record), the consumer zeroes it again: nothing to number or reset, and
+ *              the few MB a batch touches stay L2-resident, so the scatter-add never round-trips HBM
  *
  * WideTable: layer/LRLayer.java's 1x1 weights "wide.weights.<id>": 32 B records
  * {key, w, s1, s2} — one sector holds everything a probe, the forward sum and the update need.
@@ -50,9 +50,8 @@ struct EmbTable {
   /* per-batch workspace */
   int64_t Lcap = 0;
   int32_t* lk_slot = nullptr;
-  uint32_t ucap = 0;                   /* accumulator ring size (power of two) */
   float* acc = nullptr;
-  uint32_t* arrived = nullptr;
+  uint32_t* bar = nullptr;             /* grid barrier of the scatter kernel: {arrivals, generation} */
   uint32_t* counters = nullptr;        /* [0] monotonic unique-key counter, [1] error flag, [2..3] u64 row count */
   int64_t last_L = 0;
 
