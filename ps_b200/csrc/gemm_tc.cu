@@ -35,7 +35,7 @@ namespace {
 
 constexpr int BM = 128, BK = 32, UMMA_K = 8;
 /* pipeline depth: 8 stages cover a whole K = 256 operand in ONE L2 round trip; the 3xTF32 stages are twice as large */
-template <bool SPLIT> struct Depth { static constexpr int STAGES = SPLIT ? 4 : 8; };
+template <int BLOCK_N, bool SPLIT> struct Depth { static constexpr int STAGES = SPLIT ? (BLOCK_N > 64 ? 3 : 4) : (BLOCK_N > 64 ? 6 : 8); };
 enum { EPI_FWD = 0, EPI_DGRAD = 1, EPI_WGRAD = 2 };
 
 struct TcParams {
@@ -113,7 +113,7 @@ template <int BLOCK_N, bool SPLIT>
 struct SmemLayout {
   static constexpr uint32_t A_BYTES = BM * BK * 4;
   static constexpr uint32_t B_BYTES = BLOCK_N * BK * 4;
-  static constexpr int STAGES = Depth<SPLIT>::STAGES;
+  static constexpr int STAGES = Depth<BLOCK_N, SPLIT>::STAGES;
   static constexpr uint32_t STAGE_BYTES = (SPLIT ? 2u : 1u) * (A_BYTES + B_BYTES);
   static constexpr uint32_t BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr uint32_t TOTAL = BAR_OFF + 256 + 1024;   /* + barriers/tmem slot + manual 1024 B alignment slack */
@@ -228,17 +228,26 @@ __global__ void __launch_bounds__(SPLIT ? 256 : 128) gemm_tf32_kernel(const __gr
    * activation of the layer below for its derivative: read from the TRANSPOSED copy, so the 32
    * lanes = 32 consecutive rows read one 128 B line per column) are fetched while they fly.   */
   if (warp < 4) {   /* the four TMEM lane quadrants; with SPLIT warps 4-7 only produced residual tiles */
-  constexpr int NCH = BLOCK_N / 16;
+  /* the tile is drained in passes of at most 64 columns (register budget: 64 accumulators + 64 epilogue operands) */
+  constexpr int PN = BLOCK_N > 64 ? 64 : BLOCK_N;
+  constexpr int NPASS = BLOCK_N / PN;
+  constexpr int NCH = PN / 16;
   const int m = m0 + warp * 32 + lane;
   const bool row_ok = m < p.M;
   float* Cz = p.C + (size_t)blockIdx.z * p.slab;
   const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0);
-  uint32_t r[NCH][16];
   if (num_kb > 0) {
     mbar_wait(tfull, 0);
     tc_fence_after();
+  }
+#pragma unroll 1
+  for (int pass = 0; pass < NPASS; ++pass) {
+  const int np0 = n0 + pass * PN;
+  if (np0 >= p.N) break;                         /* warp-uniform */
+  uint32_t r[NCH][16];
+  if (num_kb > 0) {
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) tc_ld16_issue(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ch * 16), r[ch]);
+    for (int ch = 0; ch < NCH; ++ch) tc_ld16_issue(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(pass * PN + ch * 16), r[ch]);
   } else {
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch)
@@ -250,19 +259,19 @@ __global__ void __launch_bounds__(SPLIT ? 256 : 128) gemm_tf32_kernel(const __gr
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { const int n = n0 + ch * 16 + i; e[ch][i] = n < p.N ? __ldg(p.bias + n) : 0.f; }
+      for (int i = 0; i < 16; ++i) { const int n = np0 + ch * 16 + i; e[ch][i] = n < p.N ? __ldg(p.bias + n) : 0.f; }
   } else if (EPI == EPI_DGRAD) {
     if (p.act != PS_ACT_NONE) {
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { const int n = n0 + ch * 16 + i; e[ch][i] = (row_ok && n < p.N) ? __ldg(p.Yt + (long)n * p.ldyt + m) : 0.f; }
+        for (int i = 0; i < 16; ++i) { const int n = np0 + ch * 16 + i; e[ch][i] = (row_ok && n < p.N) ? __ldg(p.Yt + (long)n * p.ldyt + m) : 0.f; }
     }
   }
   if (num_kb > 0) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) {
-    const int nb = n0 + ch * 16;
+    const int nb = np0 + ch * 16;
     if (nb >= p.N) continue;                   /* warp-uniform */
     float v[16];
 #pragma unroll
@@ -290,6 +299,7 @@ __global__ void __launch_bounds__(SPLIT ? 256 : 128) gemm_tf32_kernel(const __gr
         for (int i = 0; i < 16; ++i) if (nb + i < p.N) p.Ct[(long)(nb + i) * p.ldct + m] = v[i];
       }
     }
+  }
   }
   }
   tc_fence_before();
@@ -354,6 +364,14 @@ void launch_tc(Ctx* ctx, const float* A, long lda, const float* B, long ldb, TcP
 
 template <int EPI>
 void dispatch_tc(Ctx* ctx, const float* A, long lda, const float* B, long ldb, TcParams& p, int nsplit) {
+  /* 128-wide tiles when 64-wide ones would not fit one wave (1 CTA per SM): fc0's dgrad at cfg2 is 7 x 32 = 224 CTAs
+   * at 64 columns, 4 x 32 = 128 at 128 — and every A tile is read (and split) half as often */
+  const bool wide = p.N >= 128 && (long)ceil_div(p.N, 64) * ceil_div(p.M, BM) * nsplit > ctx->num_sms;
+  if (wide) {
+    if (ctx->fc_precision == PS_FC_TF32X3) launch_tc<128, EPI, true>(ctx, A, lda, B, ldb, p, nsplit);
+    else launch_tc<128, EPI, false>(ctx, A, lda, B, ldb, p, nsplit);
+    return;
+  }
   if (ctx->fc_precision == PS_FC_TF32X3) {
     if (p.N <= 16) launch_tc<16, EPI, true>(ctx, A, lda, B, ldb, p, nsplit);
     else if (p.N <= 32) launch_tc<32, EPI, true>(ctx, A, lda, B, ldb, p, nsplit);
@@ -378,8 +396,8 @@ void set_attr() {
 void fc_tf32_init() {
   static bool done = false;
   if (done) return;
-  set_attr<16, false>(); set_attr<32, false>(); set_attr<64, false>();
-  set_attr<16, true>(); set_attr<32, true>(); set_attr<64, true>();
+  set_attr<16, false>(); set_attr<32, false>(); set_attr<64, false>(); set_attr<128, false>();
+  set_attr<16, true>(); set_attr<32, true>(); set_attr<64, true>(); set_attr<128, true>();
   encode_fn();
   done = true;
 }

@@ -166,167 +166,122 @@ __device__ __forceinline__ float emb_geff(float S, uint32_t n, int calls) {
   return __fdiv_rn(__fadd_rn(q, S), (float)(2u * n));
 }
 
-/* Grid-wide barrier for a kernel whose WHOLE grid is resident (launch_scatter sizes the grid with the occupancy
- * API): bar[0] counts arrivals, bar[1] is the generation the waiters watch.  Everything a block did before the
- * barrier (its L2 reductions included) is visible to every block after it.  A bounded spin turns a scheduling
- * accident into an error flag instead of a hung GPU.                                                          */
-__device__ __forceinline__ void grid_barrier(uint32_t* bar, uint32_t nblocks, uint32_t* err) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t gen, cur;
-    asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");
-    __threadfence();
-    if (atomicAdd(bar, 1u) == nblocks - 1u) {
-      bar[0] = 0u;
-      __threadfence();
-      asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(bar + 1), "r"(gen + 1u) : "memory");
-    } else {
-      unsigned long long t0 = 0, t1;
-      uint32_t spins = 0;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-      do {
-        asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(cur) : "l"(bar + 1) : "memory");
-        if (cur == gen && (++spins & 1023u) == 0u) {
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-          if (t1 - t0 > 2000000000ull) { *err = 2u; break; }
-        }
-      } while (cur == gen);
-    }
-    __threadfence();
-  }
-  __syncthreads();
-}
-
-/* Fused sparse backward, ONE launch, two phases separated by a grid barrier:
- *   phase 1  g_k = delta[:,k] * (A[:,k] > 0)  (EmbeddingField.java:91-93); lanes of a warp work on the SAME field
- *            for consecutive samples, so duplicates of a hot key are first summed inside the warp (a reduce-by-key
- *            tree over the lanes __match_any_sync groups) and the warp issues ONE red.global.add.v4.f32 per key and
- *            16 B chunk into the key's accumulator row (L2-resident, indexed by the work index of the key's first
- *            lookup, which emb_probe left in the slot record)
- *   phase 2  the lookup that owns the accumulator row reads S back from L2, forms g_eff, runs the Adam / Ftrl /
- *            SGD step on w, s1, s2 in place and resets the per-batch state (acc, cnt) — KVStore.sum + update +
- *            clear (KVStore.java:192-200,240-277).
- * TPL lanes cooperate on one lookup, each owning CPL 16 B chunks of the row.                                   */
+/* Sparse backward = two launches on one stream:
+ *   emb_scatter_kernel  g_k = delta[:,k] * (A[:,k] > 0)  (EmbeddingField.java:91-93); lanes of a warp work on the SAME
+ *            field for consecutive samples, so duplicates of a hot key are first summed inside the warp (a
+ *            reduce-by-key tree over the lanes __match_any_sync groups) and the warp issues ONE
+ *            red.global.add.v4.f32 per key and 16 B chunk into the key's accumulator row (L2-resident, indexed by
+ *            the work index of the key's first lookup, which emb_probe left in the slot record)
+ *   emb_update_kernel   the lookup that owns the accumulator row reads S back from L2, forms g_eff, runs the Adam /
+ *            Ftrl / SGD step on w, s1, s2 in place and resets the per-batch state (acc, cnt) — KVStore.sum +
+ *            update + clear (KVStore.java:192-200,240-277).
+ * TPL lanes cooperate on one lookup, each owning CPL 16 B chunks of the row.  Work index lk = j*N + n (field-major),
+ * the same index emb_probe used.                                                                               */
 template <int TPL, int CPL, bool ALIGNED>
-__global__ void __launch_bounds__(256, CPL == 2 ? 5 : 6)
-emb_scatter_update_kernel(EmbSlot* __restrict__ slots, float* __restrict__ w, float* __restrict__ s1, float* __restrict__ s2, int Dp, int D,
-                          const int32_t* __restrict__ lk_slot, int N, int F, const float* __restrict__ delta, int ldd,
-                          const float* __restrict__ act, int lda, float* __restrict__ acc, uint32_t* __restrict__ bar,
-                          uint32_t* __restrict__ counters, UpdaterDev upd, int calls, const int* __restrict__ skip_flag,
-                          const P2PState* __restrict__ p2p) {
+__global__ void __launch_bounds__(256) emb_scatter_kernel(const EmbSlot* __restrict__ slots, int Dp, int D, const int32_t* __restrict__ lk_slot, int N,
+                                                          int F, const float* __restrict__ delta, int ldd, const float* __restrict__ act, int lda,
+                                                          float* __restrict__ acc, const int* __restrict__ skip_flag,
+                                                          const P2PState* __restrict__ p2p) {
   constexpr int GPW = 32 / TPL;                  /* lookups (lane groups) per warp */
+  if (skip_flag != nullptr && *skip_flag != 0) return;   /* DNN.java:58-63 early exit: nothing is pushed */
   if (p2p != nullptr) delta = reinterpret_cast<const float*>(p2p_region(p2p, p2p->me, p2p->off_grads));   /* this step's grads_in mailbox */
-  const bool skip = skip_flag != nullptr && *skip_flag != 0;
   const long L = (long)N * F;
   const int lane = threadIdx.x & 31;
   const int part = lane % TPL, my_group = lane / TPL;
   const int c0 = part * CPL * 4;                 /* first float of this lane's chunks */
-  const long stride = (long)gridDim.x * (256 / TPL);
-  const long warp_first = ((long)blockIdx.x * 256 + (threadIdx.x & ~31)) / TPL;
-  if (skip) {                                    /* DNN.java:58-63 early exit: nothing was pushed, just forget the batch */
-    for (long wb = warp_first; wb < L; wb += stride) {
-      const long lk = wb + my_group;
-      if (lk < L && part == 0) {
-        const int j = (int)(lk / N), n = (int)(lk - (long)j * N);
-        const int slot = lk_slot[(long)n * F + j];
-        if (slot >= 0) slots[slot].cnt = 0u;
-      }
-    }
-    return;
-  }
+  const long lk = ((long)blockIdx.x * 256 + (threadIdx.x & ~31)) / TPL + my_group;
   /* lanes holding the same `part` of their lookups: bits at multiples of TPL, shifted by part */
   unsigned part_lanes = 0u;
 #pragma unroll
   for (int g = 0; g < GPW; ++g) part_lanes |= 1u << (g * TPL);
   part_lanes <<= part;
 
-  int slot_r = -1; uint32_t cnt_r = 0u, uidx_r = 0u;     /* the first iteration's lookup stays in registers across the barrier */
-  /* ---------------- phase 1: masked gradients → warp reduce-by-key → L2 reductions ---------------- */
-  for (long wb = warp_first; wb < L; wb += stride) {
-    const long lk = wb + my_group;
-    bool valid = lk < L;
-    int slot = -1, n = 0, j = 0;
-    if (valid) { j = (int)(lk / N); n = (int)(lk - (long)j * N); }
-    float4 gk[CPL];
+  bool valid = lk < L;
+  int slot = -1, n = 0, j = 0;
+  if (valid) { j = (int)(lk / N); n = (int)(lk - (long)j * N); }
+  float4 gk[CPL];
 #pragma unroll
-    for (int c = 0; c < CPL; ++c) gk[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) {
-      /* the gradient / activation loads do not depend on the slot: issue them first */
-#pragma unroll
-      for (int c = 0; c < CPL; ++c) {
-        const int cc = c0 + 4 * c;
-        if (cc < D) {
-          const size_t od = (size_t)n * ldd + j * D + cc, oa = (size_t)n * lda + j * D + cc;
-          float dv[4] = {0.f, 0.f, 0.f, 0.f}, av[4] = {0.f, 0.f, 0.f, 0.f};
-          if (ALIGNED) {
-            const float4 d4 = ld_f4(delta + od);
-            const float4 a4 = act ? ld_f4(act + oa) : make_float4(1.f, 1.f, 1.f, 1.f);   /* act == null: the mask was applied by the sender */
-            dv[0] = d4.x; dv[1] = d4.y; dv[2] = d4.z; dv[3] = d4.w;
-            av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
-          } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) if (cc + i < D) { dv[i] = delta[od + i]; av[i] = act ? act[oa + i] : 1.f; }
-          }
-          /* Relu.backward: dy *= (y > 0 ? 1 : 0)  (activations/Relu.java:14-19) */
-          gk[c].x = __fmul_rn(dv[0], av[0] > 0.f ? 1.f : 0.f); gk[c].y = __fmul_rn(dv[1], av[1] > 0.f ? 1.f : 0.f);
-          gk[c].z = __fmul_rn(dv[2], av[2] > 0.f ? 1.f : 0.f); gk[c].w = __fmul_rn(dv[3], av[3] > 0.f ? 1.f : 0.f);
-        }
-      }
-      slot = lk_slot[(long)n * F + j];
-      valid = slot >= 0;
-    }
-    uint32_t cnt = 0u, uidx = 0u;
-    if (valid) {
-      const uint4 m = *reinterpret_cast<const uint4*>(&slots[slot]);
-      cnt = m.z; uidx = m.w;
-    }
-    if (wb == warp_first) { slot_r = slot; cnt_r = cnt; uidx_r = uidx; }
-    /* ---- reduce-by-key inside the warp: rank r of a key's lanes adds rank r+s, s = 1, 2, 4, ... ---- */
-    const unsigned pmask = __match_any_sync(0xffffffffu, valid ? slot : (-1 - lane)) & part_lanes;
-    const int npeer = __popc(pmask);
-    const int rank = __popc(pmask & ((1u << lane) - 1u));
-    const int maxn = __reduce_max_sync(0xffffffffu, npeer);
-    for (int s = 1; s < maxn; s <<= 1) {
-      const bool has = rank + s < npeer;
-      const int partner = has ? (int)__fns(pmask, (unsigned)lane, s + 1) : lane;
-#pragma unroll
-      for (int c = 0; c < CPL; ++c) {
-        const float4 o = shfl_f4(gk[c], partner);
-        if (has) { gk[c].x += o.x; gk[c].y += o.y; gk[c].z += o.z; gk[c].w += o.w; }
-      }
-    }
-    if (valid && rank == 0) {
-#pragma unroll
-      for (int c = 0; c < CPL; ++c)
-        if (c0 + 4 * c < D) red_add_f4(acc + (size_t)uidx * Dp + c0 + 4 * c, gk[c]);
-    }
-  }
-  grid_barrier(bar, gridDim.x, counters + 1);
-  /* ---------------- phase 2: the key's first lookup applies the update ---------------- */
-  for (long wb = warp_first; wb < L; wb += stride) {
-    const long lk = wb + my_group;
-    int slot = -1; uint32_t cnt = 0u, uidx = 0u;
-    if (wb == warp_first) { slot = slot_r; cnt = cnt_r; uidx = uidx_r; }
-    else if (lk < L) {
-      const int j = (int)(lk / N), n = (int)(lk - (long)j * N);
-      slot = lk_slot[(long)n * F + j];
-      if (slot >= 0) { const uint4 m = *reinterpret_cast<const uint4*>(&slots[slot]); cnt = m.z; uidx = m.w; }
-    }
-    const bool owner = slot >= 0 && lk < L && uidx == (uint32_t)lk;
-    /* peer-memory exchange: senders pre-reduce, cnt packs {entries << 24 | occurrences} */
-    const uint32_t n_occ = p2p != nullptr ? (cnt & 0xFFFFFFu) : cnt;
-    float4 S[CPL];
+  for (int c = 0; c < CPL; ++c) gk[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid) {
+    slot = lk_slot[(long)n * F + j];
+    /* the gradient / activation loads do not depend on the slot: they fly together with the slot lookup */
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
       const int cc = c0 + 4 * c;
-      S[c] = (owner && cc < D) ? __ldcg(reinterpret_cast<const float4*>(acc + (size_t)uidx * Dp + cc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (cc < D) {
+        const size_t od = (size_t)n * ldd + j * D + cc, oa = (size_t)n * lda + j * D + cc;
+        float dv[4] = {0.f, 0.f, 0.f, 0.f}, av[4] = {0.f, 0.f, 0.f, 0.f};
+        if (ALIGNED) {
+          const float4 d4 = ld_f4(delta + od);
+          const float4 a4 = act ? ld_f4(act + oa) : make_float4(1.f, 1.f, 1.f, 1.f);   /* act == null: the mask was applied by the sender */
+          dv[0] = d4.x; dv[1] = d4.y; dv[2] = d4.z; dv[3] = d4.w;
+          av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) if (cc + i < D) { dv[i] = delta[od + i]; av[i] = act ? act[oa + i] : 1.f; }
+        }
+        /* Relu.backward: dy *= (y > 0 ? 1 : 0)  (activations/Relu.java:14-19) */
+        gk[c].x = __fmul_rn(dv[0], av[0] > 0.f ? 1.f : 0.f); gk[c].y = __fmul_rn(dv[1], av[1] > 0.f ? 1.f : 0.f);
+        gk[c].z = __fmul_rn(dv[2], av[2] > 0.f ? 1.f : 0.f); gk[c].w = __fmul_rn(dv[3], av[3] > 0.f ? 1.f : 0.f);
+      }
     }
-    bool do_upd = true;
-    if (upd.kind == PS_UPD_FTRL) {                /* FtrlUpdater.java:52: `if (dw.get(0) == 0) return w` */
-      const float S0 = __shfl_sync(0xffffffffu, S[0].x, my_group * TPL);
-      do_upd = emb_geff(S0, n_occ, calls) != 0.0f;
+    valid = slot >= 0;
+  }
+  uint32_t uidx = 0u;
+  if (valid) uidx = slots[slot].uidx;
+  /* ---- reduce-by-key inside the warp: rank r of a key's lanes adds rank r+s, s = 1, 2, 4, ... ---- */
+  const unsigned pmask = __match_any_sync(0xffffffffu, valid ? slot : (-1 - lane)) & part_lanes;
+  const int npeer = __popc(pmask);
+  const int rank = __popc(pmask & ((1u << lane) - 1u));
+  const int maxn = __reduce_max_sync(0xffffffffu, npeer);
+  for (int s = 1; s < maxn; s <<= 1) {
+    const bool has = rank + s < npeer;
+    const int partner = has ? (int)__fns(pmask, (unsigned)lane, s + 1) : lane;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const float4 o = shfl_f4(gk[c], partner);
+      if (has) { gk[c].x += o.x; gk[c].y += o.y; gk[c].z += o.z; gk[c].w += o.w; }
     }
-    if (!owner) continue;
+  }
+  if (valid && rank == 0) {
+#pragma unroll
+    for (int c = 0; c < CPL; ++c)
+      if (c0 + 4 * c < D) red_add_f4(acc + (size_t)uidx * Dp + c0 + 4 * c, gk[c]);
+  }
+}
+
+template <int TPL, int CPL>
+__global__ void __launch_bounds__(256) emb_update_kernel(EmbSlot* __restrict__ slots, float* __restrict__ w, float* __restrict__ s1, float* __restrict__ s2,
+                                                         int Dp, int D, const int32_t* __restrict__ lk_slot, int N, int F, float* __restrict__ acc,
+                                                         UpdaterDev upd, int calls, const int* __restrict__ skip_flag, int packed_cnt) {
+  const long L = (long)N * F;
+  const int lane = threadIdx.x & 31;
+  const int part = lane % TPL, my_group = lane / TPL;
+  const int c0 = part * CPL * 4;
+  const long lk = ((long)blockIdx.x * 256 + (threadIdx.x & ~31)) / TPL + my_group;
+  int slot = -1; uint32_t cnt = 0u, uidx = 0u;
+  if (lk < L) {
+    const int j = (int)(lk / N), n = (int)(lk - (long)j * N);
+    slot = lk_slot[(long)n * F + j];
+    if (slot >= 0) { const uint4 m = *reinterpret_cast<const uint4*>(&slots[slot]); cnt = m.z; uidx = m.w; }
+  }
+  const bool owner = slot >= 0 && uidx == (uint32_t)lk;      /* the key's first lookup of the batch */
+  const bool skip = skip_flag != nullptr && *skip_flag != 0;
+  /* peer-memory exchange: senders pre-reduce, cnt packs {entries << 24 | occurrences} */
+  const uint32_t n_occ = packed_cnt ? (cnt & 0xFFFFFFu) : cnt;
+  float4 S[CPL];
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) {
+    const int cc = c0 + 4 * c;
+    S[c] = (owner && !skip && cc < D) ? __ldcg(reinterpret_cast<const float4*>(acc + (size_t)uidx * Dp + cc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  bool do_upd = !skip;
+  if (upd.kind == PS_UPD_FTRL) {                  /* FtrlUpdater.java:52: `if (dw.get(0) == 0) return w` */
+    const float S0 = __shfl_sync(0xffffffffu, S[0].x, my_group * TPL);
+    do_upd = do_upd && emb_geff(S0, n_occ, calls) != 0.0f;
+  }
+  if (!owner) return;
+  if (!skip) {
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
       const int cc = c0 + 4 * c;
@@ -344,8 +299,8 @@ emb_scatter_update_kernel(EmbSlot* __restrict__ slots, float* __restrict__ w, fl
       }
       st_f4(acc + (size_t)uidx * Dp + cc, make_float4(0.f, 0.f, 0.f, 0.f));
     }
-    if (part == 0) slots[slot].cnt = 0u;
   }
+  if (part == 0) slots[slot].cnt = 0u;             /* KVStore.clear (also after the early exit: the batch is forgotten) */
 }
 
 __global__ void emb_clear_batch_kernel(EmbSlot* __restrict__ slots, const int32_t* __restrict__ lk_slot, int L) {
@@ -402,7 +357,6 @@ void EmbTable::create(Ctx* c, int F_, int D_, int64_t capacity, const ps_updater
   s1 = dmalloc_zero<float>((size_t)C * Dp, ctx->stream);
   s2 = dmalloc_zero<float>((size_t)C * Dp, ctx->stream);
   counters = dmalloc_zero<uint32_t>(4, ctx->stream);
-  bar = dmalloc_zero<uint32_t>(4, ctx->stream);
   reserve(max_lookups > 0 ? max_lookups : 1);
 }
 
@@ -417,7 +371,7 @@ void EmbTable::reserve(int64_t L) {
 
 void EmbTable::destroy() {
   dfree(slots); dfree(w); dfree(s1); dfree(s2); dfree(counters);
-  dfree(lk_slot); dfree(acc); dfree(bar);
+  dfree(lk_slot); dfree(acc);
   slots = nullptr; w = s1 = s2 = nullptr;
 }
 
@@ -468,32 +422,19 @@ void EmbTable::gather(float* out, int ldo, int N, int F_eff, const float* X, int
   ctx->launches++;
 }
 
-/* the scatter kernel synchronises its whole grid once: the grid never exceeds what is resident at one time */
-template <int TPL, int CPL, bool ALIGNED>
-static int scatter_max_blocks(int num_sms) {
-  static int per_sm = 0;
-  if (per_sm == 0) {
-    PS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, emb_scatter_update_kernel<TPL, CPL, ALIGNED>, 256, 0));
-    PS_REQUIRE(per_sm > 0, PS_ERR_CUDA, "embedding: scatter kernel does not fit an SM");
-  }
-  return per_sm * num_sms;
-}
-
 template <int TPL, int CPL>
 static void launch_scatter(EmbTable& t, const float* delta, int ldd, const float* act, int lda, int N, int F, int calls, const int* skip,
                            const P2PState* p2p) {
   const long L = (long)N * F;
   const bool aligned = (t.D % 4 == 0) && (ldd % 4 == 0) && (lda % 4 == 0) && ((uintptr_t)delta % 16 == 0) && ((uintptr_t)act % 16 == 0);
-  const long want = ceil_div(L * TPL, 256);
-  if (aligned) {
-    const int grid = (int)std::min<long>(want, scatter_max_blocks<TPL, CPL, true>(t.ctx->num_sms));
-    emb_scatter_update_kernel<TPL, CPL, true><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.w, t.s1, t.s2, t.Dp, t.D, t.lk_slot, N, F, delta, ldd, act, lda, t.acc,
-                                                                               t.bar, t.counters, t.upd, calls, skip, p2p);
-  } else {
-    const int grid = (int)std::min<long>(want, scatter_max_blocks<TPL, CPL, false>(t.ctx->num_sms));
-    emb_scatter_update_kernel<TPL, CPL, false><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.w, t.s1, t.s2, t.Dp, t.D, t.lk_slot, N, F, delta, ldd, act, lda, t.acc,
-                                                                                t.bar, t.counters, t.upd, calls, skip, p2p);
-  }
+  const int grid = ceil_div(L * TPL, 256);
+  if (aligned)
+    emb_scatter_kernel<TPL, CPL, true><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.Dp, t.D, t.lk_slot, N, F, delta, ldd, act, lda, t.acc, skip, p2p);
+  else
+    emb_scatter_kernel<TPL, CPL, false><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.Dp, t.D, t.lk_slot, N, F, delta, ldd, act, lda, t.acc, skip, p2p);
+  PS_LAUNCH_CHECK();
+  emb_update_kernel<TPL, CPL><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.w, t.s1, t.s2, t.Dp, t.D, t.lk_slot, N, F, t.acc, t.upd, calls, skip, p2p != nullptr ? 1 : 0);
+  t.ctx->launches += 2;
 }
 
 void EmbTable::scatter_update(const float* delta, int ldd, const float* act, int lda, int N, int calls, const int* skip_flag, int F_eff,
@@ -501,7 +442,7 @@ void EmbTable::scatter_update(const float* delta, int ldd, const float* act, int
   const int Fe = F_eff > 0 ? F_eff : F;
   PS_REQUIRE((int64_t)N * Fe == last_L, PS_ERR_STATE, "embedding: backward without a matching forward");
   PS_REQUIRE(calls == 1 || calls == 2, PS_ERR_ARG, "embedding: backward calls must be 1 or 2");
-  if (Dp % 8 == 0) {                            /* two 16 B chunks per lane: half the threads, the whole grid resident at cfg2 */
+  if (Dp % 8 == 0) {                            /* two 16 B chunks per lane: half the threads, twice the bytes in flight per thread */
     switch (pow2_ge(Dp / 8)) {
       case 1: launch_scatter<1, 2>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
       case 2: launch_scatter<2, 2>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
@@ -520,7 +461,6 @@ void EmbTable::scatter_update(const float* delta, int ldd, const float* act, int
     }
   }
   PS_LAUNCH_CHECK();
-  ctx->launches++;
   last_L = 0;
 }
 
@@ -536,7 +476,6 @@ void EmbTable::check_errors() {
   uint32_t h[4];
   PS_CUDA(cudaMemcpyAsync(h, counters, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
   PS_CUDA(cudaStreamSynchronize(ctx->stream));
-  PS_REQUIRE(h[1] != 2, PS_ERR_CUDA, "embedding: grid barrier of the scatter kernel timed out");
   PS_REQUIRE(h[1] == 0, PS_ERR_CAPACITY, "embedding table is full: raise capacity");
 }
 

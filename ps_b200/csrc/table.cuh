@@ -51,7 +51,6 @@ struct EmbTable {
   int64_t Lcap = 0;
   int32_t* lk_slot = nullptr;
   float* acc = nullptr;
-  uint32_t* bar = nullptr;             /* grid barrier of the scatter kernel: {arrivals, generation} */
   uint32_t* counters = nullptr;        /* [0] monotonic unique-key counter, [1] error flag, [2..3] u64 row count */
   int64_t last_L = 0;
 

@@ -354,7 +354,8 @@ def test_pipelined_submit_equals_sync(ps, ctx):
 
 
 # --------------------------------------------------------------------------- TF32 tcgen05 path
-@pytest.mark.parametrize("M,N,K", [(128, 64, 32), (256, 256, 413), (4096, 256, 256), (100, 1, 256), (37, 10, 50), (300, 150, 784), (1, 8, 7)])
+@pytest.mark.parametrize("M,N,K", [(128, 64, 32), (256, 256, 413), (4096, 256, 256), (100, 1, 256), (37, 10, 50), (300, 150, 784), (1, 8, 7),
+                                   (4096, 413, 256), (8192, 200, 96)])     # the last two take the 128-column tiles (more than one wave of 64-wide ones)
 def test_tf32_gemm_matches_fp64(ps, ctx, M, N, K):
     rng = np.random.default_rng(M * 7 + N * 3 + K)
     A = rng.standard_normal((M, K)).astype(np.float32)
