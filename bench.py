@@ -185,6 +185,7 @@ def main():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
     ap.add_argument("--force-sharded", action="store_true", help="use the sharded step even with one rank (profiling)")
     ap.add_argument("--large", default="cfg4", help="shapes for the large-batch embedding roofline ('' = skip)")
+    ap.add_argument("--no-kernel-times", action="store_true", help="skip the per-kernel replays (ncu runs: only the step's own launches)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     rank = int(os.environ.get("RANK", "0"))
@@ -331,7 +332,7 @@ def main():
 
     # ---- per-kernel device times and the roofline of the dominant HBM-bound kernel ----
     acc = {}
-    reps = 20 if (world == 1 and trainer is None) else 0
+    reps = 20 if (world == 1 and trainer is None and not args.no_kernel_times) else 0
     if reps:
         model.profile(True)
     for i in range(reps):
@@ -345,7 +346,7 @@ def main():
     uniq = float(np.mean([len(np.unique(b["E"] + (np.arange(F, dtype=np.int64) << 44)[None, :])) for b in ring])) if F else 0.0
     hbm_peak, peak_src = peaks()
     kernels, roofline = {}, None
-    if F and world == 1 and trainer is None:
+    if F and world == 1 and trainer is None and not args.no_kernel_times:
         # each embedding kernel replayed 64x inside a CUDA graph over the batch ring, CUDA events on the library's stream
         kt = model.kernel_times([d["E"].data_ptr() for d in dev_ring], B, reps=64)
         alg = {"emb_gather": L * (8 + 8 * D), "emb_scatter_update": L * (8 + 4 * D) + uniq * 24 * D}
@@ -364,8 +365,9 @@ def main():
         traffic = None                      # dram__bytes_read+write per launch from the committed ncu --set full capture
         tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
         if os.path.exists(tp) and args.config == "cfg2":
-            tk = json.load(open(tp))["kernels"].get({"emb_gather": "emb_gather_kernel", "emb_scatter_update": "emb_scatter_update_kernel"}[dom])
-            traffic = tk["dram_bytes_per_launch"] if tk else None
+            tk = json.load(open(tp))["kernels"]      # emb_scatter_update = the scatter launch + the update launch; gather includes its probe
+            parts = {"emb_gather": ["emb_probe_kernel", "emb_gather_kernel"], "emb_scatter_update": ["emb_scatter_kernel", "emb_update_kernel"]}[dom]
+            traffic = sum(tk[p]["dram_bytes_per_launch"] for p in parts) if all(p in tk for p in parts) else None
         roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
                     "frac": kernels[dom]["gbs"] / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                     "how": "algorithmic bytes (SURVEY 8d) / mean device time of the kernel replayed 64x in a CUDA graph over the batch ring "

@@ -2,6 +2,7 @@
 
   python scripts/ncu_summary.py launches <launches.csv> <out.md>      # per-kernel device-time shares of one bench run
   python scripts/ncu_summary.py full <prof.ncu-rep> <out.md>          # key metrics of a `--set full` capture
+  python scripts/ncu_summary.py traffic <prof.ncu-rep> <out.json>     # DRAM bytes per launch per kernel
 """
 import collections
 import csv
@@ -49,5 +50,26 @@ def full(src, dst):
             f.write("\n")
 
 
+def traffic(src, dst):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged per kernel name -> JSON (bench.py's roofline.traffic)."""
+    import json
+    import re
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    ir, iw, it = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+    agg = collections.OrderedDict()
+    for r in rows[2:]:
+        name = re.sub(r"^void ", "", r[hdr.index("Kernel Name")]).split("(")[0].split("<")[0].split("::")[-1]
+        b = float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
+        t = float(r[it]) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}[units[it]]
+        agg.setdefault(name, []).append((b, t))
+    res = {"source": f"ncu --set full --clock-control none ({src})", "kernels": {
+        k: {"dram_bytes_per_launch": sum(b for b, _ in v) / len(v), "launches": len(v), "avg_us_under_ncu": sum(t for _, t in v) / len(v)}
+        for k, v in agg.items()}}
+    json.dump(res, open(dst, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
