@@ -217,6 +217,24 @@ int ps_model_p2p_connect(ps_model* m, const void* all_handles /* R x 64 bytes */
 int ps_model_p2p_step_dev(ps_model* m, const int64_t* E_dev, const float* X_dev, const int64_t* W_dev, const float* Y_dev, int N);
 int ps_model_p2p_overflowed(ps_model* m, int* out);   /* a bucket exceeded cap at some step: results invalid, raise cap */
 
+/* ---- libsvm ingest feeding the step (host code: callable without a GPU) ---------------------------
+ * ps_libsvm_parse_line: data.LibsvmParser.parse (LibsvmParser.java:13-25) + one column of CTR.parseFeature (CTR.java:47-68):
+ *   "label idx:val idx:val ..." -> Y = label, E[j] = (float) idx of columns 1..F, X[x] = val of columns F+1..F+Xn,
+ *   W[j] = E[j] % wide_size in float arithmetic (MatrixUtil.hash, MatrixUtil.java:27-33; CTR.wideSize = 100000).
+ *   *status: 0 ok, 1 blank/short line (IndexOutOfBounds in parseFeature), 2 unparsable (exception in parser.parse).
+ * ps_reader_*: data.DataSet over data.FileSource (DataSet.java:37-100, DataSource.java:25-46): this reader sees file lines
+ *   offset, offset+step, ... in batches of `batch` (a short last batch is delivered); batches the reference loses to its
+ *   swallowed exceptions are lost here too (counted in ps_reader_stats).  A background thread keeps parsed batches ahead
+ *   of the consumer; ps_reader_next copies one into the caller's buffers — E, W: [rows][F] int64, X: [rows][Xn], Y: [rows],
+ *   the layout ps_model_train_step / ps_model_submit take — and returns *rows = 0 at end of data (DataSet.next() == null). */
+typedef struct ps_reader ps_reader;
+int ps_libsvm_parse_line(const char* line, size_t len, int F, int Xn, int64_t wide_size, int64_t* E, float* X, int64_t* W, float* Y, int* status);
+int ps_reader_open(const char* path, int F, int Xn, int64_t wide_size, int batch, int offset, int step, int threads, ps_reader** out);
+int ps_reader_next(ps_reader* r, int64_t* E, float* X, int64_t* W, float* Y, int* rows);
+int ps_reader_reset(ps_reader* r);                     /* DataSet.reset (DataSet.java:61-67) */
+int ps_reader_stats(ps_reader* r, int64_t* lines, int64_t* batches, int64_t* dropped_batches);
+int ps_reader_close(ps_reader* r);
+
 /* ---- test hooks -------------------------------------------------------------------- */
 /* C (M x N, row-major, ldc) = A (M x K, row-major, lda) * B^T (B is N x K, row-major, ldb),
  * through the FcLayer GEMM of the given precision mode.                                      */

@@ -102,6 +102,12 @@ SYMBOLS = {
     "ps_model_p2p_connect": (_i, [_vp, _vp]),
     "ps_model_p2p_step_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _i]),
     "ps_model_p2p_overflowed": (_i, [_vp, C.POINTER(_i)]),
+    "ps_libsvm_parse_line": (_i, [C.c_char_p, C.c_size_t, _i, _i, _i64, _vp, _vp, _vp, _vp, C.POINTER(_i)]),
+    "ps_reader_open": (_i, [C.c_char_p, _i, _i, _i64, _i, _i, _i, _i, _pp]),
+    "ps_reader_next": (_i, [_vp, _vp, _vp, _vp, _vp, C.POINTER(_i)]),
+    "ps_reader_reset": (_i, [_vp]),
+    "ps_reader_stats": (_i, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
+    "ps_reader_close": (_i, [_vp]),
     "ps_test_gemm_nt": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i]),
 }
 
@@ -156,6 +162,57 @@ class PinnedArray:
             self.array = None
             lib().ps_host_free(self.ptr)
             self.ptr = None
+
+
+def parse_libsvm_line(line, F=23, Xn=45, wide_size=100000):
+    """data.LibsvmParser.parse + one column of CTR.parseFeature.  Returns (status, E, X, W, Y): status 0 ok, 1 blank/short, 2 unparsable."""
+    if isinstance(line, str):
+        line = line.encode()
+    E, W = np.zeros(F, np.int64), np.zeros(F, np.int64)
+    X, Y = np.zeros(Xn, np.float32), np.zeros(1, np.float32)
+    st = C.c_int()
+    check(lib().ps_libsvm_parse_line(line, len(line), F, Xn, wide_size, _p(E), _p(X), _p(W), _p(Y), C.byref(st)))
+    return st.value, E, X, W, Y[0]
+
+
+class LibsvmReader:
+    """data.DataSet over data.FileSource with data.LibsvmParser + CTR.parseFeature (DataSet.java:37-100): batches of E, X, W, Y
+    in the layout Model.train_step / submit take.  `buffers` may hold PinnedArray-backed arrays to parse straight into pinned memory."""
+
+    def __init__(self, path, F=23, Xn=45, wide_size=100000, batch=1000, offset=0, step=1, threads=1):
+        self.F, self.Xn, self.batch = F, Xn, batch
+        self.h = C.c_void_p()
+        check(lib().ps_reader_open(os.fsencode(path), F, Xn, wide_size, batch, offset, step, threads, C.byref(self.h)))
+
+    def next(self, buffers=None):
+        """dict(E, X, W, Y) of the next batch (views trimmed to its rows), or None at end of data."""
+        b = buffers or dict(E=np.empty((self.batch, self.F), np.int64), W=np.empty((self.batch, self.F), np.int64),
+                            X=np.empty((self.batch, self.Xn), np.float32), Y=np.empty(self.batch, np.float32))
+        n = C.c_int()
+        check(lib().ps_reader_next(self.h, _p(b["E"]), _p(b["X"]), _p(b["W"]), _p(b["Y"]), C.byref(n)))
+        if n.value == 0:
+            return None
+        return {k: v[: n.value] for k, v in b.items()}
+
+    def __iter__(self):
+        while True:
+            b = self.next()
+            if b is None:
+                return
+            yield b
+
+    def reset(self):
+        check(lib().ps_reader_reset(self.h))
+
+    def stats(self):
+        a, b, c = _i64(), _i64(), _i64()
+        check(lib().ps_reader_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(lines=a.value, batches=b.value, dropped_batches=c.value)
+
+    def close(self):
+        if self.h:
+            lib().ps_reader_close(self.h)
+            self.h = None
 
 
 class Context:

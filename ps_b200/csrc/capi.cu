@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 
+#include "ingest.cuh"
 #include "model.cuh"
 
 namespace psb {
@@ -20,6 +21,7 @@ using namespace psb;
 
 struct ps_ctx { Ctx c; };
 struct ps_model { Model m; };
+struct ps_reader { std::unique_ptr<LibsvmReader> r; };
 struct ps_emb {
   Ctx* ctx = nullptr;
   EmbTable t;
@@ -58,6 +60,8 @@ int ps_ctx_create(int device, uint64_t seed, ps_ctx** out) {
   const char* pe = std::getenv("PS_STREAM_PRIO");
   c->c.prio_main = (pe && pe[0] == '0') ? 0 : prio_hi;
   c->c.prio_side = (pe && pe[0] == '0') ? 0 : prio_lo;
+  const char* pd = std::getenv("PS_PDL");
+  c->c.pdl = (pd && pd[0] == '0') ? 0 : 1;
   PS_CUDA(cudaStreamCreateWithPriority(&c->c.stream, cudaStreamNonBlocking, c->c.prio_main));
   PS_CUDA(cudaStreamCreateWithFlags(&c->c.copy_stream, cudaStreamNonBlocking));
   *out = c;
@@ -546,6 +550,50 @@ int ps_model_p2p_overflowed(ps_model* m, int* out) {
 }
 
 /* ---- test hook ---- */
+/* ---- libsvm ingest ---- */
+int ps_libsvm_parse_line(const char* line, size_t len, int F, int Xn, int64_t wide_size, int64_t* E, float* X, int64_t* W, float* Y, int* status) {
+  PS_TRY
+  PS_REQUIRE(line != nullptr && status != nullptr && F >= 0 && Xn >= 0 && wide_size > 0, PS_ERR_ARG, "ps_libsvm_parse_line: bad argument");
+  const char* e = line + len;
+  if (e > line && e[-1] == '\n') --e;
+  if (e > line && e[-1] == '\r') --e;
+  *status = parse_ctr_line(line, e, F, Xn, wide_size, E, X, W, Y);
+  PS_CATCH
+}
+int ps_reader_open(const char* path, int F, int Xn, int64_t wide_size, int batch, int offset, int step, int threads, ps_reader** out) {
+  PS_TRY
+  PS_REQUIRE(path != nullptr && out != nullptr, PS_ERR_ARG, "ps_reader_open: null argument");
+  std::unique_ptr<ps_reader> h(new ps_reader);
+  h->r.reset(new LibsvmReader(path, F, Xn, wide_size, batch, offset, step, threads, 2));
+  *out = h.release();
+  PS_CATCH
+}
+int ps_reader_next(ps_reader* r, int64_t* E, float* X, int64_t* W, float* Y, int* rows) {
+  PS_TRY
+  PS_REQUIRE(r != nullptr && rows != nullptr, PS_ERR_ARG, "ps_reader_next: null argument");
+  *rows = r->r->next(E, X, W, Y);
+  PS_CATCH
+}
+int ps_reader_reset(ps_reader* r) {
+  PS_TRY
+  PS_REQUIRE(r != nullptr, PS_ERR_ARG, "ps_reader_reset: null reader");
+  r->r->reset();
+  PS_CATCH
+}
+int ps_reader_stats(ps_reader* r, int64_t* lines, int64_t* batches, int64_t* dropped_batches) {
+  PS_TRY
+  PS_REQUIRE(r != nullptr, PS_ERR_ARG, "ps_reader_stats: null reader");
+  if (lines) *lines = r->r->lines_read.load();
+  if (batches) *batches = r->r->batches.load();
+  if (dropped_batches) *dropped_batches = r->r->dropped.load();
+  PS_CATCH
+}
+int ps_reader_close(ps_reader* r) {
+  PS_TRY
+  delete r;
+  PS_CATCH
+}
+
 int ps_test_gemm_nt(ps_ctx* ctx, int mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc) {
   PS_TRY
   PS_REQUIRE(ctx && A && B && C && M > 0 && N > 0 && K > 0, PS_ERR_ARG, "bad argument");

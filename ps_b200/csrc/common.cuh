@@ -55,6 +55,7 @@ struct Ctx {
   cudaStream_t copy_stream = nullptr; /* H2D staging for the pipelined trainer */
   int fc_precision = PS_FC_FP32;
   int prio_main = 0, prio_side = 0; /* stream priorities of the critical chain / the side branches */
+  int pdl = 1;                     /* programmatic dependent launch for producer -> consumer kernel pairs (PS_PDL=0 disables) */
   long launches = 0;               /* kernels launched by this library (bench gpu_launches) */
 };
 
@@ -73,6 +74,21 @@ T* dmalloc_zero(size_t n, cudaStream_t s) {
 }
 inline void dfree(void* p) { if (p) cudaFree(p); }
 
+/* Launch `kernel` as a programmatic dependent of the kernel enqueued before it on ctx->stream: its blocks may be
+ * scheduled once every block of that kernel has executed griddepcontrol.launch_dependents (or exited), and whatever it
+ * does before its own griddepcontrol.wait overlaps the producer's tail.  Works inside stream capture (a programmatic
+ * edge in the graph).  With ctx->pdl == 0 this is an ordinary launch and the device-side instructions are no-ops.    */
+template <class... KArgs, class... Args>
+inline void launch_pdl(Ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = ctx->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = ctx->pdl ? 1 : 0;
+  PS_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+
 static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
@@ -89,6 +105,9 @@ __device__ __forceinline__ float4 ld_f4_stream(const float* p) {
 __device__ __forceinline__ void st_f4_stream(float* p, float4 v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+/* programmatic dependent launch (sm_90+): see launch_pdl */
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 /* 128-bit vector reduction into global memory (sm_90+): one L2 atomic transaction per 16 B */
 __device__ __forceinline__ void red_add_f4(float* p, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");

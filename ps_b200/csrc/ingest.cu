@@ -1,0 +1,363 @@
+/*
+ * ingest.cu — libsvm ingest that feeds the training step (host code; no kernels).
+ *
+ * Path restated (reference, /root/reference/src/main/java/):
+ *   data/LibsvmParser.java:13-25      line -> [Feature(0, label), Feature(idx, value) ...]  (split on ' ', then on ':')
+ *   CTR.java:47-68 (parseFeature)     Y = value of column 0; E[j] = (float) idx of columns 1..F; X[x] = value of columns
+ *                                     F+1..F+Xn; W = MatrixUtil.hash(E, wideSize) = E % wideSize in float (MatrixUtil.java:27-33)
+ *   data/DataSource.java:25-46        a reader sees file lines offset, offset+step, offset+2*step, ...
+ *   data/DataSet.java:77-100 (run)    `batch` lines per batch; a short last batch is delivered; an exception while a batch is
+ *                                     being assembled is swallowed (`// ignore`) and the lines read so far are LOST:
+ *                                       - a line that does not parse (NumberFormatException, missing ':') throws inside
+ *                                         parser.parse: the partial batch is dropped and the next batch starts at the next line
+ *                                       - a blank or short line (< 1+F+Xn columns) only throws later, inside parseFeature
+ *                                         (IndexOutOfBounds): the WHOLE batch is dropped
+ *   data/DataSet.java:37-43,61-67     next() == null at end of data; reset() rewinds
+ *
+ * Here: the file is mapped once, a producer thread keeps `depth` parsed batches ahead of the consumer (the reference's reader
+ * thread + ArrayBlockingQueue(thread * 2)), a batch is parsed by `threads` workers over disjoint line ranges (deterministic,
+ * unlike the reference's thread > 1 readers, which interleave lines), and ps_reader_next copies straight into the caller's
+ * (pinned) E/X/W/Y staging buffers in the layout ps_model_submit takes.
+ */
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cctype>
+#include <cerrno>
+#include <cmath>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "ingest.cuh"
+
+namespace psb {
+
+namespace {
+
+inline bool is_java_ws(char c) { return (unsigned char)c <= ' '; }          /* String.trim() / Character.isWhitespace for ASCII */
+
+/* Long.parseLong: [+-]?digits, no whitespace, overflow is an error */
+bool parse_long(const char* b, const char* e, int64_t* out) {
+  if (b >= e) return false;
+  bool neg = false;
+  if (*b == '-' || *b == '+') { neg = *b == '-'; ++b; }
+  if (b >= e) return false;
+  uint64_t v = 0;
+  const uint64_t lim = neg ? (uint64_t)1 << 63 : ((uint64_t)1 << 63) - 1;
+  for (; b < e; ++b) {
+    if (*b < '0' || *b > '9') return false;
+    const uint64_t d = (uint64_t)(*b - '0');
+    if (v > (lim - d) / 10) return false;
+    v = v * 10 + d;
+  }
+  *out = neg ? (int64_t)(0 - v) : (int64_t)v;
+  return true;
+}
+
+/* Float.parseFloat: trims whitespace, then [+-]? ( NaN | Infinity | decimal [eE][+-]?digits [fFdD]? | hex float with a p exponent ).
+ * The value is the correctly rounded float of the decimal string, which is what glibc strtof returns. */
+bool parse_float(const char* b, const char* e, float* out) {
+  while (b < e && is_java_ws(*b)) ++b;
+  while (e > b && is_java_ws(e[-1])) --e;
+  if (b >= e || e - b > 200) return false;
+  const char* p = b;
+  if (*p == '+' || *p == '-') ++p;
+  const size_t rest = (size_t)(e - p);
+  if (rest == 3 && std::memcmp(p, "NaN", 3) == 0) { *out = NAN; return true; }
+  if (rest == 8 && std::memcmp(p, "Infinity", 8) == 0) { *out = *b == '-' ? -INFINITY : INFINITY; return true; }
+  const char* q = p;
+  bool hex = false;
+  if (rest > 2 && q[0] == '0' && (q[1] == 'x' || q[1] == 'X')) {
+    hex = true; q += 2;
+    int nd = 0;
+    while (q < e && std::isxdigit((unsigned char)*q)) { ++q; ++nd; }
+    if (q < e && *q == '.') { ++q; while (q < e && std::isxdigit((unsigned char)*q)) { ++q; ++nd; } }
+    if (nd == 0 || q >= e || (*q != 'p' && *q != 'P')) return false;     /* Java requires the binary exponent */
+    ++q;
+    if (q < e && (*q == '+' || *q == '-')) ++q;
+    int ne = 0;
+    while (q < e && *q >= '0' && *q <= '9') { ++q; ++ne; }
+    if (ne == 0) return false;
+  } else {
+    int nd = 0;
+    while (q < e && *q >= '0' && *q <= '9') { ++q; ++nd; }
+    if (q < e && *q == '.') { ++q; while (q < e && *q >= '0' && *q <= '9') { ++q; ++nd; } }
+    if (nd == 0) return false;
+    if (q < e && (*q == 'e' || *q == 'E')) {
+      ++q;
+      if (q < e && (*q == '+' || *q == '-')) ++q;
+      int ne = 0;
+      while (q < e && *q >= '0' && *q <= '9') { ++q; ++ne; }
+      if (ne == 0) return false;
+    }
+  }
+  const char* num_end = q;
+  if (q < e && (*q == 'f' || *q == 'F' || *q == 'd' || *q == 'D')) ++q;
+  if (q != e) return false;
+  (void)hex;
+  char buf[208];
+  const size_t n = (size_t)(num_end - b);
+  std::memcpy(buf, b, n);
+  buf[n] = 0;
+  char* endp = nullptr;
+  *out = std::strtof(buf, &endp);
+  return endp == buf + n;
+}
+
+/* fast path for the overwhelmingly common spellings ("1", "0.48"): up to 7 significant digits, no exponent — the decimal value
+ * m / 10^k with m < 2^24 and k <= 10 is a correctly rounded single division of two exactly representable numbers */
+inline bool parse_float_fast(const char* b, const char* e, float* out) {
+  static const float p10[11] = {1.f, 1e1f, 1e2f, 1e3f, 1e4f, 1e5f, 1e6f, 1e7f, 1e8f, 1e9f, 1e10f};
+  const char* p = b;
+  bool neg = false;
+  if (p < e && *p == '-') { neg = true; ++p; }
+  uint32_t m = 0; int nd = 0, k = 0; bool dot = false;
+  if (p >= e) return false;
+  for (; p < e; ++p) {
+    if (*p == '.') { if (dot) return false; dot = true; continue; }
+    if (*p < '0' || *p > '9') return false;
+    m = m * 10 + (uint32_t)(*p - '0');
+    if (m != 0 || nd > 0) ++nd;                 /* significant digits (leading zeros are free) */
+    if (dot) ++k;
+    if (nd > 7 || k > 10) return false;
+  }
+  if (nd == 0 && m == 0 && (e - b) == (neg ? 2 : 1) && b[neg ? 1 : 0] == '.') return false;   /* a lone "." */
+  const float v = (float)m / p10[k];             /* both exact in fp32 (m < 10^7 < 2^24; 10^k exact for k <= 10) => one rounding */
+  *out = neg ? -v : v;
+  return true;
+}
+
+}  // namespace
+
+/* One line -> one row of E/X/W/Y.  Returns LINE_OK, LINE_SHORT (blank or fewer than 1+F+Xn columns: IndexOutOfBounds in
+ * parseFeature) or LINE_BAD (an exception inside LibsvmParser.parse).                                                     */
+int parse_ctr_line(const char* b, const char* e, int F, int Xn, int64_t wide, int64_t* E, float* X, int64_t* W, float* Y) {
+  /* StringUtils.isBlank -> empty feature list */
+  {
+    const char* p = b;
+    while (p < e && is_java_ws(*p)) ++p;
+    if (p == e) return LINE_SHORT;
+  }
+  /* String.split(" "): trailing empty strings are removed, leading / inner ones are kept (and then fail to parse) */
+  while (e > b && e[-1] == ' ') --e;
+  int col = 0;
+  const int need = 1 + F + Xn;
+  bool shortline = false;
+  const char* p = b;
+  while (true) {
+    const char* t = p;
+    while (t < e && *t != ' ') ++t;              /* token [p, t) */
+    if (col == 0) {
+      float y;
+      if (!parse_float_fast(p, t, &y) && !parse_float(p, t, &y)) return LINE_BAD;
+      if (Y) *Y = y;
+    } else {
+      const char* c = p;
+      while (c < t && *c != ':') ++c;            /* pair[0] = [p, c) */
+      if (c == t) {                              /* no ':' — "abc".split(":") has one element, pair[1] throws; "5:" likewise */
+        return LINE_BAD;
+      }
+      const char* v = c + 1;
+      const char* ve = v;
+      while (ve < t && *ve != ':') ++ve;         /* pair[1] = [v, ve); further ':' segments are ignored */
+      /* "5:" -> split drops the trailing empty string -> pair.length == 1 -> ArrayIndexOutOfBounds */
+      bool only_empty_after = true;
+      for (const char* z = v; z < t; ++z) if (*z != ':') { only_empty_after = false; break; }
+      if (only_empty_after) return LINE_BAD;
+      int64_t idx;
+      float val;
+      if (!parse_long(p, c, &idx)) return LINE_BAD;
+      if (!parse_float_fast(v, ve, &val) && !parse_float(v, ve, &val)) return LINE_BAD;
+      if (col <= F) {
+        const float idf = (float)idx;            /* E[j-1][i] = cols.get(j).getIdx()  (long -> float, CTR.java:57) */
+        if (E) E[col - 1] = (int64_t)idf;
+        if (W) W[col - 1] = (int64_t)std::fmod(idf, (float)wide);   /* result.data[i] % size in float (MatrixUtil.java:30) */
+      } else if (col < need) {
+        if (X) X[col - 1 - F] = val;             /* X[j-24][i] = cols.get(j).toF() */
+      }
+    }
+    ++col;
+    if (t >= e) break;
+    p = t + 1;
+  }
+  if (col < need) shortline = true;
+  return shortline ? LINE_SHORT : LINE_OK;
+}
+
+/* ------------------------------------------------------------------ LibsvmReader */
+struct LibsvmReader::Batch {
+  int rows = 0;
+  bool eof = false;
+  std::vector<int64_t> E, W;
+  std::vector<float> X, Y;
+};
+
+LibsvmReader::LibsvmReader(const std::string& path, int F_, int Xn_, int64_t wide_, int batch_, int offset_, int step_, int threads_, int depth_)
+    : F(F_), Xn(Xn_), wide(wide_), batch(batch_), offset(offset_), step(step_), threads(threads_ < 1 ? 1 : threads_), depth(depth_ < 1 ? 1 : depth_) {
+  PS_REQUIRE(F >= 0 && Xn >= 0 && batch > 0 && offset >= 0 && step >= 1 && wide > 0, PS_ERR_ARG, "reader: bad argument");
+  fd = ::open(path.c_str(), O_RDONLY);
+  PS_REQUIRE(fd >= 0, PS_NOT_FOUND, ("reader: cannot open " + path).c_str());
+  struct stat st;
+  if (fstat(fd, &st) != 0) { ::close(fd); throw Error(PS_ERR_ARG, "reader: fstat failed"); }
+  size = (size_t)st.st_size;
+  if (size > 0) {
+    void* m = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (m == MAP_FAILED) { ::close(fd); throw Error(PS_ERR_ARG, "reader: mmap failed"); }
+    data = static_cast<const char*>(m);
+    madvise(const_cast<char*>(data), size, MADV_SEQUENTIAL);
+  }
+  start();
+}
+
+LibsvmReader::~LibsvmReader() {
+  stop();
+  if (data) munmap(const_cast<char*>(data), size);
+  if (fd >= 0) ::close(fd);
+}
+
+void LibsvmReader::start() {
+  pos = 0; line_no = 0; quit = false; produced_eof = false;
+  producer = std::thread([this] { this->produce(); });
+}
+
+void LibsvmReader::stop() {
+  {
+    std::lock_guard<std::mutex> g(mu);
+    quit = true;
+  }
+  cv_space.notify_all();
+  cv_data.notify_all();
+  if (producer.joinable()) producer.join();
+  queue.clear();
+}
+
+void LibsvmReader::reset() {                      /* DataSet.reset: shutdownNow, queue.clear, source.reset, start */
+  stop();
+  start();
+}
+
+/* BufferedReader.readLine over the mapping: next line [b, e) without its terminator; false at end of file */
+bool LibsvmReader::raw_line(const char** b, const char** e) {
+  if (pos >= size) return false;
+  const char* p = data + pos;
+  const char* nl = static_cast<const char*>(std::memchr(p, '\n', size - pos));
+  const char* end = nl ? nl : data + size;
+  pos = (size_t)((nl ? nl + 1 : end) - data);
+  *b = p;
+  *e = (end > p && end[-1] == '\r') ? end - 1 : end;
+  return true;
+}
+
+/* DataSource.readLine (DataSource.java:25-46): the first call skips `offset` lines, later calls advance by `step` */
+bool LibsvmReader::next_line(const char** b, const char** e) {
+  const int64_t skip = line_no == 0 ? offset : step - 1;
+  for (int64_t i = 0; i < skip; ++i) {
+    const char *sb, *se;
+    if (!raw_line(&sb, &se)) return false;
+  }
+  if (!raw_line(b, e)) return false;
+  ++line_no;
+  return true;
+}
+
+void LibsvmReader::produce() {
+  std::vector<std::pair<const char*, const char*>> lines;
+  std::vector<int> status;
+  bool eof = false;
+  while (!eof) {
+    /* DataSet.run: gather up to `batch` lines */
+    lines.clear();
+    while ((int)lines.size() < batch) {
+      const char *b, *e;
+      if (!next_line(&b, &e)) { eof = true; break; }
+      lines.emplace_back(b, e);
+    }
+    if (!lines.empty()) {
+      std::unique_ptr<Batch> out(new Batch);
+      const int n = (int)lines.size();
+      out->E.resize((size_t)n * F); out->W.resize((size_t)n * F); out->X.resize((size_t)n * Xn); out->Y.resize(n);
+      status.assign(n, LINE_OK);
+      auto work = [&](int lo, int hi) {
+        for (int i = lo; i < hi; ++i)
+          status[i] = parse_ctr_line(lines[i].first, lines[i].second, F, Xn, wide, out->E.data() + (size_t)i * F, out->X.data() + (size_t)i * Xn,
+                                     out->W.data() + (size_t)i * F, out->Y.data() + i);
+      };
+      const int nt = std::min(threads, std::max(1, n / 64));
+      if (nt <= 1) work(0, n);
+      else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nt; ++t) pool.emplace_back(work, (int)((int64_t)n * t / nt), (int)((int64_t)n * (t + 1) / nt));
+        for (auto& t : pool) t.join();
+      }
+      /* the reference's swallowed exceptions: a line that fails inside parser.parse drops what was gathered up to and
+       * including it — the lines after it (already consumed here) form the head of the next batch */
+      int first_bad = -1;
+      for (int i = 0; i < n; ++i) if (status[i] == LINE_BAD) { first_bad = i; break; }
+      lines_read += n;
+      if (first_bad >= 0) {
+        ++dropped;
+        /* push the tail back: rewind the cursor to just after the offending line */
+        rewind_to_after(lines[first_bad].second, n - 1 - first_bad);
+        lines_read -= n - 1 - first_bad;
+        eof = false;
+        continue;
+      }
+      bool any_short = false;
+      for (int i = 0; i < n; ++i) any_short |= status[i] == LINE_SHORT;
+      if (any_short) { ++dropped; continue; }      /* IndexOutOfBounds in parseFeature: the whole batch is lost */
+      out->rows = n;
+      ++batches;
+      std::unique_lock<std::mutex> g(mu);
+      cv_space.wait(g, [this] { return quit || (int)queue.size() < depth; });
+      if (quit) return;
+      queue.push_back(std::move(out));
+      g.unlock();
+      cv_data.notify_one();
+    }
+  }
+  std::unique_ptr<Batch> fin(new Batch);
+  fin->eof = true;
+  std::unique_lock<std::mutex> g(mu);
+  cv_space.wait(g, [this] { return quit || (int)queue.size() < depth + 1; });
+  if (quit) return;
+  queue.push_back(std::move(fin));
+  produced_eof = true;
+  g.unlock();
+  cv_data.notify_all();
+}
+
+/* un-read `count` of this reader's lines: the cursor returns to the byte after `line_end`'s terminator */
+void LibsvmReader::rewind_to_after(const char* line_end, int count) {
+  const char* p = line_end;
+  if (p < data + size && *p == '\r') ++p;
+  if (p < data + size && *p == '\n') ++p;
+  pos = (size_t)(p - data);
+  line_no -= count;
+}
+
+int LibsvmReader::next(int64_t* E, float* X, int64_t* W, float* Y) {
+  std::unique_lock<std::mutex> g(mu);
+  cv_data.wait(g, [this] { return !queue.empty(); });
+  if (queue.front()->eof) return 0;               /* stays at the front: every later call reports end of data too */
+  std::unique_ptr<Batch> b = std::move(queue.front());
+  queue.pop_front();
+  g.unlock();
+  cv_space.notify_one();
+  const size_t n = (size_t)b->rows;
+  if (E && F) std::memcpy(E, b->E.data(), sizeof(int64_t) * n * F);
+  if (W && F) std::memcpy(W, b->W.data(), sizeof(int64_t) * n * F);
+  if (X && Xn) std::memcpy(X, b->X.data(), sizeof(float) * n * Xn);
+  if (Y) std::memcpy(Y, b->Y.data(), sizeof(float) * n);
+  return b->rows;
+}
+
+}  // namespace psb

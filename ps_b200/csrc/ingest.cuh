@@ -1,0 +1,58 @@
+/*
+ * ingest.cuh — native libsvm reader feeding the step's staging buffers (see ingest.cu).
+ * Stands behind data.LibsvmParser.parse (LibsvmParser.java:13-25), CTR.parseFeature (CTR.java:47-68),
+ * data.DataSource.readLine (DataSource.java:25-46) and data.DataSet.next/hasNext/reset/run (DataSet.java:37-100).
+ */
+#pragma once
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+
+#include "common.cuh"
+
+namespace psb {
+
+enum { LINE_OK = 0, LINE_SHORT = 1, LINE_BAD = 2 };
+
+/* one text line [b, e) -> one sample: E[F], X[Xn], W[F], Y[1] (any output may be null) */
+int parse_ctr_line(const char* b, const char* e, int F, int Xn, int64_t wide, int64_t* E, float* X, int64_t* W, float* Y);
+
+struct LibsvmReader {
+  struct Batch;
+  int F, Xn;
+  int64_t wide;
+  int batch, offset, step, threads, depth;
+  /* the mapped file and this reader's cursor (producer thread only) */
+  int fd = -1;
+  const char* data = nullptr;
+  size_t size = 0, pos = 0;
+  int64_t line_no = 0;
+  /* statistics */
+  std::atomic<int64_t> lines_read{0}, batches{0}, dropped{0};
+  /* producer -> consumer queue */
+  std::mutex mu;
+  std::condition_variable cv_data, cv_space;
+  std::deque<std::unique_ptr<Batch>> queue;
+  std::thread producer;
+  bool quit = false, produced_eof = false;
+
+  LibsvmReader(const std::string& path, int F, int Xn, int64_t wide, int batch, int offset, int step, int threads, int depth);
+  ~LibsvmReader();
+  LibsvmReader(const LibsvmReader&) = delete;
+  int next(int64_t* E, float* X, int64_t* W, float* Y);   /* rows of the batch; 0 = end of data (DataSet.next() == null) */
+  void reset();
+
+ private:
+  void start();
+  void stop();
+  void produce();
+  bool raw_line(const char** b, const char** e);
+  bool next_line(const char** b, const char** e);
+  void rewind_to_after(const char* line_end, int count);
+};
+
+}  // namespace psb

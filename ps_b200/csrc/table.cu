@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(256) emb_probe_kernel(EmbSlot* __restrict__ sl
    * samples, so a hot key (a low-cardinality field) is counted with one L2 atomic per warp, not 32 */
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();                     /* the gather's blocks may be scheduled; they wait for this grid before reading */
   int slot = -1;
   bool first = false;
   uint32_t add = 1u;
@@ -100,7 +101,9 @@ __global__ void __launch_bounds__(256) emb_probe_kernel(EmbSlot* __restrict__ sl
   }
   /* warp-aggregated occurrence count: lanes holding the same slot add once */
   const unsigned peers = __match_any_sync(0xffffffffu, slot >= 0 ? slot : (-1 - lane));
-  const uint32_t total_add = __reduce_add_sync(peers, add);
+  /* every lookup counts 1 unless it is a pre-counted entry of the peer-memory exchange (a reduction over a partial
+   * mask runs once per distinct key in the warp: not worth it for a popcount) */
+  const uint32_t total_add = p2p == nullptr ? (uint32_t)__popc(peers) : __reduce_add_sync(peers, add);
   if (slot >= 0 && (__ffs(peers) - 1) == lane) first = atomicAdd(&slots[slot].cnt, total_add) == 0u;
   /* the key's accumulator row for this batch is the one indexed by the work index of its FIRST lookup: no
    * numbering pass, nothing to reset (the row is zeroed again by the lookup that consumes it)            */
@@ -126,6 +129,7 @@ __global__ void __launch_bounds__(256) emb_gather_kernel(const float* __restrict
                                                          int L, int F, float* __restrict__ out, int ldo, const float* __restrict__ X, int Xn,
                                                          int xoff, int N) {
   const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_wait();                                  /* launched as a programmatic dependent of the probe */
   if (g >= (long)L * TPL) {                    /* ConcatLayer.forward (ConcatLayer.java:30-37): numeric features next to the embeddings */
     const long i = g - (long)L * TPL;
     if (X != nullptr && i < (long)N * Xn) { const int n = (int)(i / Xn), x = (int)(i - (long)n * Xn); out[(size_t)n * ldo + xoff + x] = X[i]; }
@@ -166,141 +170,222 @@ __device__ __forceinline__ float emb_geff(float S, uint32_t n, int calls) {
   return __fdiv_rn(__fadd_rn(q, S), (float)(2u * n));
 }
 
-/* Sparse backward = two launches on one stream:
- *   emb_scatter_kernel  g_k = delta[:,k] * (A[:,k] > 0)  (EmbeddingField.java:91-93); lanes of a warp work on the SAME
- *            field for consecutive samples, so duplicates of a hot key are first summed inside the warp (a
- *            reduce-by-key tree over the lanes __match_any_sync groups) and the warp issues ONE
- *            red.global.add.v4.f32 per key and 16 B chunk into the key's accumulator row (L2-resident, indexed by
- *            the work index of the key's first lookup, which emb_probe left in the slot record)
- *   emb_update_kernel   the lookup that owns the accumulator row reads S back from L2, forms g_eff, runs the Adam /
- *            Ftrl / SGD step on w, s1, s2 in place and resets the per-batch state (acc, cnt) — KVStore.sum +
- *            update + clear (KVStore.java:192-200,240-277).
- * TPL lanes cooperate on one lookup, each owning CPL 16 B chunks of the row.  Work index lk = j*N + n (field-major),
- * the same index emb_probe used.                                                                               */
-template <int TPL, int CPL, bool ALIGNED>
+/* Sparse backward = two launches on one stream, the second a programmatic dependent of the first:
+ *   emb_scatter_kernel  g_k = delta[:,k] * (A[:,k] > 0)  (EmbeddingField.java:91-93).  A block owns a tile of consecutive
+ *            work indices lk = j*N + n (field-major: ONE field, consecutive samples), so duplicates of a key meet in
+ *            the same block.  Three levels of pre-summation keep a hot key (a low-cardinality field: thousands of
+ *            occurrences of one row) from serialising in L2:  (1) reduce-by-key tree over the lanes of a warp that
+ *            __match_any_sync groups;  (2) keys with >= kHotMin occurrences in the batch (the probe left the count in
+ *            the slot record) are summed in a per-block shared-memory table and leave the block ONCE;  (3) everything
+ *            else goes out as one red.global.add.v4.f32 per key and 16 B chunk into the key's accumulator row
+ *            (L2-resident, indexed by the work index of the key's first lookup).
+ *   emb_update_kernel   a block scans 256 work indices, compacts the ones that own an accumulator row (the key's
+ *            first lookup) in shared memory and then spends ALL its lanes on them, 4 floats per lane: read S back
+ *            from L2, form g_eff, run the Adam / Ftrl / SGD step on w, s1, s2 in place and reset the per-batch state
+ *            (acc, cnt) — KVStore.sum + update + clear (KVStore.java:192-200,240-277).  Launched with programmatic
+ *            stream serialisation: its scan, compaction and the w/s1/s2 loads of its first pass run while the scatter
+ *            kernel drains; only the accumulator read sits behind griddepcontrol.wait.                              */
+static constexpr int kHotMin = 8;        /* occurrences in the batch from which a key is pre-summed per block */
+static constexpr int kHotEntries = 32;   /* per-block hot-key table (open addressing, 4 probes) */
+
+template <int TPL, int CPL, int PASSES, bool ALIGNED>
 __global__ void __launch_bounds__(256) emb_scatter_kernel(const EmbSlot* __restrict__ slots, int Dp, int D, const int32_t* __restrict__ lk_slot, int N,
                                                           int F, const float* __restrict__ delta, int ldd, const float* __restrict__ act, int lda,
                                                           float* __restrict__ acc, const int* __restrict__ skip_flag,
                                                           const P2PState* __restrict__ p2p) {
   constexpr int GPW = 32 / TPL;                  /* lookups (lane groups) per warp */
+  constexpr int GPB = 256 / TPL;                 /* lookups per block and pass */
+  constexpr int ROWF = TPL * CPL * 4;            /* floats of a (padded) row */
+  __shared__ float hot_acc[kHotEntries][ROWF];
+  __shared__ int hot_slot[kHotEntries];
+  __shared__ uint32_t hot_uidx[kHotEntries];
+  pdl_launch_dependents();                       /* the update kernel may start its scan now (it waits before reading acc) */
   if (skip_flag != nullptr && *skip_flag != 0) return;   /* DNN.java:58-63 early exit: nothing is pushed */
   if (p2p != nullptr) delta = reinterpret_cast<const float*>(p2p_region(p2p, p2p->me, p2p->off_grads));   /* this step's grads_in mailbox */
   const long L = (long)N * F;
   const int lane = threadIdx.x & 31;
-  const int part = lane % TPL, my_group = lane / TPL;
+  const int part = lane % TPL;
   const int c0 = part * CPL * 4;                 /* first float of this lane's chunks */
-  const long lk = ((long)blockIdx.x * 256 + (threadIdx.x & ~31)) / TPL + my_group;
   /* lanes holding the same `part` of their lookups: bits at multiples of TPL, shifted by part */
   unsigned part_lanes = 0u;
 #pragma unroll
   for (int g = 0; g < GPW; ++g) part_lanes |= 1u << (g * TPL);
   part_lanes <<= part;
 
-  bool valid = lk < L;
-  int slot = -1, n = 0, j = 0;
-  if (valid) { j = (int)(lk / N); n = (int)(lk - (long)j * N); }
-  float4 gk[CPL];
+  for (int i = threadIdx.x; i < kHotEntries; i += 256) hot_slot[i] = -1;
+  for (int i = threadIdx.x; i < kHotEntries * ROWF; i += 256) (&hot_acc[0][0])[i] = 0.f;
+  __syncthreads();
+
+  /* ---- every load of the tile is issued before anything is consumed ---- */
+  int slot[PASSES];
+  float4 gk[PASSES][CPL];
 #pragma unroll
-  for (int c = 0; c < CPL; ++c) gk[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (valid) {
-    slot = lk_slot[(long)n * F + j];
-    /* the gradient / activation loads do not depend on the slot: they fly together with the slot lookup */
+  for (int p = 0; p < PASSES; ++p) {
+    const long lk = (long)blockIdx.x * (PASSES * GPB) + p * GPB + threadIdx.x / TPL;
+    slot[p] = -1;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) gk[p][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lk < L) {
+      const int j = (int)(lk / N), n = (int)(lk - (long)j * N);
+      slot[p] = lk_slot[(long)n * F + j];
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        const int cc = c0 + 4 * c;
+        if (cc < D) {
+          const size_t od = (size_t)n * ldd + j * D + cc, oa = (size_t)n * lda + j * D + cc;
+          float dv[4] = {0.f, 0.f, 0.f, 0.f}, av[4] = {0.f, 0.f, 0.f, 0.f};
+          if (ALIGNED) {
+            const float4 d4 = ld_f4(delta + od);
+            const float4 a4 = act ? ld_f4(act + oa) : make_float4(1.f, 1.f, 1.f, 1.f);   /* act == null: the mask was applied by the sender */
+            dv[0] = d4.x; dv[1] = d4.y; dv[2] = d4.z; dv[3] = d4.w;
+            av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if (cc + i < D) { dv[i] = delta[od + i]; av[i] = act ? act[oa + i] : 1.f; }
+          }
+          /* Relu.backward: dy *= (y > 0 ? 1 : 0)  (activations/Relu.java:14-19) */
+          gk[p][c].x = __fmul_rn(dv[0], av[0] > 0.f ? 1.f : 0.f); gk[p][c].y = __fmul_rn(dv[1], av[1] > 0.f ? 1.f : 0.f);
+          gk[p][c].z = __fmul_rn(dv[2], av[2] > 0.f ? 1.f : 0.f); gk[p][c].w = __fmul_rn(dv[3], av[3] > 0.f ? 1.f : 0.f);
+        }
+      }
+    }
+  }
+  uint32_t cnt[PASSES], uidx[PASSES];
+#pragma unroll
+  for (int p = 0; p < PASSES; ++p) {
+    cnt[p] = 0u; uidx[p] = 0u;
+    if (slot[p] >= 0) { const uint4 m = *reinterpret_cast<const uint4*>(&slots[slot[p]]); cnt[p] = m.z; uidx[p] = m.w; }
+  }
+#pragma unroll
+  for (int p = 0; p < PASSES; ++p) {
+    const bool valid = slot[p] >= 0;
+    /* ---- (1) reduce-by-key inside the warp: rank r of a key's lanes adds rank r+s, s = 1, 2, 4, ... ---- */
+    const unsigned pmask = __match_any_sync(0xffffffffu, valid ? slot[p] : (-1 - lane)) & part_lanes;
+    const int npeer = __popc(pmask);
+    const int rank = __popc(pmask & ((1u << lane) - 1u));
+    const int maxn = __reduce_max_sync(0xffffffffu, npeer);
+    for (int s = 1; s < maxn; s <<= 1) {
+      const bool has = rank + s < npeer;
+      const int partner = has ? (int)__fns(pmask, (unsigned)lane, s + 1) : lane;
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        const float4 o = shfl_f4(gk[p][c], partner);
+        if (has) { gk[p][c].x += o.x; gk[p][c].y += o.y; gk[p][c].z += o.z; gk[p][c].w += o.w; }
+      }
+    }
+    if (!valid || rank != 0) continue;
+    /* ---- (2) hot keys: sum inside the block (the peer-memory exchange packs {entries << 24 | occurrences}: never hot) ---- */
+    int e = -1;
+    if (p2p == nullptr && cnt[p] >= (uint32_t)kHotMin) {
+      uint32_t h = ((uint32_t)slot[p] * 2654435761u) >> 27;
+#pragma unroll 1
+      for (int t = 0; t < 4; ++t) {
+        const int old = atomicCAS(&hot_slot[h], -1, slot[p]);
+        if (old == -1) hot_uidx[h] = uidx[p];
+        if (old == -1 || old == slot[p]) { e = (int)h; break; }
+        h = (h + 1u) & (uint32_t)(kHotEntries - 1);
+      }
+    }
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
       const int cc = c0 + 4 * c;
-      if (cc < D) {
-        const size_t od = (size_t)n * ldd + j * D + cc, oa = (size_t)n * lda + j * D + cc;
-        float dv[4] = {0.f, 0.f, 0.f, 0.f}, av[4] = {0.f, 0.f, 0.f, 0.f};
-        if (ALIGNED) {
-          const float4 d4 = ld_f4(delta + od);
-          const float4 a4 = act ? ld_f4(act + oa) : make_float4(1.f, 1.f, 1.f, 1.f);   /* act == null: the mask was applied by the sender */
-          dv[0] = d4.x; dv[1] = d4.y; dv[2] = d4.z; dv[3] = d4.w;
-          av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) if (cc + i < D) { dv[i] = delta[od + i]; av[i] = act ? act[oa + i] : 1.f; }
-        }
-        /* Relu.backward: dy *= (y > 0 ? 1 : 0)  (activations/Relu.java:14-19) */
-        gk[c].x = __fmul_rn(dv[0], av[0] > 0.f ? 1.f : 0.f); gk[c].y = __fmul_rn(dv[1], av[1] > 0.f ? 1.f : 0.f);
-        gk[c].z = __fmul_rn(dv[2], av[2] > 0.f ? 1.f : 0.f); gk[c].w = __fmul_rn(dv[3], av[3] > 0.f ? 1.f : 0.f);
+      if (cc >= D) continue;
+      if (e >= 0) {
+        float* a = &hot_acc[e][cc];
+        if (gk[p][c].x != 0.f) atomicAdd(a + 0, gk[p][c].x);
+        if (gk[p][c].y != 0.f) atomicAdd(a + 1, gk[p][c].y);
+        if (gk[p][c].z != 0.f) atomicAdd(a + 2, gk[p][c].z);
+        if (gk[p][c].w != 0.f) atomicAdd(a + 3, gk[p][c].w);
+      } else {
+        red_add_f4(acc + (size_t)uidx[p] * Dp + cc, gk[p][c]);          /* ---- (3) ---- */
       }
     }
-    valid = slot >= 0;
   }
-  uint32_t uidx = 0u;
-  if (valid) uidx = slots[slot].uidx;
-  /* ---- reduce-by-key inside the warp: rank r of a key's lanes adds rank r+s, s = 1, 2, 4, ... ---- */
-  const unsigned pmask = __match_any_sync(0xffffffffu, valid ? slot : (-1 - lane)) & part_lanes;
-  const int npeer = __popc(pmask);
-  const int rank = __popc(pmask & ((1u << lane) - 1u));
-  const int maxn = __reduce_max_sync(0xffffffffu, npeer);
-  for (int s = 1; s < maxn; s <<= 1) {
-    const bool has = rank + s < npeer;
-    const int partner = has ? (int)__fns(pmask, (unsigned)lane, s + 1) : lane;
-#pragma unroll
-    for (int c = 0; c < CPL; ++c) {
-      const float4 o = shfl_f4(gk[c], partner);
-      if (has) { gk[c].x += o.x; gk[c].y += o.y; gk[c].z += o.z; gk[c].w += o.w; }
-    }
-  }
-  if (valid && rank == 0) {
-#pragma unroll
-    for (int c = 0; c < CPL; ++c)
-      if (c0 + 4 * c < D) red_add_f4(acc + (size_t)uidx * Dp + c0 + 4 * c, gk[c]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < kHotEntries * (ROWF / 4); i += 256) {
+    const int e = i / (ROWF / 4), cc = (i % (ROWF / 4)) * 4;
+    if (hot_slot[e] < 0 || cc >= D) continue;
+    const float4 v = *reinterpret_cast<const float4*>(&hot_acc[e][cc]);
+    if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) red_add_f4(acc + (size_t)hot_uidx[e] * Dp + cc, v);
   }
 }
 
-template <int TPL, int CPL>
+template <int TPK>
 __global__ void __launch_bounds__(256) emb_update_kernel(EmbSlot* __restrict__ slots, float* __restrict__ w, float* __restrict__ s1, float* __restrict__ s2,
                                                          int Dp, int D, const int32_t* __restrict__ lk_slot, int N, int F, float* __restrict__ acc,
                                                          UpdaterDev upd, int calls, const int* __restrict__ skip_flag, int packed_cnt) {
+  constexpr int KPP = 256 / TPK;                   /* keys per pass */
+  __shared__ int s_slot[256];
+  __shared__ uint32_t s_cnt[256], s_uidx[256];
+  __shared__ int s_warp[8];
   const long L = (long)N * F;
-  const int lane = threadIdx.x & 31;
-  const int part = lane % TPL, my_group = lane / TPL;
-  const int c0 = part * CPL * 4;
-  const long lk = ((long)blockIdx.x * 256 + (threadIdx.x & ~31)) / TPL + my_group;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  /* ---- scan: which of this block's 256 work indices own an accumulator row (the key's first lookup of the batch) ---- */
+  const long lk = (long)blockIdx.x * 256 + threadIdx.x;
   int slot = -1; uint32_t cnt = 0u, uidx = 0u;
   if (lk < L) {
     const int j = (int)(lk / N), n = (int)(lk - (long)j * N);
     slot = lk_slot[(long)n * F + j];
     if (slot >= 0) { const uint4 m = *reinterpret_cast<const uint4*>(&slots[slot]); cnt = m.z; uidx = m.w; }
   }
-  const bool owner = slot >= 0 && uidx == (uint32_t)lk;      /* the key's first lookup of the batch */
+  const bool owner = slot >= 0 && uidx == (uint32_t)lk;
+  const unsigned owners = __ballot_sync(0xffffffffu, owner);
+  if (lane == 0) s_warp[warp] = __popc(owners);
+  __syncthreads();
+  int base = 0, total = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const int c = s_warp[i]; if (i < warp) base += c; total += c; }
+  if (owner) {
+    const int o = base + __popc(owners & ((1u << lane) - 1u));
+    s_slot[o] = slot; s_cnt[o] = cnt; s_uidx[o] = uidx;
+  }
+  __syncthreads();
   const bool skip = skip_flag != nullptr && *skip_flag != 0;
-  /* peer-memory exchange: senders pre-reduce, cnt packs {entries << 24 | occurrences} */
-  const uint32_t n_occ = packed_cnt ? (cnt & 0xFFFFFFu) : cnt;
-  float4 S[CPL];
-#pragma unroll
-  for (int c = 0; c < CPL; ++c) {
-    const int cc = c0 + 4 * c;
-    S[c] = (owner && !skip && cc < D) ? __ldcg(reinterpret_cast<const float4*>(acc + (size_t)uidx * Dp + cc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const int part = threadIdx.x % TPK, cc = part * 4;
+  const bool col_ok = cc < D;
+  /* ---- the rows of the first pass are requested before the scatter kernel is known to be complete ---- */
+  int k = threadIdx.x / TPK;
+  bool active = k < total && col_ok;
+  size_t o = 0;
+  float4 wv = make_float4(0.f, 0.f, 0.f, 0.f), m1 = wv, m2 = wv;
+  if (active) {
+    o = (size_t)s_slot[k] * Dp + cc;
+    if (!skip) { wv = ld_f4(w + o); if (upd.kind != PS_UPD_SIMPLE) { m1 = ld_f4(s1 + o); m2 = ld_f4(s2 + o); } }
   }
-  bool do_upd = !skip;
-  if (upd.kind == PS_UPD_FTRL) {                  /* FtrlUpdater.java:52: `if (dw.get(0) == 0) return w` */
-    const float S0 = __shfl_sync(0xffffffffu, S[0].x, my_group * TPL);
-    do_upd = do_upd && emb_geff(S0, n_occ, calls) != 0.0f;
-  }
-  if (!owner) return;
-  if (!skip) {
-#pragma unroll
-    for (int c = 0; c < CPL; ++c) {
-      const int cc = c0 + 4 * c;
-      if (cc >= D) continue;
+  pdl_wait();
+  for (int kb = 0; kb < total; kb += KPP) {
+    if (kb > 0) {
+      k = kb + threadIdx.x / TPK;
+      active = k < total && col_ok;
+      if (active) {
+        o = (size_t)s_slot[k] * Dp + cc;
+        if (!skip) { wv = ld_f4(w + o); if (upd.kind != PS_UPD_SIMPLE) { m1 = ld_f4(s1 + o); m2 = ld_f4(s2 + o); } }
+      }
+    }
+    /* peer-memory exchange: senders pre-reduce, cnt packs {entries << 24 | occurrences} */
+    const uint32_t kc = k < total ? s_cnt[k] : 1u;
+    const uint32_t n_occ = packed_cnt ? (kc & 0xFFFFFFu) : kc;
+    float* arow = acc + (size_t)(k < total ? s_uidx[k] : 0u) * Dp + cc;
+    const float4 S = (active && !skip) ? __ldcg(reinterpret_cast<const float4*>(arow)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    bool do_upd = !skip;
+    if (upd.kind == PS_UPD_FTRL) {                  /* FtrlUpdater.java:52: `if (dw.get(0) == 0) return w` */
+      const float S0 = __shfl_sync(0xffffffffu, S.x, lane - (lane % TPK));
+      do_upd = do_upd && emb_geff(S0, n_occ, calls) != 0.0f;
+    }
+    if (!active) continue;
+    if (!skip) {
       if (do_upd) {
-        const size_t o = (size_t)slot * Dp + cc;
-        float4 wv = ld_f4(w + o), m1 = make_float4(0.f, 0.f, 0.f, 0.f), m2 = m1;
-        if (upd.kind != PS_UPD_SIMPLE) { m1 = ld_f4(s1 + o); m2 = ld_f4(s2 + o); }
-        apply_elem(upd, wv.x, m1.x, m2.x, emb_geff(S[c].x, n_occ, calls));
-        apply_elem(upd, wv.y, m1.y, m2.y, emb_geff(S[c].y, n_occ, calls));
-        apply_elem(upd, wv.z, m1.z, m2.z, emb_geff(S[c].z, n_occ, calls));
-        apply_elem(upd, wv.w, m1.w, m2.w, emb_geff(S[c].w, n_occ, calls));
+        apply_elem(upd, wv.x, m1.x, m2.x, emb_geff(S.x, n_occ, calls));
+        apply_elem(upd, wv.y, m1.y, m2.y, emb_geff(S.y, n_occ, calls));
+        apply_elem(upd, wv.z, m1.z, m2.z, emb_geff(S.z, n_occ, calls));
+        apply_elem(upd, wv.w, m1.w, m2.w, emb_geff(S.w, n_occ, calls));
         st_f4(w + o, wv);
         if (upd.kind != PS_UPD_SIMPLE) { st_f4(s1 + o, m1); st_f4(s2 + o, m2); }
       }
-      st_f4(acc + (size_t)uidx * Dp + cc, make_float4(0.f, 0.f, 0.f, 0.f));
+      st_f4(arow, make_float4(0.f, 0.f, 0.f, 0.f));
     }
+    if (part == 0) slots[s_slot[k]].cnt = 0u;      /* KVStore.clear (also after the early exit: the batch is forgotten) */
   }
-  if (part == 0) slots[slot].cnt = 0u;             /* KVStore.clear (also after the early exit: the batch is forgotten) */
 }
 
 __global__ void emb_clear_batch_kernel(EmbSlot* __restrict__ slots, const int32_t* __restrict__ lk_slot, int L) {
@@ -403,8 +488,8 @@ static void launch_gather(EmbTable& t, float* out, int ldo, int N, int F, const 
   const long L = (long)N * F;
   const bool aligned = (t.D % 4 == 0) && (ldo % 4 == 0) && ((uintptr_t)out % 16 == 0);
   const int grid = ceil_div(L * TPL + (X ? (long)N * Xn : 0), 256);
-  if (aligned) emb_gather_kernel<TPL, true><<<grid, 256, 0, t.ctx->stream>>>(t.w, t.Dp, t.D, t.lk_slot, (int)L, F, out, ldo, X, Xn, xoff, N);
-  else emb_gather_kernel<TPL, false><<<grid, 256, 0, t.ctx->stream>>>(t.w, t.Dp, t.D, t.lk_slot, (int)L, F, out, ldo, X, Xn, xoff, N);
+  if (aligned) launch_pdl(t.ctx, emb_gather_kernel<TPL, true>, dim3(grid), dim3(256), t.w, t.Dp, t.D, t.lk_slot, (int)L, F, out, ldo, X, Xn, xoff, N);
+  else launch_pdl(t.ctx, emb_gather_kernel<TPL, false>, dim3(grid), dim3(256), t.w, t.Dp, t.D, t.lk_slot, (int)L, F, out, ldo, X, Xn, xoff, N);
 }
 
 void EmbTable::gather(float* out, int ldo, int N, int F_eff, const float* X, int Xn, int xoff) {
@@ -422,18 +507,33 @@ void EmbTable::gather(float* out, int ldo, int N, int F_eff, const float* X, int
   ctx->launches++;
 }
 
+template <int TPK>
+static void launch_update(EmbTable& t, int N, int F, int calls, const int* skip, int packed_cnt) {
+  const long L = (long)N * F;
+  launch_pdl(t.ctx, emb_update_kernel<TPK>, dim3(ceil_div(L, 256)), dim3(256), t.slots, t.w, t.s1, t.s2, t.Dp, t.D, (const int32_t*)t.lk_slot, N, F,
+             t.acc, t.upd, calls, skip, packed_cnt);
+}
+
 template <int TPL, int CPL>
 static void launch_scatter(EmbTable& t, const float* delta, int ldd, const float* act, int lda, int N, int F, int calls, const int* skip,
                            const P2PState* p2p) {
+  constexpr int PASSES = TPL >= 4 ? 4 : TPL;     /* tile = PASSES * 256 / TPL consecutive lookups of one field: 256 (D <= 16), 128 (D = 64) */
   const long L = (long)N * F;
   const bool aligned = (t.D % 4 == 0) && (ldd % 4 == 0) && (lda % 4 == 0) && ((uintptr_t)delta % 16 == 0) && ((uintptr_t)act % 16 == 0);
-  const int grid = ceil_div(L * TPL, 256);
+  const int grid = ceil_div(L, PASSES * (256 / TPL));
   if (aligned)
-    emb_scatter_kernel<TPL, CPL, true><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.Dp, t.D, t.lk_slot, N, F, delta, ldd, act, lda, t.acc, skip, p2p);
+    emb_scatter_kernel<TPL, CPL, PASSES, true><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.Dp, t.D, t.lk_slot, N, F, delta, ldd, act, lda, t.acc, skip, p2p);
   else
-    emb_scatter_kernel<TPL, CPL, false><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.Dp, t.D, t.lk_slot, N, F, delta, ldd, act, lda, t.acc, skip, p2p);
+    emb_scatter_kernel<TPL, CPL, PASSES, false><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.Dp, t.D, t.lk_slot, N, F, delta, ldd, act, lda, t.acc, skip, p2p);
   PS_LAUNCH_CHECK();
-  emb_update_kernel<TPL, CPL><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.w, t.s1, t.s2, t.Dp, t.D, t.lk_slot, N, F, t.acc, t.upd, calls, skip, p2p != nullptr ? 1 : 0);
+  switch (t.tpl) {                              /* the update spends 4 floats per lane whatever the scatter's chunking was */
+    case 1: launch_update<1>(t, N, F, calls, skip, p2p != nullptr ? 1 : 0); break;
+    case 2: launch_update<2>(t, N, F, calls, skip, p2p != nullptr ? 1 : 0); break;
+    case 4: launch_update<4>(t, N, F, calls, skip, p2p != nullptr ? 1 : 0); break;
+    case 8: launch_update<8>(t, N, F, calls, skip, p2p != nullptr ? 1 : 0); break;
+    case 16: launch_update<16>(t, N, F, calls, skip, p2p != nullptr ? 1 : 0); break;
+    default: launch_update<32>(t, N, F, calls, skip, p2p != nullptr ? 1 : 0); break;
+  }
   t.ctx->launches += 2;
 }
 

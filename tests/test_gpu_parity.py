@@ -101,7 +101,9 @@ def test_embedding_forward_bit_exact(ps, ctx, F, D, N, V, dist):
 
 
 @pytest.mark.parametrize("opt", ["adam", "ftrl"])
-@pytest.mark.parametrize("F,D,N,V,calls", [(23, 16, 512, 3000, 2), (23, 10, 200, 500, 2), (4, 32, 256, 40, 1), (23, 16, 1024, 200000, 2)])
+@pytest.mark.parametrize("F,D,N,V,calls", [(23, 16, 512, 3000, 2), (23, 10, 200, 500, 2), (4, 32, 256, 40, 1), (23, 16, 1024, 200000, 2),
+                                           # hot keys (thousands of occurrences of one row: the per-block shared-memory pre-sum), ragged dims
+                                           (3, 64, 2048, 7, 2), (23, 16, 4096, 1000, 2), (5, 10, 700, 11, 1), (2, 128, 300, 4, 2), (1, 4, 5000, 2, 2)])
 def test_embedding_backward_update(ps, ctx, opt, F, D, N, V, calls):
     spec = ps.UpdaterSpec.adam() if opt == "adam" else ps.UpdaterSpec.ftrl()
     emb = ps.EmbeddingLayer(ctx, F, D, capacity=max(1024, 4 * N * F), updater=spec)
