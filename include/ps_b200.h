@@ -72,6 +72,11 @@ int ps_abi_version(void);
 int ps_ctx_create(int device, uint64_t seed, ps_ctx** out);
 int ps_ctx_destroy(ps_ctx* ctx);
 int ps_ctx_set_fc_precision(ps_ctx* ctx, int mode);   /* PS_FC_FP32 | PS_FC_TF32 | PS_FC_TF32X3 */
+/* the sparse (embedding-row) update: 0 = fast forms (reciprocal multiplications, approximate quotient / root; post-update
+ * rows within 1e-6 relative of the exact forms), 1 = the IEEE operation sequence of AdamUpdater.java:57-70 /
+ * FtrlUpdater.java:51-76 (bit-exact given the gradient).  Dense parameters always use the exact forms.  Default 0
+ * (PS_EXACT_UPDATERS=1 in the environment flips it).  Takes effect for graphs captured afterwards: call before the first step. */
+int ps_ctx_set_exact_updaters(ps_ctx* ctx, int on);
 int ps_ctx_synchronize(ps_ctx* ctx);
 int ps_ctx_launch_count(ps_ctx* ctx, int64_t* out);   /* kernels this library launched so far */
 int ps_ctx_device_info(ps_ctx* ctx, char* name, int cap, int* sms, int* cc_major, int* cc_minor);
@@ -116,6 +121,28 @@ int ps_emb_get_rows(ps_emb* emb, const int32_t* fields, const int64_t* ids, int 
  * replace != 0 overwrites, replace == 0 is insert-if-absent and returns the winner in w.   */
 int ps_emb_put_rows(ps_emb* emb, const int32_t* fields, const int64_t* ids, int n, float* w, int replace);
 int ps_emb_size(ps_emb* emb, int64_t* rows);
+
+/* ---- layer.FcLayer as a standalone operator ---------------------------------------
+ * For callers that walk the reference's layer list themselves (Model.train's forward / backward loops, DNN.java:44-68)
+ * instead of handing the whole step to ps_model_train_step.  Matrices are jblas column-major: A_prev is in x N, A and
+ * delta are out x N, delta_prev is in x N.  Weights "<name>.weights" / bias "<name>.bias" are created on first use with
+ * the Xavier bounds of FcLayer.java:39,46 (FcLayer.pullWeights, :112-115); `act` is PS_ACT_NONE | RELU | SIGMOID
+ * (FcLayer.setActivation incl. null, WideDeepNN.java:128); upd NULL = the "default" Adam of DNN.java:95.
+ *   ps_fc_forward   FcLayer.forward  (FcLayer.java:74-91):  A = act(W * A_prev + b 1^T)
+ *   ps_fc_backward  FcLayer.backward (FcLayer.java:93-110): delta <- act'(delta); db = rowMeans(delta), dW = delta * A_prev^T / N
+ *                   are kept on the device as the pending KVStore.sum; delta_prev = W^T * delta is returned (may be NULL)
+ *   ps_fc_gradients the pending dW (out x in) and db (out) as KVStore.sum received them
+ *   ps_fc_update    KVStore.update(updaters) + clear() for this layer's two keys (KVStore.java:240-277)
+ *   ps_fc_get / ps_fc_put  KVStore.get / put of "<name>.weights" (which = 0, out x in) or "<name>.bias" (which = 1)      */
+typedef struct ps_fc ps_fc;
+int ps_fc_create(ps_ctx* ctx, const char* name, int in, int out, int act, const ps_updater_spec* upd, int max_batch, ps_fc** out_fc);
+int ps_fc_destroy(ps_fc* fc);
+int ps_fc_forward(ps_fc* fc, const float* A_prev, int N, float* A);
+int ps_fc_backward(ps_fc* fc, const float* delta, int N, float* delta_prev);
+int ps_fc_gradients(ps_fc* fc, float* dW, float* db);
+int ps_fc_update(ps_fc* fc);
+int ps_fc_get(ps_fc* fc, int which, float* out, int cap, int* n);
+int ps_fc_put(ps_fc* fc, int which, const float* in, int n);
 
 /* ---- model.* driven by train.Trainer (thread = 1) --------------------------------
  * DNN.buildModel / WideDeepNN.buildModel / FullConnectedNN.buildModel with the reference's

@@ -53,6 +53,7 @@ SYMBOLS = {
     "ps_ctx_create": (_i, [_i, C.c_uint64, _pp]),
     "ps_ctx_destroy": (_i, [_vp]),
     "ps_ctx_set_fc_precision": (_i, [_vp, _i]),
+    "ps_ctx_set_exact_updaters": (_i, [_vp, _i]),
     "ps_ctx_synchronize": (_i, [_vp]),
     "ps_ctx_launch_count": (_i, [_vp, C.POINTER(_i64)]),
     "ps_ctx_device_info": (_i, [_vp, C.c_char_p, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
@@ -102,6 +103,14 @@ SYMBOLS = {
     "ps_model_p2p_connect": (_i, [_vp, _vp]),
     "ps_model_p2p_step_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _i]),
     "ps_model_p2p_overflowed": (_i, [_vp, C.POINTER(_i)]),
+    "ps_fc_create": (_i, [_vp, C.c_char_p, _i, _i, _i, C.POINTER(UpdaterSpec), _i, _pp]),
+    "ps_fc_destroy": (_i, [_vp]),
+    "ps_fc_forward": (_i, [_vp, _vp, _i, _vp]),
+    "ps_fc_backward": (_i, [_vp, _vp, _i, _vp]),
+    "ps_fc_gradients": (_i, [_vp, _vp, _vp]),
+    "ps_fc_update": (_i, [_vp]),
+    "ps_fc_get": (_i, [_vp, _i, _vp, _i, C.POINTER(_i)]),
+    "ps_fc_put": (_i, [_vp, _i, _vp, _i]),
     "ps_libsvm_parse_line": (_i, [C.c_char_p, C.c_size_t, _i, _i, _i64, _vp, _vp, _vp, _vp, C.POINTER(_i)]),
     "ps_reader_open": (_i, [C.c_char_p, _i, _i, _i64, _i, _i, _i, _i, _pp]),
     "ps_reader_next": (_i, [_vp, _vp, _vp, _vp, _vp, C.POINTER(_i)]),
@@ -215,6 +224,55 @@ class LibsvmReader:
             self.h = None
 
 
+PS_ACT_NONE, PS_ACT_RELU, PS_ACT_SIGMOID = 0, 1, 2
+
+
+class FcLayer:
+    """layer.FcLayer as a standalone operator (FcLayer.java:34-115).  Matrices as numpy (N, features) arrays = jblas features x N."""
+
+    def __init__(self, ctx, name, in_dims, out_dims, act=PS_ACT_RELU, updater=None, max_batch=1024):
+        self.in_dims, self.out_dims = in_dims, out_dims
+        self.h = C.c_void_p()
+        check(lib().ps_fc_create(ctx.h, name.encode(), in_dims, out_dims, act, C.byref(updater) if updater is not None else None, max_batch, C.byref(self.h)))
+
+    def forward(self, A_prev):
+        A_prev = _c(A_prev, np.float32)
+        out = np.zeros((A_prev.shape[0], self.out_dims), np.float32)
+        check(lib().ps_fc_forward(self.h, _p(A_prev), A_prev.shape[0], _p(out)))
+        return out
+
+    def backward(self, delta):
+        delta = _c(delta, np.float32)
+        dprev = np.zeros((delta.shape[0], self.in_dims), np.float32)
+        check(lib().ps_fc_backward(self.h, _p(delta), delta.shape[0], _p(dprev)))
+        return dprev
+
+    def gradients(self):
+        dW = np.zeros(self.out_dims * self.in_dims, np.float32)
+        db = np.zeros(self.out_dims, np.float32)
+        check(lib().ps_fc_gradients(self.h, _p(dW), _p(db)))
+        return dW.reshape(self.in_dims, self.out_dims).T.copy(), db     # (out, in)
+
+    def update(self):
+        check(lib().ps_fc_update(self.h))
+
+    def get(self, which):
+        n = self.out_dims * (self.in_dims if which == 0 else 1)
+        out = np.zeros(n, np.float32)
+        got = C.c_int()
+        check(lib().ps_fc_get(self.h, which, _p(out), n, C.byref(got)))
+        return out.reshape(self.in_dims, self.out_dims).T.copy() if which == 0 else out
+
+    def put(self, which, value):
+        v = _c(np.asarray(value, np.float32).T if which == 0 else value, np.float32).reshape(-1)
+        check(lib().ps_fc_put(self.h, which, _p(v), v.size))
+
+    def close(self):
+        if self.h:
+            lib().ps_fc_destroy(self.h)
+            self.h = None
+
+
 class Context:
     """store.KVStore.ins() + the device it lives on."""
 
@@ -229,6 +287,9 @@ class Context:
 
     def set_fc_precision(self, mode):
         check(lib().ps_ctx_set_fc_precision(self.h, mode))
+
+    def set_exact_updaters(self, on):
+        check(lib().ps_ctx_set_exact_updaters(self.h, 1 if on else 0))
 
     def synchronize(self):
         check(lib().ps_ctx_synchronize(self.h))

@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 
+#include "fcop.cuh"
 #include "ingest.cuh"
 #include "model.cuh"
 
@@ -21,6 +22,7 @@ using namespace psb;
 
 struct ps_ctx { Ctx c; };
 struct ps_model { Model m; };
+struct ps_fc { FcOp op; };
 struct ps_reader { std::unique_ptr<LibsvmReader> r; };
 struct ps_emb {
   Ctx* ctx = nullptr;
@@ -62,6 +64,10 @@ int ps_ctx_create(int device, uint64_t seed, ps_ctx** out) {
   c->c.prio_side = (pe && pe[0] == '0') ? 0 : prio_lo;
   const char* pd = std::getenv("PS_PDL");
   c->c.pdl = (pd && pd[0] == '0') ? 0 : 1;
+  const char* xe = std::getenv("PS_EXACT_UPDATERS");
+  c->c.exact_updaters = (xe && xe[0] == '1') ? 1 : 0;
+  const char* hm = std::getenv("PS_HOT_MIN");
+  if (hm && hm[0]) { const long v = std::atol(hm); c->c.hot_min = v <= 0 ? 0xFFFFFFFFu : (unsigned)v; }
   PS_CUDA(cudaStreamCreateWithPriority(&c->c.stream, cudaStreamNonBlocking, c->c.prio_main));
   PS_CUDA(cudaStreamCreateWithFlags(&c->c.copy_stream, cudaStreamNonBlocking));
   *out = c;
@@ -80,6 +86,12 @@ int ps_ctx_set_fc_precision(ps_ctx* ctx, int mode) {
   PS_TRY
   PS_REQUIRE(ctx && (mode == PS_FC_FP32 || mode == PS_FC_TF32 || mode == PS_FC_TF32X3), PS_ERR_ARG, "ps_ctx_set_fc_precision: bad mode");
   ctx->c.fc_precision = mode;
+  PS_CATCH
+}
+int ps_ctx_set_exact_updaters(ps_ctx* ctx, int on) {
+  PS_TRY
+  PS_REQUIRE(ctx != nullptr, PS_ERR_ARG, "ps_ctx_set_exact_updaters: null context");
+  ctx->c.exact_updaters = on ? 1 : 0;
   PS_CATCH
 }
 int ps_ctx_synchronize(ps_ctx* ctx) {
@@ -550,6 +562,63 @@ int ps_model_p2p_overflowed(ps_model* m, int* out) {
 }
 
 /* ---- test hook ---- */
+/* ---- layer.FcLayer standalone ---- */
+int ps_fc_create(ps_ctx* ctx, const char* name, int in, int out, int act, const ps_updater_spec* upd, int max_batch, ps_fc** out_fc) {
+  PS_TRY
+  PS_REQUIRE(ctx && name && out_fc, PS_ERR_ARG, "ps_fc_create: null argument");
+  ps_updater_spec u;
+  if (upd) u = *upd;
+  else { u.kind = PS_UPD_ADAM; u.p[0] = (float)0.005; u.p[1] = (float)0.9; u.p[2] = (float)0.999; u.p[3] = (float)std::pow(10.0, -8); }
+  std::unique_ptr<ps_fc> h(new ps_fc);
+  h->op.create(&ctx->c, name, in, out, act, u, max_batch);
+  *out_fc = h.release();
+  PS_CATCH
+}
+int ps_fc_destroy(ps_fc* fc) {
+  PS_TRY
+  if (fc) { fc->op.destroy(); delete fc; }
+  PS_CATCH
+}
+int ps_fc_forward(ps_fc* fc, const float* A_prev, int N, float* A) {
+  PS_TRY
+  PS_REQUIRE(fc != nullptr, PS_ERR_ARG, "ps_fc_forward: null layer");
+  fc->op.forward(A_prev, N, A);
+  PS_CATCH
+}
+int ps_fc_backward(ps_fc* fc, const float* delta, int N, float* delta_prev) {
+  PS_TRY
+  PS_REQUIRE(fc != nullptr, PS_ERR_ARG, "ps_fc_backward: null layer");
+  fc->op.backward(delta, N, delta_prev);
+  PS_CATCH
+}
+int ps_fc_gradients(ps_fc* fc, float* dW, float* db) {
+  PS_TRY
+  PS_REQUIRE(fc != nullptr, PS_ERR_ARG, "ps_fc_gradients: null layer");
+  fc->op.gradients(dW, db);
+  PS_CATCH
+}
+int ps_fc_update(ps_fc* fc) {
+  PS_TRY
+  PS_REQUIRE(fc != nullptr, PS_ERR_ARG, "ps_fc_update: null layer");
+  fc->op.update();
+  PS_CATCH
+}
+int ps_fc_get(ps_fc* fc, int which, float* out, int cap, int* n) {
+  PS_TRY
+  PS_REQUIRE(fc != nullptr && (which == 0 || which == 1), PS_ERR_ARG, "ps_fc_get: bad argument");
+  std::vector<float> v;
+  fc->op.get(which, v);
+  if (n) *n = (int)v.size();
+  if (out && cap >= (int)v.size()) std::memcpy(out, v.data(), sizeof(float) * v.size());
+  PS_CATCH
+}
+int ps_fc_put(ps_fc* fc, int which, const float* in, int n) {
+  PS_TRY
+  PS_REQUIRE(fc != nullptr && in != nullptr && (which == 0 || which == 1), PS_ERR_ARG, "ps_fc_put: bad argument");
+  fc->op.put(which, in, n);
+  PS_CATCH
+}
+
 /* ---- libsvm ingest ---- */
 int ps_libsvm_parse_line(const char* line, size_t len, int F, int Xn, int64_t wide_size, int64_t* E, float* X, int64_t* W, float* Y, int* status) {
   PS_TRY

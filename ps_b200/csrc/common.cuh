@@ -56,6 +56,8 @@ struct Ctx {
   int fc_precision = PS_FC_FP32;
   int prio_main = 0, prio_side = 0; /* stream priorities of the critical chain / the side branches */
   int pdl = 1;                     /* programmatic dependent launch for producer -> consumer kernel pairs (PS_PDL=0 disables) */
+  int exact_updaters = 0;          /* sparse update with the IEEE divisions / roots of the Java code (PS_EXACT_UPDATERS=1) instead of the fast forms */
+  unsigned hot_min = 8;            /* occurrences in a batch from which the scatter pre-sums a key per block (PS_HOT_MIN; 0 = never) */
   long launches = 0;               /* kernels launched by this library (bench gpu_launches) */
 };
 
@@ -108,6 +110,9 @@ __device__ __forceinline__ void st_f4_stream(float* p, float4 v) {
 /* programmatic dependent launch (sm_90+): see launch_pdl */
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+/* fire-and-forget 32-bit reductions (no value comes back: the issuing thread does not wait for L2) */
+__device__ __forceinline__ void red_add_u32(uint32_t* p, uint32_t v) { asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void red_max_u32(uint32_t* p, uint32_t v) { asm volatile("red.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 /* 128-bit vector reduction into global memory (sm_90+): one L2 atomic transaction per 16 B */
 __device__ __forceinline__ void red_add_f4(float* p, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");

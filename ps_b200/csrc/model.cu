@@ -171,7 +171,7 @@ void Model::run_step(const int64_t* E, const float* X, const int64_t* W, const f
     phase_names = ev_names;
     return;
   }
-  const auto key = std::make_tuple((const void*)E, (const void*)X, (const void*)W, (const void*)Y, N, (train ? 1 : 0) | (profile ? 2 : 0) | (mode << 2),
+  const auto key = std::make_tuple((const void*)E, (const void*)X, (const void*)W, (const void*)Y, N, (train ? 1 : 0) | (profile ? 2 : 0) | (mode << 2) | (ctx->exact_updaters << 6),
                                    (const void*)publish_to, ctx->fc_precision);
   auto it = graphs.find(key);
   if (it == graphs.end()) {

@@ -53,71 +53,113 @@ __device__ __forceinline__ int emb_find_or_insert(EmbSlot* slots, uint32_t C, un
   return -1;
 }
 
-/* One thread per lookup l = n*F + j.  Row creation follows KVStore.create (KVStore.java:168-190):
- * the creating thread draws the row from the deterministic initialiser of ps_spec.h; optimiser
- * state stays at the zero the arena was allocated with (AdamUpdater.initMandV, :76-84).        */
-/* F == 0: `ids` already holds packed keys (the owner side of the sharded exchange) */
+/* find-or-insert that starts from an already loaded first probe (`k0` = the key found in the home bucket) */
+__device__ __forceinline__ int emb_find_or_insert_from(EmbSlot* slots, uint32_t C, unsigned long long key, uint32_t slot, unsigned long long k,
+                                                       bool* inserted) {
+  const int limit = C < (uint32_t)kProbeLimit ? (int)C : kProbeLimit;
+  *inserted = false;
+  for (int p = 0; p < limit; ++p) {
+    if (p > 0) k = *reinterpret_cast<const volatile unsigned long long*>(&slots[slot].key);
+    if (k == key) return (int)slot;
+    if (k == PS_KEY_EMPTY) {
+      const unsigned long long old = atomicCAS(&slots[slot].key, (unsigned long long)PS_KEY_EMPTY, key);
+      if (old == PS_KEY_EMPTY) { *inserted = true; return (int)slot; }
+      if (old == key) return (int)slot;
+    }
+    slot = slot + 1 == C ? 0 : slot + 1;
+  }
+  return -1;
+}
+
+/* Key resolution of one batch.  Row creation follows KVStore.create (KVStore.java:168-190): the creating thread draws the
+ * row from the deterministic initialiser of ps_spec.h; optimiser state stays at the zero the arena was allocated with
+ * (AdamUpdater.initMandV, :76-84).
+ *
+ * Work decomposition: a block owns 32*SG consecutive samples and ALL F fields of them; a warp task is (field j, 32
+ * consecutive samples), so
+ *   - the 32 lanes of a warp probe the SAME field: duplicates of a hot key (a low-cardinality field) meet in one warp
+ *     and are counted with one L2 reduction per warp, not 32;
+ *   - the 8 warps of a block read neighbouring fields of the same samples at the same time: every 32 B sector of the
+ *     [N][F] id matrix is fetched from HBM once;
+ *   - lk_slot is FIELD-major ([F][N], index t = j*N + n): a warp stores 128 contiguous bytes, and the backward kernels,
+ *     which walk the same order, read it back coalesced.
+ * Up to 4 tasks of a warp are in flight at once (ids, then the home buckets, are loaded for all of them before any is used).
+ * Per-batch bookkeeping in the slot record needs no returned atomic: `cnt += occurrences` and `first = max(first, ~t)`
+ * are fire-and-forget reductions; the lookup with the smallest t owns the key's accumulator row (acc[t]).
+ * F == 0: `ids` already holds packed keys (the owner side of the sharded exchange); p2p: they come from this step's mailbox. */
 template <class IdT>
 __global__ void __launch_bounds__(256) emb_probe_kernel(EmbSlot* __restrict__ slots, uint32_t C, float* __restrict__ w, int Dp, int D,
-                                                        const IdT* __restrict__ ids, int L, int F, uint64_t seed, float maxv,
+                                                        const IdT* __restrict__ ids, int N, int F, int SG, uint64_t seed, float maxv,
                                                         int32_t* __restrict__ lk_slot,
                                                         uint32_t* __restrict__ counters, const P2PState* __restrict__ p2p) {
-  /* field-major work order (t = j*N + n): the 32 lanes of a warp probe the SAME field for consecutive
-   * samples, so a hot key (a low-cardinality field) is counted with one L2 atomic per warp, not 32 */
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
+  constexpr int R = 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   pdl_launch_dependents();                     /* the gather's blocks may be scheduled; they wait for this grid before reading */
-  int slot = -1;
-  bool first = false;
-  uint32_t add = 1u;
-  if (t < L) {
-    int l = t;
-    unsigned long long key = PS_KEY_EMPTY;
-    if (p2p != nullptr) {                      /* owner side of the peer-memory exchange: this step's keys_in mailbox */
-      const int src = t / p2p->cap, idx = t - src * p2p->cap;
-      if (idx < reinterpret_cast<const int32_t*>(p2p_region(p2p, p2p->me, p2p->off_counts))[src]) {
-        /* entries are {key, occurrences at the sender}: senders de-duplicate their batch (PSRouterClient sends a key once) */
-        const ulonglong2 e = reinterpret_cast<const ulonglong2*>(p2p_region(p2p, p2p->me, p2p->off_keys))[t];
-        key = e.x;
-        add = (uint32_t)e.y + (1u << 24);       /* low 24 bits: occurrences; high 8 bits: entries (= arrivals the update waits for) */
-      }
-    } else if (F > 0) {
-      const int N = L / F; const int j = t / N; l = (t - j * N) * F + j;
-      key = ps_pack_key((uint32_t)(l % F), (uint64_t)(int64_t)ids[l]);
-    } else {
-      key = (unsigned long long)ids[l];
-    }
-    if (key != PS_KEY_EMPTY) {                 /* EMPTY marks padding in the fixed-capacity sharded exchange */
-      bool inserted;
-      slot = emb_find_or_insert(slots, C, key, &inserted);
-      if (slot < 0) counters[1] = 1u;
-      else if (inserted) {
-        float* row = w + (size_t)slot * Dp;
-        for (int d = 0; d < D; ++d) row[d] = ps_init_value(seed, key, (uint32_t)d, maxv);
-        atomicAdd(reinterpret_cast<unsigned long long*>(counters + 2), 1ull);
-      }
-    }
-    lk_slot[l] = slot;
-  }
-  /* warp-aggregated occurrence count: lanes holding the same slot add once */
-  const unsigned peers = __match_any_sync(0xffffffffu, slot >= 0 ? slot : (-1 - lane));
-  /* every lookup counts 1 unless it is a pre-counted entry of the peer-memory exchange (a reduction over a partial
-   * mask runs once per distinct key in the warp: not worth it for a popcount) */
-  const uint32_t total_add = p2p == nullptr ? (uint32_t)__popc(peers) : __reduce_add_sync(peers, add);
-  if (slot >= 0 && (__ffs(peers) - 1) == lane) first = atomicAdd(&slots[slot].cnt, total_add) == 0u;
-  /* the key's accumulator row for this batch is the one indexed by the work index of its FIRST lookup: no
-   * numbering pass, nothing to reset (the row is zeroed again by the lookup that consumes it)            */
-  if (first) slots[slot].uidx = (uint32_t)t;
-  /* statistics only (StepStatus.n_unique): one fire-and-forget reduction per block on a monotonic counter */
-  __shared__ uint32_t warp_firsts[8];
-  const unsigned firsts = __ballot_sync(0xffffffffu, first);
-  if (lane == 0) warp_firsts[threadIdx.x >> 5] = (uint32_t)__popc(firsts);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t total = 0;
+  const int Fe = F > 0 ? F : 1;
+  const int tasks = Fe * SG;
+  const long n0 = (long)blockIdx.x * (32 * SG);
+  for (int task0 = warp; task0 < tasks; task0 += 8 * R) {
+    unsigned long long key[R], k0[R];
+    uint32_t bucket[R], add[R];
+    long t[R];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) total += warp_firsts[i];
-    if (total) atomicAdd(&counters[0], total);
+    for (int r = 0; r < R; ++r) {
+      const int task = task0 + 8 * r;
+      key[r] = PS_KEY_EMPTY; add[r] = 1u; t[r] = -1;
+      if (task < tasks) {
+        const int j = task % Fe, sg = task / Fe;
+        const long n = n0 + sg * 32 + lane;
+        if (n < N) {
+          t[r] = (long)j * N + n;
+          if (p2p != nullptr) {                  /* owner side of the peer-memory exchange: this step's keys_in mailbox */
+            const int src = (int)(n / p2p->cap), idx = (int)(n - (long)src * p2p->cap);
+            if (idx < reinterpret_cast<const int32_t*>(p2p_region(p2p, p2p->me, p2p->off_counts))[src]) {
+              /* entries are {key, occurrences at the sender}: senders de-duplicate their batch (PSRouterClient sends a key once) */
+              const ulonglong2 e = reinterpret_cast<const ulonglong2*>(p2p_region(p2p, p2p->me, p2p->off_keys))[n];
+              key[r] = e.x;
+              add[r] = (uint32_t)e.y + (1u << 24);   /* low 24 bits: occurrences; high 8 bits: entries */
+            }
+          } else if (F > 0) {
+            key[r] = ps_pack_key((uint32_t)j, (uint64_t)(int64_t)ids[n * F + j]);
+          } else {
+            key[r] = (unsigned long long)ids[n];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      bucket[r] = 0u; k0[r] = PS_KEY_EMPTY;
+      if (key[r] != PS_KEY_EMPTY) {              /* EMPTY marks padding in the fixed-capacity sharded exchange */
+        bucket[r] = ps_bucket_of(key[r], C);
+        k0[r] = *reinterpret_cast<const volatile unsigned long long*>(&slots[bucket[r]].key);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (task0 + 8 * r >= tasks) break;         /* warp-uniform */
+      int slot = -1;
+      if (key[r] != PS_KEY_EMPTY) {
+        bool inserted;
+        slot = emb_find_or_insert_from(slots, C, key[r], bucket[r], k0[r], &inserted);
+        if (slot < 0) counters[1] = 1u;
+        else if (inserted) {
+          float* row = w + (size_t)slot * Dp;
+          for (int d = 0; d < D; ++d) row[d] = ps_init_value(seed, key[r], (uint32_t)d, maxv);
+          atomicAdd(reinterpret_cast<unsigned long long*>(counters + 2), 1ull);
+        }
+      }
+      if (t[r] >= 0) lk_slot[t[r]] = slot;
+      /* warp-aggregated bookkeeping: lanes holding the same slot reduce once (the lowest lane has the smallest t) */
+      const unsigned peers = __match_any_sync(0xffffffffu, slot >= 0 ? slot : (-1 - lane));
+      /* every lookup counts 1 unless it is a pre-counted entry of the peer-memory exchange (a reduction over a partial
+       * mask runs once per distinct key in the warp: not worth it for a popcount) */
+      const uint32_t total_add = p2p == nullptr ? (uint32_t)__popc(peers) : __reduce_add_sync(peers, add[r]);
+      if (slot >= 0 && (__ffs(peers) - 1) == lane) {
+        red_add_u32(&slots[slot].cnt, total_add);
+        red_max_u32(&slots[slot].first, ~(uint32_t)t[r]);
+      }
+    }
   }
 }
 
@@ -137,9 +179,9 @@ __global__ void __launch_bounds__(256) emb_gather_kernel(const float* __restrict
   }
   const int l = (int)(g / TPL), part = (int)(g % TPL);
   if (part * 4 >= D) return;
-  const int slot = lk_slot[l];
-  if (slot < 0) return;
   const int n = l / F, j = l - n * F;
+  const int slot = lk_slot[(size_t)j * N + n];   /* field-major (see emb_probe_kernel) */
+  if (slot < 0) return;
   float4 v = __ldg(reinterpret_cast<const float4*>(w + (size_t)slot * Dp + part * 4));
   v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
   float* o = out + (size_t)n * ldo + j * D + part * 4;
@@ -162,49 +204,62 @@ __device__ __forceinline__ float4 shfl_f4(float4 v, int src) {
 /* Effective gradient the reference ends up applying for a key with n occurrences and S = sum of
  * its per-occurrence gradients.  calls == 2 (what DNN/WideDeepNN do): pass 1
  * stores S/n by reference in KVStore.sum, pass 2 adds the n gradients again, divides by 2n, the
- * aliased sum doubles it and KVStore.update halves it: ((S/n) + S) / (2n).  calls == 1: S/n.  */
-__device__ __forceinline__ float emb_geff(float S, uint32_t n, int calls) {
+ * aliased sum doubles it and KVStore.update halves it: ((S/n) + S) / (2n).  calls == 1: S/n.
+ * EXACT: the two IEEE divisions of the Java code.  Otherwise: multiplications by 1/n and 1/(2n), rounded once per key
+ * (<= 1.5 ulp off the exact quotient each).                                                      */
+struct GeffScale { float n, n2, rn, rn2; int calls; };
+template <bool EXACT>
+__device__ __forceinline__ GeffScale make_geff(uint32_t n, int calls) {
+  GeffScale g;
+  g.n = (float)n; g.n2 = (float)(2u * n); g.calls = calls;
+  g.rn = EXACT ? 0.f : __frcp_rn(g.n);
+  g.rn2 = 0.5f * g.rn;
+  return g;
+}
+template <bool EXACT>
+__device__ __forceinline__ float emb_geff(float S, const GeffScale& g) {
   if (S == 0.0f) return S;
-  const float q = __fdiv_rn(S, (float)n);
-  if (calls == 1) return q;
-  return __fdiv_rn(__fadd_rn(q, S), (float)(2u * n));
+  const float q = EXACT ? __fdiv_rn(S, g.n) : __fmul_rn(S, g.rn);
+  if (g.calls == 1) return q;
+  return EXACT ? __fdiv_rn(__fadd_rn(q, S), g.n2) : __fmul_rn(__fadd_rn(q, S), g.rn2);
 }
 
 /* Sparse backward = two launches on one stream, the second a programmatic dependent of the first:
- *   emb_scatter_kernel  g_k = delta[:,k] * (A[:,k] > 0)  (EmbeddingField.java:91-93).  A block owns a tile of consecutive
- *            work indices lk = j*N + n (field-major: ONE field, consecutive samples), so duplicates of a key meet in
- *            the same block.  Three levels of pre-summation keep a hot key (a low-cardinality field: thousands of
- *            occurrences of one row) from serialising in L2:  (1) reduce-by-key tree over the lanes of a warp that
- *            __match_any_sync groups;  (2) keys with >= kHotMin occurrences in the batch (the probe left the count in
- *            the slot record) are summed in a per-block shared-memory table and leave the block ONCE;  (3) everything
- *            else goes out as one red.global.add.v4.f32 per key and 16 B chunk into the key's accumulator row
- *            (L2-resident, indexed by the work index of the key's first lookup).
- *   emb_update_kernel   a block scans 256 work indices, compacts the ones that own an accumulator row (the key's
- *            first lookup) in shared memory and then spends ALL its lanes on them, 4 floats per lane: read S back
- *            from L2, form g_eff, run the Adam / Ftrl / SGD step on w, s1, s2 in place and reset the per-batch state
- *            (acc, cnt) — KVStore.sum + update + clear (KVStore.java:192-200,240-277).  Launched with programmatic
- *            stream serialisation: its scan, compaction and the w/s1/s2 loads of its first pass run while the scatter
- *            kernel drains; only the accumulator read sits behind griddepcontrol.wait.                              */
-static constexpr int kHotMin = 8;        /* occurrences in the batch from which a key is pre-summed per block */
-static constexpr int kHotEntries = 32;   /* per-block hot-key table (open addressing, 4 probes) */
+ *   emb_scatter_kernel  g_k = delta[:,k] * (A[:,k] > 0)  (EmbeddingField.java:91-93).  A block owns SB consecutive samples
+ *            and all F fields of them; a warp task is (field j, 32/TPL consecutive samples), so duplicates of a key meet
+ *            in the same warp and block, and the 8 warps read neighbouring columns of the same delta / act rows at the
+ *            same time (whole DRAM pages).  Three levels of pre-summation keep a hot key (a low-cardinality field:
+ *            thousands of occurrences of one row) from serialising in L2:  (1) reduce-by-key tree over the lanes of a
+ *            warp that __match_any_sync groups;  (2) keys frequent enough to recur inside one block's samples (the
+ *            probe left the batch count in the slot record; threshold = max(PS_HOT_MIN, 2N/SB)) are summed in a
+ *            per-block shared-memory table and leave the block ONCE;  (3) everything else goes out as one
+ *            red.global.add.v4.f32 per key and 16 B chunk into the key's accumulator row (L2-resident, indexed by the
+ *            work index of the key's first lookup).
+ *   emb_update_kernel   a warp scans 32 work indices, ballots the ones that own an accumulator row (the key's first
+ *            lookup) and deals their 16 B chunks over ALL its lanes: read S back from L2, form g_eff, run the Adam /
+ *            Ftrl / SGD step on w, s1, s2 in place and reset the per-batch state (acc, cnt, first) — KVStore.sum +
+ *            update + clear (KVStore.java:192-200,240-277).  Launched with programmatic stream serialisation: its
+ *            scan and the w/s1/s2 loads of its first round run while the scatter kernel drains; only the accumulator
+ *            read sits behind griddepcontrol.wait.                                                                  */
+static constexpr int kHotMin = 8;        /* default occurrences in the batch from which a key is pre-summed per block (PS_HOT_MIN) */
+static constexpr int kHotBits = 6;
+static constexpr int kHotEntries = 1 << kHotBits;   /* per-block hot-key table (open addressing, 4 probes) */
 
 template <int TPL, int CPL, int PASSES, bool ALIGNED>
 __global__ void __launch_bounds__(256) emb_scatter_kernel(const EmbSlot* __restrict__ slots, int Dp, int D, const int32_t* __restrict__ lk_slot, int N,
-                                                          int F, const float* __restrict__ delta, int ldd, const float* __restrict__ act, int lda,
+                                                          int F, int SB, const float* __restrict__ delta, int ldd, const float* __restrict__ act, int lda,
                                                           float* __restrict__ acc, const int* __restrict__ skip_flag,
-                                                          const P2PState* __restrict__ p2p) {
-  constexpr int GPW = 32 / TPL;                  /* lookups (lane groups) per warp */
-  constexpr int GPB = 256 / TPL;                 /* lookups per block and pass */
+                                                          const P2PState* __restrict__ p2p, uint32_t hot_min) {
+  constexpr int GPW = 32 / TPL;                  /* lookups (lane groups) per warp task */
   constexpr int ROWF = TPL * CPL * 4;            /* floats of a (padded) row */
   __shared__ float hot_acc[kHotEntries][ROWF];
   __shared__ int hot_slot[kHotEntries];
-  __shared__ uint32_t hot_uidx[kHotEntries];
+  __shared__ uint32_t hot_row[kHotEntries];
   pdl_launch_dependents();                       /* the update kernel may start its scan now (it waits before reading acc) */
   if (skip_flag != nullptr && *skip_flag != 0) return;   /* DNN.java:58-63 early exit: nothing is pushed */
   if (p2p != nullptr) delta = reinterpret_cast<const float*>(p2p_region(p2p, p2p->me, p2p->off_grads));   /* this step's grads_in mailbox */
-  const long L = (long)N * F;
-  const int lane = threadIdx.x & 31;
-  const int part = lane % TPL;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int part = lane % TPL, grp = lane / TPL;
   const int c0 = part * CPL * 4;                 /* first float of this lane's chunks */
   /* lanes holding the same `part` of their lookups: bits at multiples of TPL, shifted by part */
   unsigned part_lanes = 0u;
@@ -216,88 +271,99 @@ __global__ void __launch_bounds__(256) emb_scatter_kernel(const EmbSlot* __restr
   for (int i = threadIdx.x; i < kHotEntries * ROWF; i += 256) (&hot_acc[0][0])[i] = 0.f;
   __syncthreads();
 
-  /* ---- every load of the tile is issued before anything is consumed ---- */
-  int slot[PASSES];
-  float4 gk[PASSES][CPL];
+  /* the block's tile: SB consecutive samples x all F fields; a warp task = (field j, GPW consecutive samples); the 8 warps
+   * work on neighbouring fields of the same samples at the same time, so the rows of delta / act are read as whole
+   * DRAM pages although every lookup only needs D of their columns */
+  const int tasks = F * (SB / GPW);
+  /* persistent blocks (one wave of them, see launch_scatter) stride over the tiles: no tail wave, and the hot table keeps
+   * summing across all tiles of the block */
+  for (long n0 = (long)blockIdx.x * SB; n0 < N; n0 += (long)gridDim.x * SB)
+  for (int task0 = warp; task0 < tasks; task0 += 8 * PASSES) {
+    /* ---- every load of PASSES tasks is issued before anything is consumed ---- */
+    int slot[PASSES];
+    float4 gk[PASSES][CPL];
 #pragma unroll
-  for (int p = 0; p < PASSES; ++p) {
-    const long lk = (long)blockIdx.x * (PASSES * GPB) + p * GPB + threadIdx.x / TPL;
-    slot[p] = -1;
+    for (int p = 0; p < PASSES; ++p) {
+      const int task = task0 + 8 * p;
+      slot[p] = -1;
 #pragma unroll
-    for (int c = 0; c < CPL; ++c) gk[p][c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lk < L) {
-      const int j = (int)(lk / N), n = (int)(lk - (long)j * N);
-      slot[p] = lk_slot[(long)n * F + j];
+      for (int c = 0; c < CPL; ++c) gk[p][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int j = task % F;
+      const long n = n0 + (long)(task / F) * GPW + grp;
+      if (task < tasks && n < N) {
+        slot[p] = lk_slot[(long)j * N + n];
 #pragma unroll
-      for (int c = 0; c < CPL; ++c) {
-        const int cc = c0 + 4 * c;
-        if (cc < D) {
-          const size_t od = (size_t)n * ldd + j * D + cc, oa = (size_t)n * lda + j * D + cc;
-          float dv[4] = {0.f, 0.f, 0.f, 0.f}, av[4] = {0.f, 0.f, 0.f, 0.f};
-          if (ALIGNED) {
-            const float4 d4 = ld_f4(delta + od);
-            const float4 a4 = act ? ld_f4(act + oa) : make_float4(1.f, 1.f, 1.f, 1.f);   /* act == null: the mask was applied by the sender */
-            dv[0] = d4.x; dv[1] = d4.y; dv[2] = d4.z; dv[3] = d4.w;
-            av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
-          } else {
+        for (int c = 0; c < CPL; ++c) {
+          const int cc = c0 + 4 * c;
+          if (cc < D) {
+            const size_t od = (size_t)n * ldd + j * D + cc, oa = (size_t)n * lda + j * D + cc;
+            float dv[4] = {0.f, 0.f, 0.f, 0.f}, av[4] = {0.f, 0.f, 0.f, 0.f};
+            if (ALIGNED) {
+              const float4 d4 = ld_f4(delta + od);
+              const float4 a4 = act ? ld_f4(act + oa) : make_float4(1.f, 1.f, 1.f, 1.f);   /* act == null: the mask was applied by the sender */
+              dv[0] = d4.x; dv[1] = d4.y; dv[2] = d4.z; dv[3] = d4.w;
+              av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
+            } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) if (cc + i < D) { dv[i] = delta[od + i]; av[i] = act ? act[oa + i] : 1.f; }
+              for (int i = 0; i < 4; ++i) if (cc + i < D) { dv[i] = delta[od + i]; av[i] = act ? act[oa + i] : 1.f; }
+            }
+            /* Relu.backward: dy *= (y > 0 ? 1 : 0)  (activations/Relu.java:14-19) */
+            gk[p][c].x = __fmul_rn(dv[0], av[0] > 0.f ? 1.f : 0.f); gk[p][c].y = __fmul_rn(dv[1], av[1] > 0.f ? 1.f : 0.f);
+            gk[p][c].z = __fmul_rn(dv[2], av[2] > 0.f ? 1.f : 0.f); gk[p][c].w = __fmul_rn(dv[3], av[3] > 0.f ? 1.f : 0.f);
           }
-          /* Relu.backward: dy *= (y > 0 ? 1 : 0)  (activations/Relu.java:14-19) */
-          gk[p][c].x = __fmul_rn(dv[0], av[0] > 0.f ? 1.f : 0.f); gk[p][c].y = __fmul_rn(dv[1], av[1] > 0.f ? 1.f : 0.f);
-          gk[p][c].z = __fmul_rn(dv[2], av[2] > 0.f ? 1.f : 0.f); gk[p][c].w = __fmul_rn(dv[3], av[3] > 0.f ? 1.f : 0.f);
         }
       }
     }
-  }
-  uint32_t cnt[PASSES], uidx[PASSES];
+    uint32_t cnt[PASSES], row[PASSES];
 #pragma unroll
-  for (int p = 0; p < PASSES; ++p) {
-    cnt[p] = 0u; uidx[p] = 0u;
-    if (slot[p] >= 0) { const uint4 m = *reinterpret_cast<const uint4*>(&slots[slot[p]]); cnt[p] = m.z; uidx[p] = m.w; }
-  }
+    for (int p = 0; p < PASSES; ++p) {
+      cnt[p] = 0u; row[p] = 0u;
+      if (slot[p] >= 0) { const uint4 m = *reinterpret_cast<const uint4*>(&slots[slot[p]]); cnt[p] = m.z; row[p] = ~m.w; }   /* acc row = the key's first lookup */
+    }
 #pragma unroll
-  for (int p = 0; p < PASSES; ++p) {
-    const bool valid = slot[p] >= 0;
-    /* ---- (1) reduce-by-key inside the warp: rank r of a key's lanes adds rank r+s, s = 1, 2, 4, ... ---- */
-    const unsigned pmask = __match_any_sync(0xffffffffu, valid ? slot[p] : (-1 - lane)) & part_lanes;
-    const int npeer = __popc(pmask);
-    const int rank = __popc(pmask & ((1u << lane) - 1u));
-    const int maxn = __reduce_max_sync(0xffffffffu, npeer);
-    for (int s = 1; s < maxn; s <<= 1) {
-      const bool has = rank + s < npeer;
-      const int partner = has ? (int)__fns(pmask, (unsigned)lane, s + 1) : lane;
+    for (int p = 0; p < PASSES; ++p) {
+      if (task0 + 8 * p >= tasks) break;           /* warp-uniform */
+      const bool valid = slot[p] >= 0;
+      /* ---- (1) reduce-by-key inside the warp: rank r of a key's lanes adds rank r+s, s = 1, 2, 4, ... ---- */
+      const unsigned pmask = __match_any_sync(0xffffffffu, valid ? slot[p] : (-1 - lane)) & part_lanes;
+      const int npeer = __popc(pmask);
+      const int rank = __popc(pmask & ((1u << lane) - 1u));
+      const int maxn = __reduce_max_sync(0xffffffffu, npeer);
+      for (int s = 1; s < maxn; s <<= 1) {
+        const bool has = rank + s < npeer;
+        const int partner = has ? (int)__fns(pmask, (unsigned)lane, s + 1) : lane;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+          const float4 o = shfl_f4(gk[p][c], partner);
+          if (has) { gk[p][c].x += o.x; gk[p][c].y += o.y; gk[p][c].z += o.z; gk[p][c].w += o.w; }
+        }
+      }
+      if (!valid || rank != 0) continue;
+      /* ---- (2) hot keys: sum inside the block (the peer-memory exchange packs {entries << 24 | occurrences}: never hot) ---- */
+      int e = -1;
+      if (p2p == nullptr && cnt[p] >= hot_min) {
+        uint32_t h = ((uint32_t)slot[p] * 2654435761u) >> (32 - kHotBits);
+#pragma unroll 1
+        for (int t = 0; t < 4; ++t) {
+          const int old = atomicCAS(&hot_slot[h], -1, slot[p]);
+          if (old == -1) hot_row[h] = row[p];
+          if (old == -1 || old == slot[p]) { e = (int)h; break; }
+          h = (h + 1u) & (uint32_t)(kHotEntries - 1);
+        }
+      }
 #pragma unroll
       for (int c = 0; c < CPL; ++c) {
-        const float4 o = shfl_f4(gk[p][c], partner);
-        if (has) { gk[p][c].x += o.x; gk[p][c].y += o.y; gk[p][c].z += o.z; gk[p][c].w += o.w; }
-      }
-    }
-    if (!valid || rank != 0) continue;
-    /* ---- (2) hot keys: sum inside the block (the peer-memory exchange packs {entries << 24 | occurrences}: never hot) ---- */
-    int e = -1;
-    if (p2p == nullptr && cnt[p] >= (uint32_t)kHotMin) {
-      uint32_t h = ((uint32_t)slot[p] * 2654435761u) >> 27;
-#pragma unroll 1
-      for (int t = 0; t < 4; ++t) {
-        const int old = atomicCAS(&hot_slot[h], -1, slot[p]);
-        if (old == -1) hot_uidx[h] = uidx[p];
-        if (old == -1 || old == slot[p]) { e = (int)h; break; }
-        h = (h + 1u) & (uint32_t)(kHotEntries - 1);
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < CPL; ++c) {
-      const int cc = c0 + 4 * c;
-      if (cc >= D) continue;
-      if (e >= 0) {
-        float* a = &hot_acc[e][cc];
-        if (gk[p][c].x != 0.f) atomicAdd(a + 0, gk[p][c].x);
-        if (gk[p][c].y != 0.f) atomicAdd(a + 1, gk[p][c].y);
-        if (gk[p][c].z != 0.f) atomicAdd(a + 2, gk[p][c].z);
-        if (gk[p][c].w != 0.f) atomicAdd(a + 3, gk[p][c].w);
-      } else {
-        red_add_f4(acc + (size_t)uidx[p] * Dp + cc, gk[p][c]);          /* ---- (3) ---- */
+        const int cc = c0 + 4 * c;
+        if (cc >= D) continue;
+        if (e >= 0) {
+          float* a = &hot_acc[e][cc];
+          if (gk[p][c].x != 0.f) atomicAdd(a + 0, gk[p][c].x);
+          if (gk[p][c].y != 0.f) atomicAdd(a + 1, gk[p][c].y);
+          if (gk[p][c].z != 0.f) atomicAdd(a + 2, gk[p][c].z);
+          if (gk[p][c].w != 0.f) atomicAdd(a + 3, gk[p][c].w);
+        } else {
+          red_add_f4(acc + (size_t)row[p] * Dp + cc, gk[p][c]);          /* ---- (3) ---- */
+        }
       }
     }
   }
@@ -306,92 +372,98 @@ __global__ void __launch_bounds__(256) emb_scatter_kernel(const EmbSlot* __restr
     const int e = i / (ROWF / 4), cc = (i % (ROWF / 4)) * 4;
     if (hot_slot[e] < 0 || cc >= D) continue;
     const float4 v = *reinterpret_cast<const float4*>(&hot_acc[e][cc]);
-    if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) red_add_f4(acc + (size_t)hot_uidx[e] * Dp + cc, v);
+    if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) red_add_f4(acc + (size_t)hot_row[e] * Dp + cc, v);
   }
 }
 
-template <int TPK>
-__global__ void __launch_bounds__(256) emb_update_kernel(EmbSlot* __restrict__ slots, float* __restrict__ w, float* __restrict__ s1, float* __restrict__ s2,
-                                                         int Dp, int D, const int32_t* __restrict__ lk_slot, int N, int F, float* __restrict__ acc,
-                                                         UpdaterDev upd, int calls, const int* __restrict__ skip_flag, int packed_cnt) {
-  constexpr int KPP = 256 / TPK;                   /* keys per pass */
-  __shared__ int s_slot[256];
-  __shared__ uint32_t s_cnt[256], s_uidx[256];
-  __shared__ int s_warp[8];
-  const long L = (long)N * F;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  /* ---- scan: which of this block's 256 work indices own an accumulator row (the key's first lookup of the batch) ---- */
+/* TPK lanes per key (4 floats each).  A WARP scans 32 consecutive work indices, ballots the ones that own an accumulator
+ * row and deals the owners' (key, 16 B chunk) items round-robin over its 32 lanes, IPL items per lane and round with every
+ * load of a round issued before any is consumed; no block-level synchronisation.  EXACT: see updaters.cuh.              */
+template <int TPK, bool EXACT>
+__global__ void __launch_bounds__(256, 3) emb_update_kernel(EmbSlot* __restrict__ slots, float* __restrict__ w, float* __restrict__ s1, float* __restrict__ s2,
+                                                         int Dp, int D, const int32_t* __restrict__ lk_slot, long L, float* __restrict__ acc,
+                                                         UpdaterDev upd, int calls, const int* __restrict__ skip_flag, int packed_cnt,
+                                                         uint32_t* __restrict__ counters) {
+  constexpr int IPL = TPK < 2 ? 1 : 2;             /* items per lane and round */
+  const int lane = threadIdx.x & 31;
   const long lk = (long)blockIdx.x * 256 + threadIdx.x;
-  int slot = -1; uint32_t cnt = 0u, uidx = 0u;
+  int slot = -1; uint32_t cnt = 0u, first = 0u;
   if (lk < L) {
-    const int j = (int)(lk / N), n = (int)(lk - (long)j * N);
-    slot = lk_slot[(long)n * F + j];
-    if (slot >= 0) { const uint4 m = *reinterpret_cast<const uint4*>(&slots[slot]); cnt = m.z; uidx = m.w; }
+    slot = lk_slot[lk];
+    if (slot >= 0) { const uint4 m = *reinterpret_cast<const uint4*>(&slots[slot]); cnt = m.z; first = m.w; }
   }
-  const bool owner = slot >= 0 && uidx == (uint32_t)lk;
+  const bool owner = slot >= 0 && first == ~(uint32_t)lk;          /* the key's first lookup of the batch */
   const unsigned owners = __ballot_sync(0xffffffffu, owner);
-  if (lane == 0) s_warp[warp] = __popc(owners);
-  __syncthreads();
-  int base = 0, total = 0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { const int c = s_warp[i]; if (i < warp) base += c; total += c; }
-  if (owner) {
-    const int o = base + __popc(owners & ((1u << lane) - 1u));
-    s_slot[o] = slot; s_cnt[o] = cnt; s_uidx[o] = uidx;
-  }
-  __syncthreads();
+  const int items = __popc(owners) * TPK;
+  if (lane == 0 && owners != 0u) red_add_u32(&counters[0], (uint32_t)__popc(owners));   /* statistics (StepStatus.n_unique), monotonic */
   const bool skip = skip_flag != nullptr && *skip_flag != 0;
-  const int part = threadIdx.x % TPK, cc = part * 4;
-  const bool col_ok = cc < D;
-  /* ---- the rows of the first pass are requested before the scatter kernel is known to be complete ---- */
-  int k = threadIdx.x / TPK;
-  bool active = k < total && col_ok;
-  size_t o = 0;
-  float4 wv = make_float4(0.f, 0.f, 0.f, 0.f), m1 = wv, m2 = wv;
-  if (active) {
-    o = (size_t)s_slot[k] * Dp + cc;
-    if (!skip) { wv = ld_f4(w + o); if (upd.kind != PS_UPD_SIMPLE) { m1 = ld_f4(s1 + o); m2 = ld_f4(s2 + o); } }
-  }
+
+  int kslot[IPL]; uint32_t kcnt[IPL]; long krow[IPL]; bool act[IPL];
+  float4 wv[IPL], m1[IPL], m2[IPL];
+  auto load_round = [&](int base) {
+#pragma unroll
+    for (int q = 0; q < IPL; ++q) {
+      const int i = base + q * 32 + lane;
+      const bool in = i < items;
+      const int src = in ? (int)__fns(owners, 0u, i / TPK + 1) : 0;   /* lane of the (i / TPK)-th owner */
+      kslot[q] = __shfl_sync(0xffffffffu, slot, src);
+      kcnt[q] = __shfl_sync(0xffffffffu, cnt, src);
+      krow[q] = (long)(lk - lane + src);                              /* the owner's work index = its accumulator row */
+      const int cc = (i % TPK) * 4;
+      act[q] = in && cc < D;
+      wv[q] = m1[q] = m2[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (act[q] && !skip) {
+        const size_t o = (size_t)kslot[q] * Dp + cc;
+        wv[q] = ld_f4(w + o);
+        if (upd.kind != PS_UPD_SIMPLE) { m1[q] = ld_f4(s1 + o); m2[q] = ld_f4(s2 + o); }
+      }
+    }
+  };
+  /* ---- the rows of the first round are requested before the scatter kernel is known to be complete ---- */
+  load_round(0);
   pdl_wait();
-  for (int kb = 0; kb < total; kb += KPP) {
-    if (kb > 0) {
-      k = kb + threadIdx.x / TPK;
-      active = k < total && col_ok;
-      if (active) {
-        o = (size_t)s_slot[k] * Dp + cc;
-        if (!skip) { wv = ld_f4(w + o); if (upd.kind != PS_UPD_SIMPLE) { m1 = ld_f4(s1 + o); m2 = ld_f4(s2 + o); } }
+  for (int base = 0; base < items; base += 32 * IPL) {
+    if (base > 0) load_round(base);
+    float4 S[IPL];
+#pragma unroll
+    for (int q = 0; q < IPL; ++q) {
+      const int cc = ((base + q * 32 + lane) % TPK) * 4;
+      S[q] = (act[q] && !skip) ? __ldcg(reinterpret_cast<const float4*>(acc + (size_t)krow[q] * Dp + cc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int q = 0; q < IPL; ++q) {
+      const int cc = ((base + q * 32 + lane) % TPK) * 4;
+      /* peer-memory exchange: senders pre-reduce, cnt packs {entries << 24 | occurrences} */
+      const uint32_t n_occ = packed_cnt ? (kcnt[q] & 0xFFFFFFu) : kcnt[q];
+      const GeffScale gs = make_geff<EXACT>(n_occ > 0u ? n_occ : 1u, calls);
+      bool do_upd = !skip;
+      if (upd.kind == PS_UPD_FTRL) {                  /* FtrlUpdater.java:52: `if (dw.get(0) == 0) return w` */
+        const float S0 = __shfl_sync(0xffffffffu, S[q].x, lane - (lane % TPK));
+        do_upd = do_upd && emb_geff<EXACT>(S0, gs) != 0.0f;
       }
-    }
-    /* peer-memory exchange: senders pre-reduce, cnt packs {entries << 24 | occurrences} */
-    const uint32_t kc = k < total ? s_cnt[k] : 1u;
-    const uint32_t n_occ = packed_cnt ? (kc & 0xFFFFFFu) : kc;
-    float* arow = acc + (size_t)(k < total ? s_uidx[k] : 0u) * Dp + cc;
-    const float4 S = (active && !skip) ? __ldcg(reinterpret_cast<const float4*>(arow)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    bool do_upd = !skip;
-    if (upd.kind == PS_UPD_FTRL) {                  /* FtrlUpdater.java:52: `if (dw.get(0) == 0) return w` */
-      const float S0 = __shfl_sync(0xffffffffu, S.x, lane - (lane % TPK));
-      do_upd = do_upd && emb_geff(S0, n_occ, calls) != 0.0f;
-    }
-    if (!active) continue;
-    if (!skip) {
-      if (do_upd) {
-        apply_elem(upd, wv.x, m1.x, m2.x, emb_geff(S.x, n_occ, calls));
-        apply_elem(upd, wv.y, m1.y, m2.y, emb_geff(S.y, n_occ, calls));
-        apply_elem(upd, wv.z, m1.z, m2.z, emb_geff(S.z, n_occ, calls));
-        apply_elem(upd, wv.w, m1.w, m2.w, emb_geff(S.w, n_occ, calls));
-        st_f4(w + o, wv);
-        if (upd.kind != PS_UPD_SIMPLE) { st_f4(s1 + o, m1); st_f4(s2 + o, m2); }
+      if (!act[q]) continue;
+      if (!skip) {
+        const size_t o = (size_t)kslot[q] * Dp + cc;
+        if (do_upd) {
+          apply_elem<EXACT>(upd, wv[q].x, m1[q].x, m2[q].x, emb_geff<EXACT>(S[q].x, gs));
+          apply_elem<EXACT>(upd, wv[q].y, m1[q].y, m2[q].y, emb_geff<EXACT>(S[q].y, gs));
+          apply_elem<EXACT>(upd, wv[q].z, m1[q].z, m2[q].z, emb_geff<EXACT>(S[q].z, gs));
+          apply_elem<EXACT>(upd, wv[q].w, m1[q].w, m2[q].w, emb_geff<EXACT>(S[q].w, gs));
+          st_f4(w + o, wv[q]);
+          if (upd.kind != PS_UPD_SIMPLE) { st_f4(s1 + o, m1[q]); st_f4(s2 + o, m2[q]); }
+        }
+        st_f4(acc + (size_t)krow[q] * Dp + cc, make_float4(0.f, 0.f, 0.f, 0.f));
       }
-      st_f4(arow, make_float4(0.f, 0.f, 0.f, 0.f));
+      /* KVStore.clear (also after the early exit: the batch is forgotten): {cnt, first} = 0 in one 8 B store */
+      if (cc == 0) *reinterpret_cast<unsigned long long*>(&slots[kslot[q]].cnt) = 0ull;
     }
-    if (part == 0) slots[s_slot[k]].cnt = 0u;      /* KVStore.clear (also after the early exit: the batch is forgotten) */
   }
 }
 
 __global__ void emb_clear_batch_kernel(EmbSlot* __restrict__ slots, const int32_t* __restrict__ lk_slot, int L) {
   for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < L; l += gridDim.x * blockDim.x) {
     const int slot = lk_slot[l];
-    if (slot >= 0) slots[slot].cnt = 0u;       /* duplicates store the same zero */
+    if (slot >= 0) *reinterpret_cast<unsigned long long*>(&slots[slot].cnt) = 0ull;       /* {cnt, first}; duplicates store the same zero */
   }
 }
 
@@ -443,6 +515,7 @@ void EmbTable::create(Ctx* c, int F_, int D_, int64_t capacity, const ps_updater
   s2 = dmalloc_zero<float>((size_t)C * Dp, ctx->stream);
   counters = dmalloc_zero<uint32_t>(4, ctx->stream);
   reserve(max_lookups > 0 ? max_lookups : 1);
+  scatter_update(nullptr, 0, nullptr, 0, 0, 2, nullptr);   /* fills scatter_occ (sizes the scatter's persistent grid) */
 }
 
 void EmbTable::reserve(int64_t L) {
@@ -460,15 +533,19 @@ void EmbTable::destroy() {
   slots = nullptr; w = s1 = s2 = nullptr;
 }
 
+/* samples per block = 32 * SG with SG chosen so that a block's F * SG warp tasks keep its 8 warps busy */
+static int probe_sg(int F) { return F >= 8 ? 1 : (8 + F - 1) / F; }
+
 void EmbTable::probe(const int64_t* ids_i64, const float* ids_f32, int N) {
   const int64_t L = (int64_t)N * F;
   PS_REQUIRE(L <= Lcap, PS_ERR_ARG, "embedding: batch larger than the reserved workspace");
   last_L = L;
-  const int grid = ceil_div(L, 256);
+  const int SG = probe_sg(F);
+  const int grid = ceil_div(N, 32 * SG);
   if (ids_i64)
-    emb_probe_kernel<int64_t><<<grid, 256, 0, ctx->stream>>>(slots, (uint32_t)C, w, Dp, D, ids_i64, (int)L, F, ctx->seed, maxv, lk_slot, counters, nullptr);
+    emb_probe_kernel<int64_t><<<grid, 256, 0, ctx->stream>>>(slots, (uint32_t)C, w, Dp, D, ids_i64, N, F, SG, ctx->seed, maxv, lk_slot, counters, nullptr);
   else
-    emb_probe_kernel<float><<<grid, 256, 0, ctx->stream>>>(slots, (uint32_t)C, w, Dp, D, ids_f32, (int)L, F, ctx->seed, maxv, lk_slot, counters, nullptr);
+    emb_probe_kernel<float><<<grid, 256, 0, ctx->stream>>>(slots, (uint32_t)C, w, Dp, D, ids_f32, N, F, SG, ctx->seed, maxv, lk_slot, counters, nullptr);
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }
@@ -477,8 +554,9 @@ void EmbTable::probe_packed(const uint64_t* keys, int n, const P2PState* p2p) {
   reserve(n);
   last_L = n;
   if (n <= 0) return;
-  emb_probe_kernel<unsigned long long><<<ceil_div(n, 256), 256, 0, ctx->stream>>>(slots, (uint32_t)C, w, Dp, D, reinterpret_cast<const unsigned long long*>(keys), n, 0,
-                                                                                  ctx->seed, maxv, lk_slot, counters, p2p);
+  const int SG = probe_sg(1);
+  emb_probe_kernel<unsigned long long><<<ceil_div(n, 32 * SG), 256, 0, ctx->stream>>>(slots, (uint32_t)C, w, Dp, D, reinterpret_cast<const unsigned long long*>(keys), n, 0, SG,
+                                                                                      ctx->seed, maxv, lk_slot, counters, p2p);
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }
@@ -510,21 +588,39 @@ void EmbTable::gather(float* out, int ldo, int N, int F_eff, const float* X, int
 template <int TPK>
 static void launch_update(EmbTable& t, int N, int F, int calls, const int* skip, int packed_cnt) {
   const long L = (long)N * F;
-  launch_pdl(t.ctx, emb_update_kernel<TPK>, dim3(ceil_div(L, 256)), dim3(256), t.slots, t.w, t.s1, t.s2, t.Dp, t.D, (const int32_t*)t.lk_slot, N, F,
-             t.acc, t.upd, calls, skip, packed_cnt);
+  if (t.ctx->exact_updaters)
+    launch_pdl(t.ctx, emb_update_kernel<TPK, true>, dim3(ceil_div(L, 256)), dim3(256), t.slots, t.w, t.s1, t.s2, t.Dp, t.D, (const int32_t*)t.lk_slot, L,
+               t.acc, t.upd, calls, skip, packed_cnt, t.counters);
+  else
+    launch_pdl(t.ctx, emb_update_kernel<TPK, false>, dim3(ceil_div(L, 256)), dim3(256), t.slots, t.w, t.s1, t.s2, t.Dp, t.D, (const int32_t*)t.lk_slot, L,
+               t.acc, t.upd, calls, skip, packed_cnt, t.counters);
 }
 
 template <int TPL, int CPL>
 static void launch_scatter(EmbTable& t, const float* delta, int ldd, const float* act, int lda, int N, int F, int calls, const int* skip,
                            const P2PState* p2p) {
-  constexpr int PASSES = TPL >= 4 ? 4 : TPL;     /* tile = PASSES * 256 / TPL consecutive lookups of one field: 256 (D <= 16), 128 (D = 64) */
+  constexpr int PASSES = TPL >= 4 ? 4 : TPL;     /* warp tasks in flight per warp */
+  constexpr int GPW = 32 / TPL;
   const long L = (long)N * F;
   const bool aligned = (t.D % 4 == 0) && (ldd % 4 == 0) && (lda % 4 == 0) && ((uintptr_t)delta % 16 == 0) && ((uintptr_t)act % 16 == 0);
-  const int grid = ceil_div(L, PASSES * (256 / TPL));
+  /* samples per tile: small enough that there are >= 4 tiles per resident block (balance), at most 32 */
+  if (N == 0) {                                  /* EmbTable::create: resident blocks per SM of the two instantiations (not inside a capture) */
+    PS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t.scatter_occ[1], emb_scatter_kernel<TPL, CPL, PASSES, true>, 256, 0));
+    PS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t.scatter_occ[0], emb_scatter_kernel<TPL, CPL, PASSES, false>, 256, 0));
+    return;
+  }
+  const int resident = t.ctx->num_sms * std::max(1, t.scatter_occ[aligned ? 1 : 0]);
+  int SB = GPW;
+  while (SB * 2 <= 32 && ceil_div(N, SB * 2) >= 4 * resident) SB *= 2;
+  const int grid = std::min(ceil_div(N, SB), resident);
+  /* a key is pre-summed per block when it is frequent enough to recur among the samples one block sees */
+  const long per_block = (long)SB * ceil_div(ceil_div(N, SB), grid);
+  const uint32_t hot_min = t.ctx->hot_min == 0xFFFFFFFFu ? 0xFFFFFFFFu : std::max<uint32_t>(t.ctx->hot_min, (uint32_t)(2L * N / per_block));
+  (void)L;
   if (aligned)
-    emb_scatter_kernel<TPL, CPL, PASSES, true><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.Dp, t.D, t.lk_slot, N, F, delta, ldd, act, lda, t.acc, skip, p2p);
+    emb_scatter_kernel<TPL, CPL, PASSES, true><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.Dp, t.D, t.lk_slot, N, F, SB, delta, ldd, act, lda, t.acc, skip, p2p, hot_min);
   else
-    emb_scatter_kernel<TPL, CPL, PASSES, false><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.Dp, t.D, t.lk_slot, N, F, delta, ldd, act, lda, t.acc, skip, p2p);
+    emb_scatter_kernel<TPL, CPL, PASSES, false><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.Dp, t.D, t.lk_slot, N, F, SB, delta, ldd, act, lda, t.acc, skip, p2p, hot_min);
   PS_LAUNCH_CHECK();
   switch (t.tpl) {                              /* the update spends 4 floats per lane whatever the scatter's chunking was */
     case 1: launch_update<1>(t, N, F, calls, skip, p2p != nullptr ? 1 : 0); break;
@@ -540,8 +636,10 @@ static void launch_scatter(EmbTable& t, const float* delta, int ldd, const float
 void EmbTable::scatter_update(const float* delta, int ldd, const float* act, int lda, int N, int calls, const int* skip_flag, int F_eff,
                               const P2PState* p2p) {
   const int Fe = F_eff > 0 ? F_eff : F;
-  PS_REQUIRE((int64_t)N * Fe == last_L, PS_ERR_STATE, "embedding: backward without a matching forward");
-  PS_REQUIRE(calls == 1 || calls == 2, PS_ERR_ARG, "embedding: backward calls must be 1 or 2");
+  if (N > 0) {                                  /* N == 0: occupancy query from create() */
+    PS_REQUIRE((int64_t)N * Fe == last_L, PS_ERR_STATE, "embedding: backward without a matching forward");
+    PS_REQUIRE(calls == 1 || calls == 2, PS_ERR_ARG, "embedding: backward calls must be 1 or 2");
+  }
   if (Dp % 8 == 0) {                            /* two 16 B chunks per lane: half the threads, twice the bytes in flight per thread */
     switch (pow2_ge(Dp / 8)) {
       case 1: launch_scatter<1, 2>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
@@ -560,6 +658,7 @@ void EmbTable::scatter_update(const float* delta, int ldd, const float* act, int
       default: launch_scatter<32, 1>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
     }
   }
+  if (N == 0) return;
   PS_LAUNCH_CHECK();
   last_L = 0;
 }

@@ -29,7 +29,8 @@ namespace psb {
 struct __align__(16) EmbSlot {
   unsigned long long key;
   uint32_t cnt;    /* occurrences of this key in the current batch (EmbeddingField.java:96 wgN) */
-  uint32_t uidx;   /* index of this key among the batch's unique keys */
+  uint32_t first;  /* ~t of the key's first lookup of the current batch (max over ~t = min over t; 0 between batches): that lookup
+                      owns the key's accumulator row acc[t] and performs its update */
 };
 
 struct __align__(32) WideSlot {
@@ -51,8 +52,9 @@ struct EmbTable {
   int64_t Lcap = 0;
   int32_t* lk_slot = nullptr;
   float* acc = nullptr;
-  uint32_t* counters = nullptr;        /* [0] monotonic unique-key counter, [1] error flag, [2..3] u64 row count */
+  uint32_t* counters = nullptr;        /* [0] monotonic count of updated (unique) keys, [1] error flag, [2..3] u64 row count */
   int64_t last_L = 0;
+  int scatter_occ[2] = {1, 1};         /* resident scatter blocks per SM (unaligned / aligned instantiation) */
 
   void create(Ctx* c, int F_, int D_, int64_t capacity, const ps_updater_spec& u, int64_t max_lookups);
   void destroy();

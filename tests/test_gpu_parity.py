@@ -104,7 +104,9 @@ def test_embedding_forward_bit_exact(ps, ctx, F, D, N, V, dist):
 @pytest.mark.parametrize("F,D,N,V,calls", [(23, 16, 512, 3000, 2), (23, 10, 200, 500, 2), (4, 32, 256, 40, 1), (23, 16, 1024, 200000, 2),
                                            # hot keys (thousands of occurrences of one row: the per-block shared-memory pre-sum), ragged dims
                                            (3, 64, 2048, 7, 2), (23, 16, 4096, 1000, 2), (5, 10, 700, 11, 1), (2, 128, 300, 4, 2), (1, 4, 5000, 2, 2)])
-def test_embedding_backward_update(ps, ctx, opt, F, D, N, V, calls):
+@pytest.mark.parametrize("exact", [False, True])
+def test_embedding_backward_update(ps, ctx, opt, F, D, N, V, calls, exact):
+    ctx.set_exact_updaters(exact)             # fast forms (default) and the IEEE operation sequence of the Java updaters
     spec = ps.UpdaterSpec.adam() if opt == "adam" else ps.UpdaterSpec.ftrl()
     emb = ps.EmbeddingLayer(ctx, F, D, capacity=max(1024, 4 * N * F), updater=spec)
     o = ol.lib().pso_emb_create(F, D, SEED, 1 if opt == "ftrl" else 0)
@@ -141,6 +143,42 @@ def test_embedding_backward_update(ps, ctx, opt, F, D, N, V, calls):
             assert np.allclose(s1[i], s1o, rtol=2e-5, atol=1e-7), key
             assert np.allclose(s2[i], s2o, rtol=2e-5, atol=1e-9), key
     assert worst <= 2e-5, worst
+    om.h = None
+    ol.lib().pso_model_destroy(o)
+    emb.close()
+
+
+@pytest.mark.parametrize("opt", ["adam", "ftrl"])
+def test_embedding_update_exact_mode_is_bit_exact(ps, ctx, opt):
+    """With every key occurring once the gradient sum has one term (no reassociation), g_eff = S exactly, and the exact-mode
+    sparse update must reproduce the Java updaters' bits: weights and both optimiser states, over several steps."""
+    ctx.set_exact_updaters(True)
+    F, D, N = 3, 16, 96
+    spec = ps.UpdaterSpec.adam() if opt == "adam" else ps.UpdaterSpec.ftrl()
+    emb = ps.EmbeddingLayer(ctx, F, D, capacity=4096, updater=spec)
+    o = ol.lib().pso_emb_create(F, D, SEED, 1 if opt == "ftrl" else 0)
+    rng = np.random.default_rng(21)
+    E = np.stack([rng.permutation(1000)[:N] + 1000 * j for j in range(F)], 1).astype(np.int64)     # all distinct within a field
+    for it in range(4):
+        out_g = emb.forward(E)
+        out_o = np.zeros((N, F * D), np.float32)
+        ol.lib().pso_emb_forward(o, np.ascontiguousarray(E), N, out_o.reshape(-1))
+        assert np.array_equal(out_g.view(np.uint32), out_o.view(np.uint32)), it
+        delta = rng.standard_normal((N, F * D)).astype(np.float32)
+        emb.backward_update(delta, calls=2)
+        ol.lib().pso_emb_backward_update(o, delta.reshape(-1), F * D, N, 2)
+    fields = np.repeat(np.arange(F, dtype=np.int32), N)
+    ids = E.T.reshape(-1).copy()
+    w, s1, s2, found = emb.get_rows(fields, ids, state=True)
+    om = ol.OracleModel.__new__(ol.OracleModel)
+    om.L, om.h = ol.lib(), o
+    for i in range(len(ids)):
+        key = ol.key_string(0, int(fields[i]), int(ids[i]))
+        assert np.array_equal(w[i].view(np.uint32), om.get(key).view(np.uint32)), key
+        for mine, which in ((s1[i], 0), (s2[i], 1)):
+            so = om.get_state(key, which)                      # None until the updater first touches the key (Ftrl may skip: FtrlUpdater.java:52)
+            so = np.zeros(D, np.float32) if so is None else so
+            assert np.array_equal(mine.view(np.uint32), so.view(np.uint32)), (key, which)
     om.h = None
     ol.lib().pso_model_destroy(o)
     emb.close()
