@@ -23,4 +23,20 @@ public final class PsNative {
 	public static native void modelPut(long model, String key, float[] value);
 	public static native float[] modelTap(long model, String layer, int what);        // 0 = A, 1 = delta
 	public static native boolean modelSkippedBackward(long model);
+
+	// layer.FcLayer as a standalone operator (ps_fc_*): for models that walk their own layer list (layer/StandaloneFcLayer.java)
+	public static native long fcCreate(long ctx, String name, int in, int out, int act, float[] updater, int maxBatch);
+	public static native void fcDestroy(long fc);
+	public static native void fcForward(long fc, float[] aPrev, int N, float[] aOut);         // FcLayer.forward  (FcLayer.java:74-91)
+	public static native void fcBackward(long fc, float[] delta, int N, float[] deltaPrev);   // FcLayer.backward (FcLayer.java:93-110)
+	public static native void fcUpdate(long fc);                                              // KVStore.update + clear for its two keys
+	public static native float[] fcGet(long fc, int which);                                   // 0 weights (out x in), 1 bias
+	public static native void fcPut(long fc, int which, float[] value);
+
+	// data.DataSet over data.FileSource with LibsvmParser + CTR.parseFeature (ps_reader_*): data/NativeCtrDataSet.java
+	public static native long readerOpen(String path, int F, int Xn, long wideSize, int batch, int offset, int step, int threads);
+	/** fills E, W (F x rows ids as floats, like CTR.parseFeature), X (Xn x rows), Y (rows); returns rows, 0 at end of data */
+	public static native int readerNext(long reader, float[] E, float[] X, float[] W, float[] Y);
+	public static native void readerReset(long reader);
+	public static native void readerClose(long reader);
 }

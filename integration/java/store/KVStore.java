@@ -24,6 +24,11 @@ public class KVStore {
 	private long ctx, model;                       // opaque native handles, bound by GpuStep.bind()
 	public void bind(long ctx, long model) { this.ctx = ctx; this.model = model; }
 	public long model() { return model; }
+	public long nativeCtx() { return ctx; }
+
+	// layer-at-a-time mode (layer/StandaloneFcLayer.java): dense layers whose pending KVStore.sum lives on the device
+	private final java.util.Map<String, Long> dense = new java.util.LinkedHashMap<String, Long>();
+	public synchronized void registerDense(String name, long fcHandle) { dense.put(name, fcHandle); }
 
 	public FloatMatrix get(String key) {           // KVStore.java:129-134
 		float[] v = PsNative.modelGet(model, key);
@@ -40,7 +45,9 @@ public class KVStore {
 	public synchronized void sum(String key, FloatMatrix val) { /* gradients are accumulated on the device by the native step */ }
 	public void update(Updater updater, String key) {}
 	public void update(Updater updater) {}
-	public void update(Map<String, Updater> updaters) {}                                   // applied inside modelTrainStep
+	public void update(Map<String, Updater> updaters) {                                    // KVStore.java:240-268
+		for (long fc : dense.values()) PsNative.fcUpdate(fc);                                // whole-step mode: nothing registered, applied inside modelTrainStep
+	}
 	public void clear() {}
 	public void asyncGet(String key, Callable<FloatMatrix> init) {}                        // the probe kernel is the batched prefetch
 	public void asyncWait() {}

@@ -115,3 +115,47 @@ JNIEXPORT jboolean JNICALL Java_nativeps_PsNative_modelSkippedBackward(JNIEnv* e
   return v ? JNI_TRUE : JNI_FALSE;
 }
 /* updaterParse / modelPredict follow the same pattern (ps_updater_parse, ps_model_predict). */
+
+/* ---- layer.FcLayer standalone (ps_fc_*): jblas column-major float[] is exactly the C ABI's layout, no conversion ---- */
+JNIEXPORT void JNICALL Java_nativeps_PsNative_fcForward(JNIEnv* env, jclass c, jlong fc, jfloatArray aPrev, jint N, jfloatArray aOut) {
+  jfloat* in = (*env)->GetPrimitiveArrayCritical(env, aPrev, NULL);
+  jfloat* out = (*env)->GetPrimitiveArrayCritical(env, aOut, NULL);
+  int rc = ps_fc_forward((ps_fc*)(intptr_t)fc, in, N, out);                     /* FcLayer.forward (FcLayer.java:74-91) */
+  (*env)->ReleasePrimitiveArrayCritical(env, aOut, out, 0);
+  (*env)->ReleasePrimitiveArrayCritical(env, aPrev, in, JNI_ABORT);
+  throw_ps(env, rc);
+}
+JNIEXPORT void JNICALL Java_nativeps_PsNative_fcBackward(JNIEnv* env, jclass c, jlong fc, jfloatArray delta, jint N, jfloatArray deltaPrev) {
+  jfloat* d = (*env)->GetPrimitiveArrayCritical(env, delta, NULL);
+  jfloat* p = (*env)->GetPrimitiveArrayCritical(env, deltaPrev, NULL);
+  int rc = ps_fc_backward((ps_fc*)(intptr_t)fc, d, N, p);                       /* FcLayer.backward (FcLayer.java:93-110) */
+  (*env)->ReleasePrimitiveArrayCritical(env, deltaPrev, p, 0);
+  (*env)->ReleasePrimitiveArrayCritical(env, delta, d, JNI_ABORT);
+  throw_ps(env, rc);
+}
+JNIEXPORT void JNICALL Java_nativeps_PsNative_fcUpdate(JNIEnv* env, jclass c, jlong fc) { throw_ps(env, ps_fc_update((ps_fc*)(intptr_t)fc)); }
+/* fcCreate / fcDestroy / fcGet / fcPut: ps_fc_create / ps_fc_destroy / ps_fc_get / ps_fc_put, same pattern as modelGet / modelPut. */
+
+/* ---- data.DataSet (ps_reader_*): ids are widened back to floats because CTR.parseFeature's "E"/"W" are FloatMatrix ---- */
+JNIEXPORT jint JNICALL Java_nativeps_PsNative_readerNext(JNIEnv* env, jclass c, jlong r, jfloatArray E, jfloatArray X, jfloatArray W, jfloatArray Y) {
+  jsize ne = (*env)->GetArrayLength(env, E);
+  int64_t* e = (int64_t*)malloc(sizeof(int64_t) * (size_t)ne);
+  int64_t* w = (int64_t*)malloc(sizeof(int64_t) * (size_t)ne);
+  jfloat* x = (*env)->GetFloatArrayElements(env, X, NULL);
+  jfloat* y = (*env)->GetFloatArrayElements(env, Y, NULL);
+  int rows = 0;
+  int rc = ps_reader_next((ps_reader*)(intptr_t)r, e, x, w, y, &rows);
+  (*env)->ReleaseFloatArrayElements(env, X, x, 0);
+  (*env)->ReleaseFloatArrayElements(env, Y, y, 0);
+  if (rc == PS_OK && rows > 0) {
+    jfloat* ef = (*env)->GetFloatArrayElements(env, E, NULL);
+    jfloat* wf = (*env)->GetFloatArrayElements(env, W, NULL);
+    for (jsize i = 0; i < ne; ++i) { ef[i] = (jfloat)e[i]; wf[i] = (jfloat)w[i]; }   /* exact: the reader already applied (float) idx */
+    (*env)->ReleaseFloatArrayElements(env, E, ef, 0);
+    (*env)->ReleaseFloatArrayElements(env, W, wf, 0);
+  }
+  free(e); free(w);
+  throw_ps(env, rc);
+  return rows;
+}
+/* readerOpen / readerReset / readerClose: ps_reader_open / ps_reader_reset / ps_reader_close. */
