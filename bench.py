@@ -46,34 +46,61 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons DURING the timed region: NVML polled every 2 ms (the timed region of the default run is tens
+    of milliseconds — an nvidia-smi subprocess per sample would see it once); nvidia-smi is the fallback when NVML is unavailable."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.stop_flag, self.sm_max, self.how = index, [], False, None, "nvml"
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv, self.how = None, "nvidia-smi"
 
     def run(self):
+        nv = self.nv
         while not self.stop_flag:
             try:
+                if nv is not None:
+                    sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                        else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    self.rows.append((sm, r))
+                    time.sleep(0.002)
+                    continue
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
-                    self.rows.append([t.strip() for t in out.split(",")])
+                    t = [x.strip() for x in out.split(",")]
+                    r = 0
+                    for i, bit in enumerate([0x8, 0x40, 0x20, 0x4]):       # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap (NVML bit values)
+                        if t[3 + i].lower().startswith("active"):
+                            r |= bit
+                    self.sm_max = float(t[1])
+                    self.rows.append((float(t[0]), r))
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def summary(self):
         self.stop_flag = True
         self.join(timeout=6)
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(float(r[0]) for r in self.rows)
-        reasons = []
-        for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
-            if any(r[3 + i].lower().startswith("active") for r in self.rows):
-                reasons.append(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(self.rows)}
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unsampled"]}
+        sm = sorted(r[0] for r in self.rows)
+        bits = 0
+        for _, r in self.rows:
+            bits |= r
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max, "reasons": [n for b, n in names.items() if bits & b],
+                "samples": len(self.rows), "how": self.how}
 
 
 def model_args(cfg, n_gpus):
@@ -396,7 +423,8 @@ def main():
                        "l2": "embedding table + optimiser state (%.0f MB) exceeds the 126 MB L2; a ring of %d distinct batches; no flush" % (
                            cap * (16 + 12 * D) / 1e6, len(ring))},
             "e2e": {"value": total / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
-                    "api": "ps_model_submit/ps_model_collect (2 steps in flight)"},
+                    "api": "ps_model_submit/ps_model_collect (2 steps in flight)" if trainer is None else
+                           "pinned host batch -> device (async copy on the step's stream) -> sharded step -> ps_model_read_loss, every step"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_large_batch": large, "kernels_us": phase_us, "hbm_kernels": kernels,
             "cpu_baseline": cpu, "loss": loss, "loss_e2e": loss_e2e, "unique_keys_per_batch": uniq,
         }

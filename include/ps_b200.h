@@ -179,6 +179,12 @@ int ps_model_get_state(ps_model* m, const char* key, int which, float* out, int 
 int ps_model_tap(ps_model* m, const char* layer, int what, float* out, int cap, int* n);
 int ps_model_num_keys(ps_model* m, int64_t* out);            /* KVStore.store.size() */
 int ps_model_skipped_backward(ps_model* m, int* out);        /* DNN.java:58-63 early exit taken */
+/* Bulk dump / load of the store: every key store.KVStore would hold (KVStore.java:38-44; PServer.getList /
+ * upsertList, PServer.java:102-162, are the reference's only bulk accessors — it has no checkpoint) with its updater state,
+ * to / from one file.  Load needs a freshly created model of the same shape; embedding rows are re-inserted by key, so the
+ * table capacity may differ from the one that wrote the file.  PS_NOT_FOUND when the file cannot be opened.               */
+int ps_model_save(ps_model* m, const char* path);
+int ps_model_load(ps_model* m, const char* path);
 /* step-level timing of the last ps_model_train_step_dev: device milliseconds per phase
  * (CUDA events on the library's stream); names returned as a ';'-separated list.             */
 int ps_model_profile(ps_model* m, int enable);

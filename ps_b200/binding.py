@@ -85,6 +85,8 @@ SYMBOLS = {
     "ps_model_tap": (_i, [_vp, C.c_char_p, _i, _vp, _i, C.POINTER(_i)]),
     "ps_model_num_keys": (_i, [_vp, C.POINTER(_i64)]),
     "ps_model_skipped_backward": (_i, [_vp, C.POINTER(_i)]),
+    "ps_model_save": (_i, [_vp, C.c_char_p]),
+    "ps_model_load": (_i, [_vp, C.c_char_p]),
     "ps_model_profile": (_i, [_vp, _i]),
     "ps_model_phase_times": (_i, [_vp, _vp, _i, C.POINTER(_i), C.c_char_p, _i]),
     "ps_model_kernel_times": (_i, [_vp, _vp, _i, _i, _i, _vp]),
@@ -455,6 +457,12 @@ class Model:
         v = C.c_int64()
         check(lib().ps_model_num_keys(self.h, C.byref(v)))
         return v.value
+
+    def save(self, path):
+        check(lib().ps_model_save(self.h, os.fsencode(path)))
+
+    def load(self, path):
+        check(lib().ps_model_load(self.h, os.fsencode(path)))
 
     def skipped_backward(self):
         v = C.c_int()

@@ -64,6 +64,8 @@ int ps_ctx_create(int device, uint64_t seed, ps_ctx** out) {
   c->c.prio_side = (pe && pe[0] == '0') ? 0 : prio_lo;
   const char* pd = std::getenv("PS_PDL");
   c->c.pdl = (pd && pd[0] == '0') ? 0 : 1;
+  const char* pg = std::getenv("PS_PDL_GEMM");
+  c->c.pdl_gemm = (pg && pg[0] == '0') ? 0 : 1;
   const char* xe = std::getenv("PS_EXACT_UPDATERS");
   c->c.exact_updaters = (xe && xe[0] == '1') ? 1 : 0;
   const char* hm = std::getenv("PS_HOT_MIN");
@@ -562,6 +564,20 @@ int ps_model_p2p_overflowed(ps_model* m, int* out) {
 }
 
 /* ---- test hook ---- */
+/* ---- store dump / load ---- */
+int ps_model_save(ps_model* m, const char* path) {
+  PS_TRY
+  PS_REQUIRE(m && path, PS_ERR_ARG, "ps_model_save: null argument");
+  m->m.save(path);
+  PS_CATCH
+}
+int ps_model_load(ps_model* m, const char* path) {
+  PS_TRY
+  PS_REQUIRE(m && path, PS_ERR_ARG, "ps_model_load: null argument");
+  m->m.load(path);
+  PS_CATCH
+}
+
 /* ---- layer.FcLayer standalone ---- */
 int ps_fc_create(ps_ctx* ctx, const char* name, int in, int out, int act, const ps_updater_spec* upd, int max_batch, ps_fc** out_fc) {
   PS_TRY

@@ -122,6 +122,7 @@ struct SmemLayout {
 template <int BLOCK_N, int EPI, bool SPLIT>
 __global__ void __launch_bounds__(SPLIT ? 256 : 128) gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                         const TcParams p) {
+  pdl_launch_dependents();                     /* the next kernel of the chain may set itself up while this one runs */
   using SL = SmemLayout<BLOCK_N, SPLIT>;
   constexpr int STAGES = SL::STAGES;
   constexpr int TMEM_COLS = BLOCK_N <= 32 ? 32 : (BLOCK_N <= 64 ? 64 : (BLOCK_N <= 128 ? 128 : 256));
@@ -156,6 +157,9 @@ __global__ void __launch_bounds__(SPLIT ? 256 : 128) gemm_tf32_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tslot_gen;
+  /* launched as a programmatic dependent of the previous GEMM of the forward / dgrad chain (launch_tc): everything above
+   * (barrier init, tensor-map prefetch, TMEM allocation) overlapped that kernel's tail; its results are read from here on */
+  pdl_wait();
 
   if (warp == 0 && lane == 0) {
     /* ===== TMA producer ===== */
@@ -357,7 +361,17 @@ void launch_tc(Ctx* ctx, const float* A, long lda, const float* B, long ldb, TcP
   const int nkb = (p.K + BK - 1) / BK;
   p.kb_per_split = (nkb + nsplit - 1) / nsplit;
   dim3 grid(ceil_div(p.N, BLOCK_N), ceil_div(p.M, BM), nsplit);
-  gemm_tf32_kernel<BLOCK_N, EPI, SPLIT><<<grid, SPLIT ? 256 : 128, SL::TOTAL, ctx->stream>>>(ta, tb, p);
+  if (ctx->pdl && ctx->pdl_gemm && EPI != EPI_WGRAD) {      /* forward and dgrad GEMMs follow each other on the main stream */
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(SPLIT ? 256 : 128); cfg.dynamicSmemBytes = SL::TOTAL; cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    PS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BLOCK_N, EPI, SPLIT>, ta, tb, p));
+  } else {
+    gemm_tf32_kernel<BLOCK_N, EPI, SPLIT><<<grid, SPLIT ? 256 : 128, SL::TOTAL, ctx->stream>>>(ta, tb, p);
+  }
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }

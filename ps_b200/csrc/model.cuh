@@ -133,6 +133,9 @@ struct Model {
   int get_state(const std::string& key, int which, std::vector<float>& out);
   int tap(const std::string& layer, int what, std::vector<float>& out);
   int64_t num_keys();
+  /* bulk dump / load of every key of the store with its updater state (checkpoint.cu) */
+  void save(const std::string& path);
+  void load(const std::string& path);
   void mark(const char* phase);
   void finish_profile();
 };

@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(256) emb_gather_kernel(const float* __restrict
                                                          int L, int F, float* __restrict__ out, int ldo, const float* __restrict__ X, int Xn,
                                                          int xoff, int N) {
   const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_launch_dependents();                     /* fc0's forward GEMM may set itself up (it waits for this grid before reading) */
   pdl_wait();                                  /* launched as a programmatic dependent of the probe */
   if (g >= (long)L * TPL) {                    /* ConcatLayer.forward (ConcatLayer.java:30-37): numeric features next to the embeddings */
     const long i = g - (long)L * TPL;

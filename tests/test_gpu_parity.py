@@ -483,3 +483,46 @@ def test_fcnn_tf32(ps, ctx):
         assert rel_err(m.tap(f"fc{l}", 0), o.tap(f"fc{l}", 0)) <= 2e-2
         assert fro_err(m.tap(f"fc{l}", 1), o.tap(f"fc{l}", 1)) <= 5e-2
     m.close()
+
+
+# --------------------------------------------------------------------------- store dump / load
+def test_model_save_load_roundtrip(ps, ctx, tmp_path):
+    """Every key of the store with its updater state survives save -> load into a fresh model (of a different table capacity),
+    bit for bit, and the two models then take the same next step."""
+    kind, F, D, Xn, fc, N = "widedeep", 23, 16, 45, [64, 32, 1], 256
+    ctx.set_fc_precision(ps.PS_FC_FP32)
+    a = ps.Model(ctx, kind, F, D, Xn, fc, emb_capacity=1 << 15, max_batch=N)
+    syn = Synth(F=F, Xn=Xn, V=5000, seed=23)
+    batches = [syn.batch(N) for _ in range(4)]
+    for b in batches[:3]:
+        a.train_step(b["E"], b["X"], b["W"], b["Y"])
+    path = str(tmp_path / "store.psb")
+    a.save(path)
+    b2 = ps.Model(ctx, kind, F, D, Xn, fc, emb_capacity=1 << 16, max_batch=N)
+    with pytest.raises(ps.PsError) as e:
+        b2.load(str(tmp_path / "missing.psb"))
+    assert e.value.code == 204
+    b2.load(path)
+    assert b2.num_keys() == a.num_keys()
+    names = [f"fc{l}.{p}" for l in range(len(fc)) for p in ("weights", "bias")] + ["wide.bias"]
+    last = batches[2]
+    names += [ol.key_string(0, j, int(last["E"][n, j])) for n in range(0, N, 5) for j in range(0, F, 3)]
+    names += [ol.key_string(1, 0, int(last["W"][n, 2])) for n in range(0, N, 9)]
+    for k in names:
+        va, vb = a.get(k), b2.get(k)
+        assert va is not None and np.array_equal(va.view(np.uint32), vb.view(np.uint32)), k
+        for which in (0, 1):
+            sa, sb = a.get_state(k, which), b2.get_state(k, which)
+            assert (sa is None) == (sb is None) and (sa is None or np.array_equal(sa.view(np.uint32), sb.view(np.uint32))), (k, which)
+    nb = batches[3]
+    la = a.train_step(nb["E"], nb["X"], nb["W"], nb["Y"])
+    lb = b2.train_step(nb["E"], nb["X"], nb["W"], nb["Y"])
+    assert abs(la - lb) <= 1e-6 * max(1.0, abs(la)), (la, lb)
+    assert rel_err(b2.get("fc0.weights"), a.get("fc0.weights")) <= 1e-6
+    with pytest.raises(ps.PsError):                       # a model that already holds rows refuses to load
+        b2.load(path)
+    c = ps.Model(ctx, "dnn", F, D, Xn, fc, emb_capacity=1 << 15, max_batch=N)
+    with pytest.raises(ps.PsError):                       # shape mismatch
+        c.load(path)
+    for m in (a, b2, c):
+        m.close()
