@@ -327,15 +327,36 @@ def main():
     h2d = sum(pa.nbytes for pa in pinned[0].values())
 
     def host_loop(n, start):
-        if trainer is not None:      # sharded step: stage this rank's slice from pinned host memory, then the step
-            last = None
+        if trainer is not None and args.exchange == "p2p":
+            # peer-memory sharded step through its host-facing call: ps_model_p2p_submit copies this rank's slice from pinned host
+            # memory and enqueues the step's graph, ps_model_collect returns the global loss of the oldest of 2 steps in flight
+            for i in range(n):
+                pb = pinned[(start + i) % len(pinned)]
+                model.p2p_submit_ptrs(hp(pb, "E"), hp(pb, "X"), hp(pb, "W"), hp(pb, "Y"), B)
+                if i >= 1:
+                    model.collect()
+            return model.collect()
+        if trainer is not None:
+            # NCCL sharded step, two steps in flight like submit/collect: stage this rank's slice from pinned host memory on the step's
+            # stream, enqueue the step, copy its loss to pinned memory behind it; the host waits for step i-1 while step i runs
+            from ps_b200.sharded import _DevArray
+            loss_dev = torch.as_tensor(_DevArray(model.loss_dev(), 1), device=f"cuda:{local_rank}")
+            loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+            done = [torch.cuda.Event(), torch.cuda.Event()]
+            keep, last = [None, None], None
             for i in range(n):
                 pb = pinned[(start + i) % len(pinned)]
                 with torch.cuda.stream(stream):
                     d = {k: torch.from_numpy(pa.array).to(f"cuda:{local_rank}", non_blocking=True) for k, pa in pb.items()}
-                trainer.step(d.get("E"), d["X"], d.get("W"), d["Y"])
-                last = model.read_loss()                       # the step's result is read back every step
-            return last
+                    trainer.step(d.get("E"), d["X"], d.get("W"), d["Y"])
+                    loss_host[i & 1].copy_(loss_dev, non_blocking=True)      # the step's result is read back every step
+                    done[i & 1].record(stream)
+                keep[i & 1] = d                                              # inputs stay alive until their step has run
+                if i >= 1:
+                    done[(i - 1) & 1].synchronize()
+                    last = float(loss_host[(i - 1) & 1][0])
+            done[(n - 1) & 1].synchronize()
+            return float(loss_host[(n - 1) & 1][0])
         for i in range(n):
             pb = pinned[(start + i) % len(pinned)]
             model.submit_ptrs(hp(pb, "E"), hp(pb, "X"), hp(pb, "W"), hp(pb, "Y"), B)
@@ -422,9 +443,10 @@ def main():
                                        "+ data-parallel dense") if world > 1 else "single",
                        "l2": "embedding table + optimiser state (%.0f MB) exceeds the 126 MB L2; a ring of %d distinct batches; no flush" % (
                            cap * (16 + 12 * D) / 1e6, len(ring))},
-            "e2e": {"value": total / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
+            "e2e": {"value": total / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 if (trainer is not None and args.exchange != "p2p") else 32,
                     "api": "ps_model_submit/ps_model_collect (2 steps in flight)" if trainer is None else
-                           "pinned host batch -> device (async copy on the step's stream) -> sharded step -> ps_model_read_loss, every step"},
+                           "ps_model_p2p_submit/ps_model_collect (2 steps in flight)" if args.exchange == "p2p" else
+                           "pinned host batch -> device (async copy on the step's stream) -> sharded step -> async loss copy to pinned memory, every step; 2 steps in flight"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_large_batch": large, "kernels_us": phase_us, "hbm_kernels": kernels,
             "cpu_baseline": cpu, "loss": loss, "loss_e2e": loss_e2e, "unique_keys_per_batch": uniq,
         }

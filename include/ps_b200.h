@@ -166,6 +166,9 @@ int ps_model_collect(ps_model* m, float* loss);
  * device until ps_model_read_loss.                                                         */
 int ps_model_train_step_dev(ps_model* m, const int64_t* E_dev, const float* X_dev, const int64_t* W_dev, const float* Y_dev, int N);
 int ps_model_read_loss(ps_model* m, float* loss);
+/* device address of the step's result (a float: the loss Model.train returns, Model.java:11), valid after any *_dev step:
+ * lets a pipelined caller copy it out asynchronously on ps_ctx_stream instead of synchronising in ps_model_read_loss */
+int ps_model_loss_dev(ps_model* m, const float** loss_dev);
 /* PredictThread.call + Trainer.predict (train/PredictThread.java, Trainer.java:44-68)      */
 int ps_model_predict(ps_model* m, const int64_t* E, const float* X, const int64_t* W, int N, float* out);
 /* KVStore.get(String) on any key the reference would hold: "fc0.weights" (out x in, column
@@ -248,6 +251,9 @@ int ps_model_shard_apply_dev(ps_model* m, const float* grads_recv_dev, int n);
 int ps_model_p2p_init(ps_model* m, int R, int rank, int cap, void* ipc_handle_out64);
 int ps_model_p2p_connect(ps_model* m, const void* all_handles /* R x 64 bytes */);
 int ps_model_p2p_step_dev(ps_model* m, const int64_t* E_dev, const float* X_dev, const int64_t* W_dev, const float* Y_dev, int N);
+/* the pipelined host-facing form (ps_model_submit's twin): this rank's slice from (pinned) HOST memory, at most 2 steps in
+ * flight, ps_model_collect returns the GLOBAL loss of the oldest                                                           */
+int ps_model_p2p_submit(ps_model* m, const int64_t* E, const float* X, const int64_t* W, const float* Y, int N);
 int ps_model_p2p_overflowed(ps_model* m, int* out);   /* a bucket exceeded cap at some step: results invalid, raise cap */
 
 /* ---- libsvm ingest feeding the step (host code: callable without a GPU) ---------------------------

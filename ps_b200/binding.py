@@ -78,6 +78,7 @@ SYMBOLS = {
     "ps_model_collect": (_i, [_vp, C.POINTER(_f)]),
     "ps_model_train_step_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _i]),
     "ps_model_read_loss": (_i, [_vp, C.POINTER(_f)]),
+    "ps_model_loss_dev": (_i, [_vp, _pp]),
     "ps_model_predict": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     "ps_model_get": (_i, [_vp, C.c_char_p, _vp, _i, C.POINTER(_i)]),
     "ps_model_put": (_i, [_vp, C.c_char_p, _vp, _i]),
@@ -104,6 +105,7 @@ SYMBOLS = {
     "ps_model_p2p_init": (_i, [_vp, _i, _i, _i, _vp]),
     "ps_model_p2p_connect": (_i, [_vp, _vp]),
     "ps_model_p2p_step_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _i]),
+    "ps_model_p2p_submit": (_i, [_vp, _vp, _vp, _vp, _vp, _i]),
     "ps_model_p2p_overflowed": (_i, [_vp, C.POINTER(_i)]),
     "ps_fc_create": (_i, [_vp, C.c_char_p, _i, _i, _i, C.POINTER(UpdaterSpec), _i, _pp]),
     "ps_fc_destroy": (_i, [_vp]),
@@ -416,6 +418,9 @@ class Model:
         check(lib().ps_model_collect(self.h, C.byref(loss)))
         return loss.value
 
+    def p2p_submit_ptrs(self, E, X, W, Y, N):
+        check(lib().ps_model_p2p_submit(self.h, E, X, W, Y, N))
+
     def train_step_dev(self, E, X, W, Y, N):
         check(lib().ps_model_train_step_dev(self.h, E, X, W, Y, N))
 
@@ -423,6 +428,12 @@ class Model:
         loss = C.c_float()
         check(lib().ps_model_read_loss(self.h, C.byref(loss)))
         return loss.value
+
+    def loss_dev(self):
+        """Device address of the step's loss (for asynchronous copies on the library's stream)."""
+        p = C.c_void_p()
+        check(lib().ps_model_loss_dev(self.h, C.byref(p)))
+        return p.value
 
     def predict(self, E, X, W, N, out_rows=1):
         E, W, X = _c(E, np.int64), _c(W, np.int64), _c(X, np.float32)

@@ -4,6 +4,7 @@
  * on the CPU — if no CUDA device is present ps_ctx_create fails with PS_ERR_CUDA.
  */
 #include <cmath>
+#include <cstddef>
 #include <cstdlib>
 #include <mutex>
 #include <string>
@@ -65,7 +66,7 @@ int ps_ctx_create(int device, uint64_t seed, ps_ctx** out) {
   const char* pd = std::getenv("PS_PDL");
   c->c.pdl = (pd && pd[0] == '0') ? 0 : 1;
   const char* pg = std::getenv("PS_PDL_GEMM");
-  c->c.pdl_gemm = (pg && pg[0] == '0') ? 0 : 1;
+  c->c.pdl_gemm = (pg && pg[0] == '1') ? 1 : 0;
   const char* xe = std::getenv("PS_EXACT_UPDATERS");
   c->c.exact_updaters = (xe && xe[0] == '1') ? 1 : 0;
   const char* hm = std::getenv("PS_HOT_MIN");
@@ -372,6 +373,12 @@ int ps_model_read_loss(ps_model* m, float* loss) {
   *loss = m->m.read_loss();
   PS_CATCH
 }
+int ps_model_loss_dev(ps_model* m, const float** loss_dev) {
+  PS_TRY
+  PS_REQUIRE(m && loss_dev, PS_ERR_ARG, "null argument");
+  *loss_dev = reinterpret_cast<const float*>(reinterpret_cast<const char*>(m->m.st_dev) + offsetof(StepStatus, loss));
+  PS_CATCH
+}
 int ps_model_predict(ps_model* m, const int64_t* E, const float* X, const int64_t* W, int N, float* out) {
   PS_TRY
   PS_REQUIRE(m && X && out, PS_ERR_ARG, "null argument");
@@ -554,6 +561,13 @@ int ps_model_p2p_step_dev(ps_model* m, const int64_t* E_dev, const float* X_dev,
   PS_REQUIRE(m && X_dev && Y_dev, PS_ERR_ARG, "null argument");
   PS_REQUIRE(m->m.in_flight == 0, PS_ERR_STATE, "host steps in flight; collect first");
   m->m.run_step(E_dev, X_dev, W_dev, Y_dev, N, true, nullptr, 1);
+  PS_CATCH
+}
+int ps_model_p2p_submit(ps_model* m, const int64_t* E, const float* X, const int64_t* W, const float* Y, int N) {
+  PS_TRY
+  PS_REQUIRE(m != nullptr, PS_ERR_ARG, "null model");
+  HostBatch b; b.E = E; b.X = X; b.W = W; b.Y = Y; b.N = N;
+  m->m.submit(b, 1);
   PS_CATCH
 }
 int ps_model_p2p_overflowed(ps_model* m, int* out) {

@@ -167,7 +167,8 @@ void Model::run_step(const int64_t* E, const float* X, const int64_t* W, const f
   PS_REQUIRE(N > 0 && N <= Bmax, PS_ERR_ARG, "model: batch size must be in [1, max_batch]");
   if (!use_graph) {
     ev_n = 0; ev_names.clear();
-    if (mode == 1) p2p_step(E, X, W, Y, N); else step_device(E, X, W, Y, N, train, publish_to);
+    if (mode == 1) { p2p_step(E, X, W, Y, N); if (publish_to) publish_status(ctx, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, publish_to); }
+    else step_device(E, X, W, Y, N, train, publish_to);
     phase_names = ev_names;
     return;
   }
@@ -183,7 +184,10 @@ void Model::run_step(const int64_t* E, const float* X, const int64_t* W, const f
     cudaGraph_t graph = nullptr;
     PS_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
     capturing = true; ev_n = 0; ev_names.clear();
-    try { if (mode == 1) p2p_step(E, X, W, Y, N); else step_device(E, X, W, Y, N, train, publish_to); }
+    try {
+      if (mode == 1) { p2p_step(E, X, W, Y, N); if (publish_to) publish_status(ctx, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, publish_to); }
+      else step_device(E, X, W, Y, N, train, publish_to);
+    }
     catch (...) { capturing = false; cudaStreamEndCapture(ctx->stream, &graph); if (graph) cudaGraphDestroy(graph); throw; }
     capturing = false;
     PS_CUDA(cudaStreamEndCapture(ctx->stream, &graph));
@@ -558,7 +562,7 @@ void Model::gemm_times(int N, int reps, float* out) {
   cudaEventDestroy(e0); cudaEventDestroy(e1);
 }
 
-void Model::submit(const HostBatch& b) {
+void Model::submit(const HostBatch& b, int mode) {
   PS_REQUIRE(in_flight < 2, PS_ERR_STATE, "model: two steps already in flight; collect first");
   PS_REQUIRE(b.N > 0 && b.N <= Bmax, PS_ERR_ARG, "model: batch size must be in [1, max_batch]");
   PS_REQUIRE(b.X && b.Y && (!has_emb || b.E) && (!has_wide || b.W), PS_ERR_ARG, "model: missing input matrix");
@@ -572,7 +576,7 @@ void Model::submit(const HostBatch& b) {
   PS_CUDA(cudaEventRecord(S.h2d_done, cs));
   PS_CUDA(cudaStreamWaitEvent(ctx->stream, S.h2d_done, 0));
   S.N = b.N;
-  run_step(S.E, S.X, S.W, S.Y, b.N, true, S.st_host);
+  run_step(S.E, S.X, S.W, S.Y, b.N, true, S.st_host, mode);
   PS_CUDA(cudaEventRecord(S.step_done, ctx->stream));
   S.busy = true;
   next_stage ^= 1; in_flight++;

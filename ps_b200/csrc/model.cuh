@@ -124,7 +124,7 @@ struct Model {
   void p2p_init(int R, int rank, int cap, void* handle_out64);
   void p2p_connect(const void* all_handles);
   void p2p_step(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N);
-  void submit(const HostBatch& b);
+  void submit(const HostBatch& b, int mode = 0);     /* mode 1: the peer-memory sharded step (this rank's slice of the global batch) */
   float collect();
   float read_loss();
   void predict(const HostBatch& b, float* out);
