@@ -136,6 +136,43 @@ inline bool parse_float_fast(const char* b, const char* e, float* out) {
   return true;
 }
 
+/* The common token "digits:decimal" in ONE pass over its bytes (idx up to 18 digits: cannot overflow a long; value as in
+ * parse_float_fast).  Leaves p at the token's end on success; on anything unusual returns false with p untouched and the
+ * general code below decides. */
+inline bool fast_pair(const char*& p, const char* e, int64_t* idx, float* val) {
+  static const float p10[11] = {1.f, 1e1f, 1e2f, 1e3f, 1e4f, 1e5f, 1e6f, 1e7f, 1e8f, 1e9f, 1e10f};
+  const char* q = p;
+  uint64_t v = 0;
+  int nd = 0;
+  while (q < e && (unsigned)(*q - '0') <= 9u) { v = v * 10 + (uint64_t)(*q - '0'); ++q; ++nd; }
+  if (nd == 0 || nd > 18 || q >= e || *q != ':') return false;
+  ++q;
+  bool neg = false;
+  if (q < e && *q == '-') { neg = true; ++q; }
+  uint32_t m = 0;
+  int sig = 0, k = 0, digits = 0;
+  bool dot = false;
+  for (; q < e && *q != ' '; ++q) {
+    const unsigned d = (unsigned)(*q - '0');
+    if (d <= 9u) {
+      m = m * 10 + d; ++digits;
+      if (m != 0 || sig > 0) ++sig;
+      if (dot) ++k;
+      if (sig > 7 || k > 10) return false;
+    } else if (*q == '.' && !dot) {
+      dot = true;
+    } else {
+      return false;
+    }
+  }
+  if (digits == 0) return false;
+  const float f = (float)m / p10[k];
+  *idx = (int64_t)v;
+  *val = neg ? -f : f;
+  p = q;
+  return true;
+}
+
 }  // namespace
 
 /* One line -> one row of E/X/W/Y.  Returns LINE_OK, LINE_SHORT (blank or fewer than 1+F+Xn columns: IndexOutOfBounds in
@@ -155,12 +192,17 @@ int parse_ctr_line(const char* b, const char* e, int F, int Xn, int64_t wide, in
   const char* p = b;
   while (true) {
     const char* t = p;
-    while (t < e && *t != ' ') ++t;              /* token [p, t) */
+    int64_t idx;
+    float val;
+    bool have_pair = false;
+    if (col > 0 && fast_pair(t, e, &idx, &val)) have_pair = true;        /* t now at the token's end */
+    else while (t < e && *t != ' ') ++t;         /* token [p, t) */
     if (col == 0) {
       float y;
       if (!parse_float_fast(p, t, &y) && !parse_float(p, t, &y)) return LINE_BAD;
       if (Y) *Y = y;
     } else {
+      if (!have_pair) {
       const char* c = p;
       while (c < t && *c != ':') ++c;            /* pair[0] = [p, c) */
       if (c == t) {                              /* no ':' — "abc".split(":") has one element, pair[1] throws; "5:" likewise */
@@ -173,14 +215,14 @@ int parse_ctr_line(const char* b, const char* e, int F, int Xn, int64_t wide, in
       bool only_empty_after = true;
       for (const char* z = v; z < t; ++z) if (*z != ':') { only_empty_after = false; break; }
       if (only_empty_after) return LINE_BAD;
-      int64_t idx;
-      float val;
       if (!parse_long(p, c, &idx)) return LINE_BAD;
       if (!parse_float_fast(v, ve, &val) && !parse_float(v, ve, &val)) return LINE_BAD;
+      }
       if (col <= F) {
         const float idf = (float)idx;            /* E[j-1][i] = cols.get(j).getIdx()  (long -> float, CTR.java:57) */
         if (E) E[col - 1] = (int64_t)idf;
-        if (W) W[col - 1] = (int64_t)std::fmod(idf, (float)wide);   /* result.data[i] % size in float (MatrixUtil.java:30) */
+        /* result.data[i] % size in float (MatrixUtil.java:30): exact integer arithmetic while the id survives the float cast */
+        if (W) W[col - 1] = (idx >= 0 && idx < (1 << 24) && wide < (1 << 24)) ? idx % wide : (int64_t)std::fmod(idf, (float)wide);
       } else if (col < need) {
         if (X) X[col - 1 - F] = val;             /* X[j-24][i] = cols.get(j).toF() */
       }
