@@ -139,6 +139,76 @@ def time_oracle(cfg, batches, budget_s, threads):
     return n * cfg["B"] / dt, n, gemm, dt
 
 
+def time_oracle_replicas(cfg, batches, budget_s, replicas):
+    """`replicas` independent copies of the standalone Trainer step (thread = 1 each, single-threaded sgemm), one per host thread:
+    an UPPER bound for the reference's Trainer with thread = replicas, whose replicas share one synchronized KVStore
+    (KVStore.java:136,192,240) and serialise on it.  ctypes releases the GIL inside the C call, so the steps run in parallel."""
+    import oracle_lib as ol
+    os.environ["OMP_NUM_THREADS"] = "1"
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    gemm = "openmp-loops"
+    ob = ol.openblas_path()
+    if ob and ol.lib().pso_set_gemm(2, ob.encode()) == 0:
+        gemm = "openblas-0.3.30 (numpy bundled), 1 thread per replica"
+    else:
+        ol.lib().pso_set_gemm(1, None)
+    models = [oracle_model(cfg, 20261017 + r) for r in range(replicas)]
+    for r, o in enumerate(models):                                   # warm-up: creates keys
+        b = batches[r % len(batches)]
+        o.train_step(b.get("E"), b["X"], b.get("W"), b["Y"])
+    counts = [0] * replicas
+    t0 = time.perf_counter()
+
+    def work(r):
+        o, n = models[r], 0
+        while time.perf_counter() - t0 < budget_s and n < 64:
+            b = batches[(r + n + 1) % len(batches)]
+            o.train_step(b.get("E"), b["X"], b.get("W"), b["Y"])
+            n += 1
+        counts[r] = n
+    ths = [threading.Thread(target=work, args=(r,)) for r in range(replicas)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    ol.lib().pso_set_gemm(0, None)
+    return sum(counts) * cfg["B"] / dt, sum(counts), gemm, dt
+
+
+def time_ingest(ps, cfg, batch, threads):
+    """libsvm text -> the step's staging layout through the native reader: one synthetic batch written as text in the
+    reference's own line format (label, F "idx:1" columns, Xn "idx:value" columns), read back for about a second on the host cores."""
+    import tempfile
+    F, Xn, B = cfg["F"], cfg["Xn"], cfg["B"]
+    if not F:
+        return None
+    lines = []
+    for n in range(min(B, 4096)):
+        cols = ["%d" % int(batch["Y"][n])] + ["%d:1" % int(batch["E"][n, j]) for j in range(F)] + ["%d:%.2f" % (33895 + x, batch["X"][n, x]) for x in range(Xn)]
+        lines.append(" ".join(cols))
+    with tempfile.NamedTemporaryFile("w", suffix=".libsvm", delete=False) as f:
+        f.write("\n".join(lines) + "\n")
+        path = f.name
+    try:
+        r = ps.LibsvmReader(path, F=F, Xn=Xn, batch=len(lines), threads=threads)
+        bufs = dict(E=np.empty((len(lines), F), np.int64), W=np.empty((len(lines), F), np.int64), X=np.empty((len(lines), Xn), np.float32), Y=np.empty(len(lines), np.float32))
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < 1.0:
+            b = r.next(bufs)
+            if b is None:
+                r.reset()
+                continue
+            n += len(b["Y"])
+        dt = time.perf_counter() - t0
+        ok = bool(np.array_equal(bufs["E"][: len(lines)], batch["E"][: len(lines)]) and np.array_equal(bufs["X"][: len(lines)], batch["X"][: len(lines)]))
+        r.close()
+        return {"lines_per_s": n / dt, "threads": threads, "bytes_per_line": os.path.getsize(path) / len(lines), "roundtrip_exact": ok,
+                "sample": f"{n} lines of {len(lines)}-line synthetic libsvm text in {dt:.2f}s through ps_reader_next"}
+    finally:
+        os.unlink(path)
+
+
 def run_reference(args, cfg, rank):
     if rank != 0:
         return
@@ -147,14 +217,15 @@ def run_reference(args, cfg, rank):
     threads = os.cpu_count() or 1
     per_step_budget = 4.0
     total = args.steps + args.warmup
-    sps, n, gemm, dt = time_oracle(cfg, batches, min(150.0, per_step_budget * total), threads)
+    sps, n, gemm, dt = time_oracle_replicas(cfg, batches, min(60.0, per_step_budget * total), threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * cfg["B"] / sps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": {"workload": workload_name(args, cfg), "global_batch": cfg["B"]},
         "cpu_baseline": {"value": sps, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{n} Trainer steps of batch {cfg['B']} in {dt:.1f}s; C++ restatement of the reference's standalone Java path "
-                                   f"(JVM/jblas unavailable in this image); sgemm={gemm}; everything but sgemm is single-threaded like thread=1"},
+                         "sample": f"{n} Trainer steps of batch {cfg['B']} in {dt:.1f}s over {threads} independent replicas (one per host thread, thread=1 each): "
+                                   f"an upper bound for the reference's Trainer with thread={threads}, which shares one synchronized KVStore; C++ restatement of the "
+                                   f"reference's standalone Java path (JVM/jblas unavailable in this image); sgemm={gemm}"},
         "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -336,27 +407,15 @@ def main():
                 if i >= 1:
                     model.collect()
             return model.collect()
-        if trainer is not None:
-            # NCCL sharded step, two steps in flight like submit/collect: stage this rank's slice from pinned host memory on the step's
-            # stream, enqueue the step, copy its loss to pinned memory behind it; the host waits for step i-1 while step i runs
-            from ps_b200.sharded import _DevArray
-            loss_dev = torch.as_tensor(_DevArray(model.loss_dev(), 1), device=f"cuda:{local_rank}")
-            loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
-            done = [torch.cuda.Event(), torch.cuda.Event()]
-            keep, last = [None, None], None
+        if trainer is not None:      # NCCL sharded step: stage this rank's slice from pinned host memory, then the step, then its loss
+            last = None
             for i in range(n):
                 pb = pinned[(start + i) % len(pinned)]
                 with torch.cuda.stream(stream):
                     d = {k: torch.from_numpy(pa.array).to(f"cuda:{local_rank}", non_blocking=True) for k, pa in pb.items()}
-                    trainer.step(d.get("E"), d["X"], d.get("W"), d["Y"])
-                    loss_host[i & 1].copy_(loss_dev, non_blocking=True)      # the step's result is read back every step
-                    done[i & 1].record(stream)
-                keep[i & 1] = d                                              # inputs stay alive until their step has run
-                if i >= 1:
-                    done[(i - 1) & 1].synchronize()
-                    last = float(loss_host[(i - 1) & 1][0])
-            done[(n - 1) & 1].synchronize()
-            return float(loss_host[(n - 1) & 1][0])
+                trainer.step(d.get("E"), d["X"], d.get("W"), d["Y"])
+                last = model.read_loss()                       # the step's result is read back every step
+            return last
         for i in range(n):
             pb = pinned[(start + i) % len(pinned)]
             model.submit_ptrs(hp(pb, "E"), hp(pb, "X"), hp(pb, "W"), hp(pb, "Y"), B)
@@ -432,6 +491,12 @@ def main():
             cpu = {"value": sps, "unit": UNIT, "cores": 1, "kind": "port",
                    "sample": f"{n} Trainer steps of batch {B} in {dt:.1f}s, thread=1 (CTR.java:72); C++ restatement of the reference's standalone "
                              f"Java path (no JVM in this image); sgemm={gemm} single-threaded"}
+        ingest = None
+        if world == 1 and trainer is None:
+            try:
+                ingest = time_ingest(ps, cfg, ring[0], min(16, os.cpu_count() or 1))
+            except Exception as e:        # the reader is host-side plumbing: never fail the bench line over it
+                ingest = {"error": str(e)}
         total = B * world * args.steps
         line = {
             "metric": METRIC, "value": total / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -443,12 +508,12 @@ def main():
                                        "+ data-parallel dense") if world > 1 else "single",
                        "l2": "embedding table + optimiser state (%.0f MB) exceeds the 126 MB L2; a ring of %d distinct batches; no flush" % (
                            cap * (16 + 12 * D) / 1e6, len(ring))},
-            "e2e": {"value": total / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 if (trainer is not None and args.exchange != "p2p") else 32,
+            "e2e": {"value": total / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
                     "api": "ps_model_submit/ps_model_collect (2 steps in flight)" if trainer is None else
                            "ps_model_p2p_submit/ps_model_collect (2 steps in flight)" if args.exchange == "p2p" else
-                           "pinned host batch -> device (async copy on the step's stream) -> sharded step -> async loss copy to pinned memory, every step; 2 steps in flight"},
+                           "pinned host batch -> device (async copy on the step's stream) -> sharded step -> ps_model_read_loss, every step"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_large_batch": large, "kernels_us": phase_us, "hbm_kernels": kernels,
-            "cpu_baseline": cpu, "loss": loss, "loss_e2e": loss_e2e, "unique_keys_per_batch": uniq,
+            "cpu_baseline": cpu, "ingest": ingest, "loss": loss, "loss_e2e": loss_e2e, "unique_keys_per_batch": uniq,
         }
         print(json.dumps(line), flush=True)
     sys.stdout.flush()
