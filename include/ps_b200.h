@@ -266,6 +266,15 @@ int ps_model_p2p_overflowed(ps_model* m, int* out);   /* a bucket exceeded cap a
  *   swallowed exceptions are lost here too (counted in ps_reader_stats).  A background thread keeps parsed batches ahead
  *   of the consumer; ps_reader_next copies one into the caller's buffers — E, W: [rows][F] int64, X: [rows][Xn], Y: [rows],
  *   the layout ps_model_train_step / ps_model_submit take — and returns *rows = 0 at end of data (DataSet.next() == null). */
+/* The same parse ON the GPU, for training straight from text at step speed (raw text is ~700 B per line: PCIe carries it; the host
+ * parser does not keep up).  text_dev: `len` bytes (< 4 GiB) of complete lines in DEVICE memory, each terminated by '\n'.  At most
+ * max_rows lines are parsed into E_dev, W_dev [rows][F], X_dev [rows][Xn], Y_dev [rows]; status_dev[r]: 0 ok, 1 blank / short line,
+ * 2 = a spelling outside the fast path (exponent, suffix, hex float, NaN / Infinity, signed index, empty token ...): nothing was
+ * guessed — re-parse that line with ps_libsvm_parse_line.  Rows with status 0 are bit-identical to the host parser's.
+ * *rows = number of lines parsed (the first max_rows of those present; a last line without '\n' is not a line yet).  Kernels
+ * run on ps_ctx_stream; the call returns once the line count is known.                                                      */
+int ps_libsvm_parse_dev(ps_ctx* ctx, const char* text_dev, size_t len, int F, int Xn, int64_t wide_size, int max_rows,
+                        int64_t* E_dev, float* X_dev, int64_t* W_dev, float* Y_dev, uint8_t* status_dev, int* rows);
 typedef struct ps_reader ps_reader;
 int ps_libsvm_parse_line(const char* line, size_t len, int F, int Xn, int64_t wide_size, int64_t* E, float* X, int64_t* W, float* Y, int* status);
 int ps_reader_open(const char* path, int F, int Xn, int64_t wide_size, int batch, int offset, int step, int threads, ps_reader** out);

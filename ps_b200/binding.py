@@ -116,6 +116,7 @@ SYMBOLS = {
     "ps_fc_get": (_i, [_vp, _i, _vp, _i, C.POINTER(_i)]),
     "ps_fc_put": (_i, [_vp, _i, _vp, _i]),
     "ps_libsvm_parse_line": (_i, [C.c_char_p, C.c_size_t, _i, _i, _i64, _vp, _vp, _vp, _vp, C.POINTER(_i)]),
+    "ps_libsvm_parse_dev": (_i, [_vp, _vp, C.c_size_t, _i, _i, _i64, _i, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i)]),
     "ps_reader_open": (_i, [C.c_char_p, _i, _i, _i64, _i, _i, _i, _i, _pp]),
     "ps_reader_next": (_i, [_vp, _vp, _vp, _vp, _vp, C.POINTER(_i)]),
     "ps_reader_reset": (_i, [_vp]),
@@ -313,6 +314,13 @@ class Context:
         sms, ma, mi = C.c_int(), C.c_int(), C.c_int()
         check(lib().ps_ctx_device_info(self.h, name, 128, C.byref(sms), C.byref(ma), C.byref(mi)))
         return dict(name=name.value.decode(), sms=sms.value, cc=(ma.value, mi.value))
+
+    def parse_libsvm_dev(self, text_dev, nbytes, F, Xn, wide_size, max_rows, E_dev, X_dev, W_dev, Y_dev, status_dev):
+        """GPU-side libsvm parse (device pointers as ints); returns the number of lines found."""
+        rows = C.c_int()
+        check(lib().ps_libsvm_parse_dev(self.h, C.c_void_p(text_dev), nbytes, F, Xn, wide_size, max_rows, C.c_void_p(E_dev), C.c_void_p(X_dev),
+                                        C.c_void_p(W_dev), C.c_void_p(Y_dev), C.c_void_p(status_dev), C.byref(rows)))
+        return rows.value
 
     def updater_apply(self, spec, w, s1, s2, g):
         check(lib().ps_updater_apply(self.h, C.byref(spec), _p(w), _p(s1), _p(s2), _p(g), w.size))

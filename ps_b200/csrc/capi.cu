@@ -21,7 +21,7 @@ void set_last_error(const std::string& s) { g_last_error = s; }
 
 using namespace psb;
 
-struct ps_ctx { Ctx c; };
+struct ps_ctx { Ctx c; uint32_t* ingest_ws = nullptr; size_t ingest_ws_cap = 0; };
 struct ps_model { Model m; };
 struct ps_fc { FcOp op; };
 struct ps_reader { std::unique_ptr<LibsvmReader> r; };
@@ -81,6 +81,7 @@ int ps_ctx_destroy(ps_ctx* ctx) {
   if (ctx) {
     cudaStreamSynchronize(ctx->c.stream);
     cudaStreamDestroy(ctx->c.stream); cudaStreamDestroy(ctx->c.copy_stream);
+    dfree(ctx->ingest_ws);
     delete ctx;
   }
   PS_CATCH
@@ -657,6 +658,21 @@ int ps_libsvm_parse_line(const char* line, size_t len, int F, int Xn, int64_t wi
   if (e > line && e[-1] == '\n') --e;
   if (e > line && e[-1] == '\r') --e;
   *status = parse_ctr_line(line, e, F, Xn, wide_size, E, X, W, Y);
+  PS_CATCH
+}
+int ps_libsvm_parse_dev(ps_ctx* ctx, const char* text_dev, size_t len, int F, int Xn, int64_t wide_size, int max_rows, int64_t* E_dev, float* X_dev,
+                        int64_t* W_dev, float* Y_dev, uint8_t* status_dev, int* rows) {
+  PS_TRY
+  PS_REQUIRE(ctx != nullptr && rows != nullptr && max_rows > 0, PS_ERR_ARG, "ps_libsvm_parse_dev: bad argument");
+  const size_t need = len / 4096 + 2 + (size_t)max_rows;
+  if (need > ctx->ingest_ws_cap) {
+    PS_CUDA(cudaStreamSynchronize(ctx->c.stream));
+    dfree(ctx->ingest_ws);
+    ctx->ingest_ws = nullptr; ctx->ingest_ws_cap = 0;
+    ctx->ingest_ws = dmalloc<uint32_t>(need);
+    ctx->ingest_ws_cap = need;
+  }
+  *rows = libsvm_parse_dev(&ctx->c, text_dev, len, F, Xn, wide_size, max_rows, E_dev, X_dev, W_dev, Y_dev, status_dev, ctx->ingest_ws);
   PS_CATCH
 }
 int ps_reader_open(const char* path, int F, int Xn, int64_t wide_size, int batch, int offset, int step, int threads, ps_reader** out) {

@@ -21,6 +21,11 @@ enum { LINE_OK = 0, LINE_SHORT = 1, LINE_BAD = 2 };
 /* one text line [b, e) -> one sample: E[F], X[Xn], W[F], Y[1] (any output may be null) */
 int parse_ctr_line(const char* b, const char* e, int F, int Xn, int64_t wide, int64_t* E, float* X, int64_t* W, float* Y);
 
+/* the same on the GPU for the spellings the fast path accepts (ingest_dev.cu): device pointers, asynchronous on ctx->stream except
+ * for the line count it returns; status 2 = spelling outside the fast path, re-parse that line on the host */
+int libsvm_parse_dev(Ctx* ctx, const char* text_dev, size_t len, int F, int Xn, int64_t wide, int max_rows, int64_t* E, float* X, int64_t* W, float* Y,
+                     uint8_t* status, uint32_t* ws /* >= len / 4096 + 2 + max_rows uint32 */);
+
 struct LibsvmReader {
   struct Batch;
   int F, Xn;

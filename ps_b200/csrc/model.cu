@@ -174,6 +174,11 @@ void Model::run_step(const int64_t* E, const float* X, const int64_t* W, const f
   }
   const auto key = std::make_tuple((const void*)E, (const void*)X, (const void*)W, (const void*)Y, N, (train ? 1 : 0) | (profile ? 2 : 0) | (mode << 2) | (ctx->exact_updaters << 6),
                                    (const void*)publish_to, ctx->fc_precision);
+  if (has_emb && emb.generation != emb_generation) {     /* the embedding workspace was reallocated (p2p_init, a larger shard lookup) */
+    for (auto& g : graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+    graphs.clear();
+    emb_generation = emb.generation;
+  }
   auto it = graphs.find(key);
   if (it == graphs.end()) {
     if (graphs.size() >= 256) {

@@ -65,6 +65,7 @@ struct Model {
   void fork(cudaStream_t from, cudaStream_t to);
   /* one CUDA graph per (input buffers, batch size, mode): a step is ~25 small launches, replayed as one */
   bool use_graph = true;
+  int emb_generation = 0;        /* EmbTable::generation the cached graphs were captured with */
   struct GraphEntry { cudaGraphExec_t exec = nullptr; long kernels = 0; std::vector<std::string> names; };
   std::map<std::tuple<const void*, const void*, const void*, const void*, int, int, const void*, int>, GraphEntry> graphs;
   /* two staging sets so the H2D of step i+1 overlaps the kernels of step i */

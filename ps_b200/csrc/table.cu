@@ -523,7 +523,7 @@ void EmbTable::reserve(int64_t L) {
   if (L <= Lcap) return;
   PS_CUDA(cudaStreamSynchronize(ctx->stream));
   dfree(lk_slot); dfree(acc);
-  Lcap = L;
+  Lcap = L; ++generation;                      /* captured graphs that hold the old workspace pointers are stale now */
   lk_slot = dmalloc<int32_t>((size_t)L);
   acc = dmalloc_zero<float>((size_t)L * Dp, ctx->stream);   /* one accumulator row per lookup index; a batch uses those of its keys' first lookups */
 }

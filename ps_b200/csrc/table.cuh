@@ -50,6 +50,7 @@ struct EmbTable {
   float *w = nullptr, *s1 = nullptr, *s2 = nullptr;
   /* per-batch workspace */
   int64_t Lcap = 0;
+  int generation = 0;                  /* bumped whenever reserve() reallocates the workspace */
   int32_t* lk_slot = nullptr;
   float* acc = nullptr;
   uint32_t* counters = nullptr;        /* [0] monotonic count of updated (unique) keys, [1] error flag, [2..3] u64 row count */

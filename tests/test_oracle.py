@@ -196,3 +196,71 @@ def test_fcnn_runs_and_learns():
     Y = rng.integers(0, 4, N).astype(np.float32)
     losses = [o.train_step(None, X, None, Y) for _ in range(30)]
     assert np.isfinite(losses).all() and losses[-1] < losses[0]
+
+
+def _numpy_fcnn_step(o, Xn, fc, X, Y):
+    """One FullConnectedNN Trainer step (FullConnectedNN.java:37-68) written from the Java sources: FcLayer/ReLU stack, Softmax(10000)
+    (Softmax.java:21-45: divide by the scale in place, shift by the column max, exp in double, clip exact 0/1), SoftmaxLoss
+    (SoftmaxLoss.java:9-28), Softmax.backward (:47-67, which does NOT undo the 1/scale) and FcLayer.backward."""
+    N = Y.shape[0]
+    A = [X.T.astype(np.float32)]
+    Ws = []
+    for l, out in enumerate(fc):
+        W = o.get(f"fc{l}.weights").reshape(A[-1].shape[0], out).T
+        bias = o.get(f"fc{l}.bias")
+        Z = (W.astype(np.float64) @ A[-1].astype(np.float64)).astype(np.float32) + bias[:, None]
+        if l < len(fc) - 1:
+            Z = np.maximum(Z, 0)
+        else:
+            Z = (Z / np.float32(10000)).astype(np.float32)
+            ex = np.exp((Z - Z.max(0, keepdims=True)).astype(np.float64)).astype(np.float32)
+            Z = (ex / ex.sum(0, keepdims=True, dtype=np.float32)).astype(np.float32)
+            Z = np.where(Z == 0, np.float32(0.001), np.where(Z == 1, np.float32(0.999), Z)).astype(np.float32)
+        A.append(Z.astype(np.float32))
+        Ws.append(W)
+    P = A[-1]
+    hot = Y.astype(np.int64)
+    p = P[hot, np.arange(N)]
+    loss = np.float32(np.sum(-np.log(p.astype(np.float64))) / N)
+    d = np.zeros_like(P, dtype=np.float64)
+    for i in range(N):                                          # Softmax.backward on dy = -1/p at the hot class only
+        j = hot[i]
+        dy = -1.0 / np.float64(p[i])
+        for k in range(P.shape[0]):
+            d[k, i] = (P[k, i] * (1 - P[k, i]) if k == j else -P[j, i] * P[k, i]) * dy
+    d = d.astype(np.float32)
+    grads = {}
+    for l in range(len(fc) - 1, -1, -1):
+        grads[f"fc{l}.bias"] = d.mean(1)
+        grads[f"fc{l}.weights"] = (d.astype(np.float64) @ A[l].T.astype(np.float64) / N).astype(np.float32)
+        dprev = (Ws[l].T.astype(np.float64) @ d.astype(np.float64)).astype(np.float32)
+        if l > 0:
+            dprev = dprev * (A[l] > 0)
+        d = dprev
+    return loss, P, grads
+
+
+def test_oracle_fcnn_step_against_independent_numpy():
+    """Pins the cfg5 (Mnist.java) path of the oracle the way the DNN / WideDeepNN step is pinned above."""
+    Xn, fc, N = 7, [6, 5, 4], 11
+    o = ol.OracleModel(ol.KIND_FCNN, 0, 0, Xn, fc, 9)
+    rng = np.random.default_rng(4)
+    X0 = (rng.random((N, Xn)) * 255).astype(np.float32)
+    Y0 = rng.integers(0, 4, N).astype(np.float32)
+    o.train_step(None, X0, None, Y0)                            # non-trivial Adam state
+    for _ in range(2):
+        X = (rng.random((N, Xn)) * 255).astype(np.float32)
+        Y = rng.integers(0, 4, N).astype(np.float32)
+        loss_np, P, grads = _numpy_fcnn_step(o, Xn, fc, X, Y)
+        before = {k: o.get(k).copy() for k in grads}
+        m_before = {k: o.get_state(k, 0).copy() for k in grads}
+        v_before = {k: o.get_state(k, 1).copy() for k in grads}
+        loss_o = o.train_step(None, X, None, Y)
+        assert abs(loss_o - loss_np) < 1e-5, (loss_o, loss_np)
+        assert np.allclose(o.tap(f"fc{len(fc) - 1}", 0).reshape(N, -1).T, P, rtol=1e-5, atol=1e-7)
+        for k, g in grads.items():
+            g = g.reshape(-1, order="F").astype(np.float64)
+            m = 0.9 * m_before[k] + (1 - np.float32(0.9)) * g
+            v = 0.999 * v_before[k] + (1 - np.float32(0.999)) * g * g
+            exp = before[k] - 0.005 * (m / (1 - np.float32(0.9))) / (np.sqrt(v / (1 - np.float32(0.999))) + 1e-8)
+            assert np.allclose(o.get(k), exp, rtol=2e-4, atol=2e-6), k
