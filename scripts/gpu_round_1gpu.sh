@@ -1,15 +1,10 @@
 #!/bin/bash
-# 1-GPU call for the round's record: parity tests, bench + reference arm, launch list and full captures
+# gpurun --timeout 1100 -- "bash scripts/gpu_round_1gpu.sh": the round record on one B200 — parity tests, bench + reference arm, launch list, full captures
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/gpu.txt 2>&1
 timeout 700 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; rc=$?; echo "pytest rc=$rc" >> gpurun_out/pytest_gpu.log
 tail -25 gpurun_out/pytest_gpu.log
-if false; then
-  PS_PDL_GEMM=0 timeout 700 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_nopdlgemm.log 2>&1; echo "pytest(PS_PDL_GEMM=0) rc=$?" >> gpurun_out/pytest_gpu_nopdlgemm.log
-  tail -8 gpurun_out/pytest_gpu_nopdlgemm.log
-fi
 timeout 400 python bench.py --steps 200 --warmup 20 > gpurun_out/bench_r01.log 2>&1; echo "bench rc=$?"
-true
 timeout 300 python bench.py --steps 200 --warmup 20 --cpu-budget 0.5 --large '' --force-sharded > gpurun_out/bench_p2p_1rank.log 2>&1; echo "bench(force-sharded) rc=$?"
 timeout 200 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref_r01.log 2>&1; echo "ref rc=$?"
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_r01.csv \

@@ -1,5 +1,5 @@
 #!/bin/bash
-# 2-GPU call: the sharded parity tests (NCCL, graphed NCCL, NVLink peer memory) and the 2-rank bench
+# gpurun --gpus 2 --timeout 900 -- "bash scripts/gpu_round_2gpu.sh": sharded parity tests (NCCL, graphed NCCL, NVLink peer memory) and the 2-rank bench
 mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/gpus2.txt
 timeout 420 python -m pytest tests/test_gpu_sharded.py -m gpu -x -q > gpurun_out/pytest_gpu2.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu2.log
