@@ -156,3 +156,23 @@ def test_bundled_sample_statistics(ps):
     assert int(Y.sum()) == 35641 and E.shape == (100000, 23)
     from ps_b200.synth import FIELD_UNIQUES
     assert [len(np.unique(E[:, j])) for j in range(23)] == FIELD_UNIQUES
+
+
+def test_reader_reset_midway_and_early_close(ps, sample):
+    """DataSet.reset (DataSet.java:61-67) may come at any time: the producer thread is stopped, the queue dropped, the source rewound."""
+    path, lines = sample
+    exp = [b for b in lo.dataset_batches(lines, 32) if b is not None]
+    r = ps.LibsvmReader(path, batch=32, threads=2)
+    for _ in range(3):
+        got = [r.next(), r.next()]
+        _eq(got[0], exp[0])
+        _eq(got[1], exp[1])
+        r.reset()
+    got = list(r)
+    assert len(got) == len(exp)
+    for a, b in zip(got, exp):
+        _eq(a, b)
+    r.close()
+    r2 = ps.LibsvmReader(path, batch=7)                       # closing with parsed batches still queued must not hang or leak the thread
+    r2.next()
+    r2.close()

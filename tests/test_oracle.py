@@ -264,3 +264,48 @@ def test_oracle_fcnn_step_against_independent_numpy():
             v = 0.999 * v_before[k] + (1 - np.float32(0.999)) * g * g
             exp = before[k] - 0.005 * (m / (1 - np.float32(0.9))) / (np.sqrt(v / (1 - np.float32(0.999))) + 1e-8)
             assert np.allclose(o.get(k), exp, rtol=2e-4, atol=2e-6), k
+
+
+def test_early_exit_freezes_the_store():
+    """DNN.java:58-63: when loss <= CrossEntropy.slim (0.01) train() returns before backward — nothing reaches KVStore.sum, so
+    Trainer's update() changes nothing.  All-positive labels drive the clipped sigmoid to 0.999 (loss -> 0.001)."""
+    F, D, Xn, fc, N = 1, 2, 1, [4, 1], 8
+    o = ol.OracleModel(ol.KIND_DNN, F, D, Xn, fc, 5)
+    E = np.arange(N, dtype=np.int64).reshape(N, 1) % 3
+    X = np.full((N, Xn), 0.5, np.float32)
+    Y = np.ones(N, np.float32)
+    hit = None
+    for step in range(4000):
+        loss = o.train_step(E, X, E % 100000, Y)
+        if o.skipped_backward():
+            hit = step
+            break
+    assert hit is not None and loss <= 0.01
+    snap = {k: o.get(k).copy() for k in ("fc0.weights", "fc0.bias", "fc1.weights", "fc1.bias", ol.key_string(0, 0, 1))}
+    loss2 = o.train_step(E, X, E % 100000, Y)
+    assert o.skipped_backward() and loss2 == loss
+    for k, v in snap.items():
+        assert np.array_equal(o.get(k), v), k
+
+
+def test_wide_gradient_reaches_every_key_ever_seen():
+    """SURVEY quirk 7 (LRLayer.java:79,110-117): LRLayer.weights is never cleared, and backward pushes the SAME batch-mean delta
+    to every key in it — a wide key absent from the current batch still moves."""
+    F, D, Xn, fc, N = 2, 2, 1, [3, 1], 6
+    o = ol.OracleModel(ol.KIND_WIDEDEEP, F, D, Xn, fc, 8)
+    rng = np.random.default_rng(2)
+    X = rng.random((N, Xn)).astype(np.float32)
+    Y = (rng.random(N) < 0.5).astype(np.float32)
+    E1 = np.array([[1, 2]] * N, np.int64)
+    E2 = np.array([[3, 4]] * N, np.int64)
+    o.train_step(E1, X, E1, Y)                                  # creates wide.weights.1.0 and .2.0
+    k_old, k_new = ol.key_string(1, 0, 1), ol.key_string(1, 0, 3)
+    assert o.get(k_new) is None
+    before = o.get(k_old).copy()
+    z_before = o.get_state(k_old, 0)
+    o.train_step(E2, X, E2, Y)                                  # batch 2 does not contain id 1
+    assert o.get(k_new) is not None
+    z_after = o.get_state(k_old, 0)
+    moved = (not np.array_equal(o.get(k_old), before)) or (z_before is None) != (z_after is None) or (z_before is not None and not np.array_equal(z_before, z_after))
+    assert moved, "a key seen only in batch 1 must still receive batch 2's gradient (Ftrl state Z accumulates it)"
+    assert o.num_keys() == 2 * len(fc) + 1 + 4 + 4             # dense keys + wide.bias + 4 wide keys + 4 embedding rows
