@@ -112,7 +112,8 @@ int ps_emb_forward_f32ids(ps_emb* emb, const float* E, int N, float* out);   /* 
 /* EmbeddingLayer.backward() called `calls` times (the reference makes 2 per step:
  * ConcatLayer.java:44 and DNN.java:66-68) on delta (ld x N, rows >= F*D ignored), then
  * KVStore.update(updaters) + KVStore.clear() (Trainer.java:93,95) for the touched rows:
- * scatter-add, occurrence normalisation and the Adam/Ftrl step run in ONE kernel.        */
+ * a pre-summed scatter-add kernel, then (as its programmatic dependent) one kernel for the
+ * occurrence normalisation, the Adam/Ftrl step and the per-batch reset.                   */
 int ps_emb_backward_update(ps_emb* emb, const float* delta, int ld, int N, int calls);
 /* KVStore.get(String) / PSClient.getList (KVStore.java:129-134, PSClient.java:72-97):
  * host snapshot of rows (and optimiser state when s1/s2 non-null); found[i] = 0 if absent. */

@@ -4,16 +4,17 @@
  * EmbTable: one open-addressing hash table for all F embedding fields of a layer
  * (keys "emF<j>.<id>" of layer/EmbeddingField.java:70, packed by ps_pack_key).  HBM layout:
  *
- *   slots[C]   16 B records {key u64, cnt u32, uidx u32}: two per 32 B sector, so the probe
- *              that finds the key also brings the per-batch occurrence count and the
- *              per-batch unique index into L2 at no extra DRAM cost
+ *   slots[C]   16 B records {key u64, cnt u32, first u32}: two per 32 B sector, so the probe
+ *              that finds the key also brings the per-batch occurrence count and the index of the
+ *              key's first lookup of the batch into L2 at no extra DRAM cost
  *   w[C][Dp], s1[C][Dp], s2[C][Dp]   row = slot index; SoA across {weight, Adam M | Ftrl Z,
  *              Adam V | Ftrl N} so the forward gather touches only w.  Dp = D rounded to 4
  *              floats: every row is 16 B aligned for 128-bit loads
- *   per-batch workspace (L = N*F lookups): lk_slot[L]; acc[L][Dp] gradient accumulators — a
- *              key uses the row of its FIRST lookup in the batch (emb_probe leaves that index in
- *              the slot record), the consumer zeroes it again: nothing to number or reset, and
- *              the few MB a batch touches stay L2-resident, so the scatter-add never round-trips HBM
+ *   per-batch workspace (L = N*F lookups): lk_slot[F][N] (field-major: warps of the probe store, and warps
+ *              of the backward kernels load, 128 contiguous bytes); acc[L][Dp] gradient accumulators — a
+ *              key uses the row of its FIRST lookup in the batch (emb_probe leaves ~t of that lookup in the
+ *              slot record by a fire-and-forget red.max), the update zeroes it again: nothing to number or
+ *              reset, and the few MB a batch touches stay L2-resident, so the scatter-add never round-trips HBM
  *
  * WideTable: layer/LRLayer.java's 1x1 weights "wide.weights.<id>": 32 B records
  * {key, w, s1, s2} — one sector holds everything a probe, the forward sum and the update need.
@@ -60,7 +61,7 @@ struct EmbTable {
   void create(Ctx* c, int F_, int D_, int64_t capacity, const ps_updater_spec& u, int64_t max_lookups);
   void destroy();
   void reserve(int64_t L);
-  /* find-or-insert every (field, id) of the batch, count occurrences, number the unique keys.
+  /* find-or-insert every (field, id) of the batch, count occurrences, mark each key's first lookup.
    * ids: device pointer, [N][F]; exactly one of ids_i64 / ids_f32 non-null.                  */
   void probe(const int64_t* ids_i64, const float* ids_f32, int N);
   /* out[n*ldo + j*D + d] = relu(w[slot(n,j)][d])   (EmbeddingField.java:73-76)               */
@@ -68,7 +69,7 @@ struct EmbTable {
   void probe_packed(const uint64_t* keys, int n, const P2PState* p2p = nullptr);   /* p2p: keys come from this step's mailbox */
   /* X != null: also copies the numeric features X[N][Xn] to columns [xoff, xoff+Xn) (ConcatLayer) */
   void gather(float* out, int ldo, int N, int F_eff = 0, const float* X = nullptr, int Xn = 0, int xoff = 0);
-  /* fused scatter-add + occurrence normalisation + updater step (see table.cu)               */
+  /* pre-summed scatter-add, then occurrence normalisation + updater step + per-batch reset (two launches, see table.cu) */
   void scatter_update(const float* delta, int ldd, const float* act /* null: mask already applied */, int lda, int N, int calls,
                       const int* skip_flag, int F_eff = 0, const P2PState* p2p = nullptr /* delta = this step's grads_in mailbox */);
   /* forget the batch without updating (predict path / early exit): cnt = 0 for touched slots */
