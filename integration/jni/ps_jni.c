@@ -1,7 +1,8 @@
 /*
  * ps_jni.c — the JNI shim between integration/java/nativeps/PsNative.java and the C ABI of
  * include/ps_b200.h.  Deliberately thin: pin the Java arrays, widen float ids to int64, call.
- * NOT compiled in this repository's image (no jni.h here); build on a host with a JDK:
+ * NOT built in this repository's image (no JDK here; tests/test_capi.py type-checks it against include/ps_b200.h with the stub
+ * header integration/jni/stub/jni.h); build on a host with a JDK:
  *   gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -I../../include \
  *       ps_jni.c -L../../ps_b200/lib -lps_b200 -o libps_b200_jni.so
  */
@@ -114,7 +115,34 @@ JNIEXPORT jboolean JNICALL Java_nativeps_PsNative_modelSkippedBackward(JNIEnv* e
   ps_model_skipped_backward((ps_model*)(intptr_t)m, &v);
   return v ? JNI_TRUE : JNI_FALSE;
 }
-/* updaterParse / modelPredict follow the same pattern (ps_updater_parse, ps_model_predict). */
+JNIEXPORT jfloatArray JNICALL Java_nativeps_PsNative_updaterParse(JNIEnv* env, jclass c, jstring name) {
+  const char* k = (*env)->GetStringUTFChars(env, name, NULL);
+  ps_updater_spec spec;
+  int rc = ps_updater_parse(k, &spec);                                          /* "adam@alfa:..@beta1:..@" (T/TestPs.java:26-27) */
+  (*env)->ReleaseStringUTFChars(env, name, k);
+  if (rc != PS_OK) { throw_ps(env, rc); return NULL; }
+  jfloatArray out = (*env)->NewFloatArray(env, 5);
+  jfloat* p = (*env)->GetFloatArrayElements(env, out, NULL);
+  p[0] = (jfloat)spec.kind;
+  for (int i = 0; i < 4; ++i) p[1 + i] = spec.p[i];
+  (*env)->ReleaseFloatArrayElements(env, out, p, 0);
+  return out;
+}
+JNIEXPORT jfloatArray JNICALL Java_nativeps_PsNative_modelPredict(JNIEnv* env, jclass c, jlong m, jfloatArray E, jfloatArray X, jfloatArray W,
+                                                                  jint N, jint outRows) {
+  jsize ne, nw;
+  int64_t* e = widen_ids(env, E, &ne);
+  int64_t* w = widen_ids(env, W, &nw);
+  jfloat* x = (*env)->GetFloatArrayElements(env, X, NULL);
+  jfloatArray out = (*env)->NewFloatArray(env, N * outRows);
+  jfloat* p = (*env)->GetFloatArrayElements(env, out, NULL);
+  int rc = ps_model_predict((ps_model*)(intptr_t)m, e, x, w, N, p);             /* PredictThread.call + Trainer.predict (Trainer.java:44-68) */
+  (*env)->ReleaseFloatArrayElements(env, out, p, 0);
+  (*env)->ReleaseFloatArrayElements(env, X, x, JNI_ABORT);
+  free(e); free(w);
+  throw_ps(env, rc);
+  return out;
+}
 
 /* ---- layer.FcLayer standalone (ps_fc_*): jblas column-major float[] is exactly the C ABI's layout, no conversion ---- */
 JNIEXPORT void JNICALL Java_nativeps_PsNative_fcForward(JNIEnv* env, jclass c, jlong fc, jfloatArray aPrev, jint N, jfloatArray aOut) {
@@ -134,7 +162,41 @@ JNIEXPORT void JNICALL Java_nativeps_PsNative_fcBackward(JNIEnv* env, jclass c, 
   throw_ps(env, rc);
 }
 JNIEXPORT void JNICALL Java_nativeps_PsNative_fcUpdate(JNIEnv* env, jclass c, jlong fc) { throw_ps(env, ps_fc_update((ps_fc*)(intptr_t)fc)); }
-/* fcCreate / fcDestroy / fcGet / fcPut: ps_fc_create / ps_fc_destroy / ps_fc_get / ps_fc_put, same pattern as modelGet / modelPut. */
+JNIEXPORT jlong JNICALL Java_nativeps_PsNative_fcCreate(JNIEnv* env, jclass c, jlong ctx, jstring name, jint in, jint out, jint act, jfloatArray upd,
+                                                        jint maxBatch) {
+  const char* k = (*env)->GetStringUTFChars(env, name, NULL);
+  ps_updater_spec spec, *sp = NULL;
+  if (upd) {
+    jfloat* u = (*env)->GetFloatArrayElements(env, upd, NULL);
+    spec.kind = (int32_t)u[0]; for (int i = 0; i < 4; ++i) spec.p[i] = u[1 + i];
+    (*env)->ReleaseFloatArrayElements(env, upd, u, JNI_ABORT);
+    sp = &spec;
+  }
+  ps_fc* fc = NULL;
+  int rc = ps_fc_create((ps_ctx*)(intptr_t)ctx, k, in, out, act, sp, maxBatch, &fc);   /* FcLayer ctor + pullWeights (FcLayer.java:34-51,112-115) */
+  (*env)->ReleaseStringUTFChars(env, name, k);
+  throw_ps(env, rc);
+  return (jlong)(intptr_t)fc;
+}
+JNIEXPORT void JNICALL Java_nativeps_PsNative_fcDestroy(JNIEnv* env, jclass c, jlong fc) { ps_fc_destroy((ps_fc*)(intptr_t)fc); }
+JNIEXPORT jfloatArray JNICALL Java_nativeps_PsNative_fcGet(JNIEnv* env, jclass c, jlong fc, jint which) {
+  int n = 0;
+  int rc = ps_fc_get((ps_fc*)(intptr_t)fc, which, NULL, 0, &n);
+  if (rc != PS_OK) { throw_ps(env, rc); return NULL; }
+  jfloatArray out = (*env)->NewFloatArray(env, n);
+  jfloat* p = (*env)->GetFloatArrayElements(env, out, NULL);
+  rc = ps_fc_get((ps_fc*)(intptr_t)fc, which, p, n, &n);                        /* KVStore.get("<name>.weights" | ".bias") */
+  (*env)->ReleaseFloatArrayElements(env, out, p, 0);
+  throw_ps(env, rc);
+  return out;
+}
+JNIEXPORT void JNICALL Java_nativeps_PsNative_fcPut(JNIEnv* env, jclass c, jlong fc, jint which, jfloatArray v) {
+  jsize n = (*env)->GetArrayLength(env, v);
+  jfloat* p = (*env)->GetFloatArrayElements(env, v, NULL);
+  int rc = ps_fc_put((ps_fc*)(intptr_t)fc, which, p, n);
+  (*env)->ReleaseFloatArrayElements(env, v, p, JNI_ABORT);
+  throw_ps(env, rc);
+}
 
 /* ---- data.DataSet (ps_reader_*): ids are widened back to floats because CTR.parseFeature's "E"/"W" are FloatMatrix ---- */
 JNIEXPORT jint JNICALL Java_nativeps_PsNative_readerNext(JNIEnv* env, jclass c, jlong r, jfloatArray E, jfloatArray X, jfloatArray W, jfloatArray Y) {
@@ -158,4 +220,14 @@ JNIEXPORT jint JNICALL Java_nativeps_PsNative_readerNext(JNIEnv* env, jclass c, 
   throw_ps(env, rc);
   return rows;
 }
-/* readerOpen / readerReset / readerClose: ps_reader_open / ps_reader_reset / ps_reader_close. */
+JNIEXPORT jlong JNICALL Java_nativeps_PsNative_readerOpen(JNIEnv* env, jclass c, jstring path, jint F, jint Xn, jlong wideSize, jint batch, jint offset,
+                                                          jint step, jint threads) {
+  const char* k = (*env)->GetStringUTFChars(env, path, NULL);
+  ps_reader* r = NULL;
+  int rc = ps_reader_open(k, F, Xn, wideSize, batch, offset, step, threads, &r);   /* new CTR(new LibsvmParser(), new FileSource(file), batch, thread) */
+  (*env)->ReleaseStringUTFChars(env, path, k);
+  throw_ps(env, rc);
+  return (jlong)(intptr_t)r;
+}
+JNIEXPORT void JNICALL Java_nativeps_PsNative_readerReset(JNIEnv* env, jclass c, jlong r) { throw_ps(env, ps_reader_reset((ps_reader*)(intptr_t)r)); }
+JNIEXPORT void JNICALL Java_nativeps_PsNative_readerClose(JNIEnv* env, jclass c, jlong r) { ps_reader_close((ps_reader*)(intptr_t)r); }

@@ -58,3 +58,19 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
                 text = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle_lib" not in text and "ps_oracle" not in text and "libps_oracle" not in text, f
+
+
+def test_jni_shim_typechecks_and_covers_every_native_method():
+    """No JDK in this image: the shim is type-checked against include/ps_b200.h with a stub jni.h that carries the JNI
+    specification's signatures for the functions it uses, and every `native` method of PsNative.java must have its
+    Java_nativeps_PsNative_<name> definition."""
+    import re
+    import subprocess
+    shim = os.path.join(ROOT, "integration", "jni", "ps_jni.c")
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-Wno-unused-parameter", "-I" + os.path.join(ROOT, "integration", "jni", "stub"),
+                        "-I" + os.path.join(ROOT, "include"), shim], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    java = open(os.path.join(ROOT, "integration", "java", "nativeps", "PsNative.java")).read()
+    natives = set(re.findall(r"public static native [\w\[\]]+ (\w+)\(", java))
+    impl = set(re.findall(r"Java_nativeps_PsNative_(\w+)\(", open(shim).read()))
+    assert natives and natives == impl, (sorted(natives - impl), sorted(impl - natives))
