@@ -55,6 +55,36 @@ def test_oracle_reaches_readme_auc(ps):
         ol.lib().pso_set_gemm(0, None)
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(RES, "train.txt")), reason="the reference's bundled sample is only present in the build container")
+def test_oracle_widedeep_on_bundled_sample(ps):
+    """BASELINE.json's configs[0] names WideDeepNN; CTR.java's main builds the DNN (CTR.java:91), so the README number above is the DNN's.
+    The same data through WideDeepNN.buildModel(23, 10, 45, {150, 10, 1}) — W = E % 100000 from the ingest, the LR branch with Ftrl, every
+    wide key ever seen swept per step — must learn as well: one epoch with the seed that trains the DNN reaches AUC 0.636."""
+    if ol.openblas_path():
+        ol.lib().pso_set_gemm(2, ol.openblas_path().encode())
+    try:
+        m = ol.OracleModel(ol.KIND_WIDEDEEP, F, D, XN, FC, 1)
+        train = ps.LibsvmReader(os.path.join(RES, "train.txt"), batch=1000, threads=4)
+        test = ps.LibsvmReader(os.path.join(RES, "test.txt"), batch=100, threads=2)
+        first = last = None
+        for i, b in enumerate(train):
+            assert np.array_equal(b["W"], b["E"] % 100000)
+            loss = m.train_step(b["E"], b["X"], b["W"], b["Y"])
+            first = loss if first is None else first
+            last = loss
+        P, Y = [], []
+        for b in test:
+            P.append(m.predict(b["E"], b["X"], b["W"], len(b["Y"])))
+            Y.append(b["Y"].copy())
+        P, Y = np.concatenate(P), np.concatenate(Y)
+        auc = ol.lib().pso_auc(P, Y, len(Y))
+        assert 0.60 <= auc <= 0.70 and last < first, (auc, first, last)
+        train.close()
+        test.close()
+    finally:
+        ol.lib().pso_set_gemm(0, None)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["fp32", "tf32x3"])
 def test_ctr_fixture_steps_match_oracle(ps, ctx, tmp_path, mode):
