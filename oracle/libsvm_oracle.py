@@ -59,11 +59,14 @@ def nearest_float32(dec):
     with rationals so that no intermediate double rounding can leak in."""
     from fractions import Fraction
     exact = Fraction(dec)
-    f = np.float32(float(dec))
+    with np.errstate(over="ignore"):
+        f = np.float32(float(dec))
     if not np.isfinite(f) or exact == 0:
         return f
     best = None
-    for cand in (np.nextafter(f, np.float32(-np.inf)), f, np.nextafter(f, np.float32(np.inf))):
+    with np.errstate(over="ignore"):
+        cands = (np.nextafter(f, np.float32(-np.inf)), f, np.nextafter(f, np.float32(np.inf)))
+    for cand in cands:
         if not np.isfinite(cand):
             continue
         err = abs(Fraction(float(cand)) - exact)
@@ -111,7 +114,8 @@ def parse_feature(data_list, F=23, Xn=45, wide_size=100000):
         for j in range(1 + F, 1 + F + Xn):
             X[i, j - 1 - F] = cols[j][1]
     W = np.fmod(E, np.float32(wide_size))                     # Java float % == C fmodf
-    return dict(E=E.astype(np.int64), X=X, W=W.astype(np.int64), Y=Y)
+    with np.errstate(invalid="ignore"):                       # ids beyond the long range: Java's (long) cast saturates; out of the tested domain
+        return dict(E=E.astype(np.int64), X=X, W=W.astype(np.int64), Y=Y)
 
 
 class DataSource:

@@ -176,3 +176,51 @@ def test_reader_reset_midway_and_early_close(ps, sample):
     r2 = ps.LibsvmReader(path, batch=7)                       # closing with parsed batches still queued must not hang or leak the thread
     r2.next()
     r2.close()
+
+
+# --------------------------------------------------------------------------- property test: native parser == Java semantics
+def _expected(line, F, Xn):
+    try:
+        o = lo.parse_feature([lo.parse_line(line)], F=F, Xn=Xn)
+        return 0, o
+    except lo.JavaException as e:
+        msg = str(e)
+        return (1 if msg.startswith("IndexOutOfBounds") else 2), None
+
+
+def test_random_lines_agree_with_the_java_semantics(ps):
+    """Lines assembled from valid and invalid spellings of every token kind; status and (for status 0) every output bit must agree
+    with the Python restatement of LibsvmParser.parse + CTR.parseFeature."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+    f_ok = ["0", "1", "-1", "0.5", ".5", "5.", "-0", "00012.3400", "1e3", "1E-2", "1.5f", "2D", "NaN", "-Infinity", "0x1p3", "0x.8p1", "+7", "1234567", "12345678",
+            "0.000000001", "0.00000000001", "3.4028235e38", "1e39", "1 ", "\t3", "4\t", "99999999999999999999", "0.48", "16777217", "0.1", "7.0064923216240854e-46"]
+    f_bad = ["", ".", "-", "e5", "1e", "1..2", "nan", "inf", "0x1", "--1", "1f2"]
+    i_ok = ["0", "7", "33895", "16777217", "123456789012345678", "9223372036854775807", "-3", "+4", "007", "99999"]
+    i_bad = ["9223372036854775808", "", "x", "1.0", " 5"]
+    floats = st.sampled_from(f_ok * 12 + f_bad)                      # mostly valid spellings, so that whole lines parse
+    idxs = st.sampled_from(i_ok * 12 + i_bad)
+    pair = st.tuples(idxs, floats, st.sampled_from([""] * 20 + [":", ":9", "::"])).map(lambda t: f"{t[0]}:{t[1]}{t[2]}") | st.sampled_from(["5", ":", "", "a:b"])
+    good_pair = st.tuples(st.sampled_from(i_ok), st.sampled_from(f_ok)).map(lambda t: f"{t[0]}:{t[1]}")
+    sep = st.sampled_from([" "] * 30 + ["  "])
+    tok = st.one_of(*([good_pair] * 15 + [pair]))
+    tokens = st.lists(tok, min_size=4, max_size=7) | st.lists(tok, min_size=0, max_size=7)     # F + Xn = 4 columns make a full line
+    line = st.tuples(floats, tokens, st.lists(sep, min_size=7, max_size=7), st.sampled_from(["", "", " ", "   "])).map(
+        lambda t: t[0] + "".join(t[2][i] + p for i, p in enumerate(t[1])) + t[3])
+    seen = {0: 0, 1: 0, 2: 0}
+
+    @hyp.settings(max_examples=3000, deadline=None, derandomize=True)
+    @hyp.given(line)
+    def check(ln):
+        if "\n" in ln or "\r" in ln:
+            return
+        got = ps.parse_libsvm_line(ln, F=2, Xn=2)
+        exp_status, o = _expected(ln, 2, 2)
+        seen[exp_status] += 1
+        assert got[0] == exp_status, (ln, got[0], exp_status)
+        if exp_status == 0:
+            assert np.array_equal(got[1], o["E"][0]) and np.array_equal(got[3], o["W"][0]), ln
+            assert np.array_equal(got[2].view(np.uint32), o["X"][0].view(np.uint32)) or (np.isnan(got[2]) == np.isnan(o["X"][0])).all(), ln
+            assert np.float32(got[4]).view(np.uint32) == o["Y"][0].view(np.uint32) or (np.isnan(got[4]) and np.isnan(o["Y"][0])), ln
+    check()
+    assert min(seen.values()) >= 100, seen                            # all three outcomes are well represented
