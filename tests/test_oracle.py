@@ -309,3 +309,21 @@ def test_wide_gradient_reaches_every_key_ever_seen():
     moved = (not np.array_equal(o.get(k_old), before)) or (z_before is None) != (z_after is None) or (z_before is not None and not np.array_equal(z_before, z_after))
     assert moved, "a key seen only in batch 1 must still receive batch 2's gradient (Ftrl state Z accumulates it)"
     assert o.num_keys() == 2 * len(fc) + 1 + 4 + 4             # dense keys + wide.bias + 4 wide keys + 4 embedding rows
+
+
+@pytest.mark.parametrize("R", [2, 4, 8])
+def test_router_balance_keeps_buckets_within_capacity(R):
+    """The sharded exchange sizes every per-owner bucket as slack x L / R with slack = 2 (ps_b200/sharded.py): the production router
+    (ps_owner_of: splitmix64 of the packed key, Lemire reduction) must spread the UNIQUE keys of a bench batch evenly enough —
+    senders de-duplicate, so unique keys are what travels."""
+    from ps_b200.synth import CONFIGS
+    c = CONFIGS["cfg2"]
+    syn = Synth(F=c["F"], Xn=c["Xn"], V=c["V"], dist="zipf", seed=20261017 + 2)
+    L = ol.lib()
+    for _ in range(3):
+        E = syn.batch(c["B"])["E"]
+        keys = {int(L.pso_pack_key(j, int(v))) for j in range(c["F"]) for v in np.unique(E[:, j])}
+        owners = np.array([L.pso_owner_of(k, R) for k in keys])
+        counts = np.bincount(owners, minlength=R)
+        assert counts.min() > 0 and counts.max() <= 1.15 * len(keys) / R, counts
+        assert counts.max() <= 2 * c["B"] * c["F"] / R                  # the bucket capacity at slack 2
