@@ -163,6 +163,27 @@ int ps_model_train_step(ps_model* m, const int64_t* E, const float* X, const int
  * At most 2 steps may be in flight; host buffers must stay valid until the matching collect. */
 int ps_model_submit(ps_model* m, const int64_t* E, const float* X, const int64_t* W, const float* Y, int N);
 int ps_model_collect(ps_model* m, float* loss);
+/* Model.train CALL BY CALL, for an unchanged model.DNN / model.WideDeepNN whose loss stays in Java:
+ *   ps_model_forward          the forward loop `for (Layer layer : layers) layer.forward()` (DNN.java:44-46, WideDeepNN.java:52-58):
+ *                             P_out[N] = layers.get(last).getA(); the batch stays pending on the device (occurrence counts, ReLU
+ *                             masks, activations).  No label is passed: loss.forward / loss.backward run in the caller (DNN.java:47-49).
+ *   ps_model_backward_update  delta_top[N] = loss.backward(P, Y) exactly as setDelta() receives it (DNN.java:64: dLoss/dP, BEFORE the
+ *                             output Sigmoid's derivative); runs the reverse loop (DNN.java:65-68: FcLayer.backward incl. its
+ *                             activation.backward, LRLayer.backward, EmbeddingLayer.backward x2) and then KVStore.update + clear
+ *                             (Trainer.java:93,95).  `loss` = the caller's loss.forward value, recorded as the step's loss; the early
+ *                             exit of DNN.java:58-63 is the caller's to take (it simply does not call this; the next forward forgets
+ *                             the pending batch).  DNN and WideDeepNN only.                                                    */
+int ps_model_forward(ps_model* m, const int64_t* E, const float* X, const int64_t* W, int N, float* P_out);
+int ps_model_backward_update(ps_model* m, const float* delta_top, int N, float loss);
+/* DataSet.next + Trainer.train in one submission (DataSet.java:77-100, CTR.parseFeature CTR.java:47-68, CTR.wideSize CTR.java:36):
+ * `len` bytes of libsvm text (host memory, ideally pinned) holding exactly N complete '\n'-terminated lines; the text is copied
+ * to the device as it is, parsed THERE into E / X / W / Y and trained on, all asynchronously; ps_model_collect returns the loss.
+ * A line the device parser cannot take (short, blank, missing, or a spelling outside its fast path — see ps_libsvm_parse_dev)
+ * drops the whole batch, as the reference's swallowed exception does (DataSet.java:96-98): nothing is applied, ps_model_step_info
+ * reports skipped = 1 and the number of offending lines.                                                                    */
+int ps_model_submit_text(ps_model* m, const char* text, size_t len, int N);
+/* status of the step last collected: skipped (early exit / dropped batch / full table), bad text lines, unique embedding keys */
+int ps_model_step_info(ps_model* m, int* skipped, uint32_t* bad_lines, uint32_t* n_unique);
 /* the step on inputs ALREADY resident in device memory (bench `value` leg); loss stays on the
  * device until ps_model_read_loss.                                                         */
 int ps_model_train_step_dev(ps_model* m, const int64_t* E_dev, const float* X_dev, const int64_t* W_dev, const float* Y_dev, int N);
@@ -243,7 +264,8 @@ int ps_model_shard_apply_dev(ps_model* m, const float* grads_recv_dev, int n);
 /* ---- the same sharded step over NVLink PEER MEMORY (no collective library on the data path) --------
  * Every rank maps every peer's mailbox slab (CUDA IPC); the kernel that produces a bucket (routed keys,
  * gathered rows, row gradients, dense gradient sums, wide ids) stores it straight into the consumer's HBM
- * through NVSwitch and publishes a flag; consumers run a one-warp wait kernel.  A whole step is ONE CUDA
+ * through NVSwitch and, when its last block ends, flags the consumers, whose kernels wait for the flags in their prologue — there
+ * are no flag kernels and no collective calls.  A whole step is ONE CUDA
  * graph per rank: ps_model_p2p_step_dev enqueues it (asynchronous), ps_model_read_loss reads the result.
  *   ps_model_p2p_init    → allocates the slab, returns its 64-byte cudaIpcMemHandle_t
  *   [host: all-gather the R handles, e.g. torch.distributed.all_gather]

@@ -58,7 +58,11 @@ static MP dup(const MP& a) { return std::make_shared<FM>(*a); }
  * NativeBlas.sgemm amounts to).  All compute C(m x n) = A(m x k) * B(k x n), column-major. */
 typedef void (*cblas_sgemm_t)(int, int, int, int64_t, int64_t, int64_t, float, const float*, int64_t,
                               const float*, int64_t, float, float*, int64_t);
+typedef void (*blas_set_threads_t)(int);
+typedef int (*blas_get_threads_t)(void);
 static cblas_sgemm_t g_cblas = nullptr;
+static blas_set_threads_t g_blas_set_threads = nullptr;
+static blas_get_threads_t g_blas_get_threads = nullptr;
 static int g_gemm_kind = 0;
 
 __attribute__((target_clones("avx512f", "avx2", "default")))
@@ -665,9 +669,19 @@ int pso_set_gemm(int kind, const char* openblas_path) {
       if (!h) return -1;
       g_cblas = (cblas_sgemm_t)dlsym(h, "scipy_cblas_sgemm64_");
       if (!g_cblas) return -2;
+      g_blas_set_threads = (blas_set_threads_t)dlsym(h, "scipy_openblas_set_num_threads64_");
+      g_blas_get_threads = (blas_get_threads_t)dlsym(h, "scipy_openblas_get_num_threads64_");
     }
   }
   g_gemm_kind = kind; return 0;
+}
+/* Threads the dlopen'ed OpenBLAS uses per sgemm call.  numpy initialises the same library with one thread per core long
+ * before bench.py can set OPENBLAS_NUM_THREADS, so the environment variable alone does NOT pin it: R replicas x C BLAS
+ * threads oversubscribed the host in round 1.  Returns the value in force afterwards (-1: no OpenBLAS loaded). */
+int pso_set_blas_threads(int n) {
+  if (!g_blas_set_threads) return -1;
+  g_blas_set_threads(n);
+  return g_blas_get_threads ? g_blas_get_threads() : n;
 }
 
 void* pso_model_create(int kind, int F, int D, int Xn, const int* fc, int n_fc, uint64_t seed, int emb_opt) {

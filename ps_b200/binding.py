@@ -76,6 +76,10 @@ SYMBOLS = {
     "ps_model_train_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i, C.POINTER(_f)]),
     "ps_model_submit": (_i, [_vp, _vp, _vp, _vp, _vp, _i]),
     "ps_model_collect": (_i, [_vp, C.POINTER(_f)]),
+    "ps_model_forward": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
+    "ps_model_backward_update": (_i, [_vp, _vp, _i, _f]),
+    "ps_model_submit_text": (_i, [_vp, _vp, C.c_size_t, _i]),
+    "ps_model_step_info": (_i, [_vp, C.POINTER(_i), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "ps_model_train_step_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _i]),
     "ps_model_read_loss": (_i, [_vp, C.POINTER(_f)]),
     "ps_model_loss_dev": (_i, [_vp, _pp]),
@@ -418,6 +422,27 @@ class Model:
         check(lib().ps_model_train_step(self.h, _p(E), _p(X), _p(W), _p(Y), Y.shape[0], C.byref(loss)))
         return loss.value
 
+    def forward(self, E, X, W):
+        """The forward loop of DNN.train / WideDeepNN.train: returns P (N,), keeps the batch pending for backward_update."""
+        E, W, X = _c(E, np.int64), _c(W, np.int64), _c(X, np.float32)
+        N = X.shape[0]
+        P = np.zeros(N, np.float32)
+        check(lib().ps_model_forward(self.h, _p(E), _p(X), _p(W), N, _p(P)))
+        return P
+
+    def backward_update(self, delta_top, loss=float("nan")):
+        """The reverse loop + KVStore.update given delta_top = loss.backward(P, Y) computed by the caller."""
+        d = _c(delta_top, np.float32)
+        check(lib().ps_model_backward_update(self.h, _p(d), d.shape[0], loss))
+
+    def submit_text(self, text_ptr, nbytes, N):
+        check(lib().ps_model_submit_text(self.h, text_ptr, nbytes, N))
+
+    def step_info(self):
+        sk, bad, nu = C.c_int(), C.c_uint32(), C.c_uint32()
+        check(lib().ps_model_step_info(self.h, C.byref(sk), C.byref(bad), C.byref(nu)))
+        return dict(skipped=bool(sk.value), bad_lines=bad.value, n_unique=nu.value)
+
     def submit_ptrs(self, E, X, W, Y, N):
         check(lib().ps_model_submit(self.h, E, X, W, Y, N))
 
@@ -489,11 +514,12 @@ class Model:
         return bool(v.value)
 
     def kernel_times(self, E_ptrs, N, reps=64):
-        """device us of {probe, gather, scatter_update, clear_batch}; E_ptrs: device addresses of [N][F] int64 id batches"""
+        """device us of {key resolution alone, the fused lookup kernel (resolve + gather), scatter + update, clear_batch};
+        E_ptrs: device addresses of [N][F] int64 id batches"""
         arr = (C.c_void_p * len(E_ptrs))(*E_ptrs)
         us = np.zeros(4, np.float32)
         check(lib().ps_model_kernel_times(self.h, arr, len(E_ptrs), N, reps, _p(us)))
-        return dict(zip(["emb_probe", "emb_gather", "emb_scatter_update", "emb_clear"], us.tolist()))
+        return dict(zip(["emb_resolve", "emb_lookup", "emb_scatter_update", "emb_clear"], us.tolist()))
 
     def gemm_times(self, N, reps=64):
         us = np.zeros(3 * len(self.fc), np.float32)

@@ -69,6 +69,8 @@ int ps_ctx_create(int device, uint64_t seed, ps_ctx** out) {
   c->c.pdl_gemm = (pg && pg[0] == '1') ? 1 : 0;
   const char* xe = std::getenv("PS_EXACT_UPDATERS");
   c->c.exact_updaters = (xe && xe[0] == '1') ? 1 : 0;
+  const char* ht = std::getenv("PS_HOT_TMA");
+  c->c.hot_tma = (ht && ht[0] == '0') ? 0 : 1;
   const char* hm = std::getenv("PS_HOT_MIN");
   if (hm && hm[0]) { const long v = std::atol(hm); c->c.hot_min = v <= 0 ? 0xFFFFFFFFu : (unsigned)v; }
   PS_CUDA(cudaStreamCreateWithPriority(&c->c.stream, cudaStreamNonBlocking, c->c.prio_main));
@@ -274,14 +276,13 @@ static void emb_reserve(ps_emb* e, int N) {
 static int emb_forward_impl(ps_emb* e, const int64_t* E, const float* Ef, int N, float* out) {
   PS_TRY
   PS_REQUIRE(e && (E || Ef) && out && N > 0, PS_ERR_ARG, "null argument");
+  if (e->lastN) { e->t.clear_batch(); e->lastN = 0; }   /* a forward that was never followed by backward: drop its counts BEFORE the workspace may be reallocated */
   emb_reserve(e, N);
   cudaStream_t st = e->ctx->stream;
   const size_t L = (size_t)N * e->t.F;
   if (E) PS_CUDA(cudaMemcpyAsync(e->dE, E, sizeof(int64_t) * L, cudaMemcpyHostToDevice, st));
   else PS_CUDA(cudaMemcpyAsync(e->dEf, Ef, sizeof(float) * L, cudaMemcpyHostToDevice, st));
-  if (e->lastN) e->t.clear_batch();            /* a forward that was never followed by backward: drop its counts */
-  e->t.probe(E ? e->dE : nullptr, E ? nullptr : e->dEf, N);
-  e->t.gather(e->dOut, e->t.F * e->t.D, N);
+  e->t.lookup(E ? e->dE : nullptr, E ? nullptr : e->dEf, N, e->dOut, e->t.F * e->t.D);
   PS_CUDA(cudaMemcpyAsync(out, e->dOut, sizeof(float) * L * e->t.D, cudaMemcpyDeviceToHost, st));
   e->lastN = N;
   e->t.check_errors();
@@ -299,7 +300,7 @@ int ps_emb_backward_update(ps_emb* e, const float* delta, int ld, int N, int cal
   const size_t need = (size_t)N * ld;
   if (need > e->delta_cap) { PS_CUDA(cudaStreamSynchronize(st)); dfree(e->dDelta); e->dDelta = dmalloc<float>(need); e->delta_cap = need; }
   PS_CUDA(cudaMemcpyAsync(e->dDelta, delta, sizeof(float) * need, cudaMemcpyHostToDevice, st));
-  e->t.scatter_update(e->dDelta, ld, e->dOut, e->t.F * e->t.D, N, calls, nullptr);
+  e->t.scatter_update(e->dDelta, ld, nullptr, 0, N, calls, nullptr, 0, nullptr, true);   /* ReLU mask: the bits the forward recorded */
   e->lastN = 0;
   PS_CUDA(cudaStreamSynchronize(st));
   PS_CATCH
@@ -358,6 +359,34 @@ int ps_model_train_step(ps_model* m, const int64_t* E, const float* X, const int
   HostBatch b; b.E = E; b.X = X; b.W = W; b.Y = Y; b.N = N;
   m->m.submit(b);
   *loss = m->m.collect();
+  PS_CATCH
+}
+/* ---- DNN.train / WideDeepNN.train call by call (the loss stays in the caller) ---- */
+int ps_model_forward(ps_model* m, const int64_t* E, const float* X, const int64_t* W, int N, float* P_out) {
+  PS_TRY
+  PS_REQUIRE(m && X && P_out, PS_ERR_ARG, "null argument");
+  HostBatch b; b.E = E; b.X = X; b.W = W; b.Y = nullptr; b.N = N;
+  m->m.forward_host(b, P_out);
+  PS_CATCH
+}
+int ps_model_backward_update(ps_model* m, const float* delta_top, int N, float loss) {
+  PS_TRY
+  PS_REQUIRE(m && delta_top, PS_ERR_ARG, "null argument");
+  m->m.backward_update_host(delta_top, N, loss);
+  PS_CATCH
+}
+int ps_model_submit_text(ps_model* m, const char* text, size_t len, int N) {
+  PS_TRY
+  PS_REQUIRE(m && text, PS_ERR_ARG, "null argument");
+  m->m.submit_text(text, len, N);
+  PS_CATCH
+}
+int ps_model_step_info(ps_model* m, int* skipped, uint32_t* bad_lines, uint32_t* n_unique) {
+  PS_TRY
+  PS_REQUIRE(m != nullptr, PS_ERR_ARG, "null model");
+  if (skipped) *skipped = m->m.last_status.skip;
+  if (bad_lines) *bad_lines = m->m.last_status.pad;
+  if (n_unique) *n_unique = m->m.last_status.n_unique;
   PS_CATCH
 }
 int ps_model_train_step_dev(ps_model* m, const int64_t* E_dev, const float* X_dev, const int64_t* W_dev, const float* Y_dev, int N) {
@@ -519,7 +548,7 @@ int ps_model_shard_grad_buffer(ps_model* m, float** buf_dev, int64_t* count) {
   PS_REQUIRE(m && buf_dev && count, PS_ERR_ARG, "bad argument");
   if (!m->m.gsum) {
     const DenseUpdateArgs u = m->m.dense_args(1);
-    m->m.gsum_len = u.total + 2;
+    m->m.gsum_len = u.total + 3;
     m->m.gsum = dmalloc_zero<float>((size_t)m->m.gsum_len, m->m.ctx->stream);
     PS_CUDA(cudaStreamSynchronize(m->m.ctx->stream));
   }

@@ -23,6 +23,8 @@ constexpr uint64_t kMagic = 0x3130303242535000ull;   /* "\0PSB2001" */
 
 struct FileCloser { void operator()(FILE* f) const { if (f) std::fclose(f); } };
 using File = std::unique_ptr<FILE, FileCloser>;
+struct DevFree { void operator()(void* p) const { dfree(p); } };   /* device staging buffers are released on every exit path */
+template <class T> using DevBuf = std::unique_ptr<T, DevFree>;
 
 void wr(FILE* f, const void* p, size_t n) { PS_REQUIRE(std::fwrite(p, 1, n, f) == n, PS_ERR_ARG, "checkpoint: short write"); }
 void rd(FILE* f, void* p, size_t n) { PS_REQUIRE(std::fread(p, 1, n, f) == n, PS_ERR_ARG, "checkpoint: short read (truncated or foreign file)"); }
@@ -66,7 +68,8 @@ __global__ void __launch_bounds__(256) emb_import_kernel(EmbSlot* __restrict__ s
   const unsigned long long key = keys[i];
   uint32_t slot = ps_bucket_of(key, C);
   int found = -1;
-  for (uint32_t p = 0; p < C; ++p) {
+  const uint32_t limit = C < (uint32_t)kProbeLimit ? C : (uint32_t)kProbeLimit;   /* the bound the runtime lookups stop at: a key placed beyond it would never be found again */
+  for (uint32_t p = 0; p < limit; ++p) {
     const unsigned long long k = *reinterpret_cast<const volatile unsigned long long*>(&slots[slot].key);
     if (k == key) { found = (int)slot; break; }
     if (k == PS_KEY_EMPTY) {
@@ -82,6 +85,8 @@ __global__ void __launch_bounds__(256) emb_import_kernel(EmbSlot* __restrict__ s
     a[(size_t)found * Dp + d] = rows[((size_t)1 * cap + i) * D + d];
     b[(size_t)found * Dp + d] = rows[((size_t)2 * cap + i) * D + d];
   }
+  __threadfence();
+  atomicOr(&slots[found].uidx, kRowReady);
 }
 
 struct Header {
@@ -96,8 +101,10 @@ struct Header {
 void Model::save(const std::string& path) {
   PS_REQUIRE(in_flight == 0, PS_ERR_STATE, "save: steps in flight");
   PS_CUDA(cudaStreamSynchronize(ctx->stream));
-  File f(std::fopen(path.c_str(), "wb"));
-  PS_REQUIRE(f != nullptr, PS_ERR_ARG, ("save: cannot open " + path).c_str());
+  /* written beside the target and renamed into place once every byte is on disk: a failed dump never leaves a truncated checkpoint */
+  const std::string tmp_path = path + ".tmp";
+  File f(std::fopen(tmp_path.c_str(), "wb"));
+  PS_REQUIRE(f != nullptr, PS_ERR_ARG, ("save: cannot open " + tmp_path).c_str());
   Header h{};
   h.magic = kMagic; h.kind = kind; h.F = F; h.D = D; h.Xn = Xn; h.L = L; h.has_wide = has_wide ? 1 : 0;
   for (int l = 0; l <= L; ++l) h.dims[l] = width[l];
@@ -118,16 +125,17 @@ void Model::save(const std::string& path) {
   }
   if (has_emb) {                                /* "emF<j>.<id>": occupied slots only, in slot-range chunks */
     const uint32_t chunk = (uint32_t)std::min<int64_t>(emb.C, 1 << 20);
-    unsigned long long* d_keys = dmalloc<unsigned long long>(chunk);
-    float* d_rows = dmalloc<float>((size_t)3 * chunk * D);
-    uint32_t* d_cnt = dmalloc_zero<uint32_t>(1, ctx->stream);
+    DevBuf<unsigned long long> g_keys(dmalloc<unsigned long long>(chunk));
+    DevBuf<float> g_rows(dmalloc<float>((size_t)3 * chunk * D));
+    DevBuf<uint32_t> g_cnt(dmalloc_zero<uint32_t>(1, ctx->stream));
+    unsigned long long* d_keys = g_keys.get(); float* d_rows = g_rows.get(); uint32_t* d_cnt = g_cnt.get();
     std::vector<unsigned long long> hk(chunk);
     std::vector<float> hr((size_t)3 * chunk * D);
     int64_t written = 0;
     for (int64_t s0 = 0; s0 < emb.C; s0 += chunk) {
       const uint32_t s1 = (uint32_t)std::min<int64_t>(emb.C, s0 + chunk);
       PS_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(uint32_t), ctx->stream));
-      emb_export_kernel<<<ceil_div(s1 - (uint32_t)s0, 256), 256, 0, ctx->stream>>>(emb.slots, (uint32_t)s0, s1, emb.w, emb.s1, emb.s2, emb.Dp, D, d_keys, d_rows,
+      emb_export_kernel<<<ceil_div(s1 - (uint32_t)s0, 256), 256, 0, ctx->stream>>>(emb.slots, (uint32_t)s0, s1, emb.w, emb.s1, emb.s2, emb.rs, D, d_keys, d_rows,
                                                                                   chunk, d_cnt);
       PS_LAUNCH_CHECK();
       ctx->launches++;
@@ -146,9 +154,12 @@ void Model::save(const std::string& path) {
     }
     const uint32_t end = 0;
     wr(f.get(), &end, sizeof end);
-    dfree(d_keys); dfree(d_rows); dfree(d_cnt);
     PS_REQUIRE(written == h.emb_rows, PS_ERR_STATE, "save: embedding row count changed during the dump");
   }
+  PS_REQUIRE(std::fflush(f.get()) == 0, PS_ERR_ARG, "save: flush failed (disk full?)");
+  FILE* raw = f.release();
+  PS_REQUIRE(std::fclose(raw) == 0, PS_ERR_ARG, "save: close failed (disk full?)");
+  PS_REQUIRE(std::rename(tmp_path.c_str(), path.c_str()) == 0, PS_ERR_ARG, ("save: cannot rename into " + path).c_str());
 }
 
 void Model::load(const std::string& path) {
@@ -179,8 +190,9 @@ void Model::load(const std::string& path) {
   if (has_emb) {
     PS_REQUIRE(h.emb_rows <= emb.C, PS_ERR_CAPACITY, "load: more embedding rows than this table's capacity");
     const uint32_t chunk = 1 << 20;
-    unsigned long long* d_keys = dmalloc<unsigned long long>(chunk);
-    float* d_rows = dmalloc<float>((size_t)3 * chunk * D);
+    DevBuf<unsigned long long> g_keys(dmalloc<unsigned long long>(chunk));
+    DevBuf<float> g_rows(dmalloc<float>((size_t)3 * chunk * D));
+    unsigned long long* d_keys = g_keys.get(); float* d_rows = g_rows.get();
     std::vector<unsigned long long> hk;
     std::vector<float> hr;
     while (true) {
@@ -194,12 +206,11 @@ void Model::load(const std::string& path) {
       PS_CUDA(cudaMemcpyAsync(d_keys, hk.data(), sizeof(unsigned long long) * n, cudaMemcpyHostToDevice, ctx->stream));
       for (int which = 0; which < 3; ++which)
         PS_CUDA(cudaMemcpyAsync(d_rows + (size_t)which * chunk * D, hr.data() + (size_t)which * n * D, sizeof(float) * (size_t)n * D, cudaMemcpyHostToDevice, ctx->stream));
-      emb_import_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(emb.slots, (uint32_t)emb.C, emb.w, emb.s1, emb.s2, emb.Dp, D, d_keys, d_rows, n, chunk, emb.counters);
+      emb_import_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(emb.slots, (uint32_t)emb.C, emb.w, emb.s1, emb.s2, emb.rs, D, d_keys, d_rows, n, chunk, emb.counters);
       PS_LAUNCH_CHECK();
       ctx->launches++;
       PS_CUDA(cudaStreamSynchronize(ctx->stream));
     }
-    dfree(d_keys); dfree(d_rows);
     emb.check_errors();
     PS_REQUIRE(emb.size() == h.emb_rows, PS_ERR_STATE, "load: embedding row count does not match the header");
   }

@@ -53,13 +53,14 @@ struct Ctx {
   uint64_t seed = 0;
   cudaStream_t stream = nullptr;   /* compute stream: every kernel of a step is ordered on it */
   cudaStream_t copy_stream = nullptr; /* H2D staging for the pipelined trainer */
-  int fc_precision = PS_FC_FP32;
+  int fc_precision = PS_FC_TF32X3;  /* FcLayer arithmetic: tcgen05 tensor cores, error-compensated 3xTF32 = fp32-grade (ps_ctx_set_fc_precision) */
   int prio_main = 0, prio_side = 0; /* stream priorities of the critical chain / the side branches */
   int pdl = 1;                     /* programmatic dependent launch for producer -> consumer kernel pairs (PS_PDL=0 disables) */
   int pdl_gemm = 0;                /* ... also along the FcLayer forward / dgrad GEMM chain: measured SLOWER at cfg2 (172.8 vs 164.6 us
                                       per step: early CTAs of the next GEMM take the 20 SMs the side-stream wgrad would use), so off
                                       unless PS_PDL_GEMM=1 */
   int exact_updaters = 0;          /* sparse update with the IEEE divisions / roots of the Java code (PS_EXACT_UPDATERS=1) instead of the fast forms */
+  int hot_tma = 1;                 /* the lookup stages rows shared by >= 4 lookups of a warp task in shared memory by TMA bulk copies (PS_HOT_TMA=0: off) */
   unsigned hot_min = 8;            /* occurrences in a batch from which the scatter pre-sums a key per block (PS_HOT_MIN; 0 = never) */
   long launches = 0;               /* kernels launched by this library (bench gpu_launches) */
 };

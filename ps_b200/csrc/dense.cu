@@ -74,10 +74,8 @@ void transpose_copy(Ctx* ctx, const float* in, int ldi, float* out, int ldo, int
 __device__ __forceinline__ void publish(StepStatus* st, const uint32_t* emb_counters, const uint32_t* wide_counters, StepStatus* host) {
   StepStatus s = *st;
   s.emb_err = emb_counters ? emb_counters[1] : 0u;
-  const uint32_t cur = emb_counters ? emb_counters[0] : 0u;     /* monotonic: this step's unique keys = the increment */
-  s.n_unique = cur - st->pad;
+  s.n_unique = emb_counters ? emb_counters[0] : 0u;             /* written by the lookup kernel's last block: final long before any publish */
   s.wide_err = wide_counters ? wide_counters[0] : 0u;
-  st->pad = cur;
   *host = s;
   __threadfence_system();
 }
@@ -136,9 +134,10 @@ void dense_update(Ctx* ctx, const DenseUpdateArgs& a, StepStatus* st, const uint
 }
 
 __global__ void __launch_bounds__(256) dense_reduce_kernel(const __grid_constant__ DenseUpdateArgs a, const StepStatus* __restrict__ st,
-                                                           float* __restrict__ gsum) {
+                                                           float* __restrict__ gsum, const uint32_t* __restrict__ emb_counters) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx == 0) { gsum[a.total] = st->loss; gsum[a.total + 1] = st->gbar; }
+  /* third scalar: this rank's embedding shard is full — summed over ranks it makes EVERY replica skip the step */
+  if (idx == 0) { gsum[a.total] = st->loss; gsum[a.total + 1] = st->gbar; gsum[a.total + 2] = (emb_counters != nullptr && emb_counters[1] != 0u) ? 1.0f : 0.0f; }
   if (idx >= a.total) return;
   int li = 0;
   while (li + 1 < a.n_layers && idx >= a.l[li + 1].first) ++li;
@@ -150,52 +149,60 @@ __global__ void __launch_bounds__(256) dense_reduce_kernel(const __grid_constant
   for (int z = 0; z < L.nsplit; ++z) g = __fadd_rn(g, L.G[(size_t)z * L.slab + (size_t)o * L.ldg + c]);
   gsum[idx] = g;
 }
-void dense_reduce(Ctx* ctx, const DenseUpdateArgs& a, const StepStatus* st, float* gsum) {
-  dense_reduce_kernel<<<ceil_div(a.total + 1, 256), 256, 0, ctx->stream>>>(a, st, gsum);
+void dense_reduce(Ctx* ctx, const DenseUpdateArgs& a, const StepStatus* st, float* gsum, const uint32_t* emb_counters) {
+  dense_reduce_kernel<<<ceil_div(a.total + 1, 256), 256, 0, ctx->stream>>>(a, st, gsum, emb_counters);
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }
 
 /* dense_reduce + all-gather by stores: every rank's slot `me` of gsum_in receives this rank's sums */
 __global__ void __launch_bounds__(256) dense_reduce_send_kernel(const __grid_constant__ DenseUpdateArgs a, const StepStatus* __restrict__ st,
-                                                                const P2PState* __restrict__ p2p) {
+                                                                P2PState* __restrict__ p2p, const uint32_t* __restrict__ emb_counters) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int R = p2p->R, me = p2p->me, glen = p2p->glen;
   if (idx == 0) {
     for (int r = 0; r < R; ++r) {
       float* dst = reinterpret_cast<float*>(p2p_region(p2p, r, p2p->off_gsum)) + (size_t)me * glen;
       dst[a.total] = st->loss; dst[a.total + 1] = st->gbar;
+      dst[a.total + 2] = (emb_counters != nullptr && emb_counters[1] != 0u) ? 1.0f : 0.0f;
     }
   }
-  if (idx >= a.total) return;
-  int li = 0;
-  while (li + 1 < a.n_layers && idx >= a.l[li + 1].first) ++li;
-  const DenseLayerDesc& L = a.l[li];
-  const long r0 = idx - L.first;
-  const int cols = L.in + 1;
-  const int o = (int)(r0 / cols), c = (int)(r0 - (long)o * cols);
-  float g = 0.0f;
-  for (int z = 0; z < L.nsplit; ++z) g = __fadd_rn(g, L.G[(size_t)z * L.slab + (size_t)o * L.ldg + c]);
-  for (int r = 0; r < R; ++r) reinterpret_cast<float*>(p2p_region(p2p, r, p2p->off_gsum))[(size_t)me * glen + idx] = g;
+  if (idx < a.total) {
+    int li = 0;
+    while (li + 1 < a.n_layers && idx >= a.l[li + 1].first) ++li;
+    const DenseLayerDesc& L = a.l[li];
+    const long r0 = idx - L.first;
+    const int cols = L.in + 1;
+    const int o = (int)(r0 / cols), c = (int)(r0 - (long)o * cols);
+    float g = 0.0f;
+    for (int z = 0; z < L.nsplit; ++z) g = __fadd_rn(g, L.G[(size_t)z * L.slab + (size_t)o * L.ldg + c]);
+    for (int r = 0; r < R; ++r) reinterpret_cast<float*>(p2p_region(p2p, r, p2p->off_gsum))[(size_t)me * glen + idx] = g;
+  }
+  p2p_publish_last(p2p, CH_GSUM, gridDim.x);     /* the last block flags every replica: this rank's sums are in its gsum_in */
 }
-void dense_reduce_send(Ctx* ctx, const DenseUpdateArgs& a, const StepStatus* st, const P2PState* p2p) {
-  dense_reduce_send_kernel<<<ceil_div(a.total + 1, 256), 256, 0, ctx->stream>>>(a, st, p2p);
+void dense_reduce_send(Ctx* ctx, const DenseUpdateArgs& a, const StepStatus* st, P2PState* p2p, const uint32_t* emb_counters) {
+  dense_reduce_send_kernel<<<ceil_div(a.total + 1, 256), 256, 0, ctx->stream>>>(a, st, p2p, emb_counters);
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }
 
 /* global loss / gbar / early-exit flag from the R ranks' [loss, gbar] in the gsum_in mailbox (rank order) */
 __global__ void shard_finish_scalars_p2p_kernel(StepStatus* st, const P2PState* p2p, long total) {
+  p2p_wait_all(p2p, CH_GSUM);                    /* every replica's sums and scalars have landed */
+  if (threadIdx.x != 0) return;
   const float* in = reinterpret_cast<const float*>(p2p_region(p2p, p2p->me, p2p->off_gsum));
-  float l = 0.f, g = 0.f;
-  for (int r = 0; r < p2p->R; ++r) { l = __fadd_rn(l, in[(size_t)r * p2p->glen + total]); g = __fadd_rn(g, in[(size_t)r * p2p->glen + total + 1]); }
+  float l = 0.f, g = 0.f, full = 0.f;
+  for (int r = 0; r < p2p->R; ++r) {
+    l = __fadd_rn(l, in[(size_t)r * p2p->glen + total]); g = __fadd_rn(g, in[(size_t)r * p2p->glen + total + 1]);
+    full += in[(size_t)r * p2p->glen + total + 2];
+  }
   const float loss = __fdiv_rn(l, (float)p2p->R);
   st->loss = loss;
   st->gbar = __fdiv_rn(g, (float)p2p->R);
-  st->skip = (loss <= 0.01f || isnan(loss)) ? 1 : 0;
+  st->skip = (loss <= 0.01f || isnan(loss) || full != 0.f) ? 1 : 0;
 }
 void shard_finish_scalars_p2p(Ctx* ctx, StepStatus* st, const P2PState* p2p, long total) {
-  shard_finish_scalars_p2p_kernel<<<1, 1, 0, ctx->stream>>>(st, p2p, total);
+  shard_finish_scalars_p2p_kernel<<<1, 32, 0, ctx->stream>>>(st, p2p, total);
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }
@@ -204,7 +211,7 @@ __global__ void shard_finish_scalars_kernel(StepStatus* st, const float* tail, i
   const float loss = __fdiv_rn(tail[0], (float)R);
   st->loss = loss;
   st->gbar = __fdiv_rn(tail[1], (float)R);
-  st->skip = (loss <= 0.01f || isnan(loss)) ? 1 : 0;
+  st->skip = (loss <= 0.01f || isnan(loss) || tail[2] != 0.f) ? 1 : 0;      /* tail[2]: some rank's embedding shard is full */
 }
 void shard_finish_scalars(Ctx* ctx, StepStatus* st, const float* gsum_tail, int R) {
   shard_finish_scalars_kernel<<<1, 1, 0, ctx->stream>>>(st, gsum_tail, R);
@@ -246,7 +253,8 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
 /* Each block reduces its samples, the block that takes the last ticket adds the per-block
  * partials in block order (a fixed tree: same bits every run) and writes the step status.
  * ws: [0, 2*kTailMaxBlocks) partial sums, then one u32 ticket that the finisher resets.       */
-__device__ __forceinline__ void tail_finish(float loss_part, float d_part, int N, float* ws, StepStatus* st, float* sh) {
+__device__ __forceinline__ void tail_finish(float loss_part, float d_part, int N, float* ws, StepStatus* st, float* sh, const uint32_t* emb_counters,
+                                            bool ext_loss = false, float ext_loss_value = 0.f) {
   const float bl = block_sum(loss_part, sh), bd = block_sum(d_part, sh);
   __shared__ bool is_last;
   unsigned int* ticket = reinterpret_cast<unsigned int*>(ws + 2 * kTailMaxBlocks);
@@ -261,10 +269,14 @@ __device__ __forceinline__ void tail_finish(float loss_part, float d_part, int N
   for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) { l = __fadd_rn(l, __ldcg(ws + 2 * b)); d = __fadd_rn(d, __ldcg(ws + 2 * b + 1)); }
   l = block_sum(l, sh); d = block_sum(d, sh);
   if (threadIdx.x == 0) {
-    const float loss = __fdiv_rn(l, (float)N);
+    const float loss = ext_loss ? ext_loss_value : __fdiv_rn(l, (float)N);   /* ext_loss: the caller's own Loss.forward produced it (DNN.java:47) */
     st->loss = loss;
     st->gbar = __fdiv_rn(d, (float)N);
-    st->skip = (loss <= 0.01f || isnan(loss)) ? 1 : 0;                       /* DNN.java:58, CrossEntropy.slim */
+    /* DNN.java:58, CrossEntropy.slim — and a full embedding table: keys of this batch could not be created, so NOTHING of the
+     * step is applied (backward, dense / wide / embedding updates all honour this flag); collect() reports PS_ERR_CAPACITY */
+    const bool table_full = emb_counters != nullptr && emb_counters[1] != 0u;
+    const bool bad_input = st->pad != 0u;        /* submit_text: a line of the batch could not be parsed — the batch is dropped (DataSet.java:96-98) */
+    st->skip = (loss <= 0.01f || isnan(loss) || table_full || bad_input) ? 1 : 0;
     st->seq += 1u;
     *ticket = 0u;
   }
@@ -276,7 +288,7 @@ __device__ __forceinline__ void tail_finish(float loss_part, float d_part, int N
 __global__ void __launch_bounds__(kTailThreads) tail_binary_kernel(int N, const float* __restrict__ zdeep, int ldz, const float* __restrict__ zwide,
                                                                    const float* __restrict__ Y, float* __restrict__ p_out, int ldp,
                                                                    float* __restrict__ d_out, int ldd, float* __restrict__ dt_out, int train,
-                                                                   StepStatus* __restrict__ st, float* __restrict__ ws) {
+                                                                   StepStatus* __restrict__ st, float* __restrict__ ws, const uint32_t* __restrict__ emb_counters) {
   __shared__ float sh[kTailThreads];
   float loss_part = 0.0f, d_part = 0.0f;
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
@@ -296,19 +308,38 @@ __global__ void __launch_bounds__(kTailThreads) tail_binary_kernel(int N, const 
     }
   }
   if (!train) return;
-  tail_finish(loss_part, d_part, N, ws, st, sh);
+  tail_finish(loss_part, d_part, N, ws, st, sh, emb_counters);
 }
+/* The last layer's half of the reverse loop when the loss lives in the caller (DNN.java:47-49,64): delta_top = loss.backward(P, Y)
+ * arrives from the host; FcLayer.backward's first act is activation.backward (FcLayer.java:100-102) = Sigmoid.backward
+ * (Sigmoid.java:16-21: dy * y * (1 - y)); LRLayer.backward needs rowMeans of the result (LRLayer.java:110).               */
+__global__ void __launch_bounds__(kTailThreads) tail_binary_from_delta_kernel(int N, const float* __restrict__ p, int ldp, const float* __restrict__ dtop,
+                                                                              float* __restrict__ d_out, int ldd, float* __restrict__ dt_out, float loss,
+                                                                              StepStatus* __restrict__ st, float* __restrict__ ws,
+                                                                              const uint32_t* __restrict__ emb_counters) {
+  __shared__ float sh[kTailThreads];
+  float d_part = 0.0f;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+    const float y = p[(size_t)n * ldp];
+    const float d = __fmul_rn(dtop[n], __fmul_rn(y, __fsub_rn(1.0f, y)));
+    d_out[(size_t)n * ldd] = d;
+    if (dt_out) dt_out[n] = d;
+    d_part = __fadd_rn(d_part, d);
+  }
+  tail_finish(0.0f, d_part, N, ws, st, sh, emb_counters, true, loss);
+}
+
 static int tail_blocks(int N) { return std::max(1, std::min(kTailMaxBlocks, ceil_div(N, kTailThreads))); }
 void tail_binary(Ctx* ctx, int N, const float* zdeep, int ldz, const float* zwide, const float* Y, float* p_out, int ldp, float* d_out, int ldd,
-                 float* dt_out, int train, StepStatus* st, float* ws) {
-  tail_binary_kernel<<<tail_blocks(N), kTailThreads, 0, ctx->stream>>>(N, zdeep, ldz, zwide, Y, p_out, ldp, d_out, ldd, dt_out, train, st, ws);
+                 float* dt_out, int train, StepStatus* st, float* ws, const uint32_t* emb_counters) {
+  tail_binary_kernel<<<tail_blocks(N), kTailThreads, 0, ctx->stream>>>(N, zdeep, ldz, zwide, Y, p_out, ldp, d_out, ldd, dt_out, train, st, ws, emb_counters);
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }
 
 __global__ void __launch_bounds__(kTailThreads) tail_softmax_kernel(int N, int C, float* __restrict__ Z, int ldz, const float* __restrict__ Y,
                                                                     float* __restrict__ d_out, int ldd, float* __restrict__ dt_out, int ldt, int train,
-                                                                    StepStatus* __restrict__ st, float* __restrict__ ws) {
+                                                                    StepStatus* __restrict__ st, float* __restrict__ ws, const uint32_t* __restrict__ emb_counters) {
   __shared__ float sh[kTailThreads];
   float loss_part = 0.0f;
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
@@ -337,11 +368,18 @@ __global__ void __launch_bounds__(kTailThreads) tail_softmax_kernel(int N, int C
     }
   }
   if (!train) return;
-  tail_finish(loss_part, 0.0f, N, ws, st, sh);
+  tail_finish(loss_part, 0.0f, N, ws, st, sh, emb_counters);
 }
+void tail_binary_from_delta(Ctx* ctx, int N, const float* p, int ldp, const float* dtop, float* d_out, int ldd, float* dt_out, float loss,
+                            StepStatus* st, float* ws, const uint32_t* emb_counters) {
+  tail_binary_from_delta_kernel<<<tail_blocks(N), kTailThreads, 0, ctx->stream>>>(N, p, ldp, dtop, d_out, ldd, dt_out, loss, st, ws, emb_counters);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+}
+
 void tail_softmax(Ctx* ctx, int N, int C, float* Z, int ldz, const float* Y, float* d_out, int ldd, float* dt_out, int ldt, int train,
                   StepStatus* st, float* ws) {
-  tail_softmax_kernel<<<tail_blocks(N), kTailThreads, 0, ctx->stream>>>(N, C, Z, ldz, Y, d_out, ldd, dt_out, ldt, train, st, ws);
+  tail_softmax_kernel<<<tail_blocks(N), kTailThreads, 0, ctx->stream>>>(N, C, Z, ldz, Y, d_out, ldd, dt_out, ldt, train, st, ws, nullptr);
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }
@@ -355,7 +393,7 @@ __global__ void __launch_bounds__(kTailThreads) fc1_forward_tail_kernel(int N, i
                                                                         const float* __restrict__ Y, float* __restrict__ z_out, int ldz,
                                                                         float* __restrict__ p_out, int ldp, float* __restrict__ d_out, int ldd,
                                                                         float* __restrict__ dt_out, int train, StepStatus* __restrict__ st,
-                                                                        float* __restrict__ ws) {
+                                                                        float* __restrict__ ws, const uint32_t* __restrict__ emb_counters) {
   __shared__ float sh[kTailThreads];
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -395,12 +433,13 @@ __global__ void __launch_bounds__(kTailThreads) fc1_forward_tail_kernel(int N, i
     }
   }
   if (!train) return;
-  tail_finish(loss_part, d_part, N, ws, st, sh);
+  tail_finish(loss_part, d_part, N, ws, st, sh, emb_counters);
 }
 void fc1_forward_tail(Ctx* ctx, int N, int in, const float* A, int lda, const float* w, const float* bias, const float* zwide, const float* Y,
-                      float* z_out, int ldz, float* p_out, int ldp, float* d_out, int ldd, float* dt_out, int train, StepStatus* st, float* ws) {
+                      float* z_out, int ldz, float* p_out, int ldp, float* d_out, int ldd, float* dt_out, int train, StepStatus* st, float* ws,
+                      const uint32_t* emb_counters) {
   const int blocks = std::max(1, std::min(kTailMaxBlocks, ceil_div((long)N * 32, kTailThreads)));
-  fc1_forward_tail_kernel<<<blocks, kTailThreads, 0, ctx->stream>>>(N, in, A, lda, w, bias, zwide, Y, z_out, ldz, p_out, ldp, d_out, ldd, dt_out, train, st, ws);
+  fc1_forward_tail_kernel<<<blocks, kTailThreads, 0, ctx->stream>>>(N, in, A, lda, w, bias, zwide, Y, z_out, ldz, p_out, ldp, d_out, ldd, dt_out, train, st, ws, emb_counters);
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }

@@ -20,7 +20,7 @@ struct StepStatus {
   uint32_t wide_err;
   uint32_t n_unique;/* unique embedding keys of the batch */
   uint32_t seq;     /* step sequence number */
-  uint32_t pad;     /* device-side: unique-key counter value at the previous publish */
+  uint32_t pad;     /* submit_text: lines of the batch the device parser could not take (non-zero = the batch is dropped) */
 };
 
 /* one FcLayer's parameters as the fused update kernel sees them */
@@ -47,20 +47,24 @@ void fill_column(Ctx* ctx, float* buf, int ld, int col, int rows, float value);
 void dense_update(Ctx* ctx, const DenseUpdateArgs& a, StepStatus* st, const uint32_t* emb_counters, const uint32_t* wide_counters,
                   StepStatus* host_mapped, const P2PState* p2p = nullptr /* gradients come from this step's gsum_in mailbox */);
 /* peer-memory forms of dense_reduce / shard_finish_scalars (p2p.cuh): sums stored straight into every rank's mailbox */
-void dense_reduce_send(Ctx* ctx, const DenseUpdateArgs& a, const StepStatus* st, const P2PState* p2p);
+void dense_reduce_send(Ctx* ctx, const DenseUpdateArgs& a, const StepStatus* st, P2PState* p2p, const uint32_t* emb_counters = nullptr);   /* publishes CH_GSUM */
 void shard_finish_scalars_p2p(Ctx* ctx, StepStatus* st, const P2PState* p2p, long total);
 constexpr int kTailWorkspaceFloats = 2 * 1024 + 4;
 
 /* binary tail: z = deep (+ wide); p = clipped sigmoid; CrossEntropy forward/backward; sigmoid
  * derivative.  Writes p to p_out (stride ldp), the post-derivative delta to d_out (stride ldd). */
 void tail_binary(Ctx* ctx, int N, const float* zdeep, int ldz, const float* zwide, const float* Y, float* p_out, int ldp,
-                 float* d_out, int ldd, float* dt_out, int train, StepStatus* st, float* ws);
+                 float* d_out, int ldd, float* dt_out, int train, StepStatus* st, float* ws, const uint32_t* emb_counters = nullptr);
+/* the reverse loop's first step when the caller computed the loss itself: d = delta_top * p * (1 - p), gbar, skip; `loss` is recorded as given */
+void tail_binary_from_delta(Ctx* ctx, int N, const float* p, int ldp, const float* dtop, float* d_out, int ldd, float* dt_out, float loss,
+                            StepStatus* st, float* ws, const uint32_t* emb_counters);
 /* multi-class tail (FullConnectedNN): Softmax(10000) in place on Z, SoftmaxLoss, Softmax.backward */
 void tail_softmax(Ctx* ctx, int N, int C, float* Z, int ldz, const float* Y, float* d_out, int ldd, float* dt_out, int ldt, int train,
                   StepStatus* st, float* ws);
 /* the 1-unit top FcLayer on CUDA cores (see dense.cu): forward GEMV fused with the binary tail, dgrad, wgrad */
 void fc1_forward_tail(Ctx* ctx, int N, int in, const float* A, int lda, const float* w, const float* bias, const float* zwide, const float* Y,
-                      float* z_out, int ldz, float* p_out, int ldp, float* d_out, int ldd, float* dt_out, int train, StepStatus* st, float* ws);
+                      float* z_out, int ldz, float* p_out, int ldp, float* d_out, int ldd, float* dt_out, int train, StepStatus* st, float* ws,
+                      const uint32_t* emb_counters = nullptr /* EmbTable::counters: a full table turns into the step's skip flag */);
 void fc1_dgrad(Ctx* ctx, int N, int in, const float* d, int ldd, const float* dT /* contiguous copy of d or null */, const float* w, int act_below, const float* Y, int ldy, float* dX, int ldx,
                const float* Yt, int ldyt, float* dXt, int ldxt);
 void fc1_wgrad(Ctx* ctx, int N, int in, const float* d, int ldd, const float* A, int lda, float* G, size_t slab, int nsplit);
@@ -68,8 +72,8 @@ void fc1_wgrad(Ctx* ctx, int N, int in, const float* d, int ldd, const float* A,
 /* copies the status (plus table error flags) to mapped host memory */
 void publish_status(Ctx* ctx, StepStatus* st, const uint32_t* emb_counters, const uint32_t* wide_counters, StepStatus* host_mapped);
 /* sharded (multi-GPU) step: gsum[compact (o, c) index] = sum of the wgrad slabs, then [loss, gbar] at
- * gsum[total], gsum[total+1] — ONE flat buffer the host all-reduces across ranks               */
-void dense_reduce(Ctx* ctx, const DenseUpdateArgs& a, const StepStatus* st, float* gsum);
+ * gsum[total], gsum[total+1] (+ the table-full flag at gsum[total+2]) — ONE flat buffer the host all-reduces across ranks               */
+void dense_reduce(Ctx* ctx, const DenseUpdateArgs& a, const StepStatus* st, float* gsum, const uint32_t* emb_counters = nullptr);
 /* after the all-reduce (sum over R ranks of per-rank means): global loss / gbar / early-exit flag */
 void shard_finish_scalars(Ctx* ctx, StepStatus* st, const float* gsum_tail, int R);
 

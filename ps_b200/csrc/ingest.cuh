@@ -26,6 +26,10 @@ int parse_ctr_line(const char* b, const char* e, int F, int Xn, int64_t wide, in
 int libsvm_parse_dev(Ctx* ctx, const char* text_dev, size_t len, int F, int Xn, int64_t wide, int max_rows, int64_t* E, float* X, int64_t* W, float* Y,
                      uint8_t* status, uint32_t* ws /* >= len / 4096 + 2 + max_rows uint32 */);
 
+/* fully asynchronous form for Model::submit_text: exactly `rows` lines expected, *bad_dev counts the lines that are not usable */
+void libsvm_parse_dev_async(Ctx* ctx, const char* text_dev, size_t len, int F, int Xn, int64_t wide, int rows, int64_t* E, float* X, int64_t* W, float* Y,
+                            uint8_t* status, uint32_t* ws /* >= len / 4096 + 2 + rows uint32 */, uint32_t* bad_dev);
+
 struct LibsvmReader {
   struct Batch;
   int F, Xn;

@@ -126,9 +126,14 @@ __device__ __forceinline__ const char* dev_decimal(const char* q, const char* e,
 
 __global__ void __launch_bounds__(128) parse_lines_kernel(const char* __restrict__ text, size_t len, const uint32_t* __restrict__ line_end, int rows,
                                                           int F, int Xn, long long wide, long long* __restrict__ E, float* __restrict__ X,
-                                                          long long* __restrict__ W, float* __restrict__ Y, unsigned char* __restrict__ status) {
+                                                          long long* __restrict__ W, float* __restrict__ Y, unsigned char* __restrict__ status,
+                                                          const uint32_t* __restrict__ total, uint32_t* __restrict__ bad) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
+  if (total != nullptr) {                        /* asynchronous form: exactly `rows` lines are expected, nobody looked at the count */
+    if (r == 0 && *total != (uint32_t)rows) atomicAdd(bad, 1u);
+    if ((uint32_t)r >= *total) { status[r] = 3; return; }
+  }
   const char* b = text + (r == 0 ? 0 : (size_t)line_end[r - 1] + 1);
   const char* e = text + line_end[r];
   if (e > b && e[-1] == '\r') --e;
@@ -136,7 +141,7 @@ __global__ void __launch_bounds__(128) parse_lines_kernel(const char* __restrict
   {
     const char* p = b;
     while (p < e && (unsigned char)*p <= ' ') ++p;
-    if (p == e) { status[r] = 1; return; }
+    if (p == e) { status[r] = 1; if (bad != nullptr) atomicAdd(bad, 1u); return; }
   }
   while (e > b && e[-1] == ' ') --e;             /* String.split(" ") drops trailing empty strings */
   const int need = 1 + F + Xn;
@@ -174,6 +179,7 @@ __global__ void __launch_bounds__(128) parse_lines_kernel(const char* __restrict
   }
   if (st == 0 && col < need) st = 1;                    /* short line */
   status[r] = st;
+  if (st != 0 && bad != nullptr) atomicAdd(bad, 1u);
 }
 
 }  // namespace
@@ -198,11 +204,33 @@ int libsvm_parse_dev(Ctx* ctx, const char* text_dev, size_t len, int F, int Xn, 
   const int rows = (int)std::min<uint32_t>(n, (uint32_t)max_rows);
   if (rows > 0) {
     parse_lines_kernel<<<ceil_div(rows, 128), 128, 0, s>>>(text_dev, len, line_end, rows, F, Xn, (long long)wide, reinterpret_cast<long long*>(E), X,
-                                                          reinterpret_cast<long long*>(W), Y, status);
+                                                          reinterpret_cast<long long*>(W), Y, status, nullptr, nullptr);
     PS_LAUNCH_CHECK();
   }
   ctx->launches += 3 + (rows > 0 ? 1 : 0);
   return rows;
+}
+
+/* the same without any host synchronisation: the text is expected to hold exactly `rows` lines; *bad (device memory) ends up as the
+ * number of lines that are missing, surplus-flagged, blank, short or outside the fast path's spellings — 0 means E/X/W/Y hold
+ * exactly what the host reader would have produced.  Everything is enqueued on ctx->stream.                               */
+void libsvm_parse_dev_async(Ctx* ctx, const char* text_dev, size_t len, int F, int Xn, int64_t wide, int rows, int64_t* E, float* X, int64_t* W, float* Y,
+                            uint8_t* status, uint32_t* ws, uint32_t* bad) {
+  PS_REQUIRE(text_dev && E && X && W && Y && status && ws && bad && F >= 0 && Xn >= 0 && wide > 0 && rows > 0, PS_ERR_ARG, "libsvm_parse_dev_async: bad argument");
+  PS_REQUIRE(len > 0 && len < (1ull << 32), PS_ERR_ARG, "libsvm_parse_dev_async: text must be 1 byte .. 4 GiB");
+  cudaStream_t s = ctx->stream;
+  const int chunks = (int)((len + kChunk - 1) / kChunk);
+  uint32_t* chunk_count = ws;
+  uint32_t* total = ws + chunks;
+  uint32_t* line_end = ws + chunks + 1;
+  PS_CUDA(cudaMemsetAsync(bad, 0, sizeof(uint32_t), s));
+  newline_count_kernel<<<chunks, 256, 0, s>>>(text_dev, len, chunk_count);
+  chunk_scan_kernel<<<1, 1024, 0, s>>>(chunk_count, chunks, total);
+  newline_index_kernel<<<chunks, 256, 0, s>>>(text_dev, len, chunk_count, line_end, (uint32_t)rows);
+  parse_lines_kernel<<<ceil_div(rows, 128), 128, 0, s>>>(text_dev, len, line_end, rows, F, Xn, (long long)wide, reinterpret_cast<long long*>(E), X,
+                                                        reinterpret_cast<long long*>(W), Y, status, total, bad);
+  PS_LAUNCH_CHECK();
+  ctx->launches += 4;
 }
 
 }  // namespace psb

@@ -127,7 +127,7 @@ void Model::destroy() {
   for (auto& g : graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
   graphs.clear();
   for (auto& S : stage) {
-    dfree(S.E); dfree(S.W); dfree(S.X); dfree(S.Y);
+    dfree(S.E); dfree(S.W); dfree(S.X); dfree(S.Y); dfree(S.text); dfree(S.text_ws); dfree(S.text_status);
     if (S.st_host) cudaFreeHost(S.st_host);
     if (S.h2d_done) cudaEventDestroy(S.h2d_done);
     if (S.step_done) cudaEventDestroy(S.step_done);
@@ -228,10 +228,10 @@ void Model::run_tail(const float* Y, int N, bool train) {
   } else if (top_is_unit()) {
     const FcLayer& f = fcs[L - 1];
     fc1_forward_tail(ctx, N, f.in, act[L - 1], ld[L - 1], f.W, f.bias, has_wide ? wide_z : nullptr, Y, act[L], ld[L], has_wide ? P : act[L],
-                     has_wide ? 1 : ld[L], delta[L], ld[L], fp32 ? nullptr : delta_t[L], train ? 1 : 0, st_dev, tail_ws);
+                     has_wide ? 1 : ld[L], delta[L], ld[L], fp32 ? nullptr : delta_t[L], train ? 1 : 0, st_dev, tail_ws, has_emb ? emb.counters : nullptr);
   } else {
     tail_binary(ctx, N, act[L], ld[L], has_wide ? wide_z : nullptr, Y, has_wide ? P : act[L], has_wide ? 1 : ld[L], delta[L], ld[L],
-                fp32 ? nullptr : delta_t[L], train ? 1 : 0, st_dev, tail_ws);
+                fp32 ? nullptr : delta_t[L], train ? 1 : 0, st_dev, tail_ws, has_emb ? emb.counters : nullptr);
   }
 }
 
@@ -283,6 +283,15 @@ void Model::fork(cudaStream_t from, cudaStream_t to) {
 }
 
 void Model::forward_backward(const int64_t* W, const int64_t* W_all, int n_all, const float* Y, int N, bool train, bool wide_update_now) {
+  forward_layers(N, train);
+  run_tail(Y, N, train);
+  mark("tail");
+  if (train) backward_layers(N, wide_update_now);
+}
+
+/* the forward loop of DNN.train / predict (DNN.java:44-46) after the input layers: FcLayer.forward x L; the wide branch the caller
+ * started on side stream 1 joins before the tail */
+void Model::forward_layers(int N, bool train) {
   cudaStream_t s = ctx->stream, s1 = aux[0], s2 = aux[1];
   const bool fp32 = ctx->fc_precision == PS_FC_FP32;
   fork(s, s2);
@@ -291,10 +300,12 @@ void Model::forward_backward(const int64_t* W, const int64_t* W_all, int n_all, 
     fwd_layer(l, N);
     mark(("fc_fwd" + std::to_string(l)).c_str());
   }
-  fork(s1, s);                                   /* wide_z (the caller started the wide branch on side stream 1) */
-  run_tail(Y, N, train);
-  mark("tail");
-  if (!train) return;
+  fork(s1, s);                                   /* wide_z */
+}
+
+/* the reverse loop of DNN.train (DNN.java:64-68) given delta[L] and the step status (gbar, skip) */
+void Model::backward_layers(int N, bool wide_update_now) {
+  cudaStream_t s = ctx->stream, s1 = aux[0], s2 = aux[1];
   /* ---- backward (DNN.java:64-68): the dgrad chain is the critical path; each wgrad runs beside it ---- */
   if (has_wide && wide_update_now) {
     fork(s, s2);
@@ -318,10 +329,8 @@ void Model::step_device(const int64_t* E, const float* X, const int64_t* W, cons
   fork(s, s1);
   if (has_wide) { StreamScope sc(ctx, s1); wide.forward(W, N, F, wide_bias, wide_z); }   /* LRLayer.forward beside the deep branch */
   if (has_emb) {
-    emb.probe(E, nullptr, N);
-    mark("emb_probe");
-    emb.gather(act[0], ld[0], N, 0, X, Xn, F * D);      /* EmbeddingLayer.forward + ConcatLayer.forward */
-    mark("emb_gather");
+    emb.lookup(E, nullptr, N, act[0], ld[0], X, Xn, F * D);   /* EmbeddingLayer.forward + ConcatLayer.forward: one kernel */
+    mark("emb_lookup");
   } else {
     PS_CUDA(cudaMemcpy2DAsync(act[0], sizeof(float) * ld[0], X, sizeof(float) * Xn, sizeof(float) * Xn, N, cudaMemcpyDeviceToDevice, s));
   }
@@ -339,7 +348,7 @@ void Model::step_device(const int64_t* E, const float* X, const int64_t* W, cons
     const DenseUpdateArgs u = dense_args(N);
     dense_update(ctx, u, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, publish_to);
   }
-  if (has_emb) { emb.scatter_update(delta[0], ld[0], act[0], ld[0], N, 2, skip_ptr(st_dev)); mark("emb_bwd_update"); }
+  if (has_emb) { emb.scatter_update(delta[0], ld[0], nullptr, 0, N, 2, skip_ptr(st_dev), 0, nullptr, true); mark("emb_bwd_update"); }
   fork(s1, s);
   fork(s2, s);
   mark("end");
@@ -364,8 +373,7 @@ DenseUpdateArgs Model::dense_args(int N) {
 
 void Model::shard_emb_lookup(const uint64_t* keys, int n, float* rows_out) {
   PS_REQUIRE(has_emb, PS_ERR_STATE, "model has no embedding layer");
-  emb.probe_packed(keys, n);
-  if (n > 0) emb.gather(rows_out, emb.Dp, n, 1);
+  emb.lookup_packed(keys, n, rows_out);
 }
 
 void Model::shard_unpack_rows(const float* rows, const int32_t* send_pos, int N) {
@@ -390,8 +398,8 @@ void Model::shard_dense_step(const float* X, const int64_t* W_local, const int64
   fork(s1, s);                                     /* all wgrads */
   fork(s2, s);
   const DenseUpdateArgs u = dense_args(N);
-  if (!gsum) { gsum_len = u.total + 2; gsum = dmalloc_zero<float>((size_t)gsum_len, s); }
-  dense_reduce(ctx, u, st_dev, gsum);
+  if (!gsum) { gsum_len = u.total + 3; gsum = dmalloc_zero<float>((size_t)gsum_len, s); }
+  dense_reduce(ctx, u, st_dev, gsum, has_emb ? emb.counters : nullptr);
   last_N = N; last_train = true;
 }
 
@@ -421,7 +429,7 @@ void Model::shard_emb_apply(const float* grads_recv, int n) {
 void Model::p2p_init(int R, int rank, int cap, void* handle_out64) {
   PS_REQUIRE(!p2p.slab, PS_ERR_STATE, "p2p already initialised");
   const DenseUpdateArgs u = dense_args(1);
-  const long glen = (u.total + 2 + 3) / 4 * 4;
+  const long glen = (u.total + 3 + 3) / 4 * 4;
   if (!gsum) { gsum_len = glen; gsum = dmalloc_zero<float>((size_t)gsum_len, ctx->stream); }
   PS_REQUIRE(gsum_len >= glen, PS_ERR_STATE, "gradient buffer was created before p2p_init with a smaller size");
   p2p.create(ctx, R, rank, has_emb ? cap : 1, has_emb ? emb.Dp : 4, std::max(2, Bmax * std::max(F, 1)), (int)glen, (int64_t)Bmax * std::max(F, 1));
@@ -443,19 +451,16 @@ void Model::p2p_step(const int64_t* E, const float* X, const int64_t* W, const f
   if (has_wide) {                                                               /* wide branch beside the embedding exchange */
     PS_REQUIRE(((size_t)N * F * 8) % 16 == 0, PS_ERR_ARG, "p2p: N*F must be even");
     StreamScope sc(ctx, s1);
-    p2p.bcast(W, (size_t)N * F * 8, CH_WIDE);
-    p2p.publish_wait(CH_WIDE);
-    wide.insert(nullptr, R * N * F, p2p.state());                               /* the union of every replica's keys */
+    p2p.bcast(W, (size_t)N * F * 8, CH_WIDE);                                   /* flags the peers itself */
+    wide.insert(nullptr, R * N * F, p2p.state());                               /* the union of every replica's keys (waits for their flags) */
     wide.forward(W, N, F, wide_bias, wide_z);
   }
   if (has_emb) {
-    p2p.dedup_route(E, N, F);                                                   /* PSRouterClient.getList: each key of the batch once */
-    p2p.send_keys();
-    p2p.publish_wait(CH_KEYS);
-    emb.probe_packed(nullptr, R * cap, p2p.state());                            /* PServer.getList on the owner */
-    p2p.gather_send(emb.w, D, emb.lk_slot);                                     /* rows back, stored by the gather itself */
-    p2p.publish_wait(CH_ROWS);
-    p2p.unpack(N, F, D, act[0], ld[0], X, Xn, F * D);                           /* + ConcatLayer */
+    /* every exchange below is ONE producer kernel that flags its consumers when its last block ends and ONE consumer kernel
+     * that waits for the flags in its prologue: no flag kernels, no host */
+    p2p.route_send(E, N, F);                                                    /* PSRouterClient.getList: each key of the batch once, stored into its owner's mailbox */
+    emb.lookup_packed(nullptr, R * cap, nullptr, p2p.dev, true);                /* PServer.getList on the owner: find-or-insert, rows stored straight into the requesters' mailboxes */
+    p2p.unpack(N, F, D, act[0], ld[0], X, Xn, F * D);                           /* rows_in -> concat buffer (+ ConcatLayer) */
   } else {
     PS_CUDA(cudaMemcpy2DAsync(act[0], sizeof(float) * ld[0], X, sizeof(float) * Xn, sizeof(float) * Xn, N, cudaMemcpyDeviceToDevice, s));
   }
@@ -466,14 +471,12 @@ void Model::p2p_step(const int64_t* E, const float* X, const int64_t* W, const f
   {
     StreamScope sc(ctx, s1);
     const DenseUpdateArgs u = dense_args(N * R);
-    dense_reduce_send(ctx, u, st_dev, p2p.state());
-    p2p.publish_wait(CH_GSUM);
+    dense_reduce_send(ctx, u, st_dev, p2p.dev, has_emb ? emb.counters : nullptr);
     shard_finish_scalars_p2p(ctx, st_dev, p2p.state(), u.total);
   }
   if (has_emb) {
     p2p.grad_reduce(delta[0], ld[0], act[0], ld[0], N, F, D);                   /* client.push: one gradient sum per unique key */
-    p2p.grad_send();
-    p2p.publish_wait(CH_GRADS);
+    p2p.grad_send();                                                            /* ... with its occurrence count, to the owner */
   }
   fork(s1, s);                                                                  /* the global skip flag */
   fork(s, s2);
@@ -483,7 +486,7 @@ void Model::p2p_step(const int64_t* E, const float* X, const int64_t* W, const f
     if (has_wide) wide.update_all(gbar_ptr(st_dev), skip_ptr(st_dev), wide_bias, &upd_wide);
     dense_update(ctx, u, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, nullptr, p2p.state());
   }
-  if (has_emb) emb.scatter_update(nullptr, emb.Dp, nullptr, emb.Dp, R * cap, 2, skip_ptr(st_dev), 1, p2p.state());
+  if (has_emb) emb.scatter_update_entries(p2p.state(), R * cap, 2, skip_ptr(st_dev));   /* PServer.push (sync mode) + psUpdate on the owner */
   fork(s2, s);
   last_N = N; last_train = true;
 }
@@ -496,15 +499,14 @@ void Model::kernel_times(const int64_t* const* E_ring, int n_ring, int N, int re
   PS_CUDA(cudaEventCreate(&e0)); PS_CUDA(cudaEventCreate(&e1));
   float total[4] = {0, 0, 0, 0};
   for (int variant = 0; variant < 4; ++variant) {
-    /* 0: probe+clear   1: probe+gather+clear   2: probe+gather+scatter_update   3: probe+clear+clear */
+    /* 0: resolve-only lookup + clear   1: lookup (resolve + gather) + clear   2: lookup + scatter_update   3: resolve-only + clear + clear */
     cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
     const long l0 = ctx->launches;
     PS_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
     try {
       for (int r = 0; r < reps; ++r) {
-        emb.probe(E_ring[r % n_ring], nullptr, N);
-        if (variant == 1 || variant == 2) emb.gather(act[0], ld[0], N);
-        if (variant == 2) emb.scatter_update(delta[0], ld[0], act[0], ld[0], N, 2, nullptr);
+        emb.lookup(E_ring[r % n_ring], nullptr, N, (variant == 1 || variant == 2) ? act[0] : nullptr, ld[0]);
+        if (variant == 2) emb.scatter_update(delta[0], ld[0], nullptr, 0, N, 2, nullptr, 0, nullptr, true);
         else emb.clear_batch();
         if (variant == 3) emb.clear_batch();
       }
@@ -525,8 +527,8 @@ void Model::kernel_times(const int64_t* const* E_ring, int n_ring, int N, int re
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   const float clear = total[3] - total[0];
-  out[0] = total[0] - clear;                 /* probe (includes the 4-byte counter memset node) */
-  out[1] = total[1] - total[0];              /* gather */
+  out[0] = total[0] - clear;                 /* key resolution alone (the lookup kernel without its gather) */
+  out[1] = total[1] - clear;                 /* the lookup kernel: key resolution + gather + mask, what EmbeddingLayer.forward costs */
   out[2] = total[2] - total[1] + clear;      /* scatter_update */
   out[3] = clear;
   emb.check_errors();
@@ -574,6 +576,10 @@ void Model::submit(const HostBatch& b, int mode) {
   Stage& S = stage[next_stage];
   cudaStream_t cs = ctx->copy_stream;
   const size_t N = (size_t)b.N;
+  if (pad_dirty) {                               /* a text batch may have left its bad-line count in the status: this batch is not text */
+    PS_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(st_dev) + offsetof(StepStatus, pad), 0, sizeof(uint32_t), ctx->stream));
+    pad_dirty = false;
+  }
   if (has_emb) PS_CUDA(cudaMemcpyAsync(S.E, b.E, sizeof(int64_t) * N * F, cudaMemcpyHostToDevice, cs));
   if (has_wide) PS_CUDA(cudaMemcpyAsync(S.W, b.W, sizeof(int64_t) * N * F, cudaMemcpyHostToDevice, cs));
   PS_CUDA(cudaMemcpyAsync(S.X, b.X, sizeof(float) * N * Xn, cudaMemcpyHostToDevice, cs));
@@ -610,6 +616,97 @@ float Model::read_loss() {
   PS_REQUIRE(last_status.emb_err == 0, PS_ERR_CAPACITY, "embedding table is full: raise emb_capacity");
   PS_REQUIRE(last_status.wide_err == 0, PS_ERR_CAPACITY, "wide table is full");
   return last_status.loss;
+}
+
+/* ------------------------------------------------------------------ the reference's own train loop, call by call
+ * DNN.train / WideDeepNN.train run: forward loop -> loss.forward / loss.backward IN JAVA (DNN.java:47-49) -> setDelta on the
+ * last layer -> reverse loop (DNN.java:64-68); Trainer then calls KVStore.update + clear (Trainer.java:93,95).  forward_host is
+ * the forward loop (the batch stays pending: occurrence counts, ReLU masks, activations), backward_update_host takes the delta
+ * Java's loss.backward produced — dLoss/dP, BEFORE the output activation's derivative, exactly what setDelta receives — and runs
+ * the reverse loop and the update.  No label ever crosses the boundary.                                                    */
+void Model::forward_host(const HostBatch& b, float* P_out) {
+  PS_REQUIRE(kind != PS_MODEL_FCNN, PS_ERR_ARG, "forward/backward split: DNN and WideDeepNN only (FullConnectedNN: use train_step)");
+  PS_REQUIRE(in_flight == 0, PS_ERR_STATE, "model: steps in flight; collect first");
+  PS_REQUIRE(b.N > 0 && b.N <= Bmax, PS_ERR_ARG, "model: batch size must be in [1, max_batch]");
+  PS_REQUIRE(b.X && P_out && (!has_emb || b.E) && (!has_wide || b.W), PS_ERR_ARG, "model: missing input matrix");
+  Stage& S = stage[0];
+  cudaStream_t s = ctx->stream, s1 = aux[0], s2 = aux[1];
+  const size_t N = (size_t)b.N;
+  if (has_emb) PS_CUDA(cudaMemcpyAsync(S.E, b.E, sizeof(int64_t) * N * F, cudaMemcpyHostToDevice, s));
+  if (has_wide) PS_CUDA(cudaMemcpyAsync(S.W, b.W, sizeof(int64_t) * N * F, cudaMemcpyHostToDevice, s));
+  PS_CUDA(cudaMemcpyAsync(S.X, b.X, sizeof(float) * N * Xn, cudaMemcpyHostToDevice, s));
+  fork(s, s1);
+  if (has_wide) { StreamScope sc(ctx, s1); wide.forward(S.W, b.N, F, wide_bias, wide_z); }
+  emb.lookup(S.E, nullptr, b.N, act[0], ld[0], S.X, Xn, F * D);
+  forward_layers(b.N, true);
+  run_tail(nullptr, b.N, false);                 /* AddLayer + Sigmoid only: P */
+  if (has_wide) PS_CUDA(cudaMemcpyAsync(P_out, P, sizeof(float) * N, cudaMemcpyDeviceToHost, s));
+  else PS_CUDA(cudaMemcpy2DAsync(P_out, sizeof(float), act[L], sizeof(float) * ld[L], sizeof(float), N, cudaMemcpyDeviceToHost, s));
+  fork(s2, s);
+  PS_CUDA(cudaStreamSynchronize(s));
+  pending_forward_N = b.N;
+  last_N = b.N; last_train = false;
+}
+
+void Model::backward_update_host(const float* delta_top, int N, float loss) {
+  PS_REQUIRE(pending_forward_N > 0 && N == pending_forward_N, PS_ERR_STATE, "backward_update without a matching forward");
+  PS_REQUIRE(delta_top != nullptr, PS_ERR_ARG, "backward_update: null delta");
+  Stage& S = stage[0];
+  cudaStream_t s = ctx->stream, s1 = aux[0], s2 = aux[1];
+  const bool fp32 = ctx->fc_precision == PS_FC_FP32;
+  PS_CUDA(cudaMemcpyAsync(S.Y, delta_top, sizeof(float) * (size_t)N, cudaMemcpyHostToDevice, s));   /* the label buffer doubles as the delta staging */
+  /* last layer's activation.backward (FcLayer.java:100-102 with Sigmoid.java:16-21) + rowMeans for LRLayer; loss as Java computed it */
+  tail_binary_from_delta(ctx, N, has_wide ? P : act[L], has_wide ? 1 : ld[L], S.Y, delta[L], ld[L], fp32 ? nullptr : delta_t[L], loss, st_dev, tail_ws,
+                         has_emb ? emb.counters : nullptr);
+  backward_layers(N, true);
+  fork(s, s1);
+  {
+    StreamScope sc(ctx, s1);
+    const DenseUpdateArgs u = dense_args(N);
+    dense_update(ctx, u, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, S.st_host);
+  }
+  if (has_emb) emb.scatter_update(delta[0], ld[0], nullptr, 0, N, 2, skip_ptr(st_dev), 0, nullptr, true);
+  fork(s1, s);
+  fork(s2, s);
+  PS_CUDA(cudaStreamSynchronize(s));
+  pending_forward_N = 0;
+  last_status = *S.st_host;
+  last_N = N; last_train = true;
+  PS_REQUIRE(last_status.emb_err == 0, PS_ERR_CAPACITY, "embedding table is full: raise emb_capacity");
+  PS_REQUIRE(last_status.wide_err == 0, PS_ERR_CAPACITY, "wide table is full");
+}
+
+/* DataSet.next + Trainer.train in one submission (DataSet.java:77-100, CTR.parseFeature CTR.java:47-68): `len` bytes of libsvm
+ * text holding exactly N complete lines are copied to the device as they are, parsed there (ingest_dev.cu) into the stage's
+ * E / X / W / Y and trained on — copy, parse and step are all asynchronous, collect() returns the loss.  A line the GPU parser
+ * cannot take (a spelling outside its fast path, a short or missing line) drops the WHOLE batch like the reference's swallowed
+ * exception does (DataSet.java:96-98): the step applies nothing and collect() reports it as skipped.                       */
+void Model::submit_text(const char* text, size_t len, int N, int mode) {
+  PS_REQUIRE(in_flight < 2, PS_ERR_STATE, "model: two steps already in flight; collect first");
+  PS_REQUIRE(N > 0 && N <= Bmax && text != nullptr && len > 0, PS_ERR_ARG, "submit_text: bad argument");
+  PS_REQUIRE(has_emb, PS_ERR_ARG, "submit_text: the CTR text layout needs a model with embedding fields");
+  Stage& S = stage[next_stage];
+  if (len > S.text_cap) {
+    PS_CUDA(cudaStreamSynchronize(ctx->stream)); PS_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    dfree(S.text); dfree(S.text_ws);
+    S.text_cap = len + len / 2 + 4096;
+    S.text = dmalloc<char>(S.text_cap);
+    S.text_ws = dmalloc<uint32_t>(S.text_cap / 4096 + 4 + (size_t)Bmax);
+  }
+  if (!S.text_status) { S.text_status = dmalloc<uint8_t>((size_t)Bmax); if (!S.W) S.W = dmalloc<int64_t>((size_t)Bmax * F); }
+  cudaStream_t cs = ctx->copy_stream;
+  PS_CUDA(cudaMemcpyAsync(S.text, text, len, cudaMemcpyHostToDevice, cs));
+  PS_CUDA(cudaEventRecord(S.h2d_done, cs));
+  PS_CUDA(cudaStreamWaitEvent(ctx->stream, S.h2d_done, 0));
+  libsvm_parse_dev_async(ctx, S.text, len, F, Xn, 100000 /* CTR.wideSize, CTR.java:36 */, N, S.E, S.X, S.W, S.Y, S.text_status, S.text_ws,
+                         reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(st_dev) + offsetof(StepStatus, pad)));
+  S.N = N;
+  pad_dirty = true;
+  run_step(S.E, S.X, S.W, S.Y, N, true, S.st_host, mode);
+  PS_CUDA(cudaEventRecord(S.step_done, ctx->stream));
+  S.busy = true;
+  next_stage ^= 1; in_flight++;
+  last_N = N; last_train = true;
 }
 
 void Model::predict(const HostBatch& b, float* out) {

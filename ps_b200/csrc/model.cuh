@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "dense.cuh"
 #include "gemm.cuh"
+#include "ingest.cuh"
 #include "p2p.cuh"
 #include "shard.cuh"
 #include "table.cuh"
@@ -71,6 +72,7 @@ struct Model {
   /* two staging sets so the H2D of step i+1 overlaps the kernels of step i */
   struct Stage {
     int64_t *E = nullptr, *W = nullptr; float *X = nullptr, *Y = nullptr;
+    char* text = nullptr; size_t text_cap = 0; uint32_t* text_ws = nullptr; uint8_t* text_status = nullptr;   /* submit_text: raw libsvm text, parsed on the device */
     StepStatus* st_host = nullptr;       /* mapped pinned */
     cudaEvent_t h2d_done = nullptr, step_done = nullptr;
     int N = 0; bool busy = false;
@@ -102,6 +104,14 @@ struct Model {
    * forward, tail, dgrad chain on the main stream with each wgrad beside it on side stream 1.  On return
    * the main stream holds delta[0]; side stream 1 holds the wgrads; side stream 2 the transposes / wide update. */
   void forward_backward(const int64_t* W, const int64_t* W_all, int n_all, const float* Y, int N, bool train, bool wide_update_now);
+  void forward_layers(int N, bool train);
+  void backward_layers(int N, bool wide_update_now);
+  /* DNN.train call by call: forward loop | (loss in the caller) | reverse loop + KVStore.update (see model.cu) */
+  int pending_forward_N = 0;
+  bool pad_dirty = false;
+  void forward_host(const HostBatch& b, float* P_out);
+  void backward_update_host(const float* delta_top, int N, float loss);
+  void submit_text(const char* text, size_t len, int N, int mode = 0);
   void step_device(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, bool train, StepStatus* publish_to);
   /* the same through the graph cache (falls back to direct launches while profiling) */
   void run_step(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, bool train, StepStatus* publish_to, int mode = 0);

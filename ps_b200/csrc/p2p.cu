@@ -10,40 +10,18 @@ namespace psb {
 
 namespace {
 
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-/* Runs as its own one-warp kernel right after a producer kernel: the kernel boundary has completed every
- * store of the producer (including those that crossed NVLink), so ONE system-scope fence and one release
- * store per peer publish the payload — no per-block fences inside the bandwidth-bound producers.       */
-__global__ void p2p_publish_kernel(P2PState* st, int channel) {
-  const int r = threadIdx.x;
-  if (r >= st->R) return;
-  if (channel == CH_KEYS) {
-    const int c = min(*reinterpret_cast<volatile int32_t*>(&st->cursor[r]), st->cap);
-    reinterpret_cast<volatile int32_t*>(p2p_region(st, r, st->off_counts))[st->me] = c;
-  }
-  __threadfence_system();
-  uint32_t* f = reinterpret_cast<uint32_t*>(p2p_region(st, r, st->off_flags)) + channel * kP2PMaxRanks + st->me;
-  st_release_sys(f, st->seq);
-}
-
 __global__ void p2p_begin_kernel(P2PState* st) {
   if (threadIdx.x == 0) st->seq += 1u;
   if (threadIdx.x < kP2PMaxRanks) st->cursor[threadIdx.x] = 0;
 }
 
 /* PSRouterClient.getList, request side (PSRouterClient.java:60-68): the router sends each key of the batch ONCE to
- * its shard.  Phase 1: every lookup finds-or-inserts its key in the per-batch table, counts itself, and the first
- * occurrence reserves a position in the owner's bucket (one global atomic per (block, owner)).              */
-__global__ void __launch_bounds__(256) p2p_dedup_kernel(P2PState* st, BatchSlot* __restrict__ bt, uint32_t BT, const int64_t* __restrict__ E, int L, int F,
-                                                        int32_t* __restrict__ lk_b) {
+ * its shard.  Every lookup finds-or-inserts its key in the per-batch table and counts itself; the first occurrence
+ * reserves a position in the owner's bucket (one global atomic per (block, owner)) and stores the key straight into
+ * the owner's keys_in[me][pos] over NVLink.  The occurrence count is only complete when the kernel ends: it travels
+ * later, with the gradient push.  The table needs no clearing pass: the push clears exactly the entries it used.   */
+__global__ void __launch_bounds__(256) p2p_route_send_kernel(P2PState* st, BatchSlot* __restrict__ bt, uint32_t BT, const int64_t* __restrict__ E, int L, int F,
+                                                             int32_t* __restrict__ lk_b, int32_t* __restrict__ ulist) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;      /* field-major: a warp works on one field, consecutive samples */
   const int lane = threadIdx.x & 31;
   const int R = st->R, cap = st->cap;
@@ -84,19 +62,13 @@ __global__ void __launch_bounds__(256) p2p_dedup_kernel(P2PState* st, BatchSlot*
   __syncthreads();
   if (first) {
     const int pos = s_base[owner] + rank_in_block;
-    if (pos < cap) bt[b].upos = owner * cap + pos;
-    else { bt[b].upos = -1; st->overflow = 1; }
+    if (pos < cap) {
+      bt[b].upos = owner * cap + pos;
+      ulist[owner * cap + pos] = b;
+      reinterpret_cast<unsigned long long*>(p2p_region(st, owner, st->off_keys))[(size_t)st->me * cap + pos] = key;
+    } else { bt[b].upos = -1; st->overflow = 1; }
   }
-}
-
-/* Phase 2: {key, occurrences} of every unique key goes straight into its owner's keys_in[me][pos] */
-__global__ void __launch_bounds__(256) p2p_send_keys_kernel(P2PState* st, const BatchSlot* __restrict__ bt, uint32_t BT) {
-  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= BT) return;
-  const BatchSlot e = bt[s];
-  if (e.key == PS_KEY_EMPTY || e.upos < 0) return;
-  const int owner = e.upos / st->cap, pos = e.upos - owner * st->cap;
-  reinterpret_cast<ulonglong2*>(p2p_region(st, owner, st->off_keys))[(size_t)st->me * st->cap + pos] = make_ulonglong2(e.key, (unsigned long long)e.cnt);
+  p2p_publish_last(st, CH_KEYS, gridDim.x);
 }
 
 /* all-gather by stores: this rank's `bytes` go to slot `me` of the channel's region on every rank */
@@ -108,59 +80,14 @@ __global__ void __launch_bounds__(256) p2p_bcast_kernel(P2PState* st, const uint
     const size_t c = i - (size_t)r * n16;
     reinterpret_cast<uint4*>(p2p_region(st, r, off))[(size_t)me * n16 + c] = src[c];
   }
-}
-
-/* publish this rank's payload of `channel` and wait for everybody else's, in one launch */
-__global__ void p2p_publish_wait_kernel(P2PState* st, int channel) {
-  const int r = threadIdx.x;
-  if (r < st->R) {
-    if (channel == CH_KEYS) {
-      const int c = min(*reinterpret_cast<volatile int32_t*>(&st->cursor[r]), st->cap);
-      reinterpret_cast<volatile int32_t*>(p2p_region(st, r, st->off_counts))[st->me] = c;
-    }
-    __threadfence_system();
-    const uint32_t seq = st->seq;
-    st_release_sys(reinterpret_cast<uint32_t*>(p2p_region(st, r, st->off_flags)) + channel * kP2PMaxRanks + st->me, seq);
-    const uint32_t* f = reinterpret_cast<const uint32_t*>(p2p_region(st, st->me, st->off_flags)) + channel * kP2PMaxRanks + r;
-    while ((int32_t)(ld_acquire_sys(f) - seq) < 0) __nanosleep(32);
-  }
-  __threadfence_system();
-}
-
-__global__ void p2p_wait_kernel(const P2PState* st, int channel) {
-  const int r = threadIdx.x;
-  if (r < st->R) {
-    const uint32_t* f = reinterpret_cast<const uint32_t*>(p2p_region(st, st->me, st->off_flags)) + channel * kP2PMaxRanks + r;
-    const uint32_t seq = st->seq;
-    while ((int32_t)(ld_acquire_sys(f) - seq) < 0) __nanosleep(64);
-  }
-  __threadfence_system();
-}
-
-/* PServer.getList, response side (PServer.java:102-117): the owner's gather writes each row (ReLU applied,
- * EmbeddingField.java:75) into the REQUESTER's rows_in[me][idx] — gather and transfer are one kernel.   */
-__global__ void __launch_bounds__(256) p2p_gather_send_kernel(P2PState* st, const float* __restrict__ w, int D, const int32_t* __restrict__ lk_slot) {
-  const int cap = st->cap, Dp = st->Dp, me = st->me;
-  const int tpl = Dp >> 2;
-  const long total = (long)st->R * cap * tpl;
-  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g < total) {
-    const int q = (int)(g / tpl), part = (int)(g - (long)q * tpl);
-    const int slot = lk_slot[q];
-    if (slot >= 0) {
-      const int src = q / cap, idx = q - src * cap;
-      float4 v = __ldg(reinterpret_cast<const float4*>(w + (size_t)slot * Dp + part * 4));
-      v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-      float* dst = reinterpret_cast<float*>(p2p_region(st, src, st->off_rows)) + ((size_t)me * cap + idx) * Dp + part * 4;
-      st_f4(dst, v);
-    }
-  }
+  p2p_publish_last(st, channel, gridDim.x);
 }
 
 template <bool VEC>
 __global__ void __launch_bounds__(256) p2p_unpack_kernel(const P2PState* st, const BatchSlot* __restrict__ bt, const int32_t* __restrict__ lk_b, int L, int F, int D,
                                                          float* __restrict__ out, int ldo, const float* __restrict__ X, int Xn, int xoff, int N) {
   const int Dp = st->Dp;
+  p2p_wait_all(st, CH_ROWS);                   /* every owner's gather has landed in rows_in */
   const float* rows = reinterpret_cast<const float*>(p2p_region(st, st->me, st->off_rows));
   long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long emb_work = VEC ? (long)L * (Dp >> 2) : (long)L * Dp;
@@ -249,19 +176,28 @@ __global__ void __launch_bounds__(256) p2p_grad_reduce_kernel(const P2PState* st
   if (lane_on && leader) red_add_f4(gacc + (size_t)upos * Dp + part * 4, gk);
 }
 
-/* Phase 2: one gradient sum per unique key → its owner's grads_in[me][pos]; the local accumulator is zeroed for the next step */
-__global__ void __launch_bounds__(256) p2p_grad_send_kernel(P2PState* st, float* __restrict__ gacc) {
+/* Phase 2: one gradient sum per unique key, with the key's occurrence count in this rank's batch → its owner's
+ * grads_in[me][pos] / gcnt_in[me][pos]; the local accumulator and the per-batch table entry are cleared for the next step */
+__global__ void __launch_bounds__(256) p2p_grad_send_kernel(P2PState* st, float* __restrict__ gacc, BatchSlot* __restrict__ bt, const int32_t* __restrict__ ulist) {
   const int cap = st->cap, Dp = st->Dp, me = st->me, tpl = Dp >> 2;
   const long total = (long)st->R * cap * tpl;
   const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= total) return;
-  const int q = (int)(g / tpl), part = (int)(g - (long)q * tpl);
-  const int owner = q / cap, pos = q - owner * cap;
-  if (pos >= min(*reinterpret_cast<volatile int32_t*>(&st->cursor[owner]), cap)) return;
-  float* a = gacc + (size_t)q * Dp + part * 4;
-  const float4 v = __ldcg(reinterpret_cast<const float4*>(a));
-  st_f4(reinterpret_cast<float*>(p2p_region(st, owner, st->off_grads)) + ((size_t)me * cap + pos) * Dp + part * 4, v);
-  st_f4(a, make_float4(0.f, 0.f, 0.f, 0.f));
+  if (g < total) {
+    const int q = (int)(g / tpl), part = (int)(g - (long)q * tpl);
+    const int owner = q / cap, pos = q - owner * cap;
+    if (pos < min(*reinterpret_cast<volatile int32_t*>(&st->cursor[owner]), cap)) {
+      float* a = gacc + (size_t)q * Dp + part * 4;
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(a));
+      st_f4(reinterpret_cast<float*>(p2p_region(st, owner, st->off_grads)) + ((size_t)me * cap + pos) * Dp + part * 4, v);
+      st_f4(a, make_float4(0.f, 0.f, 0.f, 0.f));
+      if (part == 0) {
+        const int b = ulist[q];
+        reinterpret_cast<uint32_t*>(p2p_region(st, owner, st->off_gcnt))[(size_t)me * cap + pos] = bt[b].cnt;
+        *reinterpret_cast<uint4*>(&bt[b]) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+  }
+  p2p_publish_last(st, CH_GRADS, gridDim.x);
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -274,9 +210,10 @@ void P2P::create(Ctx* c, int R_, int me_, int cap_, int Dp_, int NF_, int glen_,
   size_t off = 0;
   host = P2PState{};
   host.R = R; host.me = me; host.cap = cap; host.Dp = Dp; host.NF = NF; host.glen = glen;
-  host.off_keys = off; off = align_up(off + (size_t)R * cap * 16, 256);
+  host.off_keys = off; off = align_up(off + (size_t)R * cap * 8, 256);
   host.off_rows = off; off = align_up(off + (size_t)R * cap * Dp * 4, 256);
   host.off_grads = off; off = align_up(off + (size_t)R * cap * Dp * 4, 256);
+  host.off_gcnt = off; off = align_up(off + (size_t)R * cap * 4, 256);
   host.off_wide = off; off = align_up(off + (size_t)R * NF * 8, 256);
   host.off_gsum = off; off = align_up(off + (size_t)R * glen * 4, 256);
   host.off_counts = off; off = align_up(off + (size_t)kP2PMaxRanks * 4, 256);
@@ -292,6 +229,7 @@ void P2P::create(Ctx* c, int R_, int me_, int cap_, int Dp_, int NF_, int glen_,
   bt = dmalloc_zero<BatchSlot>(BT, ctx->stream);
   lk_b = dmalloc<int32_t>((size_t)std::max<int64_t>(Lmax, 1));
   gacc = dmalloc_zero<float>((size_t)R * cap * Dp, ctx->stream);
+  ulist = dmalloc_zero<int32_t>((size_t)R * cap, ctx->stream);
   PS_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
@@ -319,26 +257,18 @@ void P2P::connect(const void* all_handles) {
 
 void P2P::destroy() {
   for (int r = 0; r < R; ++r) if (peer_mapped[r]) { cudaIpcCloseMemHandle(peer_mapped[r]); peer_mapped[r] = nullptr; }
-  dfree(slab); dfree(dev); dfree(bt); dfree(lk_b); dfree(gacc);
-  slab = nullptr; dev = nullptr; bt = nullptr; lk_b = nullptr; gacc = nullptr; connected = false;
+  dfree(slab); dfree(dev); dfree(bt); dfree(lk_b); dfree(gacc); dfree(ulist);
+  slab = nullptr; dev = nullptr; bt = nullptr; lk_b = nullptr; gacc = nullptr; ulist = nullptr; connected = false;
 }
 
 #define P2P_LAUNCHED() do { PS_LAUNCH_CHECK(); ctx->launches++; } while (0)
 
-void P2P::publish(int channel) { p2p_publish_kernel<<<1, 32, 0, ctx->stream>>>(dev, channel); P2P_LAUNCHED(); }
-
 void P2P::begin() { p2p_begin_kernel<<<1, 32, 0, ctx->stream>>>(dev); P2P_LAUNCHED(); }
 
-void P2P::dedup_route(const int64_t* E, int N, int F) {
+void P2P::route_send(const int64_t* E, int N, int F) {
   const int L = N * F;
   PS_REQUIRE(L <= Lmax, PS_ERR_ARG, "p2p: batch larger than the de-duplication table");
-  PS_CUDA(cudaMemsetAsync(bt, 0, sizeof(BatchSlot) * BT, ctx->stream));
-  p2p_dedup_kernel<<<ceil_div(L, 256), 256, 0, ctx->stream>>>(dev, bt, BT, E, L, F, lk_b);
-  P2P_LAUNCHED();
-}
-
-void P2P::send_keys() {
-  p2p_send_keys_kernel<<<ceil_div(BT, 256), 256, 0, ctx->stream>>>(dev, bt, BT);
+  p2p_route_send_kernel<<<ceil_div(L, 256), 256, 0, ctx->stream>>>(dev, bt, BT, E, L, F, lk_b, ulist);
   P2P_LAUNCHED();
 }
 
@@ -348,15 +278,6 @@ void P2P::bcast(const void* src, size_t bytes, int channel) {
   const size_t n16 = bytes / 16;
   const int grid = (int)std::min<size_t>((n16 * R + 255) / 256, (size_t)ctx->num_sms * 4);
   p2p_bcast_kernel<<<std::max(grid, 1), 256, 0, ctx->stream>>>(dev, static_cast<const uint4*>(src), n16, channel == CH_WIDE ? host.off_wide : host.off_gsum, channel);
-  P2P_LAUNCHED();
-}
-
-void P2P::publish_wait(int channel) { p2p_publish_wait_kernel<<<1, 32, 0, ctx->stream>>>(dev, channel); P2P_LAUNCHED(); }
-void P2P::wait(int channel) { p2p_wait_kernel<<<1, 32, 0, ctx->stream>>>(dev, channel); P2P_LAUNCHED(); }
-
-void P2P::gather_send(const float* w, int D, const int32_t* lk_slot) {
-  const long total = (long)R * cap * (Dp / 4);
-  p2p_gather_send_kernel<<<ceil_div(total, 256), 256, 0, ctx->stream>>>(dev, w, D, lk_slot);
   P2P_LAUNCHED();
 }
 
@@ -386,7 +307,7 @@ void P2P::grad_reduce(const float* delta, int ldd, const float* act, int lda, in
 
 void P2P::grad_send() {
   const long total = (long)R * cap * (Dp / 4);
-  p2p_grad_send_kernel<<<ceil_div(total, 256), 256, 0, ctx->stream>>>(dev, gacc);
+  p2p_grad_send_kernel<<<ceil_div(total, 256), 256, 0, ctx->stream>>>(dev, gacc, bt, ulist);
   P2P_LAUNCHED();
 }
 

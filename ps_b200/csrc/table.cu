@@ -2,14 +2,15 @@
  * table.cu — kernels of the GPU-resident embedding / wide tables (sm_100a).
  *
  * Path restated (reference, /root/reference/src/main/java/):
- *   probe   = EmbeddingField.checkExists + KVStore.get(key, init)   layer/EmbeddingField.java:49-54, store/KVStore.java:136-159,168-190
- *   gather  = EmbeddingField.forward + EmbeddingLayer.forward       layer/EmbeddingField.java:66-78, layer/EmbeddingLayer.java:25-48
+ *   lookup  = EmbeddingField.checkExists + KVStore.get(key, init)   layer/EmbeddingField.java:49-54, store/KVStore.java:136-159,168-190
+ *           + EmbeddingField.forward + EmbeddingLayer.forward       layer/EmbeddingField.java:66-78, layer/EmbeddingLayer.java:25-48
  *   scatter = EmbeddingField.backward (x2) + KVStore.sum + KVStore.update + Updater.update
  *                                                                   layer/EmbeddingField.java:86-104, store/KVStore.java:192-200,240-268
  *   wide    = LRLayer.forward / backward                            layer/LRLayer.java:62-120
  *
  * All of it is HBM/L2-bound integer and copy work: no tensor cores, 128-bit accesses,
- * one thread group (Dp/4 lanes) per looked-up row.
+ * one thread group (Dp/4 lanes) per looked-up row; rows that several lookups of a warp share are
+ * staged ONCE in shared memory by the TMA engine (cp.async.bulk + mbarrier).
  */
 #include <algorithm>
 #include <cmath>
@@ -20,9 +21,14 @@
 
 namespace psb {
 
-static constexpr int kProbeLimit = 1 << 16;
 
 /* ------------------------------------------------------------------ find / find-or-insert */
+__device__ __forceinline__ ulonglong2 ld_slot(const EmbSlot* p) {   /* {key, cnt | uidx << 32} in one 16 B transaction */
+  ulonglong2 r;
+  asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
+  return r;
+}
+
 __device__ __forceinline__ int emb_find(const EmbSlot* slots, uint32_t C, unsigned long long key) {
   uint32_t slot = ps_bucket_of(key, C);
   const int limit = C < (uint32_t)kProbeLimit ? (int)C : kProbeLimit;
@@ -53,15 +59,18 @@ __device__ __forceinline__ int emb_find_or_insert(EmbSlot* slots, uint32_t C, un
   return -1;
 }
 
-/* find-or-insert that starts from an already loaded first probe (`k0` = the key found in the home bucket) */
-__device__ __forceinline__ int emb_find_or_insert_from(EmbSlot* slots, uint32_t C, unsigned long long key, uint32_t slot, unsigned long long k,
-                                                       bool* inserted) {
+/* find-or-insert that starts from an already loaded home-bucket record.  *ready: the record that matched carried
+ * kRowReady, i.e. the row had been written (and fenced) before this thread saw the key — the row may be loaded.
+ * Otherwise (inserted here, or the key was published by a thread that may still be writing the row) the caller takes
+ * the row from the deterministic initialiser instead of from memory: same bits, no waiting.                       */
+__device__ __forceinline__ int emb_resolve(EmbSlot* slots, uint32_t C, unsigned long long key, uint32_t slot, ulonglong2 rec, bool* inserted,
+                                           bool* ready) {
   const int limit = C < (uint32_t)kProbeLimit ? (int)C : kProbeLimit;
-  *inserted = false;
+  *inserted = false; *ready = false;
   for (int p = 0; p < limit; ++p) {
-    if (p > 0) k = *reinterpret_cast<const volatile unsigned long long*>(&slots[slot].key);
-    if (k == key) return (int)slot;
-    if (k == PS_KEY_EMPTY) {
+    if (p > 0) rec = ld_slot(&slots[slot]);
+    if (rec.x == key) { *ready = ((uint32_t)(rec.y >> 32) & kRowReady) != 0u; return (int)slot; }
+    if (rec.x == PS_KEY_EMPTY) {
       const unsigned long long old = atomicCAS(&slots[slot].key, (unsigned long long)PS_KEY_EMPTY, key);
       if (old == PS_KEY_EMPTY) { *inserted = true; return (int)slot; }
       if (old == key) return (int)slot;
@@ -71,127 +80,263 @@ __device__ __forceinline__ int emb_find_or_insert_from(EmbSlot* slots, uint32_t 
   return -1;
 }
 
-/* Key resolution of one batch.  Row creation follows KVStore.create (KVStore.java:168-190): the creating thread draws the
- * row from the deterministic initialiser of ps_spec.h; optimiser state stays at the zero the arena was allocated with
- * (AdamUpdater.initMandV, :76-84).
- *
- * Work decomposition: a block owns 32*SG consecutive samples and ALL F fields of them; a warp task is (field j, 32
- * consecutive samples), so
- *   - the 32 lanes of a warp probe the SAME field: duplicates of a hot key (a low-cardinality field) meet in one warp
- *     and are counted with one L2 reduction per warp, not 32;
- *   - the 8 warps of a block read neighbouring fields of the same samples at the same time: every 32 B sector of the
- *     [N][F] id matrix is fetched from HBM once;
- *   - lk_slot is FIELD-major ([F][N], index t = j*N + n): a warp stores 128 contiguous bytes, and the backward kernels,
- *     which walk the same order, read it back coalesced.
- * Up to 4 tasks of a warp are in flight at once (ids, then the home buckets, are loaded for all of them before any is used).
- * Per-batch bookkeeping in the slot record needs no returned atomic: `cnt += occurrences` and `first = max(first, ~t)`
- * are fire-and-forget reductions; the lookup with the smallest t owns the key's accumulator row (acc[t]).
- * F == 0: `ids` already holds packed keys (the owner side of the sharded exchange); p2p: they come from this step's mailbox. */
-template <class IdT>
-__global__ void __launch_bounds__(256) emb_probe_kernel(EmbSlot* __restrict__ slots, uint32_t C, float* __restrict__ w, int Dp, int D,
-                                                        const IdT* __restrict__ ids, int N, int F, int SG, uint64_t seed, float maxv,
-                                                        int32_t* __restrict__ lk_slot,
-                                                        uint32_t* __restrict__ counters, const P2PState* __restrict__ p2p) {
-  constexpr int R = 4;
+/* ---- TMA (bulk async copy) + mbarrier wrappers for the hot-row staging ---- */
+__device__ __forceinline__ uint32_t tb_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tb_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tb_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tb_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+/* global -> shared bulk copy executed by the TMA unit; completion is signalled on the mbarrier as transferred bytes */
+__device__ __forceinline__ void tb_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+/* true in exactly one block of the grid: the one whose threads arrive last.  Call from all threads.
+ * system: the grid stored into peer memory — fence those stores for the other GPUs, not just for this one. */
+__device__ __forceinline__ bool last_block_done(uint32_t* ticket, uint32_t nblocks, bool system = false) {
+  __shared__ bool s_last;
+  if (system) __threadfence_system(); else __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t t = atomicAdd(ticket, 1u);
+    s_last = t == nblocks - 1u;
+    if (s_last) *ticket = 0u;
+  }
+  __syncthreads();
+  return s_last;
+}
+
+struct LookupArgs {
+  EmbSlot* slots; uint32_t C;
+  float* rows; int rs, Dp, D;
+  const void* ids; int N, F;             /* F == 0: ids holds packed keys (the owner side of the sharded exchange) */
+  uint64_t seed; float maxv;
+  int32_t* lk_slot; uint32_t* lk_mask; int MW;
+  int32_t* uniq; uint32_t* counters;
+  P2PState* p2p; int send_rows;          /* keys from this step's keys_in mailbox (after waiting for CH_KEYS); rows to the requesters'
+                                            rows_in mailboxes, CH_ROWS published by the last block */
+  float* out; int ldo;
+  const float* X; int Xn, xoff;
+  int task_blocks, hot_tma;
+};
+
+static constexpr int kHotShare = 4;                 /* lookups of one warp task that must share a row before it is staged by TMA */
+static constexpr int kHotRows = 32 / kHotShare;     /* so at most this many staged rows per warp */
+
+__device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int src) {
+  const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src), hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+  return ((unsigned long long)hi << 32) | lo;
+}
+
+/* EmbeddingLayer.forward as ONE kernel.  A warp task is (field j, 32 consecutive samples); every warp runs exactly one
+ * task, a block runs 8 consecutive tasks = neighbouring fields of the same samples (the 32 B sectors of the [N][F] id
+ * matrix are shared inside the block).  Per task:
+ *   1. resolve   lane <-> sample: find-or-insert the key (row creation follows KVStore.create, KVStore.java:168-190: the
+ *                creating thread draws the row from the deterministic initialiser of ps_spec.h, optimiser state stays
+ *                at the arena's zero, AdamUpdater.java:76-84); lk_slot[j][n] = slot.
+ *   2. count     duplicates of a key inside the warp (a low-cardinality field) elect one lane, which adds the group's
+ *                occurrences to the slot's batch counter with ONE returning atomic; the group that finds the counter
+ *                at zero owns the key for this batch: it appends the slot to the batch's unique list (one cursor
+ *                atomic per warp) and leaves 1 + that index in the slot record — the accumulator row of the backward.
+ *   3. gather    (overlaps the atomics of 2) TPL lanes per row move relu(row) as 128-bit chunks to
+ *                out[n][j*D ..] (EmbeddingField.java:73-76, EmbeddingLayer.java:36-46) and record the mask bits.
+ *                Rows wanted by >= kHotShare lookups of the task are fetched ONCE into shared memory by the TMA unit
+ *                (cp.async.bulk, mbarrier completion) and read from there; the others stream straight from L2/HBM.
+ * The block that finishes last publishes the number of unique keys (StepStatus.n_unique, the update kernel's bound). */
+template <class IdT, bool GATHER, int TPL, bool ALIGNED>
+__global__ void __launch_bounds__(256) emb_lookup_kernel(const __grid_constant__ LookupArgs a) {
+  extern __shared__ __align__(128) unsigned char lookup_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  pdl_launch_dependents();                     /* the gather's blocks may be scheduled; they wait for this grid before reading */
-  const int Fe = F > 0 ? F : 1;
-  const int tasks = Fe * SG;
-  const long n0 = (long)blockIdx.x * (32 * SG);
-  for (int task0 = warp; task0 < tasks; task0 += 8 * R) {
-    unsigned long long key[R], k0[R];
-    uint32_t bucket[R], add[R];
-    long t[R];
+  pdl_launch_dependents();
+  if ((int)blockIdx.x >= a.task_blocks) {          /* ConcatLayer.forward (ConcatLayer.java:30-37): numeric features next to the embeddings */
+    const long base = (long)((int)blockIdx.x - a.task_blocks) * 1024 + threadIdx.x;
+    const long total = (long)a.N * a.Xn;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int task = task0 + 8 * r;
-      key[r] = PS_KEY_EMPTY; add[r] = 1u; t[r] = -1;
-      if (task < tasks) {
-        const int j = task % Fe, sg = task / Fe;
-        const long n = n0 + sg * 32 + lane;
-        if (n < N) {
-          t[r] = (long)j * N + n;
-          if (p2p != nullptr) {                  /* owner side of the peer-memory exchange: this step's keys_in mailbox */
-            const int src = (int)(n / p2p->cap), idx = (int)(n - (long)src * p2p->cap);
-            if (idx < reinterpret_cast<const int32_t*>(p2p_region(p2p, p2p->me, p2p->off_counts))[src]) {
-              /* entries are {key, occurrences at the sender}: senders de-duplicate their batch (PSRouterClient sends a key once) */
-              const ulonglong2 e = reinterpret_cast<const ulonglong2*>(p2p_region(p2p, p2p->me, p2p->off_keys))[n];
-              key[r] = e.x;
-              add[r] = (uint32_t)e.y + (1u << 24);   /* low 24 bits: occurrences; high 8 bits: entries */
+    for (int k = 0; k < 4; ++k) {
+      const long i = base + k * 256;
+      if (i < total) { const int n = (int)(i / a.Xn), x = (int)(i - (long)n * a.Xn); a.out[(size_t)n * a.ldo + a.xoff + x] = a.X[i]; }
+    }
+    return;
+  }
+  if (a.p2p != nullptr) p2p_wait_all(a.p2p, CH_KEYS);     /* every requester's keys (and their count) have landed in keys_in */
+  const IdT* __restrict__ ids = static_cast<const IdT*>(a.ids);
+  const int Fe = a.F > 0 ? a.F : 1;
+  const long ntasks = (long)((a.N + 31) / 32) * Fe;
+  const long task = (long)blockIdx.x * 8 + warp;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(lookup_smem);
+  float* stage_all = reinterpret_cast<float*>(lookup_smem + 128);
+  if (GATHER && a.hot_tma) {
+    if (lane == 0) tb_mbar_init(tb_smem_u32(&mbar[warp]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+  }
+  if (task < ntasks) {
+    const int sg = (int)(task / Fe), j = (int)(task - (long)sg * Fe);
+    const long nbase = (long)sg * 32;
+    const long n = nbase + lane;
+    const bool in = n < a.N;
+    unsigned long long key = PS_KEY_EMPTY;
+    if (in) {
+      if (a.p2p != nullptr) {                      /* owner side of the peer-memory exchange: this step's keys_in mailbox */
+        const int src = (int)(n / a.p2p->cap), idx = (int)(n - (long)src * a.p2p->cap);
+        /* senders de-duplicate their batch (PSRouterClient sends a key once): an entry is one (requester, key) pair */
+        if (idx < reinterpret_cast<const int32_t*>(p2p_region(a.p2p, a.p2p->me, a.p2p->off_counts))[src])
+          key = reinterpret_cast<const unsigned long long*>(p2p_region(a.p2p, a.p2p->me, a.p2p->off_keys))[n];
+      } else if (a.F > 0) {
+        key = ps_pack_key((uint32_t)j, (uint64_t)(int64_t)ids[n * a.F + j]);
+      } else {
+        key = (unsigned long long)ids[n];          /* EMPTY marks padding in the fixed-capacity sharded exchange */
+      }
+    }
+    /* ---- 1. resolve ---- */
+    int slot = -1;
+    bool ready = false;
+    if (key != PS_KEY_EMPTY) {
+      const uint32_t bucket = ps_bucket_of(key, a.C);
+      const ulonglong2 rec = ld_slot(&a.slots[bucket]);
+      bool inserted;
+      slot = emb_resolve(a.slots, a.C, key, bucket, rec, &inserted, &ready);
+      if (slot < 0) a.counters[CNT_ERR] = 1u;       /* table full: the tail turns this into the step's skip flag — nothing is updated */
+      else if (inserted) {
+        float* row = a.rows + (size_t)slot * a.rs;
+        for (int d = 0; d < a.D; ++d) row[d] = ps_init_value(a.seed, key, (uint32_t)d, a.maxv);
+        __threadfence();                            /* the row is visible before anybody can see kRowReady */
+        atomicOr(&a.slots[slot].uidx, kRowReady);
+        atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + CNT_ROWS), 1ull);
+      }
+    }
+    const long t = (long)j * a.N + n;
+    if (in) a.lk_slot[t] = slot;
+    /* ---- 2. count (the atomic's result is consumed after the gather) ---- */
+    const unsigned peers = __match_any_sync(0xffffffffu, slot >= 0 ? slot : (-1 - lane));
+    const int leader = __ffs(peers) - 1;
+    /* every lookup counts 1 (owner side of the exchange: every requester's entry; the occurrence counts arrive with the push) */
+    const uint32_t total_add = (uint32_t)__popc(peers);
+    uint32_t old = 1u;
+    if (slot >= 0 && leader == lane) old = atomicAdd(&a.slots[slot].cnt, total_add);
+
+    /* ---- 3. gather ---- */
+    if (GATHER) {
+      constexpr int GPW = 32 / TPL;                 /* rows per pass */
+      constexpr int NP = TPL;                       /* passes over the task's 32 rows */
+      constexpr int UNR = NP < 8 ? NP : 8;          /* passes whose loads are in flight together */
+      constexpr int MSH = TPL < 8 ? TPL : 8;        /* lanes whose mask nibbles share one 32-bit word */
+      const int part = lane % TPL, grp = lane / TPL;
+      const bool lane_on = part * 4 < a.Dp;
+      const bool any_nr = __any_sync(0xffffffffu, slot >= 0 && !ready);
+      int hidx = -1;
+      unsigned hmask = 0u;
+      float* stage = stage_all + (size_t)warp * kHotRows * a.Dp;
+      if (a.hot_tma) {
+        const bool hot = slot >= 0 && ready && __popc(peers) >= kHotShare;
+        hmask = __ballot_sync(0xffffffffu, hot && leader == lane);
+        if (hmask != 0u) {                          /* warp-uniform */
+          const uint32_t bar = tb_smem_u32(&mbar[warp]);
+          if (lane == 0) tb_mbar_expect_tx(bar, (uint32_t)__popc(hmask) * (uint32_t)a.Dp * 4u);
+          __syncwarp();
+          if (hot) hidx = __popc(hmask & ((1u << leader) - 1u));
+          if (hot && leader == lane) tb_bulk_g2s(tb_smem_u32(stage + (size_t)hidx * a.Dp), a.rows + (size_t)slot * a.rs, (uint32_t)a.Dp * 4u, bar);
+        }
+      }
+      const int flags = (ready ? 1 : 0) | ((hidx + 1) << 1);
+      bool waited = false;
+#pragma unroll 1
+      for (int p0 = 0; p0 < NP; p0 += UNR) {
+        float4 v[UNR];
+        int rs_[UNR], rf_[UNR];
+#pragma unroll
+        for (int q = 0; q < UNR; ++q) {
+          const int r = (p0 + q) * GPW + grp;
+          rs_[q] = __shfl_sync(0xffffffffu, slot, r);
+          rf_[q] = __shfl_sync(0xffffffffu, flags, r);
+          v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rs_[q] >= 0 && lane_on && (rf_[q] & 1) && (rf_[q] >> 1) == 0) v[q] = ld_f4(a.rows + (size_t)rs_[q] * a.rs + part * 4);
+        }
+        if (hmask != 0u) {                          /* rows several lookups share: from the TMA-staged copy */
+          if (!waited) { tb_mbar_wait(tb_smem_u32(&mbar[warp]), 0u); waited = true; }
+#pragma unroll
+          for (int q = 0; q < UNR; ++q)
+            if (rs_[q] >= 0 && lane_on && (rf_[q] >> 1) != 0) v[q] = *reinterpret_cast<const float4*>(stage + (size_t)((rf_[q] >> 1) - 1) * a.Dp + part * 4);
+        }
+        if (any_nr) {                               /* rows created by this very kernel: the initialiser's bits, not memory */
+#pragma unroll
+          for (int q = 0; q < UNR; ++q) {
+            const int r = (p0 + q) * GPW + grp;
+            const unsigned long long kr = shfl_u64(key, r);
+            if (rs_[q] >= 0 && lane_on && !(rf_[q] & 1)) {
+              const int d0 = part * 4;
+              v[q].x = d0 + 0 < a.D ? ps_init_value(a.seed, kr, (uint32_t)(d0 + 0), a.maxv) : 0.f;
+              v[q].y = d0 + 1 < a.D ? ps_init_value(a.seed, kr, (uint32_t)(d0 + 1), a.maxv) : 0.f;
+              v[q].z = d0 + 2 < a.D ? ps_init_value(a.seed, kr, (uint32_t)(d0 + 2), a.maxv) : 0.f;
+              v[q].w = d0 + 3 < a.D ? ps_init_value(a.seed, kr, (uint32_t)(d0 + 3), a.maxv) : 0.f;
             }
-          } else if (F > 0) {
-            key[r] = ps_pack_key((uint32_t)j, (uint64_t)(int64_t)ids[n * F + j]);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < UNR; ++q) {
+          const int r = (p0 + q) * GPW + grp;
+          const long nr = nbase + r;
+          /* EmbeddingField.java:75: relu in place; the mask bit is what Relu.backward will ask for (Relu.java:14-19) */
+          uint32_t m = (v[q].x > 0.f ? 1u : 0u) | (v[q].y > 0.f ? 2u : 0u) | (v[q].z > 0.f ? 4u : 0u) | (v[q].w > 0.f ? 8u : 0u);
+          v[q].x = fmaxf(v[q].x, 0.f); v[q].y = fmaxf(v[q].y, 0.f); v[q].z = fmaxf(v[q].z, 0.f); v[q].w = fmaxf(v[q].w, 0.f);
+          if (a.lk_mask != nullptr) {
+            m <<= (part & 7) * 4;
+#pragma unroll
+            for (int o = 1; o < MSH; o <<= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
+            if (nr < a.N && (part & 7) == 0 && lane_on) a.lk_mask[((size_t)j * a.N + nr) * a.MW + (part >> 3)] = m;
+          }
+          if (nr >= a.N || !lane_on) continue;
+          float* o;
+          if (a.F > 0) o = a.out + (size_t)nr * a.ldo + j * a.D + part * 4;
+          else if (a.send_rows) {                   /* PServer.getList response: straight into the requester's rows_in[me][idx] */
+            if (rs_[q] < 0) continue;
+            const int src = (int)(nr / a.p2p->cap), idx = (int)(nr - (long)src * a.p2p->cap);
+            o = reinterpret_cast<float*>(p2p_region(a.p2p, src, a.p2p->off_rows)) + ((size_t)a.p2p->me * a.p2p->cap + idx) * a.Dp + part * 4;
+          } else o = a.out + (size_t)nr * a.ldo + part * 4;
+          if (ALIGNED || a.F == 0) {
+            st_f4(o, v[q]);
           } else {
-            key[r] = (unsigned long long)ids[n];
+            const float e[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if (part * 4 + i < a.D) o[i] = e[i];
           }
         }
       }
     }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      bucket[r] = 0u; k0[r] = PS_KEY_EMPTY;
-      if (key[r] != PS_KEY_EMPTY) {              /* EMPTY marks padding in the fixed-capacity sharded exchange */
-        bucket[r] = ps_bucket_of(key[r], C);
-        k0[r] = *reinterpret_cast<const volatile unsigned long long*>(&slots[bucket[r]].key);
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      if (task0 + 8 * r >= tasks) break;         /* warp-uniform */
-      int slot = -1;
-      if (key[r] != PS_KEY_EMPTY) {
-        bool inserted;
-        slot = emb_find_or_insert_from(slots, C, key[r], bucket[r], k0[r], &inserted);
-        if (slot < 0) counters[1] = 1u;
-        else if (inserted) {
-          float* row = w + (size_t)slot * Dp;
-          for (int d = 0; d < D; ++d) row[d] = ps_init_value(seed, key[r], (uint32_t)d, maxv);
-          atomicAdd(reinterpret_cast<unsigned long long*>(counters + 2), 1ull);
-        }
-      }
-      if (t[r] >= 0) lk_slot[t[r]] = slot;
-      /* warp-aggregated bookkeeping: lanes holding the same slot reduce once (the lowest lane has the smallest t) */
-      const unsigned peers = __match_any_sync(0xffffffffu, slot >= 0 ? slot : (-1 - lane));
-      /* every lookup counts 1 unless it is a pre-counted entry of the peer-memory exchange (a reduction over a partial
-       * mask runs once per distinct key in the warp: not worth it for a popcount) */
-      const uint32_t total_add = p2p == nullptr ? (uint32_t)__popc(peers) : __reduce_add_sync(peers, add[r]);
-      if (slot >= 0 && (__ffs(peers) - 1) == lane) {
-        red_add_u32(&slots[slot].cnt, total_add);
-        red_max_u32(&slots[slot].first, ~(uint32_t)t[r]);
+    /* ---- 2b. the group that found the batch counter at zero owns the key: claim its place in the unique list ---- */
+    const bool is_owner = slot >= 0 && leader == lane && old == 0u;
+    const unsigned omask = __ballot_sync(0xffffffffu, is_owner);
+    if (omask != 0u) {
+      const int first = __ffs(omask) - 1;
+      uint32_t base = 0u;
+      if (lane == first) base = atomicAdd(&a.counters[CNT_CURSOR], (uint32_t)__popc(omask));
+      base = __shfl_sync(0xffffffffu, base, first);
+      if (is_owner) {
+        const uint32_t u = base + (uint32_t)__popc(omask & ((1u << lane) - 1u));
+        a.uniq[u] = slot;
+        atomicOr(&a.slots[slot].uidx, u + 1u);
       }
     }
   }
-}
-
-/* TPL lanes per lookup, each moving one 16 B chunk of the row: consecutive lanes write
- * consecutive addresses of the (F*D) x N output (fields of one sample are adjacent), so the
- * stores of a warp coalesce into full 128 B lines; ReLU (EmbeddingField.java:75) is fused.     */
-template <int TPL, bool ALIGNED>
-__global__ void __launch_bounds__(256) emb_gather_kernel(const float* __restrict__ w, int Dp, int D, const int32_t* __restrict__ lk_slot,
-                                                         int L, int F, float* __restrict__ out, int ldo, const float* __restrict__ X, int Xn,
-                                                         int xoff, int N) {
-  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  pdl_launch_dependents();                     /* fc0's forward GEMM may set itself up (it waits for this grid before reading) */
-  pdl_wait();                                  /* launched as a programmatic dependent of the probe */
-  if (g >= (long)L * TPL) {                    /* ConcatLayer.forward (ConcatLayer.java:30-37): numeric features next to the embeddings */
-    const long i = g - (long)L * TPL;
-    if (X != nullptr && i < (long)N * Xn) { const int n = (int)(i / Xn), x = (int)(i - (long)n * Xn); out[(size_t)n * ldo + xoff + x] = X[i]; }
-    return;
-  }
-  const int l = (int)(g / TPL), part = (int)(g % TPL);
-  if (part * 4 >= D) return;
-  const int n = l / F, j = l - n * F;
-  const int slot = lk_slot[(size_t)j * N + n];   /* field-major (see emb_probe_kernel) */
-  if (slot < 0) return;
-  float4 v = __ldg(reinterpret_cast<const float4*>(w + (size_t)slot * Dp + part * 4));
-  v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-  float* o = out + (size_t)n * ldo + j * D + part * 4;
-  if (ALIGNED) {
-    st_f4(o, v);
-  } else {
-    const float e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) if (part * 4 + i < D) o[i] = e[i];
+  if (last_block_done(&a.counters[CNT_TICKET_FWD], (uint32_t)a.task_blocks, a.send_rows != 0)) {
+    if (threadIdx.x == 0) a.counters[CNT_UNIQUE] = *reinterpret_cast<volatile uint32_t*>(&a.counters[CNT_CURSOR]);
+    if (a.send_rows && (int)threadIdx.x < a.p2p->R) {         /* PServer.getList answered: flag every requester */
+      __threadfence_system();
+      p2p_st_release_sys(reinterpret_cast<uint32_t*>(p2p_region(a.p2p, threadIdx.x, a.p2p->off_flags)) + CH_ROWS * kP2PMaxRanks + a.p2p->me, a.p2p->seq);
+    }
   }
 }
 
@@ -226,28 +371,28 @@ __device__ __forceinline__ float emb_geff(float S, const GeffScale& g) {
 }
 
 /* Sparse backward = two launches on one stream, the second a programmatic dependent of the first:
- *   emb_scatter_kernel  g_k = delta[:,k] * (A[:,k] > 0)  (EmbeddingField.java:91-93).  A block owns SB consecutive samples
+ *   emb_scatter_kernel  g_k = delta[:,k] * (A[:,k] > 0)  (EmbeddingField.java:91-93; the mask comes from the bits the lookup
+ *            recorded, so the activations are not read again).  A block owns SB consecutive samples
  *            and all F fields of them; a warp task is (field j, 32/TPL consecutive samples), so duplicates of a key meet
- *            in the same warp and block, and the 8 warps read neighbouring columns of the same delta / act rows at the
+ *            in the same warp and block, and the 8 warps read neighbouring columns of the same delta rows at the
  *            same time (whole DRAM pages).  Three levels of pre-summation keep a hot key (a low-cardinality field:
  *            thousands of occurrences of one row) from serialising in L2:  (1) reduce-by-key tree over the lanes of a
  *            warp that __match_any_sync groups;  (2) keys frequent enough to recur inside one block's samples (the
- *            probe left the batch count in the slot record; threshold = max(PS_HOT_MIN, 2N/SB)) are summed in a
+ *            lookup left the batch count in the slot record; threshold = max(PS_HOT_MIN, 2N/SB)) are summed in a
  *            per-block shared-memory table and leave the block ONCE;  (3) everything else goes out as one
- *            red.global.add.v4.f32 per key and 16 B chunk into the key's accumulator row (L2-resident, indexed by the
- *            work index of the key's first lookup).
- *   emb_update_kernel   a warp scans 32 work indices, ballots the ones that own an accumulator row (the key's first
- *            lookup) and deals their 16 B chunks over ALL its lanes: read S back from L2, form g_eff, run the Adam /
- *            Ftrl / SGD step on w, s1, s2 in place and reset the per-batch state (acc, cnt, first) — KVStore.sum +
- *            update + clear (KVStore.java:192-200,240-277).  Launched with programmatic stream serialisation: its
- *            scan and the w/s1/s2 loads of its first round run while the scatter kernel drains; only the accumulator
- *            read sits behind griddepcontrol.wait.                                                                  */
+ *            red.global.add.v4.f32 per key and 16 B chunk into the key's accumulator row acc[uidx] (compact, L2-resident).
+ *   emb_update_kernel   walks the batch's unique list: 32/(Dp/4) keys per warp, one 16 B chunk per lane: read S back from
+ *            L2, form g_eff, run the Adam / Ftrl / SGD step on the key's {w | s1 | s2} record in place and reset the
+ *            per-batch state (acc, cnt, uidx) — KVStore.sum + update + clear (KVStore.java:192-200,240-277).  Launched
+ *            with programmatic stream serialisation: the list, the counts and the records of its first round are
+ *            requested while the scatter kernel drains; only the accumulator read sits behind griddepcontrol.wait. */
 static constexpr int kHotMin = 8;        /* default occurrences in the batch from which a key is pre-summed per block (PS_HOT_MIN) */
 static constexpr int kHotBits = 6;
 static constexpr int kHotEntries = 1 << kHotBits;   /* per-block hot-key table (open addressing, 4 probes) */
 
 template <int TPL, int CPL, int PASSES, bool ALIGNED>
-__global__ void __launch_bounds__(256) emb_scatter_kernel(const EmbSlot* __restrict__ slots, int Dp, int D, const int32_t* __restrict__ lk_slot, int N,
+__global__ void __launch_bounds__(256) emb_scatter_kernel(const EmbSlot* __restrict__ slots, int Dp, int D, const int32_t* __restrict__ lk_slot,
+                                                          const uint32_t* __restrict__ lk_mask, int MW, int N,
                                                           int F, int SB, const float* __restrict__ delta, int ldd, const float* __restrict__ act, int lda,
                                                           float* __restrict__ acc, const int* __restrict__ skip_flag,
                                                           const P2PState* __restrict__ p2p, uint32_t hot_min) {
@@ -256,7 +401,7 @@ __global__ void __launch_bounds__(256) emb_scatter_kernel(const EmbSlot* __restr
   __shared__ float hot_acc[kHotEntries][ROWF];
   __shared__ int hot_slot[kHotEntries];
   __shared__ uint32_t hot_row[kHotEntries];
-  pdl_launch_dependents();                       /* the update kernel may start its scan now (it waits before reading acc) */
+  pdl_launch_dependents();                       /* the update kernel may start its prefetch now (it waits before reading acc) */
   if (skip_flag != nullptr && *skip_flag != 0) return;   /* DNN.java:58-63 early exit: nothing is pushed */
   if (p2p != nullptr) delta = reinterpret_cast<const float*>(p2p_region(p2p, p2p->me, p2p->off_grads));   /* this step's grads_in mailbox */
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -273,7 +418,7 @@ __global__ void __launch_bounds__(256) emb_scatter_kernel(const EmbSlot* __restr
   __syncthreads();
 
   /* the block's tile: SB consecutive samples x all F fields; a warp task = (field j, GPW consecutive samples); the 8 warps
-   * work on neighbouring fields of the same samples at the same time, so the rows of delta / act are read as whole
+   * work on neighbouring fields of the same samples at the same time, so the rows of delta are read as whole
    * DRAM pages although every lookup only needs D of their columns */
   const int tasks = F * (SB / GPW);
   /* persistent blocks (one wave of them, see launch_scatter) stride over the tiles: no tail wave, and the hot table keeps
@@ -283,34 +428,38 @@ __global__ void __launch_bounds__(256) emb_scatter_kernel(const EmbSlot* __restr
     /* ---- every load of PASSES tasks is issued before anything is consumed ---- */
     int slot[PASSES];
     float4 gk[PASSES][CPL];
+    uint32_t mw[PASSES];
 #pragma unroll
     for (int p = 0; p < PASSES; ++p) {
       const int task = task0 + 8 * p;
-      slot[p] = -1;
+      slot[p] = -1; mw[p] = 0xFFFFFFFFu;
 #pragma unroll
       for (int c = 0; c < CPL; ++c) gk[p][c] = make_float4(0.f, 0.f, 0.f, 0.f);
       const int j = task % F;
       const long n = n0 + (long)(task / F) * GPW + grp;
       if (task < tasks && n < N) {
         slot[p] = lk_slot[(long)j * N + n];
+        if (lk_mask != nullptr && c0 < D) mw[p] = lk_mask[((size_t)j * N + n) * MW + (c0 >> 5)] >> (c0 & 31);   /* this lane's 4*CPL bits */
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
           const int cc = c0 + 4 * c;
           if (cc < D) {
             const size_t od = (size_t)n * ldd + j * D + cc, oa = (size_t)n * lda + j * D + cc;
-            float dv[4] = {0.f, 0.f, 0.f, 0.f}, av[4] = {0.f, 0.f, 0.f, 0.f};
+            float dv[4] = {0.f, 0.f, 0.f, 0.f}, av[4] = {1.f, 1.f, 1.f, 1.f};
             if (ALIGNED) {
               const float4 d4 = ld_f4(delta + od);
-              const float4 a4 = act ? ld_f4(act + oa) : make_float4(1.f, 1.f, 1.f, 1.f);   /* act == null: the mask was applied by the sender */
               dv[0] = d4.x; dv[1] = d4.y; dv[2] = d4.z; dv[3] = d4.w;
-              av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
+              if (act != nullptr) { const float4 a4 = ld_f4(act + oa); av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w; }
             } else {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) if (cc + i < D) { dv[i] = delta[od + i]; av[i] = act ? act[oa + i] : 1.f; }
+              for (int i = 0; i < 4; ++i) if (cc + i < D) { dv[i] = delta[od + i]; if (act != nullptr) av[i] = act[oa + i]; }
             }
-            /* Relu.backward: dy *= (y > 0 ? 1 : 0)  (activations/Relu.java:14-19) */
-            gk[p][c].x = __fmul_rn(dv[0], av[0] > 0.f ? 1.f : 0.f); gk[p][c].y = __fmul_rn(dv[1], av[1] > 0.f ? 1.f : 0.f);
-            gk[p][c].z = __fmul_rn(dv[2], av[2] > 0.f ? 1.f : 0.f); gk[p][c].w = __fmul_rn(dv[3], av[3] > 0.f ? 1.f : 0.f);
+            gk[p][c] = make_float4(dv[0], dv[1], dv[2], dv[3]);
+            if (act != nullptr) {
+              /* Relu.backward: dy *= (y > 0 ? 1 : 0)  (activations/Relu.java:14-19) */
+              gk[p][c].x = __fmul_rn(dv[0], av[0] > 0.f ? 1.f : 0.f); gk[p][c].y = __fmul_rn(dv[1], av[1] > 0.f ? 1.f : 0.f);
+              gk[p][c].z = __fmul_rn(dv[2], av[2] > 0.f ? 1.f : 0.f); gk[p][c].w = __fmul_rn(dv[3], av[3] > 0.f ? 1.f : 0.f);
+            }
           }
         }
       }
@@ -319,7 +468,15 @@ __global__ void __launch_bounds__(256) emb_scatter_kernel(const EmbSlot* __restr
 #pragma unroll
     for (int p = 0; p < PASSES; ++p) {
       cnt[p] = 0u; row[p] = 0u;
-      if (slot[p] >= 0) { const uint4 m = *reinterpret_cast<const uint4*>(&slots[slot[p]]); cnt[p] = m.z; row[p] = ~m.w; }   /* acc row = the key's first lookup */
+      if (slot[p] >= 0) { const uint4 m = *reinterpret_cast<const uint4*>(&slots[slot[p]]); cnt[p] = m.z; row[p] = (m.w & ~kRowReady) - 1u; }   /* the key's accumulator row */
+      if (lk_mask != nullptr) {                    /* the same multiplication by 0 / 1, the factor taken from the recorded mask bits */
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+          const uint32_t b = mw[p] >> (4 * c);
+          gk[p][c].x = __fmul_rn(gk[p][c].x, (b & 1u) ? 1.f : 0.f); gk[p][c].y = __fmul_rn(gk[p][c].y, (b & 2u) ? 1.f : 0.f);
+          gk[p][c].z = __fmul_rn(gk[p][c].z, (b & 4u) ? 1.f : 0.f); gk[p][c].w = __fmul_rn(gk[p][c].w, (b & 8u) ? 1.f : 0.f);
+        }
+      }
     }
 #pragma unroll
     for (int p = 0; p < PASSES; ++p) {
@@ -377,128 +534,146 @@ __global__ void __launch_bounds__(256) emb_scatter_kernel(const EmbSlot* __restr
   }
 }
 
-/* TPK lanes per key (4 floats each).  A WARP scans 32 consecutive work indices, ballots the ones that own an accumulator
- * row and deals the owners' (key, 16 B chunk) items round-robin over its 32 lanes, IPL items per lane and round with every
- * load of a round issued before any is consumed; no block-level synchronisation.  EXACT: see updaters.cuh.              */
-template <int TPK, bool EXACT>
-__global__ void __launch_bounds__(256, 3) emb_update_kernel(EmbSlot* __restrict__ slots, float* __restrict__ w, float* __restrict__ s1, float* __restrict__ s2,
-                                                         int Dp, int D, const int32_t* __restrict__ lk_slot, long L, float* __restrict__ acc,
-                                                         UpdaterDev upd, int calls, const int* __restrict__ skip_flag, int packed_cnt,
-                                                         uint32_t* __restrict__ counters) {
-  constexpr int IPL = TPK < 2 ? 1 : 2;             /* items per lane and round */
+/* KVStore.update + clear for the batch's unique keys.  A warp takes KPW = 32 / (Dp/4) consecutive entries of the unique
+ * list per round, lane = (key, 16 B chunk); the chunk-0 lane of a key reads its batch count once and resets the slot's
+ * per-batch fields when the key is done.  EXACT: see updaters.cuh.                                                   */
+template <bool EXACT>
+__global__ void __launch_bounds__(256) emb_update_kernel(EmbSlot* __restrict__ slots, float* __restrict__ rows, int rs, int Dp, int D,
+                                                         const int32_t* __restrict__ uniq, float* __restrict__ acc, UpdaterDev upd, int calls,
+                                                         const int* __restrict__ skip_flag, uint32_t* __restrict__ ucnt, uint32_t* __restrict__ counters) {
   const int lane = threadIdx.x & 31;
-  const long lk = (long)blockIdx.x * 256 + threadIdx.x;
-  int slot = -1; uint32_t cnt = 0u, first = 0u;
-  if (lk < L) {
-    slot = lk_slot[lk];
-    if (slot >= 0) { const uint4 m = *reinterpret_cast<const uint4*>(&slots[slot]); cnt = m.z; first = m.w; }
-  }
-  const bool owner = slot >= 0 && first == ~(uint32_t)lk;          /* the key's first lookup of the batch */
-  const unsigned owners = __ballot_sync(0xffffffffu, owner);
-  const int items = __popc(owners) * TPK;
-  if (lane == 0 && owners != 0u) red_add_u32(&counters[0], (uint32_t)__popc(owners));   /* statistics (StepStatus.n_unique), monotonic */
-  const bool skip = skip_flag != nullptr && *skip_flag != 0;
+  const int CH = Dp >> 2;
+  const int KPW = 32 / CH;
+  const int kl = lane / CH, ch = lane - kl * CH, cc = ch * 4;
+  const bool lane_on = kl < KPW;
+  const uint32_t U = counters[CNT_UNIQUE];                   /* final since the lookup kernel */
+  const bool skip = skip_flag != nullptr && *skip_flag != 0; /* written by the tail kernel, long before the scatter */
+  const long wstride = (long)gridDim.x * 8;
+  long wi = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
 
-  int kslot[IPL]; uint32_t kcnt[IPL]; long krow[IPL]; bool act[IPL];
-  float4 wv[IPL], m1[IPL], m2[IPL];
-  auto load_round = [&](int base) {
-#pragma unroll
-    for (int q = 0; q < IPL; ++q) {
-      const int i = base + q * 32 + lane;
-      const bool in = i < items;
-      const int src = in ? (int)__fns(owners, 0u, i / TPK + 1) : 0;   /* lane of the (i / TPK)-th owner */
-      kslot[q] = __shfl_sync(0xffffffffu, slot, src);
-      kcnt[q] = __shfl_sync(0xffffffffu, cnt, src);
-      krow[q] = (long)(lk - lane + src);                              /* the owner's work index = its accumulator row */
-      const int cc = (i % TPK) * 4;
-      act[q] = in && cc < D;
-      wv[q] = m1[q] = m2[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (act[q] && !skip) {
-        const size_t o = (size_t)kslot[q] * Dp + cc;
-        wv[q] = ld_f4(w + o);
-        if (upd.kind != PS_UPD_SIMPLE) { m1[q] = ld_f4(s1 + o); m2[q] = ld_f4(s2 + o); }
+  int slot = -1; uint32_t cnt = 0u;
+  float4 wv, m1, m2;
+  auto prefetch = [&](long w) {
+    const long u = w * KPW + kl;
+    slot = -1; cnt = 0u;
+    wv = m1 = m2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane_on && u < (long)U) {
+      slot = uniq[u];
+      if (ch == 0) cnt = *reinterpret_cast<const volatile uint32_t*>(&slots[slot].cnt);
+      if (!skip) {
+        const float* r = rows + (size_t)slot * rs + cc;
+        wv = ld_f4(r);
+        if (upd.kind != PS_UPD_SIMPLE) { m1 = ld_f4(r + Dp); m2 = ld_f4(r + 2 * Dp); }
       }
     }
   };
-  /* ---- the rows of the first round are requested before the scatter kernel is known to be complete ---- */
-  load_round(0);
+  /* ---- the records of the first round are requested before the scatter kernel is known to be complete ---- */
+  bool have = wi * KPW < (long)U;
+  if (have) prefetch(wi);
   pdl_wait();
-  for (int base = 0; base < items; base += 32 * IPL) {
-    if (base > 0) load_round(base);
-    float4 S[IPL];
-#pragma unroll
-    for (int q = 0; q < IPL; ++q) {
-      const int cc = ((base + q * 32 + lane) % TPK) * 4;
-      S[q] = (act[q] && !skip) ? __ldcg(reinterpret_cast<const float4*>(acc + (size_t)krow[q] * Dp + cc)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int q = 0; q < IPL; ++q) {
-      const int cc = ((base + q * 32 + lane) % TPK) * 4;
-      /* peer-memory exchange: senders pre-reduce, cnt packs {entries << 24 | occurrences} */
-      const uint32_t n_occ = packed_cnt ? (kcnt[q] & 0xFFFFFFu) : kcnt[q];
-      const GeffScale gs = make_geff<EXACT>(n_occ > 0u ? n_occ : 1u, calls);
-      bool do_upd = !skip;
-      if (upd.kind == PS_UPD_FTRL) {                  /* FtrlUpdater.java:52: `if (dw.get(0) == 0) return w` */
-        const float S0 = __shfl_sync(0xffffffffu, S[q].x, lane - (lane % TPK));
-        do_upd = do_upd && emb_geff<EXACT>(S0, gs) != 0.0f;
-      }
-      if (!act[q]) continue;
+  while (have) {
+    const long u = wi * KPW + kl;
+    const bool on = slot >= 0;
+    float4 S = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (on && !skip) S = __ldcg(reinterpret_cast<const float4*>(acc + (size_t)u * Dp + cc));
+    const int src0 = lane - ch;                               /* the key's chunk-0 lane */
+    /* owner side of the peer-memory exchange: the slot counted (requester, key) entries; the occurrences of the key in the
+     * global batch were summed into ucnt[u] by the owner-side scatter */
+    if (ucnt != nullptr && on && ch == 0) { cnt = __ldcg(ucnt + u); ucnt[u] = 0u; }
+    const uint32_t n_occ = __shfl_sync(0xffffffffu, cnt, src0);
+    const float S0 = __shfl_sync(0xffffffffu, S.x, src0);
+    const GeffScale gs = make_geff<EXACT>(n_occ > 0u ? n_occ : 1u, calls);
+    bool do_upd = !skip;
+    if (upd.kind == PS_UPD_FTRL) do_upd = do_upd && emb_geff<EXACT>(S0, gs) != 0.0f;   /* FtrlUpdater.java:52: `if (dw.get(0) == 0) return w` */
+    if (on) {
       if (!skip) {
-        const size_t o = (size_t)kslot[q] * Dp + cc;
+        float* r = rows + (size_t)slot * rs + cc;
         if (do_upd) {
-          apply_elem<EXACT>(upd, wv[q].x, m1[q].x, m2[q].x, emb_geff<EXACT>(S[q].x, gs));
-          apply_elem<EXACT>(upd, wv[q].y, m1[q].y, m2[q].y, emb_geff<EXACT>(S[q].y, gs));
-          apply_elem<EXACT>(upd, wv[q].z, m1[q].z, m2[q].z, emb_geff<EXACT>(S[q].z, gs));
-          apply_elem<EXACT>(upd, wv[q].w, m1[q].w, m2[q].w, emb_geff<EXACT>(S[q].w, gs));
-          st_f4(w + o, wv[q]);
-          if (upd.kind != PS_UPD_SIMPLE) { st_f4(s1 + o, m1[q]); st_f4(s2 + o, m2[q]); }
+          apply_elem<EXACT>(upd, wv.x, m1.x, m2.x, emb_geff<EXACT>(S.x, gs));
+          apply_elem<EXACT>(upd, wv.y, m1.y, m2.y, emb_geff<EXACT>(S.y, gs));
+          apply_elem<EXACT>(upd, wv.z, m1.z, m2.z, emb_geff<EXACT>(S.z, gs));
+          apply_elem<EXACT>(upd, wv.w, m1.w, m2.w, emb_geff<EXACT>(S.w, gs));
+          st_f4(r, wv);
+          if (upd.kind != PS_UPD_SIMPLE) { st_f4(r + Dp, m1); st_f4(r + 2 * Dp, m2); }
         }
-        st_f4(acc + (size_t)krow[q] * Dp + cc, make_float4(0.f, 0.f, 0.f, 0.f));
+        st_f4(acc + (size_t)u * Dp + cc, make_float4(0.f, 0.f, 0.f, 0.f));
       }
-      /* KVStore.clear (also after the early exit: the batch is forgotten): {cnt, first} = 0 in one 8 B store */
-      if (cc == 0) *reinterpret_cast<unsigned long long*>(&slots[kslot[q]].cnt) = 0ull;
+      /* KVStore.clear (also after the early exit: the batch is forgotten): {cnt, uidx} = {0, ready} in one 8 B store */
+      if (ch == 0) *reinterpret_cast<unsigned long long*>(&slots[slot].cnt) = (unsigned long long)kRowReady << 32;
     }
+    wi += wstride;
+    have = wi * KPW < (long)U;
+    if (have) prefetch(wi);
+  }
+  if (last_block_done(&counters[CNT_TICKET_UPD], gridDim.x) && threadIdx.x == 0) counters[CNT_CURSOR] = 0u;
+}
+
+/* Owner side of the push (PServer.push in sync mode, PServer.java:164-195: the pushes of all workers are summed, one
+ * update): entry (src, pos) of this step's grads_in mailbox is requester src's gradient sum for the key it asked for as
+ * its pos-th, already ReLU-masked; it lands in the key's accumulator row, its occurrence count in ucnt.  Waits for every
+ * requester's CH_GRADS flag in its prologue.                                                                        */
+__global__ void __launch_bounds__(256) emb_scatter_entries_kernel(const EmbSlot* __restrict__ slots, int Dp, const int32_t* __restrict__ lk_slot,
+                                                                  float* __restrict__ acc, uint32_t* __restrict__ ucnt,
+                                                                  const int* __restrict__ skip_flag, const P2PState* __restrict__ p2p) {
+  p2p_wait_all(p2p, CH_GRADS);
+  pdl_launch_dependents();
+  if (skip_flag != nullptr && *skip_flag != 0) return;
+  const int CH = Dp >> 2, cap = p2p->cap;
+  const long items = (long)p2p->R * cap * CH;
+  const float* grads = reinterpret_cast<const float*>(p2p_region(p2p, p2p->me, p2p->off_grads));
+  const uint32_t* gcnt = reinterpret_cast<const uint32_t*>(p2p_region(p2p, p2p->me, p2p->off_gcnt));
+  const int32_t* counts = reinterpret_cast<const int32_t*>(p2p_region(p2p, p2p->me, p2p->off_counts));
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long)gridDim.x * blockDim.x) {
+    const int entry = (int)(i / CH), ch = (int)(i - (long)entry * CH);
+    const int src = entry / cap, idx = entry - src * cap;
+    if (idx >= counts[src]) continue;
+    const int slot = lk_slot[entry];
+    if (slot < 0) continue;
+    const uint32_t u = (slots[slot].uidx & ~kRowReady) - 1u;
+    red_add_f4(acc + (size_t)u * Dp + ch * 4, ld_f4(grads + (size_t)entry * Dp + ch * 4));
+    if (ch == 0) atomicAdd(&ucnt[u], gcnt[entry]);
   }
 }
 
-__global__ void emb_clear_batch_kernel(EmbSlot* __restrict__ slots, const int32_t* __restrict__ lk_slot, int L) {
-  for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < L; l += gridDim.x * blockDim.x) {
-    const int slot = lk_slot[l];
-    if (slot >= 0) *reinterpret_cast<unsigned long long*>(&slots[slot].cnt) = 0ull;       /* {cnt, first}; duplicates store the same zero */
-  }
+/* forget the batch: the slots of its unique list get {cnt, uidx} = {0, ready}; the cursor restarts */
+__global__ void __launch_bounds__(256) emb_clear_batch_kernel(EmbSlot* __restrict__ slots, const int32_t* __restrict__ uniq, uint32_t* __restrict__ counters) {
+  const uint32_t U = counters[CNT_UNIQUE];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < U; i += gridDim.x * blockDim.x)
+    *reinterpret_cast<unsigned long long*>(&slots[uniq[i]].cnt) = (unsigned long long)kRowReady << 32;
+  if (last_block_done(&counters[CNT_TICKET_UPD], gridDim.x) && threadIdx.x == 0) counters[CNT_CURSOR] = 0u;
 }
 
 /* host-driven row access: thread per key */
-__global__ void emb_get_rows_kernel(const EmbSlot* __restrict__ slots, uint32_t C, const float* __restrict__ w, const float* __restrict__ s1,
-                                    const float* __restrict__ s2, int Dp, int D, const int32_t* __restrict__ fields,
-                                    const int64_t* __restrict__ ids, int n, float* __restrict__ wo, float* __restrict__ s1o,
-                                    float* __restrict__ s2o, int32_t* __restrict__ found) {
+__global__ void emb_get_rows_kernel(const EmbSlot* __restrict__ slots, uint32_t C, const float* __restrict__ rows, int rs, int Dp, int D,
+                                    const int32_t* __restrict__ fields, const int64_t* __restrict__ ids, int n, float* __restrict__ wo,
+                                    float* __restrict__ s1o, float* __restrict__ s2o, int32_t* __restrict__ found) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int slot = emb_find(slots, C, ps_pack_key((uint32_t)fields[i], (uint64_t)ids[i]));
   found[i] = slot >= 0;
   for (int d = 0; d < D; ++d) {
-    const size_t o = (size_t)(slot < 0 ? 0 : slot) * Dp + d;
-    wo[(size_t)i * D + d] = slot < 0 ? 0.f : w[o];
-    if (s1o) s1o[(size_t)i * D + d] = slot < 0 ? 0.f : s1[o];
-    if (s2o) s2o[(size_t)i * D + d] = slot < 0 ? 0.f : s2[o];
+    const size_t o = (size_t)(slot < 0 ? 0 : slot) * rs + d;
+    wo[(size_t)i * D + d] = slot < 0 ? 0.f : rows[o];
+    if (s1o) s1o[(size_t)i * D + d] = slot < 0 ? 0.f : rows[o + Dp];
+    if (s2o) s2o[(size_t)i * D + d] = slot < 0 ? 0.f : rows[o + 2 * Dp];
   }
 }
 
 /* KVStore.put (replace) / PServer.upsertList with replace=false (net/PServer.java:144-162):
  * insert-if-absent; the caller's buffer receives the winning row.                              */
-__global__ void emb_put_rows_kernel(EmbSlot* __restrict__ slots, uint32_t C, float* __restrict__ w, int Dp, int D,
+__global__ void emb_put_rows_kernel(EmbSlot* __restrict__ slots, uint32_t C, float* __restrict__ rows, int rs, int D,
                                     const int32_t* __restrict__ fields, const int64_t* __restrict__ ids, int n, float* __restrict__ wio,
                                     int replace, uint32_t* __restrict__ counters) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   bool inserted;
   const int slot = emb_find_or_insert(slots, C, ps_pack_key((uint32_t)fields[i], (uint64_t)ids[i]), &inserted);
-  if (slot < 0) { counters[1] = 1u; return; }
-  if (inserted) atomicAdd(reinterpret_cast<unsigned long long*>(counters + 2), 1ull);
-  float* row = w + (size_t)slot * Dp;
+  if (slot < 0) { counters[CNT_ERR] = 1u; return; }
+  if (inserted) atomicAdd(reinterpret_cast<unsigned long long*>(counters + CNT_ROWS), 1ull);
+  float* row = rows + (size_t)slot * rs;
   if (inserted || replace) { for (int d = 0; d < D; ++d) row[d] = wio[(size_t)i * D + d]; }
   else { for (int d = 0; d < D; ++d) wio[(size_t)i * D + d] = row[d]; }
+  if (inserted) { __threadfence(); atomicOr(&slots[slot].uidx, kRowReady); }
 }
 
 /* ------------------------------------------------------------------ EmbTable host side */
@@ -508,101 +683,100 @@ void EmbTable::create(Ctx* c, int F_, int D_, int64_t capacity, const ps_updater
   PS_REQUIRE(F_ > 0 && D_ > 0 && D_ <= 128, PS_ERR_ARG, "embedding: need F > 0 and 0 < D <= 128");
   PS_REQUIRE(capacity > 0 && capacity < (1ll << 31), PS_ERR_ARG, "embedding: capacity must be in (0, 2^31)");
   ctx = c; F = F_; D = D_; Dp = round_up(D_, 4); tpl = pow2_ge(Dp / 4); C = capacity;
+  rs = 3 * Dp; MW = std::max(1, tpl / 8);
   maxv = (float)(4 * (std::sqrt(6.0) / std::sqrt((double)(1 + D_))));   /* EmbeddingField.java:40 with in=1,out=D (EmbeddingLayer.java:52) */
   upd = make_updater_dev(u);
   slots = dmalloc_zero<EmbSlot>((size_t)C, ctx->stream);
-  w = dmalloc_zero<float>((size_t)C * Dp, ctx->stream);
-  s1 = dmalloc_zero<float>((size_t)C * Dp, ctx->stream);
-  s2 = dmalloc_zero<float>((size_t)C * Dp, ctx->stream);
-  counters = dmalloc_zero<uint32_t>(4, ctx->stream);
+  rows = dmalloc_zero<float>((size_t)C * rs, ctx->stream);
+  w = rows; s1 = rows + Dp; s2 = rows + 2 * Dp;
+  counters = dmalloc_zero<uint32_t>(CNT_WORDS, ctx->stream);
   reserve(max_lookups > 0 ? max_lookups : 1);
   scatter_update(nullptr, 0, nullptr, 0, 0, 2, nullptr);   /* fills scatter_occ (sizes the scatter's persistent grid) */
 }
 
 void EmbTable::reserve(int64_t L) {
   if (L <= Lcap) return;
+  if (last_L > 0) clear_batch();                /* a forward that was never followed by backward still owns counts in the OLD workspace's list */
   PS_CUDA(cudaStreamSynchronize(ctx->stream));
-  dfree(lk_slot); dfree(acc);
+  dfree(lk_slot); dfree(lk_mask); dfree(uniq); dfree(acc); dfree(ucnt);
   Lcap = L; ++generation;                      /* captured graphs that hold the old workspace pointers are stale now */
   lk_slot = dmalloc<int32_t>((size_t)L);
-  acc = dmalloc_zero<float>((size_t)L * Dp, ctx->stream);   /* one accumulator row per lookup index; a batch uses those of its keys' first lookups */
+  lk_mask = dmalloc<uint32_t>((size_t)L * MW);
+  uniq = dmalloc<int32_t>((size_t)L);
+  acc = dmalloc_zero<float>((size_t)L * Dp, ctx->stream);   /* one accumulator row per unique key of a batch (<= L) */
+  ucnt = dmalloc_zero<uint32_t>((size_t)L, ctx->stream);
 }
 
 void EmbTable::destroy() {
-  dfree(slots); dfree(w); dfree(s1); dfree(s2); dfree(counters);
-  dfree(lk_slot); dfree(acc);
-  slots = nullptr; w = s1 = s2 = nullptr;
+  dfree(slots); dfree(rows); dfree(counters);
+  dfree(lk_slot); dfree(lk_mask); dfree(uniq); dfree(acc); dfree(ucnt);
+  ucnt = nullptr; slots = nullptr; rows = w = s1 = s2 = nullptr; lk_slot = nullptr; lk_mask = nullptr; uniq = nullptr; acc = nullptr; counters = nullptr;
 }
 
-/* samples per block = 32 * SG with SG chosen so that a block's F * SG warp tasks keep its 8 warps busy */
-static int probe_sg(int F) { return F >= 8 ? 1 : (8 + F - 1) / F; }
+template <class IdT, int TPL>
+static void launch_lookup_t(EmbTable& t, LookupArgs& a, bool gather, bool aligned, int grid, size_t smem) {
+  cudaStream_t st = t.ctx->stream;
+  if (!gather) emb_lookup_kernel<IdT, false, 1, true><<<grid, 256, 0, st>>>(a);
+  else if (aligned) emb_lookup_kernel<IdT, true, TPL, true><<<grid, 256, smem, st>>>(a);
+  else emb_lookup_kernel<IdT, true, TPL, false><<<grid, 256, smem, st>>>(a);
+}
 
-void EmbTable::probe(const int64_t* ids_i64, const float* ids_f32, int N) {
+template <class IdT>
+static void launch_lookup(EmbTable& t, LookupArgs& a, bool gather) {
+  const long ntasks = (long)((a.N + 31) / 32) * (a.F > 0 ? a.F : 1);
+  a.task_blocks = ceil_div(ntasks, 8);
+  const int xblocks = (gather && a.X != nullptr) ? ceil_div((long)a.N * a.Xn, 1024) : 0;
+  a.hot_tma = (gather && t.ctx->hot_tma) ? 1 : 0;
+  const bool aligned = a.F == 0 || ((t.D % 4 == 0) && (a.ldo % 4 == 0) && ((uintptr_t)a.out % 16 == 0));
+  const size_t smem = a.hot_tma ? 128 + (size_t)8 * kHotRows * t.Dp * sizeof(float) : 0;
+  const int grid = a.task_blocks + xblocks;
+  switch (t.tpl) {
+    case 1: launch_lookup_t<IdT, 1>(t, a, gather, aligned, grid, smem); break;
+    case 2: launch_lookup_t<IdT, 2>(t, a, gather, aligned, grid, smem); break;
+    case 4: launch_lookup_t<IdT, 4>(t, a, gather, aligned, grid, smem); break;
+    case 8: launch_lookup_t<IdT, 8>(t, a, gather, aligned, grid, smem); break;
+    case 16: launch_lookup_t<IdT, 16>(t, a, gather, aligned, grid, smem); break;
+    default: launch_lookup_t<IdT, 32>(t, a, gather, aligned, grid, smem); break;
+  }
+  PS_LAUNCH_CHECK();
+  t.ctx->launches++;
+}
+
+static LookupArgs base_args(EmbTable& t) {
+  LookupArgs a{};
+  a.slots = t.slots; a.C = (uint32_t)t.C; a.rows = t.rows; a.rs = t.rs; a.Dp = t.Dp; a.D = t.D;
+  a.seed = t.ctx->seed; a.maxv = t.maxv;
+  a.lk_slot = t.lk_slot; a.lk_mask = nullptr; a.MW = t.MW; a.uniq = t.uniq; a.counters = t.counters;
+  return a;
+}
+
+void EmbTable::lookup(const int64_t* ids_i64, const float* ids_f32, int N, float* out, int ldo, const float* X, int Xn, int xoff) {
   const int64_t L = (int64_t)N * F;
   PS_REQUIRE(L <= Lcap, PS_ERR_ARG, "embedding: batch larger than the reserved workspace");
+  if (last_L > 0) clear_batch();               /* a forward that was never followed by backward: drop its counts */
   last_L = L;
-  const int SG = probe_sg(F);
-  const int grid = ceil_div(N, 32 * SG);
-  if (ids_i64)
-    emb_probe_kernel<int64_t><<<grid, 256, 0, ctx->stream>>>(slots, (uint32_t)C, w, Dp, D, ids_i64, N, F, SG, ctx->seed, maxv, lk_slot, counters, nullptr);
-  else
-    emb_probe_kernel<float><<<grid, 256, 0, ctx->stream>>>(slots, (uint32_t)C, w, Dp, D, ids_f32, N, F, SG, ctx->seed, maxv, lk_slot, counters, nullptr);
-  PS_LAUNCH_CHECK();
-  ctx->launches++;
+  LookupArgs a = base_args(*this);
+  a.N = N; a.F = F; a.out = out; a.ldo = ldo; a.X = out ? X : nullptr; a.Xn = Xn; a.xoff = xoff;
+  a.lk_mask = out ? lk_mask : nullptr;
+  if (ids_i64) { a.ids = ids_i64; launch_lookup<int64_t>(*this, a, out != nullptr); }
+  else { a.ids = ids_f32; launch_lookup<float>(*this, a, out != nullptr); }
 }
 
-void EmbTable::probe_packed(const uint64_t* keys, int n, const P2PState* p2p) {
+void EmbTable::lookup_packed(const uint64_t* keys, int n, float* out, P2PState* p2p, bool send_rows) {
+  if (last_L > 0) clear_batch();
   reserve(n);
   last_L = n;
   if (n <= 0) return;
-  const int SG = probe_sg(1);
-  emb_probe_kernel<unsigned long long><<<ceil_div(n, 32 * SG), 256, 0, ctx->stream>>>(slots, (uint32_t)C, w, Dp, D, reinterpret_cast<const unsigned long long*>(keys), n, 0, SG,
-                                                                                      ctx->seed, maxv, lk_slot, counters, p2p);
-  PS_LAUNCH_CHECK();
-  ctx->launches++;
-}
-
-template <int TPL>
-static void launch_gather(EmbTable& t, float* out, int ldo, int N, int F, const float* X, int Xn, int xoff) {
-  const long L = (long)N * F;
-  const bool aligned = (t.D % 4 == 0) && (ldo % 4 == 0) && ((uintptr_t)out % 16 == 0);
-  const int grid = ceil_div(L * TPL + (X ? (long)N * Xn : 0), 256);
-  if (aligned) launch_pdl(t.ctx, emb_gather_kernel<TPL, true>, dim3(grid), dim3(256), t.w, t.Dp, t.D, t.lk_slot, (int)L, F, out, ldo, X, Xn, xoff, N);
-  else launch_pdl(t.ctx, emb_gather_kernel<TPL, false>, dim3(grid), dim3(256), t.w, t.Dp, t.D, t.lk_slot, (int)L, F, out, ldo, X, Xn, xoff, N);
-}
-
-void EmbTable::gather(float* out, int ldo, int N, int F_eff, const float* X, int Xn, int xoff) {
-  const int Fe = F_eff > 0 ? F_eff : F;
-  PS_REQUIRE((int64_t)N * Fe == last_L, PS_ERR_STATE, "embedding: gather without a matching probe");
-  switch (tpl) {
-    case 1: launch_gather<1>(*this, out, ldo, N, Fe, X, Xn, xoff); break;
-    case 2: launch_gather<2>(*this, out, ldo, N, Fe, X, Xn, xoff); break;
-    case 4: launch_gather<4>(*this, out, ldo, N, Fe, X, Xn, xoff); break;
-    case 8: launch_gather<8>(*this, out, ldo, N, Fe, X, Xn, xoff); break;
-    case 16: launch_gather<16>(*this, out, ldo, N, Fe, X, Xn, xoff); break;
-    default: launch_gather<32>(*this, out, ldo, N, Fe, X, Xn, xoff); break;
-  }
-  PS_LAUNCH_CHECK();
-  ctx->launches++;
-}
-
-template <int TPK>
-static void launch_update(EmbTable& t, int N, int F, int calls, const int* skip, int packed_cnt) {
-  const long L = (long)N * F;
-  if (t.ctx->exact_updaters)
-    launch_pdl(t.ctx, emb_update_kernel<TPK, true>, dim3(ceil_div(L, 256)), dim3(256), t.slots, t.w, t.s1, t.s2, t.Dp, t.D, (const int32_t*)t.lk_slot, L,
-               t.acc, t.upd, calls, skip, packed_cnt, t.counters);
-  else
-    launch_pdl(t.ctx, emb_update_kernel<TPK, false>, dim3(ceil_div(L, 256)), dim3(256), t.slots, t.w, t.s1, t.s2, t.Dp, t.D, (const int32_t*)t.lk_slot, L,
-               t.acc, t.upd, calls, skip, packed_cnt, t.counters);
+  LookupArgs a = base_args(*this);
+  a.N = n; a.F = 0; a.ids = keys; a.out = out; a.ldo = Dp; a.p2p = p2p; a.send_rows = send_rows ? 1 : 0;
+  launch_lookup<unsigned long long>(*this, a, out != nullptr || send_rows);
 }
 
 template <int TPL, int CPL>
 static void launch_scatter(EmbTable& t, const float* delta, int ldd, const float* act, int lda, int N, int F, int calls, const int* skip,
-                           const P2PState* p2p) {
+                           const P2PState* p2p, const uint32_t* mask) {
   constexpr int PASSES = TPL >= 4 ? 4 : TPL;     /* warp tasks in flight per warp */
   constexpr int GPW = 32 / TPL;
-  const long L = (long)N * F;
   const bool aligned = (t.D % 4 == 0) && (ldd % 4 == 0) && (lda % 4 == 0) && ((uintptr_t)delta % 16 == 0) && ((uintptr_t)act % 16 == 0);
   /* samples per tile: small enough that there are >= 4 tiles per resident block (balance), at most 32 */
   if (N == 0) {                                  /* EmbTable::create: resident blocks per SM of the two instantiations (not inside a capture) */
@@ -617,46 +791,66 @@ static void launch_scatter(EmbTable& t, const float* delta, int ldd, const float
   /* a key is pre-summed per block when it is frequent enough to recur among the samples one block sees */
   const long per_block = (long)SB * ceil_div(ceil_div(N, SB), grid);
   const uint32_t hot_min = t.ctx->hot_min == 0xFFFFFFFFu ? 0xFFFFFFFFu : std::max<uint32_t>(t.ctx->hot_min, (uint32_t)(2L * N / per_block));
-  (void)L;
   if (aligned)
-    emb_scatter_kernel<TPL, CPL, PASSES, true><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.Dp, t.D, t.lk_slot, N, F, SB, delta, ldd, act, lda, t.acc, skip, p2p, hot_min);
+    emb_scatter_kernel<TPL, CPL, PASSES, true><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.Dp, t.D, t.lk_slot, mask, t.MW, N, F, SB, delta, ldd, act, lda, t.acc, skip, p2p, hot_min);
   else
-    emb_scatter_kernel<TPL, CPL, PASSES, false><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.Dp, t.D, t.lk_slot, N, F, SB, delta, ldd, act, lda, t.acc, skip, p2p, hot_min);
+    emb_scatter_kernel<TPL, CPL, PASSES, false><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.Dp, t.D, t.lk_slot, mask, t.MW, N, F, SB, delta, ldd, act, lda, t.acc, skip, p2p, hot_min);
   PS_LAUNCH_CHECK();
-  switch (t.tpl) {                              /* the update spends 4 floats per lane whatever the scatter's chunking was */
-    case 1: launch_update<1>(t, N, F, calls, skip, p2p != nullptr ? 1 : 0); break;
-    case 2: launch_update<2>(t, N, F, calls, skip, p2p != nullptr ? 1 : 0); break;
-    case 4: launch_update<4>(t, N, F, calls, skip, p2p != nullptr ? 1 : 0); break;
-    case 8: launch_update<8>(t, N, F, calls, skip, p2p != nullptr ? 1 : 0); break;
-    case 16: launch_update<16>(t, N, F, calls, skip, p2p != nullptr ? 1 : 0); break;
-    default: launch_update<32>(t, N, F, calls, skip, p2p != nullptr ? 1 : 0); break;
-  }
+  /* the update walks the unique list (<= L entries, how many is only known on the device): enough warps for one round at
+   * the typical unique fraction, a grid-stride loop beyond */
+  const long L = (long)N * F;
+  const int KPW = 32 / (t.Dp / 4);
+  const int ugrid = (int)std::max<long>(1, std::min<long>(ceil_div(ceil_div(L, KPW), 8), (long)t.ctx->num_sms * 16));
+  if (t.ctx->exact_updaters)
+    launch_pdl(t.ctx, emb_update_kernel<true>, dim3(ugrid), dim3(256), t.slots, t.rows, t.rs, t.Dp, t.D, (const int32_t*)t.uniq, t.acc, t.upd, calls, skip,
+               (uint32_t*)nullptr, t.counters);
+  else
+    launch_pdl(t.ctx, emb_update_kernel<false>, dim3(ugrid), dim3(256), t.slots, t.rows, t.rs, t.Dp, t.D, (const int32_t*)t.uniq, t.acc, t.upd, calls, skip,
+               (uint32_t*)nullptr, t.counters);
   t.ctx->launches += 2;
 }
 
+void EmbTable::scatter_update_entries(const P2PState* p2p, int n, int calls, const int* skip_flag) {
+  PS_REQUIRE((int64_t)n == last_L, PS_ERR_STATE, "embedding: push without a matching lookup");
+  const int CH = Dp / 4;
+  const int grid = (int)std::max<long>(1, std::min<long>(ceil_div((long)n * CH, 256), (long)ctx->num_sms * 8));
+  emb_scatter_entries_kernel<<<grid, 256, 0, ctx->stream>>>(slots, Dp, lk_slot, acc, ucnt, skip_flag, p2p);
+  PS_LAUNCH_CHECK();
+  const int KPW = 32 / CH;
+  const int ugrid = (int)std::max<long>(1, std::min<long>(ceil_div(ceil_div((long)n, KPW), 8), (long)ctx->num_sms * 16));
+  if (ctx->exact_updaters)
+    launch_pdl(ctx, emb_update_kernel<true>, dim3(ugrid), dim3(256), slots, rows, rs, Dp, D, (const int32_t*)uniq, acc, upd, calls, skip_flag, ucnt, counters);
+  else
+    launch_pdl(ctx, emb_update_kernel<false>, dim3(ugrid), dim3(256), slots, rows, rs, Dp, D, (const int32_t*)uniq, acc, upd, calls, skip_flag, ucnt, counters);
+  ctx->launches += 2;
+  last_L = 0;
+}
+
 void EmbTable::scatter_update(const float* delta, int ldd, const float* act, int lda, int N, int calls, const int* skip_flag, int F_eff,
-                              const P2PState* p2p) {
+                              const P2PState* p2p, bool use_mask) {
   const int Fe = F_eff > 0 ? F_eff : F;
   if (N > 0) {                                  /* N == 0: occupancy query from create() */
     PS_REQUIRE((int64_t)N * Fe == last_L, PS_ERR_STATE, "embedding: backward without a matching forward");
     PS_REQUIRE(calls == 1 || calls == 2, PS_ERR_ARG, "embedding: backward calls must be 1 or 2");
   }
+  const uint32_t* mask = use_mask ? lk_mask : nullptr;
+  if (use_mask) act = nullptr;
   if (Dp % 8 == 0) {                            /* two 16 B chunks per lane: half the threads, twice the bytes in flight per thread */
     switch (pow2_ge(Dp / 8)) {
-      case 1: launch_scatter<1, 2>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
-      case 2: launch_scatter<2, 2>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
-      case 4: launch_scatter<4, 2>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
-      case 8: launch_scatter<8, 2>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
-      default: launch_scatter<16, 2>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
+      case 1: launch_scatter<1, 2>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p, mask); break;
+      case 2: launch_scatter<2, 2>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p, mask); break;
+      case 4: launch_scatter<4, 2>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p, mask); break;
+      case 8: launch_scatter<8, 2>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p, mask); break;
+      default: launch_scatter<16, 2>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p, mask); break;
     }
   } else {
     switch (tpl) {
-      case 1: launch_scatter<1, 1>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
-      case 2: launch_scatter<2, 1>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
-      case 4: launch_scatter<4, 1>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
-      case 8: launch_scatter<8, 1>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
-      case 16: launch_scatter<16, 1>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
-      default: launch_scatter<32, 1>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p); break;
+      case 1: launch_scatter<1, 1>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p, mask); break;
+      case 2: launch_scatter<2, 1>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p, mask); break;
+      case 4: launch_scatter<4, 1>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p, mask); break;
+      case 8: launch_scatter<8, 1>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p, mask); break;
+      case 16: launch_scatter<16, 1>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p, mask); break;
+      default: launch_scatter<32, 1>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p, mask); break;
     }
   }
   if (N == 0) return;
@@ -666,7 +860,7 @@ void EmbTable::scatter_update(const float* delta, int ldd, const float* act, int
 
 void EmbTable::clear_batch() {
   if (last_L <= 0) return;
-  emb_clear_batch_kernel<<<std::min<long>(ceil_div(last_L, 256), (long)ctx->num_sms * 4), 256, 0, ctx->stream>>>(slots, lk_slot, (int)last_L);
+  emb_clear_batch_kernel<<<std::min<long>(ceil_div(last_L, 256), (long)ctx->num_sms * 4), 256, 0, ctx->stream>>>(slots, uniq, counters);
   PS_LAUNCH_CHECK();
   ctx->launches++;
   last_L = 0;
@@ -676,7 +870,7 @@ void EmbTable::check_errors() {
   uint32_t h[4];
   PS_CUDA(cudaMemcpyAsync(h, counters, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
   PS_CUDA(cudaStreamSynchronize(ctx->stream));
-  PS_REQUIRE(h[1] == 0, PS_ERR_CAPACITY, "embedding table is full: raise capacity");
+  PS_REQUIRE(h[CNT_ERR] == 0, PS_ERR_CAPACITY, "embedding table is full: raise capacity");
 }
 
 int64_t EmbTable::size() {
@@ -688,6 +882,8 @@ int64_t EmbTable::size() {
 
 void EmbTable::get_rows(const int32_t* fields, const int64_t* ids, int n, float* w_out, float* s1_out, float* s2_out, int32_t* found) {
   if (n <= 0) return;
+  for (int i = 0; i < n; ++i)                    /* a field outside [0, F) would alias another namespace (or the EMPTY sentinel) */
+    PS_REQUIRE(fields[i] >= 0 && fields[i] < F && ids[i] >= 0 && ids[i] <= (int64_t)PS_KEY_ID_MASK, PS_ERR_ARG, "embedding: key outside the (field, id) domain");
   cudaStream_t st = ctx->stream;
   int32_t* d_f = dmalloc<int32_t>(n); int64_t* d_i = dmalloc<int64_t>(n); int32_t* d_found = dmalloc<int32_t>(n);
   float* d_w = dmalloc<float>((size_t)n * D);
@@ -695,7 +891,7 @@ void EmbTable::get_rows(const int32_t* fields, const int64_t* ids, int n, float*
   float* d_s2 = s2_out ? dmalloc<float>((size_t)n * D) : nullptr;
   PS_CUDA(cudaMemcpyAsync(d_f, fields, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
   PS_CUDA(cudaMemcpyAsync(d_i, ids, sizeof(int64_t) * n, cudaMemcpyHostToDevice, st));
-  emb_get_rows_kernel<<<ceil_div(n, 128), 128, 0, st>>>(slots, (uint32_t)C, w, s1, s2, Dp, D, d_f, d_i, n, d_w, d_s1, d_s2, d_found);
+  emb_get_rows_kernel<<<ceil_div(n, 128), 128, 0, st>>>(slots, (uint32_t)C, rows, rs, Dp, D, d_f, d_i, n, d_w, d_s1, d_s2, d_found);
   PS_LAUNCH_CHECK();
   ctx->launches++;
   PS_CUDA(cudaMemcpyAsync(w_out, d_w, sizeof(float) * n * D, cudaMemcpyDeviceToHost, st));
@@ -708,13 +904,15 @@ void EmbTable::get_rows(const int32_t* fields, const int64_t* ids, int n, float*
 
 void EmbTable::put_rows(const int32_t* fields, const int64_t* ids, int n, float* w_io, int replace) {
   if (n <= 0) return;
+  for (int i = 0; i < n; ++i)
+    PS_REQUIRE(fields[i] >= 0 && fields[i] < F && ids[i] >= 0 && ids[i] <= (int64_t)PS_KEY_ID_MASK, PS_ERR_ARG, "embedding: key outside the (field, id) domain");
   cudaStream_t st = ctx->stream;
   int32_t* d_f = dmalloc<int32_t>(n); int64_t* d_i = dmalloc<int64_t>(n);
   float* d_w = dmalloc<float>((size_t)n * D);
   PS_CUDA(cudaMemcpyAsync(d_f, fields, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
   PS_CUDA(cudaMemcpyAsync(d_i, ids, sizeof(int64_t) * n, cudaMemcpyHostToDevice, st));
   PS_CUDA(cudaMemcpyAsync(d_w, w_io, sizeof(float) * n * D, cudaMemcpyHostToDevice, st));
-  emb_put_rows_kernel<<<ceil_div(n, 128), 128, 0, st>>>(slots, (uint32_t)C, w, Dp, D, d_f, d_i, n, d_w, replace, counters);
+  emb_put_rows_kernel<<<ceil_div(n, 128), 128, 0, st>>>(slots, (uint32_t)C, rows, rs, D, d_f, d_i, n, d_w, replace, counters);
   PS_LAUNCH_CHECK();
   ctx->launches++;
   PS_CUDA(cudaMemcpyAsync(w_io, d_w, sizeof(float) * n * D, cudaMemcpyDeviceToHost, st));
@@ -791,8 +989,11 @@ __global__ void __launch_bounds__(256) wide_update_all_kernel(WideSlot* __restri
 __global__ void __launch_bounds__(256) wide_insert_kernel(WideSlot* __restrict__ slots, uint32_t C, const int64_t* __restrict__ ids, int n,
                                                           uint32_t* __restrict__ counters, const P2PState* __restrict__ p2p) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p2p != nullptr) {                          /* this step's wide_in mailbox, once every replica's ids have landed */
+    p2p_wait_all(p2p, CH_WIDE);
+    ids = reinterpret_cast<const int64_t*>(p2p_region(p2p, p2p->me, p2p->off_wide));
+  }
   if (i >= n) return;
-  if (p2p != nullptr) ids = reinterpret_cast<const int64_t*>(p2p_region(p2p, p2p->me, p2p->off_wide));   /* this step's wide_in mailbox */
   bool inserted;
   const int slot = wide_find_or_insert(slots, C, ps_pack_key(0u, (uint64_t)ids[i]), true, &inserted);
   if (slot < 0) counters[0] = 1u;

@@ -4,17 +4,21 @@
  * EmbTable: one open-addressing hash table for all F embedding fields of a layer
  * (keys "emF<j>.<id>" of layer/EmbeddingField.java:70, packed by ps_pack_key).  HBM layout:
  *
- *   slots[C]   16 B records {key u64, cnt u32, first u32}: two per 32 B sector, so the probe
- *              that finds the key also brings the per-batch occurrence count and the index of the
- *              key's first lookup of the batch into L2 at no extra DRAM cost
- *   w[C][Dp], s1[C][Dp], s2[C][Dp]   row = slot index; SoA across {weight, Adam M | Ftrl Z,
- *              Adam V | Ftrl N} so the forward gather touches only w.  Dp = D rounded to 4
- *              floats: every row is 16 B aligned for 128-bit loads
- *   per-batch workspace (L = N*F lookups): lk_slot[F][N] (field-major: warps of the probe store, and warps
- *              of the backward kernels load, 128 contiguous bytes); acc[L][Dp] gradient accumulators — a
- *              key uses the row of its FIRST lookup in the batch (emb_probe leaves ~t of that lookup in the
- *              slot record by a fire-and-forget red.max), the update zeroes it again: nothing to number or
- *              reset, and the few MB a batch touches stay L2-resident, so the scatter-add never round-trips HBM
+ *   slots[C]   16 B records {key u64, cnt u32, uidx u32}: two per 32 B sector, so the probe
+ *              that finds the key also brings the per-batch bookkeeping into L2 at no extra DRAM cost.
+ *              cnt  = occurrences of the key in the current batch (0 between batches)
+ *              uidx = bit 31: the row has been written (kRowReady, permanent);
+ *                     bits 0-30: 1 + the key's index in this batch's list of unique keys (0 between batches)
+ *   rows[C][3*Dp]  array of records {w[Dp] | s1[Dp] | s2[Dp]} — weight, Adam M | Ftrl Z, Adam V | Ftrl N of one key
+ *              side by side: the update touches ONE contiguous record (one DRAM page, one TLB entry) per key,
+ *              the forward gather reads the first third of it.  Dp = D rounded to 4 floats: 16 B alignment.
+ *   per-batch workspace (L = N*F lookups):
+ *              lk_slot[F][N]  slot of every lookup, field-major (a warp works on one field of 32 consecutive samples)
+ *              lk_mask[F][N][MW]  the ReLU mask of the gathered row, one bit per element: the backward never
+ *                             re-reads the activations (EmbeddingField.java:91-93 needs only A > 0)
+ *              uniq[U]        slots of this batch's unique keys in first-arrival order (U <= L)
+ *              acc[U][Dp]     gradient accumulators, one row per unique key — compact, so the few MB a batch
+ *                             touches stay L2-resident and the scatter-add never round-trips HBM
  *
  * WideTable: layer/LRLayer.java's 1x1 weights "wide.weights.<id>": 32 B records
  * {key, w, s1, s2} — one sector holds everything a probe, the forward sum and the update need.
@@ -27,12 +31,21 @@ namespace psb { struct P2PState; }
 
 namespace psb {
 
+constexpr uint32_t kRowReady = 0x80000000u;
+constexpr int kProbeLimit = 1 << 16;        /* linear-probe bound shared by every find / insert (lookup, put, checkpoint load) */
+
 struct __align__(16) EmbSlot {
   unsigned long long key;
   uint32_t cnt;    /* occurrences of this key in the current batch (EmbeddingField.java:96 wgN) */
-  uint32_t first;  /* ~t of the key's first lookup of the current batch (max over ~t = min over t; 0 between batches): that lookup
-                      owns the key's accumulator row acc[t] and performs its update */
+  uint32_t uidx;   /* kRowReady | (1 + index in this batch's unique list); see above */
 };
+
+/* EmbTable::counters */
+enum { CNT_UNIQUE = 0,      /* unique keys of the last resolved batch (final once the lookup kernel has finished) */
+       CNT_ERR = 1,         /* an insert found the table full */
+       CNT_ROWS = 2,        /* [2..3] u64 number of keys in the table */
+       CNT_CURSOR = 4,      /* unique keys claimed so far by the running lookup kernel */
+       CNT_TICKET_FWD = 5, CNT_TICKET_UPD = 6, CNT_WORDS = 8 };
 
 struct __align__(32) WideSlot {
   unsigned long long key;
@@ -43,35 +56,46 @@ struct __align__(32) WideSlot {
 
 struct EmbTable {
   Ctx* ctx = nullptr;
-  int F = 0, D = 0, Dp = 0, tpl = 1;   /* tpl: lanes cooperating on one lookup (power of two >= Dp/4) */
+  int F = 0, D = 0, Dp = 0, tpl = 1;   /* tpl: lanes cooperating on one row (power of two >= Dp/4) */
+  int rs = 0;                          /* floats between consecutive row records (3*Dp) */
+  int MW = 1;                          /* mask words per lookup */
   int64_t C = 0;
   float maxv = 0.f;                    /* Xavier bound of EmbeddingField.java:40 */
   UpdaterDev upd;
   EmbSlot* slots = nullptr;
-  float *w = nullptr, *s1 = nullptr, *s2 = nullptr;
+  float *rows = nullptr;               /* [C][3*Dp] */
+  float *w = nullptr, *s1 = nullptr, *s2 = nullptr;   /* rows, rows + Dp, rows + 2*Dp: element (slot, d) of each lives at p[slot*rs + d] */
   /* per-batch workspace */
   int64_t Lcap = 0;
   int generation = 0;                  /* bumped whenever reserve() reallocates the workspace */
   int32_t* lk_slot = nullptr;
+  uint32_t* lk_mask = nullptr;
+  int32_t* uniq = nullptr;
   float* acc = nullptr;
-  uint32_t* counters = nullptr;        /* [0] monotonic count of updated (unique) keys, [1] error flag, [2..3] u64 row count */
+  uint32_t* ucnt = nullptr;            /* [U] occurrences per unique key as summed from the requesters' pushes (sharded exchange only) */
+  uint32_t* counters = nullptr;
   int64_t last_L = 0;
   int scatter_occ[2] = {1, 1};         /* resident scatter blocks per SM (unaligned / aligned instantiation) */
 
   void create(Ctx* c, int F_, int D_, int64_t capacity, const ps_updater_spec& u, int64_t max_lookups);
   void destroy();
   void reserve(int64_t L);
-  /* find-or-insert every (field, id) of the batch, count occurrences, mark each key's first lookup.
-   * ids: device pointer, [N][F]; exactly one of ids_i64 / ids_f32 non-null.                  */
-  void probe(const int64_t* ids_i64, const float* ids_f32, int N);
-  /* out[n*ldo + j*D + d] = relu(w[slot(n,j)][d])   (EmbeddingField.java:73-76)               */
-  /* the same on already-packed keys (owner side of the key-hash sharded exchange): n lookups, one "field" */
-  void probe_packed(const uint64_t* keys, int n, const P2PState* p2p = nullptr);   /* p2p: keys come from this step's mailbox */
-  /* X != null: also copies the numeric features X[N][Xn] to columns [xoff, xoff+Xn) (ConcatLayer) */
-  void gather(float* out, int ldo, int N, int F_eff = 0, const float* X = nullptr, int Xn = 0, int xoff = 0);
-  /* pre-summed scatter-add, then occurrence normalisation + updater step + per-batch reset (two launches, see table.cu) */
-  void scatter_update(const float* delta, int ldd, const float* act /* null: mask already applied */, int lda, int N, int calls,
-                      const int* skip_flag, int F_eff = 0, const P2PState* p2p = nullptr /* delta = this step's grads_in mailbox */);
+  /* EmbeddingLayer.forward in ONE kernel: find-or-insert every (field, id) of the batch, count occurrences, claim each
+   * key's place in the batch's unique list, and (out != null) gather relu(row) into out[n*ldo + j*D + d]
+   * (EmbeddingField.java:66-78) while recording the ReLU mask.  ids: device pointer [N][F]; exactly one of ids_i64 /
+   * ids_f32 non-null.  X != null: also copies the numeric features X[N][Xn] to columns [xoff, xoff+Xn) (ConcatLayer). */
+  void lookup(const int64_t* ids_i64, const float* ids_f32, int N, float* out, int ldo, const float* X = nullptr, int Xn = 0, int xoff = 0);
+  /* the same on already-packed keys (owner side of the key-hash sharded exchange): n lookups, one "field".
+   * out != null: rows (ReLU applied) to out[n][Dp].  p2p: keys come from this step's keys_in mailbox and, with send_rows,
+   * every row goes straight into the requester's rows_in mailbox over NVLink (PServer.getList).                      */
+  void lookup_packed(const uint64_t* keys, int n, float* out, P2PState* p2p = nullptr, bool send_rows = false);
+  /* owner side of the push over peer memory: entries of this step's grads_in / gcnt_in mailboxes (n = R*cap, after
+   * lookup_packed on the same entries) → accumulator rows → the update; waits for the requesters' flags in-kernel */
+  void scatter_update_entries(const P2PState* p2p, int n, int calls, const int* skip_flag);
+  /* pre-summed scatter-add, then occurrence normalisation + updater step + per-batch reset (two launches, see table.cu).
+   * The ReLU mask comes from the lookup's mask bits (use_mask), from `act` (non-null), or is taken as already applied. */
+  void scatter_update(const float* delta, int ldd, const float* act, int lda, int N, int calls, const int* skip_flag, int F_eff = 0,
+                      const P2PState* p2p = nullptr /* delta = this step's grads_in mailbox */, bool use_mask = false);
   /* forget the batch without updating (predict path / early exit): cnt = 0 for touched slots */
   void clear_batch();
   void check_errors();                 /* syncs; throws PS_ERR_CAPACITY if an insert found the table full */

@@ -51,6 +51,8 @@ def lib():
     L.pso_ftrl_update.argtypes = [f32p, f32p, f32p, f32p, C.c_int] + [C.c_float] * 4
     L.pso_updater_name.argtypes = [C.c_int] + [C.c_float] * 4 + [C.c_char_p, C.c_int]
     L.pso_set_gemm.argtypes = [C.c_int, C.c_char_p]
+    L.pso_set_blas_threads.restype = C.c_int
+    L.pso_set_blas_threads.argtypes = [C.c_int]
     L.pso_model_create.restype = C.c_void_p
     L.pso_model_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, i32p, C.c_int, C.c_uint64, C.c_int]
     L.pso_model_destroy.argtypes = [C.c_void_p]
