@@ -5,27 +5,39 @@
 
 A "step" is one train.Trainer step (pullWeights → forward → loss → backward → KVStore.update →
 clear) of the WideDeepNN on one synthetic Criteo-libsvm-shaped batch.
-  value : samples/s with the batch ring already resident in HBM (device-timed, CUDA events on
-          the library's stream, max over ranks)
-  e2e   : samples/s through the host-facing C-ABI call (ps_model_submit / ps_model_collect, the
-          pipelined form of Trainer.train) with inputs in pinned HOST memory: every step copies
-          its E/X/W/Y host→device and reads its loss device→host inside the timed region
-  roofline : the dominant HBM-bound kernel's algorithmic bytes / its device time vs the measured
-          copy bandwidth in MEASURED_PEAKS.json
-  cpu_baseline : the CPU oracle (C++ restatement of the reference's standalone Java path; the JVM
-          cannot run in this image) timed on this box's host cores on a bounded sample
+  value : samples/s with the batch ring already resident in HBM.  Device-timed (CUDA events on the library's stream), max over
+          ranks; the K-step loop is repeated (>= 25 times, >= 1 s in total) and the MEDIAN repetition is reported.  Before any
+          timing every batch of the ring has been stepped once, so no graph capture and no first-touch insert is timed.
+  e2e   : samples/s through the host-facing C-ABI call (ps_model_submit / ps_model_collect, the pipelined form of
+          Trainer.train) with inputs in pinned HOST memory: every step copies its E/X/W/Y host→device and reads its loss
+          device→host inside the timed region; same repetition / median protocol, wall clock around synchronised regions
+  roofline : the dominant HBM-bound kernel's algorithmic bytes / its device time vs the measured copy bandwidth in
+          MEASURED_PEAKS.json; roofline_tensor: the dominant FcLayer GEMM vs a TF32 cuBLAS ceiling measured in this run
+  parity : a fresh model of the same shape, stepped on a global batch split over the N ranks, against the CPU oracle's step on
+          the concatenated batch (loss, dense weights, >= 200 embedding rows fetched from whichever rank owns them)
+  extra_configs : BASELINE configs 3 (100 M keys, Ftrl, D = 32) and 4 (DNN, 10 M keys, D = 64) at this N, same protocol
+  cpu_baseline : the CPU oracle (C++ restatement of the reference's standalone Java path; the JVM cannot run in this image)
+          timed on this box's host cores on a bounded sample
 --impl reference times that CPU restatement as the reference arm (rank 0 only).
 """
-import argparse
-import ctypes as C
-import json
 import os
-import subprocess
 import sys
-import threading
-import time
 
-import numpy as np
+# The oracle's sgemm is the OpenBLAS that numpy bundles; numpy initialises it with one thread per core at import.  Both the
+# single-thread baseline and the one-replica-per-core reference arm want ONE BLAS thread per call: pin it before numpy loads
+# (and again, explicitly, on the dlopen'ed handle — see pin_blas()).
+os.environ["OMP_NUM_THREADS"] = "1"
+os.environ["OPENBLAS_NUM_THREADS"] = "1"
+
+import argparse  # noqa: E402
+import ctypes as C  # noqa: E402
+import json  # noqa: E402
+import math  # noqa: E402
+import subprocess  # noqa: E402
+import threading  # noqa: E402
+import time  # noqa: E402
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -35,6 +47,7 @@ from ps_b200.synth import CONFIGS, Synth  # noqa: E402
 
 METRIC = "Wide&Deep CTR training samples/sec"
 UNIT = "samples/s"
+L2_BYTES = 126e6
 
 
 def peaks():
@@ -46,8 +59,7 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """SM clock and throttle reasons DURING the timed region: NVML polled every 2 ms (the timed region of the default run is tens
-    of milliseconds — an nvidia-smi subprocess per sample would see it once); nvidia-smi is the fallback when NVML is unavailable."""
+    """SM clock and throttle reasons DURING the timed region: NVML polled every 2 ms; nvidia-smi is the fallback when NVML is unavailable."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
@@ -103,55 +115,30 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows), "how": self.how}
 
 
-def model_args(cfg, n_gpus):
-    return dict(kind=cfg["kind"], F=cfg["F"], D=cfg["D"], Xn=cfg["Xn"], fc=cfg["fc"])
-
-
+# ----------------------------------------------------------------------------------------------- CPU oracle legs
 def oracle_model(cfg, seed):
     import oracle_lib as ol
     kind = {"widedeep": ol.KIND_WIDEDEEP, "dnn": ol.KIND_DNN, "fcnn": ol.KIND_FCNN}[cfg["kind"]]
     return ol.OracleModel(kind, cfg["F"], cfg["D"], cfg["Xn"], cfg["fc"], seed, emb_opt=1 if cfg["emb_opt"] == "ftrl" else 0)
 
 
-def time_oracle(cfg, batches, budget_s, threads):
-    """Timed CPU restatement: returns (samples/s, steps run, gemm back-end)."""
+def pin_blas():
+    """Selects OpenBLAS sgemm for the oracle and forces ONE thread per call on that very library handle.  Returns (name, threads in force)."""
     import oracle_lib as ol
-    os.environ["OMP_NUM_THREADS"] = str(threads)
-    gemm = "openmp-loops"
     ob = ol.openblas_path()
     if ob and ol.lib().pso_set_gemm(2, ob.encode()) == 0:
-        gemm = "openblas-0.3.30 (numpy bundled)"
-        os.environ["OPENBLAS_NUM_THREADS"] = str(threads)
-    else:
-        ol.lib().pso_set_gemm(1, None)
-    o = oracle_model(cfg, 20261017)
-    b = batches[0]
-    o.train_step(b.get("E"), b["X"], b.get("W"), b["Y"])          # warm-up: creates keys
-    n, t0 = 0, time.perf_counter()
-    while True:
-        b = batches[(n + 1) % len(batches)]
-        o.train_step(b.get("E"), b["X"], b.get("W"), b["Y"])
-        n += 1
-        dt = time.perf_counter() - t0
-        if dt >= budget_s or n >= 64:
-            break
-    ol.lib().pso_set_gemm(0, None)
-    return n * cfg["B"] / dt, n, gemm, dt
+        n = ol.lib().pso_set_blas_threads(1)
+        return "openblas-0.3.30 (numpy bundled)", n
+    ol.lib().pso_set_gemm(1, None)
+    return "openmp-loops", 1
 
 
-def time_oracle_replicas(cfg, batches, budget_s, replicas):
+def time_oracle_replicas(cfg, batches, budget_s, replicas, max_steps=64):
     """`replicas` independent copies of the standalone Trainer step (thread = 1 each, single-threaded sgemm), one per host thread:
     an UPPER bound for the reference's Trainer with thread = replicas, whose replicas share one synchronized KVStore
     (KVStore.java:136,192,240) and serialise on it.  ctypes releases the GIL inside the C call, so the steps run in parallel."""
     import oracle_lib as ol
-    os.environ["OMP_NUM_THREADS"] = "1"
-    os.environ["OPENBLAS_NUM_THREADS"] = "1"
-    gemm = "openmp-loops"
-    ob = ol.openblas_path()
-    if ob and ol.lib().pso_set_gemm(2, ob.encode()) == 0:
-        gemm = "openblas-0.3.30 (numpy bundled), 1 thread per replica"
-    else:
-        ol.lib().pso_set_gemm(1, None)
+    gemm, blas_threads = pin_blas()
     models = [oracle_model(cfg, 20261017 + r) for r in range(replicas)]
     for r, o in enumerate(models):                                   # warm-up: creates keys
         b = batches[r % len(batches)]
@@ -161,7 +148,7 @@ def time_oracle_replicas(cfg, batches, budget_s, replicas):
 
     def work(r):
         o, n = models[r], 0
-        while time.perf_counter() - t0 < budget_s and n < 64:
+        while time.perf_counter() - t0 < budget_s and n < max_steps:
             b = batches[(r + n + 1) % len(batches)]
             o.train_step(b.get("E"), b["X"], b.get("W"), b["Y"])
             n += 1
@@ -173,26 +160,445 @@ def time_oracle_replicas(cfg, batches, budget_s, replicas):
         t.join()
     dt = time.perf_counter() - t0
     ol.lib().pso_set_gemm(0, None)
-    return sum(counts) * cfg["B"] / dt, sum(counts), gemm, dt
+    return sum(counts) * cfg["B"] / dt, sum(counts), f"{gemm}, {blas_threads} BLAS thread per call", dt
 
 
-def time_ingest(ps, cfg, batch, threads):
-    """libsvm text -> the step's staging layout through the native reader: one synthetic batch written as text in the
-    reference's own line format (label, F "idx:1" columns, Xn "idx:value" columns), read back for about a second on the host cores."""
-    import tempfile
-    F, Xn, B = cfg["F"], cfg["Xn"], cfg["B"]
-    if not F:
+def workload_name(args, cfg, name=None):
+    return (f"{name or args.config}: {cfg['kind']} synthetic Criteo-libsvm, F={cfg['F']} Xn={cfg['Xn']} D={cfg['D']} vocab={cfg['V']} "
+            f"fc={cfg['fc']} batch={cfg['B']}/GPU emb_opt={cfg['emb_opt']} keys={args.dist}")
+
+
+def run_reference(args, cfg):
+    syn = Synth(F=cfg["F"], Xn=cfg["Xn"], V=cfg["V"], dist=args.dist, seed=20261017 + 2)
+    batches = [syn.batch(cfg["B"]) for _ in range(4)]
+    threads = os.cpu_count() or 1
+    total = args.steps + args.warmup
+    single, n1, gemm, dt1 = time_oracle_replicas(cfg, batches, 4.0, 1)
+    sps, n, gemm, dt = time_oracle_replicas(cfg, batches, min(45.0, 3.0 * total), threads)
+    speedup = sps / single
+    line = {
+        "impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * cfg["B"] / sps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": workload_name(args, cfg), "global_batch": cfg["B"] * args.gpus},
+        "cpu_baseline": {"value": sps, "unit": UNIT, "cores": threads, "kind": "port",
+                         "single_thread_value": single, "replica_speedup": speedup,
+                         "replicas_scale": bool(speedup >= 0.5 * threads),     # 1-thread replicas on idle cores must scale: the round-1 arm did not (BLAS oversubscription)
+                         "sample": f"{n} Trainer steps of batch {cfg['B']} in {dt:.1f}s over {threads} independent replicas (one per host thread, thread=1 each; "
+                                   f"one replica alone: {single:.0f} samples/s, x{speedup:.1f} with {threads}): an upper bound for the reference's Trainer with "
+                                   f"thread={threads}, which shares one synchronized KVStore; C++ restatement of the reference's standalone Java path "
+                                   f"(JVM/jblas unavailable in this image); sgemm={gemm}"},
+        "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- the GPU arm
+class Env:
+    """Process-wide handles: torch / distributed / the ctypes binding / one library context per rank."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        import __graft_entry__ as g
+        self.torch, self.dist, self.args = torch, dist, args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.sharded = self.world > 1 or args.force_sharded
+        if self.local_rank == 0:
+            g.build()
+        if self.sharded:
+            if self.world == 1:
+                os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+                os.environ.setdefault("MASTER_PORT", "29533")
+                dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", self.local_rank))
+            else:
+                dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            dist.barrier()
+        from ps_b200 import binding as ps
+        self.ps = ps
+        torch.cuda.set_device(self.local_rank)
+        self.ctx = ps.Context(self.local_rank, seed=20261017)
+        self.ctx.set_fc_precision({"fp32": ps.PS_FC_FP32, "tf32": ps.PS_FC_TF32, "tf32x3": ps.PS_FC_TF32X3}[args.precision])
+        self.stream = torch.cuda.ExternalStream(self.ctx.stream(), device=self.local_rank)
+
+    def barrier(self):
+        self.ctx.synchronize()
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, values):
+        if self.world == 1:
+            return list(values)
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device=f"cuda:{self.local_rank}")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def bcast_int(self, v):
+        if self.world == 1:
+            return int(v)
+        t = self.torch.tensor([int(v)], dtype=self.torch.int64, device=f"cuda:{self.local_rank}")
+        self.dist.broadcast(t, 0)
+        return int(t.item())
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class Workload:
+    """One model + its ring of synthetic batches (device-resident and pinned-host copies) + the sharded trainer when N > 1."""
+
+    def __init__(self, env, name, cfg, ring, batch=None, capacity=None, seed_off=0):
+        ps, torch = env.ps, env.torch
+        self.env, self.name, self.cfg = env, name, cfg
+        self.B = B = batch or cfg["B"]
+        F, D, Xn = cfg["F"], cfg["D"], cfg["Xn"]
+        world = env.world
+        self.cap = capacity or (int(min(2 ** 31 - 1, max(1 << 16, (2 * cfg["V"]) // world + (1 << 16)))) if cfg["V"] else 1024)
+        upd = ps.UpdaterSpec.ftrl() if cfg["emb_opt"] == "ftrl" else None
+        self.model = ps.Model(env.ctx, cfg["kind"], F, D, Xn, cfg["fc"], emb_capacity=self.cap, emb_updater=upd, max_batch=B)
+        syn = Synth(F=F, Xn=Xn, V=cfg["V"], dist=env.args.dist, seed=20261017 + 2 + seed_off + 1000 * env.rank, n_classes=10 if cfg["kind"] == "fcnn" else 0)
+        self.ring = [syn.batch(B) for _ in range(ring)]
+        dev = env.local_rank
+        self.dev_ring = [{k: torch.from_numpy(np.ascontiguousarray(v)).cuda(dev) for k, v in b.items()} for b in self.ring]
+        torch.cuda.synchronize()
+        self.trainer = None
+        if env.sharded:
+            from ps_b200.sharded import GpuOps, GraphedShardedTrainer, P2PShardedTrainer
+            if env.args.exchange == "p2p":
+                self.trainer = P2PShardedTrainer(ps, env.ctx, self.model, env.rank, world, B, F, slack=env.args.slack, device=dev)
+            else:
+                self.trainer = GraphedShardedTrainer(GpuOps(ps, env.ctx, self.model, dev), env.rank, world, B, F, cfg["kind"] == "widedeep", slack=env.args.slack)
+        self.pinned = None
+
+    def dev_step(self, i):
+        d = self.dev_ring[i % len(self.dev_ring)]
+        if self.trainer is not None:
+            return self.trainer.step(d.get("E"), d["X"], d.get("W"), d["Y"])
+        self.model.train_step_dev(ptr(d.get("E")), ptr(d["X"]), ptr(d.get("W")), ptr(d["Y"]), self.B)
+
+    def prepare(self):
+        """Every batch of the ring once, untimed: the step graph of each ring entry is captured and instantiated, its keys are inserted."""
+        for i in range(len(self.dev_ring) + 2):
+            self.dev_step(i)
+        loss = self.model.read_loss()
+        self.env.barrier()
+        return loss
+
+    def _reps(self, K, probe_ms, min_reps=25, target_s=1.0, max_reps=1500):
+        reps = max(min_reps, int(math.ceil(target_s * 1e3 / max(probe_ms, 1e-3))))
+        return self.env.bcast_int(min(reps, max_reps))
+
+    def time_value(self, K, warmup, reps=None):
+        env, torch = self.env, self.env.torch
+        for i in range(warmup):
+            self.dev_step(i)
+        self.model.read_loss()
+        env.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def one(start):
+            env.barrier()
+            e0.record(env.stream)
+            for i in range(K):
+                self.dev_step(start + i)
+            e1.record(env.stream)
+            env.barrier()
+            return e0.elapsed_time(e1)
+        probe = env.max_over_ranks([one(warmup)])[0]
+        reps = reps or self._reps(K, probe)
+        l0 = env.ctx.launch_count()
+        ms = [one(warmup + (r + 1) * K) for r in range(reps)]
+        launches = (env.ctx.launch_count() - l0) / reps
+        if self.trainer is not None and hasattr(self.trainer, "launches_per_step"):
+            launches = K * self.trainer.launches_per_step           # torch graph replays: counted at the eager warm-up step
+        ms = sorted(env.max_over_ranks(ms))
+        return {"ms": ms[len(ms) // 2], "ms_min": ms[0], "ms_max": ms[-1], "reps": reps, "launches": launches, "loss": self.model.read_loss()}
+
+    def _pin(self):
+        if self.pinned is None:
+            ps = self.env.ps
+            self.pinned = []
+            for b in self.ring[: min(len(self.ring), 16)]:
+                pb = {}
+                for k, v in b.items():
+                    pa = ps.PinnedArray(v.shape, v.dtype)
+                    pa.array[...] = v
+                    pb[k] = pa
+                self.pinned.append(pb)
+        return self.pinned
+
+    def host_loop(self, n, start):
+        env, torch, model, B = self.env, self.env.torch, self.model, self.B
+        pinned = self._pin()
+
+        def hp(pb, k):
+            return pb[k].ptr if k in pb else None
+        if self.trainer is not None and env.args.exchange == "p2p":
+            # peer-memory sharded step through its host-facing call: ps_model_p2p_submit copies this rank's slice from pinned host
+            # memory and enqueues the step's graph, ps_model_collect returns the global loss of the oldest of 2 steps in flight
+            for i in range(n):
+                pb = pinned[(start + i) % len(pinned)]
+                model.p2p_submit_ptrs(hp(pb, "E"), hp(pb, "X"), hp(pb, "W"), hp(pb, "Y"), B)
+                if i >= 1:
+                    model.collect()
+            return model.collect()
+        if self.trainer is not None:      # NCCL sharded step: stage this rank's slice from pinned host memory, then the step, then its loss
+            last = None
+            for i in range(n):
+                pb = pinned[(start + i) % len(pinned)]
+                with torch.cuda.stream(env.stream):
+                    d = {k: torch.from_numpy(pa.array).to(f"cuda:{env.local_rank}", non_blocking=True) for k, pa in pb.items()}
+                self.trainer.step(d.get("E"), d["X"], d.get("W"), d["Y"])
+                last = model.read_loss()                       # the step's result is read back every step
+            return last
+        for i in range(n):
+            pb = pinned[(start + i) % len(pinned)]
+            model.submit_ptrs(hp(pb, "E"), hp(pb, "X"), hp(pb, "W"), hp(pb, "Y"), B)
+            if i >= 1:
+                model.collect()
+        return model.collect()
+
+    def time_e2e(self, K, warmup, reps=None):
+        env = self.env
+        self.host_loop(len(self._pin()) + max(3, warmup), 0)        # every staging-buffer graph captured, untimed
+        env.barrier()
+
+        def one(start):
+            env.barrier()
+            t0 = time.perf_counter()
+            loss = self.host_loop(K, start)
+            env.ctx.synchronize()
+            return (time.perf_counter() - t0) * 1e3, loss
+        probe = env.max_over_ranks([one(warmup)[0]])[0]
+        reps = reps or self._reps(K, probe)
+        ms, loss = [], None
+        for r in range(reps):
+            t, loss = one(warmup + (r + 1) * K)
+            ms.append(t)
+        ms = sorted(env.max_over_ranks(ms))
+        h2d = sum(pa.nbytes for pa in self._pin()[0].values())
+        return {"ms": ms[len(ms) // 2], "ms_min": ms[0], "ms_max": ms[-1], "reps": reps, "h2d": h2d, "loss": loss}
+
+    def check(self):
+        if self.trainer is not None:
+            self.trainer.check()
+
+    def unique_stats(self):
+        F = self.cfg["F"]
+        if not F:
+            return 0.0, 0
+        off = (np.arange(F, dtype=np.int64) << 44)[None, :]
+        per = [len(np.unique(b["E"] + off)) for b in self.ring]
+        allk = len(np.unique(np.concatenate([(b["E"] + off).ravel() for b in self.ring])))
+        return float(np.mean(per)), allk
+
+    def close(self):
+        if self.pinned:
+            for pb in self.pinned:
+                for pa in pb.values():
+                    pa.free()
+            self.pinned = None
+        self.dev_ring = None
+        self.model.close()
+
+
+def emb_rooflines(env, wl, hbm_peak, reps):
+    """Device time of the embedding kernels replayed in a CUDA graph over the ring vs their algorithmic bytes."""
+    cfg, B = wl.cfg, wl.B
+    F, D = cfg["F"], cfg["D"]
+    L = B * F
+    uniq, ring_unique = wl.unique_stats()
+    kt = wl.model.kernel_times([d["E"].data_ptr() for d in wl.dev_ring], B, reps=reps)
+    alg = {"emb_lookup": L * (8 + 8 * D), "emb_scatter_update": L * (8 + 4 * D) + uniq * 24 * D}
+    out = {}
+    for k, bytes_ in alg.items():
+        us = kt[k]
+        out[k] = {"us": us, "alg_bytes": bytes_, "gbs": bytes_ / max(us, 1e-3) / 1e3, "frac": bytes_ / max(us, 1e-3) / 1e3 / hbm_peak}
+    out["emb_resolve_only_us"] = kt["emb_resolve"]
+    out["unique_keys_per_batch"] = uniq
+    Dp = (D + 3) // 4 * 4
+    ws = ring_unique * (12 * Dp + 16)
+    out["ring_working_set_mb"] = ws / 1e6
+    out["working_set_exceeds_l2"] = bool(ws > L2_BYTES)
+    return out
+
+
+def large_batch_roofline(env, hbm_peak, name, seed):
+    """The embedding kernels at a batch large enough to be bandwidth- rather than launch-latency-bound (cfg4 shapes: B=16384, D=64,
+    10 M keys), for zipf AND uniform keys, over a ring of non-repeating batches whose rows exceed L2."""
+    ps, torch = env.ps, env.torch
+    out = {"peak": hbm_peak, "unit": "GB/s"}
+    for dist_name in ("zipf", "uniform"):
+        cfg = dict(CONFIGS[name])
+        saved = env.args.dist
+        env.args.dist = dist_name
+        try:
+            wl = Workload(env, name, cfg, ring=8, seed_off=77)
+        finally:
+            env.args.dist = saved
+        for _ in range(2):                       # create the ring's keys, reach the steady state of the table
+            for i in range(len(wl.dev_ring)):
+                wl.dev_step(i)
+        wl.model.read_loss()
+        r = emb_rooflines(env, wl, hbm_peak, reps=32)
+        r["workload"] = f"{name} shapes: B={cfg['B']} F={cfg['F']} D={cfg['D']} vocab={cfg['V']} keys={dist_name}, {r['unique_keys_per_batch']:.0f} unique keys/batch"
+        out[dist_name] = r
+        wl.close()
+    return out
+
+
+def tf32_ceiling(env):
+    """cuBLAS TF32 GEMM 8192^3 (reference only — the denominator of the FcLayer roofline; BASELINE.md §2 asks for it)."""
+    torch = env.torch
+    torch.backends.cuda.matmul.allow_tf32 = True
+    n = 8192
+    a = torch.randn(n, n, device=f"cuda:{env.local_rank}")
+    b = torch.randn(n, n, device=f"cuda:{env.local_rank}")
+    for _ in range(3):
+        torch.matmul(a, b)
+    best = 1e9
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(10):
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def gemm_report(wl, tf32_peak, mma_per_product):
+    cfg, B = wl.cfg, wl.B
+    gt = wl.model.gemm_times(B, reps=64)
+    dims = [cfg["F"] * cfg["D"] + cfg["Xn"]] + list(cfg["fc"])
+    out = {}
+    for l in range(len(cfg["fc"])):
+        for n in ("forward", "dgrad", "wgrad"):
+            us = gt[f"fc{l}.{n}"]
+            fl = 2.0 * B * dims[l] * dims[l + 1]
+            out[f"fc{l}.{n}"] = {"us": us, "tflops_fp32_equiv": fl / max(us, 1e-3) / 1e6, "mma_tflops": mma_per_product * fl / max(us, 1e-3) / 1e6,
+                                 "frac_of_tf32_peak": (mma_per_product * fl / max(us, 1e-3) / 1e6) / tf32_peak if dims[l + 1] > 1 else None}
+    return out
+
+
+def parity_check(env, cfg, steps=2):
+    """N-rank result == oracle(thread = 1, concatenated batch): PServer sync-mode semantics (PServer.java:164-214)."""
+    ps, torch, dist = env.ps, env.torch, env.dist
+    import oracle_lib as ol
+    world, rank = env.world, env.rank
+    Np = min(cfg["B"], 1024)
+    pcfg = dict(cfg, B=Np)
+    F, D, Xn, fc = cfg["F"], cfg["D"], cfg["Xn"], cfg["fc"]
+    model = ps.Model(env.ctx, cfg["kind"], F, D, Xn, fc, emb_capacity=1 << 18, emb_updater=ps.UpdaterSpec.ftrl() if cfg["emb_opt"] == "ftrl" else None, max_batch=Np)
+    trainer = None
+    if env.sharded:
+        from ps_b200.sharded import GpuOps, GraphedShardedTrainer, P2PShardedTrainer
+        if env.args.exchange == "p2p":
+            trainer = P2PShardedTrainer(ps, env.ctx, model, rank, world, Np, F, slack=3.0, device=env.local_rank)
+        else:
+            trainer = GraphedShardedTrainer(GpuOps(ps, env.ctx, model, env.local_rank), rank, world, Np, F, cfg["kind"] == "widedeep", slack=3.0)
+    syn = Synth(F=F, Xn=Xn, V=min(cfg["V"], 200000), dist="zipf", seed=4242)
+    batches = [syn.batch(world * Np) for _ in range(steps)]
+    losses = []
+    for b in batches:
+        sl = slice(rank * Np, (rank + 1) * Np)
+        if trainer is None:
+            losses.append(model.train_step(b.get("E")[sl] if F else None, b["X"][sl], b.get("W")[sl] if cfg["kind"] == "widedeep" else None, b["Y"][sl]))
+        else:
+            d = {k: torch.from_numpy(np.ascontiguousarray(v[sl])).cuda(env.local_rank) for k, v in b.items()}
+            trainer.step(d.get("E"), d["X"], d.get("W") if cfg["kind"] == "widedeep" else None, d["Y"])
+            losses.append(model.read_loss())
+    if trainer is not None:
+        trainer.check()
+    # sampled embedding keys of the last batch: each lives on exactly one rank
+    keys = []
+    if F:
+        b = batches[-1]
+        stride = max(1, (world * Np * F) // 400)
+        flat = [(n, j) for n in range(world * Np) for j in range(F)][::stride][:400]
+        keys = sorted({ol.key_string(0, j, int(b["E"][n, j])) for n, j in flat})
+    mine = {}
+    for k in keys:
+        w = model.get(k)
+        if w is not None:
+            mine[k] = w
+    dense = {f"fc{l}.weights": model.get(f"fc{l}.weights") for l in range(len(fc))}
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+    else:
+        gathered = [mine]
+    model.close()
+    if rank != 0:
         return None
+    o = oracle_model(pcfg, 20261017)
+    lo = [o.train_step(b.get("E"), b["X"], b.get("W") if cfg["kind"] == "widedeep" else None, b["Y"]) for b in batches]
+    loss_err = max(abs(a - b) / max(1e-12, abs(b)) for a, b in zip(losses, lo))
+    tol_loss, tol_rows = (1e-4, 2e-3) if env.args.precision != "tf32" else (2e-3, 5e-2)
+    rows, dup, rels = 0, 0, []
+    seen = set()
+    for g in gathered:
+        for k, w in g.items():
+            dup += k in seen
+            seen.add(k)
+            wo = o.get(k)
+            rows += 1
+            rels.append(float(np.abs(w - wo).max() / max(1e-6, float(np.abs(wo).max()))))
+    rels = np.sort(np.asarray(rels)) if rels else np.zeros(1)
+    # Adam's first steps move an element by ~alfa * sign(g) whatever |g| is: a gradient element within rounding of zero can
+    # flip sign against the oracle's summation order and cost 2 * alfa on that element — tolerated on <= 1 % of the rows
+    outside = int((rels > tol_rows).sum())
+    max_rel = float(rels[-1])
+    dense_rel = max(float(np.abs(v - o.get(k)).max() / max(1e-12, float(np.abs(o.get(k)).max()))) for k, v in dense.items())
+    ok = (loss_err <= tol_loss and outside <= max(1, rows // 100) and max_rel <= 2e-2 and dense_rel <= 5 * tol_rows
+          and rows >= min(200, len(keys)) and rows == len(keys) and dup == 0)
+    return {"ok": bool(ok), "loss_err": loss_err, "rows_checked": rows, "rows_sampled": len(keys), "max_rel": max_rel, "rows_outside_tol": outside,
+            "median_rel": float(rels[len(rels) // 2]), "dense_max_rel": dense_rel,
+            "keys_on_two_shards": dup, "steps": steps, "global_batch": world * Np, "tolerance": {"loss_rel": tol_loss, "rows_rel_to_max": tol_rows},
+            "against": "CPU oracle, one Trainer step (thread = 1) per global batch on the concatenated batch"}
+
+
+def extra_config(env, name, K, warmup):
+    cfg = dict(CONFIGS[name])
+    wl = Workload(env, name, cfg, ring=4, seed_off=300)
+    wl.prepare()
+    v = wl.time_value(K, max(3, warmup), reps=7)
+    e = wl.time_e2e(K, max(3, warmup), reps=5)
+    wl.check()
+    total = cfg["B"] * env.world * K
+    out = {"workload": workload_name(env.args, cfg, name), "global_batch": cfg["B"] * env.world, "value": total / (v["ms"] / 1e3), "unit": UNIT,
+           "ms_per_step": v["ms"] / K, "e2e": total / (e["ms"] / 1e3), "reps": [v["reps"], e["reps"]], "loss": v["loss"],
+           "table_rows_capacity_per_gpu": wl.cap, "table_gb_per_gpu": wl.cap * (16 + 12 * ((cfg["D"] + 3) // 4 * 4)) / 1e9}
+    wl.close()
+    return out
+
+
+def time_ingest(env, cfg, batch, threads):
+    """libsvm text → training: (a) the native host reader on `threads` host cores; (b) ps_model_submit_text — the raw text
+    is copied to the GPU, parsed THERE and trained on in the same submission (DataSet.next + Trainer.train, DataSet.java:77-100)."""
+    import tempfile
+    ps = env.ps
+    F, Xn, B = cfg["F"], cfg["Xn"], cfg["B"]
+    if not F or cfg["kind"] != "widedeep":
+        return None
+    rows = min(B, 4096)
     lines = []
-    for n in range(min(B, 4096)):
+    for n in range(rows):
         cols = ["%d" % int(batch["Y"][n])] + ["%d:1" % int(batch["E"][n, j]) for j in range(F)] + ["%d:%.2f" % (33895 + x, batch["X"][n, x]) for x in range(Xn)]
         lines.append(" ".join(cols))
-    with tempfile.NamedTemporaryFile("w", suffix=".libsvm", delete=False) as f:
-        f.write("\n".join(lines) + "\n")
+    text = ("\n".join(lines) + "\n").encode()
+    out = {"bytes_per_line": len(text) / rows}
+    with tempfile.NamedTemporaryFile("wb", suffix=".libsvm", delete=False) as f:
+        f.write(text)
         path = f.name
     try:
-        r = ps.LibsvmReader(path, F=F, Xn=Xn, batch=len(lines), threads=threads)
-        bufs = dict(E=np.empty((len(lines), F), np.int64), W=np.empty((len(lines), F), np.int64), X=np.empty((len(lines), Xn), np.float32), Y=np.empty(len(lines), np.float32))
+        r = ps.LibsvmReader(path, F=F, Xn=Xn, batch=rows, threads=threads)
+        bufs = dict(E=np.empty((rows, F), np.int64), W=np.empty((rows, F), np.int64), X=np.empty((rows, Xn), np.float32), Y=np.empty(rows, np.float32))
         n, t0 = 0, time.perf_counter()
         while time.perf_counter() - t0 < 1.0:
             b = r.next(bufs)
@@ -201,69 +607,36 @@ def time_ingest(ps, cfg, batch, threads):
                 continue
             n += len(b["Y"])
         dt = time.perf_counter() - t0
-        ok = bool(np.array_equal(bufs["E"][: len(lines)], batch["E"][: len(lines)]) and np.array_equal(bufs["X"][: len(lines)], batch["X"][: len(lines)]))
+        ok = bool(np.array_equal(bufs["E"][:rows], batch["E"][:rows]) and np.array_equal(bufs["X"][:rows], batch["X"][:rows]))
         r.close()
-        return {"lines_per_s": n / dt, "threads": threads, "bytes_per_line": os.path.getsize(path) / len(lines), "roundtrip_exact": ok,
-                "sample": f"{n} lines of {len(lines)}-line synthetic libsvm text in {dt:.2f}s through ps_reader_next"}
+        out["host_reader"] = {"lines_per_s": n / dt, "threads": threads, "roundtrip_exact": ok}
     finally:
         os.unlink(path)
-
-
-def run_reference(args, cfg, rank):
-    if rank != 0:
-        return
-    syn = Synth(F=cfg["F"], Xn=cfg["Xn"], V=cfg["V"], dist=args.dist, seed=20261017 + 2)
-    batches = [syn.batch(cfg["B"]) for _ in range(4)]
-    threads = os.cpu_count() or 1
-    per_step_budget = 4.0
-    total = args.steps + args.warmup
-    sps, n, gemm, dt = time_oracle_replicas(cfg, batches, min(60.0, per_step_budget * total), threads)
-    line = {
-        "impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * cfg["B"] / sps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": workload_name(args, cfg), "global_batch": cfg["B"]},
-        "cpu_baseline": {"value": sps, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{n} Trainer steps of batch {cfg['B']} in {dt:.1f}s over {threads} independent replicas (one per host thread, thread=1 each): "
-                                   f"an upper bound for the reference's Trainer with thread={threads}, which shares one synchronized KVStore; C++ restatement of the "
-                                   f"reference's standalone Java path (JVM/jblas unavailable in this image); sgemm={gemm}"},
-        "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
-    print(json.dumps(line), flush=True)
-
-
-def large_batch_roofline(ps, ctx, dev, hbm_peak, name, seed):
-    """The embedding kernels at a batch large enough to be bandwidth- rather than launch-latency-bound (cfg4 shapes:
-    B=16384, D=64, 10 M keys): same kernels, same measurement (replayed in a CUDA graph, CUDA events on the library's stream)."""
-    import torch
-    cfg = dict(CONFIGS[name])
-    B, F, D, Xn, V = cfg["B"], cfg["F"], cfg["D"], cfg["Xn"], cfg["V"]
-    model = ps.Model(ctx, cfg["kind"], F, D, Xn, cfg["fc"], emb_capacity=2 * V + (1 << 16), max_batch=B)
-    syn = Synth(F=F, Xn=Xn, V=V, dist="zipf", seed=seed)
-    ring = [syn.batch(B) for _ in range(8)]
-    dev_ring = [{k: torch.from_numpy(np.ascontiguousarray(v)).cuda(dev) for k, v in b.items()} for b in ring]
-    torch.cuda.synchronize()
-
-    def p(t):
-        return C.c_void_p(t.data_ptr()) if t is not None else None
-    for _ in range(2):                       # create the ring's keys, reach the steady state of the table
-        for d in dev_ring:
-            model.train_step_dev(p(d.get("E")), p(d["X"]), p(d.get("W")), p(d["Y"]), B)
-    model.read_loss()
-    kt = model.kernel_times([d["E"].data_ptr() for d in dev_ring], B, reps=32)
-    L = B * F
-    uniq = float(np.mean([len(np.unique(b["E"])) for b in ring]))
-    out = {"workload": f"{name} shapes: B={B} F={F} D={D} vocab={V} zipf, {uniq:.0f} unique keys/batch", "peak": hbm_peak, "unit": "GB/s"}
-    for k, bytes_ in {"emb_gather": L * (8 + 8 * D), "emb_scatter_update": L * (8 + 4 * D) + uniq * 24 * D}.items():
-        us = kt[k] + (kt["emb_probe"] if k == "emb_gather" else 0.0)
-        out[k] = {"us": us, "alg_bytes": bytes_, "gbs": bytes_ / max(us, 1e-3) / 1e3, "frac": bytes_ / max(us, 1e-3) / 1e3 / hbm_peak}
-    out["emb_probe_us"] = kt["emb_probe"]
+    # text → train on the GPU
+    model = ps.Model(env.ctx, cfg["kind"], F, cfg["D"], Xn, cfg["fc"], emb_capacity=1 << 20, max_batch=rows)
+    buf = ps.PinnedArray((len(text),), np.uint8)
+    buf.array[:] = np.frombuffer(text, np.uint8)
+    for i in range(4):
+        model.submit_text(buf.ptr, len(text), rows)
+        if i >= 1:
+            model.collect()
+    model.collect()
+    info = model.step_info()
+    steps = 200
+    env.ctx.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        model.submit_text(buf.ptr, len(text), rows)
+        if i >= 1:
+            model.collect()
+    model.collect()
+    env.ctx.synchronize()
+    dt = time.perf_counter() - t0
+    out["text_to_train"] = {"lines_per_s": steps * rows / dt, "api": "ps_model_submit_text / ps_model_collect (2 steps in flight): H2D of the raw text, GPU parse, train step",
+                            "h2d_bytes_per_step": len(text), "bad_lines": info["bad_lines"], "skipped": info["skipped"], "batch": rows}
+    buf.free()
     model.close()
     return out
-
-
-def workload_name(args, cfg):
-    return (f"{args.config}: {cfg['kind']} synthetic Criteo-libsvm, F={cfg['F']} Xn={cfg['Xn']} D={cfg['D']} vocab={cfg['V']} "
-            f"fc={cfg['fc']} batch={cfg['B']}/GPU emb_opt={cfg['emb_opt']} keys={args.dist}")
 
 
 def main():
@@ -274,260 +647,159 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--config", default="cfg2")
     ap.add_argument("--dist", default="zipf")
-    # FcLayer arithmetic: tf32x3 = tcgen05 tensor cores with error-compensated operand split (fp32-grade results, the
+    # FcLayer arithmetic: tf32x3 = tcgen05 tensor cores with error-compensated operand split (fp32-grade results, the library
     # default: the reference computes in fp32); tf32 = plain TF32 tensor cores; fp32 = FFMA exact mode
     ap.add_argument("--precision", default=os.environ.get("PS_FC_PRECISION", "tf32x3"))
-    ap.add_argument("--cpu-budget", type=float, default=15.0)
-    ap.add_argument("--ring", type=int, default=16)
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--ring", type=int, default=64)
     ap.add_argument("--slack", type=float, default=2.0)
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
     ap.add_argument("--force-sharded", action="store_true", help="use the sharded step even with one rank (profiling)")
     ap.add_argument("--large", default="cfg4", help="shapes for the large-batch embedding roofline ('' = skip)")
-    ap.add_argument("--no-kernel-times", action="store_true", help="skip the per-kernel replays (ncu runs: only the step's own launches)")
+    ap.add_argument("--extra", default="cfg3,cfg4", help="further BASELINE configs measured at this N ('' = skip)")
+    ap.add_argument("--no-kernel-times", action="store_true", help="skip the per-kernel replays and side measurements (ncu runs: only the step's own launches)")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--reps", type=int, default=0, help="repetitions of the K-step loop (0 = at least 25 and at least 1 s)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
         import __graft_entry__ as g
         if rank == 0:
             g.build()
-            run_reference(args, cfg, rank)
+            run_reference(args, cfg)
         return
 
-    import torch
-    import torch.distributed as dist
-    import __graft_entry__ as g
-    if local_rank == 0:
-        g.build()
-    if world > 1 or args.force_sharded:
-        if world == 1:
-            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-            os.environ.setdefault("MASTER_PORT", "29533")
-            dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", local_rank))
-        else:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        dist.barrier()
-    from ps_b200 import binding as ps
-
-    torch.cuda.set_device(local_rank)
-    B, F, D, Xn = cfg["B"], cfg["F"], cfg["D"], cfg["Xn"]
-    ctx = ps.Context(local_rank, seed=20261017)
-    ctx.set_fc_precision({"fp32": ps.PS_FC_FP32, "tf32": ps.PS_FC_TF32, "tf32x3": ps.PS_FC_TF32X3}[args.precision])
-    cap = int(min(2 ** 31 - 1, max(1 << 16, (2 * cfg["V"]) // world + (1 << 16)))) if cfg["V"] else 1024
-    upd = ps.UpdaterSpec.ftrl() if cfg["emb_opt"] == "ftrl" else None
-    model = ps.Model(ctx, cfg["kind"], F, D, Xn, cfg["fc"], emb_capacity=cap, emb_updater=upd, max_batch=B)
-
-    syn = Synth(F=F, Xn=Xn, V=cfg["V"], dist=args.dist, seed=20261017 + 2 + 1000 * rank, n_classes=10 if cfg["kind"] == "fcnn" else 0)
-    ring = [syn.batch(B) for _ in range(args.ring)]
-    stream = torch.cuda.ExternalStream(ctx.stream(), device=local_rank)
-
-    def to_dev(b):
-        d = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda(local_rank) for k, v in b.items()}
-        return d
-    dev_ring = [to_dev(b) for b in ring]
-    torch.cuda.synchronize()
-
-    def ptr(t):
-        return C.c_void_p(t.data_ptr()) if t is not None else None
-
-    # N > 1: the embedding table is sharded by key hash over the ranks and the R ranks perform ONE
-    # Trainer step on the concatenated batch (ps_b200/sharded.py); per-GPU batch fixed => weak scaling
-    trainer = None
-    if world > 1 or args.force_sharded:
-        from ps_b200.sharded import GpuOps, GraphedShardedTrainer, P2PShardedTrainer
-        if args.exchange == "p2p":
-            # every exchange is a store into the consumer's HBM over NVLink by the kernel that produced the data
-            trainer = P2PShardedTrainer(ps, ctx, model, rank, world, B, F, slack=args.slack, device=local_rank)
-        else:
-            # the whole sharded step (local kernels + NCCL collectives, fixed-capacity buckets) is one CUDA graph per rank
-            trainer = GraphedShardedTrainer(GpuOps(ps, ctx, model, local_rank), rank, world, B, F, cfg["kind"] == "widedeep", slack=args.slack)
-
-    def dev_step(i):
-        d = dev_ring[i % len(dev_ring)]
-        if trainer is not None:
-            return trainer.step(d.get("E"), d["X"], d.get("W"), d["Y"])
-        model.train_step_dev(ptr(d.get("E")), ptr(d["X"]), ptr(d.get("W")), ptr(d["Y"]), B)
-
-    def barrier():
-        ctx.synchronize()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    # ---- device-resident throughput ("value") ----
-    for i in range(args.warmup):
-        dev_step(i)
-    loss = model.read_loss()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    l0 = ctx.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for i in range(args.steps):
-        dev_step(args.warmup + i)
-    e1.record(stream)
-    loss = model.read_loss()
-    barrier()
-    ms_dev = e0.elapsed_time(e1)
-    launches = ctx.launch_count() - l0
-    if trainer is not None:
-        if hasattr(trainer, "launches_per_step"):
-            launches = args.steps * trainer.launches_per_step               # torch graph replays: counted at the eager warm-up step
-    if world > 1:
-        t = torch.tensor([ms_dev], device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_dev = float(t.item())
-
-    # ---- end-to-end through the host-facing call ("e2e") ----
-    pinned = []
-    for b in ring:
-        pb = {}
-        for k, v in b.items():
-            pa = ps.PinnedArray(v.shape, v.dtype)
-            pa.array[...] = v
-            pb[k] = pa
-        pinned.append(pb)
-
-    def hp(pb, k):
-        return pb[k].ptr if k in pb else None
-    h2d = sum(pa.nbytes for pa in pinned[0].values())
-
-    def host_loop(n, start):
-        if trainer is not None and args.exchange == "p2p":
-            # peer-memory sharded step through its host-facing call: ps_model_p2p_submit copies this rank's slice from pinned host
-            # memory and enqueues the step's graph, ps_model_collect returns the global loss of the oldest of 2 steps in flight
-            for i in range(n):
-                pb = pinned[(start + i) % len(pinned)]
-                model.p2p_submit_ptrs(hp(pb, "E"), hp(pb, "X"), hp(pb, "W"), hp(pb, "Y"), B)
-                if i >= 1:
-                    model.collect()
-            return model.collect()
-        if trainer is not None:      # NCCL sharded step: stage this rank's slice from pinned host memory, then the step, then its loss
-            last = None
-            for i in range(n):
-                pb = pinned[(start + i) % len(pinned)]
-                with torch.cuda.stream(stream):
-                    d = {k: torch.from_numpy(pa.array).to(f"cuda:{local_rank}", non_blocking=True) for k, pa in pb.items()}
-                trainer.step(d.get("E"), d["X"], d.get("W"), d["Y"])
-                last = model.read_loss()                       # the step's result is read back every step
-            return last
-        for i in range(n):
-            pb = pinned[(start + i) % len(pinned)]
-            model.submit_ptrs(hp(pb, "E"), hp(pb, "X"), hp(pb, "W"), hp(pb, "Y"), B)
-            if i >= 1:
-                model.collect()
-        return model.collect()
-    host_loop(max(3, args.warmup), 0)
-    barrier()
-    t0 = time.perf_counter()
-    loss_e2e = host_loop(args.steps, args.warmup)
-    ctx.synchronize()
-    t1 = time.perf_counter()
-    ms_e2e = (t1 - t0) * 1e3
-    if world > 1:
-        t = torch.tensor([ms_e2e], device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
-    clocks = sampler.summary()
-    if trainer is not None:
-        trainer.check()
-
-    # ---- per-kernel device times and the roofline of the dominant HBM-bound kernel ----
-    acc = {}
-    reps = 20 if (world == 1 and trainer is None and not args.no_kernel_times) else 0
-    if reps:
-        model.profile(True)
-    for i in range(reps):
-        dev_step(i)
-        model.read_loss()
-        for k, v in model.phase_times().items():
-            acc.setdefault(k, []).append(v)
-    model.profile(False)
-    phase_us = {k: 1e3 * float(np.median(v)) for k, v in acc.items()}
-    L = B * F
-    uniq = float(np.mean([len(np.unique(b["E"] + (np.arange(F, dtype=np.int64) << 44)[None, :])) for b in ring])) if F else 0.0
+    env = Env(args)
+    world, B, F, D = env.world, cfg["B"], cfg["F"], cfg["D"]
+    side = not args.no_kernel_times
     hbm_peak, peak_src = peaks()
-    kernels, roofline = {}, None
-    if F and world == 1 and trainer is None and not args.no_kernel_times:
-        # each embedding kernel replayed 64x inside a CUDA graph over the batch ring, CUDA events on the library's stream
-        kt = model.kernel_times([d["E"].data_ptr() for d in dev_ring], B, reps=64)
-        alg = {"emb_gather": L * (8 + 8 * D), "emb_scatter_update": L * (8 + 4 * D) + uniq * 24 * D}
-        for k, bytes_ in alg.items():
-            us = kt[k] + (kt["emb_probe"] if k == "emb_gather" else 0.0)     # the gather's key resolution is the probe kernel
-            kernels[k] = {"us": us, "alg_bytes": bytes_, "gbs": bytes_ / max(us, 1e-3) / 1e3}
-        kernels["emb_probe"] = {"us": kt["emb_probe"]}
-        gt = model.gemm_times(B, reps=64)
-        flops = {}
-        dims = [F * D + Xn] + list(cfg["fc"])
-        for l in range(len(cfg["fc"])):
-            for n in ("forward", "dgrad", "wgrad"):
-                us = gt[f"fc{l}.{n}"]
-                kernels[f"fc{l}.{n}"] = {"us": us, "tflops": 2.0 * B * dims[l] * dims[l + 1] / max(us, 1e-3) / 1e6}
-        dom = max(alg, key=lambda k: kernels[k]["us"])
-        traffic = None                      # dram__bytes_read+write per launch from the committed ncu --set full capture
-        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tp) and args.config == "cfg2":
-            tk = json.load(open(tp))["kernels"]      # emb_scatter_update = the scatter launch + the update launch; gather includes its probe
-            parts = {"emb_gather": ["emb_probe_kernel", "emb_gather_kernel"], "emb_scatter_update": ["emb_scatter_kernel", "emb_update_kernel"]}[dom]
-            traffic = sum(tk[p]["dram_bytes_per_launch"] for p in parts) if all(p in tk for p in parts) else None
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": kernels[dom]["gbs"] / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                    "how": "algorithmic bytes (SURVEY 8d) / mean device time of the kernel replayed 64x in a CUDA graph over the batch ring "
-                           "(CUDA events on the library's stream); emb_gather includes its probe kernel"}
 
-    large = None
-    if roofline is not None and args.large:
-        large = large_batch_roofline(ps, ctx, local_rank, hbm_peak, args.large, 20261017 + 4)
+    # ---- the headline workload ----
+    wl = Workload(env, args.config, cfg, ring=args.ring)
+    wl.prepare()
+    sampler = ClockSampler(env.local_rank)
+    sampler.start()
+    v = wl.time_value(args.steps, args.warmup, reps=args.reps or None)
+    e = wl.time_e2e(args.steps, args.warmup, reps=args.reps or None)
+    clocks = sampler.summary()
+    wl.check()
+
+    # ---- per-kernel device times and rooflines (one GPU, local step) ----
+    kernels, roofline, roofline_tensor, large, tf32_peak, phase_us, cfg5 = {}, None, None, None, None, {}, None
+    if side and world == 1 and wl.trainer is None:
+        acc = {}
+        wl.model.profile(True)
+        for i in range(20):
+            wl.dev_step(i)
+            wl.model.read_loss()
+            for k, t in wl.model.phase_times().items():
+                acc.setdefault(k, []).append(t)
+        wl.model.profile(False)
+        phase_us = {k: 1e3 * float(np.median(t)) for k, t in acc.items()}
+        tf32_peak = tf32_ceiling(env)
+        mma_per = {"fp32": 0, "tf32": 1, "tf32x3": 3}[args.precision]
+        if F:
+            kernels = emb_rooflines(env, wl, hbm_peak, reps=64)
+            dom = max(("emb_lookup", "emb_scatter_update"), key=lambda k: kernels[k]["us"])
+            traffic = None                  # dram__bytes_read+write per launch from the committed ncu --set full capture of this round
+            tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
+            if os.path.exists(tp) and args.config == "cfg2":
+                tk = json.load(open(tp)).get("kernels", {})
+                parts = {"emb_lookup": ["emb_lookup_kernel"], "emb_scatter_update": ["emb_scatter_kernel", "emb_update_kernel"]}[dom]
+                traffic = sum(tk[p]["dram_bytes_per_launch"] for p in parts) if all(p in tk for p in parts) else None
+            roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
+                        "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                        "how": "algorithmic bytes (SURVEY 8d) / mean device time of the kernel(s) replayed 64x in a CUDA graph over the batch ring "
+                               "(CUDA events on the library's stream); emb_lookup = key resolution + gather in one kernel; emb_scatter_update = "
+                               "the scatter launch + its programmatic dependent, the update launch"}
+        gk = gemm_report(wl, tf32_peak, max(mma_per, 1))
+        kernels.update(gk)
+        big = max((k for k in gk if gk[k]["frac_of_tf32_peak"] is not None), key=lambda k: gk[k]["us"])
+        roofline_tensor = {"bound": "tensor", "kernel": f"gemm_tf32_kernel ({big})", "achieved": gk[big]["mma_tflops"], "peak": tf32_peak, "unit": "TFLOP/s",
+                           "frac": gk[big]["frac_of_tf32_peak"], "fp32_equivalent_tflops": gk[big]["tflops_fp32_equiv"],
+                           "peak_source": "cuBLAS TF32 8192^3 (torch.matmul, allow_tf32), best of 10, measured in this run",
+                           "how": f"{max(mma_per, 1)} TF32 MMAs per product ({args.precision}); device time of the GEMM replayed 64x in a CUDA graph"}
+        if args.large:
+            large = large_batch_roofline(env, hbm_peak, args.large, 20261017 + 4)
+        c5 = dict(CONFIGS["cfg5"])
+        w5 = Workload(env, "cfg5", c5, ring=4, seed_off=500)
+        w5.prepare()
+        v5 = w5.time_value(min(args.steps, 50), 3, reps=7)
+        cfg5 = {"workload": workload_name(args, c5, "cfg5"), "value": c5["B"] * min(args.steps, 50) / (v5["ms"] / 1e3), "ms_per_step": v5["ms"] / min(args.steps, 50),
+                "gemms": gemm_report(w5, tf32_peak, max(mma_per, 1))}
+        w5.close()
+
+    ingest = None
+    if side and world == 1 and wl.trainer is None and rank == 0:
+        try:
+            ingest = time_ingest(env, cfg, wl.ring[0], min(16, os.cpu_count() or 1))
+        except Exception as ex:        # host-side plumbing: never fail the bench line over it
+            ingest = {"error": str(ex)}
+
+    uniq, ring_unique = wl.unique_stats()
+    loss_value = v["loss"]
+    wl_cap = wl.cap
+    wl_ring = len(wl.ring)
+    ring0 = wl.ring[:4]
+    wl.close()
+
+    # ---- parity at this N, then the other BASELINE configs at this N ----
+    parity = None
+    if not args.no_parity:
+        parity = parity_check(env, cfg)
+    extras = {}
+    if side and args.extra:
+        for name in [x for x in args.extra.split(",") if x]:
+            try:
+                extras[name] = extra_config(env, name, min(args.steps, 20), 3)
+            except Exception as ex:
+                extras[name] = {"error": str(ex)}
+                if world > 1:
+                    raise                 # ranks must not diverge inside a sharded step
 
     if rank == 0:
         cpu = None
-        if world == 1:
-            sps, n, gemm, dt = time_oracle(cfg, ring[:4], args.cpu_budget, 1)
+        if world == 1 and side:
+            sps, n, gemm, dt = time_oracle_replicas(cfg, ring0, args.cpu_budget, 1)
             cpu = {"value": sps, "unit": UNIT, "cores": 1, "kind": "port",
                    "sample": f"{n} Trainer steps of batch {B} in {dt:.1f}s, thread=1 (CTR.java:72); C++ restatement of the reference's standalone "
-                             f"Java path (no JVM in this image); sgemm={gemm} single-threaded"}
-        ingest = None
-        if world == 1 and trainer is None:
-            try:
-                ingest = time_ingest(ps, cfg, ring[0], min(16, os.cpu_count() or 1))
-            except Exception as e:        # the reader is host-side plumbing: never fail the bench line over it
-                ingest = {"error": str(e)}
+                             f"Java path (no JVM in this image); sgemm={gemm}"}
         total = B * world * args.steps
+        Dp = (D + 3) // 4 * 4
         line = {
-            "metric": METRIC, "value": total / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": total / (v["ms"] / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": v["ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "f32 via 3xTF32 tcgen05"}[args.precision], "data": "synthetic",
-            "config": {"workload": workload_name(args, cfg), "global_batch": B * world,
-                       "parallelism": (f"key-hash sharded embedding table over {world} GPUs, exchange={args.exchange} "
-                                       f"({'NVLink peer-memory stores, no collective calls' if args.exchange == 'p2p' else 'NCCL all-to-all'}) "
-                                       "+ data-parallel dense") if world > 1 else "single",
-                       "l2": "embedding table + optimiser state (%.0f MB) exceeds the 126 MB L2; a ring of %d distinct batches; no flush" % (
-                           cap * (16 + 12 * D) / 1e6, len(ring))},
-            "e2e": {"value": total / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
-                    "api": "ps_model_submit/ps_model_collect (2 steps in flight)" if trainer is None else
+            "config": {"workload": workload_name(args, cfg), "global_batch": B * world},
+            "config_detail": {
+                "parallelism": (f"key-hash sharded embedding table over {world} GPUs, exchange={args.exchange} "
+                                f"({'NVLink peer-memory stores with in-kernel flags, no collective calls' if args.exchange == 'p2p' else 'NCCL all-to-all'}) "
+                                "+ data-parallel dense") if world > 1 else "single",
+                "l2": ("a ring of %d distinct batches per GPU touching %.0f MB of table rows + slot records (%s the 126 MB L2); table %.0f MB; no flush" % (
+                    wl_ring, ring_unique * (12 * Dp + 16) / 1e6, "exceeds" if ring_unique * (12 * Dp + 16) > L2_BYTES else "FITS IN", wl_cap * (16 + 12 * Dp) / 1e6)),
+                "timing": "every ring batch stepped once untimed (graph capture, key inserts), then --warmup steps, then the K-step loop repeated; median repetition reported",
+            },
+            "timing": {"value_reps": v["reps"], "value_ms_min_med_max": [v["ms_min"], v["ms"], v["ms_max"]],
+                       "e2e_reps": e["reps"], "e2e_ms_min_med_max": [e["ms_min"], e["ms"], e["ms_max"]],
+                       "timed_region_s": (v["ms"] * v["reps"] + e["ms"] * e["reps"]) / 1e3},
+            "e2e": {"value": total / (e["ms"] / 1e3), "unit": UNIT, "h2d_bytes_per_step": e["h2d"], "d2h_bytes_per_step": 32,
+                    "api": "ps_model_submit/ps_model_collect (2 steps in flight)" if not env.sharded else
                            "ps_model_p2p_submit/ps_model_collect (2 steps in flight)" if args.exchange == "p2p" else
                            "pinned host batch -> device (async copy on the step's stream) -> sharded step -> ps_model_read_loss, every step"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_large_batch": large, "kernels_us": phase_us, "hbm_kernels": kernels,
-            "cpu_baseline": cpu, "ingest": ingest, "loss": loss, "loss_e2e": loss_e2e, "unique_keys_per_batch": uniq,
+            "gpu_launches": int(round(v["launches"])), "clocks": clocks, "roofline": roofline, "roofline_tensor": roofline_tensor,
+            "roofline_large_batch": large, "tf32_peak_tflops": tf32_peak, "kernels_us": phase_us, "hbm_kernels": kernels, "cfg5": cfg5,
+            "parity": parity, "extra_configs": extras,
+            "cpu_baseline": cpu, "ingest": ingest, "loss": loss_value, "loss_e2e": e["loss"], "unique_keys_per_batch": uniq,
         }
         print(json.dumps(line), flush=True)
     sys.stdout.flush()
-    if world > 1 or trainer is not None:
-        # captured NCCL graphs + communicator teardown order is fragile: everything is measured and printed, leave hard
-        ctx.synchronize()
-        torch.cuda.synchronize()
-        dist.barrier()
+    if env.sharded:
+        # captured graphs + communicator teardown order is fragile: everything is measured and printed, leave hard
+        env.barrier()
         os._exit(0)
-    for pb in pinned:
-        for pa in pb.values():
-            pa.free()
-    model.close()
-    ctx.close()
+    env.ctx.close()
 
 
 if __name__ == "__main__":

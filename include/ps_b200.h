@@ -71,7 +71,10 @@ int ps_abi_version(void);
  * `seed` keys the deterministic replacement of the unseeded MatrixUtil.rand (ps_spec.h). */
 int ps_ctx_create(int device, uint64_t seed, ps_ctx** out);
 int ps_ctx_destroy(ps_ctx* ctx);
+/* FcLayer arithmetic (FcLayer.java:76,105,108).  Default PS_FC_TF32X3: tcgen05 tensor cores with the error-compensated operand
+ * split (fp32-grade results: the reference computes in fp32).  PS_FC_TF32: plain TF32 tensor cores; PS_FC_FP32: FFMA exact mode. */
 int ps_ctx_set_fc_precision(ps_ctx* ctx, int mode);   /* PS_FC_FP32 | PS_FC_TF32 | PS_FC_TF32X3 */
+int ps_ctx_get_fc_precision(ps_ctx* ctx, int* mode);
 /* the sparse (embedding-row) update: 0 = fast forms (reciprocal multiplications, approximate quotient / root; post-update
  * rows within 1e-6 relative of the exact forms), 1 = the IEEE operation sequence of AdamUpdater.java:57-70 /
  * FtrlUpdater.java:51-76 (bit-exact given the gradient).  Dense parameters always use the exact forms.  Default 0

@@ -53,6 +53,7 @@ SYMBOLS = {
     "ps_ctx_create": (_i, [_i, C.c_uint64, _pp]),
     "ps_ctx_destroy": (_i, [_vp]),
     "ps_ctx_set_fc_precision": (_i, [_vp, _i]),
+    "ps_ctx_get_fc_precision": (_i, [_vp, C.POINTER(_i)]),
     "ps_ctx_set_exact_updaters": (_i, [_vp, _i]),
     "ps_ctx_synchronize": (_i, [_vp]),
     "ps_ctx_launch_count": (_i, [_vp, C.POINTER(_i64)]),
@@ -296,6 +297,11 @@ class Context:
 
     def set_fc_precision(self, mode):
         check(lib().ps_ctx_set_fc_precision(self.h, mode))
+
+    def fc_precision(self):
+        v = C.c_int()
+        check(lib().ps_ctx_get_fc_precision(self.h, C.byref(v)))
+        return v.value
 
     def set_exact_updaters(self, on):
         check(lib().ps_ctx_set_exact_updaters(self.h, 1 if on else 0))

@@ -94,6 +94,12 @@ int ps_ctx_set_fc_precision(ps_ctx* ctx, int mode) {
   ctx->c.fc_precision = mode;
   PS_CATCH
 }
+int ps_ctx_get_fc_precision(ps_ctx* ctx, int* mode) {
+  PS_TRY
+  PS_REQUIRE(ctx && mode, PS_ERR_ARG, "ps_ctx_get_fc_precision: null argument");
+  *mode = ctx->c.fc_precision;
+  PS_CATCH
+}
 int ps_ctx_set_exact_updaters(ps_ctx* ctx, int on) {
   PS_TRY
   PS_REQUIRE(ctx != nullptr, PS_ERR_ARG, "ps_ctx_set_exact_updaters: null context");

@@ -165,6 +165,8 @@ static const float* gbar_ptr(const StepStatus* st) {
 
 void Model::run_step(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, bool train, StepStatus* publish_to, int mode) {
   PS_REQUIRE(N > 0 && N <= Bmax, PS_ERR_ARG, "model: batch size must be in [1, max_batch]");
+  pending_forward_N = 0;                         /* a forward whose backward never came is forgotten: drop its counts NOW — a cached */
+  if (has_emb && emb.last_L > 0) emb.clear_batch();   /* graph was captured from a clean state and would not */
   if (!use_graph) {
     ev_n = 0; ev_names.clear();
     if (mode == 1) { p2p_step(E, X, W, Y, N); if (publish_to) publish_status(ctx, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, publish_to); }

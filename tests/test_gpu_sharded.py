@@ -35,6 +35,7 @@ def worker(rank, R, port, out, cfg, emb_opt, graphed):
     from ps_b200 import binding as ps
     from ps_b200.sharded import GpuOps, GraphedShardedTrainer, P2PShardedTrainer, ShardedTrainer
     ctx = ps.Context(rank, seed=SEED)
+    ctx.set_fc_precision(ps.PS_FC_FP32)       # the tolerances below are those of the exact FcLayer mode
     upd = ps.UpdaterSpec.ftrl() if emb_opt == "ftrl" else None
     m = ps.Model(ctx, cfg["kind"], cfg["F"], cfg["D"], cfg["Xn"], cfg["fc"], emb_capacity=1 << 16, emb_updater=upd, max_batch=cfg["N"])
     N = cfg["N"]
@@ -77,7 +78,8 @@ def worker(rank, R, port, out, cfg, emb_opt, graphed):
 
 
 @pytest.mark.parametrize("R,emb_opt,graphed", [(1, "adam", False), (1, "adam", True), (1, "adam", "p2p"), (2, "adam", False), (2, "ftrl", False),
-                                                 (2, "adam", True), (2, "adam", "p2p"), (2, "ftrl", "p2p")])
+                                                 (2, "adam", True), (2, "adam", "p2p"), (2, "ftrl", "p2p"),
+                                                 (4, "adam", "p2p"), (4, "ftrl", True), (8, "adam", "p2p"), (8, "ftrl", "p2p"), (8, "adam", True)])
 def test_sharded_step_matches_oracle_global_batch(tmp_path, R, emb_opt, graphed):
     if torch.cuda.device_count() < R:
         pytest.skip(f"needs {R} GPUs")
