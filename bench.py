@@ -322,7 +322,7 @@ class Workload:
         if self.pinned is None:
             ps = self.env.ps
             self.pinned = []
-            for b in self.ring[: min(len(self.ring), 16)]:
+            for b in self.ring:                      # the same batches as the device-resident leg: same table rows, same L2 behaviour
                 pb = {}
                 for k, v in b.items():
                     pa = ps.PinnedArray(v.shape, v.dtype)

@@ -74,7 +74,7 @@ void transpose_copy(Ctx* ctx, const float* in, int ldi, float* out, int ldo, int
 __device__ __forceinline__ void publish(StepStatus* st, const uint32_t* emb_counters, const uint32_t* wide_counters, StepStatus* host) {
   StepStatus s = *st;
   s.emb_err = emb_counters ? emb_counters[1] : 0u;
-  s.n_unique = emb_counters ? emb_counters[0] : 0u;             /* written by the lookup kernel's last block: final long before any publish */
+  /* n_unique was copied from the lookup's cursor by the tail kernel: final long before any publish, untouched by the update's reset */
   s.wide_err = wide_counters ? wide_counters[0] : 0u;
   *host = s;
   __threadfence_system();
@@ -277,6 +277,7 @@ __device__ __forceinline__ void tail_finish(float loss_part, float d_part, int N
     const bool table_full = emb_counters != nullptr && emb_counters[1] != 0u;
     const bool bad_input = st->pad != 0u;        /* submit_text: a line of the batch could not be parsed — the batch is dropped (DataSet.java:96-98) */
     st->skip = (loss <= 0.01f || isnan(loss) || table_full || bad_input) ? 1 : 0;
+    st->n_unique = emb_counters != nullptr ? emb_counters[4] : 0u;           /* EmbTable CNT_CURSOR: unique keys of this batch */
     st->seq += 1u;
     *ticket = 0u;
   }

@@ -155,7 +155,7 @@ __device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int
  *                out[n][j*D ..] (EmbeddingField.java:73-76, EmbeddingLayer.java:36-46) and record the mask bits.
  *                Rows wanted by >= kHotShare lookups of the task are fetched ONCE into shared memory by the TMA unit
  *                (cp.async.bulk, mbarrier completion) and read from there; the others stream straight from L2/HBM.
- * The block that finishes last publishes the number of unique keys (StepStatus.n_unique, the update kernel's bound). */
+ * The cursor of the unique list is final when the kernel ends: it is the update kernel's bound and StepStatus.n_unique. */
 template <class IdT, bool GATHER, int TPL, bool ALIGNED>
 __global__ void __launch_bounds__(256) emb_lookup_kernel(const __grid_constant__ LookupArgs a) {
   extern __shared__ __align__(128) unsigned char lookup_smem[];
@@ -331,12 +331,10 @@ __global__ void __launch_bounds__(256) emb_lookup_kernel(const __grid_constant__
       }
     }
   }
-  if (last_block_done(&a.counters[CNT_TICKET_FWD], (uint32_t)a.task_blocks, a.send_rows != 0)) {
-    if (threadIdx.x == 0) a.counters[CNT_UNIQUE] = *reinterpret_cast<volatile uint32_t*>(&a.counters[CNT_CURSOR]);
-    if (a.send_rows && (int)threadIdx.x < a.p2p->R) {         /* PServer.getList answered: flag every requester */
-      __threadfence_system();
-      p2p_st_release_sys(reinterpret_cast<uint32_t*>(p2p_region(a.p2p, threadIdx.x, a.p2p->off_flags)) + CH_ROWS * kP2PMaxRanks + a.p2p->me, a.p2p->seq);
-    }
+  /* owner side of the exchange only: the block that finishes last flags every requester (PServer.getList answered) */
+  if (a.send_rows && last_block_done(&a.counters[CNT_TICKET_FWD], (uint32_t)a.task_blocks, true) && (int)threadIdx.x < a.p2p->R) {
+    __threadfence_system();
+    p2p_st_release_sys(reinterpret_cast<uint32_t*>(p2p_region(a.p2p, threadIdx.x, a.p2p->off_flags)) + CH_ROWS * kP2PMaxRanks + a.p2p->me, a.p2p->seq);
   }
 }
 
@@ -546,7 +544,7 @@ __global__ void __launch_bounds__(256) emb_update_kernel(EmbSlot* __restrict__ s
   const int KPW = 32 / CH;
   const int kl = lane / CH, ch = lane - kl * CH, cc = ch * 4;
   const bool lane_on = kl < KPW;
-  const uint32_t U = counters[CNT_UNIQUE];                   /* final since the lookup kernel */
+  const uint32_t U = counters[CNT_CURSOR];                   /* final since the lookup kernel ended; reset below by the last block */
   const bool skip = skip_flag != nullptr && *skip_flag != 0; /* written by the tail kernel, long before the scatter */
   const long wstride = (long)gridDim.x * 8;
   long wi = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -637,7 +635,7 @@ __global__ void __launch_bounds__(256) emb_scatter_entries_kernel(const EmbSlot*
 
 /* forget the batch: the slots of its unique list get {cnt, uidx} = {0, ready}; the cursor restarts */
 __global__ void __launch_bounds__(256) emb_clear_batch_kernel(EmbSlot* __restrict__ slots, const int32_t* __restrict__ uniq, uint32_t* __restrict__ counters) {
-  const uint32_t U = counters[CNT_UNIQUE];
+  const uint32_t U = counters[CNT_CURSOR];
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < U; i += gridDim.x * blockDim.x)
     *reinterpret_cast<unsigned long long*>(&slots[uniq[i]].cnt) = (unsigned long long)kRowReady << 32;
   if (last_block_done(&counters[CNT_TICKET_UPD], gridDim.x) && threadIdx.x == 0) counters[CNT_CURSOR] = 0u;

@@ -41,10 +41,11 @@ struct __align__(16) EmbSlot {
 };
 
 /* EmbTable::counters */
-enum { CNT_UNIQUE = 0,      /* unique keys of the last resolved batch (final once the lookup kernel has finished) */
+enum { CNT_UNIQUE = 0,      /* (unused) */
        CNT_ERR = 1,         /* an insert found the table full */
        CNT_ROWS = 2,        /* [2..3] u64 number of keys in the table */
-       CNT_CURSOR = 4,      /* unique keys claimed so far by the running lookup kernel */
+       CNT_CURSOR = 4,      /* unique keys of the batch being processed: grows during the lookup kernel, final when it ends, read by the
+                               tail (StepStatus.n_unique) and the update kernel, whose last block resets it */
        CNT_TICKET_FWD = 5, CNT_TICKET_UPD = 6, CNT_WORDS = 8 };
 
 struct __align__(32) WideSlot {
