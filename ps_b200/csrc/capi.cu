@@ -306,7 +306,7 @@ int ps_emb_backward_update(ps_emb* e, const float* delta, int ld, int N, int cal
   const size_t need = (size_t)N * ld;
   if (need > e->delta_cap) { PS_CUDA(cudaStreamSynchronize(st)); dfree(e->dDelta); e->dDelta = dmalloc<float>(need); e->delta_cap = need; }
   PS_CUDA(cudaMemcpyAsync(e->dDelta, delta, sizeof(float) * need, cudaMemcpyHostToDevice, st));
-  e->t.scatter_update(e->dDelta, ld, nullptr, 0, N, calls, nullptr, 0, nullptr, true);   /* ReLU mask: the bits the forward recorded */
+  e->t.scatter_update(e->dDelta, ld, nullptr, 0, N, calls, nullptr, 0, true);   /* ReLU mask: the bits the forward recorded */
   e->lastN = 0;
   PS_CUDA(cudaStreamSynchronize(st));
   PS_CATCH

@@ -350,7 +350,7 @@ void Model::step_device(const int64_t* E, const float* X, const int64_t* W, cons
     const DenseUpdateArgs u = dense_args(N);
     dense_update(ctx, u, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, publish_to);
   }
-  if (has_emb) { emb.scatter_update(delta[0], ld[0], nullptr, 0, N, 2, skip_ptr(st_dev), 0, nullptr, true); mark("emb_bwd_update"); }
+  if (has_emb) { emb.scatter_update(delta[0], ld[0], nullptr, 0, N, 2, skip_ptr(st_dev), 0, true); mark("emb_bwd_update"); }
   fork(s1, s);
   fork(s2, s);
   mark("end");
@@ -477,7 +477,7 @@ void Model::p2p_step(const int64_t* E, const float* X, const int64_t* W, const f
     shard_finish_scalars_p2p(ctx, st_dev, p2p.state(), u.total);
   }
   if (has_emb) {
-    p2p.grad_reduce(delta[0], ld[0], act[0], ld[0], N, F, D);                   /* client.push: one gradient sum per unique key */
+    emb.scatter_rows(p2p.bt, p2p.lk_b, p2p.gacc, delta[0], ld[0], act[0], ld[0], N);   /* client.push: one gradient sum per unique key of this rank's batch */
     p2p.grad_send();                                                            /* ... with its occurrence count, to the owner */
   }
   fork(s1, s);                                                                  /* the global skip flag */
@@ -508,7 +508,7 @@ void Model::kernel_times(const int64_t* const* E_ring, int n_ring, int N, int re
     try {
       for (int r = 0; r < reps; ++r) {
         emb.lookup(E_ring[r % n_ring], nullptr, N, (variant == 1 || variant == 2) ? act[0] : nullptr, ld[0]);
-        if (variant == 2) emb.scatter_update(delta[0], ld[0], nullptr, 0, N, 2, nullptr, 0, nullptr, true);
+        if (variant == 2) emb.scatter_update(delta[0], ld[0], nullptr, 0, N, 2, nullptr, 0, true);
         else emb.clear_batch();
         if (variant == 3) emb.clear_batch();
       }
@@ -667,7 +667,7 @@ void Model::backward_update_host(const float* delta_top, int N, float loss) {
     const DenseUpdateArgs u = dense_args(N);
     dense_update(ctx, u, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, S.st_host);
   }
-  if (has_emb) emb.scatter_update(delta[0], ld[0], nullptr, 0, N, 2, skip_ptr(st_dev), 0, nullptr, true);
+  if (has_emb) emb.scatter_update(delta[0], ld[0], nullptr, 0, N, 2, skip_ptr(st_dev), 0, true);
   fork(s1, s);
   fork(s2, s);
   PS_CUDA(cudaStreamSynchronize(s));

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) p2p_route_send_kernel(P2PState* st, Batch
     if (b >= 0) first = atomicAdd(&bt[b].cnt, (uint32_t)__popc(peers)) == 0u;
   }
   b = __shfl_sync(0xffffffffu, b, leader);
-  if (l >= 0) lk_b[l] = b;
+  if (t < L) lk_b[t] = b;                        /* field-major like EmbTable::lk_slot: the backward's scatter walks it the same way */
   __shared__ int s_cnt[kP2PMaxRanks], s_base[kP2PMaxRanks];
   if (threadIdx.x < kP2PMaxRanks) s_cnt[threadIdx.x] = 0;
   __syncthreads();
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256) p2p_unpack_kernel(const P2PState* st, con
     const int part = (int)(g - l * tpl);
     if (l >= L) return;
     const int n = (int)(l / F), j = (int)(l - (long)n * F);
-    const int b = lk_b[l];
+    const int b = lk_b[(long)j * N + n];
     const int pos = b >= 0 ? bt[b].upos : -1;
     const float4 v = pos >= 0 ? ld_f4(rows + (size_t)pos * Dp + part * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     st_f4(out + (size_t)n * ldo + j * D + part * 4, v);
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) p2p_unpack_kernel(const P2PState* st, con
     const int d = (int)(g - l * Dp);
     if (l >= L || d >= D) return;
     const int n = (int)(l / F), j = (int)(l - (long)n * F);
-    const int b = lk_b[l];
+    const int b = lk_b[(long)j * N + n];
     const int pos = b >= 0 ? bt[b].upos : -1;
     out[(size_t)n * ldo + j * D + d] = pos >= 0 ? rows[(size_t)pos * Dp + d] : 0.f;
   }
@@ -129,53 +129,8 @@ __global__ void __launch_bounds__(256) p2p_reduce_kernel(const P2PState* st, flo
   gsum[i] = s;
 }
 
-/* KVStore.update → client.push per key (KVStore.java:257-260).  Phase 1: per-lookup row gradient (ReLU mask of
- * EmbeddingField.java:91-93) summed per unique key into the local accumulator gacc[upos]; lanes of a warp work on the
- * same field for consecutive samples, so duplicates collapse by shuffle before one 128-bit reduction.            */
-template <int TPL>
-__global__ void __launch_bounds__(256) p2p_grad_reduce_kernel(const P2PState* st, const BatchSlot* __restrict__ bt, const int32_t* __restrict__ lk_b,
-                                                              const float* __restrict__ delta, int ldd, const float* __restrict__ act, int lda,
-                                                              int N, int F, int D, float* __restrict__ gacc) {
-  const int Dp = st->Dp;
-  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long L = (long)N * F;
-  const long lk = g / TPL;
-  const int part = (int)(g % TPL);
-  const int lane = threadIdx.x & 31, my_group = lane / TPL;
-  int upos = -1, n = 0, j = 0;
-  if (lk < L) {
-    j = (int)(lk / N); n = (int)(lk - (long)j * N);
-    const int b = lk_b[(long)n * F + j];
-    if (b >= 0) upos = bt[b].upos;
-  }
-  const bool valid = upos >= 0;
-  const bool lane_on = valid && part * 4 < D;
-  float4 gk = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (lane_on) {
-    const size_t od = (size_t)n * ldd + j * D + part * 4, oa = (size_t)n * lda + j * D + part * 4;
-    float dv[4] = {0.f, 0.f, 0.f, 0.f}, av[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) if (part * 4 + i < D) { dv[i] = delta[od + i]; av[i] = act[oa + i]; }
-    gk.x = __fmul_rn(dv[0], av[0] > 0.f ? 1.f : 0.f); gk.y = __fmul_rn(dv[1], av[1] > 0.f ? 1.f : 0.f);
-    gk.z = __fmul_rn(dv[2], av[2] > 0.f ? 1.f : 0.f); gk.w = __fmul_rn(dv[3], av[3] > 0.f ? 1.f : 0.f);
-  }
-  const unsigned peers = __match_any_sync(0xffffffffu, valid ? upos : (-1 - lane));
-  const bool leader = ((__ffs(peers) - 1) / TPL) == my_group;
-  if (__any_sync(0xffffffffu, valid && __popc(peers) > TPL)) {
-    float4 sum = gk;
-#pragma unroll
-    for (int og = 0; og < 32 / TPL; ++og) {
-      const int src = og * TPL + part;
-      float4 o;
-      o.x = __shfl_sync(0xffffffffu, gk.x, src); o.y = __shfl_sync(0xffffffffu, gk.y, src);
-      o.z = __shfl_sync(0xffffffffu, gk.z, src); o.w = __shfl_sync(0xffffffffu, gk.w, src);
-      if (og != my_group && ((peers >> src) & 1u)) { sum.x += o.x; sum.y += o.y; sum.z += o.z; sum.w += o.w; }
-    }
-    gk = sum;
-  }
-  if (lane_on && leader) red_add_f4(gacc + (size_t)upos * Dp + part * 4, gk);
-}
-
+/* KVStore.update → client.push per key (KVStore.java:257-260).  Phase 1 is EmbTable::scatter_rows (table.cu): the per-lookup row
+ * gradients (ReLU mask of EmbeddingField.java:91-93) are summed per unique key of this rank's batch into gacc[bucket position]. */
 /* Phase 2: one gradient sum per unique key, with the key's occurrence count in this rank's batch → its owner's
  * grads_in[me][pos] / gcnt_in[me][pos]; the local accumulator and the per-batch table entry are cleared for the next step */
 __global__ void __launch_bounds__(256) p2p_grad_send_kernel(P2PState* st, float* __restrict__ gacc, BatchSlot* __restrict__ bt, const int32_t* __restrict__ ulist) {
@@ -291,17 +246,6 @@ void P2P::unpack(int N, int F, int D, float* out, int ldo, const float* X, int X
 
 void P2P::reduce_gsum(float* gsum) {
   p2p_reduce_kernel<<<ceil_div(glen, 256), 256, 0, ctx->stream>>>(dev, gsum);
-  P2P_LAUNCHED();
-}
-
-void P2P::grad_reduce(const float* delta, int ldd, const float* act, int lda, int N, int F, int D) {
-  int tpl = 1;
-  while (tpl < Dp / 4) tpl <<= 1;
-  const long total = (long)N * F * tpl;
-  const int grid = ceil_div(total, 256);
-#define PS_GR(T) p2p_grad_reduce_kernel<T><<<grid, 256, 0, ctx->stream>>>(dev, bt, lk_b, delta, ldd, act, lda, N, F, D, gacc)
-  switch (tpl) { case 1: PS_GR(1); break; case 2: PS_GR(2); break; case 4: PS_GR(4); break; case 8: PS_GR(8); break; case 16: PS_GR(16); break; default: PS_GR(32); break; }
-#undef PS_GR
   P2P_LAUNCHED();
 }
 

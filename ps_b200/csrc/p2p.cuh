@@ -72,8 +72,7 @@ struct P2P {
   void bcast(const void* src, size_t bytes, int channel);                           /* wide ids → every peer; publishes the channel */
   void unpack(int N, int F, int D, float* out, int ldo, const float* X, int Xn, int xoff);   /* rows_in (+ X) → concat buffer */
   void reduce_gsum(float* gsum);                                                    /* sum over ranks, fixed order */
-  /* per-lookup row gradients (ReLU mask applied) summed per unique key locally, then one sum per key to its owner */
-  void grad_reduce(const float* delta, int ldd, const float* act, int lda, int N, int F, int D);
+  /* (the per-key sums are formed by EmbTable::scatter_rows into gacc) */
   void grad_send();                                                                 /* sums + counts → owners' grads_in / gcnt_in; publishes CH_GRADS */
   /* device addresses inside the LOCAL slab for the current parity are resolved in-kernel from seq */
   const P2PState* state() const { return dev; }

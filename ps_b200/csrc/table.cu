@@ -141,20 +141,24 @@ __device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int
   return ((unsigned long long)hi << 32) | lo;
 }
 
-/* EmbeddingLayer.forward as ONE kernel.  A warp task is (field j, 32 consecutive samples); every warp runs exactly one
- * task, a block runs 8 consecutive tasks = neighbouring fields of the same samples (the 32 B sectors of the [N][F] id
- * matrix are shared inside the block).  Per task:
- *   1. resolve   lane <-> sample: find-or-insert the key (row creation follows KVStore.create, KVStore.java:168-190: the
- *                creating thread draws the row from the deterministic initialiser of ps_spec.h, optimiser state stays
- *                at the arena's zero, AdamUpdater.java:76-84); lk_slot[j][n] = slot.
- *   2. count     duplicates of a key inside the warp (a low-cardinality field) elect one lane, which adds the group's
- *                occurrences to the slot's batch counter with ONE returning atomic; the group that finds the counter
- *                at zero owns the key for this batch: it appends the slot to the batch's unique list (one cursor
- *                atomic per warp) and leaves 1 + that index in the slot record — the accumulator row of the backward.
- *   3. gather    (overlaps the atomics of 2) TPL lanes per row move relu(row) as 128-bit chunks to
- *                out[n][j*D ..] (EmbeddingField.java:73-76, EmbeddingLayer.java:36-46) and record the mask bits.
- *                Rows wanted by >= kHotShare lookups of the task are fetched ONCE into shared memory by the TMA unit
- *                (cp.async.bulk, mbarrier completion) and read from there; the others stream straight from L2/HBM.
+/* EmbeddingLayer.forward as ONE kernel.  A warp task is (field j, 32 consecutive samples); the warps of a persistent grid
+ * stride over the tasks, neighbouring warps taking neighbouring fields of the same samples (the 32 B sectors of the [N][F]
+ * id matrix are shared inside a block).  A warp's loop is software-pipelined three tasks deep so that the dependent loads of
+ * a lookup (id -> slot record -> row) of DIFFERENT tasks are in flight together:
+ *   stage A (task i+2)  load the ids
+ *   stage B (task i+1)  pack the keys, hash, load the home-bucket slot records
+ *   stage C (task i)    1. resolve   lane <-> sample: find-or-insert the key (row creation follows KVStore.create,
+ *                          KVStore.java:168-190: the creating thread draws the row from the deterministic initialiser of
+ *                          ps_spec.h, optimiser state stays at the arena's zero, AdamUpdater.java:76-84); lk_slot[j][n] = slot.
+ *                       2. count     duplicates of a key inside the warp (a low-cardinality field) elect one lane, which adds
+ *                          the group's occurrences to the slot's batch counter with ONE returning atomic; the group that
+ *                          finds the counter at zero owns the key for this batch: it appends the slot to the batch's
+ *                          unique list (one cursor atomic per warp) and leaves 1 + that index in the slot record — the
+ *                          accumulator row of the backward.  Both atomics return while the row loads are in flight.
+ *                       3. gather    TPL lanes per row move relu(row) as 128-bit chunks to out[n][j*D ..]
+ *                          (EmbeddingField.java:73-76, EmbeddingLayer.java:36-46) and record the mask bits.  Rows wanted by
+ *                          >= kHotShare lookups of the task are fetched ONCE into shared memory by the TMA unit
+ *                          (cp.async.bulk, mbarrier completion) and read from there; the others stream from L2/HBM.
  * The cursor of the unique list is final when the kernel ends: it is the update kernel's bound and StepStatus.n_unique. */
 template <class IdT, bool GATHER, int TPL, bool ALIGNED>
 __global__ void __launch_bounds__(256) emb_lookup_kernel(const __grid_constant__ LookupArgs a) {
@@ -172,164 +176,187 @@ __global__ void __launch_bounds__(256) emb_lookup_kernel(const __grid_constant__
     return;
   }
   if (a.p2p != nullptr) p2p_wait_all(a.p2p, CH_KEYS);     /* every requester's keys (and their count) have landed in keys_in */
-  const IdT* __restrict__ ids = static_cast<const IdT*>(a.ids);
+  const IdT* __restrict__ ids = a.p2p != nullptr ? reinterpret_cast<const IdT*>(p2p_region(a.p2p, a.p2p->me, a.p2p->off_keys)) : static_cast<const IdT*>(a.ids);
+  const int32_t* __restrict__ pcounts = a.p2p != nullptr ? reinterpret_cast<const int32_t*>(p2p_region(a.p2p, a.p2p->me, a.p2p->off_counts)) : nullptr;
   const int Fe = a.F > 0 ? a.F : 1;
   const long ntasks = (long)((a.N + 31) / 32) * Fe;
-  const long task = (long)blockIdx.x * 8 + warp;
+  const long W = (long)a.task_blocks * 8;          /* warps striding over the tasks */
+  const long w0 = (long)blockIdx.x * 8 + warp;
   uint64_t* mbar = reinterpret_cast<uint64_t*>(lookup_smem);
-  float* stage_all = reinterpret_cast<float*>(lookup_smem + 128);
+  float* stage = reinterpret_cast<float*>(lookup_smem + 128) + (size_t)warp * kHotRows * a.Dp;
+  uint32_t hot_parity = 0u;
   if (GATHER && a.hot_tma) {
     if (lane == 0) tb_mbar_init(tb_smem_u32(&mbar[warp]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
   }
-  if (task < ntasks) {
-    const int sg = (int)(task / Fe), j = (int)(task - (long)sg * Fe);
-    const long nbase = (long)sg * 32;
-    const long n = nbase + lane;
-    const bool in = n < a.N;
-    unsigned long long key = PS_KEY_EMPTY;
-    if (in) {
-      if (a.p2p != nullptr) {                      /* owner side of the peer-memory exchange: this step's keys_in mailbox */
-        const int src = (int)(n / a.p2p->cap), idx = (int)(n - (long)src * a.p2p->cap);
-        /* senders de-duplicate their batch (PSRouterClient sends a key once): an entry is one (requester, key) pair */
-        if (idx < reinterpret_cast<const int32_t*>(p2p_region(a.p2p, a.p2p->me, a.p2p->off_counts))[src])
-          key = reinterpret_cast<const unsigned long long*>(p2p_region(a.p2p, a.p2p->me, a.p2p->off_keys))[n];
-      } else if (a.F > 0) {
-        key = ps_pack_key((uint32_t)j, (uint64_t)(int64_t)ids[n * a.F + j]);
-      } else {
-        key = (unsigned long long)ids[n];          /* EMPTY marks padding in the fixed-capacity sharded exchange */
-      }
-    }
-    /* ---- 1. resolve ---- */
-    int slot = -1;
-    bool ready = false;
-    if (key != PS_KEY_EMPTY) {
-      const uint32_t bucket = ps_bucket_of(key, a.C);
-      const ulonglong2 rec = ld_slot(&a.slots[bucket]);
-      bool inserted;
-      slot = emb_resolve(a.slots, a.C, key, bucket, rec, &inserted, &ready);
-      if (slot < 0) a.counters[CNT_ERR] = 1u;       /* table full: the tail turns this into the step's skip flag — nothing is updated */
-      else if (inserted) {
-        float* row = a.rows + (size_t)slot * a.rs;
-        for (int d = 0; d < a.D; ++d) row[d] = ps_init_value(a.seed, key, (uint32_t)d, a.maxv);
-        __threadfence();                            /* the row is visible before anybody can see kRowReady */
-        atomicOr(&a.slots[slot].uidx, kRowReady);
-        atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + CNT_ROWS), 1ull);
-      }
-    }
-    const long t = (long)j * a.N + n;
-    if (in) a.lk_slot[t] = slot;
-    /* ---- 2. count (the atomic's result is consumed after the gather) ---- */
-    const unsigned peers = __match_any_sync(0xffffffffu, slot >= 0 ? slot : (-1 - lane));
-    const int leader = __ffs(peers) - 1;
-    /* every lookup counts 1 (owner side of the exchange: every requester's entry; the occurrence counts arrive with the push) */
-    const uint32_t total_add = (uint32_t)__popc(peers);
-    uint32_t old = 1u;
-    if (slot >= 0 && leader == lane) old = atomicAdd(&a.slots[slot].cnt, total_add);
+  /* pipeline registers: raw ids of task i+2 (loaded in the previous iteration), key / home bucket / its record of task i+1 */
+  IdT raw_n = IdT(0); bool rv_n = false;
+  unsigned long long key_c = PS_KEY_EMPTY; uint32_t bucket_c = 0u; ulonglong2 rec_c = make_ulonglong2(0ull, 0ull);
 
-    /* ---- 3. gather ---- */
-    if (GATHER) {
-      constexpr int GPW = 32 / TPL;                 /* rows per pass */
-      constexpr int NP = TPL;                       /* passes over the task's 32 rows */
-      constexpr int UNR = NP < 8 ? NP : 8;          /* passes whose loads are in flight together */
-      constexpr int MSH = TPL < 8 ? TPL : 8;        /* lanes whose mask nibbles share one 32-bit word */
-      const int part = lane % TPL, grp = lane / TPL;
-      const bool lane_on = part * 4 < a.Dp;
-      const bool any_nr = __any_sync(0xffffffffu, slot >= 0 && !ready);
-      int hidx = -1;
-      unsigned hmask = 0u;
-      float* stage = stage_all + (size_t)warp * kHotRows * a.Dp;
-      if (a.hot_tma) {
-        const bool hot = slot >= 0 && ready && __popc(peers) >= kHotShare;
-        hmask = __ballot_sync(0xffffffffu, hot && leader == lane);
-        if (hmask != 0u) {                          /* warp-uniform */
-          const uint32_t bar = tb_smem_u32(&mbar[warp]);
-          if (lane == 0) tb_mbar_expect_tx(bar, (uint32_t)__popc(hmask) * (uint32_t)a.Dp * 4u);
-          __syncwarp();
-          if (hot) hidx = __popc(hmask & ((1u << leader) - 1u));
-          if (hot && leader == lane) tb_bulk_g2s(tb_smem_u32(stage + (size_t)hidx * a.Dp), a.rows + (size_t)slot * a.rs, (uint32_t)a.Dp * 4u, bar);
+#pragma unroll 1
+  for (long it = -2;; ++it) {
+    const long tC = w0 + it * W, tB = tC + W, tA = tB + W;
+    if (it >= 0 && tC >= ntasks) break;
+    /* ---- stage A: ids of task tA ---- */
+    IdT raw_a = IdT(0); bool rv_a = false;
+    if (tA < ntasks) {
+      const int sg = (int)(tA / Fe), j = (int)(tA - (long)sg * Fe);
+      const long n = (long)sg * 32 + lane;
+      if (n < a.N) {
+        if (a.p2p != nullptr) {                    /* owner side of the peer-memory exchange: entry n = (requester n / cap, its idx-th key) */
+          const int src = (int)(n / a.p2p->cap), idx = (int)(n - (long)src * a.p2p->cap);
+          if (idx < pcounts[src]) { raw_a = ids[n]; rv_a = true; }
+        } else if (a.F > 0) { raw_a = ids[n * a.F + j]; rv_a = true; }
+        else { raw_a = ids[n]; rv_a = true; }
+      }
+    }
+    /* ---- stage B: key, hash and home-bucket record of task tB (its ids were requested one iteration ago) ---- */
+    unsigned long long key_b = PS_KEY_EMPTY; uint32_t bucket_b = 0u; ulonglong2 rec_b = make_ulonglong2(0ull, 0ull);
+    if (it >= -1 && tB < ntasks && rv_n) {
+      const int j = (int)(tB % Fe);
+      key_b = a.F > 0 ? ps_pack_key((uint32_t)j, (uint64_t)(int64_t)raw_n) : (unsigned long long)raw_n;   /* EMPTY marks padding in the fixed-capacity exchange */
+      if (key_b != PS_KEY_EMPTY) { bucket_b = ps_bucket_of(key_b, a.C); rec_b = ld_slot(&a.slots[bucket_b]); }
+    }
+    /* ---- stage C: task tC ---- */
+    if (it >= 0) {
+      const int sg = (int)(tC / Fe), j = (int)(tC - (long)sg * Fe);
+      const long nbase = (long)sg * 32;
+      const long n = nbase + lane;
+      const bool in = n < a.N;
+      const unsigned long long key = key_c;
+      /* 1. resolve */
+      int slot = -1;
+      bool ready = false;
+      if (key != PS_KEY_EMPTY) {
+        bool inserted;
+        slot = emb_resolve(a.slots, a.C, key, bucket_c, rec_c, &inserted, &ready);
+        if (slot < 0) a.counters[CNT_ERR] = 1u;       /* table full: the tail turns this into the step's skip flag — nothing is updated */
+        else if (inserted) {
+          float* row = a.rows + (size_t)slot * a.rs;
+          for (int d = 0; d < a.D; ++d) row[d] = ps_init_value(a.seed, key, (uint32_t)d, a.maxv);
+          __threadfence();                            /* the row is visible before anybody can see kRowReady */
+          atomicOr(&a.slots[slot].uidx, kRowReady);
+          atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + CNT_ROWS), 1ull);
         }
       }
-      const int flags = (ready ? 1 : 0) | ((hidx + 1) << 1);
-      bool waited = false;
+      if (in) a.lk_slot[(long)j * a.N + n] = slot;
+      /* 2. count: every lookup counts 1 (owner side of the exchange: every requester's entry; the occurrence counts arrive with the push) */
+      const unsigned peers = __match_any_sync(0xffffffffu, slot >= 0 ? slot : (-1 - lane));
+      const int leader = __ffs(peers) - 1;
+      uint32_t old = 1u, ubase = 0u;
+      if (slot >= 0 && leader == lane) old = atomicAdd(&a.slots[slot].cnt, (uint32_t)__popc(peers));
+      unsigned omask = 0u;
+      bool is_owner = false;
+      /* the group that found the batch counter at zero owns the key: claim its place in the unique list (consumes `old`) */
+      auto claim = [&]() {
+        is_owner = slot >= 0 && leader == lane && old == 0u;
+        omask = __ballot_sync(0xffffffffu, is_owner);
+        if (omask != 0u && lane == __ffs(omask) - 1) ubase = atomicAdd(&a.counters[CNT_CURSOR], (uint32_t)__popc(omask));
+      };
+      /* 3. gather */
+      if (GATHER) {
+        constexpr int GPW = 32 / TPL;                 /* rows per pass */
+        constexpr int NP = TPL;                       /* passes over the task's 32 rows */
+        constexpr int UNR = NP < 8 ? NP : 8;          /* passes whose loads are in flight together */
+        constexpr int MSH = TPL < 8 ? TPL : 8;        /* lanes whose mask nibbles share one 32-bit word */
+        const int part = lane % TPL, grp = lane / TPL;
+        const bool lane_on = part * 4 < a.Dp;
+        const bool any_nr = __any_sync(0xffffffffu, slot >= 0 && !ready);
+        int hidx = -1;
+        unsigned hmask = 0u;
+        if (a.hot_tma) {
+          const bool hot = slot >= 0 && ready && __popc(peers) >= kHotShare;
+          hmask = __ballot_sync(0xffffffffu, hot && leader == lane);
+          if (hmask != 0u) {                          /* warp-uniform */
+            const uint32_t bar = tb_smem_u32(&mbar[warp]);
+            if (lane == 0) tb_mbar_expect_tx(bar, (uint32_t)__popc(hmask) * (uint32_t)a.Dp * 4u);
+            __syncwarp();
+            if (hot) hidx = __popc(hmask & ((1u << leader) - 1u));
+            if (hot && leader == lane) tb_bulk_g2s(tb_smem_u32(stage + (size_t)hidx * a.Dp), a.rows + (size_t)slot * a.rs, (uint32_t)a.Dp * 4u, bar);
+          }
+        }
+        const int flags = (ready ? 1 : 0) | ((hidx + 1) << 1);
+        bool waited = false;
 #pragma unroll 1
-      for (int p0 = 0; p0 < NP; p0 += UNR) {
-        float4 v[UNR];
-        int rs_[UNR], rf_[UNR];
-#pragma unroll
-        for (int q = 0; q < UNR; ++q) {
-          const int r = (p0 + q) * GPW + grp;
-          rs_[q] = __shfl_sync(0xffffffffu, slot, r);
-          rf_[q] = __shfl_sync(0xffffffffu, flags, r);
-          v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (rs_[q] >= 0 && lane_on && (rf_[q] & 1) && (rf_[q] >> 1) == 0) v[q] = ld_f4(a.rows + (size_t)rs_[q] * a.rs + part * 4);
-        }
-        if (hmask != 0u) {                          /* rows several lookups share: from the TMA-staged copy */
-          if (!waited) { tb_mbar_wait(tb_smem_u32(&mbar[warp]), 0u); waited = true; }
-#pragma unroll
-          for (int q = 0; q < UNR; ++q)
-            if (rs_[q] >= 0 && lane_on && (rf_[q] >> 1) != 0) v[q] = *reinterpret_cast<const float4*>(stage + (size_t)((rf_[q] >> 1) - 1) * a.Dp + part * 4);
-        }
-        if (any_nr) {                               /* rows created by this very kernel: the initialiser's bits, not memory */
+        for (int p0 = 0; p0 < NP; p0 += UNR) {
+          float4 v[UNR];
+          int rs_[UNR], rf_[UNR];
 #pragma unroll
           for (int q = 0; q < UNR; ++q) {
             const int r = (p0 + q) * GPW + grp;
-            const unsigned long long kr = shfl_u64(key, r);
-            if (rs_[q] >= 0 && lane_on && !(rf_[q] & 1)) {
-              const int d0 = part * 4;
-              v[q].x = d0 + 0 < a.D ? ps_init_value(a.seed, kr, (uint32_t)(d0 + 0), a.maxv) : 0.f;
-              v[q].y = d0 + 1 < a.D ? ps_init_value(a.seed, kr, (uint32_t)(d0 + 1), a.maxv) : 0.f;
-              v[q].z = d0 + 2 < a.D ? ps_init_value(a.seed, kr, (uint32_t)(d0 + 2), a.maxv) : 0.f;
-              v[q].w = d0 + 3 < a.D ? ps_init_value(a.seed, kr, (uint32_t)(d0 + 3), a.maxv) : 0.f;
+            rs_[q] = __shfl_sync(0xffffffffu, slot, r);
+            rf_[q] = __shfl_sync(0xffffffffu, flags, r);
+            v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rs_[q] >= 0 && lane_on && (rf_[q] & 1) && (rf_[q] >> 1) == 0) v[q] = ld_f4(a.rows + (size_t)rs_[q] * a.rs + part * 4);
+          }
+          if (p0 == 0) claim();                       /* the count atomic has returned by now; the cursor atomic flies with the row loads */
+          if (hmask != 0u) {                          /* rows several lookups share: from the TMA-staged copy */
+            if (!waited) { tb_mbar_wait(tb_smem_u32(&mbar[warp]), hot_parity); hot_parity ^= 1u; waited = true; }
+#pragma unroll
+            for (int q = 0; q < UNR; ++q)
+              if (rs_[q] >= 0 && lane_on && (rf_[q] >> 1) != 0) v[q] = *reinterpret_cast<const float4*>(stage + (size_t)((rf_[q] >> 1) - 1) * a.Dp + part * 4);
+          }
+          if (any_nr) {                               /* rows created by this very kernel: the initialiser's bits, not memory */
+#pragma unroll
+            for (int q = 0; q < UNR; ++q) {
+              const int r = (p0 + q) * GPW + grp;
+              const unsigned long long kr = shfl_u64(key, r);
+              if (rs_[q] >= 0 && lane_on && !(rf_[q] & 1)) {
+                const int d0 = part * 4;
+                v[q].x = d0 + 0 < a.D ? ps_init_value(a.seed, kr, (uint32_t)(d0 + 0), a.maxv) : 0.f;
+                v[q].y = d0 + 1 < a.D ? ps_init_value(a.seed, kr, (uint32_t)(d0 + 1), a.maxv) : 0.f;
+                v[q].z = d0 + 2 < a.D ? ps_init_value(a.seed, kr, (uint32_t)(d0 + 2), a.maxv) : 0.f;
+                v[q].w = d0 + 3 < a.D ? ps_init_value(a.seed, kr, (uint32_t)(d0 + 3), a.maxv) : 0.f;
+              }
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < UNR; ++q) {
+            const int r = (p0 + q) * GPW + grp;
+            const long nr = nbase + r;
+            /* EmbeddingField.java:75: relu in place; the mask bit is what Relu.backward will ask for (Relu.java:14-19) */
+            uint32_t m = (v[q].x > 0.f ? 1u : 0u) | (v[q].y > 0.f ? 2u : 0u) | (v[q].z > 0.f ? 4u : 0u) | (v[q].w > 0.f ? 8u : 0u);
+            v[q].x = fmaxf(v[q].x, 0.f); v[q].y = fmaxf(v[q].y, 0.f); v[q].z = fmaxf(v[q].z, 0.f); v[q].w = fmaxf(v[q].w, 0.f);
+            if (a.lk_mask != nullptr) {
+              m <<= (part & 7) * 4;
+#pragma unroll
+              for (int o = 1; o < MSH; o <<= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
+              if (nr < a.N && (part & 7) == 0 && lane_on) a.lk_mask[((size_t)j * a.N + nr) * a.MW + (part >> 3)] = m;
+            }
+            if (nr >= a.N || !lane_on) continue;
+            float* o;
+            if (a.F > 0) o = a.out + (size_t)nr * a.ldo + j * a.D + part * 4;
+            else if (a.send_rows) {                   /* PServer.getList response: straight into the requester's rows_in[me][idx] */
+              if (rs_[q] < 0) continue;
+              const int src = (int)(nr / a.p2p->cap), idx = (int)(nr - (long)src * a.p2p->cap);
+              o = reinterpret_cast<float*>(p2p_region(a.p2p, src, a.p2p->off_rows)) + ((size_t)a.p2p->me * a.p2p->cap + idx) * a.Dp + part * 4;
+            } else o = a.out + (size_t)nr * a.ldo + part * 4;
+            if (ALIGNED || a.F == 0) {
+              st_f4(o, v[q]);
+            } else {
+              const float e[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) if (part * 4 + i < a.D) o[i] = e[i];
             }
           }
         }
-#pragma unroll
-        for (int q = 0; q < UNR; ++q) {
-          const int r = (p0 + q) * GPW + grp;
-          const long nr = nbase + r;
-          /* EmbeddingField.java:75: relu in place; the mask bit is what Relu.backward will ask for (Relu.java:14-19) */
-          uint32_t m = (v[q].x > 0.f ? 1u : 0u) | (v[q].y > 0.f ? 2u : 0u) | (v[q].z > 0.f ? 4u : 0u) | (v[q].w > 0.f ? 8u : 0u);
-          v[q].x = fmaxf(v[q].x, 0.f); v[q].y = fmaxf(v[q].y, 0.f); v[q].z = fmaxf(v[q].z, 0.f); v[q].w = fmaxf(v[q].w, 0.f);
-          if (a.lk_mask != nullptr) {
-            m <<= (part & 7) * 4;
-#pragma unroll
-            for (int o = 1; o < MSH; o <<= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
-            if (nr < a.N && (part & 7) == 0 && lane_on) a.lk_mask[((size_t)j * a.N + nr) * a.MW + (part >> 3)] = m;
-          }
-          if (nr >= a.N || !lane_on) continue;
-          float* o;
-          if (a.F > 0) o = a.out + (size_t)nr * a.ldo + j * a.D + part * 4;
-          else if (a.send_rows) {                   /* PServer.getList response: straight into the requester's rows_in[me][idx] */
-            if (rs_[q] < 0) continue;
-            const int src = (int)(nr / a.p2p->cap), idx = (int)(nr - (long)src * a.p2p->cap);
-            o = reinterpret_cast<float*>(p2p_region(a.p2p, src, a.p2p->off_rows)) + ((size_t)a.p2p->me * a.p2p->cap + idx) * a.Dp + part * 4;
-          } else o = a.out + (size_t)nr * a.ldo + part * 4;
-          if (ALIGNED || a.F == 0) {
-            st_f4(o, v[q]);
-          } else {
-            const float e[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) if (part * 4 + i < a.D) o[i] = e[i];
-          }
+      } else {
+        claim();
+      }
+      /* 2b. the owners take consecutive places after the warp's cursor reservation */
+      if (omask != 0u) {
+        ubase = __shfl_sync(0xffffffffu, ubase, __ffs(omask) - 1);
+        if (is_owner) {
+          const uint32_t u = ubase + (uint32_t)__popc(omask & ((1u << lane) - 1u));
+          a.uniq[u] = slot;
+          atomicOr(&a.slots[slot].uidx, u + 1u);
         }
       }
     }
-    /* ---- 2b. the group that found the batch counter at zero owns the key: claim its place in the unique list ---- */
-    const bool is_owner = slot >= 0 && leader == lane && old == 0u;
-    const unsigned omask = __ballot_sync(0xffffffffu, is_owner);
-    if (omask != 0u) {
-      const int first = __ffs(omask) - 1;
-      uint32_t base = 0u;
-      if (lane == first) base = atomicAdd(&a.counters[CNT_CURSOR], (uint32_t)__popc(omask));
-      base = __shfl_sync(0xffffffffu, base, first);
-      if (is_owner) {
-        const uint32_t u = base + (uint32_t)__popc(omask & ((1u << lane) - 1u));
-        a.uniq[u] = slot;
-        atomicOr(&a.slots[slot].uidx, u + 1u);
-      }
-    }
+    /* ---- rotate the pipeline ---- */
+    key_c = key_b; bucket_c = bucket_b; rec_c = rec_b;
+    raw_n = raw_a; rv_n = rv_a;
   }
   /* owner side of the exchange only: the block that finishes last flags every requester (PServer.getList answered) */
   if (a.send_rows && last_block_done(&a.counters[CNT_TICKET_FWD], (uint32_t)a.task_blocks, true) && (int)threadIdx.x < a.p2p->R) {
@@ -393,7 +420,7 @@ __global__ void __launch_bounds__(256) emb_scatter_kernel(const EmbSlot* __restr
                                                           const uint32_t* __restrict__ lk_mask, int MW, int N,
                                                           int F, int SB, const float* __restrict__ delta, int ldd, const float* __restrict__ act, int lda,
                                                           float* __restrict__ acc, const int* __restrict__ skip_flag,
-                                                          const P2PState* __restrict__ p2p, uint32_t hot_min) {
+                                                          int raw_row, uint32_t hot_min) {
   constexpr int GPW = 32 / TPL;                  /* lookups (lane groups) per warp task */
   constexpr int ROWF = TPL * CPL * 4;            /* floats of a (padded) row */
   __shared__ float hot_acc[kHotEntries][ROWF];
@@ -401,7 +428,6 @@ __global__ void __launch_bounds__(256) emb_scatter_kernel(const EmbSlot* __restr
   __shared__ uint32_t hot_row[kHotEntries];
   pdl_launch_dependents();                       /* the update kernel may start its prefetch now (it waits before reading acc) */
   if (skip_flag != nullptr && *skip_flag != 0) return;   /* DNN.java:58-63 early exit: nothing is pushed */
-  if (p2p != nullptr) delta = reinterpret_cast<const float*>(p2p_region(p2p, p2p->me, p2p->off_grads));   /* this step's grads_in mailbox */
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int part = lane % TPL, grp = lane / TPL;
   const int c0 = part * CPL * 4;                 /* first float of this lane's chunks */
@@ -466,7 +492,12 @@ __global__ void __launch_bounds__(256) emb_scatter_kernel(const EmbSlot* __restr
 #pragma unroll
     for (int p = 0; p < PASSES; ++p) {
       cnt[p] = 0u; row[p] = 0u;
-      if (slot[p] >= 0) { const uint4 m = *reinterpret_cast<const uint4*>(&slots[slot[p]]); cnt[p] = m.z; row[p] = (m.w & ~kRowReady) - 1u; }   /* the key's accumulator row */
+      if (slot[p] >= 0) {                          /* the key's batch count and accumulator row */
+        const uint4 m = *reinterpret_cast<const uint4*>(&slots[slot[p]]);
+        cnt[p] = m.z;
+        if (raw_row) { row[p] = m.w; if ((int)m.w < 0) slot[p] = -1; }       /* requester side of the sharded exchange: BatchSlot {key, cnt, bucket position | -1} */
+        else row[p] = (m.w & ~kRowReady) - 1u;
+      }
       if (lk_mask != nullptr) {                    /* the same multiplication by 0 / 1, the factor taken from the recorded mask bits */
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
@@ -495,9 +526,9 @@ __global__ void __launch_bounds__(256) emb_scatter_kernel(const EmbSlot* __restr
         }
       }
       if (!valid || rank != 0) continue;
-      /* ---- (2) hot keys: sum inside the block (the peer-memory exchange packs {entries << 24 | occurrences}: never hot) ---- */
+      /* ---- (2) hot keys: sum inside the block ---- */
       int e = -1;
-      if (p2p == nullptr && cnt[p] >= hot_min) {
+      if (cnt[p] >= hot_min) {
         uint32_t h = ((uint32_t)slot[p] * 2654435761u) >> (32 - kHotBits);
 #pragma unroll 1
         for (int t = 0; t < 4; ++t) {
@@ -677,6 +708,24 @@ __global__ void emb_put_rows_kernel(EmbSlot* __restrict__ slots, uint32_t C, flo
 /* ------------------------------------------------------------------ EmbTable host side */
 static int pow2_ge(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
+template <int TPL>
+static int lookup_occupancy(size_t smem) {
+  int occ = 1;
+  PS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, emb_lookup_kernel<int64_t, true, TPL, true>, 256, smem));
+  return occ;
+}
+static void query_lookup_occupancy(EmbTable& t) {      /* not inside a capture: called from create() */
+  const size_t smem = t.ctx->hot_tma ? 128 + (size_t)8 * kHotRows * t.Dp * sizeof(float) : 0;
+  switch (t.tpl) {
+    case 1: t.lookup_occ = lookup_occupancy<1>(smem); break;
+    case 2: t.lookup_occ = lookup_occupancy<2>(smem); break;
+    case 4: t.lookup_occ = lookup_occupancy<4>(smem); break;
+    case 8: t.lookup_occ = lookup_occupancy<8>(smem); break;
+    case 16: t.lookup_occ = lookup_occupancy<16>(smem); break;
+    default: t.lookup_occ = lookup_occupancy<32>(smem); break;
+  }
+}
+
 void EmbTable::create(Ctx* c, int F_, int D_, int64_t capacity, const ps_updater_spec& u, int64_t max_lookups) {
   PS_REQUIRE(F_ > 0 && D_ > 0 && D_ <= 128, PS_ERR_ARG, "embedding: need F > 0 and 0 < D <= 128");
   PS_REQUIRE(capacity > 0 && capacity < (1ll << 31), PS_ERR_ARG, "embedding: capacity must be in (0, 2^31)");
@@ -690,6 +739,7 @@ void EmbTable::create(Ctx* c, int F_, int D_, int64_t capacity, const ps_updater
   counters = dmalloc_zero<uint32_t>(CNT_WORDS, ctx->stream);
   reserve(max_lookups > 0 ? max_lookups : 1);
   scatter_update(nullptr, 0, nullptr, 0, 0, 2, nullptr);   /* fills scatter_occ (sizes the scatter's persistent grid) */
+  query_lookup_occupancy(*this);
 }
 
 void EmbTable::reserve(int64_t L) {
@@ -722,7 +772,9 @@ static void launch_lookup_t(EmbTable& t, LookupArgs& a, bool gather, bool aligne
 template <class IdT>
 static void launch_lookup(EmbTable& t, LookupArgs& a, bool gather) {
   const long ntasks = (long)((a.N + 31) / 32) * (a.F > 0 ? a.F : 1);
-  a.task_blocks = ceil_div(ntasks, 8);
+  /* persistent: one wave of blocks (their warps stride over the tasks three deep, see the kernel); small batches get a warp per task */
+  const int resident = t.ctx->num_sms * std::max(1, gather ? t.lookup_occ : 8);
+  a.task_blocks = (int)std::min<long>(ceil_div(ntasks, 8), resident);
   const int xblocks = (gather && a.X != nullptr) ? ceil_div((long)a.N * a.Xn, 1024) : 0;
   a.hot_tma = (gather && t.ctx->hot_tma) ? 1 : 0;
   const bool aligned = a.F == 0 || ((t.D % 4 == 0) && (a.ldo % 4 == 0) && ((uintptr_t)a.out % 16 == 0));
@@ -770,19 +822,26 @@ void EmbTable::lookup_packed(const uint64_t* keys, int n, float* out, P2PState* 
   launch_lookup<unsigned long long>(*this, a, out != nullptr || send_rows);
 }
 
+/* the scatter launch alone.  recs / lk / accp: the table's own slot records, lk_slot and accumulator rows — or, on the requester
+ * side of the sharded exchange, the per-batch de-duplication table (same 16 B record shape), its lookup index and the local
+ * per-key gradient sums (raw_row = 1: the record's last word is the row index itself).                                    */
+struct ScatterJob {
+  const EmbSlot* recs; const int32_t* lk; const uint32_t* mask; float* accp;
+  const float* delta; int ldd; const float* act; int lda; int N, F; const int* skip; int raw_row;
+};
 template <int TPL, int CPL>
-static void launch_scatter(EmbTable& t, const float* delta, int ldd, const float* act, int lda, int N, int F, int calls, const int* skip,
-                           const P2PState* p2p, const uint32_t* mask) {
+static void launch_scatter(EmbTable& t, const ScatterJob& j) {
   constexpr int PASSES = TPL >= 4 ? 4 : TPL;     /* warp tasks in flight per warp */
   constexpr int GPW = 32 / TPL;
-  const bool aligned = (t.D % 4 == 0) && (ldd % 4 == 0) && (lda % 4 == 0) && ((uintptr_t)delta % 16 == 0) && ((uintptr_t)act % 16 == 0);
-  /* samples per tile: small enough that there are >= 4 tiles per resident block (balance), at most 32 */
-  if (N == 0) {                                  /* EmbTable::create: resident blocks per SM of the two instantiations (not inside a capture) */
+  const bool aligned = (t.D % 4 == 0) && (j.ldd % 4 == 0) && (j.lda % 4 == 0) && ((uintptr_t)j.delta % 16 == 0) && ((uintptr_t)j.act % 16 == 0);
+  if (j.N == 0) {                                /* EmbTable::create: resident blocks per SM of the two instantiations (not inside a capture) */
     PS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t.scatter_occ[1], emb_scatter_kernel<TPL, CPL, PASSES, true>, 256, 0));
     PS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t.scatter_occ[0], emb_scatter_kernel<TPL, CPL, PASSES, false>, 256, 0));
     return;
   }
+  const int N = j.N;
   const int resident = t.ctx->num_sms * std::max(1, t.scatter_occ[aligned ? 1 : 0]);
+  /* samples per tile: small enough that there are >= 4 tiles per resident block (balance), at most 32 */
   int SB = GPW;
   while (SB * 2 <= 32 && ceil_div(N, SB * 2) >= 4 * resident) SB *= 2;
   const int grid = std::min(ceil_div(N, SB), resident);
@@ -790,22 +849,52 @@ static void launch_scatter(EmbTable& t, const float* delta, int ldd, const float
   const long per_block = (long)SB * ceil_div(ceil_div(N, SB), grid);
   const uint32_t hot_min = t.ctx->hot_min == 0xFFFFFFFFu ? 0xFFFFFFFFu : std::max<uint32_t>(t.ctx->hot_min, (uint32_t)(2L * N / per_block));
   if (aligned)
-    emb_scatter_kernel<TPL, CPL, PASSES, true><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.Dp, t.D, t.lk_slot, mask, t.MW, N, F, SB, delta, ldd, act, lda, t.acc, skip, p2p, hot_min);
+    emb_scatter_kernel<TPL, CPL, PASSES, true><<<grid, 256, 0, t.ctx->stream>>>(j.recs, t.Dp, t.D, j.lk, j.mask, t.MW, N, j.F, SB, j.delta, j.ldd, j.act, j.lda, j.accp, j.skip, j.raw_row, hot_min);
   else
-    emb_scatter_kernel<TPL, CPL, PASSES, false><<<grid, 256, 0, t.ctx->stream>>>(t.slots, t.Dp, t.D, t.lk_slot, mask, t.MW, N, F, SB, delta, ldd, act, lda, t.acc, skip, p2p, hot_min);
+    emb_scatter_kernel<TPL, CPL, PASSES, false><<<grid, 256, 0, t.ctx->stream>>>(j.recs, t.Dp, t.D, j.lk, j.mask, t.MW, N, j.F, SB, j.delta, j.ldd, j.act, j.lda, j.accp, j.skip, j.raw_row, hot_min);
   PS_LAUNCH_CHECK();
-  /* the update walks the unique list (<= L entries, how many is only known on the device): enough warps for one round at
-   * the typical unique fraction, a grid-stride loop beyond */
-  const long L = (long)N * F;
+  t.ctx->launches++;
+}
+
+static void dispatch_scatter(EmbTable& t, const ScatterJob& j) {
+  if (t.Dp % 8 == 0) {                          /* two 16 B chunks per lane: half the threads, twice the bytes in flight per thread */
+    switch (pow2_ge(t.Dp / 8)) {
+      case 1: launch_scatter<1, 2>(t, j); break;
+      case 2: launch_scatter<2, 2>(t, j); break;
+      case 4: launch_scatter<4, 2>(t, j); break;
+      case 8: launch_scatter<8, 2>(t, j); break;
+      default: launch_scatter<16, 2>(t, j); break;
+    }
+  } else {
+    switch (t.tpl) {
+      case 1: launch_scatter<1, 1>(t, j); break;
+      case 2: launch_scatter<2, 1>(t, j); break;
+      case 4: launch_scatter<4, 1>(t, j); break;
+      case 8: launch_scatter<8, 1>(t, j); break;
+      case 16: launch_scatter<16, 1>(t, j); break;
+      default: launch_scatter<32, 1>(t, j); break;
+    }
+  }
+}
+
+/* the update walks the unique list (<= L entries, how many is only known on the device): enough warps for one round at the
+ * typical unique fraction, a grid-stride loop beyond; a programmatic dependent of the scatter launched just before it */
+static void launch_update(EmbTable& t, long L, int calls, const int* skip, uint32_t* ucnt) {
   const int KPW = 32 / (t.Dp / 4);
   const int ugrid = (int)std::max<long>(1, std::min<long>(ceil_div(ceil_div(L, KPW), 8), (long)t.ctx->num_sms * 16));
   if (t.ctx->exact_updaters)
-    launch_pdl(t.ctx, emb_update_kernel<true>, dim3(ugrid), dim3(256), t.slots, t.rows, t.rs, t.Dp, t.D, (const int32_t*)t.uniq, t.acc, t.upd, calls, skip,
-               (uint32_t*)nullptr, t.counters);
+    launch_pdl(t.ctx, emb_update_kernel<true>, dim3(ugrid), dim3(256), t.slots, t.rows, t.rs, t.Dp, t.D, (const int32_t*)t.uniq, t.acc, t.upd, calls, skip, ucnt, t.counters);
   else
-    launch_pdl(t.ctx, emb_update_kernel<false>, dim3(ugrid), dim3(256), t.slots, t.rows, t.rs, t.Dp, t.D, (const int32_t*)t.uniq, t.acc, t.upd, calls, skip,
-               (uint32_t*)nullptr, t.counters);
-  t.ctx->launches += 2;
+    launch_pdl(t.ctx, emb_update_kernel<false>, dim3(ugrid), dim3(256), t.slots, t.rows, t.rs, t.Dp, t.D, (const int32_t*)t.uniq, t.acc, t.upd, calls, skip, ucnt, t.counters);
+  t.ctx->launches++;
+}
+
+/* requester side of the push: per-lookup row gradients (ReLU mask from `act`) summed per unique key of THIS rank's batch into
+ * gacc[bucket position], with the same three levels of pre-summation as the local backward — a hot key's thousands of
+ * occurrences leave a block once instead of serialising on one L2 line                                                  */
+void EmbTable::scatter_rows(const void* batch_slots, const int32_t* lk_batch, float* gacc, const float* delta, int ldd, const float* act, int lda, int N) {
+  ScatterJob j{reinterpret_cast<const EmbSlot*>(batch_slots), lk_batch, nullptr, gacc, delta, ldd, act, lda, N, F, nullptr, 1};
+  dispatch_scatter(*this, j);
 }
 
 void EmbTable::scatter_update_entries(const P2PState* p2p, int n, int calls, const int* skip_flag) {
@@ -814,45 +903,21 @@ void EmbTable::scatter_update_entries(const P2PState* p2p, int n, int calls, con
   const int grid = (int)std::max<long>(1, std::min<long>(ceil_div((long)n * CH, 256), (long)ctx->num_sms * 8));
   emb_scatter_entries_kernel<<<grid, 256, 0, ctx->stream>>>(slots, Dp, lk_slot, acc, ucnt, skip_flag, p2p);
   PS_LAUNCH_CHECK();
-  const int KPW = 32 / CH;
-  const int ugrid = (int)std::max<long>(1, std::min<long>(ceil_div(ceil_div((long)n, KPW), 8), (long)ctx->num_sms * 16));
-  if (ctx->exact_updaters)
-    launch_pdl(ctx, emb_update_kernel<true>, dim3(ugrid), dim3(256), slots, rows, rs, Dp, D, (const int32_t*)uniq, acc, upd, calls, skip_flag, ucnt, counters);
-  else
-    launch_pdl(ctx, emb_update_kernel<false>, dim3(ugrid), dim3(256), slots, rows, rs, Dp, D, (const int32_t*)uniq, acc, upd, calls, skip_flag, ucnt, counters);
-  ctx->launches += 2;
+  ctx->launches++;
+  launch_update(*this, n, calls, skip_flag, ucnt);
   last_L = 0;
 }
 
-void EmbTable::scatter_update(const float* delta, int ldd, const float* act, int lda, int N, int calls, const int* skip_flag, int F_eff,
-                              const P2PState* p2p, bool use_mask) {
+void EmbTable::scatter_update(const float* delta, int ldd, const float* act, int lda, int N, int calls, const int* skip_flag, int F_eff, bool use_mask) {
   const int Fe = F_eff > 0 ? F_eff : F;
   if (N > 0) {                                  /* N == 0: occupancy query from create() */
     PS_REQUIRE((int64_t)N * Fe == last_L, PS_ERR_STATE, "embedding: backward without a matching forward");
     PS_REQUIRE(calls == 1 || calls == 2, PS_ERR_ARG, "embedding: backward calls must be 1 or 2");
   }
-  const uint32_t* mask = use_mask ? lk_mask : nullptr;
-  if (use_mask) act = nullptr;
-  if (Dp % 8 == 0) {                            /* two 16 B chunks per lane: half the threads, twice the bytes in flight per thread */
-    switch (pow2_ge(Dp / 8)) {
-      case 1: launch_scatter<1, 2>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p, mask); break;
-      case 2: launch_scatter<2, 2>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p, mask); break;
-      case 4: launch_scatter<4, 2>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p, mask); break;
-      case 8: launch_scatter<8, 2>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p, mask); break;
-      default: launch_scatter<16, 2>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p, mask); break;
-    }
-  } else {
-    switch (tpl) {
-      case 1: launch_scatter<1, 1>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p, mask); break;
-      case 2: launch_scatter<2, 1>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p, mask); break;
-      case 4: launch_scatter<4, 1>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p, mask); break;
-      case 8: launch_scatter<8, 1>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p, mask); break;
-      case 16: launch_scatter<16, 1>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p, mask); break;
-      default: launch_scatter<32, 1>(*this, delta, ldd, act, lda, N, Fe, calls, skip_flag, p2p, mask); break;
-    }
-  }
+  ScatterJob j{slots, lk_slot, use_mask ? lk_mask : nullptr, acc, delta, ldd, use_mask ? nullptr : act, lda, N, Fe, skip_flag, 0};
+  dispatch_scatter(*this, j);
   if (N == 0) return;
-  PS_LAUNCH_CHECK();
+  launch_update(*this, (long)N * Fe, calls, skip_flag, nullptr);
   last_L = 0;
 }
 

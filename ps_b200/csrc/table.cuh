@@ -77,6 +77,7 @@ struct EmbTable {
   uint32_t* counters = nullptr;
   int64_t last_L = 0;
   int scatter_occ[2] = {1, 1};         /* resident scatter blocks per SM (unaligned / aligned instantiation) */
+  int lookup_occ = 2;                  /* resident blocks per SM of the gathering lookup kernel (sizes its persistent grid) */
 
   void create(Ctx* c, int F_, int D_, int64_t capacity, const ps_updater_spec& u, int64_t max_lookups);
   void destroy();
@@ -95,8 +96,9 @@ struct EmbTable {
   void scatter_update_entries(const P2PState* p2p, int n, int calls, const int* skip_flag);
   /* pre-summed scatter-add, then occurrence normalisation + updater step + per-batch reset (two launches, see table.cu).
    * The ReLU mask comes from the lookup's mask bits (use_mask), from `act` (non-null), or is taken as already applied. */
-  void scatter_update(const float* delta, int ldd, const float* act, int lda, int N, int calls, const int* skip_flag, int F_eff = 0,
-                      const P2PState* p2p = nullptr /* delta = this step's grads_in mailbox */, bool use_mask = false);
+  void scatter_update(const float* delta, int ldd, const float* act, int lda, int N, int calls, const int* skip_flag, int F_eff = 0, bool use_mask = false);
+  /* requester side of the sharded push: this batch's row gradients summed per unique key into gacc (see table.cu) */
+  void scatter_rows(const void* batch_slots, const int32_t* lk_batch, float* gacc, const float* delta, int ldd, const float* act, int lda, int N);
   /* forget the batch without updating (predict path / early exit): cnt = 0 for touched slots */
   void clear_batch();
   void check_errors();                 /* syncs; throws PS_ERR_CAPACITY if an insert found the table full */
