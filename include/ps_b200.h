@@ -187,6 +187,8 @@ int ps_model_backward_update(ps_model* m, const float* delta_top, int N, float l
 int ps_model_submit_text(ps_model* m, const char* text, size_t len, int N);
 /* status of the step last collected: skipped (early exit / dropped batch / full table), bad text lines, unique embedding keys */
 int ps_model_step_info(ps_model* m, int* skipped, uint32_t* bad_lines, uint32_t* n_unique);
+/* the geometry the model was created with (a binding checks its callers' array lengths against it before any native read) */
+int ps_model_shape(ps_model* m, int* F, int* D, int* Xn);
 /* the step on inputs ALREADY resident in device memory (bench `value` leg); loss stays on the
  * device until ps_model_read_loss.                                                         */
 int ps_model_train_step_dev(ps_model* m, const int64_t* E_dev, const float* X_dev, const int64_t* W_dev, const float* Y_dev, int N);
@@ -201,6 +203,13 @@ int ps_model_predict(ps_model* m, const int64_t* E, const float* X, const int64_
 int ps_model_get(ps_model* m, const char* key, float* out, int cap, int* n);
 int ps_model_put(ps_model* m, const char* key, const float* in, int n);      /* KVStore.put */
 /* updater state of a key: which = 0 Adam M / Ftrl Z, 1 Adam V / Ftrl N                       */
+/* PSClient.getList / updateList (net/PSClient.java:72-97,128-151; server side net/PServer.java:102-117,144-162) by reference key
+ * strings, batched: embedding keys ("emF<j>.<id>", the bulk of any list) are served by ONE lookup / insert kernel, other keys one
+ * by one.  Row i of out / io starts at i*stride floats.  get: found[i] = number of floats written (0 = absent, Resp.ec 204).
+ * update: lens[i] floats of io row i are offered; replace = 0 is the reference's insert-if-absent ("重复key不替换"), io then
+ * receives the winning value of every key.                                                                                   */
+int ps_model_get_list(ps_model* m, const char* const* keys, int n, float* out, int stride, int32_t* found);
+int ps_model_update_list(ps_model* m, const char* const* keys, int n, float* io, int stride, const int32_t* lens, int replace);
 int ps_model_get_state(ps_model* m, const char* key, int which, float* out, int cap, int* n);
 /* Layer.getA() / getDelta() after the last step (layer/Layer.java:16-45): what = 0 A, 1 delta;
  * layers: "embedding", "concat", "fc<i>", "wide", "addWideDeep"                               */
@@ -305,6 +314,7 @@ typedef struct ps_reader ps_reader;
 int ps_libsvm_parse_line(const char* line, size_t len, int F, int Xn, int64_t wide_size, int64_t* E, float* X, int64_t* W, float* Y, int* status);
 int ps_reader_open(const char* path, int F, int Xn, int64_t wide_size, int batch, int offset, int step, int threads, ps_reader** out);
 int ps_reader_next(ps_reader* r, int64_t* E, float* X, int64_t* W, float* Y, int* rows);
+int ps_reader_shape(ps_reader* r, int* batch, int* F, int* Xn);   /* ps_reader_next writes up to batch rows into every output */
 int ps_reader_reset(ps_reader* r);                     /* DataSet.reset (DataSet.java:61-67) */
 int ps_reader_stats(ps_reader* r, int64_t* lines, int64_t* batches, int64_t* dropped_batches);
 int ps_reader_close(ps_reader* r);

@@ -19,6 +19,13 @@ public final class PsNative {
 	/** E, W: F x N ids carried as floats exactly as CTR.parseFeature builds them (CTR.java:47-68). */
 	public static native float modelTrainStep(long model, float[] E, float[] X, float[] W, float[] Y, int N);
 	public static native float[] modelPredict(long model, float[] E, float[] X, float[] W, int N, int outRows);
+	/** the forward loop of DNN.train / WideDeepNN.train (DNN.java:44-46): returns P (N floats); the batch stays pending on the device */
+	public static native float[] modelForward(long model, float[] E, float[] X, float[] W, int N);
+	/** the reverse loop + KVStore.update + clear given deltaTop = loss.backward(P, Y) (DNN.java:49,64-68; Trainer.java:93,95) */
+	public static native void modelBackwardUpdate(long model, float[] deltaTop, int N, float loss);
+	/** PSClient.getList / updateList: one batched call; row i is null when key i is absent / the winning value of key i */
+	public static native float[][] modelGetList(long model, String[] keys);
+	public static native float[][] modelUpdateList(long model, String[] keys, float[][] values, boolean replace);
 	public static native float[] modelGet(long model, String key);                     // null when absent (KVStore.get)
 	public static native void modelPut(long model, String key, float[] value);
 	public static native float[] modelTap(long model, String layer, int what);        // 0 = A, 1 = delta

@@ -1,0 +1,53 @@
+package net;
+
+import nativeps.PsNative;
+import org.jblas.FloatMatrix;
+import store.KVStore;
+
+import java.util.ArrayList;
+import java.util.HashMap;
+import java.util.List;
+import java.util.Map;
+
+/**
+ * Drop-in for net/PSClient.java (ctors :31/:35, close :42, get :47, getList :72, update :100, updateList :128, push :154,
+ * barrier :177): the same public methods, served by the GPU-resident store of this process instead of a gRPC PServer.
+ * getList / updateList are ONE batched native call each (ps_model_get_list / ps_model_update_list — embedding keys go through
+ * one lookup / insert kernel).  push / barrier are no-ops: a worker's gradients never leave the device — KVStore.update's
+ * per-key client.push (KVStore.java:257-260) and the server-side sum + psUpdate (PServer.java:164-214) are what
+ * ps_model_backward_update (one GPU) or ps_model_p2p_submit (key-hash sharded over the GPUs of the box) do in their kernels.
+ * SOURCE ONLY: no JDK in the build image.
+ */
+public class PSClient {
+	static final int STRIDE = 1 << 16;             // floats reserved per listed key on the wire to the native call (embedding rows use D of them)
+	public PSClient() {}
+	public PSClient(String host, int port) {}
+	public void close() {}
+
+	public FloatMatrix get(String key) { return KVStore.ins().get(key); }
+	public Map<String, FloatMatrix> getList(List<String> keys) {
+		Map<String, FloatMatrix> out = new HashMap<String, FloatMatrix>();
+		float[][] rows = PsNative.modelGetList(KVStore.ins().model(), keys.toArray(new String[0]));
+		for (int i = 0; i < keys.size(); i++) out.put(keys.get(i), rows[i] == null ? null : new FloatMatrix(rows[i].length, 1, rows[i]));
+		return out;
+	}
+	public FloatMatrix update(String key, FloatMatrix weights, boolean replace) {
+		Map<String, FloatMatrix> one = new HashMap<String, FloatMatrix>();
+		one.put(key, weights);
+		return updateList(one, replace).get(key);
+	}
+	public Map<String, FloatMatrix> updateList(Map<String, FloatMatrix> updates, boolean replace) {
+		List<String> keys = new ArrayList<String>(updates.keySet());
+		float[][] offered = new float[keys.size()][];
+		for (int i = 0; i < keys.size(); i++) offered[i] = updates.get(keys.get(i)).data;
+		float[][] winners = PsNative.modelUpdateList(KVStore.ins().model(), keys.toArray(new String[0]), offered, replace);
+		Map<String, FloatMatrix> out = new HashMap<String, FloatMatrix>();
+		for (int i = 0; i < keys.size(); i++) {
+			FloatMatrix o = updates.get(keys.get(i));
+			out.put(keys.get(i), new FloatMatrix(o.rows, o.columns, winners[i]));
+		}
+		return out;
+	}
+	public void push(String key, FloatMatrix gradient, String updaterKey, boolean async) {}
+	public void barrier() {}
+}

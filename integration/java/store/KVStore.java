@@ -13,9 +13,9 @@ import java.util.concurrent.Callable;
  * asyncWait :113), backed by the GPU-resident store of libps_b200.so instead of Java maps.
  *
  * Differences a caller can observe (DESIGN.md §5.7): get() returns a host SNAPSHOT, not the live
- * matrix; lazily created weights come from the seeded initialiser of ps_spec.h; sum()/update()
- * for keys the native step already handled are no-ops because the native step applies
- * KVStore.update + clear itself, fused into the backward kernels.
+ * matrix; lazily created weights come from the seeded initialiser of ps_spec.h; sum() / update() / clear() are no-ops
+ * because ps_model_backward_update — started by the last layer's backward() — applies KVStore.sum + update + clear itself,
+ * fused into the backward kernels.  FC weights come back as out x in matrices (column-major, like the reference's).
  */
 public class KVStore {
 	private static final KVStore ins = new KVStore();
@@ -52,7 +52,11 @@ public class KVStore {
 	public void asyncGet(String key, Callable<FloatMatrix> init) {}                        // the probe kernel is the batched prefetch
 	public void asyncWait() {}
 
-	private static FloatMatrix shaped(String key, float[] v) {
-		return new FloatMatrix(v.length, 1, v);    // callers that need out x in reshape by their own dims (FcLayer knows them)
+	private final java.util.Map<String, int[]> shapes = new java.util.HashMap<String, int[]>();
+	/** layer.FcLayer registers out x in for "fc<i>.weights" so that get() hands back the reference's shape */
+	public void shape(String key, int rows, int cols) { shapes.put(key, new int[]{rows, cols}); }
+	private FloatMatrix shaped(String key, float[] v) {
+		int[] s = shapes.get(key);
+		return s != null && s[0] * s[1] == v.length ? new FloatMatrix(s[0], s[1], v) : new FloatMatrix(v.length, 1, v);
 	}
 }

@@ -8,6 +8,7 @@
  */
 #include <jni.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "ps_b200.h"
 
@@ -17,12 +18,22 @@ static void throw_ps(JNIEnv* env, int rc) {
   (*env)->ThrowNew(env, cls, ps_last_error());
 }
 
+/* every Java array is checked against the batch geometry BEFORE the native call reads it: a short array would otherwise be read
+ * (or, for the reader's outputs, written) past its end */
+static int check_len(JNIEnv* env, jarray a, jlong need, const char* what) {
+  if (a == NULL) return 1;
+  if ((jlong)(*env)->GetArrayLength(env, a) >= need) return 1;
+  jclass cls = (*env)->FindClass(env, "java/lang/IllegalArgumentException");
+  if (cls) (*env)->ThrowNew(env, cls, what);
+  return 0;
+}
+
 static int64_t* widen_ids(JNIEnv* env, jfloatArray a, jsize* n) {   /* float-carried ids (exact < 2^24) */
   if (!a) { *n = 0; return NULL; }
   *n = (*env)->GetArrayLength(env, a);
   jfloat* f = (*env)->GetPrimitiveArrayCritical(env, a, NULL);
-  int64_t* out = (int64_t*)malloc(sizeof(int64_t) * (size_t)*n);
-  for (jsize i = 0; i < *n; ++i) out[i] = (int64_t)f[i];
+  int64_t* out = (int64_t*)malloc(sizeof(int64_t) * (size_t)(*n > 0 ? *n : 1));
+  for (jsize i = 0; out != NULL && i < *n; ++i) out[i] = (int64_t)f[i];
   (*env)->ReleasePrimitiveArrayCritical(env, a, f, JNI_ABORT);
   return out;
 }
@@ -59,6 +70,10 @@ JNIEXPORT void JNICALL Java_nativeps_PsNative_modelDestroy(JNIEnv* env, jclass c
 JNIEXPORT jfloat JNICALL Java_nativeps_PsNative_modelTrainStep(JNIEnv* env, jclass c, jlong m, jfloatArray E, jfloatArray X, jfloatArray W,
                                                                jfloatArray Y, jint N) {
   jsize ne, nw;
+  int F = 0, Xn = 0;
+  throw_ps(env, ps_model_shape((ps_model*)(intptr_t)m, &F, NULL, &Xn));
+  if (N <= 0 || !check_len(env, E, (jlong)N * F, "E shorter than F x N") || !check_len(env, W, (jlong)N * F, "W shorter than F x N") ||
+      !check_len(env, X, (jlong)N * Xn, "X shorter than Xn x N") || !check_len(env, Y, N, "Y shorter than N")) return 0.f;
   int64_t* e = widen_ids(env, E, &ne);
   int64_t* w = widen_ids(env, W, &nw);
   jfloat* x = (*env)->GetFloatArrayElements(env, X, NULL);
@@ -131,6 +146,10 @@ JNIEXPORT jfloatArray JNICALL Java_nativeps_PsNative_updaterParse(JNIEnv* env, j
 JNIEXPORT jfloatArray JNICALL Java_nativeps_PsNative_modelPredict(JNIEnv* env, jclass c, jlong m, jfloatArray E, jfloatArray X, jfloatArray W,
                                                                   jint N, jint outRows) {
   jsize ne, nw;
+  int F = 0, Xn = 0;
+  throw_ps(env, ps_model_shape((ps_model*)(intptr_t)m, &F, NULL, &Xn));
+  if (N <= 0 || outRows <= 0 || !check_len(env, E, (jlong)N * F, "E shorter than F x N") || !check_len(env, W, (jlong)N * F, "W shorter than F x N") ||
+      !check_len(env, X, (jlong)N * Xn, "X shorter than Xn x N")) return NULL;
   int64_t* e = widen_ids(env, E, &ne);
   int64_t* w = widen_ids(env, W, &nw);
   jfloat* x = (*env)->GetFloatArrayElements(env, X, NULL);
@@ -200,9 +219,15 @@ JNIEXPORT void JNICALL Java_nativeps_PsNative_fcPut(JNIEnv* env, jclass c, jlong
 
 /* ---- data.DataSet (ps_reader_*): ids are widened back to floats because CTR.parseFeature's "E"/"W" are FloatMatrix ---- */
 JNIEXPORT jint JNICALL Java_nativeps_PsNative_readerNext(JNIEnv* env, jclass c, jlong r, jfloatArray E, jfloatArray X, jfloatArray W, jfloatArray Y) {
-  jsize ne = (*env)->GetArrayLength(env, E);
-  int64_t* e = (int64_t*)malloc(sizeof(int64_t) * (size_t)ne);
-  int64_t* w = (int64_t*)malloc(sizeof(int64_t) * (size_t)ne);
+  int batch = 0, F = 0, Xn = 0;
+  throw_ps(env, ps_reader_shape((ps_reader*)(intptr_t)r, &batch, &F, &Xn));
+  /* ps_reader_next writes up to batch rows: every output array must hold a whole batch */
+  if (!check_len(env, E, (jlong)batch * F, "E shorter than F x batch") || !check_len(env, W, (jlong)batch * F, "W shorter than F x batch") ||
+      !check_len(env, X, (jlong)batch * Xn, "X shorter than Xn x batch") || !check_len(env, Y, batch, "Y shorter than batch")) return 0;
+  jsize ne = (jsize)batch * F;
+  int64_t* e = (int64_t*)malloc(sizeof(int64_t) * (size_t)(ne > 0 ? ne : 1));
+  int64_t* w = (int64_t*)malloc(sizeof(int64_t) * (size_t)(ne > 0 ? ne : 1));
+  if (e == NULL || w == NULL) { free(e); free(w); throw_ps(env, PS_ERR_ARG); return 0; }
   jfloat* x = (*env)->GetFloatArrayElements(env, X, NULL);
   jfloat* y = (*env)->GetFloatArrayElements(env, Y, NULL);
   int rows = 0;
@@ -212,7 +237,7 @@ JNIEXPORT jint JNICALL Java_nativeps_PsNative_readerNext(JNIEnv* env, jclass c, 
   if (rc == PS_OK && rows > 0) {
     jfloat* ef = (*env)->GetFloatArrayElements(env, E, NULL);
     jfloat* wf = (*env)->GetFloatArrayElements(env, W, NULL);
-    for (jsize i = 0; i < ne; ++i) { ef[i] = (jfloat)e[i]; wf[i] = (jfloat)w[i]; }   /* exact: the reader already applied (float) idx */
+    for (jsize i = 0; i < (jsize)rows * F; ++i) { ef[i] = (jfloat)e[i]; wf[i] = (jfloat)w[i]; }   /* only the rows delivered; exact: the reader already applied (float) idx */
     (*env)->ReleaseFloatArrayElements(env, E, ef, 0);
     (*env)->ReleaseFloatArrayElements(env, W, wf, 0);
   }
@@ -231,3 +256,92 @@ JNIEXPORT jlong JNICALL Java_nativeps_PsNative_readerOpen(JNIEnv* env, jclass c,
 }
 JNIEXPORT void JNICALL Java_nativeps_PsNative_readerReset(JNIEnv* env, jclass c, jlong r) { throw_ps(env, ps_reader_reset((ps_reader*)(intptr_t)r)); }
 JNIEXPORT void JNICALL Java_nativeps_PsNative_readerClose(JNIEnv* env, jclass c, jlong r) { ps_reader_close((ps_reader*)(intptr_t)r); }
+
+/* ---- Model.train call by call: the loss stays in Java (DNN.java:44-68) ---- */
+JNIEXPORT jfloatArray JNICALL Java_nativeps_PsNative_modelForward(JNIEnv* env, jclass c, jlong m, jfloatArray E, jfloatArray X, jfloatArray W, jint N) {
+  jsize ne, nw;
+  int F = 0, Xn = 0;
+  throw_ps(env, ps_model_shape((ps_model*)(intptr_t)m, &F, NULL, &Xn));
+  if (N <= 0 || !check_len(env, E, (jlong)N * F, "E shorter than F x N") || !check_len(env, W, (jlong)N * F, "W shorter than F x N") ||
+      !check_len(env, X, (jlong)N * Xn, "X shorter than Xn x N")) return NULL;
+  int64_t* e = widen_ids(env, E, &ne);
+  int64_t* w = widen_ids(env, W, &nw);
+  jfloat* x = (*env)->GetFloatArrayElements(env, X, NULL);
+  jfloatArray out = (*env)->NewFloatArray(env, N);
+  jfloat* p = (*env)->GetFloatArrayElements(env, out, NULL);
+  int rc = ps_model_forward((ps_model*)(intptr_t)m, e, x, w, N, p);             /* the forward loop; P = layers.get(last).getA() */
+  (*env)->ReleaseFloatArrayElements(env, out, p, 0);
+  (*env)->ReleaseFloatArrayElements(env, X, x, JNI_ABORT);
+  free(e); free(w);
+  throw_ps(env, rc);
+  return out;
+}
+JNIEXPORT void JNICALL Java_nativeps_PsNative_modelBackwardUpdate(JNIEnv* env, jclass c, jlong m, jfloatArray deltaTop, jint N, jfloat loss) {
+  if (N <= 0 || !check_len(env, deltaTop, N, "delta shorter than N")) return;
+  jfloat* d = (*env)->GetFloatArrayElements(env, deltaTop, NULL);
+  int rc = ps_model_backward_update((ps_model*)(intptr_t)m, d, N, loss);        /* the reverse loop + KVStore.update + clear */
+  (*env)->ReleaseFloatArrayElements(env, deltaTop, d, JNI_ABORT);
+  throw_ps(env, rc);
+}
+
+/* ---- PSClient.getList / updateList: one batched native call per list ---- */
+#define PS_JNI_LIST_STRIDE 65536
+JNIEXPORT jobjectArray JNICALL Java_nativeps_PsNative_modelGetList(JNIEnv* env, jclass c, jlong m, jobjectArray keys) {
+  const jsize n = (*env)->GetArrayLength(env, keys);
+  int D = 0;
+  throw_ps(env, ps_model_shape((ps_model*)(intptr_t)m, NULL, &D, NULL));
+  const char** ks = (const char**)malloc(sizeof(char*) * (size_t)(n > 0 ? n : 1));
+  int32_t* found = (int32_t*)calloc((size_t)(n > 0 ? n : 1), sizeof(int32_t));
+  int stride = D > 0 ? D : 1, all_emb = 1;
+  for (jsize i = 0; i < n; ++i) {
+    ks[i] = (*env)->GetStringUTFChars(env, (jstring)(*env)->GetObjectArrayElement(env, keys, i), NULL);
+    if (strncmp(ks[i], "emF", 3) != 0) all_emb = 0;
+  }
+  if (!all_emb) stride = PS_JNI_LIST_STRIDE;        /* dense parameters in the list: rows as wide as the widest FcLayer weight may get */
+  float* out = (float*)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1) * (size_t)stride);
+  int rc = ps_model_get_list((ps_model*)(intptr_t)m, ks, n, out, stride, found);
+  jobjectArray res = (*env)->NewObjectArray(env, n, (*env)->FindClass(env, "[F"), NULL);
+  for (jsize i = 0; i < n; ++i) {
+    if (rc == PS_OK && found[i] > 0) {
+      jfloatArray row = (*env)->NewFloatArray(env, found[i]);
+      (*env)->SetFloatArrayRegion(env, row, 0, found[i], out + (size_t)i * stride);
+      (*env)->SetObjectArrayElement(env, res, i, row);
+      (*env)->DeleteLocalRef(env, row);
+    }
+    (*env)->ReleaseStringUTFChars(env, (jstring)(*env)->GetObjectArrayElement(env, keys, i), ks[i]);
+  }
+  free(out); free(found); free((void*)ks);
+  throw_ps(env, rc);
+  return res;
+}
+JNIEXPORT jobjectArray JNICALL Java_nativeps_PsNative_modelUpdateList(JNIEnv* env, jclass c, jlong m, jobjectArray keys, jobjectArray values, jboolean replace) {
+  const jsize n = (*env)->GetArrayLength(env, keys);
+  if (!check_len(env, values, n, "fewer values than keys")) return NULL;
+  const char** ks = (const char**)malloc(sizeof(char*) * (size_t)(n > 0 ? n : 1));
+  int32_t* lens = (int32_t*)calloc((size_t)(n > 0 ? n : 1), sizeof(int32_t));
+  int stride = 1;
+  for (jsize i = 0; i < n; ++i) {
+    lens[i] = (*env)->GetArrayLength(env, (jarray)(*env)->GetObjectArrayElement(env, values, i));
+    if (lens[i] > stride) stride = lens[i];
+  }
+  float* io = (float*)calloc((size_t)(n > 0 ? n : 1) * (size_t)stride, sizeof(float));
+  for (jsize i = 0; i < n; ++i) {
+    ks[i] = (*env)->GetStringUTFChars(env, (jstring)(*env)->GetObjectArrayElement(env, keys, i), NULL);
+    jfloatArray v = (jfloatArray)(*env)->GetObjectArrayElement(env, values, i);
+    jfloat* p = (*env)->GetFloatArrayElements(env, v, NULL);
+    memcpy(io + (size_t)i * stride, p, sizeof(float) * (size_t)lens[i]);
+    (*env)->ReleaseFloatArrayElements(env, v, p, JNI_ABORT);
+  }
+  int rc = ps_model_update_list((ps_model*)(intptr_t)m, ks, n, io, stride, lens, replace ? 1 : 0);   /* PServer.upsertList: insert-if-absent unless replace */
+  jobjectArray res = (*env)->NewObjectArray(env, n, (*env)->FindClass(env, "[F"), NULL);
+  for (jsize i = 0; i < n; ++i) {
+    jfloatArray row = (*env)->NewFloatArray(env, lens[i]);
+    (*env)->SetFloatArrayRegion(env, row, 0, lens[i], io + (size_t)i * stride);
+    (*env)->SetObjectArrayElement(env, res, i, row);
+    (*env)->DeleteLocalRef(env, row);
+    (*env)->ReleaseStringUTFChars(env, (jstring)(*env)->GetObjectArrayElement(env, keys, i), ks[i]);
+  }
+  free(io); free(lens); free((void*)ks);
+  throw_ps(env, rc);
+  return res;
+}

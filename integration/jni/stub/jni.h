@@ -21,6 +21,9 @@ typedef jobject jstring;
 typedef jobject jarray;
 typedef jarray jfloatArray;
 typedef jarray jintArray;
+typedef jarray jbyteArray;
+typedef jarray jobjectArray;
+typedef signed char jbyte;
 typedef jobject jthrowable;
 #define JNI_FALSE 0
 #define JNI_TRUE 1
@@ -43,6 +46,11 @@ struct JNINativeInterface_ {
   void (*ReleaseFloatArrayElements)(JNIEnv* env, jfloatArray array, jfloat* elems, jint mode);
   jint* (*GetIntArrayElements)(JNIEnv* env, jintArray array, jboolean* isCopy);
   void (*ReleaseIntArrayElements)(JNIEnv* env, jintArray array, jint* elems, jint mode);
+  jobjectArray (*NewObjectArray)(JNIEnv* env, jsize length, jclass elementClass, jobject initialElement);
+  jobject (*GetObjectArrayElement)(JNIEnv* env, jobjectArray array, jsize index);
+  void (*SetObjectArrayElement)(JNIEnv* env, jobjectArray array, jsize index, jobject value);
+  void (*SetFloatArrayRegion)(JNIEnv* env, jfloatArray array, jsize start, jsize len, const jfloat* buf);
+  void (*DeleteLocalRef)(JNIEnv* env, jobject localRef);
   void* (*GetPrimitiveArrayCritical)(JNIEnv* env, jarray array, jboolean* isCopy);
   void (*ReleasePrimitiveArrayCritical)(JNIEnv* env, jarray array, void* carray, jint mode);
 };

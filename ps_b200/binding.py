@@ -81,12 +81,15 @@ SYMBOLS = {
     "ps_model_backward_update": (_i, [_vp, _vp, _i, _f]),
     "ps_model_submit_text": (_i, [_vp, _vp, C.c_size_t, _i]),
     "ps_model_step_info": (_i, [_vp, C.POINTER(_i), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "ps_model_shape": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "ps_model_train_step_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _i]),
     "ps_model_read_loss": (_i, [_vp, C.POINTER(_f)]),
     "ps_model_loss_dev": (_i, [_vp, _pp]),
     "ps_model_predict": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     "ps_model_get": (_i, [_vp, C.c_char_p, _vp, _i, C.POINTER(_i)]),
     "ps_model_put": (_i, [_vp, C.c_char_p, _vp, _i]),
+    "ps_model_get_list": (_i, [_vp, C.POINTER(C.c_char_p), _i, _vp, _i, _vp]),
+    "ps_model_update_list": (_i, [_vp, C.POINTER(C.c_char_p), _i, _vp, _i, _vp, _i]),
     "ps_model_get_state": (_i, [_vp, C.c_char_p, _i, _vp, _i, C.POINTER(_i)]),
     "ps_model_tap": (_i, [_vp, C.c_char_p, _i, _vp, _i, C.POINTER(_i)]),
     "ps_model_num_keys": (_i, [_vp, C.POINTER(_i64)]),
@@ -124,6 +127,7 @@ SYMBOLS = {
     "ps_libsvm_parse_dev": (_i, [_vp, _vp, C.c_size_t, _i, _i, _i64, _i, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i)]),
     "ps_reader_open": (_i, [C.c_char_p, _i, _i, _i64, _i, _i, _i, _i, _pp]),
     "ps_reader_next": (_i, [_vp, _vp, _vp, _vp, _vp, C.POINTER(_i)]),
+    "ps_reader_shape": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "ps_reader_reset": (_i, [_vp]),
     "ps_reader_stats": (_i, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "ps_reader_close": (_i, [_vp]),
@@ -492,6 +496,28 @@ class Model:
 
     def get(self, key):
         return self._fetch(lib().ps_model_get, key)
+
+    def get_list(self, keys, stride):
+        """PSClient.getList: dict key -> array (None when absent)."""
+        arr = (C.c_char_p * len(keys))(*[k.encode() for k in keys])
+        out = np.zeros((len(keys), stride), np.float32)
+        found = np.zeros(len(keys), np.int32)
+        check(lib().ps_model_get_list(self.h, arr, len(keys), _p(out), stride, _p(found)))
+        return {k: (out[i, : found[i]].copy() if found[i] else None) for i, k in enumerate(keys)}
+
+    def update_list(self, updates, replace=False):
+        """PSClient.updateList: offers {key: array}; returns {key: winning array} (insert-if-absent unless replace)."""
+        keys = list(updates)
+        stride = max(len(np.ravel(v)) for v in updates.values())
+        io = np.zeros((len(keys), stride), np.float32)
+        lens = np.zeros(len(keys), np.int32)
+        for i, k in enumerate(keys):
+            v = np.ravel(np.asarray(updates[k], np.float32))
+            io[i, : v.size] = v
+            lens[i] = v.size
+        arr = (C.c_char_p * len(keys))(*[k.encode() for k in keys])
+        check(lib().ps_model_update_list(self.h, arr, len(keys), _p(io), stride, _p(lens), 1 if replace else 0))
+        return {k: io[i, : lens[i]].copy() for i, k in enumerate(keys)}
 
     def get_state(self, key, which):
         return self._fetch(lib().ps_model_get_state, key, which)

@@ -387,6 +387,14 @@ int ps_model_submit_text(ps_model* m, const char* text, size_t len, int N) {
   m->m.submit_text(text, len, N);
   PS_CATCH
 }
+int ps_model_shape(ps_model* m, int* F, int* D, int* Xn) {
+  PS_TRY
+  PS_REQUIRE(m != nullptr, PS_ERR_ARG, "null model");
+  if (F) *F = m->m.F;
+  if (D) *D = m->m.D;
+  if (Xn) *Xn = m->m.Xn;
+  PS_CATCH
+}
 int ps_model_step_info(ps_model* m, int* skipped, uint32_t* bad_lines, uint32_t* n_unique) {
   PS_TRY
   PS_REQUIRE(m != nullptr, PS_ERR_ARG, "null model");
@@ -440,6 +448,70 @@ int ps_model_put(ps_model* m, const char* key, const float* in, int n) {
   PS_TRY
   PS_REQUIRE(m && key && in, PS_ERR_ARG, "null argument");
   m->m.put(key, in, n);
+  PS_CATCH
+}
+/* PSClient.getList / PServer.getList (PSClient.java:72-97, PServer.java:102-117) and PSClient.updateList / PServer.upsertList
+ * (PSClient.java:128-151, PServer.java:144-162) by reference key strings.  Embedding keys ("emF<j>.<id>") — the bulk of any
+ * list — go through ONE batched lookup / insert kernel; any other key (dense parameters, wide weights) is served one by one. */
+int ps_model_get_list(ps_model* m, const char* const* keys, int n, float* out, int stride, int32_t* found) {
+  PS_TRY
+  PS_REQUIRE(m && keys && out && found && n >= 0 && stride > 0, PS_ERR_ARG, "ps_model_get_list: bad argument");
+  Model& M = m->m;
+  std::vector<int32_t> fields, idx, fnd;
+  std::vector<int64_t> ids;
+  for (int i = 0; i < n; ++i) {
+    int f = 0; int64_t id = 0;
+    found[i] = 0;
+    if (parse_key(keys[i], &f, &id) == 0 && M.has_emb && f >= 0 && f < M.F && id >= 0) {
+      PS_REQUIRE(stride >= M.D, PS_ERR_ARG, "ps_model_get_list: stride smaller than the embedding dimension");
+      fields.push_back(f); ids.push_back(id); idx.push_back(i);
+    } else {
+      std::vector<float> v;
+      if (M.get(keys[i], v) == PS_OK) {
+        PS_REQUIRE((int)v.size() <= stride, PS_ERR_ARG, "ps_model_get_list: stride smaller than a listed parameter");
+        std::memcpy(out + (size_t)i * stride, v.data(), sizeof(float) * v.size());
+        found[i] = (int32_t)v.size();
+      }
+    }
+  }
+  if (!idx.empty()) {
+    const int k = (int)idx.size();
+    std::vector<float> w((size_t)k * M.D);
+    fnd.assign(k, 0);
+    M.emb.get_rows(fields.data(), ids.data(), k, w.data(), nullptr, nullptr, fnd.data());
+    for (int q = 0; q < k; ++q)
+      if (fnd[q]) { std::memcpy(out + (size_t)idx[q] * stride, w.data() + (size_t)q * M.D, sizeof(float) * M.D); found[idx[q]] = M.D; }
+  }
+  PS_CATCH
+}
+int ps_model_update_list(ps_model* m, const char* const* keys, int n, float* io, int stride, const int32_t* lens, int replace) {
+  PS_TRY
+  PS_REQUIRE(m && keys && io && lens && n >= 0 && stride > 0, PS_ERR_ARG, "ps_model_update_list: bad argument");
+  Model& M = m->m;
+  std::vector<int32_t> fields, idx;
+  std::vector<int64_t> ids;
+  for (int i = 0; i < n; ++i) {
+    int f = 0; int64_t id = 0;
+    if (parse_key(keys[i], &f, &id) == 0 && M.has_emb) {
+      PS_REQUIRE(lens[i] == M.D && stride >= M.D, PS_ERR_ARG, "ps_model_update_list: embedding row length mismatch");
+      fields.push_back(f); ids.push_back(id); idx.push_back(i);
+    } else {
+      std::vector<float> cur;
+      if (!replace && M.get(keys[i], cur) == PS_OK) {          /* insert-if-absent: the caller receives the winner (PServer.java:150-158) */
+        PS_REQUIRE((int)cur.size() <= stride, PS_ERR_ARG, "ps_model_update_list: stride smaller than a listed parameter");
+        std::memcpy(io + (size_t)i * stride, cur.data(), sizeof(float) * cur.size());
+      } else {
+        M.put(keys[i], io + (size_t)i * stride, lens[i]);
+      }
+    }
+  }
+  if (!idx.empty()) {
+    const int k = (int)idx.size();
+    std::vector<float> w((size_t)k * M.D);
+    for (int q = 0; q < k; ++q) std::memcpy(w.data() + (size_t)q * M.D, io + (size_t)idx[q] * stride, sizeof(float) * M.D);
+    M.emb.put_rows(fields.data(), ids.data(), k, w.data(), replace);
+    for (int q = 0; q < k; ++q) std::memcpy(io + (size_t)idx[q] * stride, w.data() + (size_t)q * M.D, sizeof(float) * M.D);
+  }
   PS_CATCH
 }
 int ps_model_get_state(ps_model* m, const char* key, int which, float* out, int cap, int* n) {
@@ -722,6 +794,14 @@ int ps_reader_next(ps_reader* r, int64_t* E, float* X, int64_t* W, float* Y, int
   PS_TRY
   PS_REQUIRE(r != nullptr && rows != nullptr, PS_ERR_ARG, "ps_reader_next: null argument");
   *rows = r->r->next(E, X, W, Y);
+  PS_CATCH
+}
+int ps_reader_shape(ps_reader* r, int* batch, int* F, int* Xn) {
+  PS_TRY
+  PS_REQUIRE(r != nullptr, PS_ERR_ARG, "ps_reader_shape: null reader");
+  if (batch) *batch = r->r->batch;
+  if (F) *F = r->r->F;
+  if (Xn) *Xn = r->r->Xn;
   PS_CATCH
 }
 int ps_reader_reset(ps_reader* r) {

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) emb_import_kernel(EmbSlot* __restrict__ s
     }
     slot = slot + 1 == C ? 0 : slot + 1;
   }
-  if (found < 0) { counters[1] = 1u; return; }
+  if (found < 0) { atomicOr(&counters[1], 1u); return; }
   for (int d = 0; d < D; ++d) {
     w[(size_t)found * Dp + d] = rows[((size_t)0 * cap + i) * D + d];
     a[(size_t)found * Dp + d] = rows[((size_t)1 * cap + i) * D + d];

@@ -276,7 +276,8 @@ __device__ __forceinline__ void tail_finish(float loss_part, float d_part, int N
      * step is applied (backward, dense / wide / embedding updates all honour this flag); collect() reports PS_ERR_CAPACITY */
     const bool table_full = emb_counters != nullptr && emb_counters[1] != 0u;
     const bool bad_input = st->pad != 0u;        /* submit_text: a line of the batch could not be parsed — the batch is dropped (DataSet.java:96-98) */
-    st->skip = (loss <= 0.01f || isnan(loss) || table_full || bad_input) ? 1 : 0;
+    const bool slim = !ext_loss && (loss <= 0.01f || isnan(loss));   /* with the loss in the caller, the early exit of DNN.java:58-63 is the caller's too */
+    st->skip = (slim || table_full || bad_input) ? 1 : 0;
     st->n_unique = emb_counters != nullptr ? emb_counters[4] : 0u;           /* EmbTable CNT_CURSOR: unique keys of this batch */
     st->seq += 1u;
     *ticket = 0u;

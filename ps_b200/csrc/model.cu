@@ -604,6 +604,7 @@ float Model::collect() {
   S.busy = false;
   oldest_stage ^= 1; in_flight--;
   if (profile && in_flight == 0) finish_profile();
+  PS_REQUIRE((last_status.emb_err & 2u) == 0, PS_ERR_ARG, "embedding id outside [0, 2^44): the batch was refused, nothing was applied");
   PS_REQUIRE(last_status.emb_err == 0, PS_ERR_CAPACITY, "embedding table is full: raise emb_capacity");
   PS_REQUIRE(last_status.wide_err == 0, PS_ERR_CAPACITY, "wide table is full");
   return last_status.loss;
@@ -615,6 +616,7 @@ float Model::read_loss() {
   PS_CUDA(cudaStreamSynchronize(ctx->stream));
   last_status = *stage[0].st_host;
   if (profile) finish_profile();
+  PS_REQUIRE((last_status.emb_err & 2u) == 0, PS_ERR_ARG, "embedding id outside [0, 2^44): the batch was refused, nothing was applied");
   PS_REQUIRE(last_status.emb_err == 0, PS_ERR_CAPACITY, "embedding table is full: raise emb_capacity");
   PS_REQUIRE(last_status.wide_err == 0, PS_ERR_CAPACITY, "wide table is full");
   return last_status.loss;
@@ -674,6 +676,7 @@ void Model::backward_update_host(const float* delta_top, int N, float loss) {
   pending_forward_N = 0;
   last_status = *S.st_host;
   last_N = N; last_train = true;
+  PS_REQUIRE((last_status.emb_err & 2u) == 0, PS_ERR_ARG, "embedding id outside [0, 2^44): the batch was refused, nothing was applied");
   PS_REQUIRE(last_status.emb_err == 0, PS_ERR_CAPACITY, "embedding table is full: raise emb_capacity");
   PS_REQUIRE(last_status.wide_err == 0, PS_ERR_CAPACITY, "wide table is full");
 }

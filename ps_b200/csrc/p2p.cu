@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256) p2p_grad_send_kernel(P2PState* st, float*
   if (g < total) {
     const int q = (int)(g / tpl), part = (int)(g - (long)q * tpl);
     const int owner = q / cap, pos = q - owner * cap;
-    if (pos < min(*reinterpret_cast<volatile int32_t*>(&st->cursor[owner]), cap)) {
+    if (pos < min(st->cursor[owner], cap)) {       /* final since route_send ended: an ordinary cached load (a volatile one per thread serialised 6 M requests on one L2 line) */
       float* a = gacc + (size_t)q * Dp + part * 4;
       const float4 v = __ldcg(reinterpret_cast<const float4*>(a));
       st_f4(reinterpret_cast<float*>(p2p_region(st, owner, st->off_grads)) + ((size_t)me * cap + pos) * Dp + part * 4, v);

@@ -91,14 +91,15 @@ __device__ __forceinline__ uint32_t p2p_ld_acquire_sys(const uint32_t* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-/* Producer side, called by EVERY thread of the grid once its stores into peer memory are issued: fence them at system
- * scope; the block that arrives last flags every peer with the step's sequence number (CH_KEYS: after the key counts).
- * Returns true in that last block.                                                                                  */
+/* Producer side, called by EVERY thread of the grid once its stores into peer memory are issued.  The block barrier orders
+ * the block's stores before thread 0, whose ONE system-scope fence (cumulative) orders them before its ticket — a fence per
+ * thread made these small kernels 2-3x longer; the block that arrives last flags every peer with the step's sequence number
+ * (CH_KEYS: after the key counts).  Returns true in that last block.                                                    */
 __device__ __forceinline__ bool p2p_publish_last(P2PState* st, int channel, uint32_t nblocks) {
   __shared__ bool s_last;
-  __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();
     const uint32_t t = atomicAdd(&st->ticket[channel], 1u);
     s_last = t == nblocks - 1u;
     if (s_last) st->ticket[channel] = 0u;

@@ -108,9 +108,9 @@ __device__ __forceinline__ void tb_bulk_g2s(uint32_t dst, const void* src, uint3
  * system: the grid stored into peer memory — fence those stores for the other GPUs, not just for this one. */
 __device__ __forceinline__ bool last_block_done(uint32_t* ticket, uint32_t nblocks, bool system = false) {
   __shared__ bool s_last;
-  if (system) __threadfence_system(); else __threadfence();
-  __syncthreads();
+  __syncthreads();                               /* the block's writes happen-before thread 0's (cumulative) fence */
   if (threadIdx.x == 0) {
+    if (system) __threadfence_system(); else __threadfence();
     const uint32_t t = atomicAdd(ticket, 1u);
     s_last = t == nblocks - 1u;
     if (s_last) *ticket = 0u;
@@ -216,6 +216,8 @@ __global__ void __launch_bounds__(256) emb_lookup_kernel(const __grid_constant__
     if (it >= -1 && tB < ntasks && rv_n) {
       const int j = (int)(tB % Fe);
       key_b = a.F > 0 ? ps_pack_key((uint32_t)j, (uint64_t)(int64_t)raw_n) : (unsigned long long)raw_n;   /* EMPTY marks padding in the fixed-capacity exchange */
+      /* ids outside [0, 2^44) would silently alias another key's row (ps_pack_key masks): refuse the batch instead */
+      if (a.F > 0 && (uint64_t)(int64_t)raw_n > PS_KEY_ID_MASK) { atomicOr(&a.counters[CNT_ERR], 2u); key_b = PS_KEY_EMPTY; }
       if (key_b != PS_KEY_EMPTY) { bucket_b = ps_bucket_of(key_b, a.C); rec_b = ld_slot(&a.slots[bucket_b]); }
     }
     /* ---- stage C: task tC ---- */
@@ -231,7 +233,7 @@ __global__ void __launch_bounds__(256) emb_lookup_kernel(const __grid_constant__
       if (key != PS_KEY_EMPTY) {
         bool inserted;
         slot = emb_resolve(a.slots, a.C, key, bucket_c, rec_c, &inserted, &ready);
-        if (slot < 0) a.counters[CNT_ERR] = 1u;       /* table full: the tail turns this into the step's skip flag — nothing is updated */
+        if (slot < 0) atomicOr(&a.counters[CNT_ERR], 1u);   /* table full: the tail turns this into the step's skip flag — nothing is updated */
         else if (inserted) {
           float* row = a.rows + (size_t)slot * a.rs;
           for (int d = 0; d < a.D; ++d) row[d] = ps_init_value(a.seed, key, (uint32_t)d, a.maxv);
@@ -697,7 +699,7 @@ __global__ void emb_put_rows_kernel(EmbSlot* __restrict__ slots, uint32_t C, flo
   if (i >= n) return;
   bool inserted;
   const int slot = emb_find_or_insert(slots, C, ps_pack_key((uint32_t)fields[i], (uint64_t)ids[i]), &inserted);
-  if (slot < 0) { counters[CNT_ERR] = 1u; return; }
+  if (slot < 0) { atomicOr(&counters[CNT_ERR], 1u); return; }
   if (inserted) atomicAdd(reinterpret_cast<unsigned long long*>(counters + CNT_ROWS), 1ull);
   float* row = rows + (size_t)slot * rs;
   if (inserted || replace) { for (int d = 0; d < D; ++d) row[d] = wio[(size_t)i * D + d]; }
@@ -933,6 +935,7 @@ void EmbTable::check_errors() {
   uint32_t h[4];
   PS_CUDA(cudaMemcpyAsync(h, counters, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
   PS_CUDA(cudaStreamSynchronize(ctx->stream));
+  PS_REQUIRE((h[CNT_ERR] & 2u) == 0, PS_ERR_ARG, "embedding id outside [0, 2^44): the batch was refused");
   PS_REQUIRE(h[CNT_ERR] == 0, PS_ERR_CAPACITY, "embedding table is full: raise capacity");
 }
 

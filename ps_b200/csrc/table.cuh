@@ -42,7 +42,7 @@ struct __align__(16) EmbSlot {
 
 /* EmbTable::counters */
 enum { CNT_UNIQUE = 0,      /* (unused) */
-       CNT_ERR = 1,         /* an insert found the table full */
+       CNT_ERR = 1,         /* sticky error bits: 1 = an insert found the table full, 2 = a key id outside [0, 2^44) */
        CNT_ROWS = 2,        /* [2..3] u64 number of keys in the table */
        CNT_CURSOR = 4,      /* unique keys of the batch being processed: grows during the lookup kernel, final when it ends, read by the
                                tail (StepStatus.n_unique) and the update kernel, whose last block resets it */

@@ -20,6 +20,7 @@ from ps_b200 import binding as ps  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg4"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+sharded = len(sys.argv) > 3 and sys.argv[3] == "sharded"      # the peer-memory sharded step on ONE rank (every exchange kernel runs, no link)
 cfg = dict(CONFIGS[name])
 B, F, D, Xn, V = cfg["B"], cfg["F"], cfg["D"], cfg["Xn"], cfg["V"]
 ctx = ps.Context(0, seed=20261017)
@@ -34,9 +35,22 @@ def p(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
+trainer = None
+if sharded:
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29544")
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    from ps_b200.sharded import P2PShardedTrainer
+    trainer = P2PShardedTrainer(ps, ctx, model, 0, 1, B, F, slack=2.0, device=0)
 for i in range(16 + steps):
     d = ring[i % 8]
-    model.train_step_dev(p(d.get("E")), p(d["X"]), p(d.get("W")), p(d["Y"]), B)
+    if trainer is not None:
+        trainer.step(d.get("E"), d["X"], d.get("W"), d["Y"])
+    else:
+        model.train_step_dev(p(d.get("E")), p(d["X"]), p(d.get("W")), p(d["Y"]), B)
 print("loss", model.read_loss())
+if trainer is not None:
+    os._exit(0)
 model.close()
 ctx.close()

@@ -216,3 +216,50 @@ def test_tma_staged_rows_are_the_same_bits(ps, D):
     ref = np.zeros((N, F * D), np.float32)
     ol.lib().pso_emb_forward(o, E, N, ref)
     assert np.array_equal(outs[0][0], ref)
+
+
+def test_get_list_and_update_list(ps, ctx):
+    """PSClient.getList / updateList by reference key strings (PSClient.java:72-97,128-151; PServer.java:102-117,144-162)."""
+    F, D, Xn, fc, N = 23, 16, 45, [32, 1], 128
+    m = ps.Model(ctx, "widedeep", F, D, Xn, fc, emb_capacity=1 << 14, max_batch=N)
+    o = ol.OracleModel(ol.KIND_WIDEDEEP, F, D, Xn, fc, SEED)
+    b = Synth(F=F, Xn=Xn, V=5000, seed=8).batch(N)
+    m.train_step(b["E"], b["X"], b["W"], b["Y"])
+    o.train_step(b["E"], b["X"], b["W"], b["Y"])
+    keys = [ol.key_string(0, j, int(b["E"][n, j])) for n in range(0, N, 9) for j in range(F)]
+    keys += ["fc0.bias", "wide.bias", ol.key_string(1, 0, int(b["W"][3, 2])), "emF3.999999.0", "no.such.key"]
+    got = m.get_list(keys, stride=64)
+    for k in keys:
+        ref = o.get(k)
+        if ref is None:
+            assert got[k] is None, k
+        else:
+            assert got[k] is not None and np.allclose(got[k], ref, rtol=5e-4, atol=2e-6), k
+    # updateList with replace = false: existing keys keep their value and the caller receives it; absent keys are created
+    known = ol.key_string(0, 0, int(b["E"][0, 0]))
+    fresh = "emF5.424242.0"
+    offered = {known: np.full(D, 7.0, np.float32), fresh: np.arange(D, dtype=np.float32)}
+    back = m.update_list(offered, replace=False)
+    assert np.array_equal(back[known], got[known]) and np.array_equal(m.get(known), got[known])
+    assert np.array_equal(back[fresh], offered[fresh]) and np.array_equal(m.get(fresh), offered[fresh])
+    back = m.update_list({known: np.full(D, 7.0, np.float32)}, replace=True)
+    assert np.array_equal(m.get(known), np.full(D, 7.0, np.float32))
+    # a row installed through updateList trains like any other (its ready flag is set)
+    l1 = m.train_step(b["E"], b["X"], b["W"], b["Y"])
+    assert np.isfinite(l1) and not np.array_equal(m.get(known), np.full(D, 7.0, np.float32))
+    m.close()
+
+
+def test_out_of_domain_id_refuses_the_batch(ps, ctx):
+    F, D, Xn, fc, N = 3, 8, 2, [4, 1], 32
+    m = ps.Model(ctx, "dnn", F, D, Xn, fc, emb_capacity=1 << 10, max_batch=N)
+    b = Synth(F=F, Xn=Xn, V=100, seed=2).batch(N)
+    m.train_step(b["E"], b["X"], None, b["Y"])
+    w0 = m.get("fc0.weights").copy()
+    bad = {k: v.copy() for k, v in b.items()}
+    bad["E"][5, 1] = -3                                         # the reference would keep "emF1.-3.0" apart; the packed key cannot
+    with pytest.raises(ps.PsError) as e:
+        m.train_step(bad["E"], bad["X"], None, bad["Y"])
+    assert e.value.code == 400
+    assert np.array_equal(m.get("fc0.weights"), w0)
+    m.close()
