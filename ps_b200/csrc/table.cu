@@ -14,6 +14,7 @@
  */
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "p2p.cuh"
@@ -104,6 +105,11 @@ __device__ __forceinline__ void tb_bulk_g2s(uint32_t dst, const void* src, uint3
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+/* 16 B asynchronous global -> shared copy (LDGSTS, L2 only): no register is held while it is in flight */
+__device__ __forceinline__ void tb_cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
 /* true in exactly one block of the grid: the one whose threads arrive last.  Call from all threads.
  * system: the grid stored into peer memory — fence those stores for the other GPUs, not just for this one. */
 __device__ __forceinline__ bool last_block_done(uint32_t* ticket, uint32_t nblocks, bool system = false) {
@@ -133,6 +139,7 @@ struct LookupArgs {
   int task_blocks, hot_tma;
 };
 
+static size_t lookup_smem_bytes(int Dp) { return 128 + (size_t)8 * 32 * Dp * sizeof(float); }
 static constexpr int kHotShare = 4;                 /* lookups of one warp task that must share a row before it is staged by TMA */
 static constexpr int kHotRows = 32 / kHotShare;     /* so at most this many staged rows per warp */
 
@@ -183,9 +190,9 @@ __global__ void __launch_bounds__(256) emb_lookup_kernel(const __grid_constant__
   const long W = (long)a.task_blocks * 8;          /* warps striding over the tasks */
   const long w0 = (long)blockIdx.x * 8 + warp;
   uint64_t* mbar = reinterpret_cast<uint64_t*>(lookup_smem);
-  float* stage = reinterpret_cast<float*>(lookup_smem + 128) + (size_t)warp * kHotRows * a.Dp;
+  float* stage = reinterpret_cast<float*>(lookup_smem + 128) + (size_t)warp * 32 * a.Dp;   /* the warp's slab: one row per lookup of a task */
   uint32_t hot_parity = 0u;
-  if (GATHER && a.hot_tma) {
+  if (GATHER) {
     if (lane == 0) tb_mbar_init(tb_smem_u32(&mbar[warp]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
@@ -256,91 +263,76 @@ __global__ void __launch_bounds__(256) emb_lookup_kernel(const __grid_constant__
         omask = __ballot_sync(0xffffffffu, is_owner);
         if (omask != 0u && lane == __ffs(omask) - 1) ubase = atomicAdd(&a.counters[CNT_CURSOR], (uint32_t)__popc(omask));
       };
-      /* 3. gather */
+      /* 3. gather: every DISTINCT row of the task is staged once in the warp's shared-memory slab — rows several lookups of the
+       * task share (a low-cardinality field) by the TMA unit (cp.async.bulk, mbarrier completion), the others by 16 B
+       * asynchronous copies (LDGSTS) — so a whole task's rows are in flight at once without holding a register; the slab is
+       * then written out with ReLU and the mask bits.  Rows created by this very kernel come from the initialiser's bits. */
       if (GATHER) {
         constexpr int GPW = 32 / TPL;                 /* rows per pass */
         constexpr int NP = TPL;                       /* passes over the task's 32 rows */
-        constexpr int UNR = NP < 8 ? NP : 8;          /* passes whose loads are in flight together */
         constexpr int MSH = TPL < 8 ? TPL : 8;        /* lanes whose mask nibbles share one 32-bit word */
         const int part = lane % TPL, grp = lane / TPL;
         const bool lane_on = part * 4 < a.Dp;
-        const bool any_nr = __any_sync(0xffffffffu, slot >= 0 && !ready);
-        int hidx = -1;
-        unsigned hmask = 0u;
-        if (a.hot_tma) {
-          const bool hot = slot >= 0 && ready && __popc(peers) >= kHotShare;
-          hmask = __ballot_sync(0xffffffffu, hot && leader == lane);
-          if (hmask != 0u) {                          /* warp-uniform */
-            const uint32_t bar = tb_smem_u32(&mbar[warp]);
-            if (lane == 0) tb_mbar_expect_tx(bar, (uint32_t)__popc(hmask) * (uint32_t)a.Dp * 4u);
-            __syncwarp();
-            if (hot) hidx = __popc(hmask & ((1u << leader) - 1u));
-            if (hot && leader == lane) tb_bulk_g2s(tb_smem_u32(stage + (size_t)hidx * a.Dp), a.rows + (size_t)slot * a.rs, (uint32_t)a.Dp * 4u, bar);
-          }
+        const bool fetch = slot >= 0 && leader == lane;               /* one lane per distinct row */
+        const bool hot = fetch && ready && a.hot_tma && __popc(peers) >= kHotShare;
+        const unsigned hmask = __ballot_sync(0xffffffffu, hot);
+        /* the slab was read with ordinary loads by the previous task: order those before the async-proxy writes below */
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (hmask != 0u) {                            /* warp-uniform */
+          const uint32_t bar = tb_smem_u32(&mbar[warp]);
+          if (lane == 0) tb_mbar_expect_tx(bar, (uint32_t)__popc(hmask) * (uint32_t)a.Dp * 4u);
+          __syncwarp();
+          if (hot) tb_bulk_g2s(tb_smem_u32(stage + (size_t)lane * a.Dp), a.rows + (size_t)slot * a.rs, (uint32_t)a.Dp * 4u, bar);
         }
-        const int flags = (ready ? 1 : 0) | ((hidx + 1) << 1);
-        bool waited = false;
-#pragma unroll 1
-        for (int p0 = 0; p0 < NP; p0 += UNR) {
-          float4 v[UNR];
-          int rs_[UNR], rf_[UNR];
+        const int code = !fetch ? 0 : hot ? 1 : ready ? 2 : 3;       /* how row `lane` reaches the slab: - | TMA | LDGSTS | initialiser */
 #pragma unroll
-          for (int q = 0; q < UNR; ++q) {
-            const int r = (p0 + q) * GPW + grp;
-            rs_[q] = __shfl_sync(0xffffffffu, slot, r);
-            rf_[q] = __shfl_sync(0xffffffffu, flags, r);
-            v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rs_[q] >= 0 && lane_on && (rf_[q] & 1) && (rf_[q] >> 1) == 0) v[q] = ld_f4(a.rows + (size_t)rs_[q] * a.rs + part * 4);
+        for (int p = 0; p < NP; ++p) {
+          const int r = p * GPW + grp;
+          const int rs_ = __shfl_sync(0xffffffffu, slot, r);
+          const int rc_ = __shfl_sync(0xffffffffu, code, r);
+          if (rc_ == 2 && lane_on) tb_cp_async16(tb_smem_u32(stage + (size_t)r * a.Dp + part * 4), a.rows + (size_t)rs_ * a.rs + part * 4);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (code == 3) {                              /* created by this kernel (here or elsewhere): the initialiser's bits, not memory */
+          float* srow = stage + (size_t)lane * a.Dp;
+          for (int d = 0; d < a.Dp; ++d) srow[d] = d < a.D ? ps_init_value(a.seed, key, (uint32_t)d, a.maxv) : 0.f;
+        }
+        claim();                                      /* the count atomic has returned by now; the cursor atomic flies with the copies */
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (hmask != 0u) { tb_mbar_wait(tb_smem_u32(&mbar[warp]), hot_parity); hot_parity ^= 1u; }
+        __syncwarp();
+#pragma unroll 4
+        for (int p = 0; p < NP; ++p) {
+          const int r = p * GPW + grp;
+          const long nr = nbase + r;
+          const int rs_ = __shfl_sync(0xffffffffu, slot, r);
+          const int rl_ = __shfl_sync(0xffffffffu, leader, r);      /* the lane whose slab row holds row r's key */
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rs_ >= 0 && lane_on) v = *reinterpret_cast<const float4*>(stage + (size_t)rl_ * a.Dp + part * 4);
+          /* EmbeddingField.java:75: relu in place; the mask bit is what Relu.backward will ask for (Relu.java:14-19) */
+          uint32_t m = (v.x > 0.f ? 1u : 0u) | (v.y > 0.f ? 2u : 0u) | (v.z > 0.f ? 4u : 0u) | (v.w > 0.f ? 8u : 0u);
+          v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+          if (a.lk_mask != nullptr) {
+            m <<= (part & 7) * 4;
+#pragma unroll
+            for (int o = 1; o < MSH; o <<= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
+            if (nr < a.N && (part & 7) == 0 && lane_on) a.lk_mask[((size_t)j * a.N + nr) * a.MW + (part >> 3)] = m;
           }
-          if (p0 == 0) claim();                       /* the count atomic has returned by now; the cursor atomic flies with the row loads */
-          if (hmask != 0u) {                          /* rows several lookups share: from the TMA-staged copy */
-            if (!waited) { tb_mbar_wait(tb_smem_u32(&mbar[warp]), hot_parity); hot_parity ^= 1u; waited = true; }
+          if (nr >= a.N || !lane_on) continue;
+          float* o;
+          if (a.F > 0) o = a.out + (size_t)nr * a.ldo + j * a.D + part * 4;
+          else if (a.send_rows) {                     /* PServer.getList response: straight into the requester's rows_in[me][idx] */
+            if (rs_ < 0) continue;
+            const int src = (int)(nr / a.p2p->cap), idx = (int)(nr - (long)src * a.p2p->cap);
+            o = reinterpret_cast<float*>(p2p_region(a.p2p, src, a.p2p->off_rows)) + ((size_t)a.p2p->me * a.p2p->cap + idx) * a.Dp + part * 4;
+          } else o = a.out + (size_t)nr * a.ldo + part * 4;
+          if (ALIGNED || a.F == 0) {
+            st_f4(o, v);
+          } else {
+            const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int q = 0; q < UNR; ++q)
-              if (rs_[q] >= 0 && lane_on && (rf_[q] >> 1) != 0) v[q] = *reinterpret_cast<const float4*>(stage + (size_t)((rf_[q] >> 1) - 1) * a.Dp + part * 4);
-          }
-          if (any_nr) {                               /* rows created by this very kernel: the initialiser's bits, not memory */
-#pragma unroll
-            for (int q = 0; q < UNR; ++q) {
-              const int r = (p0 + q) * GPW + grp;
-              const unsigned long long kr = shfl_u64(key, r);
-              if (rs_[q] >= 0 && lane_on && !(rf_[q] & 1)) {
-                const int d0 = part * 4;
-                v[q].x = d0 + 0 < a.D ? ps_init_value(a.seed, kr, (uint32_t)(d0 + 0), a.maxv) : 0.f;
-                v[q].y = d0 + 1 < a.D ? ps_init_value(a.seed, kr, (uint32_t)(d0 + 1), a.maxv) : 0.f;
-                v[q].z = d0 + 2 < a.D ? ps_init_value(a.seed, kr, (uint32_t)(d0 + 2), a.maxv) : 0.f;
-                v[q].w = d0 + 3 < a.D ? ps_init_value(a.seed, kr, (uint32_t)(d0 + 3), a.maxv) : 0.f;
-              }
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < UNR; ++q) {
-            const int r = (p0 + q) * GPW + grp;
-            const long nr = nbase + r;
-            /* EmbeddingField.java:75: relu in place; the mask bit is what Relu.backward will ask for (Relu.java:14-19) */
-            uint32_t m = (v[q].x > 0.f ? 1u : 0u) | (v[q].y > 0.f ? 2u : 0u) | (v[q].z > 0.f ? 4u : 0u) | (v[q].w > 0.f ? 8u : 0u);
-            v[q].x = fmaxf(v[q].x, 0.f); v[q].y = fmaxf(v[q].y, 0.f); v[q].z = fmaxf(v[q].z, 0.f); v[q].w = fmaxf(v[q].w, 0.f);
-            if (a.lk_mask != nullptr) {
-              m <<= (part & 7) * 4;
-#pragma unroll
-              for (int o = 1; o < MSH; o <<= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
-              if (nr < a.N && (part & 7) == 0 && lane_on) a.lk_mask[((size_t)j * a.N + nr) * a.MW + (part >> 3)] = m;
-            }
-            if (nr >= a.N || !lane_on) continue;
-            float* o;
-            if (a.F > 0) o = a.out + (size_t)nr * a.ldo + j * a.D + part * 4;
-            else if (a.send_rows) {                   /* PServer.getList response: straight into the requester's rows_in[me][idx] */
-              if (rs_[q] < 0) continue;
-              const int src = (int)(nr / a.p2p->cap), idx = (int)(nr - (long)src * a.p2p->cap);
-              o = reinterpret_cast<float*>(p2p_region(a.p2p, src, a.p2p->off_rows)) + ((size_t)a.p2p->me * a.p2p->cap + idx) * a.Dp + part * 4;
-            } else o = a.out + (size_t)nr * a.ldo + part * 4;
-            if (ALIGNED || a.F == 0) {
-              st_f4(o, v[q]);
-            } else {
-              const float e[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) if (part * 4 + i < a.D) o[i] = e[i];
-            }
+            for (int i = 0; i < 4; ++i) if (part * 4 + i < a.D) o[i] = e[i];
           }
         }
       } else {
@@ -710,14 +702,22 @@ __global__ void emb_put_rows_kernel(EmbSlot* __restrict__ slots, uint32_t C, flo
 /* ------------------------------------------------------------------ EmbTable host side */
 static int pow2_ge(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
+/* the slab of every warp (32 rows) + the mbarriers: 64 KB at D = 64 — more than the default 48 KB, so every gathering
+ * instantiation opts in (once per table, outside any stream capture) */
+template <class IdT, int TPL>
+static void lookup_allow_smem(size_t smem) {
+  PS_CUDA(cudaFuncSetAttribute(emb_lookup_kernel<IdT, true, TPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PS_CUDA(cudaFuncSetAttribute(emb_lookup_kernel<IdT, true, TPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+}
 template <int TPL>
 static int lookup_occupancy(size_t smem) {
+  lookup_allow_smem<int64_t, TPL>(smem); lookup_allow_smem<float, TPL>(smem); lookup_allow_smem<unsigned long long, TPL>(smem);
   int occ = 1;
   PS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, emb_lookup_kernel<int64_t, true, TPL, true>, 256, smem));
   return occ;
 }
 static void query_lookup_occupancy(EmbTable& t) {      /* not inside a capture: called from create() */
-  const size_t smem = t.ctx->hot_tma ? 128 + (size_t)8 * kHotRows * t.Dp * sizeof(float) : 0;
+  const size_t smem = lookup_smem_bytes(t.Dp);
   switch (t.tpl) {
     case 1: t.lookup_occ = lookup_occupancy<1>(smem); break;
     case 2: t.lookup_occ = lookup_occupancy<2>(smem); break;
@@ -780,7 +780,7 @@ static void launch_lookup(EmbTable& t, LookupArgs& a, bool gather) {
   const int xblocks = (gather && a.X != nullptr) ? ceil_div((long)a.N * a.Xn, 1024) : 0;
   a.hot_tma = (gather && t.ctx->hot_tma) ? 1 : 0;
   const bool aligned = a.F == 0 || ((t.D % 4 == 0) && (a.ldo % 4 == 0) && ((uintptr_t)a.out % 16 == 0));
-  const size_t smem = a.hot_tma ? 128 + (size_t)8 * kHotRows * t.Dp * sizeof(float) : 0;
+  const size_t smem = gather ? lookup_smem_bytes(t.Dp) : 0;
   const int grid = a.task_blocks + xblocks;
   switch (t.tpl) {
     case 1: launch_lookup_t<IdT, 1>(t, a, gather, aligned, grid, smem); break;
@@ -906,7 +906,8 @@ void EmbTable::scatter_update_entries(const P2PState* p2p, int n, int calls, con
   emb_scatter_entries_kernel<<<grid, 256, 0, ctx->stream>>>(slots, Dp, lk_slot, acc, ucnt, skip_flag, p2p);
   PS_LAUNCH_CHECK();
   ctx->launches++;
-  launch_update(*this, n, calls, skip_flag, ucnt);
+  static const bool no_ucnt = std::getenv("PS_DEBUG_NO_UCNT") != nullptr;   /* timing experiment only: the update then normalises by the entry count */
+  launch_update(*this, n, calls, skip_flag, no_ucnt ? nullptr : ucnt);
   last_L = 0;
 }
 
