@@ -180,6 +180,7 @@ void Model::load(const std::string& path) {
     rd_dev(ctx, f.get(), q.W, wb, tmp); rd_dev(ctx, f.get(), q.sW1, wb, tmp); rd_dev(ctx, f.get(), q.sW2, wb, tmp);
     rd_dev(ctx, f.get(), q.bias, sizeof(float) * q.out, tmp); rd_dev(ctx, f.get(), q.sb1, sizeof(float) * q.out, tmp); rd_dev(ctx, f.get(), q.sb2, sizeof(float) * q.out, tmp);
     transpose_copy(ctx, q.W, q.ldw, q.Wt, q.ldwt, q.out, q.in);       /* the K-major copy the dgrad GEMM reads */
+    q.refresh_lo(ctx);
   }
   if (has_wide) {
     PS_REQUIRE(h.wide_capacity == wide.C, PS_ERR_ARG, "load: wide table capacity mismatch");

@@ -32,6 +32,17 @@ void dense_init(Ctx* ctx, float* W, int out, int in, int ldw, float* Wt, int ldw
   ctx->launches++;
 }
 
+__device__ __forceinline__ float tf32_residual(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__global__ void split_lo_kernel(const float* __restrict__ x, float* __restrict__ lo, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) lo[i] = tf32_residual(x[i]);
+}
+void split_lo(Ctx* ctx, const float* x, float* lo, size_t n) {
+  if (!x || !lo || n == 0) return;
+  split_lo_kernel<<<(int)std::min<size_t>((n + 255) / 256, 1184), 256, 0, ctx->stream>>>(x, lo, n);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+}
+
 __global__ void fill_column_kernel(float* buf, int ld, int col, int rows, float value) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < rows) buf[(size_t)r * ld + col] = value;
@@ -124,6 +135,7 @@ __global__ void __launch_bounds__(256) dense_update_kernel(const __grid_constant
     apply_elem(u, w, m1, m2, g);
     L.W[off] = w; L.sW1[off] = m1; L.sW2[off] = m2;
     if (L.Wt) L.Wt[(size_t)c * L.ldwt + o] = w;
+    if (L.Wlo) { const float lo = tf32_residual(w); L.Wlo[off] = lo; if (L.Wtlo) L.Wtlo[(size_t)c * L.ldwt + o] = lo; }
   }
 }
 void dense_update(Ctx* ctx, const DenseUpdateArgs& a, StepStatus* st, const uint32_t* emb_counters, const uint32_t* wide_counters,
@@ -158,16 +170,16 @@ void dense_reduce(Ctx* ctx, const DenseUpdateArgs& a, const StepStatus* st, floa
 /* dense_reduce + all-gather by stores: every rank's slot `me` of gsum_in receives this rank's sums */
 __global__ void __launch_bounds__(256) dense_reduce_send_kernel(const __grid_constant__ DenseUpdateArgs a, const StepStatus* __restrict__ st,
                                                                 P2PState* __restrict__ p2p, const uint32_t* __restrict__ emb_counters) {
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int R = p2p->R, me = p2p->me, glen = p2p->glen;
-  if (idx == 0) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
     for (int r = 0; r < R; ++r) {
       float* dst = reinterpret_cast<float*>(p2p_region(p2p, r, p2p->off_gsum)) + (size_t)me * glen;
       dst[a.total] = st->loss; dst[a.total + 1] = st->gbar;
       dst[a.total + 2] = (emb_counters != nullptr && emb_counters[1] != 0u) ? 1.0f : 0.0f;
     }
   }
-  if (idx < a.total) {
+  /* a capped grid striding over the parameters: the publish below costs one system fence + one ticket per block */
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < a.total; idx += (long)gridDim.x * blockDim.x) {
     int li = 0;
     while (li + 1 < a.n_layers && idx >= a.l[li + 1].first) ++li;
     const DenseLayerDesc& L = a.l[li];
@@ -181,7 +193,7 @@ __global__ void __launch_bounds__(256) dense_reduce_send_kernel(const __grid_con
   p2p_publish_last(p2p, CH_GSUM, gridDim.x);     /* the last block flags every replica: this rank's sums are in its gsum_in */
 }
 void dense_reduce_send(Ctx* ctx, const DenseUpdateArgs& a, const StepStatus* st, P2PState* p2p, const uint32_t* emb_counters) {
-  dense_reduce_send_kernel<<<ceil_div(a.total + 1, 256), 256, 0, ctx->stream>>>(a, st, p2p, emb_counters);
+  dense_reduce_send_kernel<<<std::min(ceil_div(a.total + 1, 256), ctx->num_sms * 4), 256, 0, ctx->stream>>>(a, st, p2p, emb_counters);
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }

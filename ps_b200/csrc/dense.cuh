@@ -26,6 +26,7 @@ struct StepStatus {
 /* one FcLayer's parameters as the fused update kernel sees them */
 struct DenseLayerDesc {
   float *W, *Wt, *bias;           /* W [out][ldw]; Wt [in][ldwt] transposed copy or null; bias [out] */
+  float *Wlo, *Wtlo;              /* W - tf32(W), Wt - tf32(Wt): the residual operands of the 3xTF32 GEMMs, kept current by whoever writes W (or null) */
   float *sW1, *sW2, *sb1, *sb2;   /* updater state of "fc<i>.weights" / "fc<i>.bias" */
   const float* G;                 /* [nsplit][out][ldg]; column `in` is the bias-gradient sum */
   size_t slab;
@@ -43,6 +44,8 @@ struct DenseUpdateArgs {
 
 void dense_init(Ctx* ctx, float* W, int out, int in, int ldw, float* Wt, int ldwt, uint64_t key, float maxv);
 void fill_column(Ctx* ctx, float* buf, int ld, int col, int rows, float value);
+/* lo[i] = x[i] - tf32_trunc(x[i]) over n floats: refreshes a weight matrix's residual copy after it was written from the host */
+void split_lo(Ctx* ctx, const float* x, float* lo, size_t n);
 /* also publishes the step status to mapped host memory when host_mapped is non-null */
 void dense_update(Ctx* ctx, const DenseUpdateArgs& a, StepStatus* st, const uint32_t* emb_counters, const uint32_t* wide_counters,
                   StepStatus* host_mapped, const P2PState* p2p = nullptr /* gradients come from this step's gsum_in mailbox */);

@@ -53,7 +53,7 @@ void FcOp::forward(const float* A_host, int N, float* out_host) {
   const bool fp32 = ctx->fc_precision == PS_FC_FP32;
   PS_CUDA(cudaMemcpy2DAsync(A, sizeof(float) * ldA, A_host, sizeof(float) * f.in, sizeof(float) * f.in, N, cudaMemcpyHostToDevice, s));
   FcFwdArgs a{};
-  a.B = N; a.in = f.in; a.out = f.out; a.A = A; a.lda = ldA; a.W = f.W; a.ldw = f.ldw; a.bias = f.bias; a.act = f.act;
+  a.B = N; a.in = f.in; a.out = f.out; a.A = A; a.lda = ldA; a.W = f.W; a.ldw = f.ldw; a.Wlo = f.Wlo; a.bias = f.bias; a.act = f.act;
   a.Z = Z; a.ldz = ldZ; a.Zt = nullptr; a.ldzt = ldt;
   if (fp32) fc_forward_fp32(ctx, a); else fc_forward_tf32(ctx, a);
   PS_CUDA(cudaMemcpy2DAsync(out_host, sizeof(float) * f.out, Z, sizeof(float) * ldZ, sizeof(float) * f.out, N, cudaMemcpyDeviceToHost, s));
@@ -82,7 +82,7 @@ void FcOp::backward(const float* delta_host, int N, float* dprev_host) {
   g.G = f.G; g.ldg = f.ldw; g.slab = (size_t)f.out * f.ldw; g.nsplit = f.nsplit;
   if (fp32) fc_wgrad_fp32(ctx, g); else fc_wgrad_tf32(ctx, g);
   FcDgradArgs d{};
-  d.B = N; d.in = f.in; d.out = f.out; d.dl = dl; d.ldd = ldZ; d.W = f.W; d.ldw = f.ldw; d.Wt = f.Wt; d.ldwt = f.ldwt;
+  d.B = N; d.in = f.in; d.out = f.out; d.dl = dl; d.ldd = ldZ; d.W = f.W; d.ldw = f.ldw; d.Wt = f.Wt; d.ldwt = f.ldwt; d.Wtlo = f.Wtlo;
   d.act_below = PS_ACT_NONE; d.Y = A; d.ldy = ldA; d.Yt = At; d.ldyt = ldt; d.n_cols = f.in; d.dX = dX; d.ldx = ldA; d.dXt = nullptr; d.ldxt = ldt;
   if (fp32) fc_dgrad_fp32(ctx, d); else fc_dgrad_tf32(ctx, d);
   if (dprev_host) PS_CUDA(cudaMemcpy2DAsync(dprev_host, sizeof(float) * f.in, dX, sizeof(float) * ldA, sizeof(float) * f.in, N, cudaMemcpyDeviceToHost, s));
@@ -95,7 +95,7 @@ void FcOp::update() {
   DenseUpdateArgs u{};
   u.n_layers = 1; u.N = lastN;
   DenseLayerDesc& q = u.l[0];
-  q.W = f.W; q.Wt = f.Wt; q.bias = f.bias; q.sW1 = f.sW1; q.sW2 = f.sW2; q.sb1 = f.sb1; q.sb2 = f.sb2;
+  q.W = f.W; q.Wt = f.Wt; q.Wlo = f.Wlo; q.Wtlo = f.Wtlo; q.bias = f.bias; q.sW1 = f.sW1; q.sW2 = f.sW2; q.sb1 = f.sb1; q.sb2 = f.sb2;
   q.G = f.G; q.slab = (size_t)f.out * f.ldw; q.nsplit = f.nsplit; q.out = f.out; q.in = f.in; q.ldw = f.ldw; q.ldwt = f.ldwt; q.ldg = f.ldw;
   q.updW = make_updater_dev(f.updW); q.updB = make_updater_dev(f.updB);
   q.first = 0;
@@ -156,6 +156,7 @@ void FcOp::put(int which, const float* in, int n) {
     }
   PS_CUDA(cudaMemcpyAsync(f.W, tmp.data(), sizeof(float) * tmp.size(), cudaMemcpyHostToDevice, s));
   PS_CUDA(cudaMemcpyAsync(f.Wt, tmpt.data(), sizeof(float) * tmpt.size(), cudaMemcpyHostToDevice, s));
+  f.refresh_lo(ctx);
   PS_CUDA(cudaStreamSynchronize(s));
 }
 

@@ -23,6 +23,7 @@ struct FcFwdArgs {
   int B, in, out;
   const float* A; int lda;        /* [B][lda] */
   const float* W; int ldw;        /* [out][ldw] */
+  const float* Wlo;               /* optional W - tf32(W), same layout (3xTF32: the residual arrives by TMA instead of being split per tile) */
   const float* bias;              /* [out] */
   int act;                        /* PS_ACT_NONE | RELU | SIGMOID (softmax is applied by the tail kernel) */
   float* Z; int ldz;              /* [B][ldz] */
@@ -34,6 +35,7 @@ struct FcDgradArgs {
   const float* dl; int ldd;       /* [B][ldd] delta of this layer (activation derivative already applied) */
   const float* W; int ldw;        /* [out][ldw] */
   const float* Wt; int ldwt;      /* [in][ldwt] transposed copy (TF32 path; may be null for fp32) */
+  const float* Wtlo;              /* optional Wt - tf32(Wt) */
   int act_below;                  /* activation of the layer below, whose output is Y */
   const float* Y; int ldy;        /* [B][ldy] */
   const float* Yt; int ldyt;      /* transposed copy [in][ldyt] (TF32 path: coalesced read in the epilogue) */

@@ -119,9 +119,11 @@ struct SmemLayout {
   static constexpr uint32_t TOTAL = BAR_OFF + 256 + 1024;   /* + barriers/tmem slot + manual 1024 B alignment slack */
 };
 
-template <int BLOCK_N, int EPI, bool SPLIT>
+/* PRE_B (3xTF32 only): the B operand is a weight matrix whose residual B_lo = B - tf32(B) is kept in HBM by the kernels that write the
+ * weights (dense_update / split_lo) and arrives by TMA like B itself; only the A tiles (activations, deltas) are split in the kernel */
+template <int BLOCK_N, int EPI, bool SPLIT, bool PRE_B>
 __global__ void __launch_bounds__(SPLIT ? 256 : 128) gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                                                        const TcParams p) {
+                                                        const __grid_constant__ CUtensorMap tmBlo, const TcParams p) {
   pdl_launch_dependents();                     /* the next kernel of the chain may set itself up while this one runs */
   using SL = SmemLayout<BLOCK_N, SPLIT>;
   constexpr int STAGES = SL::STAGES;
@@ -148,6 +150,7 @@ __global__ void __launch_bounds__(SPLIT ? 256 : 128) gemm_tf32_kernel(const __gr
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (PRE_B) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "r"((uint32_t)TMEM_COLS) : "memory");
@@ -166,10 +169,11 @@ __global__ void __launch_bounds__(SPLIT ? 256 : 128) gemm_tf32_kernel(const __gr
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % STAGES;
       mbar_wait(empty0 + 8 * s, ((kb / STAGES) & 1) ^ 1);
-      mbar_expect_tx(full0 + 8 * s, SL::A_BYTES + SL::B_BYTES);
+      mbar_expect_tx(full0 + 8 * s, SL::A_BYTES + (PRE_B ? 2u : 1u) * SL::B_BYTES);
       const int k = (kb_begin + kb) * BK;
       tma_load_2d(stage0 + s * SL::STAGE_BYTES, &tmA, full0 + 8 * s, k, m0);
       tma_load_2d(stage0 + s * SL::STAGE_BYTES + OFF_B, &tmB, full0 + 8 * s, k, n0);
+      if (PRE_B) tma_load_2d(stage0 + s * SL::STAGE_BYTES + OFF_BLO, &tmBlo, full0 + 8 * s, k, n0);
     }
   } else if (warp == 1 && lane == 0) {
     /* ===== MMA issuer ===== */
@@ -204,7 +208,7 @@ __global__ void __launch_bounds__(SPLIT ? 256 : 128) gemm_tf32_kernel(const __gr
     /* ===== residual producers (warps 2-7, 192 threads): lo = x - tf32(x), element-wise, so the swizzled tile
      * layout carries over byte for byte; generic-proxy stores are fenced for the async proxy ===== */
     const int t = threadIdx.x - 64;                 /* 0..191 */
-    constexpr int CHUNKS = (int)((SL::A_BYTES + SL::B_BYTES) / 16);
+    constexpr int CHUNKS = (int)((SL::A_BYTES + (PRE_B ? 0u : SL::B_BYTES)) / 16);   /* [A | B] are contiguous, and so are [A_lo | B_lo] */
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % STAGES;
       mbar_wait(full0 + 8 * s, (kb / STAGES) & 1);
@@ -218,7 +222,8 @@ __global__ void __launch_bounds__(SPLIT ? 256 : 128) gemm_tf32_kernel(const __gr
         hi.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); lo.y = x.y - hi.y;
         hi.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); lo.z = x.z - hi.z;
         hi.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); lo.w = x.w - hi.w;
-        *reinterpret_cast<float4*>(src + 16 * c) = hi;     /* explicit high part: exact in TF32 whatever the core's rounding */
+        /* the raw tile stays as it is: kind::tf32 TRUNCATES its operands to the top 19 bits (scripts/tf32_rounding_probe.py on B200:
+         * 1 + 3*2^-12 -> 1, -(1 + 3*2^-12) -> -1, 1 + 2^-11 + 2^-20 -> 1), so the tensor core reads exactly `hi` from it */
         *reinterpret_cast<float4*>(dst + 16 * c) = lo;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -353,11 +358,12 @@ const CUtensorMap& tensor_map(const float* ptr, int rows, int k_extent, long ld,
   return cache.emplace(key, m).first->second;
 }
 
-template <int BLOCK_N, int EPI, bool SPLIT>
-void launch_tc(Ctx* ctx, const float* A, long lda, const float* B, long ldb, TcParams& p, int nsplit) {
+template <int BLOCK_N, int EPI, bool SPLIT, bool PRE_B>
+void launch_tc(Ctx* ctx, const float* A, long lda, const float* B, long ldb, const float* Blo, TcParams& p, int nsplit) {
   using SL = SmemLayout<BLOCK_N, SPLIT>;
   const CUtensorMap ta = tensor_map(A, p.M, p.K, lda, BM);
   const CUtensorMap tb = tensor_map(B, p.N, p.K, ldb, BLOCK_N);
+  const CUtensorMap tbl = PRE_B ? tensor_map(Blo, p.N, p.K, ldb, BLOCK_N) : tb;
   const int nkb = (p.K + BK - 1) / BK;
   p.kb_per_split = (nkb + nsplit - 1) / nsplit;
   dim3 grid(ceil_div(p.N, BLOCK_N), ceil_div(p.M, BM), nsplit);
@@ -368,41 +374,42 @@ void launch_tc(Ctx* ctx, const float* A, long lda, const float* B, long ldb, TcP
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    PS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BLOCK_N, EPI, SPLIT>, ta, tb, p));
+    PS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BLOCK_N, EPI, SPLIT, PRE_B>, ta, tb, tbl, p));
   } else {
-    gemm_tf32_kernel<BLOCK_N, EPI, SPLIT><<<grid, SPLIT ? 256 : 128, SL::TOTAL, ctx->stream>>>(ta, tb, p);
+    gemm_tf32_kernel<BLOCK_N, EPI, SPLIT, PRE_B><<<grid, SPLIT ? 256 : 128, SL::TOTAL, ctx->stream>>>(ta, tb, tbl, p);
   }
   PS_LAUNCH_CHECK();
   ctx->launches++;
 }
 
+template <int BLOCK_N, int EPI>
+void launch_tc_mode(Ctx* ctx, const float* A, long lda, const float* B, long ldb, const float* Blo, TcParams& p, int nsplit) {
+  if (ctx->fc_precision != PS_FC_TF32X3) launch_tc<BLOCK_N, EPI, false, false>(ctx, A, lda, B, ldb, nullptr, p, nsplit);
+  else if (Blo != nullptr && EPI != EPI_WGRAD) launch_tc<BLOCK_N, EPI, true, true>(ctx, A, lda, B, ldb, Blo, p, nsplit);
+  else launch_tc<BLOCK_N, EPI, true, false>(ctx, A, lda, B, ldb, nullptr, p, nsplit);
+}
+
 template <int EPI>
-void dispatch_tc(Ctx* ctx, const float* A, long lda, const float* B, long ldb, TcParams& p, int nsplit) {
+void dispatch_tc(Ctx* ctx, const float* A, long lda, const float* B, long ldb, const float* Blo, TcParams& p, int nsplit) {
   /* 128-wide tiles when 64-wide ones would not fit one wave (1 CTA per SM): fc0's dgrad at cfg2 is 7 x 32 = 224 CTAs
    * at 64 columns, 4 x 32 = 128 at 128 — and every A tile is read (and split) half as often */
   const bool wide = p.N >= 128 && (long)ceil_div(p.N, 64) * ceil_div(p.M, BM) * nsplit > ctx->num_sms;
-  if (wide) {
-    if (ctx->fc_precision == PS_FC_TF32X3) launch_tc<128, EPI, true>(ctx, A, lda, B, ldb, p, nsplit);
-    else launch_tc<128, EPI, false>(ctx, A, lda, B, ldb, p, nsplit);
-    return;
-  }
-  if (ctx->fc_precision == PS_FC_TF32X3) {
-    if (p.N <= 16) launch_tc<16, EPI, true>(ctx, A, lda, B, ldb, p, nsplit);
-    else if (p.N <= 32) launch_tc<32, EPI, true>(ctx, A, lda, B, ldb, p, nsplit);
-    else launch_tc<64, EPI, true>(ctx, A, lda, B, ldb, p, nsplit);
-  } else {
-    if (p.N <= 16) launch_tc<16, EPI, false>(ctx, A, lda, B, ldb, p, nsplit);
-    else if (p.N <= 32) launch_tc<32, EPI, false>(ctx, A, lda, B, ldb, p, nsplit);
-    else launch_tc<64, EPI, false>(ctx, A, lda, B, ldb, p, nsplit);
-  }
+  if (wide) launch_tc_mode<128, EPI>(ctx, A, lda, B, ldb, Blo, p, nsplit);
+  else if (p.N <= 16) launch_tc_mode<16, EPI>(ctx, A, lda, B, ldb, Blo, p, nsplit);
+  else if (p.N <= 32) launch_tc_mode<32, EPI>(ctx, A, lda, B, ldb, Blo, p, nsplit);
+  else launch_tc_mode<64, EPI>(ctx, A, lda, B, ldb, Blo, p, nsplit);
 }
 
 template <int BLOCK_N, bool SPLIT>
 void set_attr() {
   const int bytes = (int)SmemLayout<BLOCK_N, SPLIT>::TOTAL;
-  PS_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, EPI_FWD, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  PS_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, EPI_DGRAD, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  PS_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, EPI_WGRAD, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  PS_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, EPI_FWD, SPLIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  PS_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, EPI_DGRAD, SPLIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  PS_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, EPI_WGRAD, SPLIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if (SPLIT) {
+    PS_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, EPI_FWD, SPLIT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    PS_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, EPI_DGRAD, SPLIT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  }
 }
 
 }  // namespace
@@ -422,7 +429,7 @@ void fc_forward_tf32(Ctx* ctx, const FcFwdArgs& a) {
   p.M = a.B; p.N = a.out; p.K = a.in;
   p.C = a.Z; p.ldc = a.ldz; p.slab = 0; p.Ct = a.Zt; p.ldct = a.ldzt;
   p.bias = a.bias; p.act = a.act;
-  dispatch_tc<EPI_FWD>(ctx, a.A, a.lda, a.W, a.ldw, p, 1);
+  dispatch_tc<EPI_FWD>(ctx, a.A, a.lda, a.W, a.ldw, a.Wlo, p, 1);
 }
 
 void fc_dgrad_tf32(Ctx* ctx, const FcDgradArgs& a) {
@@ -432,7 +439,7 @@ void fc_dgrad_tf32(Ctx* ctx, const FcDgradArgs& a) {
   p.C = a.dX; p.ldc = a.ldx; p.slab = 0; p.Ct = a.dXt; p.ldct = a.ldxt;
   p.act = a.act_below; p.Yt = a.Yt; p.ldyt = a.ldyt;
   PS_REQUIRE(p.act == PS_ACT_NONE || p.Yt != nullptr, PS_ERR_ARG, "tf32 dgrad needs the transposed activation of the layer below");
-  dispatch_tc<EPI_DGRAD>(ctx, a.dl, a.ldd, a.Wt, a.ldwt, p, 1);
+  dispatch_tc<EPI_DGRAD>(ctx, a.dl, a.ldd, a.Wt, a.ldwt, a.Wtlo, p, 1);
 }
 
 void fc_wgrad_tf32(Ctx* ctx, const FcWgradArgs& a) {
@@ -440,7 +447,7 @@ void fc_wgrad_tf32(Ctx* ctx, const FcWgradArgs& a) {
   TcParams p{};
   p.M = a.out; p.N = a.in + 1; p.K = a.B;
   p.C = a.G; p.ldc = a.ldg; p.slab = a.slab; p.Ct = nullptr;
-  dispatch_tc<EPI_WGRAD>(ctx, a.dlT, a.ldt, a.AT, a.ldt, p, a.nsplit);
+  dispatch_tc<EPI_WGRAD>(ctx, a.dlT, a.ldt, a.AT, a.ldt, nullptr, p, a.nsplit);
 }
 
 }  // namespace psb

@@ -35,6 +35,8 @@ void FcLayer::create(Ctx* ctx, const std::string& nm, int in_, int out_, int act
   cudaStream_t s = ctx->stream;
   W = dmalloc_zero<float>((size_t)out * ldw, s);
   Wt = dmalloc_zero<float>((size_t)in * ldwt, s);
+  Wlo = dmalloc_zero<float>((size_t)out * ldw, s);
+  Wtlo = dmalloc_zero<float>((size_t)in * ldwt, s);
   bias = dmalloc_zero<float>(out, s);
   sW1 = dmalloc_zero<float>((size_t)out * ldw, s); sW2 = dmalloc_zero<float>((size_t)out * ldw, s);
   sb1 = dmalloc_zero<float>(out, s); sb2 = dmalloc_zero<float>(out, s);
@@ -42,10 +44,15 @@ void FcLayer::create(Ctx* ctx, const std::string& nm, int in_, int out_, int act
   /* FcLayer.pullWeights (FcLayer.java:112-115): KVStore.get(name + ".weights", initW) creates on first use */
   dense_init(ctx, W, out, in, ldw, Wt, ldwt, ps_name_key((name + ".weights").c_str()), xavier(in, out));
   dense_init(ctx, bias, out, 1, 1, nullptr, 0, ps_name_key((name + ".bias").c_str()), xavier(in, 1));
+  refresh_lo(ctx);
+}
+void FcLayer::refresh_lo(Ctx* ctx) {
+  split_lo(ctx, W, Wlo, (size_t)out * ldw);
+  split_lo(ctx, Wt, Wtlo, (size_t)in * ldwt);
 }
 void FcLayer::destroy() {
-  dfree(W); dfree(Wt); dfree(bias); dfree(sW1); dfree(sW2); dfree(sb1); dfree(sb2); dfree(G);
-  W = Wt = bias = sW1 = sW2 = sb1 = sb2 = G = nullptr;
+  dfree(W); dfree(Wt); dfree(Wlo); dfree(Wtlo); dfree(bias); dfree(sW1); dfree(sW2); dfree(sb1); dfree(sb2); dfree(G);
+  W = Wt = Wlo = Wtlo = bias = sW1 = sW2 = sb1 = sb2 = G = nullptr;
 }
 
 static ps_updater_spec mk_spec(int kind, float a, float b, float c, float d) {
@@ -217,7 +224,7 @@ void Model::fwd_layer(int l, int N) {                /* FcLayer.forward (FcLayer
   const bool fp32 = ctx->fc_precision == PS_FC_FP32;
   FcFwdArgs a{};
   a.B = N; a.in = fcs[l].in; a.out = fcs[l].out;
-  a.A = act[l]; a.lda = ld[l]; a.W = fcs[l].W; a.ldw = fcs[l].ldw; a.bias = fcs[l].bias; a.act = fcs[l].act;
+  a.A = act[l]; a.lda = ld[l]; a.W = fcs[l].W; a.ldw = fcs[l].ldw; a.Wlo = fcs[l].Wlo; a.bias = fcs[l].bias; a.act = fcs[l].act;
   a.Z = act[l + 1]; a.ldz = ld[l + 1];
   a.Zt = (!fp32 && l + 1 < L) ? act_t[l + 1] : nullptr; a.ldzt = ldt;
   if (fp32) fc_forward_fp32(ctx, a); else fc_forward_tf32(ctx, a);
@@ -262,7 +269,7 @@ void Model::dgrad_layer(int l, int N) {              /* FcLayer.backward: delta 
   }
   FcDgradArgs d{};
   d.B = N; d.in = f.in; d.out = f.out;
-  d.dl = delta[l + 1]; d.ldd = ld[l + 1]; d.W = f.W; d.ldw = f.ldw; d.Wt = f.Wt; d.ldwt = f.ldwt;
+  d.dl = delta[l + 1]; d.ldd = ld[l + 1]; d.W = f.W; d.ldw = f.ldw; d.Wt = f.Wt; d.ldwt = f.ldwt; d.Wtlo = f.Wtlo;
   d.act_below = act_below; d.Y = act[l]; d.ldy = ld[l]; d.Yt = act_t[l]; d.ldyt = ldt;
   d.n_cols = f.in; d.dX = delta[l]; d.ldx = ld[l];
   d.dXt = (!fp32 && l > 0) ? delta_t[l] : nullptr; d.ldxt = ldt;
@@ -364,7 +371,7 @@ DenseUpdateArgs Model::dense_args(int N) {
   for (int l = 0; l < L; ++l) {
     DenseLayerDesc& q = u.l[l];
     const FcLayer& f = fcs[l];
-    q.W = f.W; q.Wt = f.Wt; q.bias = f.bias; q.sW1 = f.sW1; q.sW2 = f.sW2; q.sb1 = f.sb1; q.sb2 = f.sb2;
+    q.W = f.W; q.Wt = f.Wt; q.Wlo = f.Wlo; q.Wtlo = f.Wtlo; q.bias = f.bias; q.sW1 = f.sW1; q.sW2 = f.sW2; q.sb1 = f.sb1; q.sb2 = f.sb2;
     q.G = f.G; q.slab = (size_t)f.out * f.ldw; q.nsplit = f.nsplit; q.out = f.out; q.in = f.in; q.ldw = f.ldw; q.ldwt = f.ldwt; q.ldg = f.ldw;
     q.updW = make_updater_dev(f.updW); q.updB = make_updater_dev(f.updB);
     q.first = first; first += (long)f.out * (f.in + 1);
@@ -872,6 +879,7 @@ void Model::put(const std::string& key, const float* in, int n) {
       }
     PS_CUDA(cudaMemcpyAsync(f.W, tmp.data(), sizeof(float) * tmp.size(), cudaMemcpyHostToDevice, ctx->stream));
     PS_CUDA(cudaMemcpyAsync(f.Wt, tmpt.data(), sizeof(float) * tmpt.size(), cudaMemcpyHostToDevice, ctx->stream));
+    f.refresh_lo(ctx);
     PS_CUDA(cudaStreamSynchronize(ctx->stream));
     return;
   }

@@ -28,6 +28,8 @@ struct FcLayer {
   int in = 0, out = 0, act = PS_ACT_NONE;
   int ldw = 0, ldwt = 0;
   float *W = nullptr, *Wt = nullptr, *bias = nullptr;
+  float *Wlo = nullptr, *Wtlo = nullptr;   /* residuals W - tf32(W), Wt - tf32(Wt) for the 3xTF32 GEMMs (TMA operands) */
+  void refresh_lo(Ctx* ctx);               /* after W / Wt were written from the host */
   float *sW1 = nullptr, *sW2 = nullptr, *sb1 = nullptr, *sb2 = nullptr;
   float* G = nullptr;            /* wgrad partial slabs [nsplit][out][ldw] */
   int nsplit = 1;

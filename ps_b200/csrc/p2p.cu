@@ -22,51 +22,55 @@ __global__ void p2p_begin_kernel(P2PState* st) {
  * later, with the gradient push.  The table needs no clearing pass: the push clears exactly the entries it used.   */
 __global__ void __launch_bounds__(256) p2p_route_send_kernel(P2PState* st, BatchSlot* __restrict__ bt, uint32_t BT, const int64_t* __restrict__ E, int L, int F,
                                                              int32_t* __restrict__ lk_b, int32_t* __restrict__ ulist) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;      /* field-major: a warp works on one field, consecutive samples */
   const int lane = threadIdx.x & 31;
   const int R = st->R, cap = st->cap;
-  int b = -1, owner = 0, l = -1;
-  unsigned long long key = PS_KEY_EMPTY;
-  if (t < L) {
-    const int N = L / F, j = t / N;
-    l = (t - j * N) * F + j;
-    key = ps_pack_key((uint32_t)j, (uint64_t)E[l]);
-    owner = (int)ps_owner_of(key, (uint32_t)R);
-  }
-  /* duplicates inside the warp (a hot key fills whole warps) are resolved by ONE lane: one probe, one count update */
-  const unsigned peers = __match_any_sync(0xffffffffu, key != PS_KEY_EMPTY ? key : (unsigned long long)lane);
-  const int leader = __ffs(peers) - 1;
-  bool first = false;
-  if (key != PS_KEY_EMPTY && lane == leader) {
-    uint32_t s = (uint32_t)(ps_mix64(key) >> 20) & (BT - 1u);
-    for (uint32_t p = 0; p < BT; ++p) {
-      const unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(&bt[s].key);
-      if (k == key) { b = (int)s; break; }
-      if (k == PS_KEY_EMPTY) {
-        const unsigned long long old = atomicCAS(&bt[s].key, (unsigned long long)PS_KEY_EMPTY, key);
-        if (old == PS_KEY_EMPTY || old == key) { b = (int)s; break; }
-      }
-      s = (s + 1u) & (BT - 1u);
-    }
-    if (b >= 0) first = atomicAdd(&bt[b].cnt, (uint32_t)__popc(peers)) == 0u;
-  }
-  b = __shfl_sync(0xffffffffu, b, leader);
-  if (t < L) lk_b[t] = b;                        /* field-major like EmbTable::lk_slot: the backward's scatter walks it the same way */
+  const int N = L / F;
   __shared__ int s_cnt[kP2PMaxRanks], s_base[kP2PMaxRanks];
-  if (threadIdx.x < kP2PMaxRanks) s_cnt[threadIdx.x] = 0;
-  __syncthreads();
-  int rank_in_block = 0;
-  if (first) rank_in_block = atomicAdd(&s_cnt[owner], 1);
-  __syncthreads();
-  if (threadIdx.x < R) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&st->cursor[threadIdx.x], s_cnt[threadIdx.x]) : 0;
-  __syncthreads();
-  if (first) {
-    const int pos = s_base[owner] + rank_in_block;
-    if (pos < cap) {
-      bt[b].upos = owner * cap + pos;
-      ulist[owner * cap + pos] = b;
-      reinterpret_cast<unsigned long long*>(p2p_region(st, owner, st->off_keys))[(size_t)st->me * cap + pos] = key;
-    } else { bt[b].upos = -1; st->overflow = 1; }
+  /* a capped grid striding over tiles of 256 lookups (the publish at the end costs one system fence + one ticket per block) */
+  for (int t0 = blockIdx.x * 256; t0 < L; t0 += gridDim.x * 256) {
+    const int t = t0 + threadIdx.x;                           /* field-major: a warp works on one field, consecutive samples */
+    int b = -1, owner = 0;
+    unsigned long long key = PS_KEY_EMPTY;
+    if (t < L) {
+      const int j = t / N;
+      key = ps_pack_key((uint32_t)j, (uint64_t)E[(size_t)(t - j * N) * F + j]);
+      owner = (int)ps_owner_of(key, (uint32_t)R);
+    }
+    /* duplicates inside the warp (a hot key fills whole warps) are resolved by ONE lane: one probe, one count update */
+    const unsigned peers = __match_any_sync(0xffffffffu, key != PS_KEY_EMPTY ? key : (unsigned long long)lane);
+    const int leader = __ffs(peers) - 1;
+    bool first = false;
+    if (key != PS_KEY_EMPTY && lane == leader) {
+      uint32_t s = (uint32_t)(ps_mix64(key) >> 20) & (BT - 1u);
+      for (uint32_t p = 0; p < BT; ++p) {
+        const unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(&bt[s].key);
+        if (k == key) { b = (int)s; break; }
+        if (k == PS_KEY_EMPTY) {
+          const unsigned long long old = atomicCAS(&bt[s].key, (unsigned long long)PS_KEY_EMPTY, key);
+          if (old == PS_KEY_EMPTY || old == key) { b = (int)s; break; }
+        }
+        s = (s + 1u) & (BT - 1u);
+      }
+      if (b >= 0) first = atomicAdd(&bt[b].cnt, (uint32_t)__popc(peers)) == 0u;
+    }
+    b = __shfl_sync(0xffffffffu, b, leader);
+    if (t < L) lk_b[t] = b;                      /* field-major like EmbTable::lk_slot: the backward's scatter walks it the same way */
+    if (threadIdx.x < kP2PMaxRanks) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    int rank_in_block = 0;
+    if (first) rank_in_block = atomicAdd(&s_cnt[owner], 1);
+    __syncthreads();
+    if (threadIdx.x < R) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&st->cursor[threadIdx.x], s_cnt[threadIdx.x]) : 0;
+    __syncthreads();
+    if (first) {
+      const int pos = s_base[owner] + rank_in_block;
+      if (pos < cap) {
+        bt[b].upos = owner * cap + pos;
+        ulist[owner * cap + pos] = b;
+        reinterpret_cast<unsigned long long*>(p2p_region(st, owner, st->off_keys))[(size_t)st->me * cap + pos] = key;
+      } else { bt[b].upos = -1; st->overflow = 1; }
+    }
+    __syncthreads();                             /* s_cnt / s_base are rewritten by the next tile */
   }
   p2p_publish_last(st, CH_KEYS, gridDim.x);
 }
@@ -134,20 +138,23 @@ __global__ void __launch_bounds__(256) p2p_reduce_kernel(const P2PState* st, flo
 /* Phase 2: one gradient sum per unique key, with the key's occurrence count in this rank's batch → its owner's
  * grads_in[me][pos] / gcnt_in[me][pos]; the local accumulator and the per-batch table entry are cleared for the next step */
 __global__ void __launch_bounds__(256) p2p_grad_send_kernel(P2PState* st, float* __restrict__ gacc, BatchSlot* __restrict__ bt, const int32_t* __restrict__ ulist) {
-  const int cap = st->cap, Dp = st->Dp, me = st->me, tpl = Dp >> 2;
-  const long total = (long)st->R * cap * tpl;
-  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g < total) {
-    const int q = (int)(g / tpl), part = (int)(g - (long)q * tpl);
-    const int owner = q / cap, pos = q - owner * cap;
-    if (pos < min(st->cursor[owner], cap)) {       /* final since route_send ended: an ordinary cached load (a volatile one per thread serialised 6 M requests on one L2 line) */
+  const int cap = st->cap, Dp = st->Dp, me = st->me, tpl = Dp >> 2, R = st->R;
+  /* a persistent grid (the publish at the end costs one system fence and one ticket per BLOCK): the blocks stride over the
+   * valid prefix of every owner's bucket — cursor[] is final since route_send ended */
+  for (int owner = 0; owner < R; ++owner) {
+    const long valid = (long)min(st->cursor[owner], cap) * tpl;
+    float* dst_rows = reinterpret_cast<float*>(p2p_region(st, owner, st->off_grads)) + (size_t)me * cap * Dp;
+    uint32_t* dst_cnt = reinterpret_cast<uint32_t*>(p2p_region(st, owner, st->off_gcnt)) + (size_t)me * cap;
+    for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < valid; g += (long)gridDim.x * blockDim.x) {
+      const int pos = (int)(g / tpl), part = (int)(g - (long)pos * tpl);
+      const int q = owner * cap + pos;
       float* a = gacc + (size_t)q * Dp + part * 4;
       const float4 v = __ldcg(reinterpret_cast<const float4*>(a));
-      st_f4(reinterpret_cast<float*>(p2p_region(st, owner, st->off_grads)) + ((size_t)me * cap + pos) * Dp + part * 4, v);
+      st_f4(dst_rows + (size_t)pos * Dp + part * 4, v);
       st_f4(a, make_float4(0.f, 0.f, 0.f, 0.f));
       if (part == 0) {
         const int b = ulist[q];
-        reinterpret_cast<uint32_t*>(p2p_region(st, owner, st->off_gcnt))[(size_t)me * cap + pos] = bt[b].cnt;
+        dst_cnt[pos] = bt[b].cnt;
         *reinterpret_cast<uint4*>(&bt[b]) = make_uint4(0u, 0u, 0u, 0u);
       }
     }
@@ -223,7 +230,7 @@ void P2P::begin() { p2p_begin_kernel<<<1, 32, 0, ctx->stream>>>(dev); P2P_LAUNCH
 void P2P::route_send(const int64_t* E, int N, int F) {
   const int L = N * F;
   PS_REQUIRE(L <= Lmax, PS_ERR_ARG, "p2p: batch larger than the de-duplication table");
-  p2p_route_send_kernel<<<ceil_div(L, 256), 256, 0, ctx->stream>>>(dev, bt, BT, E, L, F, lk_b, ulist);
+  p2p_route_send_kernel<<<std::min(ceil_div(L, 256), ctx->num_sms * 4), 256, 0, ctx->stream>>>(dev, bt, BT, E, L, F, lk_b, ulist);
   P2P_LAUNCHED();
 }
 
@@ -251,7 +258,8 @@ void P2P::reduce_gsum(float* gsum) {
 
 void P2P::grad_send() {
   const long total = (long)R * cap * (Dp / 4);
-  p2p_grad_send_kernel<<<ceil_div(total, 256), 256, 0, ctx->stream>>>(dev, gacc, bt, ulist);
+  const int grid = (int)std::max<long>(1, std::min<long>(ceil_div(total, 256), (long)ctx->num_sms * 6));
+  p2p_grad_send_kernel<<<grid, 256, 0, ctx->stream>>>(dev, gacc, bt, ulist);
   P2P_LAUNCHED();
 }
 

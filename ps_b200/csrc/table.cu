@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(256) emb_update_kernel(EmbSlot* __restrict__ s
     const int src0 = lane - ch;                               /* the key's chunk-0 lane */
     /* owner side of the peer-memory exchange: the slot counted (requester, key) entries; the occurrences of the key in the
      * global batch were summed into ucnt[u] by the owner-side scatter */
-    if (ucnt != nullptr && on && ch == 0) { cnt = __ldcg(ucnt + u); ucnt[u] = 0u; }
+    if (ucnt != nullptr && on && ch == 0) cnt = __ldcg(ucnt + u);   /* (zeroed at the end of the round, away from this load) */
     const uint32_t n_occ = __shfl_sync(0xffffffffu, cnt, src0);
     const float S0 = __shfl_sync(0xffffffffu, S.x, src0);
     const GeffScale gs = make_geff<EXACT>(n_occ > 0u ? n_occ : 1u, calls);
@@ -622,7 +622,10 @@ __global__ void __launch_bounds__(256) emb_update_kernel(EmbSlot* __restrict__ s
         st_f4(acc + (size_t)u * Dp + cc, make_float4(0.f, 0.f, 0.f, 0.f));
       }
       /* KVStore.clear (also after the early exit: the batch is forgotten): {cnt, uidx} = {0, ready} in one 8 B store */
-      if (ch == 0) *reinterpret_cast<unsigned long long*>(&slots[slot].cnt) = (unsigned long long)kRowReady << 32;
+      if (ch == 0) {
+        *reinterpret_cast<unsigned long long*>(&slots[slot].cnt) = (unsigned long long)kRowReady << 32;
+        if (ucnt != nullptr) ucnt[u] = 0u;
+      }
     }
     wi += wstride;
     have = wi * KPW < (long)U;
