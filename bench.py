@@ -554,11 +554,21 @@ def parity_check(env, cfg, steps=2):
     # flip sign against the oracle's summation order and cost 2 * alfa on that element — tolerated on <= 1 % of the rows
     outside = int((rels > tol_rows).sum())
     max_rel = float(rels[-1])
-    dense_rel = max(float(np.abs(v - o.get(k)).max() / max(1e-12, float(np.abs(o.get(k)).max()))) for k, v in dense.items())
-    ok = (loss_err <= tol_loss and outside <= max(1, rows // 100) and max_rel <= 2e-2 and dense_rel <= 5 * tol_rows
-          and rows >= min(200, len(keys)) and rows == len(keys) and dup == 0)
+    # dense weights: the same Adam sensitivity (an element whose gradient cancels to rounding noise moves by +-alfa per step in a
+    # direction the summation order decides): at most 0.1 % of a matrix's elements may be outside the tolerance, none by more than
+    # the 2 * alfa * steps an opposite-sign step sequence can produce
+    dense_rel, dense_frac, dense_abs = 0.0, 0.0, 0.0
+    for k, v in dense.items():
+        ov = o.get(k)
+        err = np.abs(v - ov)
+        scale = max(1e-12, float(np.abs(ov).max()))
+        dense_rel = max(dense_rel, float(np.quantile(err, 0.999)) / scale)
+        dense_frac = max(dense_frac, float((err > tol_rows * scale).mean()))
+        dense_abs = max(dense_abs, float(err.max()))
+    ok = (loss_err <= tol_loss and outside <= max(1, rows // 100) and max_rel <= 2e-2 and dense_rel <= tol_rows and dense_frac <= 1e-3
+          and dense_abs <= 2.2 * 0.005 * steps and rows >= min(200, len(keys)) and rows == len(keys) and dup == 0)
     return {"ok": bool(ok), "loss_err": loss_err, "rows_checked": rows, "rows_sampled": len(keys), "max_rel": max_rel, "rows_outside_tol": outside,
-            "median_rel": float(rels[len(rels) // 2]), "dense_max_rel": dense_rel,
+            "median_rel": float(rels[len(rels) // 2]), "dense_p999_rel": dense_rel, "dense_frac_outside_tol": dense_frac, "dense_max_abs": dense_abs,
             "keys_on_two_shards": dup, "steps": steps, "global_batch": world * Np, "tolerance": {"loss_rel": tol_loss, "rows_rel_to_max": tol_rows},
             "against": "CPU oracle, one Trainer step (thread = 1) per global batch on the concatenated batch"}
 

@@ -71,6 +71,10 @@ int ps_ctx_create(int device, uint64_t seed, ps_ctx** out) {
   c->c.exact_updaters = (xe && xe[0] == '1') ? 1 : 0;
   const char* ht = std::getenv("PS_HOT_TMA");
   c->c.hot_tma = (ht && ht[0] == '0') ? 0 : 1;
+  const char* ss = std::getenv("PS_SCATTER_SLAB");
+  c->c.scatter_slab = (ss && ss[0] == '0') ? 0 : 1;
+  const char* hs = std::getenv("PS_HOT_SHARE");
+  if (hs && hs[0]) c->c.hot_share = std::max(1, std::atoi(hs));
   const char* hm = std::getenv("PS_HOT_MIN");
   if (hm && hm[0]) { const long v = std::atol(hm); c->c.hot_min = v <= 0 ? 0xFFFFFFFFu : (unsigned)v; }
   PS_CUDA(cudaStreamCreateWithPriority(&c->c.stream, cudaStreamNonBlocking, c->c.prio_main));

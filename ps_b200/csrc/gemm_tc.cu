@@ -35,7 +35,13 @@ namespace {
 
 constexpr int BM = 128, BK = 32, UMMA_K = 8;
 /* pipeline depth: 8 stages cover a whole K = 256 operand in ONE L2 round trip; the 3xTF32 stages are twice as large */
-template <int BLOCK_N, bool SPLIT> struct Depth { static constexpr int STAGES = SPLIT ? (BLOCK_N > 64 ? 3 : 4) : (BLOCK_N > 64 ? 6 : 8); };
+/* 3xTF32 tiles up to 64 columns run TWO CTAs per SM (2 stages of 48 KB each, <= 128 registers): a 128-CTA GEMM no longer owns the GPU,
+ * so the weight-gradient GEMM on the side stream genuinely overlaps the dgrad chain, and one CTA's TMA latency / epilogue hides
+ * behind the other's MMAs */
+template <int BLOCK_N, bool SPLIT> struct Depth {
+  static constexpr int STAGES = SPLIT ? (BLOCK_N > 64 ? 3 : 2) : (BLOCK_N > 64 ? 6 : 8);
+  static constexpr int MIN_CTAS = (SPLIT && BLOCK_N <= 64) ? 2 : 1;
+};
 enum { EPI_FWD = 0, EPI_DGRAD = 1, EPI_WGRAD = 2 };
 
 struct TcParams {
@@ -122,7 +128,7 @@ struct SmemLayout {
 /* PRE_B (3xTF32 only): the B operand is a weight matrix whose residual B_lo = B - tf32(B) is kept in HBM by the kernels that write the
  * weights (dense_update / split_lo) and arrives by TMA like B itself; only the A tiles (activations, deltas) are split in the kernel */
 template <int BLOCK_N, int EPI, bool SPLIT, bool PRE_B>
-__global__ void __launch_bounds__(SPLIT ? 256 : 128) gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+__global__ void __launch_bounds__(SPLIT ? 256 : 128, Depth<BLOCK_N, SPLIT>::MIN_CTAS) gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                         const __grid_constant__ CUtensorMap tmBlo, const TcParams p) {
   pdl_launch_dependents();                     /* the next kernel of the chain may set itself up while this one runs */
   using SL = SmemLayout<BLOCK_N, SPLIT>;
@@ -238,7 +244,7 @@ __global__ void __launch_bounds__(SPLIT ? 256 : 128) gemm_tf32_kernel(const __gr
    * lanes = 32 consecutive rows read one 128 B line per column) are fetched while they fly.   */
   if (warp < 4) {   /* the four TMEM lane quadrants; with SPLIT warps 4-7 only produced residual tiles */
   /* the tile is drained in passes of at most 64 columns (register budget: 64 accumulators + 64 epilogue operands) */
-  constexpr int PN = BLOCK_N > 64 ? 64 : BLOCK_N;
+  constexpr int PN = (SPLIT && BLOCK_N <= 64) ? (BLOCK_N > 32 ? 32 : BLOCK_N) : (BLOCK_N > 64 ? 64 : BLOCK_N);   /* 2 CTAs / SM: half the epilogue registers */
   constexpr int NPASS = BLOCK_N / PN;
   constexpr int NCH = PN / 16;
   const int m = m0 + warp * 32 + lane;
@@ -393,7 +399,8 @@ template <int EPI>
 void dispatch_tc(Ctx* ctx, const float* A, long lda, const float* B, long ldb, const float* Blo, TcParams& p, int nsplit) {
   /* 128-wide tiles when 64-wide ones would not fit one wave (1 CTA per SM): fc0's dgrad at cfg2 is 7 x 32 = 224 CTAs
    * at 64 columns, 4 x 32 = 128 at 128 — and every A tile is read (and split) half as often */
-  const bool wide = p.N >= 128 && (long)ceil_div(p.N, 64) * ceil_div(p.M, BM) * nsplit > ctx->num_sms;
+  const int ctas_per_sm = ctx->fc_precision == PS_FC_TF32X3 ? 2 : 1;
+  const bool wide = p.N >= 128 && (long)ceil_div(p.N, 64) * ceil_div(p.M, BM) * nsplit > (long)ctas_per_sm * ctx->num_sms;
   if (wide) launch_tc_mode<128, EPI>(ctx, A, lda, B, ldb, Blo, p, nsplit);
   else if (p.N <= 16) launch_tc_mode<16, EPI>(ctx, A, lda, B, ldb, Blo, p, nsplit);
   else if (p.N <= 32) launch_tc_mode<32, EPI>(ctx, A, lda, B, ldb, Blo, p, nsplit);

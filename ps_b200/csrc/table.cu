@@ -136,7 +136,7 @@ struct LookupArgs {
                                             rows_in mailboxes, CH_ROWS published by the last block */
   float* out; int ldo;
   const float* X; int Xn, xoff;
-  int task_blocks, hot_tma;
+  int task_blocks, hot_tma, hot_share;   /* hot_share: lookups of one warp task that must share a row before the TMA unit fetches it (1: every row) */
 };
 
 static size_t lookup_smem_bytes(int Dp) { return 128 + (size_t)8 * 32 * Dp * sizeof(float); }
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(256) emb_lookup_kernel(const __grid_constant__
         const int part = lane % TPL, grp = lane / TPL;
         const bool lane_on = part * 4 < a.Dp;
         const bool fetch = slot >= 0 && leader == lane;               /* one lane per distinct row */
-        const bool hot = fetch && ready && a.hot_tma && __popc(peers) >= kHotShare;
+        const bool hot = fetch && ready && a.hot_tma && __popc(peers) >= a.hot_share;
         const unsigned hmask = __ballot_sync(0xffffffffu, hot);
         /* the slab was read with ordinary loads by the previous task: order those before the async-proxy writes below */
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -557,6 +557,132 @@ __global__ void __launch_bounds__(256) emb_scatter_kernel(const EmbSlot* __restr
   }
 }
 
+/* The scatter for the common case (16 B aligned rows, ReLU mask from the lookup's bits): same three levels of pre-summation, but
+ * a warp task is (field j, 32 consecutive samples) and the task's 32 delta rows are STAGED in the warp's shared-memory slab by
+ * 16 B asynchronous copies (LDGSTS) issued before anything else — the whole task is in flight at once without holding
+ * registers, beside the lk_slot / mask / slot-record loads.  Then, in shared memory: (1) every row is masked in place,
+ * (2) rows whose key another lane of the task leads are added into the leader's row, (3) leader rows leave the warp — into the
+ * block's hot-key table when the key is frequent in the batch, else as one red.global.add.v4.f32 per 16 B chunk into acc[uidx]. */
+template <int TPL>
+__global__ void __launch_bounds__(256) emb_scatter_slab_kernel(const EmbSlot* __restrict__ slots, int Dp, int D, const int32_t* __restrict__ lk_slot,
+                                                               const uint32_t* __restrict__ lk_mask, int MW, int N, int F,
+                                                               const float* __restrict__ delta, int ldd, float* __restrict__ acc,
+                                                               const int* __restrict__ skip_flag, uint32_t hot_min) {
+  constexpr int GPW = 32 / TPL, NP = TPL;
+  extern __shared__ __align__(128) unsigned char scatter_smem[];
+  int* hot_slot = reinterpret_cast<int*>(scatter_smem);                                  /* [kHotEntries] */
+  uint32_t* hot_row = reinterpret_cast<uint32_t*>(scatter_smem + 4 * kHotEntries);       /* [kHotEntries] */
+  uint32_t* maskw_all = reinterpret_cast<uint32_t*>(scatter_smem + 8 * kHotEntries);     /* [8 warps][32][4] */
+  float* hot_acc = reinterpret_cast<float*>(scatter_smem + 8 * kHotEntries + 8 * 32 * 4 * 4);   /* [kHotEntries][Dp] */
+  float* slab_all = hot_acc + (size_t)kHotEntries * Dp;                                  /* [8 warps][32][Dp] */
+  pdl_launch_dependents();                       /* the update kernel may start its prefetch now (it waits before reading acc) */
+  if (skip_flag != nullptr && *skip_flag != 0) return;   /* DNN.java:58-63 early exit: nothing is pushed */
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int part = lane % TPL, grp = lane / TPL;
+  const bool lane_on = part * 4 < D;
+  float* slab = slab_all + (size_t)warp * 32 * Dp;
+  uint32_t* maskw = maskw_all + warp * 32 * 4;
+  for (int i = threadIdx.x; i < kHotEntries; i += 256) hot_slot[i] = -1;
+  for (int i = threadIdx.x; i < kHotEntries * Dp; i += 256) hot_acc[i] = 0.f;
+  __syncthreads();
+
+  const long ntasks = (long)((N + 31) / 32) * F;
+  for (long task = (long)blockIdx.x * 8 + warp; task < ntasks; task += (long)gridDim.x * 8) {
+    const int sg = (int)(task / F), j = (int)(task - (long)sg * F);
+    const long nbase = (long)sg * 32, n = nbase + lane;
+    const bool in = n < N;
+    /* the task's delta rows: addresses are plain arithmetic, so the copies go out first */
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const int r = p * GPW + grp;
+      if (nbase + r < N && lane_on) tb_cp_async16(tb_smem_u32(slab + (size_t)r * Dp + part * 4), delta + (size_t)(nbase + r) * ldd + j * D + part * 4);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const long t = (long)j * N + n;
+    const int slot = in ? lk_slot[t] : -1;
+    if (in) {
+#pragma unroll 4
+      for (int w = 0; w < MW; ++w) maskw[lane * 4 + w] = lk_mask[(size_t)t * MW + w];
+    }
+    uint32_t cnt = 0u, row = 0u;
+    if (slot >= 0) { const uint4 m = *reinterpret_cast<const uint4*>(&slots[slot]); cnt = m.z; row = (m.w & ~kRowReady) - 1u; }
+    const unsigned peers = __match_any_sync(0xffffffffu, slot >= 0 ? slot : (-1 - lane));
+    const int leader = __ffs(peers) - 1;
+    /* keys frequent in the batch are summed in the block's table and leave the block once */
+    int e = -1;
+    if (slot >= 0 && leader == lane && cnt >= hot_min) {
+      uint32_t h = ((uint32_t)slot * 2654435761u) >> (32 - kHotBits);
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        const int old = atomicCAS(&hot_slot[h], -1, slot);
+        if (old == -1) hot_row[h] = row;
+        if (old == -1 || old == slot) { e = (int)h; break; }
+        h = (h + 1u) & (uint32_t)(kHotEntries - 1);
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    /* (1) Relu.backward in place: dy *= (y > 0 ? 1 : 0)  (activations/Relu.java:14-19), the factor from the recorded mask bits */
+#pragma unroll 4
+    for (int p = 0; p < NP; ++p) {
+      const int r = p * GPW + grp;
+      if (nbase + r < N && lane_on) {
+        float4 v = *reinterpret_cast<float4*>(slab + (size_t)r * Dp + part * 4);
+        const uint32_t b = maskw[r * 4 + (part >> 3)] >> ((part & 7) * 4);
+        v.x = __fmul_rn(v.x, (b & 1u) ? 1.f : 0.f); v.y = __fmul_rn(v.y, (b & 2u) ? 1.f : 0.f);
+        v.z = __fmul_rn(v.z, (b & 4u) ? 1.f : 0.f); v.w = __fmul_rn(v.w, (b & 8u) ? 1.f : 0.f);
+        *reinterpret_cast<float4*>(slab + (size_t)r * Dp + part * 4) = v;
+      }
+    }
+    __syncwarp();
+    /* (2) reduce-by-key inside the task: a row whose key another lane leads is added into the leader's row */
+    if (__any_sync(0xffffffffu, slot >= 0 && leader != lane)) {
+#pragma unroll 4
+      for (int p = 0; p < NP; ++p) {
+        const int r = p * GPW + grp;
+        const int sr = __shfl_sync(0xffffffffu, slot, r), lr = __shfl_sync(0xffffffffu, leader, r);
+        if (sr >= 0 && lr != r && lane_on) {
+          const float4 v = *reinterpret_cast<const float4*>(slab + (size_t)r * Dp + part * 4);
+          float* a = slab + (size_t)lr * Dp + part * 4;
+          if (v.x != 0.f) atomicAdd(a + 0, v.x);
+          if (v.y != 0.f) atomicAdd(a + 1, v.y);
+          if (v.z != 0.f) atomicAdd(a + 2, v.z);
+          if (v.w != 0.f) atomicAdd(a + 3, v.w);
+        }
+      }
+      __syncwarp();
+    }
+    /* (3) leader rows leave the warp */
+#pragma unroll 4
+    for (int p = 0; p < NP; ++p) {
+      const int r = p * GPW + grp;
+      const int sr = __shfl_sync(0xffffffffu, slot, r), lr = __shfl_sync(0xffffffffu, leader, r);
+      const int er = __shfl_sync(0xffffffffu, e, r);
+      const uint32_t rr = __shfl_sync(0xffffffffu, row, r);
+      if (sr < 0 || lr != r || !lane_on) continue;
+      const float4 v = *reinterpret_cast<const float4*>(slab + (size_t)r * Dp + part * 4);
+      if (er >= 0) {
+        float* a = hot_acc + (size_t)er * Dp + part * 4;
+        if (v.x != 0.f) atomicAdd(a + 0, v.x);
+        if (v.y != 0.f) atomicAdd(a + 1, v.y);
+        if (v.z != 0.f) atomicAdd(a + 2, v.z);
+        if (v.w != 0.f) atomicAdd(a + 3, v.w);
+      } else {
+        red_add_f4(acc + (size_t)rr * Dp + part * 4, v);
+      }
+    }
+    __syncwarp();                                /* the slab and the mask words are rewritten by the next task */
+  }
+  __syncthreads();
+  const int CH = Dp >> 2;
+  for (int i = threadIdx.x; i < kHotEntries * CH; i += 256) {
+    const int he = i / CH, cc = (i - he * CH) * 4;
+    if (hot_slot[he] < 0 || cc >= D) continue;
+    const float4 v = *reinterpret_cast<const float4*>(hot_acc + (size_t)he * Dp + cc);
+    if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) red_add_f4(acc + (size_t)hot_row[he] * Dp + cc, v);
+  }
+}
+
 /* KVStore.update + clear for the batch's unique keys.  A warp takes KPW = 32 / (Dp/4) consecutive entries of the unique
  * list per round, lane = (key, 16 B chunk); the chunk-0 lane of a key reads its batch count once and resets the slot's
  * per-batch fields when the key is done.  EXACT: see updaters.cuh.                                                   */
@@ -782,6 +908,7 @@ static void launch_lookup(EmbTable& t, LookupArgs& a, bool gather) {
   a.task_blocks = (int)std::min<long>(ceil_div(ntasks, 8), resident);
   const int xblocks = (gather && a.X != nullptr) ? ceil_div((long)a.N * a.Xn, 1024) : 0;
   a.hot_tma = (gather && t.ctx->hot_tma) ? 1 : 0;
+  a.hot_share = t.ctx->hot_share;
   const bool aligned = a.F == 0 || ((t.D % 4 == 0) && (a.ldo % 4 == 0) && ((uintptr_t)a.out % 16 == 0));
   const size_t smem = gather ? lookup_smem_bytes(t.Dp) : 0;
   const int grid = a.task_blocks + xblocks;
@@ -861,7 +988,38 @@ static void launch_scatter(EmbTable& t, const ScatterJob& j) {
   t.ctx->launches++;
 }
 
+static size_t scatter_slab_smem(int Dp) { return 8 * kHotEntries + 8 * 32 * 4 * 4 + (size_t)kHotEntries * Dp * 4 + (size_t)8 * 32 * Dp * 4; }
+template <int TPL>
+static void launch_scatter_slab(EmbTable& t, const ScatterJob& j) {
+  const size_t smem = scatter_slab_smem(t.Dp);
+  if (j.N == 0) {                                /* EmbTable::create (not inside a capture): opt in to the slab's shared memory, size the persistent grid */
+    PS_CUDA(cudaFuncSetAttribute(emb_scatter_slab_kernel<TPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t.scatter_slab_occ, emb_scatter_slab_kernel<TPL>, 256, smem));
+    return;
+  }
+  const long ntasks = (long)((j.N + 31) / 32) * j.F;
+  const int grid = (int)std::max<long>(1, std::min<long>(ceil_div(ntasks, 8), (long)t.ctx->num_sms * std::max(1, t.scatter_slab_occ)));
+  const long per_block = 32L * ceil_div(ntasks, (long)grid * 8) * 8 / std::max(1, j.F) + 32;      /* samples of one field a block sees */
+  const uint32_t hot_min = t.ctx->hot_min == 0xFFFFFFFFu ? 0xFFFFFFFFu : std::max<uint32_t>(t.ctx->hot_min, (uint32_t)(2L * j.N / per_block));
+  emb_scatter_slab_kernel<TPL><<<grid, 256, smem, t.ctx->stream>>>(j.recs, t.Dp, t.D, j.lk, j.mask, t.MW, j.N, j.F, j.delta, j.ldd, j.accp, j.skip, hot_min);
+  PS_LAUNCH_CHECK();
+  t.ctx->launches++;
+}
+
 static void dispatch_scatter(EmbTable& t, const ScatterJob& j) {
+  /* the staged form: 16 B aligned rows, the lookup's mask bits, the table's own records */
+  const bool slab_ok = t.ctx->scatter_slab && t.D % 4 == 0 && (j.N == 0 || (j.mask != nullptr && j.act == nullptr && !j.raw_row && j.ldd % 4 == 0 && (uintptr_t)j.delta % 16 == 0));
+  if (slab_ok) {
+    switch (t.tpl) {
+      case 1: launch_scatter_slab<1>(t, j); break;
+      case 2: launch_scatter_slab<2>(t, j); break;
+      case 4: launch_scatter_slab<4>(t, j); break;
+      case 8: launch_scatter_slab<8>(t, j); break;
+      case 16: launch_scatter_slab<16>(t, j); break;
+      default: launch_scatter_slab<32>(t, j); break;
+    }
+    if (j.N != 0) return;                        /* N == 0: also query the general kernel below */
+  }
   if (t.Dp % 8 == 0) {                          /* two 16 B chunks per lane: half the threads, twice the bytes in flight per thread */
     switch (pow2_ge(t.Dp / 8)) {
       case 1: launch_scatter<1, 2>(t, j); break;

@@ -77,6 +77,7 @@ struct EmbTable {
   uint32_t* counters = nullptr;
   int64_t last_L = 0;
   int scatter_occ[2] = {1, 1};         /* resident scatter blocks per SM (unaligned / aligned instantiation) */
+  int scatter_slab_occ = 1;            /* ... of the staged scatter kernel */
   int lookup_occ = 2;                  /* resident blocks per SM of the gathering lookup kernel (sizes its persistent grid) */
 
   void create(Ctx* c, int F_, int D_, int64_t capacity, const ps_updater_spec& u, int64_t max_lookups);
