@@ -469,7 +469,8 @@ void Model::p2p_step(const int64_t* E, const float* X, const int64_t* W, const f
      * that waits for the flags in its prologue: no flag kernels, no host */
     p2p.route_send(E, N, F);                                                    /* PSRouterClient.getList: each key of the batch once, stored into its owner's mailbox */
     emb.lookup_packed(nullptr, R * cap, nullptr, p2p.dev, true);                /* PServer.getList on the owner: find-or-insert, rows stored straight into the requesters' mailboxes */
-    p2p.unpack(N, F, D, act[0], ld[0], X, Xn, F * D);                           /* rows_in -> concat buffer (+ ConcatLayer) */
+    if (D % 4 == 0) emb.gather_resolved(p2p.bt, p2p.lk_b, p2p.dev, N, act[0], ld[0], X, Xn, F * D);   /* rows_in -> concat buffer (+ mask bits, ConcatLayer) */
+    else p2p.unpack(N, F, D, act[0], ld[0], X, Xn, F * D);
   } else {
     PS_CUDA(cudaMemcpy2DAsync(act[0], sizeof(float) * ld[0], X, sizeof(float) * Xn, sizeof(float) * Xn, N, cudaMemcpyDeviceToDevice, s));
   }
@@ -484,7 +485,7 @@ void Model::p2p_step(const int64_t* E, const float* X, const int64_t* W, const f
     shard_finish_scalars_p2p(ctx, st_dev, p2p.state(), u.total);
   }
   if (has_emb) {
-    emb.scatter_rows(p2p.bt, p2p.lk_b, p2p.gacc, delta[0], ld[0], act[0], ld[0], N);   /* client.push: one gradient sum per unique key of this rank's batch */
+    emb.scatter_rows(p2p.bt, p2p.lk_b, p2p.gacc, delta[0], ld[0], D % 4 == 0 ? nullptr : act[0], ld[0], N);   /* client.push: one gradient sum per unique key of this rank's batch */
     p2p.grad_send();                                                            /* ... with its occurrence count, to the owner */
   }
   fork(s1, s);                                                                  /* the global skip flag */

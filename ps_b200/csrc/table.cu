@@ -136,6 +136,9 @@ struct LookupArgs {
                                             rows_in mailboxes, CH_ROWS published by the last block */
   float* out; int ldo;
   const float* X; int Xn, xoff;
+  /* requester side of the exchange ("pre-resolved"): lookup t reads record pre_recs[pre_lk[t]] = {key, count, row index | -1} of the
+   * per-batch de-duplication table instead of probing; rows come from this step's rows_in mailbox (after waiting for CH_ROWS) */
+  const EmbSlot* pre_recs; const int32_t* pre_lk;
   int task_blocks, hot_tma, hot_share;   /* hot_share: lookups of one warp task that must share a row before the TMA unit fetches it (1: every row) */
 };
 
@@ -182,9 +185,12 @@ __global__ void __launch_bounds__(256) emb_lookup_kernel(const __grid_constant__
     }
     return;
   }
-  if (a.p2p != nullptr) p2p_wait_all(a.p2p, CH_KEYS);     /* every requester's keys (and their count) have landed in keys_in */
-  const IdT* __restrict__ ids = a.p2p != nullptr ? reinterpret_cast<const IdT*>(p2p_region(a.p2p, a.p2p->me, a.p2p->off_keys)) : static_cast<const IdT*>(a.ids);
-  const int32_t* __restrict__ pcounts = a.p2p != nullptr ? reinterpret_cast<const int32_t*>(p2p_region(a.p2p, a.p2p->me, a.p2p->off_counts)) : nullptr;
+  const bool pre = a.pre_lk != nullptr;
+  if (a.p2p != nullptr) p2p_wait_all(a.p2p, pre ? CH_ROWS : CH_KEYS);   /* the owners' rows / every requester's keys (and their count) have landed */
+  const float* __restrict__ rowsp = pre ? reinterpret_cast<const float*>(p2p_region(a.p2p, a.p2p->me, a.p2p->off_rows)) : a.rows;
+  const int rsp = pre ? a.Dp : a.rs;
+  const IdT* __restrict__ ids = (a.p2p != nullptr && !pre) ? reinterpret_cast<const IdT*>(p2p_region(a.p2p, a.p2p->me, a.p2p->off_keys)) : static_cast<const IdT*>(a.ids);
+  const int32_t* __restrict__ pcounts = (a.p2p != nullptr && !pre) ? reinterpret_cast<const int32_t*>(p2p_region(a.p2p, a.p2p->me, a.p2p->off_counts)) : nullptr;
   const int Fe = a.F > 0 ? a.F : 1;
   const long ntasks = (long)((a.N + 31) / 32) * Fe;
   const long W = (long)a.task_blocks * 8;          /* warps striding over the tasks */
@@ -211,7 +217,8 @@ __global__ void __launch_bounds__(256) emb_lookup_kernel(const __grid_constant__
       const int sg = (int)(tA / Fe), j = (int)(tA - (long)sg * Fe);
       const long n = (long)sg * 32 + lane;
       if (n < a.N) {
-        if (a.p2p != nullptr) {                    /* owner side of the peer-memory exchange: entry n = (requester n / cap, its idx-th key) */
+        if (pre) { const int b = a.pre_lk[(long)j * a.N + n]; raw_a = (IdT)b; rv_a = b >= 0; }
+        else if (a.p2p != nullptr) {               /* owner side of the peer-memory exchange: entry n = (requester n / cap, its idx-th key) */
           const int src = (int)(n / a.p2p->cap), idx = (int)(n - (long)src * a.p2p->cap);
           if (idx < pcounts[src]) { raw_a = ids[n]; rv_a = true; }
         } else if (a.F > 0) { raw_a = ids[n * a.F + j]; rv_a = true; }
@@ -220,7 +227,9 @@ __global__ void __launch_bounds__(256) emb_lookup_kernel(const __grid_constant__
     }
     /* ---- stage B: key, hash and home-bucket record of task tB (its ids were requested one iteration ago) ---- */
     unsigned long long key_b = PS_KEY_EMPTY; uint32_t bucket_b = 0u; ulonglong2 rec_b = make_ulonglong2(0ull, 0ull);
-    if (it >= -1 && tB < ntasks && rv_n) {
+    if (pre) {
+      if (it >= -1 && tB < ntasks && rv_n) { key_b = 1ull; bucket_b = (uint32_t)(int64_t)raw_n; rec_b = ld_slot(&a.pre_recs[bucket_b]); }
+    } else if (it >= -1 && tB < ntasks && rv_n) {
       const int j = (int)(tB % Fe);
       key_b = a.F > 0 ? ps_pack_key((uint32_t)j, (uint64_t)(int64_t)raw_n) : (unsigned long long)raw_n;   /* EMPTY marks padding in the fixed-capacity exchange */
       /* ids outside [0, 2^44) would silently alias another key's row (ps_pack_key masks): refuse the batch instead */
@@ -237,7 +246,9 @@ __global__ void __launch_bounds__(256) emb_lookup_kernel(const __grid_constant__
       /* 1. resolve */
       int slot = -1;
       bool ready = false;
-      if (key != PS_KEY_EMPTY) {
+      if (pre) {
+        if (key != PS_KEY_EMPTY) { slot = (int)(uint32_t)(rec_c.y >> 32); ready = slot >= 0; }   /* the row's place in rows_in (-1: its bucket overflowed) */
+      } else if (key != PS_KEY_EMPTY) {
         bool inserted;
         slot = emb_resolve(a.slots, a.C, key, bucket_c, rec_c, &inserted, &ready);
         if (slot < 0) atomicOr(&a.counters[CNT_ERR], 1u);   /* table full: the tail turns this into the step's skip flag — nothing is updated */
@@ -249,12 +260,12 @@ __global__ void __launch_bounds__(256) emb_lookup_kernel(const __grid_constant__
           atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + CNT_ROWS), 1ull);
         }
       }
-      if (in) a.lk_slot[(long)j * a.N + n] = slot;
+      if (in && !pre) a.lk_slot[(long)j * a.N + n] = slot;
       /* 2. count: every lookup counts 1 (owner side of the exchange: every requester's entry; the occurrence counts arrive with the push) */
       const unsigned peers = __match_any_sync(0xffffffffu, slot >= 0 ? slot : (-1 - lane));
       const int leader = __ffs(peers) - 1;
       uint32_t old = 1u, ubase = 0u;
-      if (slot >= 0 && leader == lane) old = atomicAdd(&a.slots[slot].cnt, (uint32_t)__popc(peers));
+      if (slot >= 0 && leader == lane && !pre) old = atomicAdd(&a.slots[slot].cnt, (uint32_t)__popc(peers));
       unsigned omask = 0u;
       bool is_owner = false;
       /* the group that found the batch counter at zero owns the key: claim its place in the unique list (consumes `old`) */
@@ -283,7 +294,7 @@ __global__ void __launch_bounds__(256) emb_lookup_kernel(const __grid_constant__
           const uint32_t bar = tb_smem_u32(&mbar[warp]);
           if (lane == 0) tb_mbar_expect_tx(bar, (uint32_t)__popc(hmask) * (uint32_t)a.Dp * 4u);
           __syncwarp();
-          if (hot) tb_bulk_g2s(tb_smem_u32(stage + (size_t)lane * a.Dp), a.rows + (size_t)slot * a.rs, (uint32_t)a.Dp * 4u, bar);
+          if (hot) tb_bulk_g2s(tb_smem_u32(stage + (size_t)lane * a.Dp), rowsp + (size_t)slot * rsp, (uint32_t)a.Dp * 4u, bar);
         }
         const int code = !fetch ? 0 : hot ? 1 : ready ? 2 : 3;       /* how row `lane` reaches the slab: - | TMA | LDGSTS | initialiser */
 #pragma unroll
@@ -291,7 +302,7 @@ __global__ void __launch_bounds__(256) emb_lookup_kernel(const __grid_constant__
           const int r = p * GPW + grp;
           const int rs_ = __shfl_sync(0xffffffffu, slot, r);
           const int rc_ = __shfl_sync(0xffffffffu, code, r);
-          if (rc_ == 2 && lane_on) tb_cp_async16(tb_smem_u32(stage + (size_t)r * a.Dp + part * 4), a.rows + (size_t)rs_ * a.rs + part * 4);
+          if (rc_ == 2 && lane_on) tb_cp_async16(tb_smem_u32(stage + (size_t)r * a.Dp + part * 4), rowsp + (size_t)rs_ * rsp + part * 4);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         if (code == 3) {                              /* created by this kernel (here or elsewhere): the initialiser's bits, not memory */
@@ -567,7 +578,7 @@ template <int TPL>
 __global__ void __launch_bounds__(256) emb_scatter_slab_kernel(const EmbSlot* __restrict__ slots, int Dp, int D, const int32_t* __restrict__ lk_slot,
                                                                const uint32_t* __restrict__ lk_mask, int MW, int N, int F,
                                                                const float* __restrict__ delta, int ldd, float* __restrict__ acc,
-                                                               const int* __restrict__ skip_flag, uint32_t hot_min) {
+                                                               const int* __restrict__ skip_flag, int raw_row, uint32_t hot_min) {
   constexpr int GPW = 32 / TPL, NP = TPL;
   extern __shared__ __align__(128) unsigned char scatter_smem[];
   int* hot_slot = reinterpret_cast<int*>(scatter_smem);                                  /* [kHotEntries] */
@@ -599,13 +610,18 @@ __global__ void __launch_bounds__(256) emb_scatter_slab_kernel(const EmbSlot* __
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     const long t = (long)j * N + n;
-    const int slot = in ? lk_slot[t] : -1;
+    int slot = in ? lk_slot[t] : -1;
     if (in) {
 #pragma unroll 4
       for (int w = 0; w < MW; ++w) maskw[lane * 4 + w] = lk_mask[(size_t)t * MW + w];
     }
     uint32_t cnt = 0u, row = 0u;
-    if (slot >= 0) { const uint4 m = *reinterpret_cast<const uint4*>(&slots[slot]); cnt = m.z; row = (m.w & ~kRowReady) - 1u; }
+    if (slot >= 0) {
+      const uint4 m = *reinterpret_cast<const uint4*>(&slots[slot]);
+      cnt = m.z;
+      if (raw_row) { row = m.w; if ((int)m.w < 0) slot = -1; }         /* requester side of the exchange: BatchSlot {key, cnt, bucket position | -1} */
+      else row = (m.w & ~kRowReady) - 1u;
+    }
     const unsigned peers = __match_any_sync(0xffffffffu, slot >= 0 ? slot : (-1 - lane));
     const int leader = __ffs(peers) - 1;
     /* keys frequent in the batch are summed in the block's table and leave the block once */
@@ -787,6 +803,106 @@ __global__ void __launch_bounds__(256) emb_scatter_entries_kernel(const EmbSlot*
   }
 }
 
+/* The same update with the TMA unit doing the memory work.  A warp takes kUpdKeys consecutive entries of the unique list per
+ * round: lane k fetches key k's whole record {w | s1 | s2} (ONE 12*Dp-byte cp.async.bulk — contiguous, one DRAM page) and its
+ * accumulator row into the warp's shared-memory slab, the 32 lanes run the updater on the slab, and lane k writes the record back
+ * (and the zeroed accumulator row) with one bulk store each.  No register holds data in flight; a round moves 8 KB per warp at D = 64. */
+static constexpr int kUpdKeys = 8;
+__device__ __forceinline__ void tb_bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+template <bool EXACT>
+__global__ void __launch_bounds__(256) emb_update_slab_kernel(EmbSlot* __restrict__ slots, float* __restrict__ rows, int rs, int Dp, int D,
+                                                              const int32_t* __restrict__ uniq, float* __restrict__ acc, UpdaterDev upd, int calls,
+                                                              const int* __restrict__ skip_flag, uint32_t* __restrict__ ucnt, uint32_t* __restrict__ counters) {
+  extern __shared__ __align__(128) unsigned char update_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(update_smem);
+  uint32_t* kcnt = reinterpret_cast<uint32_t*>(update_smem + 128) + warp * kUpdKeys;             /* occurrence count of the round's keys */
+  float* slab = reinterpret_cast<float*>(update_smem + 512) + (size_t)warp * (kUpdKeys * 4 + 1) * Dp;   /* [key][w | s1 | s2 | S], then one row of zeros */
+  float* zero_row = slab + (size_t)kUpdKeys * 4 * Dp;
+  const uint32_t bar = tb_smem_u32(&mbar[warp]);
+  for (int i = lane; i < Dp; i += 32) zero_row[i] = 0.f;
+  if (lane == 0) tb_mbar_init(bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  const int CH = Dp >> 2;
+  const uint32_t U = counters[CNT_CURSOR];                   /* final since the lookup kernel ended; reset below by the last block */
+  const bool skip = skip_flag != nullptr && *skip_flag != 0; /* written by the tail kernel, long before the scatter */
+  const long rounds = ((long)U + kUpdKeys - 1) / kUpdKeys;
+  const long wstride = (long)gridDim.x * 8;
+  long wi = (long)blockIdx.x * 8 + warp;
+  uint32_t parity = 0u;
+  const uint32_t rec_bytes = 12u * (uint32_t)Dp, row_bytes = 4u * (uint32_t)Dp;
+
+  int slot = -1; uint32_t cnt = 0u;
+  auto fetch_records = [&](long w) {               /* lane k: key k of round w — its slot, its batch count, its record on the way */
+    const long u = w * kUpdKeys + lane;
+    slot = -1; cnt = 0u;
+    if (lane < kUpdKeys && u < (long)U) {
+      slot = uniq[u];
+      cnt = *reinterpret_cast<const volatile uint32_t*>(&slots[slot].cnt);
+    }
+    const unsigned vm = __ballot_sync(0xffffffffu, slot >= 0);
+    if (!skip && vm != 0u) {
+      if (lane == 0) tb_mbar_expect_tx(bar, (uint32_t)__popc(vm) * (rec_bytes + row_bytes));
+      __syncwarp();
+      if (slot >= 0) tb_bulk_g2s(tb_smem_u32(slab + (size_t)lane * 4 * Dp), rows + (size_t)slot * rs, rec_bytes, bar);
+    }
+  };
+  bool have = wi < rounds;
+  if (have) fetch_records(wi);                     /* before the scatter kernel is known to be complete */
+  pdl_wait();
+  while (have) {
+    const long u = wi * kUpdKeys + lane;
+    if (!skip) {
+      if (slot >= 0) tb_bulk_g2s(tb_smem_u32(slab + (size_t)lane * 4 * Dp + 3 * Dp), acc + (size_t)u * Dp, row_bytes, bar);
+      if (ucnt != nullptr && slot >= 0) cnt = __ldcg(ucnt + u);   /* owner side of the exchange: the global occurrence count summed from the pushes */
+      if (lane < kUpdKeys) kcnt[lane] = cnt;
+      if (__any_sync(0xffffffffu, slot >= 0)) { tb_mbar_wait(bar, parity); parity ^= 1u; }
+      const int nk = __popc(__ballot_sync(0xffffffffu, slot >= 0));
+      __syncwarp();
+      for (int i = lane; i < nk * CH; i += 32) {
+        const int k = i / CH, cc = (i - k * CH) * 4;
+        float* r = slab + (size_t)k * 4 * Dp;
+        const uint32_t n_occ = kcnt[k];
+        const GeffScale gs = make_geff<EXACT>(n_occ > 0u ? n_occ : 1u, calls);
+        float4 wv = *reinterpret_cast<float4*>(r + cc), m1 = *reinterpret_cast<float4*>(r + Dp + cc), m2 = *reinterpret_cast<float4*>(r + 2 * Dp + cc);
+        const float4 S = *reinterpret_cast<float4*>(r + 3 * Dp + cc);
+        bool do_upd = true;
+        if (upd.kind == PS_UPD_FTRL) do_upd = emb_geff<EXACT>(r[3 * Dp], gs) != 0.0f;   /* FtrlUpdater.java:52: `if (dw.get(0) == 0) return w` */
+        if (do_upd) {
+          apply_elem<EXACT>(upd, wv.x, m1.x, m2.x, emb_geff<EXACT>(S.x, gs));
+          apply_elem<EXACT>(upd, wv.y, m1.y, m2.y, emb_geff<EXACT>(S.y, gs));
+          apply_elem<EXACT>(upd, wv.z, m1.z, m2.z, emb_geff<EXACT>(S.z, gs));
+          apply_elem<EXACT>(upd, wv.w, m1.w, m2.w, emb_geff<EXACT>(S.w, gs));
+        }
+        *reinterpret_cast<float4*>(r + cc) = wv;    /* S stays as it is (another lane may still need S[0]): the accumulator is zeroed from zero_row */
+        if (upd.kind != PS_UPD_SIMPLE) { *reinterpret_cast<float4*>(r + Dp + cc) = m1; *reinterpret_cast<float4*>(r + 2 * Dp + cc) = m2; }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   /* the slab's new contents are visible to the TMA unit */
+      __syncwarp();
+      if (slot >= 0) {
+        tb_bulk_s2g(rows + (size_t)slot * rs, tb_smem_u32(slab + (size_t)lane * 4 * Dp), rec_bytes);
+        tb_bulk_s2g(acc + (size_t)u * Dp, tb_smem_u32(zero_row), row_bytes);
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    /* KVStore.clear (also after the early exit: the batch is forgotten): {cnt, uidx} = {0, ready} in one 8 B store */
+    if (slot >= 0) {
+      *reinterpret_cast<unsigned long long*>(&slots[slot].cnt) = (unsigned long long)kRowReady << 32;
+      if (ucnt != nullptr) ucnt[u] = 0u;
+    }
+    if (!skip) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   /* the slab may be refilled */
+    __syncwarp();
+    wi += wstride;
+    have = wi < rounds;
+    if (have) fetch_records(wi);
+  }
+  if (!skip) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (last_block_done(&counters[CNT_TICKET_UPD], gridDim.x) && threadIdx.x == 0) counters[CNT_CURSOR] = 0u;
+}
+
 /* forget the batch: the slots of its unique list get {cnt, uidx} = {0, ready}; the cursor restarts */
 __global__ void __launch_bounds__(256) emb_clear_batch_kernel(EmbSlot* __restrict__ slots, const int32_t* __restrict__ uniq, uint32_t* __restrict__ counters) {
   const uint32_t U = counters[CNT_CURSOR];
@@ -830,6 +946,7 @@ __global__ void emb_put_rows_kernel(EmbSlot* __restrict__ slots, uint32_t C, flo
 
 /* ------------------------------------------------------------------ EmbTable host side */
 static int pow2_ge(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+static void launch_update(EmbTable& t, long L, int calls, const int* skip, uint32_t* ucnt);
 
 /* the slab of every warp (32 rows) + the mbarriers: 64 KB at D = 64 — more than the default 48 KB, so every gathering
  * instantiation opts in (once per table, outside any stream capture) */
@@ -870,6 +987,7 @@ void EmbTable::create(Ctx* c, int F_, int D_, int64_t capacity, const ps_updater
   counters = dmalloc_zero<uint32_t>(CNT_WORDS, ctx->stream);
   reserve(max_lookups > 0 ? max_lookups : 1);
   scatter_update(nullptr, 0, nullptr, 0, 0, 2, nullptr);   /* fills scatter_occ (sizes the scatter's persistent grid) */
+  launch_update(*this, 0, 2, nullptr, nullptr);             /* opt-in shared memory + occupancy of the staged update kernel */
   query_lookup_occupancy(*this);
 }
 
@@ -961,6 +1079,14 @@ struct ScatterJob {
   const EmbSlot* recs; const int32_t* lk; const uint32_t* mask; float* accp;
   const float* delta; int ldd; const float* act; int lda; int N, F; const int* skip; int raw_row;
 };
+void EmbTable::gather_resolved(const void* batch_slots, const int32_t* lk_batch, P2PState* p2p, int N, float* out, int ldo, const float* X, int Xn, int xoff) {
+  PS_REQUIRE((int64_t)N * F <= Lcap, PS_ERR_ARG, "embedding: batch larger than the reserved workspace");
+  LookupArgs a = base_args(*this);
+  a.N = N; a.F = F; a.out = out; a.ldo = ldo; a.X = X; a.Xn = Xn; a.xoff = xoff;
+  a.lk_mask = lk_mask; a.p2p = p2p; a.pre_recs = reinterpret_cast<const EmbSlot*>(batch_slots); a.pre_lk = lk_batch; a.ids = nullptr;
+  launch_lookup<int64_t>(*this, a, true);
+}
+
 template <int TPL, int CPL>
 static void launch_scatter(EmbTable& t, const ScatterJob& j) {
   constexpr int PASSES = TPL >= 4 ? 4 : TPL;     /* warp tasks in flight per warp */
@@ -1001,14 +1127,14 @@ static void launch_scatter_slab(EmbTable& t, const ScatterJob& j) {
   const int grid = (int)std::max<long>(1, std::min<long>(ceil_div(ntasks, 8), (long)t.ctx->num_sms * std::max(1, t.scatter_slab_occ)));
   const long per_block = 32L * ceil_div(ntasks, (long)grid * 8) * 8 / std::max(1, j.F) + 32;      /* samples of one field a block sees */
   const uint32_t hot_min = t.ctx->hot_min == 0xFFFFFFFFu ? 0xFFFFFFFFu : std::max<uint32_t>(t.ctx->hot_min, (uint32_t)(2L * j.N / per_block));
-  emb_scatter_slab_kernel<TPL><<<grid, 256, smem, t.ctx->stream>>>(j.recs, t.Dp, t.D, j.lk, j.mask, t.MW, j.N, j.F, j.delta, j.ldd, j.accp, j.skip, hot_min);
+  emb_scatter_slab_kernel<TPL><<<grid, 256, smem, t.ctx->stream>>>(j.recs, t.Dp, t.D, j.lk, j.mask, t.MW, j.N, j.F, j.delta, j.ldd, j.accp, j.skip, j.raw_row, hot_min);
   PS_LAUNCH_CHECK();
   t.ctx->launches++;
 }
 
 static void dispatch_scatter(EmbTable& t, const ScatterJob& j) {
   /* the staged form: 16 B aligned rows, the lookup's mask bits, the table's own records */
-  const bool slab_ok = t.ctx->scatter_slab && t.D % 4 == 0 && (j.N == 0 || (j.mask != nullptr && j.act == nullptr && !j.raw_row && j.ldd % 4 == 0 && (uintptr_t)j.delta % 16 == 0));
+  const bool slab_ok = t.ctx->scatter_slab && t.D % 4 == 0 && (j.N == 0 || (j.mask != nullptr && j.act == nullptr && j.ldd % 4 == 0 && (uintptr_t)j.delta % 16 == 0));
   if (slab_ok) {
     switch (t.tpl) {
       case 1: launch_scatter_slab<1>(t, j); break;
@@ -1042,7 +1168,32 @@ static void dispatch_scatter(EmbTable& t, const ScatterJob& j) {
 
 /* the update walks the unique list (<= L entries, how many is only known on the device): enough warps for one round at the
  * typical unique fraction, a grid-stride loop beyond; a programmatic dependent of the scatter launched just before it */
+static size_t update_slab_smem(int Dp) { return 512 + (size_t)8 * (kUpdKeys * 4 + 1) * Dp * sizeof(float); }
 static void launch_update(EmbTable& t, long L, int calls, const int* skip, uint32_t* ucnt) {
+  if (t.ctx->update_slab) {
+    const size_t smem = update_slab_smem(t.Dp);
+    if (L == 0) {                                /* EmbTable::create (not inside a capture) */
+      PS_CUDA(cudaFuncSetAttribute(emb_update_slab_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PS_CUDA(cudaFuncSetAttribute(emb_update_slab_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t.update_slab_occ, emb_update_slab_kernel<false>, 256, smem));
+      return;
+    }
+    const long rounds = ceil_div(L, kUpdKeys);
+    const int ugrid = (int)std::max<long>(1, std::min<long>(ceil_div(rounds, 8), (long)t.ctx->num_sms * std::max(1, t.update_slab_occ)));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ugrid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = t.ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = t.ctx->pdl ? 1 : 0;
+    if (t.ctx->exact_updaters)
+      PS_CUDA(cudaLaunchKernelEx(&cfg, emb_update_slab_kernel<true>, t.slots, t.rows, t.rs, t.Dp, t.D, (const int32_t*)t.uniq, t.acc, t.upd, calls, skip, ucnt, t.counters));
+    else
+      PS_CUDA(cudaLaunchKernelEx(&cfg, emb_update_slab_kernel<false>, t.slots, t.rows, t.rs, t.Dp, t.D, (const int32_t*)t.uniq, t.acc, t.upd, calls, skip, ucnt, t.counters));
+    t.ctx->launches++;
+    return;
+  }
+  if (L == 0) return;
   const int KPW = 32 / (t.Dp / 4);
   const int ugrid = (int)std::max<long>(1, std::min<long>(ceil_div(ceil_div(L, KPW), 8), (long)t.ctx->num_sms * 16));
   if (t.ctx->exact_updaters)
@@ -1056,7 +1207,8 @@ static void launch_update(EmbTable& t, long L, int calls, const int* skip, uint3
  * gacc[bucket position], with the same three levels of pre-summation as the local backward — a hot key's thousands of
  * occurrences leave a block once instead of serialising on one L2 line                                                  */
 void EmbTable::scatter_rows(const void* batch_slots, const int32_t* lk_batch, float* gacc, const float* delta, int ldd, const float* act, int lda, int N) {
-  ScatterJob j{reinterpret_cast<const EmbSlot*>(batch_slots), lk_batch, nullptr, gacc, delta, ldd, act, lda, N, F, nullptr, 1};
+  /* act == null: the mask bits gather_resolved recorded for this batch */
+  ScatterJob j{reinterpret_cast<const EmbSlot*>(batch_slots), lk_batch, act ? nullptr : lk_mask, gacc, delta, ldd, act, lda, N, F, nullptr, 1};
   dispatch_scatter(*this, j);
 }
 

@@ -77,6 +77,7 @@ struct EmbTable {
   uint32_t* counters = nullptr;
   int64_t last_L = 0;
   int scatter_occ[2] = {1, 1};         /* resident scatter blocks per SM (unaligned / aligned instantiation) */
+  int update_slab_occ = 1;             /* ... of the staged update kernel */
   int scatter_slab_occ = 1;            /* ... of the staged scatter kernel */
   int lookup_occ = 2;                  /* resident blocks per SM of the gathering lookup kernel (sizes its persistent grid) */
 
@@ -92,6 +93,10 @@ struct EmbTable {
    * out != null: rows (ReLU applied) to out[n][Dp].  p2p: keys come from this step's keys_in mailbox and, with send_rows,
    * every row goes straight into the requester's rows_in mailbox over NVLink (PServer.getList).                      */
   void lookup_packed(const uint64_t* keys, int n, float* out, P2PState* p2p = nullptr, bool send_rows = false);
+  /* requester side of the exchange: EmbeddingLayer.forward once the owners have answered — lookup t was resolved by the route kernel to
+   * record batch_slots[lk_batch[t]] (its row's place in this step's rows_in mailbox); same gather, ReLU mask bits and ConcatLayer copy
+   * as lookup(), no probing and no counting; waits for the owners' flags in-kernel */
+  void gather_resolved(const void* batch_slots, const int32_t* lk_batch, P2PState* p2p, int N, float* out, int ldo, const float* X, int Xn, int xoff);
   /* owner side of the push over peer memory: entries of this step's grads_in / gcnt_in mailboxes (n = R*cap, after
    * lookup_packed on the same entries) → accumulator rows → the update; waits for the requesters' flags in-kernel */
   void scatter_update_entries(const P2PState* p2p, int n, int calls, const int* skip_flag);
