@@ -115,6 +115,25 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows), "how": self.how}
 
 
+def nvlink_kib(index):
+    """Cumulative NVLink payload KiB (tx, rx) of one GPU over all its links (NVML field counters); None when NVML cannot say."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        out = []
+        for fid in (pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX):
+            v = pynvml.nvmlDeviceGetFieldValues(h, [(fid, 0xFFFFFFFF)])[0]
+            if v.nvmlReturn != 0:
+                return None
+            out.append(int(v.value.ullVal))
+        return tuple(out)
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------------------------- CPU oracle legs
 def oracle_model(cfg, seed):
     import oracle_lib as ol
@@ -311,7 +330,12 @@ class Workload:
         probe = env.max_over_ranks([one(warmup)])[0]
         reps = reps or self._reps(K, probe)
         l0 = env.ctx.launch_count()
+        nv0 = nvlink_kib(env.local_rank) if env.world > 1 else None
         ms = [one(warmup + (r + 1) * K) for r in range(reps)]
+        nv1 = nvlink_kib(env.local_rank) if env.world > 1 else None
+        self.nvlink = None
+        if nv0 and nv1:                              # NVML's own counters: what actually crossed this GPU's links during the timed steps
+            self.nvlink = {"tx_bytes_per_step": 1024.0 * (nv1[0] - nv0[0]) / (reps * K), "rx_bytes_per_step": 1024.0 * (nv1[1] - nv0[1]) / (reps * K)}
         launches = (env.ctx.launch_count() - l0) / reps
         if self.trainer is not None and hasattr(self.trainer, "launches_per_step"):
             launches = K * self.trainer.launches_per_step           # torch graph replays: counted at the eager warm-up step
@@ -749,6 +773,14 @@ def main():
             ingest = {"error": str(ex)}
 
     uniq, ring_unique = wl.unique_stats()
+    nvlink = getattr(wl, "nvlink", None)
+    if nvlink is not None and F:
+        Dp_ = (D + 3) // 4 * 4
+        remote = uniq * (world - 1) / world          # unique keys of a batch owned by another rank
+        glen = sum((a + 1) * b for a, b in zip([F * D + cfg["Xn"]] + list(cfg["fc"])[:-1], cfg["fc"])) + 3
+        nvlink["expected_payload_bytes_per_step"] = (remote * (8 + 2 * 4 * Dp_ + 4)            # keys out, rows back, gradient sums + counts out
+                                                     + (world - 1) * (4 * glen + (8 * B * F if cfg["kind"] == "widedeep" else 0)))   # dense sums, wide ids to every replica
+        nvlink["how"] = "NVML NVLINK_THROUGHPUT_DATA_TX/RX of rank 0's GPU around the timed device-resident steps; expected = de-duplicated keys, rows and gradient sums to/from other owners + dense gradient sums and wide ids to every replica"
     loss_value = v["loss"]
     wl_cap = wl.cap
     wl_ring = len(wl.ring)
@@ -800,7 +832,7 @@ def main():
                            "pinned host batch -> device (async copy on the step's stream) -> sharded step -> ps_model_read_loss, every step"},
             "gpu_launches": int(round(v["launches"])), "clocks": clocks, "roofline": roofline, "roofline_tensor": roofline_tensor,
             "roofline_large_batch": large, "tf32_peak_tflops": tf32_peak, "kernels_us": phase_us, "hbm_kernels": kernels, "cfg5": cfg5,
-            "parity": parity, "extra_configs": extras,
+            "parity": parity, "extra_configs": extras, "nvlink": nvlink,
             "cpu_baseline": cpu, "ingest": ingest, "loss": loss_value, "loss_e2e": e["loss"], "unique_keys_per_batch": uniq,
         }
         print(json.dumps(line), flush=True)

@@ -61,6 +61,8 @@ void fc_wgrad_fp32(Ctx* ctx, const FcWgradArgs& a);
 void fc_forward_tf32(Ctx* ctx, const FcFwdArgs& a);
 void fc_dgrad_tf32(Ctx* ctx, const FcDgradArgs& a);
 void fc_wgrad_tf32(Ctx* ctx, const FcWgradArgs& a);
+/* the weight-gradient GEMMs of n layers in one launch (false: not groupable — launch them one by one) */
+bool fc_wgrad_grouped_tf32(Ctx* ctx, const FcWgradArgs* a, int n);
 void fc_tf32_init();   /* one-time kernel attributes (must not happen inside a stream capture) */
 
 #if defined(__CUDACC__)

@@ -128,8 +128,9 @@ struct SmemLayout {
 /* PRE_B (3xTF32 only): the B operand is a weight matrix whose residual B_lo = B - tf32(B) is kept in HBM by the kernels that write the
  * weights (dense_update / split_lo) and arrives by TMA like B itself; only the A tiles (activations, deltas) are split in the kernel */
 template <int BLOCK_N, int EPI, bool SPLIT, bool PRE_B>
-__global__ void __launch_bounds__(SPLIT ? 256 : 128, Depth<BLOCK_N, SPLIT>::MIN_CTAS) gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                                                        const __grid_constant__ CUtensorMap tmBlo, const TcParams p) {
+__device__ __forceinline__ void gemm_tf32_body(const CUtensorMap* tmA_, const CUtensorMap* tmB_, const CUtensorMap* tmBlo_, const TcParams& p,
+                                               int bx, int by, int bz) {
+  const CUtensorMap& tmA = *tmA_; const CUtensorMap& tmB = *tmB_; const CUtensorMap& tmBlo = *tmBlo_;
   pdl_launch_dependents();                     /* the next kernel of the chain may set itself up while this one runs */
   using SL = SmemLayout<BLOCK_N, SPLIT>;
   constexpr int STAGES = SL::STAGES;
@@ -145,9 +146,9 @@ __global__ void __launch_bounds__(SPLIT ? 256 : 128, Depth<BLOCK_N, SPLIT>::MIN_
   volatile uint32_t* tslot_gen = reinterpret_cast<volatile uint32_t*>(gen_base + SL::BAR_OFF + 24 * STAGES + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BLOCK_N;
+  const int m0 = by * BM, n0 = bx * BLOCK_N;
   const int nkb_total = (p.K + BK - 1) / BK;
-  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_begin = bz * p.kb_per_split;
   const int num_kb = max(0, min(nkb_total, kb_begin + p.kb_per_split) - kb_begin);
 
   if (threadIdx.x == 0) {
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(SPLIT ? 256 : 128, Depth<BLOCK_N, SPLIT>::MIN_
   constexpr int NCH = PN / 16;
   const int m = m0 + warp * 32 + lane;
   const bool row_ok = m < p.M;
-  float* Cz = p.C + (size_t)blockIdx.z * p.slab;
+  float* Cz = p.C + (size_t)bz * p.slab;
   const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0);
   if (num_kb > 0) {
     mbar_wait(tfull, 0);
@@ -323,6 +324,31 @@ __global__ void __launch_bounds__(SPLIT ? 256 : 128, Depth<BLOCK_N, SPLIT>::MIN_
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TMEM_COLS) : "memory");
   }
+}
+
+template <int BLOCK_N, int EPI, bool SPLIT, bool PRE_B>
+__global__ void __launch_bounds__(SPLIT ? 256 : 128, Depth<BLOCK_N, SPLIT>::MIN_CTAS) gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                        const __grid_constant__ CUtensorMap tmBlo, const TcParams p) {
+  gemm_tf32_body<BLOCK_N, EPI, SPLIT, PRE_B>(&tmA, &tmB, &tmBlo, p, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+/* Every FcLayer's weight-gradient GEMM of a step in ONE launch (FcLayer.java:103-106 for all layers): the contractions are independent
+ * once the dgrad chain has produced the deltas, each alone fills barely half the GPU (80-112 CTAs), together they are one wave at two
+ * CTAs per SM — and the dgrad chain before them runs without a competitor for the SMs.                                          */
+constexpr int kMaxGroup = 8;
+struct GroupedTc {
+  CUtensorMap tmA[kMaxGroup], tmB[kMaxGroup];
+  TcParams p[kMaxGroup];
+  int first[kMaxGroup + 1], gx[kMaxGroup], gy[kMaxGroup];
+  int n;
+};
+template <int BLOCK_N, bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? 256 : 128, Depth<BLOCK_N, SPLIT>::MIN_CTAS) gemm_tf32_grouped_wgrad_kernel(const __grid_constant__ GroupedTc g) {
+  int pi = 0;
+  while (pi + 1 < g.n && (int)blockIdx.x >= g.first[pi + 1]) ++pi;
+  const int local = (int)blockIdx.x - g.first[pi];
+  const int bx = local % g.gx[pi], by = (local / g.gx[pi]) % g.gy[pi], bz = local / (g.gx[pi] * g.gy[pi]);
+  gemm_tf32_body<BLOCK_N, EPI_WGRAD, SPLIT, false>(&g.tmA[pi], &g.tmB[pi], &g.tmB[pi], g.p[pi], bx, by, bz);
 }
 
 /* ---- host: tensor maps ---------------------------------------------------------------- */
@@ -426,6 +452,8 @@ void fc_tf32_init() {
   if (done) return;
   set_attr<16, false>(); set_attr<32, false>(); set_attr<64, false>(); set_attr<128, false>();
   set_attr<16, true>(); set_attr<32, true>(); set_attr<64, true>(); set_attr<128, true>();
+  PS_CUDA(cudaFuncSetAttribute(gemm_tf32_grouped_wgrad_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<64, true>::TOTAL));
+  PS_CUDA(cudaFuncSetAttribute(gemm_tf32_grouped_wgrad_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<64, false>::TOTAL));
   encode_fn();
   done = true;
 }
@@ -447,6 +475,39 @@ void fc_dgrad_tf32(Ctx* ctx, const FcDgradArgs& a) {
   p.act = a.act_below; p.Yt = a.Yt; p.ldyt = a.ldyt;
   PS_REQUIRE(p.act == PS_ACT_NONE || p.Yt != nullptr, PS_ERR_ARG, "tf32 dgrad needs the transposed activation of the layer below");
   dispatch_tc<EPI_DGRAD>(ctx, a.dl, a.ldd, a.Wt, a.ldwt, a.Wtlo, p, 1);
+}
+
+/* all layers whose [A | 1]^T is at most 64 x ... tiles wide share the 64-column instantiation; returns false when a layer does not fit
+ * the group (the caller then launches the layers one by one) */
+bool fc_wgrad_grouped_tf32(Ctx* ctx, const FcWgradArgs* a, int n) {
+  fc_tf32_init();
+  if (n < 2 || n > kMaxGroup) return false;
+  GroupedTc g{};
+  g.n = n;
+  int total = 0;
+  for (int i = 0; i < n; ++i) {
+    if (a[i].dlT == nullptr || a[i].AT == nullptr) return false;
+    TcParams& p = g.p[i];
+    p = TcParams{};
+    p.M = a[i].out; p.N = a[i].in + 1; p.K = a[i].B;
+    if (p.N < 64) return false;                  /* narrower layers use narrower tiles: launched one by one */
+    p.C = a[i].G; p.ldc = a[i].ldg; p.slab = a[i].slab; p.Ct = nullptr;
+    const int nkb = (p.K + BK - 1) / BK;
+    p.kb_per_split = (nkb + a[i].nsplit - 1) / a[i].nsplit;
+    g.tmA[i] = tensor_map(a[i].dlT, p.M, p.K, a[i].ldt, BM);
+    g.tmB[i] = tensor_map(a[i].AT, p.N, p.K, a[i].ldt, 64);
+    g.gx[i] = ceil_div(p.N, 64); g.gy[i] = ceil_div(p.M, BM);
+    g.first[i] = total;
+    total += g.gx[i] * g.gy[i] * a[i].nsplit;
+  }
+  g.first[n] = total;
+  if (ctx->fc_precision == PS_FC_TF32X3)
+    gemm_tf32_grouped_wgrad_kernel<64, true><<<total, 256, SmemLayout<64, true>::TOTAL, ctx->stream>>>(g);
+  else
+    gemm_tf32_grouped_wgrad_kernel<64, false><<<total, 128, SmemLayout<64, false>::TOTAL, ctx->stream>>>(g);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+  return true;
 }
 
 void fc_wgrad_tf32(Ctx* ctx, const FcWgradArgs& a) {

@@ -321,12 +321,41 @@ void Model::backward_layers(int N, bool wide_update_now) {
     StreamScope sc(ctx, s2);
     wide.update_all(gbar_ptr(st_dev), skip_ptr(st_dev), wide_bias, &upd_wide);
   }
+  const bool fp32 = ctx->fc_precision == PS_FC_FP32;
+  if (fp32 || !ctx->group_wgrad) {               /* each wgrad beside its layer's dgrad */
+    for (int l = L - 1; l >= 0; --l) {
+      fork(s, s1);                               /* delta[l+1] (tail or dgrad(l+1)) is ready */
+      if (l == 0) fork(s2, s1);                  /* act_t[0] */
+      dgrad_layer(l, N);                         /* captured first: the critical chain's node precedes its sibling */
+      { StreamScope sc(ctx, s1); wgrad_layer(l, N); }
+      mark(("fc_dgrad" + std::to_string(l)).c_str());
+    }
+    return;
+  }
+  /* tensor-core modes: the dgrad chain runs alone (a 128-CTA GEMM shares its SMs with nobody), then EVERY layer's weight gradient
+   * goes out as one grouped launch on side stream 1 — beside the embedding scatter / update that follows on the main stream */
   for (int l = L - 1; l >= 0; --l) {
-    fork(s, s1);                                 /* delta[l+1] (tail or dgrad(l+1)) is ready */
-    if (l == 0) fork(s2, s1);                    /* act_t[0] */
-    dgrad_layer(l, N);                           /* captured first: the critical chain's node precedes its sibling */
-    { StreamScope sc(ctx, s1); wgrad_layer(l, N); }
+    if (l == L - 1 && top_is_unit()) { fork(s, s1); StreamScope sc(ctx, s1); wgrad_layer(l, N); }   /* the 1-unit top layer's CUDA-core wgrad needs only the tail */
+    dgrad_layer(l, N);
     mark(("fc_dgrad" + std::to_string(l)).c_str());
+  }
+  fork(s, s1); fork(s2, s1);                     /* every delta; act_t[0] */
+  {
+    StreamScope sc(ctx, s1);
+    FcWgradArgs ga[kMaxDenseLayers];
+    int n = 0;
+    for (int l = L - 1; l >= 0; --l) {
+      if (l == L - 1 && top_is_unit()) continue;
+      const FcLayer& f = fcs[l];
+      FcWgradArgs& g = ga[n++];
+      g = FcWgradArgs{};
+      g.B = N; g.in = f.in; g.out = f.out;
+      g.dl = delta[l + 1]; g.ldd = ld[l + 1]; g.A = act[l]; g.lda = ld[l];
+      g.dlT = delta_t[l + 1]; g.AT = act_t[l]; g.ldt = ldt;
+      g.G = f.G; g.ldg = f.ldw; g.slab = (size_t)f.out * f.ldw; g.nsplit = f.nsplit;
+    }
+    if (!fc_wgrad_grouped_tf32(ctx, ga, n))
+      for (int i = 0; i < n; ++i) fc_wgrad_tf32(ctx, ga[i]);
   }
 }
 
