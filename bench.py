@@ -686,7 +686,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("PS_FC_PRECISION", "tf32x3"))
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--ring", type=int, default=64)
-    ap.add_argument("--slack", type=float, default=2.0)
+    ap.add_argument("--slack", type=float, default=1.25, help="per-owner bucket capacity = lookups / ranks * slack (de-duplicated keys need far less; uniform keys ~1.05)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
     ap.add_argument("--force-sharded", action="store_true", help="use the sharded step even with one rank (profiling)")
     ap.add_argument("--large", default="cfg4", help="shapes for the large-batch embedding roofline ('' = skip)")

@@ -72,7 +72,7 @@ int ps_ctx_create(int device, uint64_t seed, ps_ctx** out) {
   const char* ht = std::getenv("PS_HOT_TMA");
   c->c.hot_tma = (ht && ht[0] == '0') ? 0 : 1;
   const char* gw = std::getenv("PS_GROUP_WGRAD");
-  c->c.group_wgrad = (gw && gw[0] == '0') ? 0 : 1;
+  c->c.group_wgrad = (gw && gw[0] == '1') ? 1 : 0;
   const char* us = std::getenv("PS_UPDATE_SLAB");
   c->c.update_slab = (us && us[0] == '0') ? 0 : 1;
   const char* ss = std::getenv("PS_SCATTER_SLAB");

@@ -61,7 +61,8 @@ struct Ctx {
                                       unless PS_PDL_GEMM=1 */
   int exact_updaters = 0;          /* sparse update with the IEEE divisions / roots of the Java code (PS_EXACT_UPDATERS=1) instead of the fast forms */
   int hot_tma = 1;                 /* the lookup stages rows shared by >= 4 lookups of a warp task in shared memory by TMA bulk copies (PS_HOT_TMA=0: off) */
-  int group_wgrad = 1;             /* tensor-core modes: all weight-gradient GEMMs of a step in one grouped launch after the dgrad chain (PS_GROUP_WGRAD=0: each beside its dgrad) */
+  int group_wgrad = 0;             /* PS_GROUP_WGRAD=1: all weight-gradient GEMMs of a step in one grouped launch after the dgrad chain.  Measured
+                                      SLOWER at cfg2 (164.9 vs 158.9 us per step: the 272-CTA launch delays the embedding update it runs beside), so off */
   int update_slab = 1;             /* the sparse update moves records by TMA bulk copies through shared memory (PS_UPDATE_SLAB=0: the register-path kernel) */
   int scatter_slab = 1;            /* the backward scatter stages a task's delta rows in shared memory (PS_SCATTER_SLAB=0: the register-path kernel) */
   int hot_share = 4;               /* ... PS_HOT_SHARE: how many lookups of a task must share the row (1 = every row goes through TMA) */
