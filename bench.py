@@ -125,10 +125,15 @@ def nvlink_kib(index):
         h = pynvml.nvmlDeviceGetHandleByIndex(phys)
         out = []
         for fid in (pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX):
-            v = pynvml.nvmlDeviceGetFieldValues(h, [(fid, 0xFFFFFFFF)])[0]
-            if v.nvmlReturn != 0:
+            v = pynvml.nvmlDeviceGetFieldValues(h, [(fid, 0xFFFFFFFF)])[0]           # scope UINT_MAX = all links
+            if v.nvmlReturn == 0:
+                out.append(int(v.value.ullVal))
+                continue
+            per_link = pynvml.nvmlDeviceGetFieldValues(h, [(fid, l) for l in range(18)])   # NV18: sum the links
+            good = [int(x.value.ullVal) for x in per_link if x.nvmlReturn == 0]
+            if not good:
                 return None
-            out.append(int(v.value.ullVal))
+            out.append(sum(good))
         return tuple(out)
     except Exception:
         return None
