@@ -175,7 +175,8 @@ int ps_model_collect(ps_model* m, float* loss);
  *                             activation.backward, LRLayer.backward, EmbeddingLayer.backward x2) and then KVStore.update + clear
  *                             (Trainer.java:93,95).  `loss` = the caller's loss.forward value, recorded as the step's loss; the early
  *                             exit of DNN.java:58-63 is the caller's to take (it simply does not call this; the next forward forgets
- *                             the pending batch).  DNN and WideDeepNN only.                                                    */
+ *                             the pending batch).  FullConnectedNN (Softmax + SoftmaxLoss, FullConnectedNN.java:37-70): P_out and
+ *                             delta_top are C x N (N rows of C floats); Softmax.backward (Softmax.java:45-67) runs in the library.   */
 int ps_model_forward(ps_model* m, const int64_t* E, const float* X, const int64_t* W, int N, float* P_out);
 int ps_model_backward_update(ps_model* m, const float* delta_top, int N, float loss);
 /* DataSet.next + Trainer.train in one submission (DataSet.java:77-100, CTR.parseFeature CTR.java:47-68, CTR.wideSize CTR.java:36):

@@ -71,6 +71,8 @@ int ps_ctx_create(int device, uint64_t seed, ps_ctx** out) {
   c->c.exact_updaters = (xe && xe[0] == '1') ? 1 : 0;
   const char* ht = std::getenv("PS_HOT_TMA");
   c->c.hot_tma = (ht && ht[0] == '0') ? 0 : 1;
+  const char* gn = std::getenv("PS_GEMM_NARROW");
+  c->c.gemm_narrow = (gn && gn[0] == '1') ? 1 : 0;
   const char* gw = std::getenv("PS_GROUP_WGRAD");
   c->c.group_wgrad = (gw && gw[0] == '1') ? 1 : 0;
   const char* us = std::getenv("PS_UPDATE_SLAB");

@@ -61,6 +61,7 @@ struct Ctx {
                                       unless PS_PDL_GEMM=1 */
   int exact_updaters = 0;          /* sparse update with the IEEE divisions / roots of the Java code (PS_EXACT_UPDATERS=1) instead of the fast forms */
   int hot_tma = 1;                 /* the lookup stages rows shared by >= 4 lookups of a warp task in shared memory by TMA bulk copies (PS_HOT_TMA=0: off) */
+  int gemm_narrow = 0;             /* PS_GEMM_NARROW=1: 32-column 3xTF32 tiles when 64-column ones leave half the CTA slots empty */
   int group_wgrad = 0;             /* PS_GROUP_WGRAD=1: all weight-gradient GEMMs of a step in one grouped launch after the dgrad chain.  Measured
                                       SLOWER at cfg2 (164.9 vs 158.9 us per step: the 272-CTA launch delays the embedding update it runs beside), so off */
   int update_slab = 1;             /* the sparse update moves records by TMA bulk copies through shared memory (PS_UPDATE_SLAB=0: the register-path kernel) */

@@ -391,6 +391,36 @@ void tail_binary_from_delta(Ctx* ctx, int N, const float* p, int ldp, const floa
   ctx->launches++;
 }
 
+/* FullConnectedNN with the loss in the caller: delta_top[N][C] = SoftmaxLoss.backward(P, Y) (or any dy) -> Softmax.backward
+ * (Softmax.java:45-67) operation by operation, including its `delta[k] *= d` INSIDE the class loop (for a one-hot dy — what
+ * SoftmaxLoss produces — this is the usual Jacobian product; for several non-zero entries the reference's own arithmetic is kept) */
+__global__ void __launch_bounds__(kTailThreads) tail_softmax_from_delta_kernel(int N, int C, const float* __restrict__ P, int ldp, const float* __restrict__ dtop,
+                                                                               float* __restrict__ d_out, int ldd, float* __restrict__ dt_out, int ldt, float loss,
+                                                                               StepStatus* __restrict__ st, float* __restrict__ ws) {
+  __shared__ float sh[kTailThreads];
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+    const float* y = P + (size_t)n * ldp;
+    float* d = d_out + (size_t)n * ldd;
+    for (int k = 0; k < C; ++k) d[k] = 0.0f;
+    for (int j = 0; j < C; ++j) {
+      const float dj = dtop[(size_t)n * C + j];
+      if (dj == 0.0f) continue;
+      for (int k = 0; k < C; ++k) {
+        const float t = (j == k) ? __fmul_rn(y[k], __fsub_rn(1.0f, y[k])) : __fmul_rn(-y[j], y[k]);
+        d[k] = __fmul_rn(__fadd_rn(d[k], t), dj);
+      }
+    }
+    if (dt_out) for (int k = 0; k < C; ++k) dt_out[(size_t)k * ldt + n] = d[k];
+  }
+  tail_finish(0.0f, 0.0f, N, ws, st, sh, nullptr, true, loss);
+}
+void tail_softmax_from_delta(Ctx* ctx, int N, int C, const float* P, int ldp, const float* dtop, float* d_out, int ldd, float* dt_out, int ldt, float loss,
+                             StepStatus* st, float* ws) {
+  tail_softmax_from_delta_kernel<<<tail_blocks(N), kTailThreads, 0, ctx->stream>>>(N, C, P, ldp, dtop, d_out, ldd, dt_out, ldt, loss, st, ws);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+}
+
 void tail_softmax(Ctx* ctx, int N, int C, float* Z, int ldz, const float* Y, float* d_out, int ldd, float* dt_out, int ldt, int train,
                   StepStatus* st, float* ws) {
   tail_softmax_kernel<<<tail_blocks(N), kTailThreads, 0, ctx->stream>>>(N, C, Z, ldz, Y, d_out, ldd, dt_out, ldt, train, st, ws, nullptr);

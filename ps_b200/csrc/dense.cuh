@@ -61,6 +61,8 @@ void tail_binary(Ctx* ctx, int N, const float* zdeep, int ldz, const float* zwid
 /* the reverse loop's first step when the caller computed the loss itself: d = delta_top * p * (1 - p), gbar, skip; `loss` is recorded as given */
 void tail_binary_from_delta(Ctx* ctx, int N, const float* p, int ldp, const float* dtop, float* d_out, int ldd, float* dt_out, float loss,
                             StepStatus* st, float* ws, const uint32_t* emb_counters);
+void tail_softmax_from_delta(Ctx* ctx, int N, int C, const float* P, int ldp, const float* dtop, float* d_out, int ldd, float* dt_out, int ldt, float loss,
+                             StepStatus* st, float* ws);
 /* multi-class tail (FullConnectedNN): Softmax(10000) in place on Z, SoftmaxLoss, Softmax.backward */
 void tail_softmax(Ctx* ctx, int N, int C, float* Z, int ldz, const float* Y, float* d_out, int ldd, float* dt_out, int ldt, int train,
                   StepStatus* st, float* ws);

@@ -427,7 +427,10 @@ void dispatch_tc(Ctx* ctx, const float* A, long lda, const float* B, long ldb, c
    * at 64 columns, 4 x 32 = 128 at 128 — and every A tile is read (and split) half as often */
   const int ctas_per_sm = ctx->fc_precision == PS_FC_TF32X3 ? 2 : 1;
   const bool wide = p.N >= 128 && (long)ceil_div(p.N, 64) * ceil_div(p.M, BM) * nsplit > (long)ctas_per_sm * ctx->num_sms;
+  /* 64-column tiles that leave the second CTA slot of every SM empty (a 128-CTA grid): 32-column tiles fill it */
+  const bool narrow = ctx->gemm_narrow && ctas_per_sm == 2 && p.N > 32 && (long)ceil_div(p.N, 64) * ceil_div(p.M, BM) * nsplit <= ctx->num_sms;
   if (wide) launch_tc_mode<128, EPI>(ctx, A, lda, B, ldb, Blo, p, nsplit);
+  else if (narrow) launch_tc_mode<32, EPI>(ctx, A, lda, B, ldb, Blo, p, nsplit);
   else if (p.N <= 16) launch_tc_mode<16, EPI>(ctx, A, lda, B, ldb, Blo, p, nsplit);
   else if (p.N <= 32) launch_tc_mode<32, EPI>(ctx, A, lda, B, ldb, Blo, p, nsplit);
   else launch_tc_mode<64, EPI>(ctx, A, lda, B, ldb, Blo, p, nsplit);

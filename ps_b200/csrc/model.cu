@@ -129,7 +129,7 @@ void Model::destroy() {
   for (auto p : delta_t) dfree(p);
   if (has_emb) emb.destroy();
   if (has_wide) { wide.destroy(); dfree(wide_bias); dfree(wide_z); dfree(P); }
-  dfree(st_dev); dfree(tail_ws); dfree(gsum); dfree(send_pos);
+  dfree(st_dev); dfree(tail_ws); dfree(gsum); dfree(send_pos); dfree(dtop_stage); dtop_stage = nullptr;
   if (p2p.slab) p2p.destroy();
   for (auto& g : graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
   graphs.clear();
@@ -666,7 +666,6 @@ float Model::read_loss() {
  * Java's loss.backward produced — dLoss/dP, BEFORE the output activation's derivative, exactly what setDelta receives — and runs
  * the reverse loop and the update.  No label ever crosses the boundary.                                                    */
 void Model::forward_host(const HostBatch& b, float* P_out) {
-  PS_REQUIRE(kind != PS_MODEL_FCNN, PS_ERR_ARG, "forward/backward split: DNN and WideDeepNN only (FullConnectedNN: use train_step)");
   PS_REQUIRE(in_flight == 0, PS_ERR_STATE, "model: steps in flight; collect first");
   PS_REQUIRE(b.N > 0 && b.N <= Bmax, PS_ERR_ARG, "model: batch size must be in [1, max_batch]");
   PS_REQUIRE(b.X && P_out && (!has_emb || b.E) && (!has_wide || b.W), PS_ERR_ARG, "model: missing input matrix");
@@ -678,10 +677,13 @@ void Model::forward_host(const HostBatch& b, float* P_out) {
   PS_CUDA(cudaMemcpyAsync(S.X, b.X, sizeof(float) * N * Xn, cudaMemcpyHostToDevice, s));
   fork(s, s1);
   if (has_wide) { StreamScope sc(ctx, s1); wide.forward(S.W, b.N, F, wide_bias, wide_z); }
-  emb.lookup(S.E, nullptr, b.N, act[0], ld[0], S.X, Xn, F * D);
+  if (has_emb) emb.lookup(S.E, nullptr, b.N, act[0], ld[0], S.X, Xn, F * D);
+  else PS_CUDA(cudaMemcpy2DAsync(act[0], sizeof(float) * ld[0], S.X, sizeof(float) * Xn, sizeof(float) * Xn, N, cudaMemcpyDeviceToDevice, s));
   forward_layers(b.N, true);
-  run_tail(nullptr, b.N, false);                 /* AddLayer + Sigmoid only: P */
-  if (has_wide) PS_CUDA(cudaMemcpyAsync(P_out, P, sizeof(float) * N, cudaMemcpyDeviceToHost, s));
+  run_tail(nullptr, b.N, false);                 /* AddLayer + Sigmoid (or Softmax) only: P */
+  if (kind == PS_MODEL_FCNN)                     /* FullConnectedNN: P is C x N (FullConnectedNN.java:47) */
+    PS_CUDA(cudaMemcpy2DAsync(P_out, sizeof(float) * width[L], act[L], sizeof(float) * ld[L], sizeof(float) * width[L], N, cudaMemcpyDeviceToHost, s));
+  else if (has_wide) PS_CUDA(cudaMemcpyAsync(P_out, P, sizeof(float) * N, cudaMemcpyDeviceToHost, s));
   else PS_CUDA(cudaMemcpy2DAsync(P_out, sizeof(float), act[L], sizeof(float) * ld[L], sizeof(float), N, cudaMemcpyDeviceToHost, s));
   fork(s2, s);
   PS_CUDA(cudaStreamSynchronize(s));
@@ -695,10 +697,18 @@ void Model::backward_update_host(const float* delta_top, int N, float loss) {
   Stage& S = stage[0];
   cudaStream_t s = ctx->stream, s1 = aux[0], s2 = aux[1];
   const bool fp32 = ctx->fc_precision == PS_FC_FP32;
-  PS_CUDA(cudaMemcpyAsync(S.Y, delta_top, sizeof(float) * (size_t)N, cudaMemcpyHostToDevice, s));   /* the label buffer doubles as the delta staging */
-  /* last layer's activation.backward (FcLayer.java:100-102 with Sigmoid.java:16-21) + rowMeans for LRLayer; loss as Java computed it */
-  tail_binary_from_delta(ctx, N, has_wide ? P : act[L], has_wide ? 1 : ld[L], S.Y, delta[L], ld[L], fp32 ? nullptr : delta_t[L], loss, st_dev, tail_ws,
-                         has_emb ? emb.counters : nullptr);
+  if (kind == PS_MODEL_FCNN) {
+    /* delta_top is C x N: staged in delta[L]'s transposed twin's neighbour — the (unused) top delta_t buffer is [C][ldt], large enough */
+    const int Cn = width[L];
+    if (!dtop_stage) dtop_stage = dmalloc<float>((size_t)Bmax * Cn);
+    PS_CUDA(cudaMemcpyAsync(dtop_stage, delta_top, sizeof(float) * (size_t)N * Cn, cudaMemcpyHostToDevice, s));
+    tail_softmax_from_delta(ctx, N, Cn, act[L], ld[L], dtop_stage, delta[L], ld[L], fp32 ? nullptr : delta_t[L], ldt, loss, st_dev, tail_ws);
+  } else {
+    PS_CUDA(cudaMemcpyAsync(S.Y, delta_top, sizeof(float) * (size_t)N, cudaMemcpyHostToDevice, s));   /* the label buffer doubles as the delta staging */
+    /* last layer's activation.backward (FcLayer.java:100-102 with Sigmoid.java:16-21) + rowMeans for LRLayer; loss as Java computed it */
+    tail_binary_from_delta(ctx, N, has_wide ? P : act[L], has_wide ? 1 : ld[L], S.Y, delta[L], ld[L], fp32 ? nullptr : delta_t[L], loss, st_dev, tail_ws,
+                           has_emb ? emb.counters : nullptr);
+  }
   backward_layers(N, true);
   fork(s, s1);
   {

@@ -110,6 +110,7 @@ struct Model {
   void backward_layers(int N, bool wide_update_now);
   /* DNN.train call by call: forward loop | (loss in the caller) | reverse loop + KVStore.update (see model.cu) */
   int pending_forward_N = 0;
+  float* dtop_stage = nullptr;         /* FullConnectedNN: the caller's C x N delta on the device */
   bool pad_dirty = false;
   void forward_host(const HostBatch& b, float* P_out);
   void backward_update_host(const float* delta_top, int N, float loss);

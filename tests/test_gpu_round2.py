@@ -263,3 +263,29 @@ def test_out_of_domain_id_refuses_the_batch(ps, ctx):
     assert e.value.code == 400
     assert np.array_equal(m.get("fc0.weights"), w0)
     m.close()
+
+
+def test_fcnn_forward_backward_split_matches_oracle(ps, ctx):
+    """FullConnectedNN.train call by call (FullConnectedNN.java:37-70): forward loop -> SoftmaxLoss in the caller
+    (loss/SoftmaxLoss.java:9-28) -> Softmax.backward + reverse loop + KVStore.update in the library."""
+    Xn, fc, N, Cn = 784, [150, 50, 10], 96, 10
+    m = ps.Model(ctx, "fcnn", 0, 0, Xn, fc, max_batch=N)
+    o = ol.OracleModel(ol.KIND_FCNN, 0, 0, Xn, fc, SEED)
+    syn = Synth(F=0, Xn=Xn, V=0, seed=23, n_classes=Cn)
+    for it in range(3):
+        b = syn.batch(N)
+        P = np.zeros((N, Cn), np.float32)
+        X = np.ascontiguousarray(b["X"], np.float32)
+        ps.check(ps.lib().ps_model_forward(m.h, None, X.ctypes.data_as(C.c_void_p), None, N, P.ctypes.data_as(C.c_void_p)))
+        hot = b["Y"].astype(np.int64)
+        ph = P[np.arange(N), hot]
+        loss = float(np.float32(np.sum(-np.log(ph.astype(np.float64)).astype(np.float32), dtype=np.float32) / np.float32(N)))
+        delta = np.zeros((N, Cn), np.float32)
+        delta[np.arange(N), hot] = np.float32(-1.0) / ph
+        ps.check(ps.lib().ps_model_backward_update(m.h, delta.ctypes.data_as(C.c_void_p), N, loss))
+        lo = o.train_step(None, b["X"], None, b["Y"])
+        assert abs(loss - lo) <= 5e-5 * max(1.0, abs(lo)), (it, loss, lo)
+    for l in range(3):
+        assert rel_err(m.get(f"fc{l}.weights"), o.get(f"fc{l}.weights")) <= 2e-4, l
+        assert rel_err(m.get(f"fc{l}.bias"), o.get(f"fc{l}.bias")) <= 2e-4, l
+    m.close()
