@@ -746,8 +746,11 @@ def main():
             tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
             if os.path.exists(tp) and args.config == "cfg2":
                 tk = json.load(open(tp)).get("kernels", {})
-                parts = {"emb_lookup": ["emb_lookup_kernel"], "emb_scatter_update": ["emb_scatter_kernel", "emb_update_kernel"]}[dom]
-                traffic = sum(tk[p]["dram_bytes_per_launch"] for p in parts) if all(p in tk for p in parts) else None
+                # the scatter and the update each have a shared-memory slab variant (the default) and a register variant
+                alts = {"emb_lookup": [["emb_lookup_kernel"]],
+                        "emb_scatter_update": [["emb_scatter_slab_kernel", "emb_scatter_kernel"], ["emb_update_slab_kernel", "emb_update_kernel"]]}[dom]
+                picked = [next((p for p in names if p in tk), None) for names in alts]
+                traffic = sum(tk[p]["dram_bytes_per_launch"] for p in picked) if all(picked) else None
             roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
                         "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
                         "how": "algorithmic bytes (SURVEY 8d) / mean device time of the kernel(s) replayed 64x in a CUDA graph over the batch ring "

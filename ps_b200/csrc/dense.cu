@@ -171,13 +171,7 @@ void dense_reduce(Ctx* ctx, const DenseUpdateArgs& a, const StepStatus* st, floa
 __global__ void __launch_bounds__(256) dense_reduce_send_kernel(const __grid_constant__ DenseUpdateArgs a, const StepStatus* __restrict__ st,
                                                                 P2PState* __restrict__ p2p, const uint32_t* __restrict__ emb_counters) {
   const int R = p2p->R, me = p2p->me, glen = p2p->glen;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    for (int r = 0; r < R; ++r) {
-      float* dst = reinterpret_cast<float*>(p2p_region(p2p, r, p2p->off_gsum)) + (size_t)me * glen;
-      dst[a.total] = st->loss; dst[a.total + 1] = st->gbar;
-      dst[a.total + 2] = (emb_counters != nullptr && emb_counters[1] != 0u) ? 1.0f : 0.0f;
-    }
-  }
+  /* (the scalars [loss, gbar, table-full] at the tail of the vector travelled earlier, right after the tail kernel: scalars_send) */
   /* a capped grid striding over the parameters: the publish below costs one system fence + one ticket per block */
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < a.total; idx += (long)gridDim.x * blockDim.x) {
     int li = 0;
@@ -198,9 +192,27 @@ void dense_reduce_send(Ctx* ctx, const DenseUpdateArgs& a, const StepStatus* st,
   ctx->launches++;
 }
 
+/* Right after the tail kernel: this rank's [loss, gbar, table-full] into the tail of its slot of every replica's gsum_in mailbox, on a
+ * channel of its own — the global early-exit flag (and LRLayer's gbar) is known long before the weight gradients are, so the owner-side
+ * embedding update does not wait for the dense gradient exchange */
+__global__ void scalars_send_kernel(const StepStatus* __restrict__ st, P2PState* __restrict__ p2p, long total, const uint32_t* __restrict__ emb_counters) {
+  const int r = threadIdx.x;
+  if (r < p2p->R) {
+    float* dst = reinterpret_cast<float*>(p2p_region(p2p, r, p2p->off_gsum)) + (size_t)p2p->me * p2p->glen;
+    dst[total] = st->loss; dst[total + 1] = st->gbar;
+    dst[total + 2] = (emb_counters != nullptr && emb_counters[1] != 0u) ? 1.0f : 0.0f;
+  }
+  p2p_publish_last(p2p, CH_SCAL, 1);
+}
+void scalars_send(Ctx* ctx, const StepStatus* st, P2PState* p2p, long total, const uint32_t* emb_counters) {
+  scalars_send_kernel<<<1, 32, 0, ctx->stream>>>(st, p2p, total, emb_counters);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+}
+
 /* global loss / gbar / early-exit flag from the R ranks' [loss, gbar] in the gsum_in mailbox (rank order) */
 __global__ void shard_finish_scalars_p2p_kernel(StepStatus* st, const P2PState* p2p, long total) {
-  p2p_wait_all(p2p, CH_GSUM);                    /* every replica's sums and scalars have landed */
+  p2p_wait_all(p2p, CH_SCAL);                    /* every replica's scalars have landed */
   if (threadIdx.x != 0) return;
   const float* in = reinterpret_cast<const float*>(p2p_region(p2p, p2p->me, p2p->off_gsum));
   float l = 0.f, g = 0.f, full = 0.f;

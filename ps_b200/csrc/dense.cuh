@@ -52,6 +52,7 @@ void dense_update(Ctx* ctx, const DenseUpdateArgs& a, StepStatus* st, const uint
 /* peer-memory forms of dense_reduce / shard_finish_scalars (p2p.cuh): sums stored straight into every rank's mailbox */
 void dense_reduce_send(Ctx* ctx, const DenseUpdateArgs& a, const StepStatus* st, P2PState* p2p, const uint32_t* emb_counters = nullptr);   /* publishes CH_GSUM */
 void shard_finish_scalars_p2p(Ctx* ctx, StepStatus* st, const P2PState* p2p, long total);
+void scalars_send(Ctx* ctx, const StepStatus* st, P2PState* p2p, long total, const uint32_t* emb_counters);   /* publishes CH_SCAL */
 constexpr int kTailWorkspaceFloats = 2 * 1024 + 4;
 
 /* binary tail: z = deep (+ wide); p = clipped sigmoid; CrossEntropy forward/backward; sigmoid

@@ -295,6 +295,15 @@ void Model::forward_backward(const int64_t* W, const int64_t* W_all, int n_all, 
   forward_layers(N, train);
   run_tail(Y, N, train);
   mark("tail");
+  if (train && p2p_scalars_now) {                /* sharded step over peer memory: the global loss / gbar / early-exit flag, exchanged NOW on side stream 2 */
+    cudaStream_t s = ctx->stream, s2 = aux[1];
+    fork(s, s2);
+    StreamScope sc(ctx, s2);
+    const DenseUpdateArgs u = dense_args(N * p2p.R);
+    scalars_send(ctx, st_dev, p2p.dev, u.total, has_emb ? emb.counters : nullptr);
+    shard_finish_scalars_p2p(ctx, st_dev, p2p.state(), u.total);
+    if (has_wide) wide.update_all(gbar_ptr(st_dev), skip_ptr(st_dev), wide_bias, &upd_wide);   /* LRLayer.backward needs only the global gbar */
+  }
   if (train) backward_layers(N, wide_update_now);
 }
 
@@ -503,30 +512,28 @@ void Model::p2p_step(const int64_t* E, const float* X, const int64_t* W, const f
   } else {
     PS_CUDA(cudaMemcpy2DAsync(act[0], sizeof(float) * ld[0], X, sizeof(float) * Xn, sizeof(float) * Xn, N, cudaMemcpyDeviceToDevice, s));
   }
-  forward_backward(W, nullptr, 0, Y, N, true, false);                           /* main: delta[0]; side 1: the wgrads */
-  /* side stream 1: PServer sync mode — every rank's dense gradient sums + [loss, gbar] into every mailbox, then the
-   * global scalars, the wide update and the dense update, all beside the row-gradient push on the main stream      */
-  fork(s2, s1);
+  p2p_scalars_now = true;
+  try { forward_backward(W, nullptr, 0, Y, N, true, false); }                   /* main: delta[0]; side 1: the wgrads; side 2: the global scalars + wide update */
+  catch (...) { p2p_scalars_now = false; throw; }
+  p2p_scalars_now = false;
+  /* side stream 1, behind the weight gradients: PServer sync mode for the dense keys — every rank's gradient sums into every mailbox,
+   * then the dense update (which waits for the replicas' flags itself), all beside the row-gradient push on the main stream        */
+  fork(s2, s1);                                                                 /* the global skip flag */
+  fork(s, s1);                                                                  /* every dgrad has read W / Wt: the dense update may overwrite them */
   {
     StreamScope sc(ctx, s1);
     const DenseUpdateArgs u = dense_args(N * R);
     dense_reduce_send(ctx, u, st_dev, p2p.dev, has_emb ? emb.counters : nullptr);
-    shard_finish_scalars_p2p(ctx, st_dev, p2p.state(), u.total);
+    p2p.wait(CH_GSUM);                                                          /* every replica's sums have landed */
+    dense_update(ctx, u, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, nullptr, p2p.state());
   }
   if (has_emb) {
     emb.scatter_rows(p2p.bt, p2p.lk_b, p2p.gacc, delta[0], ld[0], D % 4 == 0 ? nullptr : act[0], ld[0], N);   /* client.push: one gradient sum per unique key of this rank's batch */
     p2p.grad_send();                                                            /* ... with its occurrence count, to the owner */
   }
-  fork(s1, s);                                                                  /* the global skip flag */
-  fork(s, s2);
-  {
-    StreamScope sc(ctx, s2);                                                    /* psUpdate for dense + wide keys beside the embedding update */
-    const DenseUpdateArgs u = dense_args(N * R);
-    if (has_wide) wide.update_all(gbar_ptr(st_dev), skip_ptr(st_dev), wide_bias, &upd_wide);
-    dense_update(ctx, u, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, nullptr, p2p.state());
-  }
+  fork(s2, s);                                                                  /* the global skip flag (exchanged right after the tail) — NOT the weight gradients */
   if (has_emb) emb.scatter_update_entries(p2p.state(), R * cap, 2, skip_ptr(st_dev));   /* PServer.push (sync mode) + psUpdate on the owner */
-  fork(s2, s);
+  fork(s1, s);                                                                  /* the dense update */
   last_N = N; last_train = true;
 }
 

@@ -109,6 +109,7 @@ struct Model {
   void forward_layers(int N, bool train);
   void backward_layers(int N, bool wide_update_now);
   /* DNN.train call by call: forward loop | (loss in the caller) | reverse loop + KVStore.update (see model.cu) */
+  bool p2p_scalars_now = false;        /* forward_backward exchanges the global scalars right after the tail (set by p2p_step) */
   int pending_forward_N = 0;
   float* dtop_stage = nullptr;         /* FullConnectedNN: the caller's C x N delta on the device */
   bool pad_dirty = false;

@@ -225,6 +225,11 @@ void P2P::destroy() {
 
 #define P2P_LAUNCHED() do { PS_LAUNCH_CHECK(); ctx->launches++; } while (0)
 
+/* a one-warp wait on side streams whose consumer kernel has a large grid: 900 spinning blocks would hold every SM's thread slots
+ * against the main stream's kernels, one warp holds none */
+__global__ void p2p_wait_kernel(const P2PState* st, int channel) { p2p_wait_all(st, channel); }
+void P2P::wait(int channel) { p2p_wait_kernel<<<1, 32, 0, ctx->stream>>>(dev, channel); P2P_LAUNCHED(); }
+
 void P2P::begin() { p2p_begin_kernel<<<1, 32, 0, ctx->stream>>>(dev); P2P_LAUNCHED(); }
 
 void P2P::route_send(const int64_t* E, int N, int F) {

@@ -29,7 +29,7 @@
 namespace psb {
 
 constexpr int kP2PMaxRanks = 8;
-enum { CH_KEYS = 0, CH_ROWS = 1, CH_GRADS = 2, CH_WIDE = 3, CH_GSUM = 4, CH_COUNT = 5 };
+enum { CH_KEYS = 0, CH_ROWS = 1, CH_GRADS = 2, CH_WIDE = 3, CH_GSUM = 4, CH_SCAL = 5, CH_COUNT = 6 };
 
 struct P2PState {                      /* lives in device memory; kernels read it, p2p_begin advances seq */
   int R, me, cap, Dp, NF, glen;
@@ -69,6 +69,7 @@ struct P2P {
   BatchSlot* bt = nullptr; uint32_t BT = 0; int32_t* lk_b = nullptr; float* gacc = nullptr; int64_t Lmax = 0;
   int32_t* ulist = nullptr;                                                         /* bucket position -> batch slot (its count travels with the push; the push clears it) */
   void route_send(const int64_t* E, int N, int F);                                  /* de-duplicate, reserve, store each key into its owner's keys_in; publishes CH_KEYS */
+  void wait(int channel);                                                           /* one-warp consumer-side wait (before a large-grid consumer on a side stream) */
   void bcast(const void* src, size_t bytes, int channel);                           /* wide ids → every peer; publishes the channel */
   void unpack(int N, int F, int D, float* out, int ldo, const float* X, int Xn, int xoff);   /* rows_in (+ X) → concat buffer */
   void reduce_gsum(float* gsum);                                                    /* sum over ranks, fixed order */
