@@ -115,8 +115,13 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows), "how": self.how}
 
 
+NVLINK_WHY = []                      # why the NVLink counters could not be read (reported in the JSON line instead of a silent null)
+
+
 def nvlink_kib(index):
-    """Cumulative NVLink payload KiB (tx, rx) of one GPU over all its links (NVML field counters); None when NVML cannot say."""
+    """Cumulative NVLink payload KiB (tx, rx) of one GPU over all its links; None when neither NVML nor nvidia-smi can say (the reason
+    goes to NVLINK_WHY).  Tries the NVML field counters (all-links scope, then per link), then `nvidia-smi nvlink -gt d`."""
+    why = []
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -132,11 +137,27 @@ def nvlink_kib(index):
             per_link = pynvml.nvmlDeviceGetFieldValues(h, [(fid, l) for l in range(18)])   # NV18: sum the links
             good = [int(x.value.ullVal) for x in per_link if x.nvmlReturn == 0]
             if not good:
-                return None
+                why.append("NVML field %d: nvmlReturn %d (all links), %s (per link)" % (fid, v.nvmlReturn, sorted({int(x.nvmlReturn) for x in per_link})))
+                out = None
+                break
             out.append(sum(good))
-        return tuple(out)
-    except Exception:
-        return None
+        if out is not None:
+            return tuple(out)
+    except Exception as e:
+        why.append("NVML: %s: %s" % (type(e).__name__, e))
+    try:
+        import re
+        import subprocess
+        txt = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True, timeout=20).stdout
+        tx = [int(m) for m in re.findall(r"Data Tx:\s*(\d+)\s*KiB", txt)]
+        rx = [int(m) for m in re.findall(r"Data Rx:\s*(\d+)\s*KiB", txt)]
+        if tx and rx:
+            return (sum(tx), sum(rx))
+        why.append("nvidia-smi nvlink -gt d: no counters in %r" % txt.strip()[:160])
+    except Exception as e:
+        why.append("nvidia-smi nvlink: %s: %s" % (type(e).__name__, e))
+    NVLINK_WHY[:] = why
+    return None
 
 
 # ----------------------------------------------------------------------------------------------- CPU oracle legs
@@ -727,7 +748,8 @@ def main():
 
     # ---- per-kernel device times and rooflines (one GPU, local step) ----
     kernels, roofline, roofline_tensor, large, tf32_peak, phase_us, cfg5 = {}, None, None, None, None, {}, None
-    if side and world == 1 and wl.trainer is None:
+    if side and (wl.trainer is None or args.exchange == "p2p"):
+        # events between the kernels of the MAIN stream (the step's critical path); at N > 1 every rank steps, rank 0's times are reported
         acc = {}
         wl.model.profile(True)
         for i in range(20):
@@ -737,6 +759,7 @@ def main():
                 acc.setdefault(k, []).append(t)
         wl.model.profile(False)
         phase_us = {k: 1e3 * float(np.median(t)) for k, t in acc.items()}
+    if side and world == 1 and wl.trainer is None:
         tf32_peak = tf32_ceiling(env)
         mma_per = {"fp32": 0, "tf32": 1, "tf32x3": 3}[args.precision]
         if F:
@@ -782,6 +805,8 @@ def main():
 
     uniq, ring_unique = wl.unique_stats()
     nvlink = getattr(wl, "nvlink", None)
+    if nvlink is None and env.world > 1:
+        nvlink = {"unavailable": "; ".join(NVLINK_WHY) or "counters did not move"}
     if nvlink is not None and F:
         Dp_ = (D + 3) // 4 * 4
         remote = uniq * (world - 1) / world          # unique keys of a batch owned by another rank

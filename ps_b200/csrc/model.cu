@@ -493,7 +493,15 @@ void Model::p2p_step(const int64_t* E, const float* X, const int64_t* W, const f
   PS_REQUIRE(N > 0 && N <= Bmax, PS_ERR_ARG, "model: batch size must be in [1, max_batch]");
   cudaStream_t s = ctx->stream, s1 = aux[0], s2 = aux[1];
   const int R = p2p.R, cap = p2p.cap;
-  p2p.begin();
+  mark("begin");
+  /* every exchange below is ONE producer kernel that flags its consumers when its last block ends and ONE consumer kernel
+   * that waits for the flags in its prologue: no flag kernels, no send kernels on the way back, no host */
+  if (has_emb) {
+    p2p.route_send(E, N, F);                                                    /* PSRouterClient.getList: the step's sequence number; each key of the batch once, stored into its owner's mailbox */
+    mark("route_send");
+  } else {
+    p2p.begin();
+  }
   fork(s, s1);
   if (has_wide) {                                                               /* wide branch beside the embedding exchange */
     PS_REQUIRE(((size_t)N * F * 8) % 16 == 0, PS_ERR_ARG, "p2p: N*F must be even");
@@ -503,12 +511,13 @@ void Model::p2p_step(const int64_t* E, const float* X, const int64_t* W, const f
     wide.forward(W, N, F, wide_bias, wide_z);
   }
   if (has_emb) {
-    /* every exchange below is ONE producer kernel that flags its consumers when its last block ends and ONE consumer kernel
-     * that waits for the flags in its prologue: no flag kernels, no host */
-    p2p.route_send(E, N, F);                                                    /* PSRouterClient.getList: each key of the batch once, stored into its owner's mailbox */
+    fork(s, s2);
+    { StreamScope sc(ctx, s2); p2p.counts(); }                                  /* the keys' occurrence counts next to where their gradient sums will be */
     emb.lookup_packed(nullptr, R * cap, nullptr, p2p.dev, true);                /* PServer.getList on the owner: find-or-insert, rows stored straight into the requesters' mailboxes */
+    mark("owner_lookup");
     if (D % 4 == 0) emb.gather_resolved(p2p.bt, p2p.lk_b, p2p.dev, N, act[0], ld[0], X, Xn, F * D);   /* rows_in -> concat buffer (+ mask bits, ConcatLayer) */
     else p2p.unpack(N, F, D, act[0], ld[0], X, Xn, F * D);
+    mark("gather");
   } else {
     PS_CUDA(cudaMemcpy2DAsync(act[0], sizeof(float) * ld[0], X, sizeof(float) * Xn, sizeof(float) * Xn, N, cudaMemcpyDeviceToDevice, s));
   }
@@ -527,13 +536,19 @@ void Model::p2p_step(const int64_t* E, const float* X, const int64_t* W, const f
     p2p.wait(CH_GSUM);                                                          /* every replica's sums have landed */
     dense_update(ctx, u, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, nullptr, p2p.state());
   }
+  /* s2 carries, in order: the counts, the global scalars + wide update (forward_backward) */
+  fork(s2, s);                                                                  /* the counts are in place; the global skip flag — NOT the weight gradients */
   if (has_emb) {
-    emb.scatter_rows(p2p.bt, p2p.lk_b, p2p.gacc, delta[0], ld[0], D % 4 == 0 ? nullptr : act[0], ld[0], N);   /* client.push: one gradient sum per unique key of this rank's batch */
-    p2p.grad_send();                                                            /* ... with its occurrence count, to the owner */
+    emb.scatter_rows(p2p.bt, p2p.lk_b, p2p.dev, delta[0], ld[0], D % 4 == 0 ? nullptr : act[0], ld[0], N);   /* client.push: one gradient sum per unique key of this rank's batch, left in this rank's slab; flags the owners */
+    mark("scatter_rows");
+    fork(s, s2);
+    { StreamScope sc(ctx, s2); p2p.tidy(); }                                    /* beside the update: forget the batch's de-duplication, zero the other parity's sums */
+    emb.update_pull(p2p.state(), R * cap, 2, skip_ptr(st_dev));                 /* PServer.push (sync mode) + psUpdate on the owner: reads the requesters' sums over NVLink */
+    mark("owner_update");
   }
-  fork(s2, s);                                                                  /* the global skip flag (exchanged right after the tail) — NOT the weight gradients */
-  if (has_emb) emb.scatter_update_entries(p2p.state(), R * cap, 2, skip_ptr(st_dev));   /* PServer.push (sync mode) + psUpdate on the owner */
   fork(s1, s);                                                                  /* the dense update */
+  fork(s2, s);                                                                  /* the tidy */
+  mark("end");
   last_N = N; last_train = true;
 }
 

@@ -5,6 +5,7 @@
 #include "p2p.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace psb {
 
@@ -12,20 +13,24 @@ namespace {
 
 __global__ void p2p_begin_kernel(P2PState* st) {
   if (threadIdx.x == 0) st->seq += 1u;
-  if (threadIdx.x < kP2PMaxRanks) st->cursor[threadIdx.x] = 0;
 }
 
 /* PSRouterClient.getList, request side (PSRouterClient.java:60-68): the router sends each key of the batch ONCE to
  * its shard.  Every lookup finds-or-inserts its key in the per-batch table and counts itself; the first occurrence
  * reserves a position in the owner's bucket (one global atomic per (block, owner)) and stores the key straight into
- * the owner's keys_in[me][pos] over NVLink.  The occurrence count is only complete when the kernel ends: it travels
- * later, with the gradient push.  The table needs no clearing pass: the push clears exactly the entries it used.   */
+ * the owner's keys_in[me][pos] over NVLink.  The occurrence count is only complete when the kernel ends (p2p_counts_kernel
+ * copies it next to the gradient sums).  This is the FIRST kernel of a sharded step: it works with seq + 1 throughout, and
+ * the block that finishes last makes that the step's sequence number before it flags the owners — every other block has
+ * read the old value by then (its ticket comes after), every later kernel of the step reads the new one.               */
 __global__ void __launch_bounds__(256) p2p_route_send_kernel(P2PState* st, BatchSlot* __restrict__ bt, uint32_t BT, const int64_t* __restrict__ E, int L, int F,
                                                              int32_t* __restrict__ lk_b, int32_t* __restrict__ ulist) {
   const int lane = threadIdx.x & 31;
   const int R = st->R, cap = st->cap;
   const int N = L / F;
+  const uint32_t seq = *reinterpret_cast<const volatile uint32_t*>(&st->seq) + 1u;
+  int32_t* cursor = st->cursor[seq & 1u];
   __shared__ int s_cnt[kP2PMaxRanks], s_base[kP2PMaxRanks];
+  __shared__ bool s_last;
   /* a capped grid striding over tiles of 256 lookups (the publish at the end costs one system fence + one ticket per block) */
   for (int t0 = blockIdx.x * 256; t0 < L; t0 += gridDim.x * 256) {
     const int t = t0 + threadIdx.x;                           /* field-major: a warp works on one field, consecutive samples */
@@ -60,19 +65,78 @@ __global__ void __launch_bounds__(256) p2p_route_send_kernel(P2PState* st, Batch
     int rank_in_block = 0;
     if (first) rank_in_block = atomicAdd(&s_cnt[owner], 1);
     __syncthreads();
-    if (threadIdx.x < R) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&st->cursor[threadIdx.x], s_cnt[threadIdx.x]) : 0;
+    if (threadIdx.x < R) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&cursor[threadIdx.x], s_cnt[threadIdx.x]) : 0;
     __syncthreads();
     if (first) {
       const int pos = s_base[owner] + rank_in_block;
       if (pos < cap) {
         bt[b].upos = owner * cap + pos;
         ulist[owner * cap + pos] = b;
-        reinterpret_cast<unsigned long long*>(p2p_region(st, owner, st->off_keys))[(size_t)st->me * cap + pos] = key;
+        reinterpret_cast<unsigned long long*>(p2p_region_of(st, owner, st->off_keys, seq))[(size_t)st->me * cap + pos] = key;
       } else { bt[b].upos = -1; st->overflow = 1; }
     }
     __syncthreads();                             /* s_cnt / s_base are rewritten by the next tile */
   }
-  p2p_publish_last(st, CH_KEYS, gridDim.x);
+  /* p2p_publish_last with the sequence number this kernel introduces */
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    p2p_block_fence(st);
+    const uint32_t tk = atomicAdd(&st->ticket[CH_KEYS], 1u);
+    s_last = tk == gridDim.x - 1u;
+    if (s_last) { st->ticket[CH_KEYS] = 0u; st->seq = seq; }
+  }
+  __syncthreads();
+  if (s_last && (int)threadIdx.x < R) {
+    const int r = threadIdx.x;
+    const int c = min(*reinterpret_cast<volatile int32_t*>(&cursor[r]), cap);
+    reinterpret_cast<volatile int32_t*>(p2p_region_of(st, r, st->off_counts, seq))[st->me] = c;
+    __threadfence_system();
+    p2p_st_release_sys(reinterpret_cast<uint32_t*>(p2p_region_of(st, r, st->off_flags, seq)) + CH_KEYS * kP2PMaxRanks + st->me, seq);
+  }
+}
+
+/* the occurrence count of every unique key of the batch, next to its gradient sum (the owner reads both): side stream, after route_send */
+__global__ void __launch_bounds__(256) p2p_counts_kernel(const P2PState* st, const BatchSlot* __restrict__ bt, const int32_t* __restrict__ ulist) {
+  const int cap = st->cap, R = st->R;
+  const int32_t* cursor = st->cursor[st->seq & 1u];
+  uint32_t* gc = reinterpret_cast<uint32_t*>(p2p_region(st, st->me, st->off_gcnt));
+  for (int owner = 0; owner < R; ++owner) {
+    const int valid = min(cursor[owner], cap);
+    for (int pos = blockIdx.x * blockDim.x + threadIdx.x; pos < valid; pos += gridDim.x * blockDim.x) {
+      const int q = owner * cap + pos;
+      gc[q] = bt[ulist[q]].cnt;
+    }
+  }
+}
+
+/* side stream, after the backward's scatter (the last reader of the de-duplication table): (1) clears exactly the table entries
+ * this batch used; (2) zeroes the gradient sums of the OTHER parity — the owners read them during their previous step's update,
+ * which they have all left (this rank has seen their CH_KEYS of the current step) — and then that parity's cursors.       */
+__global__ void __launch_bounds__(256) p2p_tidy_kernel(P2PState* st, BatchSlot* __restrict__ bt, const int32_t* __restrict__ ulist) {
+  const int cap = st->cap, R = st->R, tpl = st->Dp >> 2, Dp = st->Dp;
+  const uint32_t seq = st->seq;
+  const int32_t* cur = st->cursor[seq & 1u];
+  int32_t* old = st->cursor[(seq + 1u) & 1u];
+  float* gs = reinterpret_cast<float*>(p2p_region_of(st, st->me, st->off_grads, seq + 1u));
+  const long g0 = (long)blockIdx.x * blockDim.x + threadIdx.x, gstride = (long)gridDim.x * blockDim.x;
+  for (int owner = 0; owner < R; ++owner) {
+    const int valid = min(cur[owner], cap);
+    for (long pos = g0; pos < valid; pos += gstride)
+      *reinterpret_cast<uint4*>(&bt[ulist[(long)owner * cap + pos]]) = make_uint4(0u, 0u, 0u, 0u);
+    const long zv = (long)min(*reinterpret_cast<volatile int32_t*>(&old[owner]), cap) * tpl;
+    float* base = gs + (size_t)owner * cap * Dp;
+    for (long g = g0; g < zv; g += gstride) st_f4(base + g * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+  }
+  __shared__ bool s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const uint32_t tk = atomicAdd(&st->tidy_ticket, 1u);
+    s_last = tk == gridDim.x - 1u;
+    if (s_last) st->tidy_ticket = 0u;
+  }
+  __syncthreads();
+  if (s_last && (int)threadIdx.x < kP2PMaxRanks) old[threadIdx.x] = 0;
 }
 
 /* all-gather by stores: this rank's `bytes` go to slot `me` of the channel's region on every rank */
@@ -133,35 +197,9 @@ __global__ void __launch_bounds__(256) p2p_reduce_kernel(const P2PState* st, flo
   gsum[i] = s;
 }
 
-/* KVStore.update → client.push per key (KVStore.java:257-260).  Phase 1 is EmbTable::scatter_rows (table.cu): the per-lookup row
- * gradients (ReLU mask of EmbeddingField.java:91-93) are summed per unique key of this rank's batch into gacc[bucket position]. */
-/* Phase 2: one gradient sum per unique key, with the key's occurrence count in this rank's batch → its owner's
- * grads_in[me][pos] / gcnt_in[me][pos]; the local accumulator and the per-batch table entry are cleared for the next step */
-__global__ void __launch_bounds__(256) p2p_grad_send_kernel(P2PState* st, float* __restrict__ gacc, BatchSlot* __restrict__ bt, const int32_t* __restrict__ ulist) {
-  const int cap = st->cap, Dp = st->Dp, me = st->me, tpl = Dp >> 2, R = st->R;
-  /* a persistent grid (the publish at the end costs one system fence and one ticket per BLOCK): the blocks stride over the
-   * valid prefix of every owner's bucket — cursor[] is final since route_send ended */
-  for (int owner = 0; owner < R; ++owner) {
-    const long valid = (long)min(st->cursor[owner], cap) * tpl;
-    float* dst_rows = reinterpret_cast<float*>(p2p_region(st, owner, st->off_grads)) + (size_t)me * cap * Dp;
-    uint32_t* dst_cnt = reinterpret_cast<uint32_t*>(p2p_region(st, owner, st->off_gcnt)) + (size_t)me * cap;
-    for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < valid; g += (long)gridDim.x * blockDim.x) {
-      const int pos = (int)(g / tpl), part = (int)(g - (long)pos * tpl);
-      const int q = owner * cap + pos;
-      float* a = gacc + (size_t)q * Dp + part * 4;
-      const float4 v = __ldcg(reinterpret_cast<const float4*>(a));
-      st_f4(dst_rows + (size_t)pos * Dp + part * 4, v);
-      st_f4(a, make_float4(0.f, 0.f, 0.f, 0.f));
-      if (part == 0) {
-        const int b = ulist[q];
-        dst_cnt[pos] = bt[b].cnt;
-        *reinterpret_cast<uint4*>(&bt[b]) = make_uint4(0u, 0u, 0u, 0u);
-      }
-    }
-  }
-  p2p_publish_last(st, CH_GRADS, gridDim.x);
-}
-
+/* KVStore.update → client.push per key (KVStore.java:257-260): EmbTable::scatter_rows (table.cu) sums the per-lookup row gradients
+ * (ReLU mask of EmbeddingField.java:91-93) per unique key of this rank's batch into the gsums region of this rank's slab and flags
+ * the owners; an owner's update kernel reads the sums of every requester straight out of their slabs (EmbTable::update_pull). */
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
@@ -171,6 +209,7 @@ void P2P::create(Ctx* c, int R_, int me_, int cap_, int Dp_, int NF_, int glen_,
   ctx = c; R = R_; me = me_; cap = cap_; Dp = Dp_; NF = NF_; glen = (glen_ + 3) / 4 * 4;
   size_t off = 0;
   host = P2PState{};
+  { const char* e = std::getenv("PS_P2P_BLOCK_FENCE_SYS"); host.block_fence_sys = (e && std::atoi(e) != 0) ? 1 : 0; }
   host.R = R; host.me = me; host.cap = cap; host.Dp = Dp; host.NF = NF; host.glen = glen;
   host.off_keys = off; off = align_up(off + (size_t)R * cap * 8, 256);
   host.off_rows = off; off = align_up(off + (size_t)R * cap * Dp * 4, 256);
@@ -190,7 +229,6 @@ void P2P::create(Ctx* c, int R_, int me_, int cap_, int Dp_, int NF_, int glen_,
   while ((int64_t)BT < 2 * Lmax) BT <<= 1;
   bt = dmalloc_zero<BatchSlot>(BT, ctx->stream);
   lk_b = dmalloc<int32_t>((size_t)std::max<int64_t>(Lmax, 1));
-  gacc = dmalloc_zero<float>((size_t)R * cap * Dp, ctx->stream);
   ulist = dmalloc_zero<int32_t>((size_t)R * cap, ctx->stream);
   PS_CUDA(cudaStreamSynchronize(ctx->stream));
 }
@@ -219,8 +257,8 @@ void P2P::connect(const void* all_handles) {
 
 void P2P::destroy() {
   for (int r = 0; r < R; ++r) if (peer_mapped[r]) { cudaIpcCloseMemHandle(peer_mapped[r]); peer_mapped[r] = nullptr; }
-  dfree(slab); dfree(dev); dfree(bt); dfree(lk_b); dfree(gacc); dfree(ulist);
-  slab = nullptr; dev = nullptr; bt = nullptr; lk_b = nullptr; gacc = nullptr; ulist = nullptr; connected = false;
+  dfree(slab); dfree(dev); dfree(bt); dfree(lk_b); dfree(ulist);
+  slab = nullptr; dev = nullptr; bt = nullptr; lk_b = nullptr; ulist = nullptr; connected = false;
 }
 
 #define P2P_LAUNCHED() do { PS_LAUNCH_CHECK(); ctx->launches++; } while (0)
@@ -261,10 +299,14 @@ void P2P::reduce_gsum(float* gsum) {
   P2P_LAUNCHED();
 }
 
-void P2P::grad_send() {
-  const long total = (long)R * cap * (Dp / 4);
-  const int grid = (int)std::max<long>(1, std::min<long>(ceil_div(total, 256), (long)ctx->num_sms * 6));
-  p2p_grad_send_kernel<<<grid, 256, 0, ctx->stream>>>(dev, gacc, bt, ulist);
+void P2P::counts() {
+  p2p_counts_kernel<<<std::max(1, std::min(ceil_div(cap, 256), ctx->num_sms * 2)), 256, 0, ctx->stream>>>(dev, bt, ulist);
+  P2P_LAUNCHED();
+}
+
+void P2P::tidy() {
+  const long total = (long)cap * (Dp / 4);
+  p2p_tidy_kernel<<<(int)std::max<long>(1, std::min<long>(ceil_div(total, 256), (long)ctx->num_sms * 4)), 256, 0, ctx->stream>>>(dev, bt, ulist);
   P2P_LAUNCHED();
 }
 

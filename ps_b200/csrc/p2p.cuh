@@ -7,21 +7,24 @@
  * the pack step and the transfer are one kernel, there is no collective call and no host
  * involvement — a whole sharded step is one CUDA graph per rank.
  *
- * Mailbox slab of a rank (double-buffered by step parity p = seq & 1):
- *   keys_in [p][R][cap]      u64   rank r's DE-DUPLICATED packed keys         (getList request)
- *   rows_in [p][R][cap][Dp]  f32   rows returned by owner r                  (getList response)
- *   grads_in[p][R][cap][Dp]  f32   per-key gradient SUMS pushed by rank r    (push)
- *   gcnt_in [p][R][cap]      u32   occurrences of the key in rank r's batch  (travels with the push: the owner needs
- *                                  the global count only when it applies the update)
+ * Slab of a rank (double-buffered by step parity p = seq & 1):
+ *   keys_in [p][R][cap]      u64   rank r's DE-DUPLICATED packed keys         (getList request, stored by r)
+ *   rows_in [p][R][cap][Dp]  f32   rows returned by owner r                  (getList response, stored by r)
+ *   gsums   [p][R][cap][Dp]  f32   THIS rank's per-key gradient sums FOR owner o at [o]  (push: formed here by the backward's
+ *                                  scatter, READ by owner o over NVLink inside its update kernel — there is no send kernel)
+ *   gcnt    [p][R][cap]      u32   occurrences of those keys in this rank's batch (read by the owner with the sums)
  *   wide_in [p][R][NF]       i64   wide ids of rank r                        (replicated wide table)
  *   gsum_in [p][R][glen]     f32   dense gradient sums + loss + gbar of r    (PServer sync-mode sum)
  *   counts  [p][R]           i32   number of valid keys from rank r
  *   flags   [p][CH][R]       u32   step sequence number, written last with release.sys
- * There are no flag kernels: every thread of a PRODUCER kernel fences its peer stores at system scope, the block that
- * finishes last (a ticket) release-stores the flag into every consumer's slab (p2p_publish_last); a CONSUMER kernel
+ * There are no flag kernels: thread 0 of every block of a PRODUCER kernel fences the block's stores at system scope, the block
+ * that finishes last (a ticket) release-stores the flag into every consumer's slab (p2p_publish_last); a CONSUMER kernel
  * spins on its own flags in its prologue (p2p_wait_all, acquire.sys).  Every send precedes the matching wait in every
  * rank's program order on the same logical stream, and a waiting block depends on no other block of its own grid, so
- * there is no circular wait; ranks can drift by at most one step, which the parity double-buffering covers.
+ * there is no circular wait.  Ranks can drift by at most one step, which the parity double-buffering covers: a rank that has
+ * seen every peer's CH_KEYS flag of step t knows that every peer is past its update of step t-1, so what the peers read or
+ * wrote for step t-1 (this rank's gsums of the other parity among it) is free — the tidy kernel zeroes it then.
+ * A sharded step has no begin kernel either: route_send works with seq + 1 and its last block publishes the new seq.
  */
 #pragma once
 #include "common.cuh"
@@ -36,9 +39,11 @@ struct P2PState {                      /* lives in device memory; kernels read i
   unsigned char* peer[kP2PMaxRanks];   /* base of every rank's slab as mapped into THIS process */
   size_t off_keys, off_rows, off_grads, off_gcnt, off_wide, off_gsum, off_counts, off_flags, parity_stride;
   uint32_t seq;
-  int32_t cursor[kP2PMaxRanks];
+  int32_t cursor[2][kP2PMaxRanks];     /* by parity: unique keys of this rank's batch per owner (final when route_send ends; zeroed by the NEXT step's tidy) */
   uint32_t ticket[CH_COUNT];           /* blocks of the running producer kernel of each channel that have finished */
+  uint32_t tidy_ticket;
   int32_t overflow;
+  int32_t block_fence_sys;             /* 1: every block of a producer fences at system scope before its ticket (PS_P2P_BLOCK_FENCE_SYS=1); default 0, see p2p_publish_last */
 };
 
 struct __align__(16) BatchSlot {       /* the sender's per-batch de-duplication table: key → bucket position, occurrences */
@@ -63,18 +68,19 @@ struct P2P {
   void destroy();
 
   /* --- kernels (asynchronous on ctx->stream) --- */
-  void begin();                                                                     /* seq += 1, cursors = 0 */
+  void begin();                                                                     /* seq += 1 (models without an embedding table: no route_send) */
   /* sender-side de-duplication (what PSRouterClient's key→shard map does): unique keys get a bucket position,
    * every lookup remembers its batch slot; then {key, occurrences} of each unique key goes to its owner    */
-  BatchSlot* bt = nullptr; uint32_t BT = 0; int32_t* lk_b = nullptr; float* gacc = nullptr; int64_t Lmax = 0;
-  int32_t* ulist = nullptr;                                                         /* bucket position -> batch slot (its count travels with the push; the push clears it) */
-  void route_send(const int64_t* E, int N, int F);                                  /* de-duplicate, reserve, store each key into its owner's keys_in; publishes CH_KEYS */
+  BatchSlot* bt = nullptr; uint32_t BT = 0; int32_t* lk_b = nullptr; int64_t Lmax = 0;
+  int32_t* ulist = nullptr;                                                         /* bucket position -> batch slot */
+  void route_send(const int64_t* E, int N, int F);                                  /* seq + 1; de-duplicate, reserve, store each key into its owner's keys_in; publishes seq and CH_KEYS */
+  void counts();                                                                    /* side stream, after route_send: gcnt[q] = occurrences of the q-th unique key */
+  void tidy();                                                                      /* side stream, after the backward's scatter: clears the de-duplication table; zeroes the OTHER parity's gsums */
   void wait(int channel);                                                           /* one-warp consumer-side wait (before a large-grid consumer on a side stream) */
   void bcast(const void* src, size_t bytes, int channel);                           /* wide ids → every peer; publishes the channel */
   void unpack(int N, int F, int D, float* out, int ldo, const float* X, int Xn, int xoff);   /* rows_in (+ X) → concat buffer */
   void reduce_gsum(float* gsum);                                                    /* sum over ranks, fixed order */
-  /* (the per-key sums are formed by EmbTable::scatter_rows into gacc) */
-  void grad_send();                                                                 /* sums + counts → owners' grads_in / gcnt_in; publishes CH_GRADS */
+  /* (the per-key sums are formed by EmbTable::scatter_rows in this rank's gsums region; its last block publishes CH_GRADS) */
   /* device addresses inside the LOCAL slab for the current parity are resolved in-kernel from seq */
   const P2PState* state() const { return dev; }
   bool overflowed();
@@ -84,23 +90,43 @@ struct P2P {
 __device__ __forceinline__ unsigned char* p2p_region(const P2PState* st, int rank, size_t off) {
   return st->peer[rank] + (size_t)(st->seq & 1u) * st->parity_stride + off;
 }
+__device__ __forceinline__ unsigned char* p2p_region_of(const P2PState* st, int rank, size_t off, uint32_t seq) {
+  return st->peer[rank] + (size_t)(seq & 1u) * st->parity_stride + off;
+}
 __device__ __forceinline__ void p2p_st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+/* loads from ANOTHER GPU's memory (after the acquire of its flag): system-scope relaxed, never served from a stale local line */
+__device__ __forceinline__ float4 p2p_ld_sys_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t p2p_ld_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
 __device__ __forceinline__ uint32_t p2p_ld_acquire_sys(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-/* Producer side, called by EVERY thread of the grid once its stores into peer memory are issued.  The block barrier orders
- * the block's stores before thread 0, whose ONE system-scope fence (cumulative) orders them before its ticket — a fence per
- * thread made these small kernels 2-3x longer; the block that arrives last flags every peer with the step's sequence number
- * (CH_KEYS: after the key counts).  Returns true in that last block.                                                    */
+/* Producer side, called by EVERY thread of the grid once its stores (into peer memory, or into local memory the peers will
+ * read) are issued.  The block barrier orders the block's stores before thread 0, whose ONE device-scope fence (cumulative)
+ * orders them before its ticket; the block that takes the last ticket has thereby observed every other block's stores, and
+ * ITS system-scope fence + release store (cumulative again, PTX memory model: causality order is transitive across scopes)
+ * publishes all of them to the peers with the step's sequence number.  A system-scope fence in every block is not needed for
+ * that, and costs: system fences are served one after the other chip-wide — with a few hundred blocks that was 10-15 us per
+ * producer kernel (r02_notes.md).  Returns true in the last block.                                                        */
+__device__ __forceinline__ void p2p_block_fence(const P2PState* st) {
+  if (st->block_fence_sys) __threadfence_system(); else __threadfence();
+}
 __device__ __forceinline__ bool p2p_publish_last(P2PState* st, int channel, uint32_t nblocks) {
   __shared__ bool s_last;
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence_system();
+    p2p_block_fence(st);
     const uint32_t t = atomicAdd(&st->ticket[channel], 1u);
     s_last = t == nblocks - 1u;
     if (s_last) st->ticket[channel] = 0u;
@@ -108,10 +134,6 @@ __device__ __forceinline__ bool p2p_publish_last(P2PState* st, int channel, uint
   __syncthreads();
   if (s_last && (int)threadIdx.x < st->R) {
     const int r = threadIdx.x;
-    if (channel == CH_KEYS) {
-      const int c = min(*reinterpret_cast<volatile int32_t*>(&st->cursor[r]), st->cap);
-      reinterpret_cast<volatile int32_t*>(p2p_region(st, r, st->off_counts))[st->me] = c;
-    }
     __threadfence_system();
     p2p_st_release_sys(reinterpret_cast<uint32_t*>(p2p_region(st, r, st->off_flags)) + channel * kP2PMaxRanks + st->me, st->seq);
   }

@@ -111,7 +111,8 @@ __device__ __forceinline__ void tb_cp_async16(uint32_t dst, const void* src) {
 }
 
 /* true in exactly one block of the grid: the one whose threads arrive last.  Call from all threads.
- * system: the grid stored into peer memory — fence those stores for the other GPUs, not just for this one. */
+ * system: fence the block's stores at system scope before the ticket (only for the A/B switch of p2p_publish_last: the last
+ * block's own system-scope fence is cumulative over everything the tickets made it observe). */
 __device__ __forceinline__ bool last_block_done(uint32_t* ticket, uint32_t nblocks, bool system = false) {
   __shared__ bool s_last;
   __syncthreads();                               /* the block's writes happen-before thread 0's (cumulative) fence */
@@ -139,6 +140,10 @@ struct LookupArgs {
   /* requester side of the exchange ("pre-resolved"): lookup t reads record pre_recs[pre_lk[t]] = {key, count, row index | -1} of the
    * per-batch de-duplication table instead of probing; rows come from this step's rows_in mailbox (after waiting for CH_ROWS) */
   const EmbSlot* pre_recs; const int32_t* pre_lk;
+  /* owner side of the exchange: instead of counting, every entry (requester, position) links itself into its key's chain — the
+   * slot's batch counter holds 1 + the chain's head entry, chain[entry] the next one (0 ends it).  The update kernel walks it to
+   * find the gradient sums the requesters hold for the key (at most one entry per requester: they de-duplicate).            */
+  int32_t* chain;
   int task_blocks, hot_tma, hot_share;   /* hot_share: lookups of one warp task that must share a row before the TMA unit fetches it (1: every row) */
 };
 
@@ -265,12 +270,16 @@ __global__ void __launch_bounds__(256) emb_lookup_kernel(const __grid_constant__
       const unsigned peers = __match_any_sync(0xffffffffu, slot >= 0 ? slot : (-1 - lane));
       const int leader = __ffs(peers) - 1;
       uint32_t old = 1u, ubase = 0u;
-      if (slot >= 0 && leader == lane && !pre) old = atomicAdd(&a.slots[slot].cnt, (uint32_t)__popc(peers));
+      const bool counts_itself = a.chain != nullptr || leader == lane;
+      if (slot >= 0 && !pre) {
+        if (a.chain != nullptr) { old = atomicExch(&a.slots[slot].cnt, (uint32_t)n + 1u); a.chain[n] = (int32_t)old; }
+        else if (leader == lane) old = atomicAdd(&a.slots[slot].cnt, (uint32_t)__popc(peers));
+      }
       unsigned omask = 0u;
       bool is_owner = false;
       /* the group that found the batch counter at zero owns the key: claim its place in the unique list (consumes `old`) */
       auto claim = [&]() {
-        is_owner = slot >= 0 && leader == lane && old == 0u;
+        is_owner = slot >= 0 && counts_itself && old == 0u;
         omask = __ballot_sync(0xffffffffu, is_owner);
         if (omask != 0u && lane == __ffs(omask) - 1) ubase = atomicAdd(&a.counters[CNT_CURSOR], (uint32_t)__popc(omask));
       };
@@ -364,7 +373,7 @@ __global__ void __launch_bounds__(256) emb_lookup_kernel(const __grid_constant__
     raw_n = raw_a; rv_n = rv_a;
   }
   /* owner side of the exchange only: the block that finishes last flags every requester (PServer.getList answered) */
-  if (a.send_rows && last_block_done(&a.counters[CNT_TICKET_FWD], (uint32_t)a.task_blocks, true) && (int)threadIdx.x < a.p2p->R) {
+  if (a.send_rows && last_block_done(&a.counters[CNT_TICKET_FWD], (uint32_t)a.task_blocks, a.p2p->block_fence_sys != 0) && (int)threadIdx.x < a.p2p->R) {
     __threadfence_system();
     p2p_st_release_sys(reinterpret_cast<uint32_t*>(p2p_region(a.p2p, threadIdx.x, a.p2p->off_flags)) + CH_ROWS * kP2PMaxRanks + a.p2p->me, a.p2p->seq);
   }
@@ -425,8 +434,11 @@ __global__ void __launch_bounds__(256) emb_scatter_kernel(const EmbSlot* __restr
                                                           const uint32_t* __restrict__ lk_mask, int MW, int N,
                                                           int F, int SB, const float* __restrict__ delta, int ldd, const float* __restrict__ act, int lda,
                                                           float* __restrict__ acc, const int* __restrict__ skip_flag,
-                                                          int raw_row, uint32_t hot_min) {
+                                                          int raw_row, uint32_t hot_min, P2PState* pub) {
   constexpr int GPW = 32 / TPL;                  /* lookups (lane groups) per warp task */
+  /* requester side of the sharded push (skip_flag is null there): the sums go to this step's gsums region of this rank's slab,
+   * where the owners read them; the block that finishes last flags them (CH_GRADS) */
+  if (pub != nullptr) acc = reinterpret_cast<float*>(p2p_region(pub, pub->me, pub->off_grads));
   constexpr int ROWF = TPL * CPL * 4;            /* floats of a (padded) row */
   __shared__ float hot_acc[kHotEntries][ROWF];
   __shared__ int hot_slot[kHotEntries];
@@ -566,6 +578,7 @@ __global__ void __launch_bounds__(256) emb_scatter_kernel(const EmbSlot* __restr
     const float4 v = *reinterpret_cast<const float4*>(&hot_acc[e][cc]);
     if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) red_add_f4(acc + (size_t)hot_row[e] * Dp + cc, v);
   }
+  if (pub != nullptr) p2p_publish_last(pub, CH_GRADS, gridDim.x);
 }
 
 /* The scatter for the common case (16 B aligned rows, ReLU mask from the lookup's bits): same three levels of pre-summation, but
@@ -578,8 +591,9 @@ template <int TPL>
 __global__ void __launch_bounds__(256) emb_scatter_slab_kernel(const EmbSlot* __restrict__ slots, int Dp, int D, const int32_t* __restrict__ lk_slot,
                                                                const uint32_t* __restrict__ lk_mask, int MW, int N, int F,
                                                                const float* __restrict__ delta, int ldd, float* __restrict__ acc,
-                                                               const int* __restrict__ skip_flag, int raw_row, uint32_t hot_min) {
+                                                               const int* __restrict__ skip_flag, int raw_row, uint32_t hot_min, P2PState* pub) {
   constexpr int GPW = 32 / TPL, NP = TPL;
+  if (pub != nullptr) acc = reinterpret_cast<float*>(p2p_region(pub, pub->me, pub->off_grads));   /* see emb_scatter_kernel */
   extern __shared__ __align__(128) unsigned char scatter_smem[];
   int* hot_slot = reinterpret_cast<int*>(scatter_smem);                                  /* [kHotEntries] */
   uint32_t* hot_row = reinterpret_cast<uint32_t*>(scatter_smem + 4 * kHotEntries);       /* [kHotEntries] */
@@ -697,6 +711,7 @@ __global__ void __launch_bounds__(256) emb_scatter_slab_kernel(const EmbSlot* __
     const float4 v = *reinterpret_cast<const float4*>(hot_acc + (size_t)he * Dp + cc);
     if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) red_add_f4(acc + (size_t)hot_row[he] * Dp + cc, v);
   }
+  if (pub != nullptr) p2p_publish_last(pub, CH_GRADS, gridDim.x);
 }
 
 /* KVStore.update + clear for the batch's unique keys.  A warp takes KPW = 32 / (Dp/4) consecutive entries of the unique
@@ -705,7 +720,7 @@ __global__ void __launch_bounds__(256) emb_scatter_slab_kernel(const EmbSlot* __
 template <bool EXACT>
 __global__ void __launch_bounds__(256) emb_update_kernel(EmbSlot* __restrict__ slots, float* __restrict__ rows, int rs, int Dp, int D,
                                                          const int32_t* __restrict__ uniq, float* __restrict__ acc, UpdaterDev upd, int calls,
-                                                         const int* __restrict__ skip_flag, uint32_t* __restrict__ ucnt, uint32_t* __restrict__ counters) {
+                                                         const int* __restrict__ skip_flag, uint32_t* __restrict__ counters) {
   const int lane = threadIdx.x & 31;
   const int CH = Dp >> 2;
   const int KPW = 32 / CH;
@@ -742,9 +757,6 @@ __global__ void __launch_bounds__(256) emb_update_kernel(EmbSlot* __restrict__ s
     float4 S = make_float4(0.f, 0.f, 0.f, 0.f);
     if (on && !skip) S = __ldcg(reinterpret_cast<const float4*>(acc + (size_t)u * Dp + cc));
     const int src0 = lane - ch;                               /* the key's chunk-0 lane */
-    /* owner side of the peer-memory exchange: the slot counted (requester, key) entries; the occurrences of the key in the
-     * global batch were summed into ucnt[u] by the owner-side scatter */
-    if (ucnt != nullptr && on && ch == 0) cnt = __ldcg(ucnt + u);   /* (zeroed at the end of the round, away from this load) */
     const uint32_t n_occ = __shfl_sync(0xffffffffu, cnt, src0);
     const float S0 = __shfl_sync(0xffffffffu, S.x, src0);
     const GeffScale gs = make_geff<EXACT>(n_occ > 0u ? n_occ : 1u, calls);
@@ -764,43 +776,13 @@ __global__ void __launch_bounds__(256) emb_update_kernel(EmbSlot* __restrict__ s
         st_f4(acc + (size_t)u * Dp + cc, make_float4(0.f, 0.f, 0.f, 0.f));
       }
       /* KVStore.clear (also after the early exit: the batch is forgotten): {cnt, uidx} = {0, ready} in one 8 B store */
-      if (ch == 0) {
-        *reinterpret_cast<unsigned long long*>(&slots[slot].cnt) = (unsigned long long)kRowReady << 32;
-        if (ucnt != nullptr) ucnt[u] = 0u;
-      }
+      if (ch == 0) *reinterpret_cast<unsigned long long*>(&slots[slot].cnt) = (unsigned long long)kRowReady << 32;
     }
     wi += wstride;
     have = wi * KPW < (long)U;
     if (have) prefetch(wi);
   }
   if (last_block_done(&counters[CNT_TICKET_UPD], gridDim.x) && threadIdx.x == 0) counters[CNT_CURSOR] = 0u;
-}
-
-/* Owner side of the push (PServer.push in sync mode, PServer.java:164-195: the pushes of all workers are summed, one
- * update): entry (src, pos) of this step's grads_in mailbox is requester src's gradient sum for the key it asked for as
- * its pos-th, already ReLU-masked; it lands in the key's accumulator row, its occurrence count in ucnt.  Waits for every
- * requester's CH_GRADS flag in its prologue.                                                                        */
-__global__ void __launch_bounds__(256) emb_scatter_entries_kernel(const EmbSlot* __restrict__ slots, int Dp, const int32_t* __restrict__ lk_slot,
-                                                                  float* __restrict__ acc, uint32_t* __restrict__ ucnt,
-                                                                  const int* __restrict__ skip_flag, const P2PState* __restrict__ p2p) {
-  p2p_wait_all(p2p, CH_GRADS);
-  pdl_launch_dependents();
-  if (skip_flag != nullptr && *skip_flag != 0) return;
-  const int CH = Dp >> 2, cap = p2p->cap;
-  const long items = (long)p2p->R * cap * CH;
-  const float* grads = reinterpret_cast<const float*>(p2p_region(p2p, p2p->me, p2p->off_grads));
-  const uint32_t* gcnt = reinterpret_cast<const uint32_t*>(p2p_region(p2p, p2p->me, p2p->off_gcnt));
-  const int32_t* counts = reinterpret_cast<const int32_t*>(p2p_region(p2p, p2p->me, p2p->off_counts));
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long)gridDim.x * blockDim.x) {
-    const int entry = (int)(i / CH), ch = (int)(i - (long)entry * CH);
-    const int src = entry / cap, idx = entry - src * cap;
-    if (idx >= counts[src]) continue;
-    const int slot = lk_slot[entry];
-    if (slot < 0) continue;
-    const uint32_t u = (slots[slot].uidx & ~kRowReady) - 1u;
-    red_add_f4(acc + (size_t)u * Dp + ch * 4, ld_f4(grads + (size_t)entry * Dp + ch * 4));
-    if (ch == 0) atomicAdd(&ucnt[u], gcnt[entry]);
-  }
 }
 
 /* The same update with the TMA unit doing the memory work.  A warp takes kUpdKeys consecutive entries of the unique list per
@@ -811,15 +793,23 @@ static constexpr int kUpdKeys = 8;
 __device__ __forceinline__ void tb_bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
 }
-template <bool EXACT>
+/* PULL — the owner side of the sharded push (PServer.push in sync mode, PServer.java:164-195: the pushes of all workers are summed,
+ * one update): there is no accumulator row.  The lookup linked every (requester, position) entry that asked for the key into the
+ * key's chain (LookupArgs::chain); lane k walks key k's chain (<= R hops, local), then the warp reads the requesters' gradient
+ * sums for the key straight out of THEIR slabs over NVLink — rank order, so the sum is the same on every run — and the occurrence
+ * counts beside them.  The kernel waits for every requester's CH_GRADS flag once its first records are on the way.          */
+static constexpr int kUpdSlabOff = 512 + 8 * kUpdKeys * kP2PMaxRanks * 4;
+template <bool EXACT, bool PULL>
 __global__ void __launch_bounds__(256) emb_update_slab_kernel(EmbSlot* __restrict__ slots, float* __restrict__ rows, int rs, int Dp, int D,
                                                               const int32_t* __restrict__ uniq, float* __restrict__ acc, UpdaterDev upd, int calls,
-                                                              const int* __restrict__ skip_flag, uint32_t* __restrict__ ucnt, uint32_t* __restrict__ counters) {
+                                                              const int* __restrict__ skip_flag, uint32_t* __restrict__ counters,
+                                                              const int32_t* __restrict__ chain, const P2PState* __restrict__ p2p) {
   extern __shared__ __align__(128) unsigned char update_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint64_t* mbar = reinterpret_cast<uint64_t*>(update_smem);
   uint32_t* kcnt = reinterpret_cast<uint32_t*>(update_smem + 128) + warp * kUpdKeys;             /* occurrence count of the round's keys */
-  float* slab = reinterpret_cast<float*>(update_smem + 512) + (size_t)warp * (kUpdKeys * 4 + 1) * Dp;   /* [key][w | s1 | s2 | S], then one row of zeros */
+  int* kpos = reinterpret_cast<int*>(update_smem + 512) + warp * kUpdKeys * kP2PMaxRanks;        /* PULL: [key][requester] position in the requester's bucket, -1: none */
+  float* slab = reinterpret_cast<float*>(update_smem + kUpdSlabOff) + (size_t)warp * (kUpdKeys * 4 + 1) * Dp;   /* [key][w | s1 | s2 | S], then one row of zeros */
   float* zero_row = slab + (size_t)kUpdKeys * 4 * Dp;
   const uint32_t bar = tb_smem_u32(&mbar[warp]);
   for (int i = lane; i < Dp; i += 32) zero_row[i] = 0.f;
@@ -845,22 +835,61 @@ __global__ void __launch_bounds__(256) emb_update_slab_kernel(EmbSlot* __restric
     }
     const unsigned vm = __ballot_sync(0xffffffffu, slot >= 0);
     if (!skip && vm != 0u) {
-      if (lane == 0) tb_mbar_expect_tx(bar, (uint32_t)__popc(vm) * (rec_bytes + row_bytes));
+      if (lane == 0) tb_mbar_expect_tx(bar, (uint32_t)__popc(vm) * (PULL ? rec_bytes : rec_bytes + row_bytes));
       __syncwarp();
       if (slot >= 0) tb_bulk_g2s(tb_smem_u32(slab + (size_t)lane * 4 * Dp), rows + (size_t)slot * rs, rec_bytes, bar);
     }
   };
   bool have = wi < rounds;
   if (have) fetch_records(wi);                     /* before the scatter kernel is known to be complete */
-  pdl_wait();
+  if (PULL) p2p_wait_all(p2p, CH_GRADS);           /* every requester's sums (and counts) of this step are final */
+  else pdl_wait();
   while (have) {
     const long u = wi * kUpdKeys + lane;
     if (!skip) {
-      if (slot >= 0) tb_bulk_g2s(tb_smem_u32(slab + (size_t)lane * 4 * Dp + 3 * Dp), acc + (size_t)u * Dp, row_bytes, bar);
-      if (ucnt != nullptr && slot >= 0) cnt = __ldcg(ucnt + u);   /* owner side of the exchange: the global occurrence count summed from the pushes */
-      if (lane < kUpdKeys) kcnt[lane] = cnt;
-      if (__any_sync(0xffffffffu, slot >= 0)) { tb_mbar_wait(bar, parity); parity ^= 1u; }
       const int nk = __popc(__ballot_sync(0xffffffffu, slot >= 0));
+      if (PULL) {
+        const int R = p2p->R, cap = p2p->cap, me = p2p->me;
+        if (lane < kUpdKeys) {                     /* `cnt` is the head of key `lane`'s chain: 1 + entry, entry = requester * cap + position */
+          int* sp = kpos + lane * kP2PMaxRanks;
+#pragma unroll
+          for (int r = 0; r < kP2PMaxRanks; ++r) sp[r] = -1;
+          uint32_t e = cnt;
+          for (int hop = 0; e != 0u && hop < kP2PMaxRanks; ++hop) {
+            const int entry = (int)e - 1, src = entry / cap;
+            sp[src] = entry - src * cap;
+            e = (uint32_t)chain[entry];
+          }
+        }
+        __syncwarp();
+        for (int i = lane; i < nk * CH; i += 32) {
+          const int k = i / CH, cc = (i - k * CH) * 4;
+          float4 v[kP2PMaxRanks];
+#pragma unroll
+          for (int r = 0; r < kP2PMaxRanks; ++r) {   /* every requester's load is issued before the first is consumed */
+            const int pos = r < R ? kpos[k * kP2PMaxRanks + r] : -1;
+            v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pos >= 0) v[r] = p2p_ld_sys_f4(reinterpret_cast<const float*>(p2p_region(p2p, r, p2p->off_grads)) + ((size_t)me * cap + pos) * Dp + cc);
+          }
+          float4 S = v[0];
+#pragma unroll
+          for (int r = 1; r < kP2PMaxRanks; ++r) { S.x += v[r].x; S.y += v[r].y; S.z += v[r].z; S.w += v[r].w; }
+          *reinterpret_cast<float4*>(slab + (size_t)k * 4 * Dp + 3 * Dp + cc) = S;
+        }
+        if (lane < kUpdKeys) {
+          uint32_t n = 0u;
+          if (slot >= 0)
+            for (int r = 0; r < R; ++r) {
+              const int pos = kpos[lane * kP2PMaxRanks + r];
+              if (pos >= 0) n += p2p_ld_sys_u32(reinterpret_cast<const uint32_t*>(p2p_region(p2p, r, p2p->off_gcnt)) + (size_t)me * cap + pos);
+            }
+          kcnt[lane] = n;
+        }
+      } else {
+        if (slot >= 0) tb_bulk_g2s(tb_smem_u32(slab + (size_t)lane * 4 * Dp + 3 * Dp), acc + (size_t)u * Dp, row_bytes, bar);
+        if (lane < kUpdKeys) kcnt[lane] = cnt;
+      }
+      if (nk != 0) { tb_mbar_wait(bar, parity); parity ^= 1u; }
       __syncwarp();
       for (int i = lane; i < nk * CH; i += 32) {
         const int k = i / CH, cc = (i - k * CH) * 4;
@@ -884,15 +913,12 @@ __global__ void __launch_bounds__(256) emb_update_slab_kernel(EmbSlot* __restric
       __syncwarp();
       if (slot >= 0) {
         tb_bulk_s2g(rows + (size_t)slot * rs, tb_smem_u32(slab + (size_t)lane * 4 * Dp), rec_bytes);
-        tb_bulk_s2g(acc + (size_t)u * Dp, tb_smem_u32(zero_row), row_bytes);
+        if (!PULL) tb_bulk_s2g(acc + (size_t)u * Dp, tb_smem_u32(zero_row), row_bytes);
       }
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
     /* KVStore.clear (also after the early exit: the batch is forgotten): {cnt, uidx} = {0, ready} in one 8 B store */
-    if (slot >= 0) {
-      *reinterpret_cast<unsigned long long*>(&slots[slot].cnt) = (unsigned long long)kRowReady << 32;
-      if (ucnt != nullptr) ucnt[u] = 0u;
-    }
+    if (slot >= 0) *reinterpret_cast<unsigned long long*>(&slots[slot].cnt) = (unsigned long long)kRowReady << 32;
     if (!skip) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   /* the slab may be refilled */
     __syncwarp();
     wi += wstride;
@@ -946,7 +972,7 @@ __global__ void emb_put_rows_kernel(EmbSlot* __restrict__ slots, uint32_t C, flo
 
 /* ------------------------------------------------------------------ EmbTable host side */
 static int pow2_ge(int x) { int p = 1; while (p < x) p <<= 1; return p; }
-static void launch_update(EmbTable& t, long L, int calls, const int* skip, uint32_t* ucnt);
+static void launch_update(EmbTable& t, long L, int calls, const int* skip, const P2PState* pull);
 
 /* the slab of every warp (32 rows) + the mbarriers: 64 KB at D = 64 — more than the default 48 KB, so every gathering
  * instantiation opts in (once per table, outside any stream capture) */
@@ -995,19 +1021,19 @@ void EmbTable::reserve(int64_t L) {
   if (L <= Lcap) return;
   if (last_L > 0) clear_batch();                /* a forward that was never followed by backward still owns counts in the OLD workspace's list */
   PS_CUDA(cudaStreamSynchronize(ctx->stream));
-  dfree(lk_slot); dfree(lk_mask); dfree(uniq); dfree(acc); dfree(ucnt);
+  dfree(lk_slot); dfree(lk_mask); dfree(uniq); dfree(acc); dfree(chain);
   Lcap = L; ++generation;                      /* captured graphs that hold the old workspace pointers are stale now */
   lk_slot = dmalloc<int32_t>((size_t)L);
   lk_mask = dmalloc<uint32_t>((size_t)L * MW);
   uniq = dmalloc<int32_t>((size_t)L);
   acc = dmalloc_zero<float>((size_t)L * Dp, ctx->stream);   /* one accumulator row per unique key of a batch (<= L) */
-  ucnt = dmalloc_zero<uint32_t>((size_t)L, ctx->stream);
+  chain = dmalloc_zero<int32_t>((size_t)L, ctx->stream);
 }
 
 void EmbTable::destroy() {
   dfree(slots); dfree(rows); dfree(counters);
-  dfree(lk_slot); dfree(lk_mask); dfree(uniq); dfree(acc); dfree(ucnt);
-  ucnt = nullptr; slots = nullptr; rows = w = s1 = s2 = nullptr; lk_slot = nullptr; lk_mask = nullptr; uniq = nullptr; acc = nullptr; counters = nullptr;
+  dfree(lk_slot); dfree(lk_mask); dfree(uniq); dfree(acc); dfree(chain);
+  chain = nullptr; slots = nullptr; rows = w = s1 = s2 = nullptr; lk_slot = nullptr; lk_mask = nullptr; uniq = nullptr; acc = nullptr; counters = nullptr;
 }
 
 template <class IdT, int TPL>
@@ -1069,6 +1095,7 @@ void EmbTable::lookup_packed(const uint64_t* keys, int n, float* out, P2PState* 
   if (n <= 0) return;
   LookupArgs a = base_args(*this);
   a.N = n; a.F = 0; a.ids = keys; a.out = out; a.ldo = Dp; a.p2p = p2p; a.send_rows = send_rows ? 1 : 0;
+  a.chain = (p2p != nullptr && send_rows) ? chain : nullptr;    /* the owner's update will pull the requesters' sums along the chains */
   launch_lookup<unsigned long long>(*this, a, out != nullptr || send_rows);
 }
 
@@ -1078,6 +1105,7 @@ void EmbTable::lookup_packed(const uint64_t* keys, int n, float* out, P2PState* 
 struct ScatterJob {
   const EmbSlot* recs; const int32_t* lk; const uint32_t* mask; float* accp;
   const float* delta; int ldd; const float* act; int lda; int N, F; const int* skip; int raw_row;
+  P2PState* pub;                                 /* requester side of the sharded push: sums into this rank's slab, CH_GRADS published by the last block */
 };
 void EmbTable::gather_resolved(const void* batch_slots, const int32_t* lk_batch, P2PState* p2p, int N, float* out, int ldo, const float* X, int Xn, int xoff) {
   PS_REQUIRE((int64_t)N * F <= Lcap, PS_ERR_ARG, "embedding: batch larger than the reserved workspace");
@@ -1107,9 +1135,9 @@ static void launch_scatter(EmbTable& t, const ScatterJob& j) {
   const long per_block = (long)SB * ceil_div(ceil_div(N, SB), grid);
   const uint32_t hot_min = t.ctx->hot_min == 0xFFFFFFFFu ? 0xFFFFFFFFu : std::max<uint32_t>(t.ctx->hot_min, (uint32_t)(2L * N / per_block));
   if (aligned)
-    emb_scatter_kernel<TPL, CPL, PASSES, true><<<grid, 256, 0, t.ctx->stream>>>(j.recs, t.Dp, t.D, j.lk, j.mask, t.MW, N, j.F, SB, j.delta, j.ldd, j.act, j.lda, j.accp, j.skip, j.raw_row, hot_min);
+    emb_scatter_kernel<TPL, CPL, PASSES, true><<<grid, 256, 0, t.ctx->stream>>>(j.recs, t.Dp, t.D, j.lk, j.mask, t.MW, N, j.F, SB, j.delta, j.ldd, j.act, j.lda, j.accp, j.skip, j.raw_row, hot_min, j.pub);
   else
-    emb_scatter_kernel<TPL, CPL, PASSES, false><<<grid, 256, 0, t.ctx->stream>>>(j.recs, t.Dp, t.D, j.lk, j.mask, t.MW, N, j.F, SB, j.delta, j.ldd, j.act, j.lda, j.accp, j.skip, j.raw_row, hot_min);
+    emb_scatter_kernel<TPL, CPL, PASSES, false><<<grid, 256, 0, t.ctx->stream>>>(j.recs, t.Dp, t.D, j.lk, j.mask, t.MW, N, j.F, SB, j.delta, j.ldd, j.act, j.lda, j.accp, j.skip, j.raw_row, hot_min, j.pub);
   PS_LAUNCH_CHECK();
   t.ctx->launches++;
 }
@@ -1127,7 +1155,7 @@ static void launch_scatter_slab(EmbTable& t, const ScatterJob& j) {
   const int grid = (int)std::max<long>(1, std::min<long>(ceil_div(ntasks, 8), (long)t.ctx->num_sms * std::max(1, t.scatter_slab_occ)));
   const long per_block = 32L * ceil_div(ntasks, (long)grid * 8) * 8 / std::max(1, j.F) + 32;      /* samples of one field a block sees */
   const uint32_t hot_min = t.ctx->hot_min == 0xFFFFFFFFu ? 0xFFFFFFFFu : std::max<uint32_t>(t.ctx->hot_min, (uint32_t)(2L * j.N / per_block));
-  emb_scatter_slab_kernel<TPL><<<grid, 256, smem, t.ctx->stream>>>(j.recs, t.Dp, t.D, j.lk, j.mask, t.MW, j.N, j.F, j.delta, j.ldd, j.accp, j.skip, j.raw_row, hot_min);
+  emb_scatter_slab_kernel<TPL><<<grid, 256, smem, t.ctx->stream>>>(j.recs, t.Dp, t.D, j.lk, j.mask, t.MW, j.N, j.F, j.delta, j.ldd, j.accp, j.skip, j.raw_row, hot_min, j.pub);
   PS_LAUNCH_CHECK();
   t.ctx->launches++;
 }
@@ -1168,14 +1196,28 @@ static void dispatch_scatter(EmbTable& t, const ScatterJob& j) {
 
 /* the update walks the unique list (<= L entries, how many is only known on the device): enough warps for one round at the
  * typical unique fraction, a grid-stride loop beyond; a programmatic dependent of the scatter launched just before it */
-static size_t update_slab_smem(int Dp) { return 512 + (size_t)8 * (kUpdKeys * 4 + 1) * Dp * sizeof(float); }
-static void launch_update(EmbTable& t, long L, int calls, const int* skip, uint32_t* ucnt) {
-  if (t.ctx->update_slab) {
+static size_t update_slab_smem(int Dp) { return kUpdSlabOff + (size_t)8 * (kUpdKeys * 4 + 1) * Dp * sizeof(float); }
+static void launch_update(EmbTable& t, long L, int calls, const int* skip, const P2PState* pull) {
+  if (t.ctx->update_slab || pull != nullptr) {   /* the owner side of the sharded push exists in the staged form only */
     const size_t smem = update_slab_smem(t.Dp);
     if (L == 0) {                                /* EmbTable::create (not inside a capture) */
-      PS_CUDA(cudaFuncSetAttribute(emb_update_slab_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      PS_CUDA(cudaFuncSetAttribute(emb_update_slab_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      PS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t.update_slab_occ, emb_update_slab_kernel<false>, 256, smem));
+      PS_CUDA(cudaFuncSetAttribute(emb_update_slab_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PS_CUDA(cudaFuncSetAttribute(emb_update_slab_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PS_CUDA(cudaFuncSetAttribute(emb_update_slab_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PS_CUDA(cudaFuncSetAttribute(emb_update_slab_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t.update_slab_occ, emb_update_slab_kernel<false, false>, 256, smem));
+      PS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t.update_pull_occ, emb_update_slab_kernel<false, true>, 256, smem));
+      return;
+    }
+    if (pull != nullptr) {                       /* an ordinary launch: the kernel's own flag wait orders it behind the requesters */
+      const long rounds = ceil_div(L, kUpdKeys);
+      const int ugrid = (int)std::max<long>(1, std::min<long>(ceil_div(rounds, 8), (long)t.ctx->num_sms * std::max(1, t.update_pull_occ)));
+      if (t.ctx->exact_updaters)
+        emb_update_slab_kernel<true, true><<<ugrid, 256, smem, t.ctx->stream>>>(t.slots, t.rows, t.rs, t.Dp, t.D, (const int32_t*)t.uniq, nullptr, t.upd, calls, skip, t.counters, (const int32_t*)t.chain, pull);
+      else
+        emb_update_slab_kernel<false, true><<<ugrid, 256, smem, t.ctx->stream>>>(t.slots, t.rows, t.rs, t.Dp, t.D, (const int32_t*)t.uniq, nullptr, t.upd, calls, skip, t.counters, (const int32_t*)t.chain, pull);
+      PS_LAUNCH_CHECK();
+      t.ctx->launches++;
       return;
     }
     const long rounds = ceil_div(L, kUpdKeys);
@@ -1187,9 +1229,9 @@ static void launch_update(EmbTable& t, long L, int calls, const int* skip, uint3
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = t.ctx->pdl ? 1 : 0;
     if (t.ctx->exact_updaters)
-      PS_CUDA(cudaLaunchKernelEx(&cfg, emb_update_slab_kernel<true>, t.slots, t.rows, t.rs, t.Dp, t.D, (const int32_t*)t.uniq, t.acc, t.upd, calls, skip, ucnt, t.counters));
+      PS_CUDA(cudaLaunchKernelEx(&cfg, emb_update_slab_kernel<true, false>, t.slots, t.rows, t.rs, t.Dp, t.D, (const int32_t*)t.uniq, t.acc, t.upd, calls, skip, t.counters, (const int32_t*)nullptr, (const P2PState*)nullptr));
     else
-      PS_CUDA(cudaLaunchKernelEx(&cfg, emb_update_slab_kernel<false>, t.slots, t.rows, t.rs, t.Dp, t.D, (const int32_t*)t.uniq, t.acc, t.upd, calls, skip, ucnt, t.counters));
+      PS_CUDA(cudaLaunchKernelEx(&cfg, emb_update_slab_kernel<false, false>, t.slots, t.rows, t.rs, t.Dp, t.D, (const int32_t*)t.uniq, t.acc, t.upd, calls, skip, t.counters, (const int32_t*)nullptr, (const P2PState*)nullptr));
     t.ctx->launches++;
     return;
   }
@@ -1197,30 +1239,27 @@ static void launch_update(EmbTable& t, long L, int calls, const int* skip, uint3
   const int KPW = 32 / (t.Dp / 4);
   const int ugrid = (int)std::max<long>(1, std::min<long>(ceil_div(ceil_div(L, KPW), 8), (long)t.ctx->num_sms * 16));
   if (t.ctx->exact_updaters)
-    launch_pdl(t.ctx, emb_update_kernel<true>, dim3(ugrid), dim3(256), t.slots, t.rows, t.rs, t.Dp, t.D, (const int32_t*)t.uniq, t.acc, t.upd, calls, skip, ucnt, t.counters);
+    launch_pdl(t.ctx, emb_update_kernel<true>, dim3(ugrid), dim3(256), t.slots, t.rows, t.rs, t.Dp, t.D, (const int32_t*)t.uniq, t.acc, t.upd, calls, skip, t.counters);
   else
-    launch_pdl(t.ctx, emb_update_kernel<false>, dim3(ugrid), dim3(256), t.slots, t.rows, t.rs, t.Dp, t.D, (const int32_t*)t.uniq, t.acc, t.upd, calls, skip, ucnt, t.counters);
+    launch_pdl(t.ctx, emb_update_kernel<false>, dim3(ugrid), dim3(256), t.slots, t.rows, t.rs, t.Dp, t.D, (const int32_t*)t.uniq, t.acc, t.upd, calls, skip, t.counters);
   t.ctx->launches++;
 }
 
 /* requester side of the push: per-lookup row gradients (ReLU mask from `act`) summed per unique key of THIS rank's batch into
- * gacc[bucket position], with the same three levels of pre-summation as the local backward — a hot key's thousands of
- * occurrences leave a block once instead of serialising on one L2 line                                                  */
-void EmbTable::scatter_rows(const void* batch_slots, const int32_t* lk_batch, float* gacc, const float* delta, int ldd, const float* act, int lda, int N) {
+ * the gsums region of this rank's slab (row = bucket position), with the same three levels of pre-summation as the local
+ * backward — a hot key's thousands of occurrences leave a block once instead of serialising on one L2 line.  The kernel's last
+ * block flags the owners (CH_GRADS): they read the sums from here, nothing is sent                                        */
+void EmbTable::scatter_rows(const void* batch_slots, const int32_t* lk_batch, P2PState* p2p, const float* delta, int ldd, const float* act, int lda, int N) {
   /* act == null: the mask bits gather_resolved recorded for this batch */
-  ScatterJob j{reinterpret_cast<const EmbSlot*>(batch_slots), lk_batch, act ? nullptr : lk_mask, gacc, delta, ldd, act, lda, N, F, nullptr, 1};
+  ScatterJob j{reinterpret_cast<const EmbSlot*>(batch_slots), lk_batch, act ? nullptr : lk_mask, nullptr, delta, ldd, act, lda, N, F, nullptr, 1, p2p};
   dispatch_scatter(*this, j);
 }
 
-void EmbTable::scatter_update_entries(const P2PState* p2p, int n, int calls, const int* skip_flag) {
+/* owner side of the push + psUpdate: see emb_update_slab_kernel<.., PULL> */
+void EmbTable::update_pull(const P2PState* p2p, int n, int calls, const int* skip_flag) {
   PS_REQUIRE((int64_t)n == last_L, PS_ERR_STATE, "embedding: push without a matching lookup");
-  const int CH = Dp / 4;
-  const int grid = (int)std::max<long>(1, std::min<long>(ceil_div((long)n * CH, 256), (long)ctx->num_sms * 8));
-  emb_scatter_entries_kernel<<<grid, 256, 0, ctx->stream>>>(slots, Dp, lk_slot, acc, ucnt, skip_flag, p2p);
-  PS_LAUNCH_CHECK();
-  ctx->launches++;
-  static const bool no_ucnt = std::getenv("PS_DEBUG_NO_UCNT") != nullptr;   /* timing experiment only: the update then normalises by the entry count */
-  launch_update(*this, n, calls, skip_flag, no_ucnt ? nullptr : ucnt);
+  PS_REQUIRE(calls == 1 || calls == 2, PS_ERR_ARG, "embedding: backward calls must be 1 or 2");
+  launch_update(*this, n, calls, skip_flag, p2p);
   last_L = 0;
 }
 
@@ -1230,7 +1269,7 @@ void EmbTable::scatter_update(const float* delta, int ldd, const float* act, int
     PS_REQUIRE((int64_t)N * Fe == last_L, PS_ERR_STATE, "embedding: backward without a matching forward");
     PS_REQUIRE(calls == 1 || calls == 2, PS_ERR_ARG, "embedding: backward calls must be 1 or 2");
   }
-  ScatterJob j{slots, lk_slot, use_mask ? lk_mask : nullptr, acc, delta, ldd, use_mask ? nullptr : act, lda, N, Fe, skip_flag, 0};
+  ScatterJob j{slots, lk_slot, use_mask ? lk_mask : nullptr, acc, delta, ldd, use_mask ? nullptr : act, lda, N, Fe, skip_flag, 0, nullptr};
   dispatch_scatter(*this, j);
   if (N == 0) return;
   launch_update(*this, (long)N * Fe, calls, skip_flag, nullptr);

@@ -73,11 +73,12 @@ struct EmbTable {
   uint32_t* lk_mask = nullptr;
   int32_t* uniq = nullptr;
   float* acc = nullptr;
-  uint32_t* ucnt = nullptr;            /* [U] occurrences per unique key as summed from the requesters' pushes (sharded exchange only) */
+  int32_t* chain = nullptr;            /* [Lcap] owner side of the sharded exchange: next entry of the same key (see LookupArgs::chain) */
   uint32_t* counters = nullptr;
   int64_t last_L = 0;
   int scatter_occ[2] = {1, 1};         /* resident scatter blocks per SM (unaligned / aligned instantiation) */
   int update_slab_occ = 1;             /* ... of the staged update kernel */
+  int update_pull_occ = 1;             /* ... and of its owner-side (pulling) form */
   int scatter_slab_occ = 1;            /* ... of the staged scatter kernel */
   int lookup_occ = 2;                  /* resident blocks per SM of the gathering lookup kernel (sizes its persistent grid) */
 
@@ -97,14 +98,15 @@ struct EmbTable {
    * record batch_slots[lk_batch[t]] (its row's place in this step's rows_in mailbox); same gather, ReLU mask bits and ConcatLayer copy
    * as lookup(), no probing and no counting; waits for the owners' flags in-kernel */
   void gather_resolved(const void* batch_slots, const int32_t* lk_batch, P2PState* p2p, int N, float* out, int ldo, const float* X, int Xn, int xoff);
-  /* owner side of the push over peer memory: entries of this step's grads_in / gcnt_in mailboxes (n = R*cap, after
-   * lookup_packed on the same entries) → accumulator rows → the update; waits for the requesters' flags in-kernel */
-  void scatter_update_entries(const P2PState* p2p, int n, int calls, const int* skip_flag);
+  /* owner side of the push over peer memory (n = R*cap, after lookup_packed on the same entries): the update kernel itself
+   * reads every requester's gradient sum and count for each of this shard's keys out of the requester's slab (rank order),
+   * applies the updater, resets the per-batch state; waits for the requesters' flags in-kernel */
+  void update_pull(const P2PState* p2p, int n, int calls, const int* skip_flag);
   /* pre-summed scatter-add, then occurrence normalisation + updater step + per-batch reset (two launches, see table.cu).
    * The ReLU mask comes from the lookup's mask bits (use_mask), from `act` (non-null), or is taken as already applied. */
   void scatter_update(const float* delta, int ldd, const float* act, int lda, int N, int calls, const int* skip_flag, int F_eff = 0, bool use_mask = false);
-  /* requester side of the sharded push: this batch's row gradients summed per unique key into gacc (see table.cu) */
-  void scatter_rows(const void* batch_slots, const int32_t* lk_batch, float* gacc, const float* delta, int ldd, const float* act, int lda, int N);
+  /* requester side of the sharded push: this batch's row gradients summed per unique key into this rank's slab (see table.cu) */
+  void scatter_rows(const void* batch_slots, const int32_t* lk_batch, P2PState* p2p, const float* delta, int ldd, const float* act, int lda, int N);
   /* forget the batch without updating (predict path / early exit): cnt = 0 for touched slots */
   void clear_batch();
   void check_errors();                 /* syncs; throws PS_ERR_CAPACITY if an insert found the table full */

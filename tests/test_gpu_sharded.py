@@ -3,7 +3,6 @@ R ranks, each with a slice of the global batch, must reproduce the CPU oracle's 
 step (thread = 1) on the CONCATENATED batch — loss, dense weights, and the embedding rows held by
 whichever rank owns them.  R = 1 exercises every shard kernel on one GPU; R = 2 needs two."""
 import os
-import socket
 import sys
 
 import numpy as np
@@ -29,9 +28,9 @@ def batches(R, cfg):
 
 def worker(rank, R, port, out, cfg, emb_opt, graphed):
     import torch.distributed as dist
-    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=R, device_id=torch.device("cuda", rank))
+    # file rendezvous: a port picked by bind-and-close can be taken again before rank 0 listens on it (EADDRINUSE, seen on the GPU box)
+    dist.init_process_group("nccl", init_method=f"file://{out}/rendezvous", rank=rank, world_size=R, device_id=torch.device("cuda", rank))
     from ps_b200 import binding as ps
     from ps_b200.sharded import GpuOps, GraphedShardedTrainer, P2PShardedTrainer, ShardedTrainer
     ctx = ps.Context(rank, seed=SEED)
@@ -85,10 +84,7 @@ def test_sharded_step_matches_oracle_global_batch(tmp_path, R, emb_opt, graphed)
         pytest.skip(f"needs {R} GPUs")
     import __graft_entry__ as g
     g.build()
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
+    port = 0
     cfg = CFG
     mp.spawn(worker, args=(R, port, str(tmp_path), cfg, emb_opt, graphed), nprocs=R, join=True)
     res = [torch.load(os.path.join(tmp_path, f"r{r}.pt"), weights_only=False) for r in range(R)]

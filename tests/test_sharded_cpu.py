@@ -4,7 +4,6 @@ the rank-local kernels (this file's FakeOps — test infrastructure, not a produ
 checks: every lookup gets the row its key maps to regardless of which rank owns it; every owner
 sees the GLOBAL occurrence count and gradient sum of its keys; the dense buffer is all-reduced."""
 import os
-import socket
 import sys
 
 import numpy as np
@@ -104,8 +103,7 @@ def global_batch(R):
 
 
 def worker(rank, R, port, out):
-    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=R)
+    dist.init_process_group("gloo", init_method=f"file://{out}/rendezvous", rank=rank, world_size=R)   # no port to lose a race for
     from ps_b200.sharded import ShardedTrainer
     E, X, Y = global_batch(R)
     sl = slice(rank * N, (rank + 1) * N)
@@ -120,10 +118,7 @@ def worker(rank, R, port, out):
 
 @pytest.mark.parametrize("R", [2, 3])
 def test_sharded_step_host_logic(tmp_path, R):
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
+    port = 0
     mp.spawn(worker, args=(R, port, str(tmp_path)), nprocs=R, join=True)
     res = [torch.load(os.path.join(tmp_path, f"r{r}.pt"), weights_only=False) for r in range(R)]
     # single-process reference on the concatenated batch
