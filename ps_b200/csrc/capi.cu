@@ -67,6 +67,10 @@ int ps_ctx_create(int device, uint64_t seed, ps_ctx** out) {
   c->c.pdl = (pd && pd[0] == '0') ? 0 : 1;
   const char* pg = std::getenv("PS_PDL_GEMM");
   c->c.pdl_gemm = (pg && pg[0] == '1') ? 1 : 0;
+  const char* pf = std::getenv("PS_P2P_DEFER");
+  c->c.p2p_defer = pf ? (pf[0] == '0' ? 0 : pf[0] == '1' ? 1 : 2) : 2;
+  const char* px = std::getenv("PS_PDL_EXCHANGE");
+  c->c.pdl_exchange = (px && px[0] == '1') ? 1 : 0;
   const char* xe = std::getenv("PS_EXACT_UPDATERS");
   c->c.exact_updaters = (xe && xe[0] == '1') ? 1 : 0;
   const char* ht = std::getenv("PS_HOT_TMA");
@@ -465,6 +469,7 @@ int ps_model_put(ps_model* m, const char* key, const float* in, int n) {
  * list — go through ONE batched lookup / insert kernel; any other key (dense parameters, wide weights) is served one by one. */
 int ps_model_get_list(ps_model* m, const char* const* keys, int n, float* out, int stride, int32_t* found) {
   PS_TRY
+  if (m) m->m.flush_deferred();
   PS_REQUIRE(m && keys && out && found && n >= 0 && stride > 0, PS_ERR_ARG, "ps_model_get_list: bad argument");
   Model& M = m->m;
   std::vector<int32_t> fields, idx, fnd;
@@ -496,6 +501,7 @@ int ps_model_get_list(ps_model* m, const char* const* keys, int n, float* out, i
 }
 int ps_model_update_list(ps_model* m, const char* const* keys, int n, float* io, int stride, const int32_t* lens, int replace) {
   PS_TRY
+  if (m) m->m.flush_deferred();
   PS_REQUIRE(m && keys && io && lens && n >= 0 && stride > 0, PS_ERR_ARG, "ps_model_update_list: bad argument");
   Model& M = m->m;
   std::vector<int32_t> fields, idx;

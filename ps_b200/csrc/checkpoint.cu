@@ -99,6 +99,7 @@ struct Header {
 }  // namespace
 
 void Model::save(const std::string& path) {
+  flush_deferred();                              /* a sharded step may have left its update to "the next step" */
   PS_REQUIRE(in_flight == 0, PS_ERR_STATE, "save: steps in flight");
   PS_CUDA(cudaStreamSynchronize(ctx->stream));
   /* written beside the target and renamed into place once every byte is on disk: a failed dump never leaves a truncated checkpoint */
@@ -163,6 +164,7 @@ void Model::save(const std::string& path) {
 }
 
 void Model::load(const std::string& path) {
+  flush_deferred();                              /* a sharded step may have left its update to "the next step" */
   PS_REQUIRE(in_flight == 0, PS_ERR_STATE, "load: steps in flight");
   File f(std::fopen(path.c_str(), "rb"));
   PS_REQUIRE(f != nullptr, PS_NOT_FOUND, ("load: cannot open " + path).c_str());

@@ -59,6 +59,13 @@ struct Ctx {
   int pdl_gemm = 0;                /* ... also along the FcLayer forward / dgrad GEMM chain: measured SLOWER at cfg2 (172.8 vs 164.6 us
                                       per step: early CTAs of the next GEMM take the 20 SMs the side-stream wgrad would use), so off
                                       unless PS_PDL_GEMM=1 */
+  int p2p_defer = 2;               /* the sharded step leaves its owner-side embedding update and its dense update to the head of the NEXT sharded step,
+                                      where they run beside that step's route_send (any other use of the model runs them first).  2 (default): only while
+                                      the step is latency-bound (< 16 MB of embedding rows per rank and batch: 2 GPUs, cfg2 210.0 vs 212.6 us and e2e +5.7 %,
+                                      cfg3 365 vs 372 us — but cfg4, 54 MB, 812 vs 792 us: there the update competes with the lookups for HBM);
+                                      PS_P2P_DEFER=1 always, =0 never */
+  int pdl_exchange = 0;            /* PS_PDL_EXCHANGE=1: the sharded step's exchange kernels (route_send -> owner lookup -> gather, scatter_rows -> owner
+                                      update) and the backward's scatter are programmatic dependents of their predecessors */
   int exact_updaters = 0;          /* sparse update with the IEEE divisions / roots of the Java code (PS_EXACT_UPDATERS=1) instead of the fast forms */
   int hot_tma = 1;                 /* the lookup stages rows shared by >= 4 lookups of a warp task in shared memory by TMA bulk copies (PS_HOT_TMA=0: off) */
   int gemm_narrow = 0;             /* PS_GEMM_NARROW=1: 32-column 3xTF32 tiles when 64-column ones leave half the CTA slots empty */
@@ -98,6 +105,18 @@ inline void launch_pdl(Ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = ctx->pdl ? 1 : 0;
+  PS_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+
+/* the same with dynamic shared memory, and the attribute only when `dependent` */
+template <class... KArgs, class... Args>
+inline void launch_dep(Ctx* ctx, bool dependent, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = (dependent && ctx->pdl) ? 1 : 0;
   PS_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
 }
 

@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) dense_update_kernel(const __grid_constant
   size_t slab = L.slab;
   int nsplit = L.nsplit, ldg = L.ldg;
   if (p2p != nullptr) {
-    G = reinterpret_cast<const float*>(p2p_region(p2p, p2p->me, p2p->off_gsum)) + L.first;
+    G = reinterpret_cast<const float*>(p2p_region_of(p2p, p2p->me, p2p->off_gsum, p2p->pub_seq[CH_GSUM])) + L.first;   /* (the step this rank last sent its sums for) */
     slab = (size_t)p2p->glen; nsplit = p2p->R; ldg = cols;
   }
   float g = 0.0f;

@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <exception>
 #include <cstddef>
 #include <cstdlib>
 
@@ -172,16 +173,28 @@ static const float* gbar_ptr(const StepStatus* st) {
 
 void Model::run_step(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, bool train, StepStatus* publish_to, int mode) {
   PS_REQUIRE(N > 0 && N <= Bmax, PS_ERR_ARG, "model: batch size must be in [1, max_batch]");
+  if (mode != 1) flush_deferred();
+  const int consume_N = (mode == 1 && deferred_pending) ? deferred_N : 0;
+  const bool defer = mode == 1 && (ctx->p2p_defer == 1 || (ctx->p2p_defer == 2 && (!has_emb || (size_t)N * F * emb.Dp * sizeof(float) < ((size_t)16 << 20))));
   pending_forward_N = 0;                         /* a forward whose backward never came is forgotten: drop its counts NOW — a cached */
-  if (has_emb && emb.last_L > 0) emb.clear_batch();   /* graph was captured from a clean state and would not */
+  if (has_emb && emb.last_L > 0 && consume_N == 0) emb.clear_batch();   /* graph was captured from a clean state and would not */
+  struct AfterStep {                             /* host-side state a REPLAYED graph cannot set */
+    Model* m; int mode, N; bool defer;
+    ~AfterStep() {
+      if (mode != 1 || std::uncaught_exceptions() > 0) return;
+      m->deferred_pending = defer; m->deferred_N = N;
+      if (m->has_emb) m->emb.last_L = defer ? (int64_t)m->p2p.R * m->p2p.cap : 0;
+    }
+  } after{this, mode, N, defer};
   if (!use_graph) {
     ev_n = 0; ev_names.clear();
-    if (mode == 1) { p2p_step(E, X, W, Y, N); if (publish_to) publish_status(ctx, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, publish_to); }
+    if (mode == 1) { p2p_step(E, X, W, Y, N, consume_N, defer); if (publish_to) publish_status(ctx, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, publish_to); }
     else step_device(E, X, W, Y, N, train, publish_to);
     phase_names = ev_names;
     return;
   }
-  const auto key = std::make_tuple((const void*)E, (const void*)X, (const void*)W, (const void*)Y, N, (train ? 1 : 0) | (profile ? 2 : 0) | (mode << 2) | (ctx->exact_updaters << 6),
+  const auto key = std::make_tuple((const void*)E, (const void*)X, (const void*)W, (const void*)Y, N,
+                                   (train ? 1 : 0) | (profile ? 2 : 0) | (mode << 2) | (ctx->exact_updaters << 6) | ((defer ? 1 : 0) << 7) | (consume_N << 8),
                                    (const void*)publish_to, ctx->fc_precision);
   if (has_emb && emb.generation != emb_generation) {     /* the embedding workspace was reallocated (p2p_init, a larger shard lookup) */
     for (auto& g : graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
@@ -199,7 +212,7 @@ void Model::run_step(const int64_t* E, const float* X, const int64_t* W, const f
     PS_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
     capturing = true; ev_n = 0; ev_names.clear();
     try {
-      if (mode == 1) { p2p_step(E, X, W, Y, N); if (publish_to) publish_status(ctx, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, publish_to); }
+      if (mode == 1) { p2p_step(E, X, W, Y, N, consume_N, defer); if (publish_to) publish_status(ctx, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, publish_to); }
       else step_device(E, X, W, Y, N, train, publish_to);
     }
     catch (...) { capturing = false; cudaStreamEndCapture(ctx->stream, &graph); if (graph) cudaGraphDestroy(graph); throw; }
@@ -419,11 +432,13 @@ DenseUpdateArgs Model::dense_args(int N) {
 }
 
 void Model::shard_emb_lookup(const uint64_t* keys, int n, float* rows_out) {
+  flush_deferred();                              /* a sharded step may have left its update to "the next step" */
   PS_REQUIRE(has_emb, PS_ERR_STATE, "model has no embedding layer");
   emb.lookup_packed(keys, n, rows_out);
 }
 
 void Model::shard_unpack_rows(const float* rows, const int32_t* send_pos, int N) {
+  flush_deferred();                              /* a sharded step may have left its update to "the next step" */
   PS_REQUIRE(has_emb && N > 0 && N <= Bmax, PS_ERR_ARG, "shard_unpack_rows: bad batch");
   shard_unpack(ctx, rows, send_pos, N, F, D, emb.Dp, act[0], ld[0]);
 }
@@ -431,6 +446,7 @@ void Model::shard_unpack_rows(const float* rows, const int32_t* send_pos, int N)
 /* everything between the two exchanges: concat, wide branch, FcLayer forward, tail, FcLayer backward,
  * then the per-rank gradient sums and scalars go into ONE flat buffer for the all-reduce.      */
 void Model::shard_dense_step(const float* X, const int64_t* W_local, const int64_t* W_all, int n_all, const float* Y, int N) {
+  flush_deferred();                              /* a sharded step may have left its update to "the next step" */
   PS_REQUIRE(N > 0 && N <= Bmax, PS_ERR_ARG, "model: batch size must be in [1, max_batch]");
   cudaStream_t s = ctx->stream, s1 = aux[0], s2 = aux[1];
   fork(s, s1);
@@ -451,6 +467,7 @@ void Model::shard_dense_step(const float* X, const int64_t* W_local, const int64
 }
 
 void Model::shard_pack(const int32_t* send_pos, int N, float* grads_send) {
+  flush_deferred();                              /* a sharded step may have left its update to "the next step" */
   PS_REQUIRE(has_emb, PS_ERR_STATE, "model has no embedding layer");
   shard_pack_grads(ctx, delta[0], ld[0], act[0], ld[0], send_pos, N, F, D, emb.Dp, grads_send);
 }
@@ -458,6 +475,7 @@ void Model::shard_pack(const int32_t* send_pos, int N, float* grads_send) {
 /* gsum now holds the SUM over R ranks of per-rank batch sums / means: every replica applies the
  * same global-batch update — N-GPU result == 1-GPU result on the concatenated batch */
 void Model::shard_finish(int N_global, int R) {
+  flush_deferred();                              /* a sharded step may have left its update to "the next step" */
   PS_REQUIRE(gsum != nullptr, PS_ERR_STATE, "shard_finish before shard_dense_step");
   DenseUpdateArgs u = dense_args(N_global);
   shard_finish_scalars(ctx, st_dev, gsum + u.total, R);
@@ -467,6 +485,7 @@ void Model::shard_finish(int N_global, int R) {
 }
 
 void Model::shard_emb_apply(const float* grads_recv, int n) {
+  flush_deferred();                              /* a sharded step may have left its update to "the next step" */
   PS_REQUIRE(has_emb, PS_ERR_STATE, "model has no embedding layer");
   if (n > 0) emb.scatter_update(grads_recv, emb.Dp, nullptr, emb.Dp, n, 2, skip_ptr(st_dev), 1);
   else emb.last_L = 0;
@@ -474,6 +493,7 @@ void Model::shard_emb_apply(const float* grads_recv, int n) {
 
 /* ------------------------------------------------------------------ sharded step over peer memory */
 void Model::p2p_init(int R, int rank, int cap, void* handle_out64) {
+  flush_deferred();                              /* a sharded step may have left its update to "the next step" */
   PS_REQUIRE(!p2p.slab, PS_ERR_STATE, "p2p already initialised");
   const DenseUpdateArgs u = dense_args(1);
   const long glen = (u.total + 3 + 3) / 4 * 4;
@@ -488,12 +508,38 @@ void Model::p2p_connect(const void* all_handles) { p2p.connect(all_handles); }
 
 /* one Trainer step of the R-rank group on the concatenated batch, this rank's share: every exchange is a
  * store into the consumer's mailbox by the kernel that produced the data (see p2p.cuh)              */
-void Model::p2p_step(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N) {
+void Model::flush_deferred() {
+  if (!deferred_pending) return;
+  deferred_pending = false;
+  const int R = p2p.R;
+  if (has_emb) emb.update_pull(p2p.state(), R * p2p.cap, 2, skip_ptr(st_dev));
+  const DenseUpdateArgs u = dense_args(deferred_N * R);
+  p2p.wait(CH_GSUM);
+  dense_update(ctx, u, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, nullptr, p2p.state());
+}
+
+void Model::p2p_step(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, int consume_N, bool defer) {
   PS_REQUIRE(p2p.connected, PS_ERR_STATE, "p2p_step before p2p_connect");
   PS_REQUIRE(N > 0 && N <= Bmax, PS_ERR_ARG, "model: batch size must be in [1, max_batch]");
   cudaStream_t s = ctx->stream, s1 = aux[0], s2 = aux[1];
   const int R = p2p.R, cap = p2p.cap;
   mark("begin");
+  cudaEvent_t dense_done = nullptr;
+  if (consume_N > 0) {
+    /* the previous sharded step's owner-side embedding update (PServer.push + psUpdate) and dense update, beside this step's route_send:
+     * they wait for the flags of THAT step (P2PState::pub_seq) and read nothing this step's first kernels write */
+    fork(s, s2);
+    if (has_emb) { StreamScope sc(ctx, s2); emb.update_pull(p2p.state(), R * cap, 2, skip_ptr(st_dev)); }
+    fork(s, s1);
+    {
+      StreamScope sc(ctx, s1);
+      const DenseUpdateArgs u = dense_args(consume_N * R);
+      p2p.wait(CH_GSUM);                                                        /* every replica's sums have landed */
+      dense_update(ctx, u, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, nullptr, p2p.state());
+      dense_done = sync_ev[sync_n++ % 24];
+      PS_CUDA(cudaEventRecord(dense_done, s1));                                 /* (waited for just before the first FcLayer: the wide branch follows on s1) */
+    }
+  }
   /* every exchange below is ONE producer kernel that flags its consumers when its last block ends and ONE consumer kernel
    * that waits for the flags in its prologue: no flag kernels, no send kernels on the way back, no host */
   if (has_emb) {
@@ -513,6 +559,7 @@ void Model::p2p_step(const int64_t* E, const float* X, const int64_t* W, const f
   if (has_emb) {
     fork(s, s2);
     { StreamScope sc(ctx, s2); p2p.counts(); }                                  /* the keys' occurrence counts next to where their gradient sums will be */
+    if (consume_N > 0) fork(s2, s);                                             /* the previous step's rows are updated, its batch forgotten */
     emb.lookup_packed(nullptr, R * cap, nullptr, p2p.dev, true);                /* PServer.getList on the owner: find-or-insert, rows stored straight into the requesters' mailboxes */
     mark("owner_lookup");
     if (D % 4 == 0) emb.gather_resolved(p2p.bt, p2p.lk_b, p2p.dev, N, act[0], ld[0], X, Xn, F * D);   /* rows_in -> concat buffer (+ mask bits, ConcatLayer) */
@@ -521,6 +568,7 @@ void Model::p2p_step(const int64_t* E, const float* X, const int64_t* W, const f
   } else {
     PS_CUDA(cudaMemcpy2DAsync(act[0], sizeof(float) * ld[0], X, sizeof(float) * Xn, sizeof(float) * Xn, N, cudaMemcpyDeviceToDevice, s));
   }
+  if (dense_done != nullptr) PS_CUDA(cudaStreamWaitEvent(s, dense_done, 0));    /* the previous step's dense update */
   p2p_scalars_now = true;
   try { forward_backward(W, nullptr, 0, Y, N, true, false); }                   /* main: delta[0]; side 1: the wgrads; side 2: the global scalars + wide update */
   catch (...) { p2p_scalars_now = false; throw; }
@@ -533,8 +581,10 @@ void Model::p2p_step(const int64_t* E, const float* X, const int64_t* W, const f
     StreamScope sc(ctx, s1);
     const DenseUpdateArgs u = dense_args(N * R);
     dense_reduce_send(ctx, u, st_dev, p2p.dev, has_emb ? emb.counters : nullptr);
-    p2p.wait(CH_GSUM);                                                          /* every replica's sums have landed */
-    dense_update(ctx, u, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, nullptr, p2p.state());
+    if (!defer) {
+      p2p.wait(CH_GSUM);                                                        /* every replica's sums have landed */
+      dense_update(ctx, u, st_dev, has_emb ? emb.counters : nullptr, has_wide ? wide.counters : nullptr, nullptr, p2p.state());
+    }
   }
   /* s2 carries, in order: the counts, the global scalars + wide update (forward_backward) */
   fork(s2, s);                                                                  /* the counts are in place; the global skip flag — NOT the weight gradients */
@@ -543,8 +593,10 @@ void Model::p2p_step(const int64_t* E, const float* X, const int64_t* W, const f
     mark("scatter_rows");
     fork(s, s2);
     { StreamScope sc(ctx, s2); p2p.tidy(); }                                    /* beside the update: forget the batch's de-duplication, zero the other parity's sums */
-    emb.update_pull(p2p.state(), R * cap, 2, skip_ptr(st_dev));                 /* PServer.push (sync mode) + psUpdate on the owner: reads the requesters' sums over NVLink */
-    mark("owner_update");
+    if (!defer) {
+      emb.update_pull(p2p.state(), R * cap, 2, skip_ptr(st_dev));               /* PServer.push (sync mode) + psUpdate on the owner: reads the requesters' sums over NVLink */
+      mark("owner_update");
+    }
   }
   fork(s1, s);                                                                  /* the dense update */
   fork(s2, s);                                                                  /* the tidy */
@@ -553,6 +605,7 @@ void Model::p2p_step(const int64_t* E, const float* X, const int64_t* W, const f
 }
 
 void Model::kernel_times(const int64_t* const* E_ring, int n_ring, int N, int reps, float* out) {
+  flush_deferred();                              /* a sharded step may have left its update to "the next step" */
   PS_REQUIRE(has_emb && n_ring > 0 && reps > 0 && N > 0 && N <= Bmax, PS_ERR_ARG, "kernel_times: bad argument");
   PS_REQUIRE(in_flight == 0, PS_ERR_STATE, "kernel_times: steps in flight");
   cudaStream_t s = ctx->stream;
@@ -596,6 +649,7 @@ void Model::kernel_times(const int64_t* const* E_ring, int n_ring, int N, int re
 }
 
 void Model::gemm_times(int N, int reps, float* out) {
+  flush_deferred();                              /* a sharded step may have left its update to "the next step" */
   PS_REQUIRE(reps > 0 && N > 0 && N <= Bmax, PS_ERR_ARG, "gemm_times: bad argument");
   PS_REQUIRE(in_flight == 0, PS_ERR_STATE, "gemm_times: steps in flight");
   cudaStream_t s = ctx->stream;
@@ -688,6 +742,7 @@ float Model::read_loss() {
  * Java's loss.backward produced — dLoss/dP, BEFORE the output activation's derivative, exactly what setDelta receives — and runs
  * the reverse loop and the update.  No label ever crosses the boundary.                                                    */
 void Model::forward_host(const HostBatch& b, float* P_out) {
+  flush_deferred();                              /* a sharded step may have left its update to "the next step" */
   PS_REQUIRE(in_flight == 0, PS_ERR_STATE, "model: steps in flight; collect first");
   PS_REQUIRE(b.N > 0 && b.N <= Bmax, PS_ERR_ARG, "model: batch size must be in [1, max_batch]");
   PS_REQUIRE(b.X && P_out && (!has_emb || b.E) && (!has_wide || b.W), PS_ERR_ARG, "model: missing input matrix");
@@ -714,6 +769,7 @@ void Model::forward_host(const HostBatch& b, float* P_out) {
 }
 
 void Model::backward_update_host(const float* delta_top, int N, float loss) {
+  flush_deferred();                              /* a sharded step may have left its update to "the next step" */
   PS_REQUIRE(pending_forward_N > 0 && N == pending_forward_N, PS_ERR_STATE, "backward_update without a matching forward");
   PS_REQUIRE(delta_top != nullptr, PS_ERR_ARG, "backward_update: null delta");
   Stage& S = stage[0];
@@ -784,6 +840,7 @@ void Model::submit_text(const char* text, size_t len, int N, int mode) {
 }
 
 void Model::predict(const HostBatch& b, float* out) {
+  flush_deferred();                              /* a sharded step may have left its update to "the next step" */
   PS_REQUIRE(in_flight == 0, PS_ERR_STATE, "model: steps in flight; collect first");
   PS_REQUIRE(b.N > 0 && b.N <= Bmax, PS_ERR_ARG, "model: batch size must be in [1, max_batch]");
   Stage& S = stage[0];
@@ -851,6 +908,7 @@ static void fetch_fc(Ctx* ctx, const FcLayer& f, bool is_bias, const float* Wsrc
 }
 
 int Model::get(const std::string& key, std::vector<float>& out) {
+  flush_deferred();                              /* a sharded step may have left its update to "the next step" */
   int field = 0; int64_t id = 0; int l = 0; bool is_bias = false;
   const int k = parse_key(key, &field, &id);
   if (k == 0) {
@@ -876,6 +934,7 @@ int Model::get(const std::string& key, std::vector<float>& out) {
 }
 
 int Model::get_state(const std::string& key, int which, std::vector<float>& out) {
+  flush_deferred();                              /* a sharded step may have left its update to "the next step" */
   int field = 0; int64_t id = 0; int l = 0; bool is_bias = false;
   const int k = parse_key(key, &field, &id);
   if (k == 0) {
@@ -908,6 +967,7 @@ int Model::get_state(const std::string& key, int which, std::vector<float>& out)
 }
 
 void Model::put(const std::string& key, const float* in, int n) {
+  flush_deferred();                              /* a sharded step may have left its update to "the next step" */
   int field = 0; int64_t id = 0; int l = 0; bool is_bias = false;
   const int k = parse_key(key, &field, &id);
   if (k == 0) {
@@ -964,6 +1024,7 @@ static void fetch_cols(Ctx* ctx, const float* src, int ldsrc, int cols, int N, s
  * updates: fc<l>.delta = W_l^T d_l, later multiplied in place by the activation derivative of
  * fc<l-1> (FcLayer.java:100-102 acting on next.delta).                                         */
 int Model::tap(const std::string& layer, int what, std::vector<float>& out) {
+  flush_deferred();                              /* a sharded step may have left its update to "the next step" */
   const int N = last_N;
   if (N <= 0) return PS_NOT_FOUND;
   if (what == 1 && !last_train) return PS_NOT_FOUND;
@@ -981,6 +1042,7 @@ int Model::tap(const std::string& layer, int what, std::vector<float>& out) {
 }
 
 int64_t Model::num_keys() {
+  flush_deferred();                              /* a sharded step may have left its update to "the next step" */
   int64_t n = 2 * (int64_t)L;
   if (has_emb) n += emb.size();
   if (has_wide) n += wide.size() + 1;

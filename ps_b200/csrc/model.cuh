@@ -138,7 +138,11 @@ struct Model {
   int32_t* send_pos = nullptr;
   void p2p_init(int R, int rank, int cap, void* handle_out64);
   void p2p_connect(const void* all_handles);
-  void p2p_step(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N);
+  /* consume_N > 0: the previous sharded step (of consume_N samples per rank) left its owner-side embedding update and its dense update
+   * to this one; defer: this step leaves its own to the next */
+  void p2p_step(const int64_t* E, const float* X, const int64_t* W, const float* Y, int N, int consume_N, bool defer);
+  bool deferred_pending = false; int deferred_N = 0;
+  void flush_deferred();             /* runs a pending deferred update now (every entry point that is not a sharded step calls it first) */
   void submit(const HostBatch& b, int mode = 0);     /* mode 1: the peer-memory sharded step (this rank's slice of the global batch) */
   float collect();
   float read_loss();

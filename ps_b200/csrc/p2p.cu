@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(256) p2p_route_send_kernel(P2PState* st, Batch
   const int lane = threadIdx.x & 31;
   const int R = st->R, cap = st->cap;
   const int N = L / F;
+  pdl_launch_dependents();                       /* the owner-side lookup may be scheduled: it waits for this grid's completion before it reads seq */
   const uint32_t seq = *reinterpret_cast<const volatile uint32_t*>(&st->seq) + 1u;
   int32_t* cursor = st->cursor[seq & 1u];
   __shared__ int s_cnt[kP2PMaxRanks], s_base[kP2PMaxRanks];
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(256) p2p_route_send_kernel(P2PState* st, Batch
     p2p_block_fence(st);
     const uint32_t tk = atomicAdd(&st->ticket[CH_KEYS], 1u);
     s_last = tk == gridDim.x - 1u;
-    if (s_last) { st->ticket[CH_KEYS] = 0u; st->seq = seq; }
+    if (s_last) { st->ticket[CH_KEYS] = 0u; st->seq = seq; st->pub_seq[CH_KEYS] = seq; }
   }
   __syncthreads();
   if (s_last && (int)threadIdx.x < R) {
@@ -265,7 +266,7 @@ void P2P::destroy() {
 
 /* a one-warp wait on side streams whose consumer kernel has a large grid: 900 spinning blocks would hold every SM's thread slots
  * against the main stream's kernels, one warp holds none */
-__global__ void p2p_wait_kernel(const P2PState* st, int channel) { p2p_wait_all(st, channel); }
+__global__ void p2p_wait_kernel(const P2PState* st, int channel) { p2p_wait_all_seq(st, channel, st->pub_seq[channel]); }
 void P2P::wait(int channel) { p2p_wait_kernel<<<1, 32, 0, ctx->stream>>>(dev, channel); P2P_LAUNCHED(); }
 
 void P2P::begin() { p2p_begin_kernel<<<1, 32, 0, ctx->stream>>>(dev); P2P_LAUNCHED(); }

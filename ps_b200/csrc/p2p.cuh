@@ -42,6 +42,8 @@ struct P2PState {                      /* lives in device memory; kernels read i
   int32_t cursor[2][kP2PMaxRanks];     /* by parity: unique keys of this rank's batch per owner (final when route_send ends; zeroed by the NEXT step's tidy) */
   uint32_t ticket[CH_COUNT];           /* blocks of the running producer kernel of each channel that have finished */
   uint32_t tidy_ticket;
+  uint32_t pub_seq[CH_COUNT];          /* the sequence number this rank last published on each channel: what a DEFERRED consumer (the owner update and
+                                          the dense update of step t may run at the head of step t+1, beside its route_send, which moves seq on) works with */
   int32_t overflow;
   int32_t block_fence_sys;             /* 1: every block of a producer fences at system scope before its ticket (PS_P2P_BLOCK_FENCE_SYS=1); default 0, see p2p_publish_last */
 };
@@ -76,7 +78,7 @@ struct P2P {
   void route_send(const int64_t* E, int N, int F);                                  /* seq + 1; de-duplicate, reserve, store each key into its owner's keys_in; publishes seq and CH_KEYS */
   void counts();                                                                    /* side stream, after route_send: gcnt[q] = occurrences of the q-th unique key */
   void tidy();                                                                      /* side stream, after the backward's scatter: clears the de-duplication table; zeroes the OTHER parity's gsums */
-  void wait(int channel);                                                           /* one-warp consumer-side wait (before a large-grid consumer on a side stream) */
+  void wait(int channel);                                                           /* one-warp consumer-side wait for the step this rank last published on the channel */
   void bcast(const void* src, size_t bytes, int channel);                           /* wide ids → every peer; publishes the channel */
   void unpack(int N, int F, int D, float* out, int ldo, const float* X, int Xn, int xoff);   /* rows_in (+ X) → concat buffer */
   void reduce_gsum(float* gsum);                                                    /* sum over ranks, fixed order */
@@ -134,20 +136,21 @@ __device__ __forceinline__ bool p2p_publish_last(P2PState* st, int channel, uint
   __syncthreads();
   if (s_last && (int)threadIdx.x < st->R) {
     const int r = threadIdx.x;
+    if (r == 0) st->pub_seq[channel] = st->seq;
     __threadfence_system();
     p2p_st_release_sys(reinterpret_cast<uint32_t*>(p2p_region(st, r, st->off_flags)) + channel * kP2PMaxRanks + st->me, st->seq);
   }
   return s_last;
 }
 /* Consumer side, called by EVERY thread of a block before it reads the channel's mailbox */
-__device__ __forceinline__ void p2p_wait_all(const P2PState* st, int channel) {
+__device__ __forceinline__ void p2p_wait_all_seq(const P2PState* st, int channel, uint32_t seq) {
   if ((int)threadIdx.x < st->R) {
-    const uint32_t* f = reinterpret_cast<const uint32_t*>(p2p_region(st, st->me, st->off_flags)) + channel * kP2PMaxRanks + threadIdx.x;
-    const uint32_t seq = st->seq;
+    const uint32_t* f = reinterpret_cast<const uint32_t*>(p2p_region_of(st, st->me, st->off_flags, seq)) + channel * kP2PMaxRanks + threadIdx.x;
     while ((int32_t)(p2p_ld_acquire_sys(f) - seq) < 0) __nanosleep(20);
   }
   __syncthreads();
 }
+__device__ __forceinline__ void p2p_wait_all(const P2PState* st, int channel) { p2p_wait_all_seq(st, channel, st->seq); }
 #endif
 
 }  // namespace psb

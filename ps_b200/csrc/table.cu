@@ -179,6 +179,9 @@ template <class IdT, bool GATHER, int TPL, bool ALIGNED>
 __global__ void __launch_bounds__(256) emb_lookup_kernel(const __grid_constant__ LookupArgs a) {
   extern __shared__ __align__(128) unsigned char lookup_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  /* owner side of the exchange, launched as a programmatic dependent of route_send: that grid must be complete (it publishes the
+   * step's sequence number last).  Only then are this kernel's own dependents released, so whatever follows also runs after it. */
+  if (a.p2p != nullptr && a.pre_lk == nullptr) pdl_wait();
   pdl_launch_dependents();
   if ((int)blockIdx.x >= a.task_blocks) {          /* ConcatLayer.forward (ConcatLayer.java:30-37): numeric features next to the embeddings */
     const long base = (long)((int)blockIdx.x - a.task_blocks) * 1024 + threadIdx.x;
@@ -456,6 +459,7 @@ __global__ void __launch_bounds__(256) emb_scatter_kernel(const EmbSlot* __restr
 
   for (int i = threadIdx.x; i < kHotEntries; i += 256) hot_slot[i] = -1;
   for (int i = threadIdx.x; i < kHotEntries * ROWF; i += 256) (&hot_acc[0][0])[i] = 0.f;
+  pdl_wait();                                    /* (as a programmatic dependent of the last dgrad: delta is complete from here on) */
   __syncthreads();
 
   /* the block's tile: SB consecutive samples x all F fields; a warp task = (field j, GPW consecutive samples); the 8 warps
@@ -609,6 +613,7 @@ __global__ void __launch_bounds__(256) emb_scatter_slab_kernel(const EmbSlot* __
   uint32_t* maskw = maskw_all + warp * 32 * 4;
   for (int i = threadIdx.x; i < kHotEntries; i += 256) hot_slot[i] = -1;
   for (int i = threadIdx.x; i < kHotEntries * Dp; i += 256) hot_acc[i] = 0.f;
+  pdl_wait();                                    /* (as a programmatic dependent of the last dgrad: delta is complete from here on) */
   __syncthreads();
 
   const long ntasks = (long)((N + 31) / 32) * F;
@@ -842,7 +847,10 @@ __global__ void __launch_bounds__(256) emb_update_slab_kernel(EmbSlot* __restric
   };
   bool have = wi < rounds;
   if (have) fetch_records(wi);                     /* before the scatter kernel is known to be complete */
-  if (PULL) p2p_wait_all(p2p, CH_GRADS);           /* every requester's sums (and counts) of this step are final */
+  /* the step this rank last published its own sums for — when the update is deferred to the head of the next step, that step's
+   * route_send may already have moved seq on */
+  const uint32_t pseq = PULL ? p2p->pub_seq[CH_GRADS] : 0u;
+  if (PULL) p2p_wait_all_seq(p2p, CH_GRADS, pseq);   /* every requester's sums (and counts) of that step are final */
   else pdl_wait();
   while (have) {
     const long u = wi * kUpdKeys + lane;
@@ -869,7 +877,7 @@ __global__ void __launch_bounds__(256) emb_update_slab_kernel(EmbSlot* __restric
           for (int r = 0; r < kP2PMaxRanks; ++r) {   /* every requester's load is issued before the first is consumed */
             const int pos = r < R ? kpos[k * kP2PMaxRanks + r] : -1;
             v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (pos >= 0) v[r] = p2p_ld_sys_f4(reinterpret_cast<const float*>(p2p_region(p2p, r, p2p->off_grads)) + ((size_t)me * cap + pos) * Dp + cc);
+            if (pos >= 0) v[r] = p2p_ld_sys_f4(reinterpret_cast<const float*>(p2p_region_of(p2p, r, p2p->off_grads, pseq)) + ((size_t)me * cap + pos) * Dp + cc);
           }
           float4 S = v[0];
 #pragma unroll
@@ -881,7 +889,7 @@ __global__ void __launch_bounds__(256) emb_update_slab_kernel(EmbSlot* __restric
           if (slot >= 0)
             for (int r = 0; r < R; ++r) {
               const int pos = kpos[lane * kP2PMaxRanks + r];
-              if (pos >= 0) n += p2p_ld_sys_u32(reinterpret_cast<const uint32_t*>(p2p_region(p2p, r, p2p->off_gcnt)) + (size_t)me * cap + pos);
+              if (pos >= 0) n += p2p_ld_sys_u32(reinterpret_cast<const uint32_t*>(p2p_region_of(p2p, r, p2p->off_gcnt, pseq)) + (size_t)me * cap + pos);
             }
           kcnt[lane] = n;
         }
@@ -1038,10 +1046,15 @@ void EmbTable::destroy() {
 
 template <class IdT, int TPL>
 static void launch_lookup_t(EmbTable& t, LookupArgs& a, bool gather, bool aligned, int grid, size_t smem) {
-  cudaStream_t st = t.ctx->stream;
-  if (!gather) emb_lookup_kernel<IdT, false, 1, true><<<grid, 256, 0, st>>>(a);
-  else if (aligned) emb_lookup_kernel<IdT, true, TPL, true><<<grid, 256, smem, st>>>(a);
-  else emb_lookup_kernel<IdT, true, TPL, false><<<grid, 256, smem, st>>>(a);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = gather ? smem : 0; cfg.stream = t.ctx->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = (a.p2p != nullptr && t.ctx->pdl && t.ctx->pdl_exchange) ? 1 : 0;   /* the exchange's lookups order themselves by flags */
+  if (!gather) PS_CUDA(cudaLaunchKernelEx(&cfg, emb_lookup_kernel<IdT, false, 1, true>, a));
+  else if (aligned) PS_CUDA(cudaLaunchKernelEx(&cfg, emb_lookup_kernel<IdT, true, TPL, true>, a));
+  else PS_CUDA(cudaLaunchKernelEx(&cfg, emb_lookup_kernel<IdT, true, TPL, false>, a));
 }
 
 template <class IdT>
@@ -1134,10 +1147,11 @@ static void launch_scatter(EmbTable& t, const ScatterJob& j) {
   /* a key is pre-summed per block when it is frequent enough to recur among the samples one block sees */
   const long per_block = (long)SB * ceil_div(ceil_div(N, SB), grid);
   const uint32_t hot_min = t.ctx->hot_min == 0xFFFFFFFFu ? 0xFFFFFFFFu : std::max<uint32_t>(t.ctx->hot_min, (uint32_t)(2L * N / per_block));
+  const bool dep = t.ctx->pdl_exchange != 0;
   if (aligned)
-    emb_scatter_kernel<TPL, CPL, PASSES, true><<<grid, 256, 0, t.ctx->stream>>>(j.recs, t.Dp, t.D, j.lk, j.mask, t.MW, N, j.F, SB, j.delta, j.ldd, j.act, j.lda, j.accp, j.skip, j.raw_row, hot_min, j.pub);
+    launch_dep(t.ctx, dep, emb_scatter_kernel<TPL, CPL, PASSES, true>, dim3(grid), dim3(256), 0, j.recs, t.Dp, t.D, j.lk, j.mask, t.MW, N, j.F, SB, j.delta, j.ldd, j.act, j.lda, j.accp, j.skip, j.raw_row, hot_min, j.pub);
   else
-    emb_scatter_kernel<TPL, CPL, PASSES, false><<<grid, 256, 0, t.ctx->stream>>>(j.recs, t.Dp, t.D, j.lk, j.mask, t.MW, N, j.F, SB, j.delta, j.ldd, j.act, j.lda, j.accp, j.skip, j.raw_row, hot_min, j.pub);
+    launch_dep(t.ctx, dep, emb_scatter_kernel<TPL, CPL, PASSES, false>, dim3(grid), dim3(256), 0, j.recs, t.Dp, t.D, j.lk, j.mask, t.MW, N, j.F, SB, j.delta, j.ldd, j.act, j.lda, j.accp, j.skip, j.raw_row, hot_min, j.pub);
   PS_LAUNCH_CHECK();
   t.ctx->launches++;
 }
@@ -1155,7 +1169,7 @@ static void launch_scatter_slab(EmbTable& t, const ScatterJob& j) {
   const int grid = (int)std::max<long>(1, std::min<long>(ceil_div(ntasks, 8), (long)t.ctx->num_sms * std::max(1, t.scatter_slab_occ)));
   const long per_block = 32L * ceil_div(ntasks, (long)grid * 8) * 8 / std::max(1, j.F) + 32;      /* samples of one field a block sees */
   const uint32_t hot_min = t.ctx->hot_min == 0xFFFFFFFFu ? 0xFFFFFFFFu : std::max<uint32_t>(t.ctx->hot_min, (uint32_t)(2L * j.N / per_block));
-  emb_scatter_slab_kernel<TPL><<<grid, 256, smem, t.ctx->stream>>>(j.recs, t.Dp, t.D, j.lk, j.mask, t.MW, j.N, j.F, j.delta, j.ldd, j.accp, j.skip, j.raw_row, hot_min, j.pub);
+  launch_dep(t.ctx, t.ctx->pdl_exchange != 0, emb_scatter_slab_kernel<TPL>, dim3(grid), dim3(256), smem, j.recs, t.Dp, t.D, j.lk, j.mask, t.MW, j.N, j.F, j.delta, j.ldd, j.accp, j.skip, j.raw_row, hot_min, j.pub);
   PS_LAUNCH_CHECK();
   t.ctx->launches++;
 }
@@ -1212,10 +1226,12 @@ static void launch_update(EmbTable& t, long L, int calls, const int* skip, const
     if (pull != nullptr) {                       /* an ordinary launch: the kernel's own flag wait orders it behind the requesters */
       const long rounds = ceil_div(L, kUpdKeys);
       const int ugrid = (int)std::max<long>(1, std::min<long>(ceil_div(rounds, 8), (long)t.ctx->num_sms * std::max(1, t.update_pull_occ)));
+      /* (optionally a programmatic dependent of the scatter: it may start while that drains — it reads nothing of it before the flags) */
+      const bool dep = t.ctx->pdl_exchange != 0;
       if (t.ctx->exact_updaters)
-        emb_update_slab_kernel<true, true><<<ugrid, 256, smem, t.ctx->stream>>>(t.slots, t.rows, t.rs, t.Dp, t.D, (const int32_t*)t.uniq, nullptr, t.upd, calls, skip, t.counters, (const int32_t*)t.chain, pull);
+        launch_dep(t.ctx, dep, emb_update_slab_kernel<true, true>, dim3(ugrid), dim3(256), smem, t.slots, t.rows, t.rs, t.Dp, t.D, (const int32_t*)t.uniq, (float*)nullptr, t.upd, calls, skip, t.counters, (const int32_t*)t.chain, pull);
       else
-        emb_update_slab_kernel<false, true><<<ugrid, 256, smem, t.ctx->stream>>>(t.slots, t.rows, t.rs, t.Dp, t.D, (const int32_t*)t.uniq, nullptr, t.upd, calls, skip, t.counters, (const int32_t*)t.chain, pull);
+        launch_dep(t.ctx, dep, emb_update_slab_kernel<false, true>, dim3(ugrid), dim3(256), smem, t.slots, t.rows, t.rs, t.Dp, t.D, (const int32_t*)t.uniq, (float*)nullptr, t.upd, calls, skip, t.counters, (const int32_t*)t.chain, pull);
       PS_LAUNCH_CHECK();
       t.ctx->launches++;
       return;
