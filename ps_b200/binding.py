@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(ROOT, "ps_b200", "lib", "libps_b200.so")
+LIB_PATH = os.environ.get("PS_B200_LIB") or os.path.join(ROOT, "ps_b200", "lib", "libps_b200.so")   # (the override is for A/B builds of one kernel)
 
 PS_OK, PS_NOT_FOUND = 0, 204
 PS_FC_FP32, PS_FC_TF32, PS_FC_TF32X3 = 0, 1, 2

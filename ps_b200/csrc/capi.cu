@@ -75,6 +75,10 @@ int ps_ctx_create(int device, uint64_t seed, ps_ctx** out) {
   c->c.exact_updaters = (xe && xe[0] == '1') ? 1 : 0;
   const char* ht = std::getenv("PS_HOT_TMA");
   c->c.hot_tma = (ht && ht[0] == '0') ? 0 : 1;
+  const char* td = std::getenv("PS_TC_DEEP");
+  if (td && td[0] >= '0' && td[0] <= '2') c->c.tc_deep = td[0] - '0';
+  const char* tw = std::getenv("PS_TC_DEEP_WGRAD");
+  if (tw && tw[0] >= '0' && tw[0] <= '2') c->c.tc_deep_wgrad = tw[0] - '0';
   const char* gn = std::getenv("PS_GEMM_NARROW");
   c->c.gemm_narrow = (gn && gn[0] == '1') ? 1 : 0;
   const char* gw = std::getenv("PS_GROUP_WGRAD");

@@ -38,9 +38,12 @@ constexpr int BM = 128, BK = 32, UMMA_K = 8;
 /* 3xTF32 tiles up to 64 columns run TWO CTAs per SM (2 stages of 48 KB each, <= 128 registers): a 128-CTA GEMM no longer owns the GPU,
  * so the weight-gradient GEMM on the side stream genuinely overlaps the dgrad chain, and one CTA's TMA latency / epilogue hides
  * behind the other's MMAs */
-template <int BLOCK_N, bool SPLIT> struct Depth {
-  static constexpr int STAGES = SPLIT ? (BLOCK_N > 64 ? 3 : 2) : (BLOCK_N > 64 ? 6 : 8);
-  static constexpr int MIN_CTAS = (SPLIT && BLOCK_N <= 64) ? 2 : 1;
+/* DEEP: the same tiles with FOUR stages and one CTA per SM — for grids that fit one wave at one CTA per SM anyway (a 128-CTA GEMM at
+ * batch 4096: the second CTA slot stays empty and two stages leave the TMA latency of 8 k-blocks exposed: cfg2 159.2 -> 151.7 us per step)
+ * and for the weight-gradient GEMMs, whose K loop is the batch.  Chosen per launch (dispatch_tc, PS_TC_DEEP / PS_TC_DEEP_WGRAD). */
+template <int BLOCK_N, bool SPLIT, bool DEEP> struct Depth {
+  static constexpr int STAGES = SPLIT ? (BLOCK_N > 64 ? 3 : (DEEP ? 4 : 2)) : (BLOCK_N > 64 ? 6 : 8);
+  static constexpr int MIN_CTAS = (SPLIT && BLOCK_N <= 64 && !DEEP) ? 2 : 1;
 };
 enum { EPI_FWD = 0, EPI_DGRAD = 1, EPI_WGRAD = 2 };
 
@@ -115,11 +118,11 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
 }
 
 /* SPLIT (3xTF32): every stage also holds the residual tiles A_lo = A - tf32(A), B_lo = B - tf32(B) */
-template <int BLOCK_N, bool SPLIT>
+template <int BLOCK_N, bool SPLIT, bool DEEP = false>
 struct SmemLayout {
   static constexpr uint32_t A_BYTES = BM * BK * 4;
   static constexpr uint32_t B_BYTES = BLOCK_N * BK * 4;
-  static constexpr int STAGES = Depth<BLOCK_N, SPLIT>::STAGES;
+  static constexpr int STAGES = Depth<BLOCK_N, SPLIT, DEEP>::STAGES;
   static constexpr uint32_t STAGE_BYTES = (SPLIT ? 2u : 1u) * (A_BYTES + B_BYTES);
   static constexpr uint32_t BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr uint32_t TOTAL = BAR_OFF + 256 + 1024;   /* + barriers/tmem slot + manual 1024 B alignment slack */
@@ -127,12 +130,12 @@ struct SmemLayout {
 
 /* PRE_B (3xTF32 only): the B operand is a weight matrix whose residual B_lo = B - tf32(B) is kept in HBM by the kernels that write the
  * weights (dense_update / split_lo) and arrives by TMA like B itself; only the A tiles (activations, deltas) are split in the kernel */
-template <int BLOCK_N, int EPI, bool SPLIT, bool PRE_B>
+template <int BLOCK_N, int EPI, bool SPLIT, bool PRE_B, bool DEEP>
 __device__ __forceinline__ void gemm_tf32_body(const CUtensorMap* tmA_, const CUtensorMap* tmB_, const CUtensorMap* tmBlo_, const TcParams& p,
                                                int bx, int by, int bz) {
   const CUtensorMap& tmA = *tmA_; const CUtensorMap& tmB = *tmB_; const CUtensorMap& tmBlo = *tmBlo_;
   pdl_launch_dependents();                     /* the next kernel of the chain may set itself up while this one runs */
-  using SL = SmemLayout<BLOCK_N, SPLIT>;
+  using SL = SmemLayout<BLOCK_N, SPLIT, DEEP>;
   constexpr int STAGES = SL::STAGES;
   constexpr int TMEM_COLS = BLOCK_N <= 32 ? 32 : (BLOCK_N <= 64 ? 64 : (BLOCK_N <= 128 ? 128 : 256));
   extern __shared__ uint8_t smem_raw[];
@@ -326,10 +329,10 @@ __device__ __forceinline__ void gemm_tf32_body(const CUtensorMap* tmA_, const CU
   }
 }
 
-template <int BLOCK_N, int EPI, bool SPLIT, bool PRE_B>
-__global__ void __launch_bounds__(SPLIT ? 256 : 128, Depth<BLOCK_N, SPLIT>::MIN_CTAS) gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+template <int BLOCK_N, int EPI, bool SPLIT, bool PRE_B, bool DEEP>
+__global__ void __launch_bounds__(SPLIT ? 256 : 128, Depth<BLOCK_N, SPLIT, DEEP>::MIN_CTAS) gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                         const __grid_constant__ CUtensorMap tmBlo, const TcParams p) {
-  gemm_tf32_body<BLOCK_N, EPI, SPLIT, PRE_B>(&tmA, &tmB, &tmBlo, p, blockIdx.x, blockIdx.y, blockIdx.z);
+  gemm_tf32_body<BLOCK_N, EPI, SPLIT, PRE_B, DEEP>(&tmA, &tmB, &tmBlo, p, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 
 /* Every FcLayer's weight-gradient GEMM of a step in ONE launch (FcLayer.java:103-106 for all layers): the contractions are independent
@@ -343,12 +346,12 @@ struct GroupedTc {
   int n;
 };
 template <int BLOCK_N, bool SPLIT>
-__global__ void __launch_bounds__(SPLIT ? 256 : 128, Depth<BLOCK_N, SPLIT>::MIN_CTAS) gemm_tf32_grouped_wgrad_kernel(const __grid_constant__ GroupedTc g) {
+__global__ void __launch_bounds__(SPLIT ? 256 : 128, Depth<BLOCK_N, SPLIT, false>::MIN_CTAS) gemm_tf32_grouped_wgrad_kernel(const __grid_constant__ GroupedTc g) {
   int pi = 0;
   while (pi + 1 < g.n && (int)blockIdx.x >= g.first[pi + 1]) ++pi;
   const int local = (int)blockIdx.x - g.first[pi];
   const int bx = local % g.gx[pi], by = (local / g.gx[pi]) % g.gy[pi], bz = local / (g.gx[pi] * g.gy[pi]);
-  gemm_tf32_body<BLOCK_N, EPI_WGRAD, SPLIT, false>(&g.tmA[pi], &g.tmB[pi], &g.tmB[pi], g.p[pi], bx, by, bz);
+  gemm_tf32_body<BLOCK_N, EPI_WGRAD, SPLIT, false, false>(&g.tmA[pi], &g.tmB[pi], &g.tmB[pi], g.p[pi], bx, by, bz);
 }
 
 /* ---- host: tensor maps ---------------------------------------------------------------- */
@@ -390,9 +393,9 @@ const CUtensorMap& tensor_map(const float* ptr, int rows, int k_extent, long ld,
   return cache.emplace(key, m).first->second;
 }
 
-template <int BLOCK_N, int EPI, bool SPLIT, bool PRE_B>
+template <int BLOCK_N, int EPI, bool SPLIT, bool PRE_B, bool DEEP>
 void launch_tc(Ctx* ctx, const float* A, long lda, const float* B, long ldb, const float* Blo, TcParams& p, int nsplit) {
-  using SL = SmemLayout<BLOCK_N, SPLIT>;
+  using SL = SmemLayout<BLOCK_N, SPLIT, DEEP>;
   const CUtensorMap ta = tensor_map(A, p.M, p.K, lda, BM);
   const CUtensorMap tb = tensor_map(B, p.N, p.K, ldb, BLOCK_N);
   const CUtensorMap tbl = PRE_B ? tensor_map(Blo, p.N, p.K, ldb, BLOCK_N) : tb;
@@ -406,9 +409,9 @@ void launch_tc(Ctx* ctx, const float* A, long lda, const float* B, long ldb, con
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    PS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BLOCK_N, EPI, SPLIT, PRE_B>, ta, tb, tbl, p));
+    PS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BLOCK_N, EPI, SPLIT, PRE_B, DEEP>, ta, tb, tbl, p));
   } else {
-    gemm_tf32_kernel<BLOCK_N, EPI, SPLIT, PRE_B><<<grid, SPLIT ? 256 : 128, SL::TOTAL, ctx->stream>>>(ta, tb, tbl, p);
+    gemm_tf32_kernel<BLOCK_N, EPI, SPLIT, PRE_B, DEEP><<<grid, SPLIT ? 256 : 128, SL::TOTAL, ctx->stream>>>(ta, tb, tbl, p);
   }
   PS_LAUNCH_CHECK();
   ctx->launches++;
@@ -416,9 +419,18 @@ void launch_tc(Ctx* ctx, const float* A, long lda, const float* B, long ldb, con
 
 template <int BLOCK_N, int EPI>
 void launch_tc_mode(Ctx* ctx, const float* A, long lda, const float* B, long ldb, const float* Blo, TcParams& p, int nsplit) {
-  if (ctx->fc_precision != PS_FC_TF32X3) launch_tc<BLOCK_N, EPI, false, false>(ctx, A, lda, B, ldb, nullptr, p, nsplit);
-  else if (Blo != nullptr && EPI != EPI_WGRAD) launch_tc<BLOCK_N, EPI, true, true>(ctx, A, lda, B, ldb, Blo, p, nsplit);
-  else launch_tc<BLOCK_N, EPI, true, false>(ctx, A, lda, B, ldb, nullptr, p, nsplit);
+  if (ctx->fc_precision != PS_FC_TF32X3) { launch_tc<BLOCK_N, EPI, false, false, false>(ctx, A, lda, B, ldb, nullptr, p, nsplit); return; }
+  /* four stages at one CTA per SM, or two stages at two (see Depth) */
+  const long ctas = (long)ceil_div(p.N, BLOCK_N) * ceil_div(p.M, BM) * nsplit;
+  const int mode = EPI == EPI_WGRAD ? ctx->tc_deep_wgrad : ctx->tc_deep;
+  const bool deep = BLOCK_N <= 64 && (mode == 1 || (mode == 2 && ctas <= ctx->num_sms));
+  if (Blo != nullptr && EPI != EPI_WGRAD) {
+    if (deep) launch_tc<BLOCK_N, EPI, true, true, (BLOCK_N <= 64)>(ctx, A, lda, B, ldb, Blo, p, nsplit);
+    else launch_tc<BLOCK_N, EPI, true, true, false>(ctx, A, lda, B, ldb, Blo, p, nsplit);
+  } else {
+    if (deep) launch_tc<BLOCK_N, EPI, true, false, (BLOCK_N <= 64)>(ctx, A, lda, B, ldb, nullptr, p, nsplit);
+    else launch_tc<BLOCK_N, EPI, true, false, false>(ctx, A, lda, B, ldb, nullptr, p, nsplit);
+  }
 }
 
 template <int EPI>
@@ -436,15 +448,15 @@ void dispatch_tc(Ctx* ctx, const float* A, long lda, const float* B, long ldb, c
   else launch_tc_mode<64, EPI>(ctx, A, lda, B, ldb, Blo, p, nsplit);
 }
 
-template <int BLOCK_N, bool SPLIT>
+template <int BLOCK_N, bool SPLIT, bool DEEP>
 void set_attr() {
-  const int bytes = (int)SmemLayout<BLOCK_N, SPLIT>::TOTAL;
-  PS_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, EPI_FWD, SPLIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  PS_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, EPI_DGRAD, SPLIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  PS_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, EPI_WGRAD, SPLIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  const int bytes = (int)SmemLayout<BLOCK_N, SPLIT, DEEP>::TOTAL;
+  PS_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, EPI_FWD, SPLIT, false, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  PS_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, EPI_DGRAD, SPLIT, false, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  PS_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, EPI_WGRAD, SPLIT, false, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   if (SPLIT) {
-    PS_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, EPI_FWD, SPLIT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    PS_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, EPI_DGRAD, SPLIT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    PS_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, EPI_FWD, SPLIT, SPLIT, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    PS_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N, EPI_DGRAD, SPLIT, SPLIT, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   }
 }
 
@@ -453,10 +465,11 @@ void set_attr() {
 void fc_tf32_init() {
   static bool done = false;
   if (done) return;
-  set_attr<16, false>(); set_attr<32, false>(); set_attr<64, false>(); set_attr<128, false>();
-  set_attr<16, true>(); set_attr<32, true>(); set_attr<64, true>(); set_attr<128, true>();
-  PS_CUDA(cudaFuncSetAttribute(gemm_tf32_grouped_wgrad_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<64, true>::TOTAL));
-  PS_CUDA(cudaFuncSetAttribute(gemm_tf32_grouped_wgrad_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<64, false>::TOTAL));
+  set_attr<16, false, false>(); set_attr<32, false, false>(); set_attr<64, false, false>(); set_attr<128, false, false>();
+  set_attr<16, true, false>(); set_attr<32, true, false>(); set_attr<64, true, false>(); set_attr<128, true, false>();
+  set_attr<16, true, true>(); set_attr<32, true, true>(); set_attr<64, true, true>();
+  PS_CUDA(cudaFuncSetAttribute(gemm_tf32_grouped_wgrad_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<64, true, false>::TOTAL));
+  PS_CUDA(cudaFuncSetAttribute(gemm_tf32_grouped_wgrad_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemLayout<64, false, false>::TOTAL));
   encode_fn();
   done = true;
 }
@@ -505,9 +518,9 @@ bool fc_wgrad_grouped_tf32(Ctx* ctx, const FcWgradArgs* a, int n) {
   }
   g.first[n] = total;
   if (ctx->fc_precision == PS_FC_TF32X3)
-    gemm_tf32_grouped_wgrad_kernel<64, true><<<total, 256, SmemLayout<64, true>::TOTAL, ctx->stream>>>(g);
+    gemm_tf32_grouped_wgrad_kernel<64, true><<<total, 256, SmemLayout<64, true, false>::TOTAL, ctx->stream>>>(g);
   else
-    gemm_tf32_grouped_wgrad_kernel<64, false><<<total, 128, SmemLayout<64, false>::TOTAL, ctx->stream>>>(g);
+    gemm_tf32_grouped_wgrad_kernel<64, false><<<total, 128, SmemLayout<64, false, false>::TOTAL, ctx->stream>>>(g);
   PS_LAUNCH_CHECK();
   ctx->launches++;
   return true;

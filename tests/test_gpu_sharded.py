@@ -33,6 +33,9 @@ def worker(rank, R, port, out, cfg, emb_opt, graphed):
     dist.init_process_group("nccl", init_method=f"file://{out}/rendezvous", rank=rank, world_size=R, device_id=torch.device("cuda", rank))
     from ps_b200 import binding as ps
     from ps_b200.sharded import GpuOps, GraphedShardedTrainer, P2PShardedTrainer, ShardedTrainer
+    if graphed in ("p2p-defer", "p2p-nodefer"):   # the owner-side / dense update at the head of the next step, or inside the step (read at context creation)
+        os.environ["PS_P2P_DEFER"] = "1" if graphed == "p2p-defer" else "0"
+        graphed = "p2p"
     ctx = ps.Context(rank, seed=SEED)
     ctx.set_fc_precision(ps.PS_FC_FP32)       # the tolerances below are those of the exact FcLayer mode
     upd = ps.UpdaterSpec.ftrl() if emb_opt == "ftrl" else None
@@ -77,7 +80,8 @@ def worker(rank, R, port, out, cfg, emb_opt, graphed):
 
 
 @pytest.mark.parametrize("R,emb_opt,graphed", [(1, "adam", False), (1, "adam", True), (1, "adam", "p2p"), (2, "adam", False), (2, "ftrl", False),
-                                                 (2, "adam", True), (2, "adam", "p2p"), (2, "ftrl", "p2p"),
+                                                 (2, "adam", True), (2, "adam", "p2p"), (2, "ftrl", "p2p"), (2, "adam", "p2p-defer"), (2, "ftrl", "p2p-nodefer"),
+                                                 (1, "adam", "p2p-defer"), (1, "adam", "p2p-nodefer"),
                                                  (4, "adam", "p2p"), (4, "ftrl", True), (8, "adam", "p2p"), (8, "ftrl", "p2p"), (8, "adam", True)])
 def test_sharded_step_matches_oracle_global_batch(tmp_path, R, emb_opt, graphed):
     if torch.cuda.device_count() < R:
