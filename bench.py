@@ -48,6 +48,7 @@ from ps_b200.synth import CONFIGS, Synth  # noqa: E402
 METRIC = "Wide&Deep CTR training samples/sec"
 UNIT = "samples/s"
 L2_BYTES = 126e6
+DEPTH = 4                            # steps the host keeps in flight through ps_model_submit / collect (the library stages 4)
 
 
 def peaks():
@@ -389,12 +390,15 @@ class Workload:
             return pb[k].ptr if k in pb else None
         if self.trainer is not None and env.args.exchange == "p2p":
             # peer-memory sharded step through its host-facing call: ps_model_p2p_submit copies this rank's slice from pinned host
-            # memory and enqueues the step's graph, ps_model_collect returns the global loss of the oldest of 2 steps in flight
+            # memory and enqueues the step's graph, ps_model_collect returns the global loss of the oldest step in flight; the host
+            # runs up to DEPTH steps ahead (every step's loss is still read back: Trainer.java:89 prints it per step)
             for i in range(n):
                 pb = pinned[(start + i) % len(pinned)]
                 model.p2p_submit_ptrs(hp(pb, "E"), hp(pb, "X"), hp(pb, "W"), hp(pb, "Y"), B)
-                if i >= 1:
+                if i >= DEPTH - 1:
                     model.collect()
+            for _ in range(min(n, DEPTH - 1) - 1):
+                model.collect()
             return model.collect()
         if self.trainer is not None:      # NCCL sharded step: stage this rank's slice from pinned host memory, then the step, then its loss
             last = None
@@ -408,8 +412,10 @@ class Workload:
         for i in range(n):
             pb = pinned[(start + i) % len(pinned)]
             model.submit_ptrs(hp(pb, "E"), hp(pb, "X"), hp(pb, "W"), hp(pb, "Y"), B)
-            if i >= 1:
+            if i >= DEPTH - 1:
                 model.collect()
+        for _ in range(min(n, DEPTH - 1) - 1):
+            model.collect()
         return model.collect()
 
     def time_e2e(self, K, warmup, reps=None):
@@ -860,8 +866,8 @@ def main():
                        "e2e_reps": e["reps"], "e2e_ms_min_med_max": [e["ms_min"], e["ms"], e["ms_max"]],
                        "timed_region_s": (v["ms"] * v["reps"] + e["ms"] * e["reps"]) / 1e3},
             "e2e": {"value": total / (e["ms"] / 1e3), "unit": UNIT, "h2d_bytes_per_step": e["h2d"], "d2h_bytes_per_step": 32,
-                    "api": "ps_model_submit/ps_model_collect (2 steps in flight)" if not env.sharded else
-                           "ps_model_p2p_submit/ps_model_collect (2 steps in flight)" if args.exchange == "p2p" else
+                    "api": f"ps_model_submit/ps_model_collect (up to {DEPTH} steps in flight, every step's loss read back)" if not env.sharded else
+                           f"ps_model_p2p_submit/ps_model_collect (up to {DEPTH} steps in flight, every step's loss read back)" if args.exchange == "p2p" else
                            "pinned host batch -> device (async copy on the step's stream) -> sharded step -> ps_model_read_loss, every step"},
             "gpu_launches": int(round(v["launches"])), "clocks": clocks, "roofline": roofline, "roofline_tensor": roofline_tensor,
             "roofline_large_batch": large, "tf32_peak_tflops": tf32_peak, "kernels_us": phase_us, "hbm_kernels": kernels, "cfg5": cfg5,

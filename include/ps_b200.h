@@ -163,7 +163,7 @@ int ps_model_train_step(ps_model* m, const int64_t* E, const float* X, const int
 /* the same step split in two so the host copy of batch i+1 overlaps the kernels of batch i
  * (what the reference's DataSet reader thread does for parsing, data/DataSet.java:77-100):
  * submit() enqueues H2D + the whole step, collect() waits for the oldest and returns its loss.
- * At most 2 steps may be in flight; host buffers must stay valid until the matching collect. */
+ * At most 4 steps may be in flight; host buffers must stay valid until the matching collect. */
 int ps_model_submit(ps_model* m, const int64_t* E, const float* X, const int64_t* W, const float* Y, int N);
 int ps_model_collect(ps_model* m, float* loss);
 /* Model.train CALL BY CALL, for an unchanged model.DNN / model.WideDeepNN whose loss stays in Java:

@@ -685,7 +685,7 @@ void Model::gemm_times(int N, int reps, float* out) {
 }
 
 void Model::submit(const HostBatch& b, int mode) {
-  PS_REQUIRE(in_flight < 2, PS_ERR_STATE, "model: two steps already in flight; collect first");
+  PS_REQUIRE(in_flight < kStages, PS_ERR_STATE, "model: four steps already in flight; collect first");
   PS_REQUIRE(b.N > 0 && b.N <= Bmax, PS_ERR_ARG, "model: batch size must be in [1, max_batch]");
   PS_REQUIRE(b.X && b.Y && (!has_emb || b.E) && (!has_wide || b.W), PS_ERR_ARG, "model: missing input matrix");
   Stage& S = stage[next_stage];
@@ -705,7 +705,7 @@ void Model::submit(const HostBatch& b, int mode) {
   run_step(S.E, S.X, S.W, S.Y, b.N, true, S.st_host, mode);
   PS_CUDA(cudaEventRecord(S.step_done, ctx->stream));
   S.busy = true;
-  next_stage ^= 1; in_flight++;
+  next_stage = (next_stage + 1) % kStages; in_flight++;
   last_N = b.N; last_train = true;
 }
 
@@ -715,7 +715,7 @@ float Model::collect() {
   PS_CUDA(cudaEventSynchronize(S.step_done));
   last_status = *S.st_host;
   S.busy = false;
-  oldest_stage ^= 1; in_flight--;
+  oldest_stage = (oldest_stage + 1) % kStages; in_flight--;
   if (profile && in_flight == 0) finish_profile();
   PS_REQUIRE((last_status.emb_err & 2u) == 0, PS_ERR_ARG, "embedding id outside [0, 2^44): the batch was refused, nothing was applied");
   PS_REQUIRE(last_status.emb_err == 0, PS_ERR_CAPACITY, "embedding table is full: raise emb_capacity");
@@ -812,7 +812,7 @@ void Model::backward_update_host(const float* delta_top, int N, float loss) {
  * cannot take (a spelling outside its fast path, a short or missing line) drops the WHOLE batch like the reference's swallowed
  * exception does (DataSet.java:96-98): the step applies nothing and collect() reports it as skipped.                       */
 void Model::submit_text(const char* text, size_t len, int N, int mode) {
-  PS_REQUIRE(in_flight < 2, PS_ERR_STATE, "model: two steps already in flight; collect first");
+  PS_REQUIRE(in_flight < kStages, PS_ERR_STATE, "model: four steps already in flight; collect first");
   PS_REQUIRE(N > 0 && N <= Bmax && text != nullptr && len > 0, PS_ERR_ARG, "submit_text: bad argument");
   PS_REQUIRE(has_emb, PS_ERR_ARG, "submit_text: the CTR text layout needs a model with embedding fields");
   Stage& S = stage[next_stage];
@@ -835,7 +835,7 @@ void Model::submit_text(const char* text, size_t len, int N, int mode) {
   run_step(S.E, S.X, S.W, S.Y, N, true, S.st_host, mode);
   PS_CUDA(cudaEventRecord(S.step_done, ctx->stream));
   S.busy = true;
-  next_stage ^= 1; in_flight++;
+  next_stage = (next_stage + 1) % kStages; in_flight++;
   last_N = N; last_train = true;
 }
 

@@ -27,11 +27,19 @@ for f in ("bench_r02_20_5", "bench_r02_200_20", "bench_ref_r02"):
 PY
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches_r02_cfg2.csv \
   python bench.py --steps 3 --warmup 2 --reps 2 --no-kernel-times --no-parity --ring 4 > gpurun_out/ncu_l1.log 2>&1; echo "ncu launches cfg2 rc=$?"
-timeout 500 ncu --set full --clock-control none --import-source on -k regex:'emb_|gemm_tf32|dense_update|wide_' -s 150 -c 22 -f -o gpurun_out/prof_r02_cfg2 \
+timeout 500 ncu --set full --clock-control none -k regex:'emb_|gemm_tf32|dense_update|wide_' -s 150 -c 22 -f -o gpurun_out/prof_r02_cfg2 \
   python bench.py --steps 3 --warmup 2 --reps 2 --no-kernel-times --no-parity --ring 4 > gpurun_out/ncu_f1.log 2>&1; echo "ncu full cfg2 rc=$?"
-timeout 500 ncu --set full --clock-control none --import-source on -k regex:'emb_lookup|emb_scatter_slab|emb_update_slab' -s 48 -c 6 -f -o gpurun_out/prof_r02_large \
+timeout 500 ncu --set full --clock-control none -k regex:'emb_lookup|emb_scatter_slab|emb_update_slab' -s 48 -c 6 -f -o gpurun_out/prof_r02_large \
   python scripts/large_batch_steps.py cfg4 4 > gpurun_out/ncu_large.log 2>&1; echo "ncu large rc=$?"
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/launches_r02_fs_cfg2.csv \
   python bench.py --steps 3 --warmup 2 --reps 2 --force-sharded --no-kernel-times --no-parity --ring 4 > gpurun_out/ncu_l2.log 2>&1; echo "ncu launches sharded cfg2 rc=$?"
 for f in r02_cfg2 r02_fs_cfg2; do python scripts/ncu_summary.py launches gpurun_out/launches_$f.csv gpurun_out/launches_$f.md; done
-ls -la gpurun_out/*.ncu-rep
+# the reports themselves exceed what gpurun brings back (64 MiB): summarise them here, keep the text
+python scripts/ncu_summary.py full gpurun_out/prof_r02_cfg2.ncu-rep gpurun_out/ncu_full_cfg2.md
+python scripts/ncu_summary.py traffic gpurun_out/prof_r02_cfg2.ncu-rep gpurun_out/traffic_cfg2.json
+python scripts/ncu_summary.py full gpurun_out/prof_r02_large.ncu-rep gpurun_out/ncu_full_large.md
+for r in prof_r02_cfg2 prof_r02_large; do
+  ncu -i gpurun_out/$r.ncu-rep --page details --csv 2>/dev/null | grep -i -E "stall|Issue Slots|Eligible|No Eligible|One or More" | cut -c1-400 | head -400 > gpurun_out/${r}_details.csv
+done
+ls -la gpurun_out/*.ncu-rep; rm -f gpurun_out/*.ncu-rep
+du -sh gpurun_out
