@@ -483,6 +483,25 @@ def emb_rooflines(env, wl, hbm_peak, reps):
     return out
 
 
+def hbm_roofline(kernels, hbm_peak, peak_src, args):
+    """The `roofline` object of the JSON line: the slower of the two embedding kernels (SURVEY 8d's algorithmic bytes / device time)."""
+    dom = max(("emb_lookup", "emb_scatter_update"), key=lambda k: kernels[k]["us"])
+    traffic = None                  # dram__bytes_read+write per launch from the committed ncu --set full capture of this round
+    tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(tp) and args.config == "cfg2":
+        tk = json.load(open(tp)).get("kernels", {})
+        # the scatter and the update each have a shared-memory slab variant (the default) and a register variant
+        alts = {"emb_lookup": [["emb_lookup_kernel"]],
+                "emb_scatter_update": [["emb_scatter_slab_kernel", "emb_scatter_kernel"], ["emb_update_slab_kernel", "emb_update_kernel"]]}[dom]
+        picked = [next((p for p in names if p in tk), None) for names in alts]
+        traffic = sum(tk[p]["dram_bytes_per_launch"] for p in picked) if all(picked) else None
+    return {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
+            "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+            "how": "algorithmic bytes (SURVEY 8d) / mean device time of the kernel(s) replayed 64x in a CUDA graph over the batch ring "
+                   "(CUDA events on the library's stream); emb_lookup = key resolution + gather in one kernel; emb_scatter_update = "
+                   "the scatter launch + its programmatic dependent, the update launch"}
+
+
 def large_batch_roofline(env, hbm_peak, name, seed):
     """The embedding kernels at a batch large enough to be bandwidth- rather than launch-latency-bound (cfg4 shapes: B=16384, D=64,
     10 M keys), for zipf AND uniform keys, over a ring of non-repeating batches whose rows exceed L2."""
@@ -770,21 +789,7 @@ def main():
         mma_per = {"fp32": 0, "tf32": 1, "tf32x3": 3}[args.precision]
         if F:
             kernels = emb_rooflines(env, wl, hbm_peak, reps=64)
-            dom = max(("emb_lookup", "emb_scatter_update"), key=lambda k: kernels[k]["us"])
-            traffic = None                  # dram__bytes_read+write per launch from the committed ncu --set full capture of this round
-            tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
-            if os.path.exists(tp) and args.config == "cfg2":
-                tk = json.load(open(tp)).get("kernels", {})
-                # the scatter and the update each have a shared-memory slab variant (the default) and a register variant
-                alts = {"emb_lookup": [["emb_lookup_kernel"]],
-                        "emb_scatter_update": [["emb_scatter_slab_kernel", "emb_scatter_kernel"], ["emb_update_slab_kernel", "emb_update_kernel"]]}[dom]
-                picked = [next((p for p in names if p in tk), None) for names in alts]
-                traffic = sum(tk[p]["dram_bytes_per_launch"] for p in picked) if all(picked) else None
-            roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
-                        "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
-                        "how": "algorithmic bytes (SURVEY 8d) / mean device time of the kernel(s) replayed 64x in a CUDA graph over the batch ring "
-                               "(CUDA events on the library's stream); emb_lookup = key resolution + gather in one kernel; emb_scatter_update = "
-                               "the scatter launch + its programmatic dependent, the update launch"}
+            roofline = hbm_roofline(kernels, hbm_peak, peak_src, args)
         gk = gemm_report(wl, tf32_peak, max(mma_per, 1))
         kernels.update(gk)
         big = max((k for k in gk if gk[k]["frac_of_tf32_peak"] is not None), key=lambda k: gk[k]["us"])
@@ -839,6 +844,25 @@ def main():
                 extras[name] = {"error": str(ex)}
                 if world > 1:
                     raise                 # ranks must not diverge inside a sharded step
+
+    if side and world > 1 and rank == 0 and F:
+        # the same two embedding kernels on rank 0's GPU, on a standalone single-GPU table holding the whole vocabulary, over rank 0's ring
+        # (the sharded step runs these kernels' owner / requester forms; this is the number the N = 1 line reports)
+        class _Local:
+            pass
+        lw = _Local()
+        lw.cfg, lw.B, lw.dev_ring, lw.unique_stats = cfg, B, wl.dev_ring, wl.unique_stats
+        upd = env.ps.UpdaterSpec.ftrl() if cfg["emb_opt"] == "ftrl" else None
+        lw.model = env.ps.Model(env.ctx, cfg["kind"], F, D, cfg["Xn"], cfg["fc"], emb_capacity=int(min(2 ** 31 - 1, 2 * cfg["V"] + (1 << 16))),
+                                emb_updater=upd, max_batch=B)
+        try:
+            kernels = emb_rooflines(env, lw, hbm_peak, reps=64)
+            roofline = hbm_roofline(kernels, hbm_peak, peak_src, args)
+            roofline["how"] += "; N > 1: measured on rank 0 with a standalone single-GPU table"
+        except Exception as ex:                       # a side measurement must not cost the line
+            kernels, roofline = {"error": str(ex)}, None
+        finally:
+            lw.model.close()
 
     if rank == 0:
         cpu = None

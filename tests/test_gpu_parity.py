@@ -369,9 +369,9 @@ def test_model_put_get_roundtrip(ps, ctx):
 def test_pipelined_submit_equals_sync(ps, ctx):
     F, D, Xn, fc, N = 23, 16, 45, [32, 1], 128
     syn = Synth(F=F, Xn=Xn, V=3000, seed=21)
-    batches = [syn.batch(N) for _ in range(5)]
+    batches = [syn.batch(N) for _ in range(9)]
     losses = []
-    for mode in ("sync", "pipe"):
+    for mode in ("sync", "pipe", "pipe4"):
         c2 = ps.Context(0, seed=SEED)
         m = ps.Model(c2, "widedeep", F, D, Xn, fc, emb_capacity=1 << 15, max_batch=N)
         out = []
@@ -382,15 +382,24 @@ def test_pipelined_submit_equals_sync(ps, ctx):
             import ctypes as C
             keep = [{k: np.ascontiguousarray(v) for k, v in b.items()} for b in batches]
             ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+            depth = 2 if mode == "pipe" else 4                  # the library stages four batches
             for i, b in enumerate(keep):
                 m.submit_ptrs(ptr(b["E"]), ptr(b["X"]), ptr(b["W"]), ptr(b["Y"]), N)
-                if i >= 1:
+                if i >= depth - 1:
                     out.append(m.collect())
-            out.append(m.collect())
+                if mode == "pipe4" and i == 3:                  # a fifth step in flight is refused, nothing is enqueued
+                    m.submit_ptrs(ptr(keep[4]["E"]), ptr(keep[4]["X"]), ptr(keep[4]["W"]), ptr(keep[4]["Y"]), N)
+                    with pytest.raises(ps.PsError):
+                        m.submit_ptrs(ptr(keep[5]["E"]), ptr(keep[5]["X"]), ptr(keep[5]["W"]), ptr(keep[5]["Y"]), N)
+                    out.append(m.collect())
+                    break
+            while len(out) < (5 if mode == "pipe4" else len(keep)):
+                out.append(m.collect())
         losses.append(out)
         m.close()
         c2.close()
     assert np.allclose(losses[0], losses[1], rtol=1e-5, atol=1e-7)
+    assert np.allclose(losses[0][:5], losses[2], rtol=1e-5, atol=1e-7)
 
 
 # --------------------------------------------------------------------------- TF32 tcgen05 path
