@@ -853,16 +853,18 @@ def main():
         lw = _Local()
         lw.cfg, lw.B, lw.dev_ring, lw.unique_stats = cfg, B, wl.dev_ring, wl.unique_stats
         upd = env.ps.UpdaterSpec.ftrl() if cfg["emb_opt"] == "ftrl" else None
-        lw.model = env.ps.Model(env.ctx, cfg["kind"], F, D, cfg["Xn"], cfg["fc"], emb_capacity=int(min(2 ** 31 - 1, 2 * cfg["V"] + (1 << 16))),
-                                emb_updater=upd, max_batch=B)
+        lw.model = None
         try:
+            lw.model = env.ps.Model(env.ctx, cfg["kind"], F, D, cfg["Xn"], cfg["fc"], emb_capacity=int(min(2 ** 31 - 1, 2 * cfg["V"] + (1 << 16))),
+                                    emb_updater=upd, max_batch=B)
             kernels = emb_rooflines(env, lw, hbm_peak, reps=64)
             roofline = hbm_roofline(kernels, hbm_peak, peak_src, args)
             roofline["how"] += "; N > 1: measured on rank 0 with a standalone single-GPU table"
         except Exception as ex:                       # a side measurement must not cost the line
             kernels, roofline = {"error": str(ex)}, None
         finally:
-            lw.model.close()
+            if lw.model is not None:
+                lw.model.close()
 
     if rank == 0:
         cpu = None
