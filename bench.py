@@ -825,26 +825,6 @@ def main():
         nvlink["expected_payload_bytes_per_step"] = (remote * (8 + 2 * 4 * Dp_ + 4)            # keys out, rows back, gradient sums + counts out
                                                      + (world - 1) * (4 * glen + (8 * B * F if cfg["kind"] == "widedeep" else 0)))   # dense sums, wide ids to every replica
         nvlink["how"] = "NVML NVLINK_THROUGHPUT_DATA_TX/RX of rank 0's GPU around the timed device-resident steps; expected = de-duplicated keys, rows and gradient sums to/from other owners + dense gradient sums and wide ids to every replica"
-    loss_value = v["loss"]
-    wl_cap = wl.cap
-    wl_ring = len(wl.ring)
-    ring0 = wl.ring[:4]
-    wl.close()
-
-    # ---- parity at this N, then the other BASELINE configs at this N ----
-    parity = None
-    if not args.no_parity:
-        parity = parity_check(env, cfg)
-    extras = {}
-    if side and args.extra:
-        for name in [x for x in args.extra.split(",") if x]:
-            try:
-                extras[name] = extra_config(env, name, min(args.steps, 20), 3)
-            except Exception as ex:
-                extras[name] = {"error": str(ex)}
-                if world > 1:
-                    raise                 # ranks must not diverge inside a sharded step
-
     if side and world > 1 and rank == 0 and F:
         # the same two embedding kernels on rank 0's GPU, on a standalone single-GPU table holding the whole vocabulary, over rank 0's ring
         # (the sharded step runs these kernels' owner / requester forms; this is the number the N = 1 line reports)
@@ -865,6 +845,26 @@ def main():
         finally:
             if lw.model is not None:
                 lw.model.close()
+
+    loss_value = v["loss"]
+    wl_cap = wl.cap
+    wl_ring = len(wl.ring)
+    ring0 = wl.ring[:4]
+    wl.close()
+
+    # ---- parity at this N, then the other BASELINE configs at this N ----
+    parity = None
+    if not args.no_parity:
+        parity = parity_check(env, cfg)
+    extras = {}
+    if side and args.extra:
+        for name in [x for x in args.extra.split(",") if x]:
+            try:
+                extras[name] = extra_config(env, name, min(args.steps, 20), 3)
+            except Exception as ex:
+                extras[name] = {"error": str(ex)}
+                if world > 1:
+                    raise                 # ranks must not diverge inside a sharded step
 
     if rank == 0:
         cpu = None

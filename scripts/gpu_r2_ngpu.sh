@@ -3,9 +3,12 @@
 N=${1:-2}
 mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/gpus_n$N.txt
-timeout 600 python -m pytest tests/test_gpu_sharded.py -m gpu -x -q > gpurun_out/pytest_gpu_n$N.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu_n$N.log
+SEL=${2:-}   # optional pytest -k expression (e.g. "8- or 4-": only the 4- and 8-rank cases)
+timeout 600 python -m pytest tests/test_gpu_sharded.py -m gpu -x -q ${SEL:+-k "$SEL"} > gpurun_out/pytest_gpu_n$N.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu_n$N.log
 tail -12 gpurun_out/pytest_gpu_n$N.log
 nvidia-smi topo -m > gpurun_out/topo_n$N.txt 2>&1
+nvidia-smi nvlink -s -i 0 >> gpurun_out/topo_n$N.txt 2>&1
+timeout 120 python scripts/p2p_bw_probe.py >> gpurun_out/topo_n$N.txt 2>&1; tail -1 gpurun_out/topo_n$N.txt
 nvidia-smi nvlink -gt d -i 0 > gpurun_out/nvlink_before_n$N.txt 2>&1
 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_r02_n$N.log 2>&1; echo "bench$N rc=$?"
 nvidia-smi nvlink -gt d -i 0 > gpurun_out/nvlink_after_n$N.txt 2>&1
