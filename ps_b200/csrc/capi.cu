@@ -79,6 +79,8 @@ int ps_ctx_create(int device, uint64_t seed, ps_ctx** out) {
   if (td && td[0] >= '0' && td[0] <= '2') c->c.tc_deep = td[0] - '0';
   const char* tw = std::getenv("PS_TC_DEEP_WGRAD");
   if (tw && tw[0] >= '0' && tw[0] <= '2') c->c.tc_deep_wgrad = tw[0] - '0';
+  const char* wr = std::getenv("PS_TC_WIDE_RULE");
+  c->c.tc_wide_rule = (wr && wr[0] == '0') ? 0 : 1;
   const char* gn = std::getenv("PS_GEMM_NARROW");
   c->c.gemm_narrow = (gn && gn[0] == '1') ? 1 : 0;
   const char* gw = std::getenv("PS_GROUP_WGRAD");

@@ -70,6 +70,7 @@ struct Ctx {
   int hot_tma = 1;                 /* the lookup stages rows shared by >= 4 lookups of a warp task in shared memory by TMA bulk copies (PS_HOT_TMA=0: off) */
   int tc_deep = 2, tc_deep_wgrad = 2; /* 3xTF32 GEMM pipeline: 0 two stages x two CTAs per SM, 1 four stages x one CTA per SM, 2 the latter when the grid fits
                                       one wave of SMs (PS_TC_DEEP: forward / dgrad; PS_TC_DEEP_WGRAD: weight gradients) */
+  int tc_wide_rule = 1;            /* PS_TC_WIDE_RULE=0: see dispatch_tc */
   int gemm_narrow = 0;             /* PS_GEMM_NARROW=1: 32-column 3xTF32 tiles when 64-column ones leave half the CTA slots empty */
   int group_wgrad = 0;             /* PS_GROUP_WGRAD=1: all weight-gradient GEMMs of a step in one grouped launch after the dgrad chain.  Measured
                                       SLOWER at cfg2 (164.9 vs 158.9 us per step: the 272-CTA launch delays the embedding update it runs beside), so off */

@@ -438,7 +438,12 @@ void dispatch_tc(Ctx* ctx, const float* A, long lda, const float* B, long ldb, c
   /* 128-wide tiles when 64-wide ones would not fit one wave (1 CTA per SM): fc0's dgrad at cfg2 is 7 x 32 = 224 CTAs
    * at 64 columns, 4 x 32 = 128 at 128 — and every A tile is read (and split) half as often */
   const int ctas_per_sm = ctx->fc_precision == PS_FC_TF32X3 ? 2 : 1;
-  const bool wide = p.N >= 128 && (long)ceil_div(p.N, 64) * ceil_div(p.M, BM) * nsplit > (long)ctas_per_sm * ctx->num_sms;
+  const long ctas64 = (long)ceil_div(p.N, 64) * ceil_div(p.M, BM) * nsplit, ctas128 = (long)ceil_div(p.N, 128) * ceil_div(p.M, BM) * nsplit;
+  /* ... and when the 64-wide grid needs the second CTA slot of the SMs while the 128-wide one is a single wave at one CTA per SM, unless
+   * the wider tiles pad N by more than an eighth (measured: cfg3's 8192 x 256 x 256 layers 289.9 -> 274.8 us per step; cfg2's fc0 dgrad,
+   * N = 413 -> 512 columns, 147.1 -> 150.6: excluded).  PS_TC_WIDE_RULE=0: the first rule only */
+  const bool low_pad = (long)ceil_div(p.N, 128) * 128 - p.N <= p.N / 8;
+  const bool wide = p.N >= 128 && (ctas64 > (long)ctas_per_sm * ctx->num_sms || (ctx->tc_wide_rule == 1 && low_pad && ctas64 > ctx->num_sms && ctas128 <= ctx->num_sms));
   /* 64-column tiles that leave the second CTA slot of every SM empty (a 128-CTA grid): 32-column tiles fill it */
   const bool narrow = ctx->gemm_narrow && ctas_per_sm == 2 && p.N > 32 && (long)ceil_div(p.N, 64) * ceil_div(p.M, BM) * nsplit <= ctx->num_sms;
   if (wide) launch_tc_mode<128, EPI>(ctx, A, lda, B, ldb, Blo, p, nsplit);
