@@ -34,7 +34,7 @@ namespace psb {
 constexpr int kP2PMaxRanks = 8;
 enum { CH_KEYS = 0, CH_ROWS = 1, CH_GRADS = 2, CH_WIDE = 3, CH_GSUM = 4, CH_SCAL = 5, CH_COUNT = 6 };
 
-struct P2PState {                      /* lives in device memory; kernels read it, p2p_begin advances seq */
+struct P2PState {                      /* lives in device memory; kernels read it, route_send (or p2p_begin: no embedding table) advances seq */
   int R, me, cap, Dp, NF, glen;
   unsigned char* peer[kP2PMaxRanks];   /* base of every rank's slab as mapped into THIS process */
   size_t off_keys, off_rows, off_grads, off_gcnt, off_wide, off_gsum, off_counts, off_flags, parity_stride;
