@@ -251,6 +251,10 @@ int ps_model_gemm_times(ps_model* m, int N, int reps, float* us, int cap);
 /* owner(key) = ps_owner_of(pack(field, id), R) (include/ps_spec.h): a net/Router.java:5.  counts_dev[R]
  * and cursor_dev[R] are int32 scratch (zeroed by the call); send_keys_dev[N*F] is grouped by owner,
  * send_pos_dev[N*F] maps each lookup to its place in that order.                                      */
+/* net/Router.java:5 `int shard(String key)` for the reference's key strings, host side, no device: *owner = the shard of an embedding key
+ * ("emF<field>.<id>.0" → ps_owner_of(pack(field, id), n_shards)), or -1 for keys every shard holds (wide and dense parameters are replicated).
+ * What PSRouterClient.java:55-57 asks its Router before it picks a client; the device-side route kernels use the same function. */
+int ps_key_owner(const char* key, int n_shards, int* owner);
 int ps_shard_route_dev(ps_ctx* ctx, const int64_t* E_dev, int N, int F, int R, uint64_t* send_keys_dev, int32_t* send_pos_dev,
                        int32_t* counts_dev, int32_t* cursor_dev);
 /* the same with a FIXED bucket capacity per owner (send_keys_dev[R*cap], unused entries = 0 = EMPTY, which

@@ -14,6 +14,7 @@ public final class PsNative {
 	public static native void ctxDestroy(long ctx);
 	public static native void ctxSetFcPrecision(long ctx, int mode);                   // 0 fp32 | 1 tf32 tcgen05
 	public static native float[] updaterParse(String name);                            // {kind, p0..p3}
+	public static native int keyOwner(String key, int nShards);                        // ps_key_owner: net/Router.java:5 for the native store; -1 = replicated
 	public static native long modelCreate(long ctx, int kind, int F, int D, int Xn, int[] fc, long embCapacity, float[] embUpdater, int maxBatch);
 	public static native void modelDestroy(long model);
 	/** E, W: F x N ids carried as floats exactly as CTR.parseFeature builds them (CTR.java:47-68). */

@@ -20,14 +20,21 @@ import java.util.Map;
  */
 public class PSClient {
 	static final int STRIDE = 1 << 16;             // floats reserved per listed key on the wire to the native call (embedding rows use D of them)
-	public PSClient() {}
-	public PSClient(String host, int port) {}
+	final long model;                              // 0: the process-wide store (KVStore.ins()); else one shard's native model (PSRouterClient)
+	public PSClient() { this.model = 0; }
+	public PSClient(String host, int port) { this.model = 0; }
+	public PSClient(long model) { this.model = model; }
 	public void close() {}
+	long handle() { return model != 0 ? model : KVStore.ins().model(); }
 
-	public FloatMatrix get(String key) { return KVStore.ins().get(key); }
+	public FloatMatrix get(String key) {
+		if (model == 0) return KVStore.ins().get(key);
+		float[] v = PsNative.modelGet(model, key);
+		return v == null ? null : new FloatMatrix(v.length, 1, v);
+	}
 	public Map<String, FloatMatrix> getList(List<String> keys) {
 		Map<String, FloatMatrix> out = new HashMap<String, FloatMatrix>();
-		float[][] rows = PsNative.modelGetList(KVStore.ins().model(), keys.toArray(new String[0]));
+		float[][] rows = PsNative.modelGetList(handle(), keys.toArray(new String[0]));
 		for (int i = 0; i < keys.size(); i++) out.put(keys.get(i), rows[i] == null ? null : new FloatMatrix(rows[i].length, 1, rows[i]));
 		return out;
 	}
@@ -40,7 +47,7 @@ public class PSClient {
 		List<String> keys = new ArrayList<String>(updates.keySet());
 		float[][] offered = new float[keys.size()][];
 		for (int i = 0; i < keys.size(); i++) offered[i] = updates.get(keys.get(i)).data;
-		float[][] winners = PsNative.modelUpdateList(KVStore.ins().model(), keys.toArray(new String[0]), offered, replace);
+		float[][] winners = PsNative.modelUpdateList(handle(), keys.toArray(new String[0]), offered, replace);
 		Map<String, FloatMatrix> out = new HashMap<String, FloatMatrix>();
 		for (int i = 0; i < keys.size(); i++) {
 			FloatMatrix o = updates.get(keys.get(i));

@@ -130,6 +130,15 @@ JNIEXPORT jboolean JNICALL Java_nativeps_PsNative_modelSkippedBackward(JNIEnv* e
   ps_model_skipped_backward((ps_model*)(intptr_t)m, &v);
   return v ? JNI_TRUE : JNI_FALSE;
 }
+/* net/Router.java:5 for the native store: the shard of a key, -1 when every shard holds it */
+JNIEXPORT jint JNICALL Java_nativeps_PsNative_keyOwner(JNIEnv* env, jclass c, jstring key, jint nShards) {
+  const char* k = (*env)->GetStringUTFChars(env, key, NULL);
+  int owner = -1;
+  const int rc = ps_key_owner(k, nShards, &owner);
+  (*env)->ReleaseStringUTFChars(env, key, k);
+  throw_ps(env, rc);
+  return owner;
+}
 JNIEXPORT jfloatArray JNICALL Java_nativeps_PsNative_updaterParse(JNIEnv* env, jclass c, jstring name) {
   const char* k = (*env)->GetStringUTFChars(env, name, NULL);
   ps_updater_spec spec;

@@ -100,6 +100,7 @@ SYMBOLS = {
     "ps_model_phase_times": (_i, [_vp, _vp, _i, C.POINTER(_i), C.c_char_p, _i]),
     "ps_model_kernel_times": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "ps_model_gemm_times": (_i, [_vp, _i, _i, _vp, _i]),
+    "ps_key_owner": (_i, [C.c_char_p, _i, C.POINTER(_i)]),
     "ps_shard_route_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "ps_shard_route_padded_dev": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "ps_model_shard_lookup_dev": (_i, [_vp, _vp, _i, _vp]),
@@ -352,6 +353,13 @@ def updater_parse(name):
     s = UpdaterSpec()
     check(lib().ps_updater_parse(name.encode(), C.byref(s)))
     return s
+
+
+def key_owner(key, n_shards):
+    """net/Router.java:5 for the native store: the shard of an embedding key string, -1 for keys every shard holds."""
+    o = C.c_int()
+    check(lib().ps_key_owner(key.encode(), int(n_shards), C.byref(o)))
+    return o.value
 
 
 def updater_name(spec):

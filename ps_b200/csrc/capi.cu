@@ -601,6 +601,15 @@ int ps_model_gemm_times(ps_model* m, int N, int reps, float* us, int cap) {
 }
 
 /* ---- sharded table ---- */
+int ps_key_owner(const char* key, int n_shards, int* owner) {
+  PS_TRY
+  PS_REQUIRE(key && owner && n_shards > 0, PS_ERR_ARG, "bad argument");
+  int field = 0; int64_t id = 0;
+  if (psb::parse_key(key, &field, &id) != 0) { *owner = -1; return PS_OK; }      /* wide / dense: replicated */
+  PS_REQUIRE(field >= 0 && id >= 0 && id <= (int64_t)PS_KEY_ID_MASK, PS_ERR_ARG, "embedding key outside the (field, id) domain");
+  *owner = (int)ps_owner_of(ps_pack_key((uint32_t)field, (uint64_t)id), (uint32_t)n_shards);
+  PS_CATCH
+}
 int ps_shard_route_dev(ps_ctx* ctx, const int64_t* E_dev, int N, int F, int R, uint64_t* send_keys_dev, int32_t* send_pos_dev,
                        int32_t* counts_dev, int32_t* cursor_dev) {
   PS_TRY

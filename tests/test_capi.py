@@ -5,6 +5,7 @@ import os
 import re
 import subprocess
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -50,6 +51,27 @@ def test_updater_name_grammar(ps):
     assert ps.updater_name(ps.UpdaterSpec.adam(1, 2, 3, 1e7)) == "adam@alfa:1.0@beta1:2.0@beta2:3.0@epsilon:1.0E7@"
     with pytest.raises(ps.PsError):
         ps.updater_parse("bogus")
+
+
+def test_key_owner_is_the_route_kernels_owner(ps):
+    """ps_key_owner (host, key strings: what PSRouterClient asks its Router, PSRouterClient.java:55-57) = ps_owner_of of the packed key,
+    the function the device-side route kernels and the oracle's router use; dense and wide keys are replicated (-1)."""
+    import oracle_lib as ol
+    L = ol.lib()
+    rng = np.random.default_rng(5)
+    for R in (1, 2, 3, 8):
+        seen = set()
+        for _ in range(300):
+            f, v = int(rng.integers(0, 26)), int(rng.integers(0, 1 << 24))     # the reference's ids are floats: exact below 2^24
+            key = ol.key_string(0, f, v)
+            o = ps.key_owner(key, R)
+            assert o == L.pso_owner_of((f + 1) << 44 | v, R) and 0 <= o < R
+            seen.add(o)
+        assert len(seen) == R                                   # every shard gets keys
+    assert ps.key_owner("fc0.weights", 4) == -1 and ps.key_owner("wide.weights.77.0", 4) == -1 and ps.key_owner("wide.bias", 4) == -1
+    assert ps.key_owner("emF3.15757.0", 1) == 0
+    with pytest.raises(ps.PsError):
+        ps.key_owner("emF0.5.0", 0)
 
 
 def test_product_never_imports_oracle():
