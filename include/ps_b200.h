@@ -81,6 +81,9 @@ int ps_ctx_get_fc_precision(ps_ctx* ctx, int* mode);
  * (PS_EXACT_UPDATERS=1 in the environment flips it).  Takes effect for graphs captured afterwards: call before the first step. */
 int ps_ctx_set_exact_updaters(ps_ctx* ctx, int on);
 int ps_ctx_synchronize(ps_ctx* ctx);
+/* A context belongs to one device; its creating thread has that device current.  Any OTHER host thread that is going to call into the
+ * context (a JVM worker pool, the gRPC threads of ps_b200/wire.py) calls this first.  Calls on one context must not overlap in time. */
+int ps_ctx_make_current(ps_ctx* ctx);
 int ps_ctx_launch_count(ps_ctx* ctx, int64_t* out);   /* kernels this library launched so far */
 int ps_ctx_device_info(ps_ctx* ctx, char* name, int cap, int* sms, int* cc_major, int* cc_minor);
 int ps_ctx_stream(ps_ctx* ctx, void** stream);        /* the cudaStream_t every step is ordered on (for event timing) */
@@ -212,6 +215,11 @@ int ps_model_put(ps_model* m, const char* key, const float* in, int n);      /* 
 int ps_model_get_list(ps_model* m, const char* const* keys, int n, float* out, int stride, int32_t* found);
 int ps_model_update_list(ps_model* m, const char* const* keys, int n, float* io, int stride, const int32_t* lens, int replace);
 int ps_model_get_state(ps_model* m, const char* key, int which, float* out, int cap, int* n);
+/* PServer.push (net/PServer.java:164-184) → KVStore.update(updater, key) (store/KVStore.java:202-208): ONE step of the updater `spec` names
+ * (the request's updaterKey, parsed with ps_updater_parse) on an existing key, with the gradient a worker pushed — in the reference's layout
+ * (rows x cols column-major, as ps_model_put takes values).  For workers that still compute gradients themselves and speak the gRPC protocol
+ * (ps_b200/wire.py serves it); the native step never needs it.  PS_NOT_FOUND: no such key (the reference's updaters exit on a null weight). */
+int ps_model_push(ps_model* m, const char* key, const float* grad, int n, const ps_updater_spec* spec);
 /* Layer.getA() / getDelta() after the last step (layer/Layer.java:16-45): what = 0 A, 1 delta;
  * layers: "embedding", "concat", "fc<i>", "wide", "addWideDeep"                               */
 int ps_model_tap(ps_model* m, const char* layer, int what, float* out, int cap, int* n);

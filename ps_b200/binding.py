@@ -56,6 +56,7 @@ SYMBOLS = {
     "ps_ctx_get_fc_precision": (_i, [_vp, C.POINTER(_i)]),
     "ps_ctx_set_exact_updaters": (_i, [_vp, _i]),
     "ps_ctx_synchronize": (_i, [_vp]),
+    "ps_ctx_make_current": (_i, [_vp]),
     "ps_ctx_launch_count": (_i, [_vp, C.POINTER(_i64)]),
     "ps_ctx_device_info": (_i, [_vp, C.c_char_p, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "ps_ctx_stream": (_i, [_vp, _pp]),
@@ -88,6 +89,7 @@ SYMBOLS = {
     "ps_model_predict": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     "ps_model_get": (_i, [_vp, C.c_char_p, _vp, _i, C.POINTER(_i)]),
     "ps_model_put": (_i, [_vp, C.c_char_p, _vp, _i]),
+    "ps_model_push": (_i, [_vp, C.c_char_p, _vp, _i, _vp]),
     "ps_model_get_list": (_i, [_vp, C.POINTER(C.c_char_p), _i, _vp, _i, _vp]),
     "ps_model_update_list": (_i, [_vp, C.POINTER(C.c_char_p), _i, _vp, _i, _vp, _i]),
     "ps_model_get_state": (_i, [_vp, C.c_char_p, _i, _vp, _i, C.POINTER(_i)]),
@@ -314,6 +316,10 @@ class Context:
     def synchronize(self):
         check(lib().ps_ctx_synchronize(self.h))
 
+    def make_current(self):
+        """For host threads other than the one that created the context (see ps_ctx_make_current)."""
+        check(lib().ps_ctx_make_current(self.h))
+
     def launch_count(self):
         v = C.c_int64()
         check(lib().ps_ctx_launch_count(self.h, C.byref(v)))
@@ -532,6 +538,16 @@ class Model:
 
     def tap(self, layer, what=0):
         return self._fetch(lib().ps_model_tap, layer, what)
+
+    def push(self, key, grad, spec):
+        """PServer.push: one step of the updater `spec` (an UpdaterSpec, e.g. updater_parse(updaterKey)) on an existing key with a pushed
+        gradient in the reference's layout.  False when the key does not exist."""
+        g = _c(grad, np.float32)
+        rc = lib().ps_model_push(self.h, key.encode(), _p(g), g.size, C.byref(spec))
+        if rc == PS_NOT_FOUND:
+            return False
+        check(rc)
+        return True
 
     def put(self, key, v):
         v = _c(v, np.float32)

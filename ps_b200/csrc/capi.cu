@@ -126,6 +126,12 @@ int ps_ctx_set_exact_updaters(ps_ctx* ctx, int on) {
   ctx->c.exact_updaters = on ? 1 : 0;
   PS_CATCH
 }
+int ps_ctx_make_current(ps_ctx* ctx) {
+  PS_TRY
+  PS_REQUIRE(ctx, PS_ERR_ARG, "null ctx");
+  PS_CUDA(cudaSetDevice(ctx->c.device));
+  PS_CATCH
+}
 int ps_ctx_synchronize(ps_ctx* ctx) {
   PS_TRY
   PS_REQUIRE(ctx, PS_ERR_ARG, "null ctx");
@@ -534,6 +540,12 @@ int ps_model_update_list(ps_model* m, const char* const* keys, int n, float* io,
     M.emb.put_rows(fields.data(), ids.data(), k, w.data(), replace);
     for (int q = 0; q < k; ++q) std::memcpy(io + (size_t)idx[q] * stride, w.data() + (size_t)q * M.D, sizeof(float) * M.D);
   }
+  PS_CATCH
+}
+int ps_model_push(ps_model* m, const char* key, const float* grad, int n, const ps_updater_spec* spec) {
+  PS_TRY
+  PS_REQUIRE(m && key && grad && spec && n > 0, PS_ERR_ARG, "bad argument");
+  return m->m.push(key, grad, n, *spec);
   PS_CATCH
 }
 int ps_model_get_state(ps_model* m, const char* key, int which, float* out, int cap, int* n) {

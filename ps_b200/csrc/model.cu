@@ -1014,6 +1014,58 @@ void Model::put(const std::string& key, const float* in, int n) {
   PS_REQUIRE(false, PS_ERR_ARG, "put: unknown key");
 }
 
+int Model::push(const std::string& key, const float* g, int n, const ps_updater_spec& spec) {
+  flush_deferred();
+  PS_REQUIRE(in_flight == 0, PS_ERR_STATE, "model: steps in flight; collect first");
+  int field = 0; int64_t id = 0; int l = 0; bool is_bias = false;
+  const int k = parse_key(key, &field, &id);
+  if (k == 0) {
+    if (!has_emb || field < 0 || field >= F) return PS_NOT_FOUND;
+    PS_REQUIRE(n == D, PS_ERR_ARG, "push: gradient length != embedding dimension");
+    int32_t f32 = field, found = 0;
+    emb.push_rows(&f32, &id, 1, g, spec, &found);
+    return found ? PS_OK : PS_NOT_FOUND;
+  }
+  if (k == 1) {
+    if (!has_wide) return PS_NOT_FOUND;
+    PS_REQUIRE(n == 1, PS_ERR_ARG, "push: a wide weight is 1x1");
+    return wide.push(id, g[0], spec) ? PS_OK : PS_NOT_FOUND;
+  }
+  const UpdaterDev u = make_updater_dev(spec);
+  auto apply_in_place = [&](float* w, float* s1, float* s2, const std::vector<float>& gh) {
+    float* gd = dmalloc<float>(gh.size());
+    PS_CUDA(cudaMemcpyAsync(gd, gh.data(), sizeof(float) * gh.size(), cudaMemcpyHostToDevice, ctx->stream));
+    updater_apply(ctx, u, w, s1, s2, gd, (int)gh.size());
+    PS_CUDA(cudaStreamSynchronize(ctx->stream));
+    dfree(gd);
+  };
+  if (fc_key(fcs, key, &l, &is_bias)) {
+    FcLayer& f = fcs[l];
+    if (is_bias) {
+      PS_REQUIRE(n == f.out, PS_ERR_ARG, "push: bias length mismatch");
+      apply_in_place(f.bias, f.sb1, f.sb2, std::vector<float>(g, g + n));
+      return PS_OK;
+    }
+    PS_REQUIRE(n == f.out * f.in, PS_ERR_ARG, "push: weight length mismatch");
+    /* the gradient in the layout of W and its states ([out][ldw], padding columns zero: a zero gradient leaves a zero weight with zero state
+     * where it is under every updater); element 0 stays element (0, 0), which FtrlUpdater.java:52 looks at */
+    std::vector<float> gh((size_t)f.out * f.ldw, 0.f);
+    for (int i = 0; i < f.in; ++i)
+      for (int o = 0; o < f.out; ++o) gh[(size_t)o * f.ldw + i] = g[(size_t)o + (size_t)f.out * i];
+    apply_in_place(f.W, f.sW1, f.sW2, gh);
+    std::vector<float> w;                        /* W changed: rebuild the transposed copy and the TF32 residuals the way put() does */
+    fetch_fc(ctx, f, false, f.W, nullptr, w);
+    put(key, w.data(), (int)w.size());
+    return PS_OK;
+  }
+  if (has_wide && key == "wide.bias") {
+    PS_REQUIRE(n == 1, PS_ERR_ARG, "push: wide.bias is 1x1");
+    apply_in_place(wide_bias, wide_bias + 1, wide_bias + 2, std::vector<float>(g, g + 1));
+    return PS_OK;
+  }
+  return PS_NOT_FOUND;
+}
+
 static void fetch_cols(Ctx* ctx, const float* src, int ldsrc, int cols, int N, std::vector<float>& out) {
   out.resize((size_t)N * cols);
   PS_CUDA(cudaMemcpy2DAsync(out.data(), sizeof(float) * cols, src, sizeof(float) * ldsrc, sizeof(float) * cols, N, cudaMemcpyDeviceToHost, ctx->stream));

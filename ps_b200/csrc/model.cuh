@@ -153,6 +153,9 @@ struct Model {
   int get(const std::string& key, std::vector<float>& out);
   void put(const std::string& key, const float* in, int n);
   int get_state(const std::string& key, int which, std::vector<float>& out);
+  /* PServer.push (PServer.java:164-184 → KVStore.update(updater, key), KVStore.java:202-208): one step of the updater `spec` names on an EXISTING
+   * key with the gradient a legacy worker pushed (reference layout: rows x cols column-major, like put).  PS_NOT_FOUND for a missing key. */
+  int push(const std::string& key, const float* g, int n, const ps_updater_spec& spec);
   int tap(const std::string& layer, int what, std::vector<float>& out);
   int64_t num_keys();
   /* bulk dump / load of every key of the store with its updater state (checkpoint.cu) */

@@ -961,6 +961,21 @@ __global__ void emb_get_rows_kernel(const EmbSlot* __restrict__ slots, uint32_t 
   }
 }
 
+/* PServer.push → KVStore.update(updater, key) (PServer.java:164-184, KVStore.java:202-208): one updater step on an existing row with
+ * the gradient a (legacy gRPC) worker pushed; thread per key, the exact updater forms; found[i] = 0 and nothing happens for a missing key */
+__global__ void emb_push_rows_kernel(const EmbSlot* __restrict__ slots, uint32_t C, float* __restrict__ rows, int rs, int Dp, int D,
+                                     const int32_t* __restrict__ fields, const int64_t* __restrict__ ids, int n, const float* __restrict__ g,
+                                     UpdaterDev upd, int32_t* __restrict__ found) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int slot = emb_find(slots, C, ps_pack_key((uint32_t)fields[i], (uint64_t)ids[i]));
+  found[i] = slot >= 0;
+  if (slot < 0) return;
+  if (upd.kind == PS_UPD_FTRL && g[(size_t)i * D] == 0.0f) return;        /* FtrlUpdater.java:52 */
+  float* row = rows + (size_t)slot * rs;
+  for (int d = 0; d < D; ++d) apply_elem<true>(upd, row[d], row[Dp + d], row[2 * Dp + d], g[(size_t)i * D + d]);
+}
+
 /* KVStore.put (replace) / PServer.upsertList with replace=false (net/PServer.java:144-162):
  * insert-if-absent; the caller's buffer receives the winning row.                              */
 __global__ void emb_put_rows_kernel(EmbSlot* __restrict__ slots, uint32_t C, float* __restrict__ rows, int rs, int D,
@@ -1337,6 +1352,24 @@ void EmbTable::get_rows(const int32_t* fields, const int64_t* ids, int n, float*
   dfree(d_f); dfree(d_i); dfree(d_found); dfree(d_w); dfree(d_s1); dfree(d_s2);
 }
 
+void EmbTable::push_rows(const int32_t* fields, const int64_t* ids, int n, const float* grads, const ps_updater_spec& spec, int32_t* found) {
+  if (n <= 0) return;
+  for (int i = 0; i < n; ++i)
+    PS_REQUIRE(fields[i] >= 0 && fields[i] < F && ids[i] >= 0 && ids[i] <= (int64_t)PS_KEY_ID_MASK, PS_ERR_ARG, "embedding: key outside the (field, id) domain");
+  cudaStream_t st = ctx->stream;
+  int32_t* d_f = dmalloc<int32_t>(n); int64_t* d_i = dmalloc<int64_t>(n); int32_t* d_found = dmalloc<int32_t>(n);
+  float* d_g = dmalloc<float>((size_t)n * D);
+  PS_CUDA(cudaMemcpyAsync(d_f, fields, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+  PS_CUDA(cudaMemcpyAsync(d_i, ids, sizeof(int64_t) * n, cudaMemcpyHostToDevice, st));
+  PS_CUDA(cudaMemcpyAsync(d_g, grads, sizeof(float) * n * D, cudaMemcpyHostToDevice, st));
+  emb_push_rows_kernel<<<ceil_div(n, 128), 128, 0, st>>>(slots, (uint32_t)C, rows, rs, Dp, D, d_f, d_i, n, d_g, make_updater_dev(spec), d_found);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+  PS_CUDA(cudaMemcpyAsync(found, d_found, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+  PS_CUDA(cudaStreamSynchronize(st));
+  dfree(d_f); dfree(d_i); dfree(d_found); dfree(d_g);
+}
+
 void EmbTable::put_rows(const int32_t* fields, const int64_t* ids, int n, float* w_io, int replace) {
   if (n <= 0) return;
   for (int i = 0; i < n; ++i)
@@ -1441,6 +1474,13 @@ __global__ void wide_get_kernel(WideSlot* slots, uint32_t C, int64_t id, float* 
   out[0] = slot >= 0 ? 1.f : 0.f;
   if (slot >= 0) { out[1] = slots[slot].w; out[2] = slots[slot].s1; out[3] = slots[slot].s2; }
 }
+__global__ void wide_push_kernel(WideSlot* slots, uint32_t C, int64_t id, float g, UpdaterDev upd, int* found) {
+  bool ins;
+  const int slot = wide_find_or_insert(slots, C, ps_pack_key(0u, (uint64_t)id), false, &ins);
+  *found = slot >= 0;
+  if (slot < 0 || (upd.kind == PS_UPD_FTRL && g == 0.0f)) return;
+  apply_elem<true>(upd, slots[slot].w, slots[slot].s1, slots[slot].s2, g);
+}
 __global__ void wide_put_kernel(WideSlot* slots, uint32_t C, int64_t id, float wv, uint32_t* counters) {
   bool ins;
   const int slot = wide_find_or_insert(slots, C, ps_pack_key(0u, (uint64_t)id), true, &ins);
@@ -1497,6 +1537,17 @@ int WideTable::get(int64_t id, float* wv, float* s1v, float* s2v) {
   if (h[0] == 0.f) return 0;
   if (wv) *wv = h[1]; if (s1v) *s1v = h[2]; if (s2v) *s2v = h[3];
   return 1;
+}
+int WideTable::push(int64_t id, float g, const ps_updater_spec& spec) {
+  int* d = dmalloc_zero<int>(1, ctx->stream);
+  wide_push_kernel<<<1, 1, 0, ctx->stream>>>(slots, (uint32_t)C, id, g, make_updater_dev(spec), d);
+  PS_LAUNCH_CHECK();
+  ctx->launches++;
+  int h = 0;
+  PS_CUDA(cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+  PS_CUDA(cudaStreamSynchronize(ctx->stream));
+  dfree(d);
+  return h;
 }
 void WideTable::put(int64_t id, float wv) {
   wide_put_kernel<<<1, 1, 0, ctx->stream>>>(slots, (uint32_t)C, id, wv, counters);

@@ -114,6 +114,8 @@ struct EmbTable {
   /* host-driven row access (KVStore.get / put, PSClient.getList / updateList) */
   void get_rows(const int32_t* fields, const int64_t* ids, int n, float* w_out, float* s1_out, float* s2_out, int32_t* found);
   void put_rows(const int32_t* fields, const int64_t* ids, int n, float* w_io, int replace);
+  /* PServer.push: one updater step per listed (existing) key with a host-supplied gradient [n][D] */
+  void push_rows(const int32_t* fields, const int64_t* ids, int n, const float* grads, const ps_updater_spec& spec, int32_t* found);
 };
 
 struct WideTable {
@@ -134,6 +136,7 @@ struct WideTable {
   int64_t size();
   int get(int64_t id, float* w, float* s1, float* s2);   /* 0 = absent */
   void put(int64_t id, float w);
+  int push(int64_t id, float g, const ps_updater_spec& spec);   /* PServer.push on one wide key; 0 when the key does not exist */
   void check_errors();
 };
 

@@ -289,3 +289,70 @@ def test_fcnn_forward_backward_split_matches_oracle(ps, ctx):
         assert rel_err(m.get(f"fc{l}.weights"), o.get(f"fc{l}.weights")) <= 2e-4, l
         assert rel_err(m.get(f"fc{l}.bias"), o.get(f"fc{l}.bias")) <= 2e-4, l
     m.close()
+
+
+def test_push_is_one_updater_step_on_every_kind_of_key(ps, ctx):
+    """ps_model_push = PServer.push → KVStore.update(updater, key) (PServer.java:164-184, KVStore.java:202-208): the named updater's step on the
+    stored weight and state with the pushed gradient — bit for bit what ps_updater_apply (checked against the oracle elsewhere) gives."""
+    F, D, Xn, fc, N = 23, 16, 45, [32, 1], 128
+    m = ps.Model(ctx, "widedeep", F, D, Xn, fc, emb_capacity=1 << 14, max_batch=N)
+    b = Synth(F=F, Xn=Xn, V=5000, seed=12).batch(N)
+    m.train_step(b["E"], b["X"], b["W"], b["Y"])
+    rng = np.random.default_rng(4)
+    keys = [ol.key_string(0, 2, int(b["E"][5, 2])), "fc0.weights", "fc0.bias", ol.key_string(1, 0, int(b["W"][3, 2])), "wide.bias"]
+    for spec in (ps.UpdaterSpec.adam(0.01, 0.9, 0.999, 1e-8), ps.UpdaterSpec.ftrl(0.05, 1.0, 0.001, 0.001)):
+        for k in keys:
+            w, s1, s2 = m.get(k).copy(), m.get_state(k, 0).copy(), m.get_state(k, 1).copy()
+            g = rng.standard_normal(w.size).astype(np.float32)
+            assert m.push(k, g, spec), k
+            ctx.updater_apply(spec, w, s1, s2, g)
+            assert np.array_equal(m.get(k), w) and np.array_equal(m.get_state(k, 0), s1) and np.array_equal(m.get_state(k, 1), s2), k
+    # FtrlUpdater.java:52: a gradient whose first element is zero leaves the key alone
+    k = keys[0]
+    before = m.get(k).copy()
+    g = rng.standard_normal(D).astype(np.float32)
+    g[0] = 0.0
+    assert m.push(k, g, ps.UpdaterSpec.ftrl()) and np.array_equal(m.get(k), before)
+    assert not m.push("emF3.999999.0", np.zeros(D, np.float32), ps.UpdaterSpec.adam())       # unknown key
+    # the FcLayer's transposed / residual copies follow a pushed weight: the model still trains and predicts like one whose weights were put
+    m2 = ps.Model(ctx, "widedeep", F, D, Xn, fc, emb_capacity=1 << 14, max_batch=N)
+    m2.train_step(b["E"], b["X"], b["W"], b["Y"])
+    for k in keys:
+        m2.put(k, m.get(k))
+    assert np.allclose(m.predict(b["E"], b["X"], b["W"], N), m2.predict(b["E"], b["X"], b["W"], N), rtol=1e-6, atol=1e-7)
+    m.close()
+    m2.close()
+
+
+def test_wire_server_over_the_gpu_store(ps, ctx):
+    """ps_b200/wire.py: a legacy worker's getList / push / barrier against the tables the native step trains."""
+    pytest.importorskip("grpc")
+    from ps_b200 import wire
+    F, D, Xn, fc, N = 23, 16, 45, [32, 1], 128
+    m = ps.Model(ctx, "widedeep", F, D, Xn, fc, emb_capacity=1 << 14, max_batch=N)
+    b = Synth(F=F, Xn=Xn, V=5000, seed=13).batch(N)
+    m.train_step(b["E"], b["X"], b["W"], b["Y"])
+    srv = wire.PsWireServer(wire.ModelStore(ps, m), worker_num=1, is_async=True)
+    port = srv.start(0)
+    cl = wire.WireClient(f"127.0.0.1:{port}")
+    try:
+        k = ol.key_string(0, 1, int(b["E"][7, 1]))
+        got = cl.get_list([k, "fc0.bias", "emF3.999999.0"])
+        assert got["emF3.999999.0"] is None and np.array_equal(got[k][2], m.get(k)) and np.array_equal(got["fc0.bias"][2], m.get("fc0.bias"))
+        assert cl.get("emF3.999999.0") is None
+        assert cl.get("fc0.weights")[:2] == (fc[0], F * D + Xn) and cl.get(k)[:2] == (D, 1)
+        name = ps.updater_name(ps.UpdaterSpec.adam(0.01, 0.9, 0.999, 1e-8))        # the updaterKey a worker sends: Updater.getName()
+        w, s1, s2 = m.get(k).copy(), m.get_state(k, 0).copy(), m.get_state(k, 1).copy()
+        g = np.linspace(-1, 1, D).astype(np.float32)
+        assert cl.push(k, g, name).resp.ec == 0
+        ctx.updater_apply(ps.updater_parse(name), w, s1, s2, g)                     # first push of the key: the server's running sum is g itself
+        assert np.array_equal(m.get(k), w)
+        assert cl.push(k, g, "nosuch@").resp.ec == 500
+        fresh = "emF4.31337.0"
+        back = cl.update_list({fresh: (D, 1, np.arange(D, dtype=np.float32))}, replace=False)
+        assert not back[fresh][1] and np.array_equal(m.get(fresh), np.arange(D, dtype=np.float32))
+        assert cl.barrier().resp.ec == 200
+    finally:
+        cl.close()
+        srv.stop()
+        m.close()
