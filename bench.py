@@ -740,6 +740,7 @@ def main():
     ap.add_argument("--slack", type=float, default=1.25, help="per-owner bucket capacity = lookups / ranks * slack (de-duplicated keys need far less; uniform keys ~1.05)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
     ap.add_argument("--force-sharded", action="store_true", help="use the sharded step even with one rank (profiling)")
+    ap.add_argument("--roofline-at-n", action="store_true", help="N > 1: rank 0 also times the two embedding kernels on a standalone table (the N = 1 roofline)")
     ap.add_argument("--large", default="cfg4", help="shapes for the large-batch embedding roofline ('' = skip)")
     ap.add_argument("--extra", default="cfg3,cfg4", help="further BASELINE configs measured at this N ('' = skip)")
     ap.add_argument("--no-kernel-times", action="store_true", help="skip the per-kernel replays and side measurements (ncu runs: only the step's own launches)")
@@ -825,8 +826,8 @@ def main():
         nvlink["expected_payload_bytes_per_step"] = (remote * (8 + 2 * 4 * Dp_ + 4)            # keys out, rows back, gradient sums + counts out
                                                      + (world - 1) * (4 * glen + (8 * B * F if cfg["kind"] == "widedeep" else 0)))   # dense sums, wide ids to every replica
         nvlink["how"] = "NVML NVLINK_THROUGHPUT_DATA_TX/RX of rank 0's GPU around the timed device-resident steps; expected = de-duplicated keys, rows and gradient sums to/from other owners + dense gradient sums and wide ids to every replica"
-    if side and world > 1 and rank == 0 and F:
-        # the same two embedding kernels on rank 0's GPU, on a standalone single-GPU table holding the whole vocabulary, over rank 0's ring
+    if side and world > 1 and rank == 0 and F and args.roofline_at_n:
+        # (opt-in: --roofline-at-n; verified at N = 2 only)  the same two embedding kernels on rank 0's GPU, on a standalone single-GPU table holding the whole vocabulary, over rank 0's ring
         # (the sharded step runs these kernels' owner / requester forms; this is the number the N = 1 line reports)
         class _Local:
             pass
