@@ -60,7 +60,7 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """SM clock and throttle reasons DURING the timed region: NVML polled every 2 ms; nvidia-smi is the fallback when NVML is unavailable."""
+    """SM clock and throttle reasons DURING the timed region: NVML polled every 5 ms; nvidia-smi is the fallback when NVML is unavailable."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
@@ -86,7 +86,7 @@ class ClockSampler(threading.Thread):
                     r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
                         else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
                     self.rows.append((sm, r))
-                    time.sleep(0.002)
+                    time.sleep(0.005)
                     continue
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
@@ -757,6 +757,12 @@ def main():
             run_reference(args, cfg)
         return
 
+    # The cyclic collector never runs by itself in this process: started from the clock-sampler thread (which allocates ctypes objects a few
+    # hundred times a second) it would run finalizers while the main thread is inside a native call — two 8-GPU runs ended in a segmentation
+    # fault inside exactly such a collection (faulthandler: "Garbage-collecting" under nvmlDeviceGetClockInfo, the main thread in
+    # ps_model_p2p_submit).  It is run explicitly, in the main thread, between the measurements; it also keeps GC pauses out of the timed loops.
+    import gc
+    gc.disable()
     env = Env(args)
     world, B, F, D = env.world, cfg["B"], cfg["F"], cfg["D"]
     side = not args.no_kernel_times
@@ -765,11 +771,13 @@ def main():
     # ---- the headline workload ----
     wl = Workload(env, args.config, cfg, ring=args.ring)
     wl.prepare()
+    gc.collect()
     sampler = ClockSampler(env.local_rank)
     sampler.start()
     v = wl.time_value(args.steps, args.warmup, reps=args.reps or None)
     e = wl.time_e2e(args.steps, args.warmup, reps=args.reps or None)
     clocks = sampler.summary()
+    gc.collect()
     wl.check()
 
     # ---- per-kernel device times and rooflines (one GPU, local step) ----
@@ -855,13 +863,16 @@ def main():
 
     # ---- parity at this N, then the other BASELINE configs at this N ----
     parity = None
+    gc.collect()
     if not args.no_parity:
         parity = parity_check(env, cfg)
+        gc.collect()
     extras = {}
     if side and args.extra:
         for name in [x for x in args.extra.split(",") if x]:
             try:
                 extras[name] = extra_config(env, name, min(args.steps, 20), 3)
+                gc.collect()
             except Exception as ex:
                 extras[name] = {"error": str(ex)}
                 if world > 1:
