@@ -761,7 +761,9 @@ def main():
     # hundred times a second) it would run finalizers while the main thread is inside a native call — two 8-GPU runs ended in a segmentation
     # fault inside exactly such a collection (faulthandler: "Garbage-collecting" under nvmlDeviceGetClockInfo, the main thread in
     # ps_model_p2p_submit).  It is run explicitly, in the main thread, between the measurements; it also keeps GC pauses out of the timed loops.
+    import faulthandler
     import gc
+    faulthandler.enable()            # a crash in any rank leaves its Python stacks in the log
     gc.disable()
     env = Env(args)
     world, B, F, D = env.world, cfg["B"], cfg["F"], cfg["D"]
