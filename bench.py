@@ -760,12 +760,14 @@ def main():
     # The cyclic collector never runs by itself in this process: started from the clock-sampler thread (which allocates ctypes objects a few
     # hundred times a second) it would run finalizers while the main thread is inside a native call — two 8-GPU runs ended in a segmentation
     # fault inside exactly such a collection (faulthandler: "Garbage-collecting" under nvmlDeviceGetClockInfo, the main thread in
-    # ps_model_p2p_submit).  It is run explicitly, in the main thread, between the measurements; it also keeps GC pauses out of the timed loops.
+    # ps_model_p2p_submit).  With one rank it is run explicitly, in the main thread, between the measurements (which also keeps GC pauses out
+    # of the timed loops); a multi-rank run, which leaves through os._exit, does not run it at all — everything large is released explicitly.
     import faulthandler
     import gc
     faulthandler.enable()            # a crash in any rank leaves its Python stacks in the log
     gc.disable()
     env = Env(args)
+    collect = gc.collect if env.world == 1 else (lambda: 0)
     world, B, F, D = env.world, cfg["B"], cfg["F"], cfg["D"]
     side = not args.no_kernel_times
     hbm_peak, peak_src = peaks()
@@ -773,13 +775,13 @@ def main():
     # ---- the headline workload ----
     wl = Workload(env, args.config, cfg, ring=args.ring)
     wl.prepare()
-    gc.collect()
+    collect()
     sampler = ClockSampler(env.local_rank)
     sampler.start()
     v = wl.time_value(args.steps, args.warmup, reps=args.reps or None)
     e = wl.time_e2e(args.steps, args.warmup, reps=args.reps or None)
     clocks = sampler.summary()
-    gc.collect()
+    collect()
     wl.check()
 
     # ---- per-kernel device times and rooflines (one GPU, local step) ----
@@ -865,16 +867,16 @@ def main():
 
     # ---- parity at this N, then the other BASELINE configs at this N ----
     parity = None
-    gc.collect()
+    collect()
     if not args.no_parity:
         parity = parity_check(env, cfg)
-        gc.collect()
+        collect()
     extras = {}
     if side and args.extra:
         for name in [x for x in args.extra.split(",") if x]:
             try:
                 extras[name] = extra_config(env, name, min(args.steps, 20), 3)
-                gc.collect()
+                collect()
             except Exception as ex:
                 extras[name] = {"error": str(ex)}
                 if world > 1:
