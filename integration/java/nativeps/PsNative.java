@@ -29,6 +29,8 @@ public final class PsNative {
 	public static native float[][] modelUpdateList(long model, String[] keys, float[][] values, boolean replace);
 	public static native float[] modelGet(long model, String key);                     // null when absent (KVStore.get)
 	public static native void modelPut(long model, String key, float[] value);
+	public static native boolean modelPush(long model, String key, float[] gradient, String updaterKey);   // ps_model_push: PServer.push; false = no such key
+	public static native void ctxMakeCurrent(long ctx);                                 // ps_ctx_make_current: first call of any other thread
 	public static native float[] modelTap(long model, String layer, int what);        // 0 = A, 1 = delta
 	public static native boolean modelSkippedBackward(long model);
 

@@ -55,6 +55,8 @@ public class KVStore {
 	private final java.util.Map<String, int[]> shapes = new java.util.HashMap<String, int[]>();
 	/** layer.FcLayer registers out x in for "fc<i>.weights" so that get() hands back the reference's shape */
 	public void shape(String key, int rows, int cols) { shapes.put(key, new int[]{rows, cols}); }
+	public int[] shapeOf(String key) { return shapes.get(key); }                           // net/PServer.java: rows x cols on the wire
+	public void rememberShape(String key, int rows, int cols) { shape(key, rows, cols); }
 	private FloatMatrix shaped(String key, float[] v) {
 		int[] s = shapes.get(key);
 		return s != null && s[0] * s[1] == v.length ? new FloatMatrix(s[0], s[1], v) : new FloatMatrix(v.length, 1, v);

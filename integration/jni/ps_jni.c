@@ -111,6 +111,27 @@ JNIEXPORT void JNICALL Java_nativeps_PsNative_modelPut(JNIEnv* env, jclass c, jl
   (*env)->ReleaseStringUTFChars(env, key, k);
   throw_ps(env, rc);
 }
+/* PServer.push → KVStore.update(updater, key): false when the key does not exist (the reference's updaters exit the JVM on a null weight) */
+JNIEXPORT jboolean JNICALL Java_nativeps_PsNative_modelPush(JNIEnv* env, jclass c, jlong m, jstring key, jfloatArray grad, jstring updaterKey) {
+  const char* k = (*env)->GetStringUTFChars(env, key, NULL);
+  const char* u = (*env)->GetStringUTFChars(env, updaterKey, NULL);
+  ps_updater_spec spec;
+  int rc = ps_updater_parse(u, &spec);
+  if (rc == PS_OK) {
+    jsize n = (*env)->GetArrayLength(env, grad);
+    jfloat* p = (*env)->GetFloatArrayElements(env, grad, NULL);
+    rc = ps_model_push((ps_model*)(intptr_t)m, k, p, n, &spec);
+    (*env)->ReleaseFloatArrayElements(env, grad, p, JNI_ABORT);
+  }
+  (*env)->ReleaseStringUTFChars(env, updaterKey, u);
+  (*env)->ReleaseStringUTFChars(env, key, k);
+  if (rc != PS_OK && rc != PS_NOT_FOUND) throw_ps(env, rc);
+  return rc == PS_OK ? JNI_TRUE : JNI_FALSE;
+}
+/* for JVM threads other than the one that created the context (a gRPC executor, Trainer's pool) */
+JNIEXPORT void JNICALL Java_nativeps_PsNative_ctxMakeCurrent(JNIEnv* env, jclass c, jlong ctx) {
+  throw_ps(env, ps_ctx_make_current((ps_ctx*)(intptr_t)ctx));
+}
 JNIEXPORT jfloatArray JNICALL Java_nativeps_PsNative_modelTap(JNIEnv* env, jclass c, jlong m, jstring layer, jint what) {
   const char* k = (*env)->GetStringUTFChars(env, layer, NULL);
   int n = 0;
