@@ -236,11 +236,18 @@ int parse_ctr_line(const char* b, const char* e, int F, int Xn, int64_t wide, in
 }
 
 /* ------------------------------------------------------------------ LibsvmReader */
+/* batch storage that is NOT zero-filled on allocation (every element of a delivered batch is written by the parser; a 4096-row batch is 2.3 MB) */
+template <class T> struct RawBuf {
+  std::unique_ptr<T[]> p;
+  void resize(size_t n) { p.reset(new T[n]); }
+  T* data() { return p.get(); }
+  const T* data() const { return p.get(); }
+};
 struct LibsvmReader::Batch {
   int rows = 0;
   bool eof = false;
-  std::vector<int64_t> E, W;
-  std::vector<float> X, Y;
+  RawBuf<int64_t> E, W;
+  RawBuf<float> X, Y;
 };
 
 LibsvmReader::LibsvmReader(const std::string& path, int F_, int Xn_, int64_t wide_, int batch_, int offset_, int step_, int threads_, int depth_)
@@ -262,12 +269,21 @@ LibsvmReader::LibsvmReader(const std::string& path, int F_, int Xn_, int64_t wid
 
 LibsvmReader::~LibsvmReader() {
   stop();
+  {
+    std::lock_guard<std::mutex> g(wmu);
+    wquit = true;
+  }
+  wcv_job.notify_all();
+  for (auto& w : workers) if (w.joinable()) w.join();
+  workers.clear();
   if (data) munmap(const_cast<char*>(data), size);
   if (fd >= 0) ::close(fd);
 }
 
 void LibsvmReader::start() {
   pos = 0; line_no = 0; quit = false; produced_eof = false;
+  if (workers.empty())                             /* the helpers outlive reset(): DataSet.reset between epochs restarts the producer only */
+    for (int t = 1; t < threads; ++t) workers.emplace_back([this] { this->worker_loop(); });
   producer = std::thread([this] { this->produce(); });
 }
 
@@ -280,6 +296,63 @@ void LibsvmReader::stop() {
   cv_data.notify_all();
   if (producer.joinable()) producer.join();
   queue.clear();
+}
+
+static constexpr int kParseChunk = 64;            /* lines per unit of work */
+
+/* takes chunks of job `gen` until none is left (or the counter has moved on to another job) */
+void LibsvmReader::parse_chunks(const ParseJob& j, uint64_t gen, int nchunks) {
+  while (true) {
+    /* claim by compare-exchange: a helper that is late leaving job g must not take (and lose) a chunk of job g + 1 */
+    uint64_t t = chunk_counter.load(std::memory_order_acquire);
+    int c;
+    while (true) {
+      if ((t >> 32) != (gen & 0xFFFFFFFFull)) return;
+      c = (int)(t & 0xFFFFFFFFull);
+      if (c >= nchunks) return;
+      if (chunk_counter.compare_exchange_weak(t, t + 1, std::memory_order_acq_rel, std::memory_order_acquire)) break;
+    }
+    const int lo = c * kParseChunk, hi = std::min(j.n, lo + kParseChunk);
+    for (int i = lo; i < hi; ++i)
+      j.status[i] = parse_ctr_line(j.lines[i].first, j.lines[i].second, F, Xn, wide, j.out->E.data() + (size_t)i * F, j.out->X.data() + (size_t)i * Xn,
+                                   j.out->W.data() + (size_t)i * F, j.out->Y.data() + i);
+    if (chunks_done.fetch_add(1, std::memory_order_acq_rel) + 1 == nchunks) {
+      std::lock_guard<std::mutex> g(wmu);
+      wcv_done.notify_all();
+    }
+  }
+}
+
+void LibsvmReader::worker_loop() {
+  uint64_t seen = 0;
+  while (true) {
+    ParseJob j; uint64_t gen; int nchunks;
+    {
+      std::unique_lock<std::mutex> g(wmu);
+      wcv_job.wait(g, [&] { return wquit || job_gen != seen; });
+      if (wquit) return;
+      seen = gen = job_gen; j = job; nchunks = n_chunks;
+    }
+    parse_chunks(j, gen, nchunks);
+  }
+}
+
+/* every line of the batch parsed into `out`, status[i] = LINE_*; the producer works alongside its helpers and returns when all chunks are done */
+void LibsvmReader::parse_batch(const std::vector<std::pair<const char*, const char*>>& lines, Batch* out, int* status) {
+  ParseJob j;
+  j.lines = lines.data(); j.out = out; j.status = status; j.n = (int)lines.size();
+  const int nchunks = (j.n + kParseChunk - 1) / kParseChunk;
+  uint64_t gen;
+  {
+    std::lock_guard<std::mutex> g(wmu);
+    job = j; n_chunks = nchunks; gen = ++job_gen;
+    chunks_done.store(0, std::memory_order_release);
+    chunk_counter.store((gen & 0xFFFFFFFFull) << 32, std::memory_order_release);
+  }
+  if (!workers.empty() && nchunks > 1) wcv_job.notify_all();
+  parse_chunks(j, gen, nchunks);
+  std::unique_lock<std::mutex> g(wmu);
+  wcv_done.wait(g, [&] { return chunks_done.load(std::memory_order_acquire) >= nchunks; });
 }
 
 void LibsvmReader::reset() {                      /* DataSet.reset: shutdownNow, queue.clear, source.reset, start */
@@ -328,18 +401,7 @@ void LibsvmReader::produce() {
       const int n = (int)lines.size();
       out->E.resize((size_t)n * F); out->W.resize((size_t)n * F); out->X.resize((size_t)n * Xn); out->Y.resize(n);
       status.assign(n, LINE_OK);
-      auto work = [&](int lo, int hi) {
-        for (int i = lo; i < hi; ++i)
-          status[i] = parse_ctr_line(lines[i].first, lines[i].second, F, Xn, wide, out->E.data() + (size_t)i * F, out->X.data() + (size_t)i * Xn,
-                                     out->W.data() + (size_t)i * F, out->Y.data() + i);
-      };
-      const int nt = std::min(threads, std::max(1, n / 64));
-      if (nt <= 1) work(0, n);
-      else {
-        std::vector<std::thread> pool;
-        for (int t = 0; t < nt; ++t) pool.emplace_back(work, (int)((int64_t)n * t / nt), (int)((int64_t)n * (t + 1) / nt));
-        for (auto& t : pool) t.join();
-      }
+      parse_batch(lines, out.get(), status.data());
       /* the reference's swallowed exceptions: a line that fails inside parser.parse drops what was gathered up to and
        * including it — the lines after it (already consumed here) form the head of the next batch */
       int first_bad = -1;

@@ -11,6 +11,8 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <utility>
+#include <vector>
 
 #include "common.cuh"
 
@@ -48,6 +50,21 @@ struct LibsvmReader {
   std::deque<std::unique_ptr<Batch>> queue;
   std::thread producer;
   bool quit = false, produced_eof = false;
+  /* parse workers: threads - 1 persistent helpers (the producer parses too) take 64-line chunks of the batch being parsed.  The chunk
+   * counter carries the job's generation in its upper half, so a helper that is late leaving the previous job cannot touch the next one. */
+  struct ParseJob { const std::pair<const char*, const char*>* lines = nullptr; Batch* out = nullptr; int* status = nullptr; int n = 0; };
+  std::vector<std::thread> workers;
+  std::mutex wmu;
+  std::condition_variable wcv_job, wcv_done;
+  ParseJob job;
+  uint64_t job_gen = 0;
+  std::atomic<uint64_t> chunk_counter{0};
+  std::atomic<int> chunks_done{0};
+  int n_chunks = 0;
+  bool wquit = false;
+  void parse_chunks(const ParseJob& j, uint64_t gen, int nchunks);
+  void worker_loop();
+  void parse_batch(const std::vector<std::pair<const char*, const char*>>& lines, Batch* out, int* status);
 
   LibsvmReader(const std::string& path, int F, int Xn, int64_t wide, int batch, int offset, int step, int threads, int depth);
   ~LibsvmReader();
