@@ -337,24 +337,6 @@ void LibsvmReader::worker_loop() {
   }
 }
 
-/* every line of the batch parsed into `out`, status[i] = LINE_*; the producer works alongside its helpers and returns when all chunks are done */
-void LibsvmReader::parse_batch(const std::vector<std::pair<const char*, const char*>>& lines, Batch* out, int* status) {
-  ParseJob j;
-  j.lines = lines.data(); j.out = out; j.status = status; j.n = (int)lines.size();
-  const int nchunks = (j.n + kParseChunk - 1) / kParseChunk;
-  uint64_t gen;
-  {
-    std::lock_guard<std::mutex> g(wmu);
-    job = j; n_chunks = nchunks; gen = ++job_gen;
-    chunks_done.store(0, std::memory_order_release);
-    chunk_counter.store((gen & 0xFFFFFFFFull) << 32, std::memory_order_release);
-  }
-  if (!workers.empty() && nchunks > 1) wcv_job.notify_all();
-  parse_chunks(j, gen, nchunks);
-  std::unique_lock<std::mutex> g(wmu);
-  wcv_done.wait(g, [&] { return chunks_done.load(std::memory_order_acquire) >= nchunks; });
-}
-
 void LibsvmReader::reset() {                      /* DataSet.reset: shutdownNow, queue.clear, source.reset, start */
   stop();
   start();
@@ -384,40 +366,74 @@ bool LibsvmReader::next_line(const char** b, const char** e) {
   return true;
 }
 
+/* every line of the batch parsed into `out`, status[i] = LINE_*.  begin_parse publishes the job and wakes the helpers; the producer gathers the
+ * NEXT batch's lines meanwhile (the serial part of a batch: one memchr pass over its 2-3 MB), then finish_parse takes chunks itself and
+ * returns when all are done */
+void LibsvmReader::begin_parse(const std::vector<std::pair<const char*, const char*>>& lines, Batch* out, int* status) {
+  ParseJob j;
+  j.lines = lines.data(); j.out = out; j.status = status; j.n = (int)lines.size();
+  const int nchunks = (j.n + kParseChunk - 1) / kParseChunk;
+  {
+    std::lock_guard<std::mutex> g(wmu);
+    job = j; n_chunks = nchunks; cur_gen = ++job_gen;
+    chunks_done.store(0, std::memory_order_release);
+    chunk_counter.store((cur_gen & 0xFFFFFFFFull) << 32, std::memory_order_release);
+  }
+  if (!workers.empty() && nchunks > 1) wcv_job.notify_all();
+}
+void LibsvmReader::finish_parse() {
+  const ParseJob j = job;                        /* (only this thread writes it) */
+  const int nchunks = n_chunks;
+  parse_chunks(j, cur_gen, nchunks);
+  std::unique_lock<std::mutex> g(wmu);
+  wcv_done.wait(g, [&] { return chunks_done.load(std::memory_order_acquire) >= nchunks; });
+}
+
+/* DataSet.run: gather up to `batch` lines; true when the end of the data was reached while gathering */
+bool LibsvmReader::gather(std::vector<std::pair<const char*, const char*>>& lines) {
+  lines.clear();
+  while ((int)lines.size() < batch) {
+    const char *b, *e;
+    if (!next_line(&b, &e)) return true;
+    lines.emplace_back(b, e);
+  }
+  return false;
+}
+
 void LibsvmReader::produce() {
-  std::vector<std::pair<const char*, const char*>> lines;
+  std::vector<std::pair<const char*, const char*>> lines, ahead;
   std::vector<int> status;
-  bool eof = false;
-  while (!eof) {
-    /* DataSet.run: gather up to `batch` lines */
-    lines.clear();
-    while ((int)lines.size() < batch) {
-      const char *b, *e;
-      if (!next_line(&b, &e)) { eof = true; break; }
-      lines.emplace_back(b, e);
+  bool eof = gather(lines);
+  while (!lines.empty()) {
+    std::unique_ptr<Batch> out(new Batch);
+    const int n = (int)lines.size();
+    out->E.resize((size_t)n * F); out->W.resize((size_t)n * F); out->X.resize((size_t)n * Xn); out->Y.resize(n);
+    status.assign(n, LINE_OK);
+    begin_parse(lines, out.get(), status.data());
+    /* look ahead while the helpers parse; the cursor is remembered so that a bad line in THIS batch can take the lookahead back */
+    const size_t pos_before = pos;
+    const int64_t line_no_before = line_no;
+    bool eof_ahead = eof;
+    ahead.clear();
+    if (!eof) eof_ahead = gather(ahead);
+    finish_parse();
+    /* the reference's swallowed exceptions: a line that fails inside parser.parse drops what was gathered up to and
+     * including it — the lines after it (already consumed here) form the head of the next batch */
+    int first_bad = -1;
+    for (int i = 0; i < n; ++i) if (status[i] == LINE_BAD) { first_bad = i; break; }
+    lines_read += n;
+    if (first_bad >= 0) {
+      ++dropped;
+      pos = pos_before; line_no = line_no_before;  /* undo the lookahead, then push this batch's tail back: the cursor goes to just after the offending line */
+      rewind_to_after(lines[first_bad].second, n - 1 - first_bad);
+      lines_read -= n - 1 - first_bad;
+      eof = gather(lines);
+      continue;
     }
-    if (!lines.empty()) {
-      std::unique_ptr<Batch> out(new Batch);
-      const int n = (int)lines.size();
-      out->E.resize((size_t)n * F); out->W.resize((size_t)n * F); out->X.resize((size_t)n * Xn); out->Y.resize(n);
-      status.assign(n, LINE_OK);
-      parse_batch(lines, out.get(), status.data());
-      /* the reference's swallowed exceptions: a line that fails inside parser.parse drops what was gathered up to and
-       * including it — the lines after it (already consumed here) form the head of the next batch */
-      int first_bad = -1;
-      for (int i = 0; i < n; ++i) if (status[i] == LINE_BAD) { first_bad = i; break; }
-      lines_read += n;
-      if (first_bad >= 0) {
-        ++dropped;
-        /* push the tail back: rewind the cursor to just after the offending line */
-        rewind_to_after(lines[first_bad].second, n - 1 - first_bad);
-        lines_read -= n - 1 - first_bad;
-        eof = false;
-        continue;
-      }
-      bool any_short = false;
-      for (int i = 0; i < n; ++i) any_short |= status[i] == LINE_SHORT;
-      if (any_short) { ++dropped; continue; }      /* IndexOutOfBounds in parseFeature: the whole batch is lost */
+    bool any_short = false;
+    for (int i = 0; i < n; ++i) any_short |= status[i] == LINE_SHORT;
+    if (any_short) ++dropped;                      /* IndexOutOfBounds in parseFeature: the whole batch is lost */
+    else {
       out->rows = n;
       ++batches;
       std::unique_lock<std::mutex> g(mu);
@@ -427,6 +443,8 @@ void LibsvmReader::produce() {
       g.unlock();
       cv_data.notify_one();
     }
+    lines.swap(ahead);
+    eof = eof_ahead;
   }
   std::unique_ptr<Batch> fin(new Batch);
   fin->eof = true;

@@ -64,7 +64,10 @@ struct LibsvmReader {
   bool wquit = false;
   void parse_chunks(const ParseJob& j, uint64_t gen, int nchunks);
   void worker_loop();
-  void parse_batch(const std::vector<std::pair<const char*, const char*>>& lines, Batch* out, int* status);
+  uint64_t cur_gen = 0;
+  void begin_parse(const std::vector<std::pair<const char*, const char*>>& lines, Batch* out, int* status);
+  void finish_parse();
+  bool gather(std::vector<std::pair<const char*, const char*>>& lines);
 
   LibsvmReader(const std::string& path, int F, int Xn, int64_t wide, int batch, int offset, int step, int threads, int depth);
   ~LibsvmReader();

@@ -224,3 +224,32 @@ def test_random_lines_agree_with_the_java_semantics(ps):
             assert np.float32(got[4]).view(np.uint32) == o["Y"][0].view(np.uint32) or (np.isnan(got[4]) and np.isnan(o["Y"][0])), ln
     check()
     assert min(seen.values()) >= 100, seen                            # all three outcomes are well represented
+
+
+def test_reader_with_random_damage_matches_dataset(ps, sample, tmp_path):
+    """The reader gathers the next batch while its helpers parse the current one; a line that throws inside the parser takes that lookahead
+    back and restarts the batch behind it (DataSet.java:84-98).  Random damage, batch sizes, thread counts, offset / step: delivered batches,
+    dropped batches and line counts must equal the Java-semantics restatement's."""
+    _, lines = sample
+    rng = np.random.default_rng(11)
+    for trial in range(12):
+        n = min(len(lines), int(rng.integers(60, 700)))
+        ls = list(lines[:n])
+        for _ in range(int(rng.integers(0, 9))):
+            i = int(rng.integers(0, n))
+            ls[i] = ["1 oops", "", "0 1:1 2:1", "0 1:1 2:x", "   ", "1 5:"][int(rng.integers(0, 6))]
+        p = tmp_path / f"damaged{trial}.txt"
+        p.write_text("\n".join(ls) + ("\n" if rng.random() < 0.7 else ""))
+        batch = int(rng.choice([1, 3, 16, 64, 65, 130, 500]))
+        offset, step = (int(rng.integers(0, 5)), int(rng.integers(1, 4))) if rng.random() < 0.4 else (0, 1)
+        threads = int(rng.integers(1, 6))
+        exp_all = list(lo.dataset_batches(ls, batch, offset=offset, step=step))
+        exp = [b for b in exp_all if b is not None]
+        r = ps.LibsvmReader(str(p), batch=batch, offset=offset, step=step, threads=threads)
+        for epoch in range(2):
+            got = list(r)
+            assert len(got) == len(exp), (trial, batch, offset, step, threads)
+            for a, b in zip(got, exp):
+                _eq(a, b)
+            r.reset()
+        r.close()
