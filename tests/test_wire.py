@@ -132,3 +132,50 @@ def test_messages_use_the_reference_field_numbers():
     # Matrix: key = 1 (0x0a), row = 2 (0x10), cols = 3 (0x18), data = 4 packed (0x22), 1.5f = 00 00 c0 3f
     assert inner == b"\x0a\x01k\x10\x01\x18\x01\x22\x04\x00\x00\xc0\x3f"
     assert wire.message("GetMessage").DESCRIPTOR.fields_by_name["resp"].number == 4       # ps.proto:44 (not 3)
+
+
+def test_model_store_shapes_and_locking_without_a_gpu():
+    """ModelStore over a stand-in for binding.Model: FcLayer weights travel as out x in (FcLayer.java:40-47), everything else n x 1; the
+    context is made current and calls are serialised (gRPC serves from a thread pool)."""
+    calls = []
+
+    class Ctx:
+        def make_current(self):
+            calls.append("current")
+
+    class FakeModel:
+        F, D, Xn, fc, ctx = 3, 4, 2, [5, 1], Ctx()
+
+        def __init__(self):
+            self.d = {"fc0.weights": np.arange(5 * 14, dtype=np.float32), "fc1.weights": np.zeros(5, np.float32), "emF1.7.0": np.ones(4, np.float32)}
+
+        def get(self, k):
+            return self.d.get(k)
+
+        def put(self, k, v):
+            self.d[k] = np.array(v, np.float32)
+
+        def push(self, k, g, spec):
+            if k not in self.d:
+                return False
+            self.d[k] = self.d[k] - spec * np.asarray(g, np.float32)
+            return True
+
+    class FakePs:
+        @staticmethod
+        def updater_parse(name):
+            if not name.startswith("sgd@alfa:"):
+                raise ValueError(name)
+            return np.float32(name.split(":")[1].rstrip("@"))
+
+    m = FakeModel()
+    st = wire.ModelStore(FakePs, m)
+    assert st.get("fc0.weights")[:2] == (5, 3 * 4 + 2) and st.get("fc1.weights")[:2] == (1, 5) and st.get("emF1.7.0")[:2] == (4, 1)
+    assert st.get("nope") is None and st.has_updater("sgd@alfa:0.5@") and not st.has_updater("adam@")
+    st.put("emF2.9.0", (4, 1, np.full(4, 2.0, np.float32)))
+    assert st.push("emF2.9.0", np.ones(4, np.float32), "sgd@alfa:0.5@") and np.allclose(m.d["emF2.9.0"], 1.5)
+    assert not st.push("emF2.10.0", np.ones(4, np.float32), "sgd@alfa:0.5@")
+    assert calls.count("current") >= 6
+    srv = wire.PsWireServer(st)
+    G = wire.message("GradientMessage")
+    assert srv.push(G(gradient=wire.to_matrix("emF2.10.0", (4, 1, np.ones(4, np.float32))), isAsync=True, updaterKey="sgd@alfa:1@")).resp.ec == 500
