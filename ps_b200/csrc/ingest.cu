@@ -147,6 +147,10 @@ inline bool fast_pair(const char*& p, const char* e, int64_t* idx, float* val) {
   while (q < e && (unsigned)(*q - '0') <= 9u) { v = v * 10 + (uint64_t)(*q - '0'); ++q; ++nd; }
   if (nd == 0 || nd > 18 || q >= e || *q != ':') return false;
   ++q;
+  if (q < e && *q == '1' && (q + 1 == e || q[1] == ' ')) {   /* "<id>:1": every categorical column of a CTR line */
+    *idx = (int64_t)v; *val = 1.0f; p = q + 1;
+    return true;
+  }
   bool neg = false;
   if (q < e && *q == '-') { neg = true; ++q; }
   uint32_t m = 0;
@@ -190,6 +194,9 @@ int parse_ctr_line(const char* b, const char* e, int F, int Xn, int64_t wide, in
   const int need = 1 + F + Xn;
   bool shortline = false;
   const char* p = b;
+  /* idx % wide for 32-bit operands without a division per column (Lemire's fastmod: exact for a, d < 2^32) */
+  const bool small_wide = wide > 0 && wide < (1 << 24);
+  const uint64_t modM = small_wide ? UINT64_C(0xFFFFFFFFFFFFFFFF) / (uint64_t)wide + 1 : 0;
   while (true) {
     const char* t = p;
     int64_t idx;
@@ -222,7 +229,14 @@ int parse_ctr_line(const char* b, const char* e, int F, int Xn, int64_t wide, in
         const float idf = (float)idx;            /* E[j-1][i] = cols.get(j).getIdx()  (long -> float, CTR.java:57) */
         if (E) E[col - 1] = (int64_t)idf;
         /* result.data[i] % size in float (MatrixUtil.java:30): exact integer arithmetic while the id survives the float cast */
-        if (W) W[col - 1] = (idx >= 0 && idx < (1 << 24) && wide < (1 << 24)) ? idx % wide : (int64_t)std::fmod(idf, (float)wide);
+        if (W) {
+          if (small_wide && idx >= 0 && idx < (1 << 24)) {
+            const uint64_t low = modM * (uint64_t)idx;
+            W[col - 1] = (int64_t)(uint64_t)(((unsigned __int128)low * (uint64_t)wide) >> 64);
+          } else {
+            W[col - 1] = (idx >= 0 && idx < (1 << 24) && wide < (1 << 24)) ? idx % wide : (int64_t)std::fmod(idf, (float)wide);
+          }
+        }
       } else if (col < need) {
         if (X) X[col - 1 - F] = val;             /* X[j-24][i] = cols.get(j).toF() */
       }
