@@ -63,9 +63,12 @@ class ClockSampler(threading.Thread):
     """SM clock and throttle reasons DURING the timed region: NVML polled every 5 ms; nvidia-smi is the fallback when NVML is unavailable."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index):
+    def __init__(self, index, threaded=True):
+        """threaded = False (multi-rank runs): no second Python thread in the process — poll() is called by the main thread while the GPU
+        works on the steps it has just enqueued (see main(): a collection started from the sampler thread ended two 8-GPU runs)."""
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag, self.sm_max, self.how = index, [], False, None, "nvml"
+        self.threaded, self.started = threaded, False
         self.nv = None
         try:
             import pynvml
@@ -76,6 +79,26 @@ class ClockSampler(threading.Thread):
             self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception:
             self.nv, self.how = None, "nvidia-smi"
+
+    def begin(self):
+        if self.threaded:
+            self.started = True
+            self.start()
+        else:
+            self.how += ", polled by the main thread between the enqueue and the synchronisation of a repetition"
+
+    def poll(self):
+        """One sample, from the calling thread (inline mode only; NVML: ~20 us)."""
+        nv = self.nv
+        if self.threaded or nv is None:
+            return
+        try:
+            sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            self.rows.append((sm, r))
+        except Exception:
+            pass
 
     def run(self):
         nv = self.nv
@@ -104,7 +127,8 @@ class ClockSampler(threading.Thread):
 
     def summary(self):
         self.stop_flag = True
-        self.join(timeout=6)
+        if self.started:
+            self.join(timeout=6)
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unsampled"]}
         sm = sorted(r[0] for r in self.rows)
@@ -267,6 +291,7 @@ class Env:
         self.ctx = ps.Context(self.local_rank, seed=20261017)
         self.ctx.set_fc_precision({"fp32": ps.PS_FC_FP32, "tf32": ps.PS_FC_TF32, "tf32x3": ps.PS_FC_TF32X3}[args.precision])
         self.stream = torch.cuda.ExternalStream(self.ctx.stream(), device=self.local_rank)
+        self.sampler = None                  # the clock sampler while the headline workload is timed (polled inline in multi-rank runs)
 
     def barrier(self):
         self.ctx.synchronize()
@@ -352,6 +377,8 @@ class Workload:
             for i in range(K):
                 self.dev_step(start + i)
             e1.record(env.stream)
+            if env.sampler is not None:
+                env.sampler.poll()                   # the GPU is working on the K steps just enqueued
             env.barrier()
             return e0.elapsed_time(e1)
         probe = env.max_over_ranks([one(warmup)])[0]
@@ -382,7 +409,8 @@ class Workload:
                 self.pinned.append(pb)
         return self.pinned
 
-    def host_loop(self, n, start):
+    def host_loop(self, n, start, mid=None):
+        """n steps through the host-facing calls; mid: called once, half way (the inline clock sample of a multi-rank run)."""
         env, torch, model, B = self.env, self.env.torch, self.model, self.B
         pinned = self._pin()
 
@@ -395,6 +423,8 @@ class Workload:
             for i in range(n):
                 pb = pinned[(start + i) % len(pinned)]
                 model.p2p_submit_ptrs(hp(pb, "E"), hp(pb, "X"), hp(pb, "W"), hp(pb, "Y"), B)
+                if mid is not None and i == n // 2:
+                    mid()
                 if i >= DEPTH - 1:
                     model.collect()
             for _ in range(min(n, DEPTH - 1) - 1):
@@ -423,17 +453,17 @@ class Workload:
         self.host_loop(len(self._pin()) + max(3, warmup), 0)        # every staging-buffer graph captured, untimed
         env.barrier()
 
-        def one(start):
+        def one(start, sample=False):
             env.barrier()
             t0 = time.perf_counter()
-            loss = self.host_loop(K, start)
+            loss = self.host_loop(K, start, env.sampler.poll if (sample and env.sampler is not None) else None)
             env.ctx.synchronize()
             return (time.perf_counter() - t0) * 1e3, loss
         probe = env.max_over_ranks([one(warmup)[0]])[0]
         reps = reps or self._reps(K, probe)
         ms, loss = [], None
         for r in range(reps):
-            t, loss = one(warmup + (r + 1) * K)
+            t, loss = one(warmup + (r + 1) * K, sample=(r % 4 == 0))     # (one ~20 us NVML query inside every fourth repetition of ~4 ms)
             ms.append(t)
         ms = sorted(env.max_over_ranks(ms))
         h2d = sum(pa.nbytes for pa in self._pin()[0].values())
@@ -776,11 +806,13 @@ def main():
     wl = Workload(env, args.config, cfg, ring=args.ring)
     wl.prepare()
     collect()
-    sampler = ClockSampler(env.local_rank)
-    sampler.start()
+    sampler = ClockSampler(env.local_rank, threaded=(env.world == 1))
+    env.sampler = sampler
+    sampler.begin()
     v = wl.time_value(args.steps, args.warmup, reps=args.reps or None)
     e = wl.time_e2e(args.steps, args.warmup, reps=args.reps or None)
     clocks = sampler.summary()
+    env.sampler = None
     collect()
     wl.check()
 
